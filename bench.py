@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s of the fused per-level Godunov sweep (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+A "step" is one level step of a levelmin=levelmax run: courant_fine -> set_unew -> godunov_fine -> set_uold
+(-> ghost exchange -> boundaries), amr/amr_step.f90:326-514.  Workload at N=1: BASELINE.json configs[1],
+"sedov3d uniform 256^3 (levelmin=levelmax=8), exact Riemann" (namelist/sedov3d.nml with riemann='exact').
+With N ranks every rank owns one 256^3 coarse cell of an (nx,ny,nz) periodic coarse grid (weak scaling, 512^3 at
+N=8), ghost octs exchanged with ncclSend/ncclRecv.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GAMMA = 1.4
+WORKLOADS = {
+    # name: (levelmax per rank cube, riemann, slope_type, ic)
+    "sedov3d_256_exact": dict(level=8, riemann="exact", slope_type=1, ic="sedov"),
+    "sedov3d_512_hllc": dict(level=9, riemann="hllc", slope_type=1, ic="sedov"),
+    "smooth_256_hllc": dict(level=8, riemann="hllc", slope_type=1, ic="smooth"),
+    "smooth_256_exact": dict(level=8, riemann="exact", slope_type=1, ic="smooth"),
+    "smooth_256_llf": dict(level=8, riemann="llf", slope_type=1, ic="smooth"),
+    "sedov3d_128_exact": dict(level=7, riemann="exact", slope_type=1, ic="sedov"),
+    "sedov3d_64_exact": dict(level=6, riemann="exact", slope_type=1, ic="sedov"),
+}
+BYTES_PER_CELL = 80.0   # algorithmic: read uold once + write unew once = 2*nvar*8 B
+
+
+def sedov_ic(boxlen, nx, level):
+    """namelist/sedov3d.nml:19-34 evaluated like region_condinit (hydro/init_flow_fine.f90:475-596)."""
+    scale = boxlen / nx
+    dx = 0.5 ** level * scale
+
+    def fn(x, y, z):                      # x,y,z in coarse-cell units
+        xs, ys, zs = x * scale, y * scale, z * scale
+        r = (np.maximum(1.0 - np.abs(xs) / dx, 0.0) * np.maximum(1.0 - np.abs(ys) / dx, 0.0)
+             * np.maximum(1.0 - np.abs(zs) / dx, 0.0))
+        p = 1e-5 + 0.4 * r / dx ** 3
+        u = np.zeros((5, len(x)))
+        u[0] = 1.0
+        u[4] = p / (GAMMA - 1.0)
+        return u
+    return fn
+
+
+def smooth_ic(nxyz):
+    """smooth, everywhere non-trivial periodic state."""
+    def fn(x, y, z):
+        tw = 2 * np.pi
+        xs, ys, zs = x / nxyz[0], y / nxyz[1], z / nxyz[2]
+        rho = 1 + 0.2 * np.sin(tw * xs) * np.cos(tw * ys)
+        vx, vy, vz = 0.3 * np.sin(tw * ys), 0.3 * np.sin(tw * zs), 0.3 * np.sin(tw * xs)
+        p = 1 + 0.1 * np.cos(tw * (xs + ys + zs))
+        u = np.zeros((5, len(x)))
+        u[0] = rho
+        u[1], u[2], u[3] = rho * vx, rho * vy, rho * vz
+        u[4] = p / (GAMMA - 1) + 0.5 * rho * (vx ** 2 + vy ** 2 + vz ** 2)
+        return u
+    return fn
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for i, nm in enumerate(names):
+                    if r[5 + i].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(workload, steps, warmup, sample_level=7):
+    """The reference algorithm on the host cores: oracle/ (C restatement of RAMSES, reference-shaped per-oct
+    6^3 patches, nvector=32 batches, OpenMP over batches).  The F90 itself cannot be built (no gfortran/MPI)."""
+    from oracle import orc
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    w = WORKLOADS[workload]
+    nthr = host_threads()
+    p = orc.make_params(ndim=3, riemann=w["riemann"], slope_type=w["slope_type"], boxlen=0.5, gamma=GAMMA,
+                        courant_factor=0.8)
+    m = orc.Mesh(3, sample_level, order=0)
+    u = m.new_state(5)
+    if w["ic"] == "sedov":
+        from helpers import SEDOV3D_REGIONS
+        orc.condinit_regions(p, m, sample_level, u, SEDOV3D_REGIONS)
+    else:
+        from helpers import smooth_state
+        m.dense_to_level(smooth_state(3, 1 << sample_level), u, sample_level, 5)
+    ncell = (1 << sample_level) ** 3
+    if warmup:
+        orc.run_uniform(p, m, sample_level, warmup, u, nthreads=nthr)
+    t0 = time.perf_counter()
+    orc.run_uniform(p, m, sample_level, steps, u, nthreads=nthr)
+    el = time.perf_counter() - t0
+    n = 1 << sample_level
+    return {"value": ncell * steps / el, "unit": "cell-updates/s", "cores": nthr, "kind": "port",
+            "sample": f"{w['ic']} {n}^3 periodic, riemann={w['riemann']}, {steps} level steps "
+                      f"(courant_fine+set_unew+godunov_fine+set_uold), C restatement of the RAMSES algorithm "
+                      f"(oracle/ramses_oracle.c, gcc -O2 -ffp-contract=off, OpenMP over nvector=32 oct batches)",
+            "seconds": el}, el / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sedov3d_256_exact", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--order", default="creation")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = WORKLOADS[args.workload]
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    # ------------------------------------------------------------------ reference arm (host cores, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb, sec_per_step = cpu_reference_run(args.workload, steps, warmup)
+        line = {"impl": "reference", "metric": "cell_updates_per_s", "value": cb["value"], "unit": "cell-updates/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec_per_step * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "note": "each step is a bounded 128^3 sample of the workload"},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    from ramses_b200.hydro import HydroGPU
+    from ramses_b200.tree import build_uniform_tree, coarse_dims_for_ranks, fill_state
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    level = w["level"]
+    coarse = coarse_dims_for_ranks(3, world)
+    boxlen = 0.5
+    a = build_uniform_tree(3, level, coarse=coarse, myid=rank + 1, ncpu=world, order=args.order, boxlen=boxlen)
+    a.gamma, a.courant_factor, a.slope_type, a.riemann = GAMMA, 0.8, w["slope_type"], w["riemann"]
+    fill_state(a, level, sedov_ic(boxlen, coarse[0], level) if w["ic"] == "sedov" else smooth_ic(coarse))
+    h = HydroGPU(a, device=local_rank)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            from ramses_b200 import lib as _l
+            _l.check(h.L.rgpu_comm_unique_id(buf))
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        buf = (C.c_ubyte * 128)(*uid.cpu().tolist())
+        from ramses_b200 import lib as _l
+        _l.check(h.L.rgpu_comm_init(world, rank, buf))
+    h.bind_level(level)
+    info0 = h.level_info(level)
+    assert info0.dense == 1
+    h.host_register(a.uold)
+    h.host_register(a.unew)
+    h.upload_state(level)
+    ncell_rank = len(a.active[level]) * 8
+    ncell_total = ncell_rank * world
+
+    def barrier():
+        h.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up
+    h.level_steps(level, warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = h.level_info(level).kernel_launches
+    barrier()
+    t0 = time.perf_counter()
+    dts, _ = h.level_steps(level, steps)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = h.level_info(level).last_steps_ms      # CUDA events on the launching stream
+    launches = h.level_info(level).kernel_launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = dev_ms * 1e-3
+    if world > 1:
+        tt = torch.tensor([t_dev, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, wall = tt.tolist()
+    value = ncell_total * steps / t_dev
+
+    # kernel-only roofline: average duration of the sweep kernel, CUDA events around each launch
+    h.set_timing(True)
+    ks = []
+    for _ in range(5):
+        h.level_steps(level, 1)
+        ks.append(h.level_info(level).last_sweep_ms)
+    h.set_timing(False)
+    k_ms = float(np.mean(ks))
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        peak, peak_src = json.load(open(peaks_file))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = BYTES_PER_CELL * ncell_rank / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tf):
+        traffic = json.load(open(tf)).get(args.workload)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "sweep_dense_kernel<3,%s>" % w["riemann"], "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": BYTES_PER_CELL * ncell_rank, "peak_source": peak_src,
+                "note": "FP64 issue rate, not HBM, is the binding roof for this kernel (DESIGN.md)"}
+
+    # end-to-end through the reference-facing call godunov_fine(ilevel) on HOST arrays (H2D + sweep + D2H per step)
+    h.download_state(level)
+    a.dtnew[level] = float(dts[-1])      # a CFL-limited dt of this run
+    h.godunov_fine(level)           # warm
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        h.godunov_fine(level)
+        a.uold, a.unew = a.unew, a.uold
+    barrier()
+    e2e_t = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_t = tt.item()
+    info = h.level_info(level)
+    gspan = info.nslot        # contiguous igrid window of the level on this rank
+    e2e = {"value": ncell_total * args.e2e_steps / e2e_t, "unit": "cell-updates/s",
+           "h2d_bytes_per_step": int(5 * 8 * gspan * 8), "d2h_bytes_per_step": int(5 * 8 * gspan * 8),
+           "steps": args.e2e_steps, "api": "rgpu_godunov_fine(ilevel, dt, uold_host, unew_host), pinned host arrays"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu_baseline, _ = cpu_reference_run(args.workload, 3, 1)
+            cpu_baseline.pop("seconds", None)
+        except Exception as e:      # the checker is optional for the measurement
+            cpu_baseline = {"error": repr(e)}
+    h.finalize()
+    if rank == 0:
+        n = 1 << level
+        line = {"metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+                "steps": steps, "warmup": warmup, "ms_per_step": t_dev / steps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "grid_per_gpu": f"{n}^3", "global_grid":
+                           f"{n * coarse[0]}x{n * coarse[1]}x{n * coarse[2]}", "riemann": w["riemann"],
+                           "slope_type": w["slope_type"], "decomposition": f"{coarse[0]}x{coarse[1]}x{coarse[2]} coarse cells, one per rank",
+                           "oct_order": args.order,
+                           "l2": "inputs larger than L2 (state %.2f GB per rank vs 126 MB L2), no flush" % (5 * 8 * ncell_rank / 1e9)},
+                "wall_ms_per_step": wall / steps * 1e3, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,147 @@
+/*
+ * ramses_gpu.h -- C-ABI of the B200 (sm_100a) per-level Godunov sweep for RAMSES.
+ *
+ * This is the drop-in boundary: a Fortran patch directory (PATCH=..., reference
+ * bin/Makefile:19,153) shadows hydro/godunov_fine.f90 with a shim that forwards
+ * each routine to the entry point of the same name below through ISO_C_BINDING
+ * (see INTEGRATION.md for the interface block).  Plain pointers and sizes only;
+ * all arrays are the reference's own Fortran arrays: column-major, 1-based
+ * indices stored as 32-bit integers, never freed or reallocated by the callee.
+ *
+ * Every function returns 0 on success or a negative RGPU_E* code; the last
+ * error text is available from rgpu_last_error().  The reference has no error
+ * channel besides write(*,*)+stop (hydro/umuscl.f90:801-803, amr/end.f90:26-46),
+ * so the shim maps non-zero to `call clean_stop`.
+ *
+ * There is NO CPU fallback: every entry point fails with RGPU_ECUDA when no
+ * CUDA device is usable.
+ */
+#ifndef RAMSES_GPU_H
+#define RAMSES_GPU_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGPU_ABI_VERSION 1
+
+enum {
+  RGPU_OK = 0,
+  RGPU_EINVAL = -1,       /* bad argument / call order                        */
+  RGPU_ECUDA = -2,        /* CUDA runtime error (no device, OOM, launch)      */
+  RGPU_EUNSUPPORTED = -3, /* valid RAMSES configuration not covered yet        */
+  RGPU_ENCCL = -4         /* NCCL error                                       */
+};
+
+/* riemann / scheme selectors: the strings of &HYDRO_PARAMS
+ * (hydro/hydro_parameters.f90:84-85, dispatch hydro/umuscl.f90:791-804)       */
+enum { RGPU_RIEMANN_LLF = 0, RGPU_RIEMANN_EXACT = 1, RGPU_RIEMANN_ACOUSTIC = 2,
+       RGPU_RIEMANN_HLLC = 3, RGPU_RIEMANN_HLL = 4 };
+enum { RGPU_SCHEME_MUSCL = 0, RGPU_SCHEME_PLMDE = 1 };
+
+/* Run parameters: compile-time constants of the reference build (NDIM, NVAR,
+ * bin/Makefile:65-84) and the &HYDRO_PARAMS / &AMR_PARAMS namelist values the
+ * path reads (hydro/read_hydro_params.f90:43-54).                            */
+typedef struct rgpu_params {
+  int ndim;            /* NDIM 1,2,3                                          */
+  int nvar;            /* NVAR (= ndim+2; passive scalars not yet supported)  */
+  int nvector;         /* NVECTOR: accepted for interface parity, unused      */
+  int slope_type;      /* 0,1,2,3,7,8 (+4,5,6 in 1-D)                          */
+  int niter_riemann;   /* Newton iterations of riemann='exact'                */
+  int scheme;          /* RGPU_SCHEME_MUSCL only                              */
+  int riemann;         /* RGPU_RIEMANN_*                                       */
+  int pressure_fix;    /* must be 0 (tmp/divu/enew path not built)            */
+  double gamma, smallr, smallc, slope_theta, difmag, courant_factor;
+  double boxlen;
+  int nx, ny, nz;      /* coarse grid incl. boundary cells (amr_parameters)   */
+  int icoarse_min, icoarse_max, jcoarse_min, jcoarse_max, kcoarse_min, kcoarse_max;
+  int nlevelmax;
+} rgpu_params;
+
+/* ---- life cycle -------------------------------------------------------------
+ * rgpu_init: once, after read_params (amr/read_params.f90:1).  device<0 picks
+ * LOCAL_RANK (or 0).  myid is 1-based like the reference's.                     */
+int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device);
+int rgpu_finalize(void);
+const char* rgpu_last_error(void);
+int rgpu_abi_version(void);
+
+/* ---- tree mirror (amr/amr_commons.f90:68-79; re-call after refine/defrag/
+ * load_balance, amr/amr_step.f90:92,109-117) ---------------------------------
+ * son(1:ncell), father(1:ngridmax), nbor(1:ngridmax,1:2*ndim): pointers to the
+ * first element of the Fortran arrays.  They must stay valid until the next
+ * rgpu_bind_tree (the library reads them inside rgpu_bind_level only).         */
+int rgpu_bind_tree(int ncoarse, int ngridmax, const int* son, const int* father, const int* nbor);
+
+/* ---- per-level communicator lists (amr/amr_commons.f90:108-119,170-180; built
+ * by build_comm, amr/virtual_boundaries.f90:1286) ------------------------------
+ * igrid_* are the %igrid arrays (1-based oct indices).  recv/emit are indexed by
+ * peer cpu 0..ncpu-1 (entry myid-1 is ignored); pass ncpu=1 and NULLs for a
+ * serial run.  bound lists are boundary(ibound,ilevel)%igrid with
+ * boundary_type(ibound) as computed in hydro/read_hydro_params.f90:316-420.    */
+int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active,
+                    int ncpu, const int* ngrid_recv, const int* const* igrid_recv,
+                    const int* ngrid_emit, const int* const* igrid_emit,
+                    int nboundary, const int* boundary_type,
+                    const int* ngrid_bound, const int* const* igrid_bound);
+
+/* ---- Level-0 contract: host arrays in, host arrays out ------------------------
+ * godunov_fine(ilevel) (hydro/godunov_fine.f90:5) on uold(1:ncell,1:nvar) ->
+ * unew(1:ncell,1:nvar): for every active cell of the level
+ *   unew = uold + sum_d (F_d^- - F_d^+), order x,y,z (godunov_fine.f90:751-792)
+ * (unew == uold on entry, i.e. right after set_unew; true for every
+ * levelmin=levelmax run).  dt = dtnew(ilevel).  Includes H2D/D2H copies.       */
+int rgpu_godunov_fine(int ilevel, double dt, const double* uold, double* unew);
+
+/* Page-lock / unlock a host array so the copies above run at full PCIe rate.   */
+int rgpu_host_register(void* ptr, size_t bytes);
+int rgpu_host_unregister(void* ptr);
+
+/* ---- Level-1 contract: device-resident state, same semantics as the F90 routines
+ * of the same name -------------------------------------------------------------- */
+int rgpu_upload_state(int ilevel, const double* uold);     /* host uold -> device level store */
+int rgpu_download_state(int ilevel, double* uold);         /* device level store -> host uold  */
+int rgpu_set_unew(int ilevel);                             /* hydro/godunov_fine.f90:40        */
+int rgpu_godunov_fine_dev(int ilevel, double dt);          /* hydro/godunov_fine.f90:5         */
+int rgpu_set_uold(int ilevel);                             /* hydro/godunov_fine.f90:135       */
+/* courant_fine (hydro/courant_fine.f90:1): *dt_io = min(*dt_io, CFL dt over the leaf
+ * cells of the level [over all ranks]); sums[3] += (mass, total E, internal E)      */
+int rgpu_courant_fine(int ilevel, double* dt_io, double sums[3]);
+int rgpu_make_boundary_hydro(int ilevel);                  /* hydro/hydro_boundary.f90:5       */
+int rgpu_make_virtual_fine(int ilevel);                    /* amr/virtual_boundaries.f90:373, all nvar at once */
+int rgpu_make_virtual_reverse(int ilevel);                 /* amr/virtual_boundaries.f90:693   */
+
+/* ---- fused fast path --------------------------------------------------------------
+ * nstep level steps of a levelmin=levelmax run in amr_step order
+ * (amr/amr_step.f90:326 courant, :333 set_unew, :388 godunov_fine, :423 set_uold,
+ * :505 ghost exchange, :514 boundary), state and dt staying on the device.
+ * dt_hist (nstep doubles, may be NULL) receives the dt of every step; sums_last[3]
+ * (may be NULL) the courant_fine sums of the final state.                         */
+int rgpu_level_steps(int ilevel, int nstep, double* dt_hist, double sums_last[3]);
+
+/* ---- multi-GPU: NCCL communicator replacing MPI_COMM_WORLD ----------------------
+ * unique_id: the 128-byte ncclUniqueId produced by rgpu_comm_unique_id on rank 0 and
+ * broadcast by the host program (MPI_Bcast in the Fortran driver).                */
+int rgpu_comm_unique_id(void* unique_id_128);
+int rgpu_comm_init(int nranks, int rank, const void* unique_id_128);
+
+/* ---- introspection (tests / bench) ---------------------------------------------- */
+typedef struct rgpu_level_info {
+  int dense;                 /* 1: dense-box fast path                             */
+  int ncell_box[3];          /* box extent in cells                                */
+  int own_lo[3], own_hi[3];  /* owned cell range                                   */
+  int wrap[3];
+  long long nslot;
+  long long kernel_launches; /* kernels launched on this level since bind          */
+  double last_sweep_ms;      /* CUDA-event duration of the last sweep kernel (timing on) */
+  double last_steps_ms;      /* CUDA-event duration of the last rgpu_level_steps call, on the launching stream */
+} rgpu_level_info;
+int rgpu_get_level_info(int ilevel, rgpu_level_info* out);
+/* time the next sweeps with CUDA events on the launching stream (bench)            */
+int rgpu_set_timing(int enable);
+int rgpu_device_synchronize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAMSES_GPU_H */

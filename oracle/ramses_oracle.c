@@ -1147,7 +1147,7 @@ orc_mesh* orc_mesh_build_uniform(int ndim, int levelmax, const int bt[6], int or
   for (int l = 1; l <= levelmax; l++) {
     /* candidate father cells, in the chosen creation order */
     int ncand = 0;
-    int* cand = (int*)malloc(sizeof(int) * (size_t)(l == 1 ? m->ncoarse : (size_t)nprev * twotondim));
+    int* cand = (int*)malloc(sizeof(int) * (l == 1 ? (size_t)m->ncoarse : (size_t)nprev * twotondim));
     if (l == 1) {
       for (int ic = 1; ic <= m->ncoarse; ic++) cand[ncand++] = ic;
     } else {

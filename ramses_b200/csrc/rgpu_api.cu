@@ -1,0 +1,926 @@
+// rgpu_api.cu -- host side of the C-ABI declared in include/ramses_gpu.h.
+//
+// Mirrors the reference's per-level driver routines (hydro/godunov_fine.f90,
+// hydro/courant_fine.f90, hydro/hydro_boundary.f90, amr/virtual_boundaries.f90)
+// on device-resident "level stores": for every bound level the octs named by the
+// communicator lists are renumbered into lattice order ("slots") and the state
+// lives as u[ivar][cell-in-oct][slot] -- the oct-tree layout of the reference
+// (hydro/hydro_commons.f90:4) with contiguous, spatially ordered octs.
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+#include "../../include/ramses_gpu.h"
+#include "sweep_dense.cuh"
+
+namespace rgpu {
+// launchers instantiated in sweep_inst_*.cu
+template <int NDIM, int RIEMANN> cudaError_t launch_sweep_dense(const SweepArgs& a, int nblocks, cudaStream_t st);
+#define DECL(ND, R) extern template cudaError_t launch_sweep_dense<ND, R>(const SweepArgs&, int, cudaStream_t);
+DECL(1, 0) DECL(1, 1) DECL(1, 2) DECL(1, 3) DECL(1, 4)
+DECL(2, 0) DECL(2, 1) DECL(2, 2) DECL(2, 3) DECL(2, 4)
+DECL(3, 0) DECL(3, 1) DECL(3, 2) DECL(3, 3) DECL(3, 4)
+#undef DECL
+}  // namespace rgpu
+
+using namespace rgpu;
+
+namespace {
+
+constexpr int MAXLEVEL = 32;
+char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_OK(x)                                                                                        \
+  do {                                                                                                    \
+    cudaError_t e_ = (x);                                                                                 \
+    if (e_ != cudaSuccess) return fail(RGPU_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+  } while (0)
+#define NCCL_OK(x)                                                                                        \
+  do {                                                                                                    \
+    ncclResult_t r_ = (x);                                                                                \
+    if (r_ != ncclSuccess) return fail(RGPU_ENCCL, "%s:%d %s: %s", __FILE__, __LINE__, #x, ncclGetErrorString(r_)); \
+  } while (0)
+
+struct BoundRegion {
+  int type = 0;          // boundary_type(ibound)
+  int n = 0;             // octs
+  int* d_slots = nullptr;
+};
+
+struct PeerList {        // one peer rank
+  int nrecv = 0, nemit = 0;
+  int* d_recv = nullptr; // slots of reception (ghost) octs, in the order of reception(icpu,ilevel)%igrid
+  int* d_emit = nullptr; // slots of emission octs
+  double* d_sbuf = nullptr;
+  double* d_rbuf = nullptr;
+};
+
+struct Level {
+  bool bound = false;
+  bool dense = false;
+  DenseGeom g{};
+  int lo[3] = {0, 0, 0};             // box origin in oct units (global oct coordinates)
+  int gmin = 0, gmax = 0;            // igrid range covered by the level (host mirror window)
+  long long nslot = 0;
+  std::vector<int> slot_igrid;       // igrid of every slot (0: empty)
+  int* d_slot_igrid = nullptr;
+  double* d_mirror = nullptr;        // host-layout window [nvar][2^ndim][gmax-gmin+1]
+  double* d_u[2] = {nullptr, nullptr};
+  int cur = 0;                       // d_u[cur] = uold, d_u[1-cur] = unew
+  bool unew_valid = false;
+  std::vector<BoundRegion> regions;
+  std::vector<PeerList> peers;
+  int ntx = 0, nty = 0, ntz = 0, zseg = 0, nblocks = 0;
+  double* d_part = nullptr;          // [4][nblocks_max]
+  int part_cap = 0;
+  double* d_dt = nullptr;            // [1] dt used by the next sweep
+  double* d_out = nullptr;           // [4] dt, mass, etot, eint of the last scan
+  double* d_hist = nullptr; int hist_cap = 0;
+  long long launches = 0;
+  double last_sweep_ms = 0;
+  double last_steps_ms = 0;
+  double dx = 0;
+};
+
+struct Context {
+  bool init = false;
+  rgpu_params p{};
+  Phys phys{};
+  int myid = 1, ncpu = 1, device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  bool timing = false;
+  int ncoarse = 0, ngridmax = 0;
+  const int *son = nullptr, *father = nullptr, *nbor = nullptr;
+  Level lev[MAXLEVEL + 1];
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+} G;
+
+// ----------------------------------------------------------------------------- kernels
+__global__ void gather_slots_kernel(const double* __restrict__ mirror, double* __restrict__ u, const int* __restrict__ slot_igrid,
+                                    long long nslot, int gmin, long long gspan, int nplanes) {
+  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= nslot) return;
+  const int ig = slot_igrid[s];
+  if (ig <= 0) return;
+  for (int pl = 0; pl < nplanes; pl++) u[(size_t)pl * nslot + s] = mirror[(size_t)pl * gspan + (ig - gmin)];
+}
+__global__ void scatter_slots_kernel(double* __restrict__ mirror, const double* __restrict__ u, const int* __restrict__ slot_igrid,
+                                     long long nslot, int gmin, long long gspan, int nplanes, int owned_only, DenseGeom g) {
+  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= nslot) return;
+  const int ig = slot_igrid[s];
+  if (ig <= 0) return;
+  if (owned_only) {   // only the active octs (owned cell range) are written back
+    const int ox = (int)(s % g.nox), oy = (int)((s / g.nox) % g.noy), oz = (int)(s / ((long long)g.nox * g.noy));
+    if (2 * ox < g.ox0 || 2 * ox >= g.ox1) return;
+    if (g.ncy > 1 && (2 * oy < g.oy0 || 2 * oy >= g.oy1)) return;
+    if (g.ncz > 1 && (2 * oz < g.oz0 || 2 * oz >= g.oz1)) return;
+  }
+  for (int pl = 0; pl < nplanes; pl++) mirror[(size_t)pl * gspan + (ig - gmin)] = u[(size_t)pl * nslot + s];
+}
+
+// set_unew on the owned cells: unew = uold (hydro/godunov_fine.f90:58-66); ghost octs: unew = 0 (:93-100)
+__global__ void copy_state_kernel(const double* __restrict__ src, double* __restrict__ dst, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+__global__ void zero_octs_kernel(double* __restrict__ u, const int* __restrict__ slots, int n, long long nslot, int nplanes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int pl = 0; pl < nplanes; pl++) u[(size_t)pl * nslot + slots[i]] = 0.0;
+}
+
+// carry a list of octs from one state buffer to the other (ghost / boundary shells across the uold<->unew swap)
+__global__ void copy_octs_kernel(const double* __restrict__ src, double* __restrict__ dst, const int* __restrict__ slots, int n,
+                                 long long nslot, int nplanes) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n * nplanes) return;
+  const size_t a = (size_t)(i / n) * nslot + slots[i % n];
+  dst[a] = src[a];
+}
+
+// make_boundary_hydro (hydro/hydro_boundary.f90:5-269) for one boundary region.
+struct BoundArgs {
+  int n; const int* slots; long long nslot; long long nbr_off; // slot offset of the reference oct (towards the domain)
+  int ind_ref[8]; double gs[3]; int kind;  // 0 wall (reflexive), 1 free (outflow)
+  int ndim, nvar; double smallr;
+};
+__global__ void boundary_kernel(double* __restrict__ u, const BoundArgs b) {
+  const int T = 1 << b.ndim;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n * T) return;
+  const int o = i / T, ind = i % T;
+  const long long s = b.slots[o], sr = s + b.nbr_off;
+  const int indr = b.ind_ref[ind] - 1;
+  double uu[8];
+  for (int iv = 0; iv < b.nvar; iv++) uu[iv] = u[((size_t)iv * T + indr) * b.nslot + sr];
+  if (b.kind == 0) {   // :141-157
+    for (int iv = 0; iv < b.nvar; iv++) {
+      double sw = 1.0;
+      if (iv >= 1 && iv <= b.ndim) sw = b.gs[iv - 1];
+      u[((size_t)iv * T + ind) * b.nslot + s] = uu[iv] * sw;
+    }
+  } else {             // :160-211 (no_inflow = .false.)
+    double ekin = 0.0;
+    double d = fmx(uu[0], b.smallr);
+    for (int idim = 0; idim < b.ndim; idim++) { const double v = uu[idim + 1] / d; ekin = ekin + 0.5 * d * (v * v); }
+    uu[b.ndim + 1] = uu[b.ndim + 1] - ekin;
+    ekin = 0.0;
+    d = fmx(uu[0], b.smallr);
+    for (int idim = 0; idim < b.ndim; idim++) { const double v = uu[idim + 1] / d; ekin = ekin + 0.5 * d * (v * v); }
+    uu[b.ndim + 1] = uu[b.ndim + 1] + ekin;
+    for (int iv = 0; iv < b.nvar; iv++) u[((size_t)iv * T + ind) * b.nslot + s] = uu[iv];
+  }
+}
+
+// stand-alone courant_fine scan over the owned cells (hydro/courant_fine.f90:1-159)
+template <int NDIM>
+__global__ void courant_kernel(const double* __restrict__ u, DenseGeom g, Phys P, double dx, double* __restrict__ part) {
+  constexpr int NV = NDIM + 2, T = 1 << NDIM;
+  __shared__ double red[4][32];
+  const long long nx = g.ox1 - g.ox0, ny = NDIM > 1 ? g.oy1 - g.oy0 : 1, nz = NDIM > 2 ? g.oz1 - g.oz0 : 1;
+  const long long ncell = nx * ny * nz;
+  double my_dt = 1e300, m0 = 0, m1 = 0, m2 = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ncell; i += (long long)gridDim.x * blockDim.x) {
+    const int x = g.ox0 + (int)(i % nx), y = NDIM > 1 ? g.oy0 + (int)((i / nx) % ny) : 0, z = NDIM > 2 ? g.oz0 + (int)(i / (nx * ny)) : 0;
+    const long long off = cell_offset<NDIM>(g, x, y, z);
+    double uu[NV];
+#pragma unroll
+    for (int n = 0; n < NV; n++) uu[n] = u[(size_t)n * T * g.nslot + off];
+    const double dtc = cmpdt_cell<NDIM>(uu, dx, P);
+    my_dt = dtc < my_dt ? dtc : my_dt;
+    m0 += uu[0]; m1 += uu[NDIM + 1];
+    double ei = uu[NDIM + 1];
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) ei = ei - 0.5 * (uu[d + 1] * uu[d + 1]) / fmx(uu[0], P.smallr);
+    m2 += ei;
+  }
+  my_dt = warp_min(my_dt); m0 = warp_sum(m0); m1 = warp_sum(m1); m2 = warp_sum(m2);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = my_dt; red[1][w] = m0; red[2][w] = m1; red[3][w] = m2; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    double v0 = l < nw ? red[0][l] : 1e300, v1 = l < nw ? red[1][l] : 0, v2 = l < nw ? red[2][l] : 0, v3 = l < nw ? red[3][l] : 0;
+    v0 = warp_min(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+    if (l == 0) {
+      const size_t nb = gridDim.x;
+      part[0 * nb + blockIdx.x] = v0; part[1 * nb + blockIdx.x] = v1; part[2 * nb + blockIdx.x] = v2; part[3 * nb + blockIdx.x] = v3;
+    }
+  }
+}
+
+// final reduction of the per-CTA partials: dt = min(dt_cap, courant_factor*dx/smallc, min dtcell)
+// (cmpdt godunov_utils.f90:113-118, courant_fine.f90:121-123,155); fixed summation order.
+__global__ void courant_reduce_kernel(const double* __restrict__ part, int nb, double dt_cap, double dt_floor0, double vol,
+                                      double* __restrict__ out /*[4]*/, double* __restrict__ dt_dev, double* __restrict__ hist) {
+  __shared__ double red[4][32];
+  double v0 = 1e300, v1 = 0, v2 = 0, v3 = 0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    v0 = part[i] < v0 ? part[i] : v0; v1 += part[(size_t)nb + i]; v2 += part[2 * (size_t)nb + i]; v3 += part[3 * (size_t)nb + i];
+  }
+  v0 = warp_min(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = v0; red[1][w] = v1; red[2][w] = v2; red[3][w] = v3; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    v0 = l < nw ? red[0][l] : 1e300; v1 = l < nw ? red[1][l] : 0; v2 = l < nw ? red[2][l] : 0; v3 = l < nw ? red[3][l] : 0;
+    v0 = warp_min(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+    if (l == 0) {
+      double dt = dt_floor0 < v0 ? dt_floor0 : v0;
+      dt = dt_cap < dt ? dt_cap : dt;
+      out[0] = dt; out[1] = v1 * vol; out[2] = v2 * vol; out[3] = v3 * vol;
+      if (dt_dev) *dt_dev = dt;
+      if (hist) *hist = dt;
+    }
+  }
+}
+
+// pack / unpack of ghost-oct exchange buffers: all variables of one peer in one message
+// (replaces the per-variable messages of make_virtual_fine_dp, amr/virtual_boundaries.f90:454-464,492-506)
+__global__ void pack_kernel(const double* __restrict__ u, const int* __restrict__ slots, int n, long long nslot, int nplanes, double* __restrict__ buf) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n * nplanes) return;
+  const int o = (int)(i % n), pl = (int)(i / n);
+  buf[i] = u[(size_t)pl * nslot + slots[o]];
+}
+__global__ void unpack_kernel(double* __restrict__ u, const int* __restrict__ slots, int n, long long nslot, int nplanes, const double* __restrict__ buf, int accumulate) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n * nplanes) return;
+  const int o = (int)(i % n), pl = (int)(i / n);
+  const size_t a = (size_t)pl * nslot + slots[o];
+  if (accumulate) u[a] = u[a] + buf[i]; else u[a] = buf[i];
+}
+
+// ----------------------------------------------------------------------------- helpers
+inline int T_() { return 1 << G.p.ndim; }
+inline size_t nplanes_() { return (size_t)G.p.nvar * T_(); }
+
+double level_dx(int ilevel) {  // godunov_fine.f90:532-534
+  const int nx_loc = G.p.icoarse_max - G.p.icoarse_min + 1;
+  const double scale = G.p.boxlen / (double)nx_loc;
+  return std::pow(0.5, ilevel) * scale;
+}
+
+// integer position of an oct (units of its own size): walk the father chain (amr_commons: father(igrid)
+// = father cell; cell index = ncoarse + (ind-1)*ngridmax + igrid)
+void oct_pos(int ilevel, int igrid, int pos[3]) {
+  int chain[MAXLEVEL];
+  int g = igrid;
+  int n = 0;
+  for (int l = ilevel; l > 1; l--) {
+    const int ic = G.father[g - 1];
+    const int ind = (ic - G.ncoarse - 1) / G.ngridmax;
+    g = ic - G.ncoarse - ind * G.ngridmax;
+    chain[n++] = ind;
+  }
+  const int ic = G.father[g - 1];
+  const int nxny = G.p.nx * G.p.ny;
+  int pz = (ic - 1) / nxny, py = (ic - 1 - pz * nxny) / G.p.nx, px = ic - 1 - py * G.p.nx - pz * nxny;
+  for (int i = n - 1; i >= 0; i--) {
+    px = 2 * px + (chain[i] & 1);
+    py = 2 * py + ((chain[i] >> 1) & 1);
+    pz = 2 * pz + ((chain[i] >> 2) & 1);
+  }
+  pos[0] = px; pos[1] = py; pos[2] = pz;
+}
+
+void free_level(Level& L) {
+  cudaFree(L.d_slot_igrid); cudaFree(L.d_mirror); cudaFree(L.d_u[0]); cudaFree(L.d_u[1]);
+  cudaFree(L.d_part); cudaFree(L.d_dt); cudaFree(L.d_out); cudaFree(L.d_hist);
+  for (auto& r : L.regions) cudaFree(r.d_slots);
+  for (auto& p : L.peers) { cudaFree(p.d_recv); cudaFree(p.d_emit); cudaFree(p.d_sbuf); cudaFree(p.d_rbuf); }
+  L = Level();
+}
+
+int check_level(int ilevel, Level** out) {
+  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  if (ilevel < 1 || ilevel > MAXLEVEL) return fail(RGPU_EINVAL, "ilevel %d out of range", ilevel);
+  Level& L = G.lev[ilevel];
+  if (!L.bound) return fail(RGPU_EINVAL, "level %d is not bound (rgpu_bind_level)", ilevel);
+  if (!L.dense) return fail(RGPU_EUNSUPPORTED, "level %d is not a dense box; the AMR oct-batch path is not built yet", ilevel);
+  *out = &L;
+  return RGPU_OK;
+}
+
+template <int ND>
+cudaError_t dispatch_sweep_nd(int riemann, const SweepArgs& a, int nb, cudaStream_t st) {
+  switch (riemann) {
+    case RGPU_RIEMANN_LLF: return launch_sweep_dense<ND, RIEMANN_LLF>(a, nb, st);
+    case RGPU_RIEMANN_EXACT: return launch_sweep_dense<ND, RIEMANN_EXACT>(a, nb, st);
+    case RGPU_RIEMANN_ACOUSTIC: return launch_sweep_dense<ND, RIEMANN_ACOUSTIC>(a, nb, st);
+    case RGPU_RIEMANN_HLLC: return launch_sweep_dense<ND, RIEMANN_HLLC>(a, nb, st);
+    default: return launch_sweep_dense<ND, RIEMANN_HLL>(a, nb, st);
+  }
+}
+
+int launch_sweep(Level& L) {
+  SweepArgs a{};
+  a.uin = L.d_u[L.cur];
+  a.uout = L.d_u[1 - L.cur];
+  a.g = L.g;
+  a.P = G.phys;
+  a.dt_dev = L.d_dt;
+  a.dx = L.dx;
+  a.inv_dx = 1.0 / L.dx;
+  int ex;
+  a.dx_pow2 = (std::frexp(L.dx, &ex) == 0.5) ? 1 : 0;
+  a.ntx = L.ntx; a.nty = L.nty; a.ntz = L.ntz; a.zseg = L.zseg;
+  a.part = L.d_part;
+  if (G.timing) cudaEventRecord(G.ev0, G.stream);
+  cudaError_t e;
+  if (G.p.ndim == 1) e = dispatch_sweep_nd<1>(G.p.riemann, a, L.nblocks, G.stream);
+  else if (G.p.ndim == 2) e = dispatch_sweep_nd<2>(G.p.riemann, a, L.nblocks, G.stream);
+  else e = dispatch_sweep_nd<3>(G.p.riemann, a, L.nblocks, G.stream);
+  if (e != cudaSuccess) return fail(RGPU_ECUDA, "sweep launch: %s", cudaGetErrorString(e));
+  if (G.timing) {
+    cudaEventRecord(G.ev1, G.stream);
+    cudaEventSynchronize(G.ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, G.ev0, G.ev1);
+    L.last_sweep_ms = ms;
+  }
+  L.launches++;
+  return RGPU_OK;
+}
+
+// reduce partials of the last sweep / courant scan into d_out and d_dt
+int launch_reduce(Level& L, int nb, double dt_cap, double* hist_slot) {
+  const double vol = std::pow(L.dx, G.p.ndim);
+  const double dt0 = G.p.courant_factor * L.dx / G.p.smallc;   // cmpdt: dt = courant_factor*dx/smallc
+  courant_reduce_kernel<<<1, 1024, 0, G.stream>>>(L.d_part, nb, dt_cap, dt0, vol, L.d_out, L.d_dt, hist_slot);
+  CUDA_OK(cudaGetLastError());
+  L.launches++;
+  return RGPU_OK;
+}
+
+int launch_courant(Level& L, double dt_cap, double* hist_slot) {
+  const int nb = std::min(L.part_cap, 148 * 8);
+  if (G.p.ndim == 1) courant_kernel<1><<<nb, 256, 0, G.stream>>>(L.d_u[L.cur], L.g, G.phys, L.dx, L.d_part);
+  else if (G.p.ndim == 2) courant_kernel<2><<<nb, 256, 0, G.stream>>>(L.d_u[L.cur], L.g, G.phys, L.dx, L.d_part);
+  else courant_kernel<3><<<nb, 256, 0, G.stream>>>(L.d_u[L.cur], L.g, G.phys, L.dx, L.d_part);
+  CUDA_OK(cudaGetLastError());
+  L.launches++;
+  return launch_reduce(L, nb, dt_cap, hist_slot);
+}
+
+int launch_boundaries(Level& L, double* u) {
+  // boundaries are applied in the order ibound = 1..nboundary like the reference loop
+  // (hydro_boundary.f90:53): corner octs read neighbours that a later region refreshes.
+  static const int ref_x[8] = {2, 1, 4, 3, 6, 5, 8, 7}, ref_y[8] = {3, 4, 1, 2, 7, 8, 5, 6}, ref_z[8] = {5, 6, 7, 8, 1, 2, 3, 4};
+  static const int fre[6][8] = {{1, 1, 3, 3, 5, 5, 7, 7}, {2, 2, 4, 4, 6, 6, 8, 8}, {1, 2, 1, 2, 5, 6, 5, 6},
+                                {3, 4, 3, 4, 7, 8, 7, 8}, {1, 2, 3, 4, 1, 2, 3, 4}, {5, 6, 7, 8, 5, 6, 7, 8}};
+  for (auto& r : L.regions) {
+    if (r.n == 0) continue;
+    const int bt = r.type, dir = bt - 10 * (bt / 10);
+    if (bt / 10 > 1) return fail(RGPU_EUNSUPPORTED, "imposed boundary (boundana) type %d not supported", bt);
+    BoundArgs b{};
+    b.n = r.n; b.slots = r.d_slots; b.nslot = L.nslot;
+    const long long str[3] = {1, L.g.nox, (long long)L.g.nox * L.g.noy};
+    const int d = (dir - 1) / 2;
+    b.nbr_off = (dir % 2 == 1) ? str[d] : -str[d];   // boundary at the min face looks towards +d
+    const int* ir = (bt / 10 == 0) ? (d == 0 ? ref_x : d == 1 ? ref_y : ref_z) : fre[dir - 1];
+    for (int i = 0; i < 8; i++) b.ind_ref[i] = ir[i];
+    b.gs[0] = b.gs[1] = b.gs[2] = 1.0;
+    if (bt >= 1 && bt <= 6) b.gs[d] = -1.0;
+    b.kind = bt / 10;
+    b.ndim = G.p.ndim; b.nvar = G.p.nvar; b.smallr = G.p.smallr;
+    const int nthr = r.n * T_();
+    boundary_kernel<<<(nthr + 127) / 128, 128, 0, G.stream>>>(u, b);
+    CUDA_OK(cudaGetLastError());
+    L.launches++;
+  }
+  return RGPU_OK;
+}
+
+int exchange_ghosts(Level& L, double* u, bool reverse);
+
+// set_uold only touches the active cells: the boundary / ghost shells keep their uold values until the next
+// make_boundary_hydro / make_virtual_fine.  With ping-pong buffers those values must be carried over explicitly
+// (corner boundary octs read neighbours that are refreshed later in the same pass, hydro_boundary.f90:53).
+int carry_shells(Level& L, const double* from, double* to) {
+  const long long np = (long long)nplanes_();
+  for (auto& r : L.regions)
+    if (r.n) {
+      copy_octs_kernel<<<(unsigned)(((long long)r.n * np + 255) / 256), 256, 0, G.stream>>>(from, to, r.d_slots, r.n, L.nslot, (int)np);
+      CUDA_OK(cudaGetLastError());
+      L.launches++;
+    }
+  for (auto& P : L.peers)
+    if (P.nrecv) {
+      copy_octs_kernel<<<(unsigned)(((long long)P.nrecv * np + 255) / 256), 256, 0, G.stream>>>(from, to, P.d_recv, P.nrecv, L.nslot, (int)np);
+      CUDA_OK(cudaGetLastError());
+      L.launches++;
+    }
+  return RGPU_OK;
+}
+
+}  // namespace
+
+// ============================================================================= C ABI
+extern "C" {
+
+int rgpu_abi_version(void) { return RGPU_ABI_VERSION; }
+const char* rgpu_last_error(void) { return g_err; }
+
+int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device) {
+  if (!p) return fail(RGPU_EINVAL, "null params");
+  if (p->ndim < 1 || p->ndim > 3) return fail(RGPU_EINVAL, "ndim=%d", p->ndim);
+  if (p->nvar != p->ndim + 2) return fail(RGPU_EUNSUPPORTED, "nvar=%d: passive scalars / NENER not supported (need nvar=ndim+2)", p->nvar);
+  if (p->scheme != RGPU_SCHEME_MUSCL) return fail(RGPU_EUNSUPPORTED, "scheme='plmde' not supported");
+  if (p->riemann < 0 || p->riemann > 4) return fail(RGPU_EINVAL, "unknown Riemann solver %d", p->riemann);
+  if (p->pressure_fix) return fail(RGPU_EUNSUPPORTED, "pressure_fix not supported");
+  if (p->difmag > 0.0) return fail(RGPU_EUNSUPPORTED, "difmag>0 not supported");
+  {
+    const int st = p->slope_type;
+    const bool ok = st == 0 || st == 1 || st == 2 || st == 3 || st == 7 || st == 8 || (p->ndim == 1 && st >= 4 && st <= 6);
+    if (!ok) return fail(RGPU_EINVAL, "Unknown slope type %d", st);   // umuscl.f90:1083,1203,1476
+  }
+  if (G.init) rgpu_finalize();
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(RGPU_ECUDA, "no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e));
+  if (device < 0) {
+    const char* lr = getenv("LOCAL_RANK");
+    device = lr ? atoi(lr) % ndev : 0;
+  }
+  CUDA_OK(cudaSetDevice(device));
+  G.p = *p; G.myid = myid; G.ncpu = ncpu; G.device = device;
+  CUDA_OK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&G.ev0));
+  CUDA_OK(cudaEventCreate(&G.ev1));
+  CUDA_OK(cudaEventCreate(&G.ev2));
+  CUDA_OK(cudaEventCreate(&G.ev3));
+  Phys& P = G.phys;
+  P.gamma = p->gamma; P.smallr = p->smallr; P.smallc = p->smallc; P.slope_theta = p->slope_theta;
+  P.courant_factor = p->courant_factor;
+  P.smalle = p->smallc * p->smallc / p->gamma / (p->gamma - 1.0);
+  P.smallp = p->smallc * p->smallc / p->gamma;
+  P.smallpp = p->smallr * P.smallp;
+  P.entho = 1.0 / (p->gamma - 1.0);
+  P.gamma6 = (p->gamma + 1.0) / (2.0 * p->gamma);
+  P.smallc2 = p->smallc * p->smallc;
+  P.inv_gamma = 1.0 / p->gamma;
+  P.slope_type = p->slope_type; P.niter_riemann = p->niter_riemann;
+  G.init = true;
+  return RGPU_OK;
+}
+
+int rgpu_finalize(void) {
+  if (!G.init) return RGPU_OK;
+  cudaStreamSynchronize(G.stream);
+  for (int l = 0; l <= MAXLEVEL; l++) if (G.lev[l].bound) free_level(G.lev[l]);
+  if (G.comm) { ncclCommDestroy(G.comm); G.comm = nullptr; }
+  cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); cudaEventDestroy(G.ev2); cudaEventDestroy(G.ev3);
+  cudaStreamDestroy(G.stream);
+  G.init = false;
+  return RGPU_OK;
+}
+
+int rgpu_bind_tree(int ncoarse, int ngridmax, const int* son, const int* father, const int* nbor) {
+  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  if (!son || !father || !nbor) return fail(RGPU_EINVAL, "null tree array");
+  if (ncoarse != G.p.nx * G.p.ny * G.p.nz) return fail(RGPU_EINVAL, "ncoarse=%d != nx*ny*nz", ncoarse);
+  G.ncoarse = ncoarse; G.ngridmax = ngridmax; G.son = son; G.father = father; G.nbor = nbor;
+  return RGPU_OK;
+}
+
+int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int ncpu, const int* ngrid_recv,
+                    const int* const* igrid_recv, const int* ngrid_emit, const int* const* igrid_emit, int nboundary,
+                    const int* boundary_type, const int* ngrid_bound, const int* const* igrid_bound) {
+  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  if (!G.son) return fail(RGPU_EINVAL, "rgpu_bind_tree has not been called");
+  if (ilevel < 1 || ilevel > MAXLEVEL) return fail(RGPU_EINVAL, "ilevel %d out of range", ilevel);
+  if (ngrid_active <= 0 || !igrid_active) return fail(RGPU_EINVAL, "level %d has no active oct", ilevel);
+  Level& L = G.lev[ilevel];
+  if (L.bound) free_level(L);
+  const int nd = G.p.ndim, T = T_();
+  L.dx = level_dx(ilevel);
+  // ---- collect every oct of the level with its position -------------------------------------
+  struct Rec { int ig; int pos[3]; int kind; int sub; };  // kind 0 active, 1 recv(peer sub), 2 boundary(region sub)
+  std::vector<Rec> recs;
+  recs.reserve((size_t)ngrid_active + 1024);
+  auto add = [&](int ig, int kind, int sub) { Rec r; r.ig = ig; r.kind = kind; r.sub = sub; oct_pos(ilevel, ig, r.pos); recs.push_back(r); };
+  for (int i = 0; i < ngrid_active; i++) add(igrid_active[i], 0, 0);
+  if (ncpu > 1 && ngrid_recv && igrid_recv)
+    for (int c = 0; c < ncpu; c++) if (c != G.myid - 1) for (int i = 0; i < ngrid_recv[c]; i++) add(igrid_recv[c][i], 1, c);
+  for (int b = 0; b < nboundary; b++) for (int i = 0; i < ngrid_bound[b]; i++) add(igrid_bound[b][i], 2, b);
+  // ---- owned box ------------------------------------------------------------------------------
+  int alo[3] = {1 << 30, 1 << 30, 1 << 30}, ahi[3] = {-1, -1, -1};
+  for (int i = 0; i < ngrid_active; i++)
+    for (int d = 0; d < 3; d++) { alo[d] = std::min(alo[d], recs[i].pos[d]); ahi[d] = std::max(ahi[d], recs[i].pos[d]); }
+  long long avol = 1;
+  for (int d = 0; d < nd; d++) avol *= (ahi[d] - alo[d] + 1);
+  // full extent of the level in octs per dimension (periodic images of ghost octs are unwrapped against it)
+  const int ncoarse_d[3] = {G.p.nx, G.p.ny, G.p.nz};
+  long long ext[3] = {1, 1, 1};
+  for (int d = 0; d < nd; d++) ext[d] = (long long)ncoarse_d[d] << (ilevel - 1);
+  // unwrap ghost octs that sit across a periodic boundary so that they become adjacent to the owned box
+  for (size_t i = ngrid_active; i < recs.size(); i++)
+    for (int d = 0; d < nd; d++) {
+      if (recs[i].pos[d] > ahi[d] + 1 && recs[i].pos[d] - ext[d] >= alo[d] - 1) recs[i].pos[d] -= (int)ext[d];
+      else if (recs[i].pos[d] < alo[d] - 1 && recs[i].pos[d] + ext[d] <= ahi[d] + 1) recs[i].pos[d] += (int)ext[d];
+    }
+  int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  for (int d = 0; d < nd; d++) { lo[d] = alo[d]; hi[d] = ahi[d]; }
+  bool in_shell = true;
+  for (size_t i = ngrid_active; i < recs.size(); i++)
+    for (int d = 0; d < nd; d++) {
+      lo[d] = std::min(lo[d], recs[i].pos[d]); hi[d] = std::max(hi[d], recs[i].pos[d]);
+      if (recs[i].pos[d] < alo[d] - 1 || recs[i].pos[d] > ahi[d] + 1) in_shell = false;
+    }
+  L.bound = true;
+  L.dense = (avol == ngrid_active) && in_shell;
+  if (!L.dense) return RGPU_OK;   // bound, but only the AMR path (not built) could run it
+  // every dimension must either be periodic over the whole level (no shell) or carry a shell on both sides
+  int wrap[3] = {0, 0, 0};
+  for (int d = 0; d < nd; d++) {
+    const bool shell_lo = lo[d] < alo[d], shell_hi = hi[d] > ahi[d];
+    if (!shell_lo && !shell_hi) {
+      if ((long long)(ahi[d] - alo[d] + 1) != ext[d] || alo[d] != 0) { L.dense = false; return RGPU_OK; }
+      wrap[d] = 1;
+    } else if (!(shell_lo && shell_hi)) { L.dense = false; return RGPU_OK; }
+  }
+  long long nslot = 1;
+  int no[3] = {1, 1, 1};
+  for (int d = 0; d < nd; d++) { no[d] = hi[d] - lo[d] + 1; nslot *= no[d]; }
+  L.nslot = nslot;
+  for (int d = 0; d < 3; d++) L.lo[d] = lo[d];
+  DenseGeom& g = L.g;
+  g.nox = no[0]; g.noy = no[1]; g.noz = no[2];
+  g.ncx = 2 * no[0]; g.ncy = nd > 1 ? 2 * no[1] : 1; g.ncz = nd > 2 ? 2 * no[2] : 1;
+  g.ox0 = 2 * (alo[0] - lo[0]); g.ox1 = 2 * (ahi[0] - lo[0] + 1);
+  g.oy0 = nd > 1 ? 2 * (alo[1] - lo[1]) : 0; g.oy1 = nd > 1 ? 2 * (ahi[1] - lo[1] + 1) : 1;
+  g.oz0 = nd > 2 ? 2 * (alo[2] - lo[2]) : 0; g.oz1 = nd > 2 ? 2 * (ahi[2] - lo[2] + 1) : 1;
+  g.wrapx = wrap[0]; g.wrapy = wrap[1]; g.wrapz = wrap[2];
+  g.nslot = nslot;
+  // ---- slot maps ------------------------------------------------------------------------------
+  L.slot_igrid.assign((size_t)nslot, 0);
+  auto slot_of = [&](const int* pos) {
+    long long s = pos[0] - lo[0];
+    if (nd > 1) s += (long long)no[0] * (pos[1] - lo[1]);
+    if (nd > 2) s += (long long)no[0] * no[1] * (pos[2] - lo[2]);
+    return s;
+  };
+  L.gmin = 1 << 30; L.gmax = 0;
+  std::vector<std::vector<int>> bslots(nboundary), rslots(ncpu > 1 ? ncpu : 0);
+  for (auto& r : recs) {
+    const long long s = slot_of(r.pos);
+    if (L.slot_igrid[s] != 0) return fail(RGPU_EINVAL, "level %d: two octs (%d,%d) at the same lattice site", ilevel, L.slot_igrid[s], r.ig);
+    L.slot_igrid[s] = r.ig;
+    L.gmin = std::min(L.gmin, r.ig); L.gmax = std::max(L.gmax, r.ig);
+    if (r.kind == 2) bslots[r.sub].push_back((int)s);
+    if (r.kind == 1) rslots[r.sub].push_back((int)s);
+  }
+  if (nslot >= (1LL << 31)) return fail(RGPU_EUNSUPPORTED, "level too large for 32-bit slots");
+  const long long gspan = (long long)L.gmax - L.gmin + 1;
+  const size_t np = nplanes_();
+  CUDA_OK(cudaMalloc(&L.d_slot_igrid, sizeof(int) * nslot));
+  CUDA_OK(cudaMemcpy(L.d_slot_igrid, L.slot_igrid.data(), sizeof(int) * nslot, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&L.d_mirror, sizeof(double) * np * gspan));
+  CUDA_OK(cudaMalloc(&L.d_u[0], sizeof(double) * np * nslot));
+  CUDA_OK(cudaMalloc(&L.d_u[1], sizeof(double) * np * nslot));
+  CUDA_OK(cudaMemset(L.d_u[0], 0, sizeof(double) * np * nslot));
+  CUDA_OK(cudaMemset(L.d_u[1], 0, sizeof(double) * np * nslot));
+  L.regions.resize(nboundary);
+  for (int b = 0; b < nboundary; b++) {
+    L.regions[b].type = boundary_type[b];
+    L.regions[b].n = (int)bslots[b].size();
+    if (L.regions[b].n) {
+      CUDA_OK(cudaMalloc(&L.regions[b].d_slots, sizeof(int) * bslots[b].size()));
+      CUDA_OK(cudaMemcpy(L.regions[b].d_slots, bslots[b].data(), sizeof(int) * bslots[b].size(), cudaMemcpyHostToDevice));
+    }
+  }
+  // ---- peers (ghost exchange lists) ----------------------------------------------------------
+  if (ncpu > 1) {
+    L.peers.resize(ncpu);
+    for (int c = 0; c < ncpu; c++) {
+      if (c == G.myid - 1) continue;
+      PeerList& P = L.peers[c];
+      P.nrecv = (int)rslots[c].size();
+      if (P.nrecv) {
+        CUDA_OK(cudaMalloc(&P.d_recv, sizeof(int) * P.nrecv));
+        CUDA_OK(cudaMemcpy(P.d_recv, rslots[c].data(), sizeof(int) * P.nrecv, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&P.d_rbuf, sizeof(double) * np * P.nrecv));
+      }
+      P.nemit = (ngrid_emit && igrid_emit) ? ngrid_emit[c] : 0;
+      if (P.nemit) {
+        std::vector<int> es(P.nemit);
+        for (int i = 0; i < P.nemit; i++) {
+          int pos[3];
+          oct_pos(ilevel, igrid_emit[c][i], pos);
+          es[i] = (int)slot_of(pos);
+        }
+        CUDA_OK(cudaMalloc(&P.d_emit, sizeof(int) * P.nemit));
+        CUDA_OK(cudaMemcpy(P.d_emit, es.data(), sizeof(int) * P.nemit, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&P.d_sbuf, sizeof(double) * np * P.nemit));
+      }
+    }
+  }
+  // ---- tile decomposition of the owned range ----------------------------------------------------
+  const int bx = nd == 1 ? TileShape<1>::BX : nd == 2 ? TileShape<2>::BX : TileShape<3>::BX;
+  const int by = nd == 1 ? 1 : nd == 2 ? TileShape<2>::BY : TileShape<3>::BY;
+  const int txo = bx - 2, tyo = nd > 1 ? by - 2 : 1;
+  L.ntx = (g.ox1 - g.ox0 + txo - 1) / txo;
+  L.nty = nd > 1 ? (g.oy1 - g.oy0 + tyo - 1) / tyo : 1;
+  if (nd > 2) {
+    // z segments: aim at >= 4 CTAs per SM-slot so that the tail of the last wave stays small
+    const int nzo = g.oz1 - g.oz0;
+    const long long cols = (long long)L.ntx * L.nty;
+    int nseg = (int)std::max<long long>(1, (148LL * 4 + cols - 1) / cols);
+    nseg = std::min(nseg, std::max(1, nzo / 8));
+    L.zseg = (nzo + nseg - 1) / nseg;
+    L.ntz = (nzo + L.zseg - 1) / L.zseg;
+  } else { L.zseg = 1; L.ntz = 1; }
+  L.nblocks = L.ntx * L.nty * L.ntz;
+  L.part_cap = std::max(L.nblocks, 148 * 8);
+  CUDA_OK(cudaMalloc(&L.d_part, sizeof(double) * 4 * L.part_cap));
+  CUDA_OK(cudaMalloc(&L.d_dt, sizeof(double)));
+  CUDA_OK(cudaMalloc(&L.d_out, sizeof(double) * 4));
+  L.cur = 0; L.unew_valid = false;
+  return RGPU_OK;
+}
+
+int rgpu_host_register(void* ptr, size_t bytes) {
+  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  CUDA_OK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return RGPU_OK;
+}
+int rgpu_host_unregister(void* ptr) {
+  CUDA_OK(cudaHostUnregister(ptr));
+  return RGPU_OK;
+}
+
+static int upload_into(Level& L, const double* host, double* dst) {
+  const int T = T_();
+  const long long gspan = (long long)L.gmax - L.gmin + 1;
+  const size_t ncell = (size_t)G.ncoarse + (size_t)T * G.ngridmax;
+  for (int iv = 0; iv < G.p.nvar; iv++)
+    for (int ind = 0; ind < T; ind++) {
+      const double* src = host + (size_t)iv * ncell + G.ncoarse + (size_t)ind * G.ngridmax + (L.gmin - 1);
+      CUDA_OK(cudaMemcpyAsync(L.d_mirror + ((size_t)iv * T + ind) * gspan, src, sizeof(double) * gspan, cudaMemcpyHostToDevice, G.stream));
+    }
+  const int nthr = 256;
+  gather_slots_kernel<<<(unsigned)((L.nslot + nthr - 1) / nthr), nthr, 0, G.stream>>>(L.d_mirror, dst, L.d_slot_igrid, L.nslot, L.gmin, gspan, (int)nplanes_());
+  CUDA_OK(cudaGetLastError());
+  L.launches++;
+  return RGPU_OK;
+}
+// device level store -> host array.  owned_only: write back the active octs only (unew of godunov_fine);
+// the mirror window is pre-loaded from the host whenever it also covers octs that must keep the host's values.
+static int download_from(Level& L, double* host, const double* srcdev, bool owned_only) {
+  const int T = T_();
+  const long long gspan = (long long)L.gmax - L.gmin + 1;
+  const size_t ncell = (size_t)G.ncoarse + (size_t)T * G.ngridmax;
+  long long nown = (L.g.ox1 - L.g.ox0) / 2;
+  if (G.p.ndim > 1) nown *= (L.g.oy1 - L.g.oy0) / 2;
+  if (G.p.ndim > 2) nown *= (L.g.oz1 - L.g.oz0) / 2;
+  const bool preload = (gspan != L.nslot) || (owned_only && nown != L.nslot);
+  if (preload)
+    for (int iv = 0; iv < G.p.nvar; iv++)
+      for (int ind = 0; ind < T; ind++) {
+        const double* src = host + (size_t)iv * ncell + G.ncoarse + (size_t)ind * G.ngridmax + (L.gmin - 1);
+        CUDA_OK(cudaMemcpyAsync(L.d_mirror + ((size_t)iv * T + ind) * gspan, src, sizeof(double) * gspan, cudaMemcpyHostToDevice, G.stream));
+      }
+  const int nthr = 256;
+  scatter_slots_kernel<<<(unsigned)((L.nslot + nthr - 1) / nthr), nthr, 0, G.stream>>>(L.d_mirror, srcdev, L.d_slot_igrid, L.nslot, L.gmin, gspan,
+                                                                                  (int)nplanes_(), owned_only ? 1 : 0, L.g);
+  CUDA_OK(cudaGetLastError());
+  L.launches++;
+  for (int iv = 0; iv < G.p.nvar; iv++)
+    for (int ind = 0; ind < T; ind++) {
+      double* dst = host + (size_t)iv * ncell + G.ncoarse + (size_t)ind * G.ngridmax + (L.gmin - 1);
+      CUDA_OK(cudaMemcpyAsync(dst, L.d_mirror + ((size_t)iv * T + ind) * gspan, sizeof(double) * gspan, cudaMemcpyDeviceToHost, G.stream));
+    }
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  return RGPU_OK;
+}
+
+int rgpu_upload_state(int ilevel, const double* uold) {
+  Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
+  if (!uold) return fail(RGPU_EINVAL, "null uold");
+  rc = upload_into(*L, uold, L->d_u[L->cur]); if (rc) return rc;
+  L->unew_valid = false;
+  return RGPU_OK;
+}
+int rgpu_download_state(int ilevel, double* uold) {
+  Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
+  if (!uold) return fail(RGPU_EINVAL, "null uold");
+  return download_from(*L, uold, L->d_u[L->cur], false);
+}
+
+int rgpu_set_unew(int ilevel) {
+  Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
+  const size_t n = nplanes_() * (size_t)L->nslot;
+  copy_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, G.stream>>>(L->d_u[L->cur], L->d_u[1 - L->cur], n);
+  CUDA_OK(cudaGetLastError());
+  L->launches++;
+  for (auto& P : L->peers)
+    if (P.nrecv) {   // unew = 0 in the reception octs (godunov_fine.f90:93-100)
+      zero_octs_kernel<<<(P.nrecv + 127) / 128, 128, 0, G.stream>>>(L->d_u[1 - L->cur], P.d_recv, P.nrecv, L->nslot, (int)nplanes_());
+      CUDA_OK(cudaGetLastError());
+      L->launches++;
+    }
+  L->unew_valid = true;
+  return RGPU_OK;
+}
+
+int rgpu_godunov_fine_dev(int ilevel, double dt) {
+  Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
+  if (!(dt > 0)) return fail(RGPU_EINVAL, "dt=%g", dt);
+  CUDA_OK(cudaMemcpyAsync(L->d_dt, &dt, sizeof(double), cudaMemcpyHostToDevice, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  // the fused kernel evaluates unew = uold + dF for the owned cells (== set_unew followed by the flux update)
+  rc = launch_sweep(*L); if (rc) return rc;
+  L->unew_valid = true;
+  return RGPU_OK;
+}
+
+int rgpu_set_uold(int ilevel) {
+  Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
+  if (!L->unew_valid) return fail(RGPU_EINVAL, "set_uold before set_unew/godunov_fine");
+  // uold <- unew on the active cells (godunov_fine.f90:193-197); shells keep their uold values
+  rc = carry_shells(*L, L->d_u[L->cur], L->d_u[1 - L->cur]); if (rc) return rc;
+  L->cur = 1 - L->cur;
+  L->unew_valid = false;
+  return RGPU_OK;
+}
+
+int rgpu_courant_fine(int ilevel, double* dt_io, double sums[3]) {
+  Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
+  if (!dt_io) return fail(RGPU_EINVAL, "null dt");
+  rc = launch_courant(*L, *dt_io, nullptr); if (rc) return rc;
+  double out[4];
+  CUDA_OK(cudaMemcpyAsync(out, L->d_out, sizeof(out), cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  if (G.comm && G.nranks > 1) {
+    // MPI_ALLREDUCE SUM(3) + MIN(1) of courant_fine.f90:138-141, carried by NCCL
+    double* d = L->d_out;
+    NCCL_OK(ncclAllReduce(d, d, 1, ncclDouble, ncclMin, G.comm, G.stream));
+    NCCL_OK(ncclAllReduce(d + 1, d + 1, 3, ncclDouble, ncclSum, G.comm, G.stream));
+    CUDA_OK(cudaMemcpyAsync(out, L->d_out, sizeof(out), cudaMemcpyDeviceToHost, G.stream));
+    CUDA_OK(cudaStreamSynchronize(G.stream));
+  }
+  *dt_io = std::min(*dt_io, out[0]);
+  if (sums) { sums[0] += out[1]; sums[1] += out[2]; sums[2] += out[3]; }
+  return RGPU_OK;
+}
+
+int rgpu_make_boundary_hydro(int ilevel) {
+  Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
+  return launch_boundaries(*L, L->d_u[L->cur]);
+}
+
+int rgpu_make_virtual_fine(int ilevel) {
+  Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
+  return exchange_ghosts(*L, L->d_u[L->cur], false);
+}
+int rgpu_make_virtual_reverse(int ilevel) {
+  Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
+  if (!L->unew_valid) return fail(RGPU_EINVAL, "make_virtual_reverse before godunov_fine");
+  return exchange_ghosts(*L, L->d_u[1 - L->cur], true);
+}
+
+int rgpu_godunov_fine(int ilevel, double dt, const double* uold, double* unew) {
+  Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
+  if (!uold || !unew) return fail(RGPU_EINVAL, "null state array");
+  if (!(dt > 0)) return fail(RGPU_EINVAL, "dt=%g", dt);
+  CUDA_OK(cudaMemcpyAsync(L->d_dt, &dt, sizeof(double), cudaMemcpyHostToDevice, G.stream));
+  rc = upload_into(*L, uold, L->d_u[L->cur]); if (rc) return rc;
+  rc = launch_sweep(*L); if (rc) return rc;
+  L->unew_valid = true;
+  return download_from(*L, unew, L->d_u[1 - L->cur], true);
+}
+
+int rgpu_level_steps(int ilevel, int nstep, double* dt_hist, double sums_last[3]) {
+  Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
+  if (nstep < 1) return fail(RGPU_EINVAL, "nstep=%d", nstep);
+  if (L->hist_cap < nstep + 1) {
+    cudaFree(L->d_hist);
+    CUDA_OK(cudaMalloc(&L->d_hist, sizeof(double) * (nstep + 1)));
+    L->hist_cap = nstep + 1;
+  }
+  const double dt_cap = G.p.boxlen / G.p.smallc;   // pm/newdt_fine.f90:47-51
+  CUDA_OK(cudaEventRecord(G.ev2, G.stream));
+  // amr_step order.  Ghost shells of uold are current on entry (upload / previous step).
+  rc = exchange_ghosts(*L, L->d_u[L->cur], false); if (rc) return rc;
+  rc = launch_boundaries(*L, L->d_u[L->cur]); if (rc) return rc;
+  rc = launch_courant(*L, dt_cap, L->d_hist); if (rc) return rc;                    // courant_fine  amr_step.f90:326
+  for (int s = 0; s < nstep; s++) {
+    if (G.comm && G.nranks > 1) {
+      NCCL_OK(ncclAllReduce(L->d_dt, L->d_dt, 1, ncclDouble, ncclMin, G.comm, G.stream));
+      if (s < nstep) CUDA_OK(cudaMemcpyAsync(L->d_hist + s, L->d_dt, sizeof(double), cudaMemcpyDeviceToDevice, G.stream));
+    }
+    rc = launch_sweep(*L); if (rc) return rc;                                        // set_unew + godunov_fine + set_uold  :333,:388,:423
+    rc = launch_reduce(*L, L->nblocks, dt_cap, L->d_hist + s + 1); if (rc) return rc;  // courant_fine of the next step
+    rc = carry_shells(*L, L->d_u[L->cur], L->d_u[1 - L->cur]); if (rc) return rc;
+    L->cur = 1 - L->cur;
+    rc = exchange_ghosts(*L, L->d_u[L->cur], false); if (rc) return rc;             // make_virtual_fine :505
+    rc = launch_boundaries(*L, L->d_u[L->cur]); if (rc) return rc;                  // make_boundary_hydro :514
+  }
+  L->unew_valid = false;
+  CUDA_OK(cudaEventRecord(G.ev3, G.stream));
+  if (dt_hist) CUDA_OK(cudaMemcpyAsync(dt_hist, L->d_hist, sizeof(double) * nstep, cudaMemcpyDeviceToHost, G.stream));
+  double out[4];
+  CUDA_OK(cudaMemcpyAsync(out, L->d_out, sizeof(out), cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  if (sums_last) { sums_last[0] = out[1]; sums_last[1] = out[2]; sums_last[2] = out[3]; }
+  { float ms = 0; cudaEventElapsedTime(&ms, G.ev2, G.ev3); L->last_steps_ms = ms; }
+  return RGPU_OK;
+}
+
+int rgpu_comm_unique_id(void* unique_id_128) {
+  if (!unique_id_128) return fail(RGPU_EINVAL, "null id");
+  ncclUniqueId id;
+  NCCL_OK(ncclGetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(unique_id_128, &id, 128);
+  return RGPU_OK;
+}
+int rgpu_comm_init(int nranks, int rank, const void* unique_id_128) {
+  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  if (G.comm) { ncclCommDestroy(G.comm); G.comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, unique_id_128, 128);
+  NCCL_OK(ncclCommInitRank(&G.comm, nranks, id, rank));
+  G.nranks = nranks; G.rank = rank;
+  return RGPU_OK;
+}
+
+int rgpu_get_level_info(int ilevel, rgpu_level_info* o) {
+  if (!G.init || ilevel < 1 || ilevel > MAXLEVEL || !G.lev[ilevel].bound || !o) return fail(RGPU_EINVAL, "level %d not bound", ilevel);
+  Level& L = G.lev[ilevel];
+  o->dense = L.dense;
+  o->ncell_box[0] = L.g.ncx; o->ncell_box[1] = L.g.ncy; o->ncell_box[2] = L.g.ncz;
+  o->own_lo[0] = L.g.ox0; o->own_lo[1] = L.g.oy0; o->own_lo[2] = L.g.oz0;
+  o->own_hi[0] = L.g.ox1; o->own_hi[1] = L.g.oy1; o->own_hi[2] = L.g.oz1;
+  o->wrap[0] = L.g.wrapx; o->wrap[1] = L.g.wrapy; o->wrap[2] = L.g.wrapz;
+  o->nslot = L.nslot; o->kernel_launches = L.launches; o->last_sweep_ms = L.last_sweep_ms; o->last_steps_ms = L.last_steps_ms;
+  return RGPU_OK;
+}
+int rgpu_set_timing(int enable) { G.timing = enable != 0; return RGPU_OK; }
+int rgpu_device_synchronize(void) {
+  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  return RGPU_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// make_virtual_fine_dp / make_virtual_reverse_dp (amr/virtual_boundaries.f90:373,693) for ALL variables at once:
+// one packed message per peer inside a single NCCL group (ncclSend/ncclRecv over NVLink) instead of nvar
+// MPI_ISEND/IRECV rounds.  forward: emission octs -> peer's reception octs (copy); reverse: reception octs ->
+// owner's emission octs (accumulate, in peer order like :852-863).
+int exchange_ghosts(Level& L, double* u, bool reverse) {
+  if (L.peers.empty()) return RGPU_OK;
+  if (!G.comm) return fail(RGPU_EINVAL, "ghost exchange needs rgpu_comm_init");
+  const long long np = (long long)nplanes_();
+  for (auto& P : L.peers) {
+    const int n = reverse ? P.nrecv : P.nemit;
+    const int* sl = reverse ? P.d_recv : P.d_emit;
+    double* buf = reverse ? P.d_rbuf : P.d_sbuf;
+    if (n) {
+      pack_kernel<<<(unsigned)(((long long)n * np + 255) / 256), 256, 0, G.stream>>>(u, sl, n, L.nslot, (int)np, buf);
+      CUDA_OK(cudaGetLastError());
+      L.launches++;
+    }
+  }
+  NCCL_OK(ncclGroupStart());
+  for (int c = 0; c < (int)L.peers.size(); c++) {
+    PeerList& P = L.peers[c];
+    const int nsend = reverse ? P.nrecv : P.nemit, nrecv = reverse ? P.nemit : P.nrecv;
+    double* sb = reverse ? P.d_rbuf : P.d_sbuf;
+    double* rb = reverse ? P.d_sbuf : P.d_rbuf;
+    if (nsend) NCCL_OK(ncclSend(sb, (size_t)nsend * np, ncclDouble, c, G.comm, G.stream));
+    if (nrecv) NCCL_OK(ncclRecv(rb, (size_t)nrecv * np, ncclDouble, c, G.comm, G.stream));
+  }
+  NCCL_OK(ncclGroupEnd());
+  for (auto& P : L.peers) {
+    const int n = reverse ? P.nemit : P.nrecv;
+    const int* sl = reverse ? P.d_emit : P.d_recv;
+    const double* buf = reverse ? P.d_sbuf : P.d_rbuf;
+    if (n) {
+      unpack_kernel<<<(unsigned)(((long long)n * np + 255) / 256), 256, 0, G.stream>>>(u, sl, n, L.nslot, (int)np, buf, reverse ? 1 : 0);
+      CUDA_OK(cudaGetLastError());
+      L.launches++;
+    }
+  }
+  return RGPU_OK;
+}
+}  // namespace

@@ -1,0 +1,199 @@
+"""Host-side mirror of the reference's driver interface for the hydro sweep.
+
+The reference keeps all state in module globals (amr_commons, hydro_commons,
+hydro_parameters) and its routines take only `ilevel`:
+
+    call courant_fine(ilevel)   ! hydro/courant_fine.f90:1
+    call set_unew(ilevel)       ! hydro/godunov_fine.f90:40
+    call godunov_fine(ilevel)   ! hydro/godunov_fine.f90:5
+    call set_uold(ilevel)       ! hydro/godunov_fine.f90:135
+    call make_boundary_hydro(ilevel)  ! hydro/hydro_boundary.f90:5
+
+`AmrCommons` plays the role of those modules (same array names, shapes and 1-based
+index conventions, stored as Fortran-ordered numpy arrays) and `HydroGPU` exposes the
+routines under the same names, forwarding to the C-ABI (include/ramses_gpu.h).
+"""
+import ctypes as C
+import numpy as np
+from . import lib as _lib
+
+
+class AmrCommons:
+    """amr_commons + hydro_commons + hydro_parameters of one rank (amr/amr_commons.f90, hydro/hydro_commons.f90).
+
+    son(1:ncell), father(1:ngridmax), nbor(1:ngridmax,1:twondim) are int32 numpy arrays holding the Fortran
+    arrays element for element (index i of Fortran = index i-1 here); uold/unew(1:ncell,1:nvar) are float64
+    arrays of shape (nvar, ncell) (= column-major (ncell,nvar)).  active[l] / boundary[b][l] / reception[c][l] /
+    emission[c][l] are the %igrid lists (1-based oct indices).
+    """
+
+    def __init__(self, ndim, nvar, ncoarse, ngridmax, nx, ny, nz, icoarse=(0, 0), jcoarse=(0, 0), kcoarse=(0, 0),
+                 nlevelmax=1, boxlen=1.0, myid=1, ncpu=1):
+        self.ndim, self.nvar = ndim, nvar
+        self.ncoarse, self.ngridmax = ncoarse, ngridmax
+        self.twotondim, self.twondim = 1 << ndim, 2 * ndim
+        self.ncell = ncoarse + self.twotondim * ngridmax
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.icoarse_min, self.icoarse_max = icoarse
+        self.jcoarse_min, self.jcoarse_max = jcoarse
+        self.kcoarse_min, self.kcoarse_max = kcoarse
+        self.nlevelmax, self.boxlen = nlevelmax, boxlen
+        self.myid, self.ncpu = myid, ncpu
+        self.son = np.zeros(self.ncell, dtype=np.int32)
+        self.father = np.zeros(ngridmax, dtype=np.int32)
+        self.nbor = np.zeros((self.twondim, ngridmax), dtype=np.int32)   # Fortran nbor(1:ngridmax,1:twondim)
+        self.uold = np.zeros((nvar, self.ncell), dtype=np.float64)
+        self.unew = np.zeros((nvar, self.ncell), dtype=np.float64)
+        self.active = {}       # ilevel -> int32 array of igrid
+        self.boundary = {}     # ilevel -> list of int32 arrays, one per ibound
+        self.boundary_type = []
+        self.reception = {}    # ilevel -> list (per cpu) of int32 arrays
+        self.emission = {}
+        self.dtnew = {}
+        # hydro_parameters defaults (hydro/hydro_parameters.f90:75-85)
+        self.gamma, self.courant_factor = 1.4, 0.5
+        self.smallr, self.smallc = 1e-10, 1e-10
+        self.slope_type, self.slope_theta = 1, 1.5
+        self.niter_riemann, self.difmag = 10, 0.0
+        self.scheme, self.riemann = "muscl", "llf"
+        self.nvector = 32
+        self.pressure_fix = False
+        self.mass_tot = self.ekin_tot = self.eint_tot = 0.0
+
+    def dx(self, ilevel):
+        nx_loc = self.icoarse_max - self.icoarse_min + 1
+        return 0.5 ** ilevel * self.boxlen / nx_loc
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class HydroGPU:
+    """The patched routines of hydro/godunov_fine.f90 & friends, running on the GPU through the C-ABI."""
+
+    def __init__(self, amr: AmrCommons, device=-1):
+        self.a = amr
+        self.L = _lib.load()
+        p = _lib.Params()
+        p.ndim, p.nvar, p.nvector = amr.ndim, amr.nvar, amr.nvector
+        p.slope_type, p.niter_riemann = amr.slope_type, amr.niter_riemann
+        if amr.scheme not in ("muscl", "plmde"):
+            raise ValueError("unknown scheme")
+        p.scheme = 0 if amr.scheme == "muscl" else 1
+        if amr.riemann not in _lib.RIEMANN:
+            raise ValueError("unknown Riemann solver")          # hydro/umuscl.f90:801-803
+        p.riemann = _lib.RIEMANN[amr.riemann]
+        p.pressure_fix = int(bool(amr.pressure_fix))
+        p.gamma, p.smallr, p.smallc = amr.gamma, amr.smallr, amr.smallc
+        p.slope_theta, p.difmag, p.courant_factor, p.boxlen = amr.slope_theta, amr.difmag, amr.courant_factor, amr.boxlen
+        p.nx, p.ny, p.nz = amr.nx, amr.ny, amr.nz
+        p.icoarse_min, p.icoarse_max = amr.icoarse_min, amr.icoarse_max
+        p.jcoarse_min, p.jcoarse_max = amr.jcoarse_min, amr.jcoarse_max
+        p.kcoarse_min, p.kcoarse_max = amr.kcoarse_min, amr.kcoarse_max
+        p.nlevelmax = amr.nlevelmax
+        self.params = p
+        _lib.check(self.L.rgpu_init(C.byref(p), amr.myid, amr.ncpu, device))
+        self._keep = []
+        self.bind_tree()
+
+    # -- bookkeeping the Fortran shim performs after build_comm / refine ------------------------------
+    def bind_tree(self):
+        a = self.a
+        assert a.son.dtype == np.int32 and a.father.dtype == np.int32 and a.nbor.dtype == np.int32
+        assert a.nbor.flags["C_CONTIGUOUS"]
+        _lib.check(self.L.rgpu_bind_tree(a.ncoarse, a.ngridmax, _ip(a.son), _ip(a.father), _ip(a.nbor)))
+
+    def bind_level(self, ilevel):
+        a = self.a
+        act = np.ascontiguousarray(a.active[ilevel], dtype=np.int32)
+        bl = [np.ascontiguousarray(x, dtype=np.int32) for x in a.boundary.get(ilevel, [])]
+        nb = len(bl)
+        btype = (C.c_int * max(nb, 1))(*a.boundary_type[:nb])
+        nbnd = (C.c_int * max(nb, 1))(*[len(x) for x in bl])
+        bptr = (C.POINTER(C.c_int) * max(nb, 1))(*[_ip(x) for x in bl])
+        ncpu = a.ncpu
+        if ncpu > 1:
+            rl = [np.ascontiguousarray(x, dtype=np.int32) for x in a.reception[ilevel]]
+            el = [np.ascontiguousarray(x, dtype=np.int32) for x in a.emission[ilevel]]
+            nr = (C.c_int * ncpu)(*[len(x) for x in rl])
+            ne = (C.c_int * ncpu)(*[len(x) for x in el])
+            rp = (C.POINTER(C.c_int) * ncpu)(*[_ip(x) for x in rl])
+            ep = (C.POINTER(C.c_int) * ncpu)(*[_ip(x) for x in el])
+            self._keep.append((rl, el))
+        else:
+            nr = ne = rp = ep = None
+        self._keep.append((act, bl))
+        _lib.check(self.L.rgpu_bind_level(ilevel, len(act), _ip(act), ncpu, nr, rp, ne, ep, nb, btype, nbnd, bptr))
+
+    def level_info(self, ilevel):
+        info = _lib.LevelInfo()
+        _lib.check(self.L.rgpu_get_level_info(ilevel, C.byref(info)))
+        return info
+
+    # -- Level-0 contract: the drop-in godunov_fine(ilevel) on host arrays --------------------------------
+    def godunov_fine(self, ilevel):
+        """godunov_fine(ilevel): unew(active cells) = uold + flux differences, dt = dtnew(ilevel)."""
+        a = self.a
+        _lib.check(self.L.rgpu_godunov_fine(ilevel, float(a.dtnew[ilevel]), _dp(a.uold), _dp(a.unew)))
+
+    # -- Level-1 contract: device resident ----------------------------------------------------------------
+    def upload_state(self, ilevel):
+        _lib.check(self.L.rgpu_upload_state(ilevel, _dp(self.a.uold)))
+
+    def download_state(self, ilevel):
+        _lib.check(self.L.rgpu_download_state(ilevel, _dp(self.a.uold)))
+
+    def set_unew(self, ilevel):
+        _lib.check(self.L.rgpu_set_unew(ilevel))
+
+    def godunov_fine_dev(self, ilevel):
+        _lib.check(self.L.rgpu_godunov_fine_dev(ilevel, float(self.a.dtnew[ilevel])))
+
+    def set_uold(self, ilevel):
+        _lib.check(self.L.rgpu_set_uold(ilevel))
+
+    def courant_fine(self, ilevel):
+        """courant_fine(ilevel): dtnew(ilevel) = min(dtnew(ilevel), CFL dt); mass_tot etc. accumulated."""
+        a = self.a
+        dt = C.c_double(a.dtnew[ilevel])
+        sums = (C.c_double * 3)(0.0, 0.0, 0.0)
+        _lib.check(self.L.rgpu_courant_fine(ilevel, C.byref(dt), sums))
+        a.dtnew[ilevel] = dt.value
+        a.mass_tot += sums[0]; a.ekin_tot += sums[1]; a.eint_tot += sums[2]
+        return dt.value
+
+    def make_boundary_hydro(self, ilevel):
+        _lib.check(self.L.rgpu_make_boundary_hydro(ilevel))
+
+    def make_virtual_fine(self, ilevel):
+        _lib.check(self.L.rgpu_make_virtual_fine(ilevel))
+
+    def make_virtual_reverse(self, ilevel):
+        _lib.check(self.L.rgpu_make_virtual_reverse(ilevel))
+
+    def level_steps(self, ilevel, nstep):
+        """nstep fused level steps (courant -> set_unew -> godunov_fine -> set_uold -> ghosts -> boundaries)."""
+        dts = np.zeros(nstep)
+        sums = (C.c_double * 3)()
+        _lib.check(self.L.rgpu_level_steps(ilevel, nstep, _dp(dts), sums))
+        return dts, list(sums)
+
+    def host_register(self, arr):
+        _lib.check(self.L.rgpu_host_register(arr.ctypes.data, arr.nbytes))
+
+    def host_unregister(self, arr):
+        _lib.check(self.L.rgpu_host_unregister(arr.ctypes.data))
+
+    def set_timing(self, on):
+        _lib.check(self.L.rgpu_set_timing(int(on)))
+
+    def synchronize(self):
+        _lib.check(self.L.rgpu_device_synchronize())
+
+    def finalize(self):
+        _lib.check(self.L.rgpu_finalize())
