@@ -137,6 +137,9 @@ typedef struct rgpu_level_info {
   double last_steps_ms;      /* CUDA-event duration of the last rgpu_level_steps call, on the launching stream */
 } rgpu_level_info;
 int rgpu_get_level_info(int ilevel, rgpu_level_info* out);
+/* bitwise check of the shared-reciprocal division (hydro_device.cuh div_rn) against the IEEE `/` on npairs
+ * pseudo-random and adversarial operand pairs; *mismatches must come back 0                                  */
+int rgpu_selftest_div(long long npairs, unsigned long long seed, long long* mismatches);
 /* time the next sweeps with CUDA events on the launching stream (bench)            */
 int rgpu_set_timing(int enable);
 int rgpu_device_synchronize(void);

@@ -82,7 +82,8 @@ struct Level {
   bool unew_valid = false;
   std::vector<BoundRegion> regions;
   std::vector<PeerList> peers;
-  int ntx = 0, nty = 0, ntz = 0, zseg = 0, nblocks = 0;
+  int ntx = 0, nty = 0, nblocks = 0;
+  long long nwork = 0;
   double* d_part = nullptr;          // [4][nblocks_max]
   int part_cap = 0;
   double* d_dt = nullptr;            // [1] dt used by the next sweep
@@ -201,12 +202,10 @@ __global__ void courant_kernel(const double* __restrict__ u, DenseGeom g, Phys P
     double uu[NV];
 #pragma unroll
     for (int n = 0; n < NV; n++) uu[n] = u[(size_t)n * T * g.nslot + off];
-    const double dtc = cmpdt_cell<NDIM>(uu, dx, P);
+    double ei;
+    const double dtc = cmpdt_cell<NDIM>(uu, dx, P, ei);
     my_dt = dtc < my_dt ? dtc : my_dt;
     m0 += uu[0]; m1 += uu[NDIM + 1];
-    double ei = uu[NDIM + 1];
-#pragma unroll
-    for (int d = 0; d < NDIM; d++) ei = ei - 0.5 * (uu[d + 1] * uu[d + 1]) / fmx(uu[0], P.smallr);
     m2 += ei;
   }
   my_dt = warp_min(my_dt); m0 = warp_sum(m0); m1 = warp_sum(m1); m2 = warp_sum(m2);
@@ -265,6 +264,30 @@ __global__ void unpack_kernel(double* __restrict__ u, const int* __restrict__ sl
   const int o = (int)(i % n), pl = (int)(i / n);
   const size_t a = (size_t)pl * nslot + slots[o];
   if (accumulate) u[a] = u[a] + buf[i]; else u[a] = buf[i];
+}
+
+// self test of div_rn(a, b, rcp_rn(b)) == a / b (IEEE) on pseudo-random and adversarial operand pairs
+__device__ __forceinline__ unsigned long long xs64(unsigned long long& s) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
+__global__ void selftest_div_kernel(long long n_per_thread, unsigned long long seed, unsigned long long* mismatches) {
+  unsigned long long s = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+  unsigned long long bad = 0;
+  for (long long i = 0; i < n_per_thread; i++) {
+    const unsigned long long ra = xs64(s), rb = xs64(s), rc = xs64(s);
+    // significands: uniform, or adversarial (near 1, near 2, long runs of ones / zeros)
+    unsigned long long ma = ra & 0xFFFFFFFFFFFFFull, mb = rb & 0xFFFFFFFFFFFFFull;
+    const int mode = (int)(rc & 7);
+    if (mode == 1) { ma &= 0xFFull; mb |= 0xFFFFFFFFFFF00ull; }
+    else if (mode == 2) { ma |= 0xFFFFFFFFFFF00ull; mb &= 0xFFull; }
+    else if (mode == 3) { ma = (ma & 0x3ull) | (0xFFFFFFFFFFFFFull << (rc >> 8 & 31) & 0xFFFFFFFFFFFFFull); mb &= ~0ull << (rc >> 16 & 31); }
+    else if (mode == 4) { mb = 0xFFFFFFFFFFFFFull - (rb & 0xFull); }
+    const int ea = 1023 + (int)((rc >> 24) % 201) - 100, eb = 1023 + (int)((rc >> 40) % 201) - 100;
+    const double a = __longlong_as_double((long long)(((unsigned long long)ea << 52) | ma | ((rc >> 60 & 1ull) << 63)));
+    const double b = __longlong_as_double((long long)(((unsigned long long)eb << 52) | mb | ((rc >> 61 & 1ull) << 63)));
+    const double q1 = div_rn(a, b, rcp_rn(b));
+    const double q2 = a / b;
+    if (__double_as_longlong(q1) != __double_as_longlong(q2)) bad++;
+  }
+  if (bad) atomicAdd(mismatches, bad);
 }
 
 // ----------------------------------------------------------------------------- helpers
@@ -340,7 +363,7 @@ int launch_sweep(Level& L) {
   a.inv_dx = 1.0 / L.dx;
   int ex;
   a.dx_pow2 = (std::frexp(L.dx, &ex) == 0.5) ? 1 : 0;
-  a.ntx = L.ntx; a.nty = L.nty; a.ntz = L.ntz; a.zseg = L.zseg;
+  a.ntx = L.ntx; a.nty = L.nty; a.nwork = L.nwork;
   a.part = L.d_part;
   if (G.timing) cudaEventRecord(G.ev0, G.stream);
   cudaError_t e;
@@ -476,6 +499,9 @@ int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device) {
   P.gamma6 = (p->gamma + 1.0) / (2.0 * p->gamma);
   P.smallc2 = p->smallc * p->smallc;
   P.inv_gamma = 1.0 / p->gamma;
+  P.cfl_g = 0.0001;
+  P.cfl_rg = 1.0 / P.cfl_g;
+  P.cfl_k = std::sqrt(1.0 + 2.0 * p->courant_factor * P.cfl_g) - 1.0;
   P.slope_type = p->slope_type; P.niter_riemann = p->niter_riemann;
   G.init = true;
   return RGPU_OK;
@@ -633,21 +659,18 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
     }
   }
   // ---- tile decomposition of the owned range ----------------------------------------------------
-  const int bx = nd == 1 ? TileShape<1>::BX : nd == 2 ? TileShape<2>::BX : TileShape<3>::BX;
+  const int bx = 32;
   const int by = nd == 1 ? 1 : nd == 2 ? TileShape<2>::BY : TileShape<3>::BY;
   const int txo = bx - 2, tyo = nd > 1 ? by - 2 : 1;
   L.ntx = (g.ox1 - g.ox0 + txo - 1) / txo;
   L.nty = nd > 1 ? (g.oy1 - g.oy0 + tyo - 1) / tyo : 1;
-  if (nd > 2) {
-    // z segments: aim at >= 4 CTAs per SM-slot so that the tail of the last wave stays small
-    const int nzo = g.oz1 - g.oz0;
-    const long long cols = (long long)L.ntx * L.nty;
-    int nseg = (int)std::max<long long>(1, (148LL * 4 + cols - 1) / cols);
-    nseg = std::min(nseg, std::max(1, nzo / 8));
-    L.zseg = (nzo + nseg - 1) / nseg;
-    L.ntz = (nzo + L.zseg - 1) / L.zseg;
-  } else { L.zseg = 1; L.ntz = 1; }
-  L.nblocks = L.ntx * L.nty * L.ntz;
+  // persistent kernel: one CTA per SM, equal contiguous shares of the (column tile, z plane) space
+  L.nwork = (long long)L.ntx * L.nty * (nd > 2 ? (g.oz1 - g.oz0) : 1);
+  {
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, G.device);
+    L.nblocks = (int)std::min<long long>(nsm, L.nwork);
+  }
   L.part_cap = std::max(L.nblocks, 148 * 8);
   CUDA_OK(cudaMalloc(&L.d_part, sizeof(double) * 4 * L.part_cap));
   CUDA_OK(cudaMalloc(&L.d_dt, sizeof(double)));
@@ -871,6 +894,22 @@ int rgpu_get_level_info(int ilevel, rgpu_level_info* o) {
   o->own_hi[0] = L.g.ox1; o->own_hi[1] = L.g.oy1; o->own_hi[2] = L.g.oz1;
   o->wrap[0] = L.g.wrapx; o->wrap[1] = L.g.wrapy; o->wrap[2] = L.g.wrapz;
   o->nslot = L.nslot; o->kernel_launches = L.launches; o->last_sweep_ms = L.last_sweep_ms; o->last_steps_ms = L.last_steps_ms;
+  return RGPU_OK;
+}
+int rgpu_selftest_div(long long npairs, unsigned long long seed, long long* mismatches) {
+  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  unsigned long long* d;
+  CUDA_OK(cudaMalloc(&d, 8));
+  CUDA_OK(cudaMemset(d, 0, 8));
+  const int nb = 148 * 8, nt = 256;
+  const long long per = (npairs + (long long)nb * nt - 1) / ((long long)nb * nt);
+  selftest_div_kernel<<<nb, nt, 0, G.stream>>>(per, seed, d);
+  CUDA_OK(cudaGetLastError());
+  unsigned long long h = 0;
+  CUDA_OK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  cudaFree(d);
+  *mismatches = (long long)h;
   return RGPU_OK;
 }
 int rgpu_set_timing(int enable) { G.timing = enable != 0; return RGPU_OK; }

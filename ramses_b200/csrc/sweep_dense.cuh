@@ -1,17 +1,30 @@
-// sweep_dense.cuh -- fused per-level Godunov sweep over a dense box of octs.
+// sweep_dense.cuh -- fused per-level Godunov sweep over a dense box of octs (sm_100a).
 //
-// One kernel = set_unew + godunov_fine (ctoprim -> uslope -> trace -> cmpflxm/
-// riemann -> conservative update) + set_uold + the Courant scan of the NEW
-// state, for a level whose octs fill a Cartesian box (levelmin=levelmax runs,
-// and the owned sub-box + ghost shell of one rank in multi-GPU runs).
+// One persistent kernel = set_unew + godunov_fine (ctoprim -> uslope -> trace ->
+// cmpflxm/riemann -> conservative update) + set_uold + the Courant scan of the NEW
+// state, for a level whose octs fill a Cartesian box (levelmin=levelmax runs, and the
+// owned sub-box + ghost shell of one rank in multi-GPU runs).
 //
 // Reference semantics: hydro/godunov_fine.f90:5-35,486-911 (godfine1),
-// hydro/umuscl.f90:22-171 (unsplit).  The reference gathers a private 6^ndim
-// patch per oct (ctoprim 27x, slopes/trace 8x, Riemann 1.5x per cell); here a
-// CTA owns a (BX-2)x(BY-2) column of cells and marches along z, so every
-// primitive state, slope, traced state and face flux is evaluated once (plus a
-// one-cell halo ring) -- bit-identical because each value is a deterministic
-// function of the same inputs evaluated in the same operation order.
+// hydro/umuscl.f90:22-171 (unsplit).  The reference gathers a private 6^ndim patch
+// per oct (ctoprim 27x, slopes/trace 8x, Riemann 1.5x per cell); here a CTA owns a
+// (BX-2)x(BY-2) column of cells and marches along z, so every primitive state, slope,
+// traced state and face flux is evaluated once (plus a one-cell halo ring) --
+// bit-identical because each value is a deterministic function of the same inputs
+// evaluated in the same operation order.
+//
+// Execution model:
+//  * grid = one CTA per SM; the (column tile, z plane) space is cut into equal
+//    contiguous shares, so every SM does the same work (no wave tail);
+//  * a warp is one row of 32 cells along x: x-neighbour exchange (left face state,
+//    right face flux) by warp shuffles; y exchange through shared memory; the z
+//    exchange is a carry from the previous plane;
+//  * the raw conserved state of plane k+2 is staged into shared memory with cp.async
+//    while plane k is computed; ctoprim runs from the staging buffer into a 3-plane
+//    ring of primitive variables (+1/rho);
+//  * divisions that share a divisor use one correctly rounded reciprocal and a
+//    3-instruction FMA correction per quotient (div_rn below) -- same bits as IEEE
+//    division at a fraction of the FP64 issue slots.
 //
 // Data layout in HBM (the oct-tree layout, octs renumbered in lattice order):
 //   u[(ivar*2^ndim + ind)*nslot + slot],  ind = ix+2*iy+4*iz cell-in-oct,
@@ -37,12 +50,13 @@ struct SweepArgs {
   const double* dt_dev;       // time step, device resident (written by the Courant reduce)
   double dx, inv_dx;
   int dx_pow2;                // dx is a power of two: x/dx == x*inv_dx exactly
-  int ntx, nty, ntz, zseg;    // tile decomposition of the owned range
-  double* part;               // per-CTA partials [4][nblocks]: min dt, mass, etot, eint of the new state
+  int ntx, nty;               // column tiles of the owned range
+  long long nwork;            // ntx*nty*(owned planes): plane-tiles to distribute
+  double* part;               // per-CTA partials [4][gridDim.x]: min dt, mass, etot, eint of the new state
 };
 
 __device__ __forceinline__ int wrap_or_clamp(int c, int n, int wrap) {
-  if (wrap) { if (c < 0) c += n; else if (c >= n) c -= n; }
+  if (wrap) { c %= n; if (c < 0) c += n; }
   else { c = c < 0 ? 0 : (c >= n ? n - 1 : c); }
   return c;
 }
@@ -73,303 +87,378 @@ __device__ __forceinline__ double scale_flux(double f, double dt, double dx, dou
   return pow2 ? t * inv_dx : t / dx;
 }
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+template <int NDIM, int BX, int BY>
+struct SweepSmem {
+  static constexpr int NV = NDIM + 2;
+  static constexpr int HY = (NDIM > 1) ? 1 : 0;
+  static constexpr int HZ = (NDIM > 2) ? 1 : 0;
+  static constexpr int QX = BX + 2, QY = HY ? BY + 2 : 1;
+  static constexpr int NQ = NV + 1;                       // primitive variables + 1/rho
+  static constexpr int NRING = HZ ? 3 : 1;
+  static constexpr int NT = BX * BY;
+  static constexpr size_t ring = (size_t)NRING * NQ * QY * QX;
+  static constexpr size_t stage = HZ ? (size_t)NV * QY * QX : 0;
+  static constexpr size_t exq = HY ? (size_t)NV * NT : 0;  // qm_y
+  static constexpr size_t exf = HY ? (size_t)NV * NT : 0;  // Fy
+  static constexpr size_t carry = HZ ? (size_t)3 * NV * NT : 0;
+  static constexpr size_t doubles = ring + stage + exq + exf + carry;
+};
+
 template <int NDIM, int RIEMANN, int BX, int BY>
 __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs a) {
-  constexpr int NV = NDIM + 2;
-  constexpr int HY = (NDIM > 1) ? 1 : 0;
-  constexpr int HZ = (NDIM > 2) ? 1 : 0;
+  using S = SweepSmem<NDIM, BX, BY>;
+  constexpr int NV = S::NV, HY = S::HY, HZ = S::HZ, QX = S::QX, QY = S::QY, NQ = S::NQ, NT = S::NT;
   constexpr int TXO = BX - 2;                 // owned cells per tile in x
   constexpr int TYO = HY ? BY - 2 : 1;
-  constexpr int QX = BX + 2, QY = HY ? BY + 2 : 1;
-  constexpr int NRING = HZ ? 3 : 1;
   constexpr int TWOTONDIM = 1 << NDIM;
-  constexpr int NT = BX * BY;
+  constexpr int PL = QY * QX;                 // one variable of one q plane
+  static_assert(BX == 32, "a warp must be one x-row of the tile");
   extern __shared__ double smem[];
-  double* qring = smem;                                   // [NRING][NV][QY][QX]
-  double* exq = qring + NRING * NV * QY * QX;             // [1+HY][NV][BY][BX]  qm_x, qm_y
-  double* exf = exq + (1 + HY) * NV * BY * BX;            // [1+HY][NV][BY][BX]  Fx, Fy
+  double* qring = smem;                        // [NRING][NQ][QY][QX]
+  double* stage = qring + S::ring;             // [NV][QY][QX] raw conserved state of the next plane
+  double* exq = stage + S::stage;              // [NV][NT] qm_y
+  double* exf = exq + S::exq;                  // [NV][NT] Fy
+  double* carry = exf + S::exf;                // [3][NV][NT]: qm_z, Fz, partial update of the previous plane
   __shared__ double red[4][NT / 32];
 
   const DenseGeom& g = a.g;
   const Phys& P = a.P;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * BX + tx;
-  int b = blockIdx.x;
-  const int tix = b % a.ntx; b /= a.ntx;
-  const int tiy = b % a.nty; b /= a.nty;
-  const int tiz = b;
-  const int x0 = g.ox0 + tix * TXO;
-  const int y0 = HY ? g.oy0 + tiy * TYO : 0;
-  const int z0 = HZ ? g.oz0 + tiz * a.zseg : 0;
-  const int z1 = HZ ? min(z0 + a.zseg, g.oz1) : 1;
-  const int cx = x0 - 1 + tx;
-  const int cy = HY ? y0 - 1 + ty : 0;
   const double dt = *a.dt_dev;
-  const double dtdx = dt / a.dx;   // trace3d: dtdx = dt/dx (hydro/umuscl.f90:516)
-
-  const bool col_own = (tx >= 1) && (tx <= BX - 2) && (cx < g.ox1);
-  const bool row_own = HY ? ((ty >= 1) && (ty <= BY - 2) && (cy < g.oy1)) : true;
-  const bool own = col_own && row_own;
-  const bool need_tr = (cx <= g.ox1) && (HY ? (cy <= g.oy1) : true);
-  const bool need_fx = (tx >= 1) && row_own && (cx <= g.ox1);
-  const bool need_fy = HY && (ty >= 1) && col_own && (cy <= g.oy1);
-
-  const size_t vstride = (size_t)TWOTONDIM * g.nslot;   // stride between variables
-
-  // cooperative load of one plane of primitive variables (ctoprim fused into the load)
-  auto load_plane = [&](int z, int slot) {
-    const int zc = HZ ? wrap_or_clamp(z, g.ncz, g.wrapz) : 0;
-    double* qs = qring + slot * NV * QY * QX;
-    for (int i = tid; i < QX * QY; i += NT) {
-      const int qx = i % QX, qy = i / QX;
-      const int xc = wrap_or_clamp(x0 - 2 + qx, g.ncx, g.wrapx);
-      const int yc = HY ? wrap_or_clamp(y0 - 2 + qy, g.ncy, g.wrapy) : 0;
-      const long long off = cell_offset<NDIM>(g, xc, yc, zc);
-      double u[NV], q[NV];
-#pragma unroll
-      for (int n = 0; n < NV; n++) u[n] = __ldg(a.uin + n * vstride + off);
-      ctoprim<NDIM>(u, q, P);
-#pragma unroll
-      for (int n = 0; n < NV; n++) qs[(n * QY + qy) * QX + qx] = q[n];
-    }
-  };
+  const double dtdx = dt / a.dx;               // trace3d: dtdx = dt/dx (hydro/umuscl.f90:516)
+  const size_t vstride = (size_t)TWOTONDIM * g.nslot;
+  const int nzo = HZ ? g.oz1 - g.oz0 : 1;
 
   double my_dt = 1e300, my_mass = 0.0, my_etot = 0.0, my_eint = 0.0;
-  double qmz_prev[NV], fz_prev[NV], acc_prev[NV];
-#pragma unroll
-  for (int n = 0; n < NV; n++) { qmz_prev[n] = 0; fz_prev[n] = 0; acc_prev[n] = 0; }
 
-  if (HZ) { load_plane(z0 - 2, 0); load_plane(z0 - 1, 1); }
-  const int kbeg = HZ ? z0 - 1 : 0, kend = HZ ? z1 : 0;
-  for (int k = kbeg; k <= kend; k++) {
-    const int c = k - kbeg;
-    const int sm1 = HZ ? c % 3 : 0, s0_ = HZ ? (c + 1) % 3 : 0, sp1 = HZ ? (c + 2) % 3 : 0;
-    if (HZ) load_plane(k + 1, sp1); else load_plane(0, 0);
-    __syncthreads();
+  // equal contiguous shares of the (column tile, plane) space
+  long long w0 = a.nwork * blockIdx.x / gridDim.x;
+  const long long w1 = a.nwork * (blockIdx.x + 1) / gridDim.x;
+  while (w0 < w1) {
+    const long long col = w0 / nzo;
+    const int zs = (int)(w0 - col * nzo);
+    const int zn = (int)min((long long)(nzo - zs), w1 - w0);
+    w0 += zn;
+    const int tix = (int)(col % a.ntx), tiy = (int)(col / a.ntx);
+    const int x0 = g.ox0 + tix * TXO;
+    const int y0 = HY ? g.oy0 + tiy * TYO : 0;
+    const int z0 = HZ ? g.oz0 + zs : 0;
+    const int z1 = HZ ? z0 + zn : 1;
+    const int cx = x0 - 1 + tx;
+    const int cy = HY ? y0 - 1 + ty : 0;
 
-    const int qx = tx + 1, qy = HY ? ty + 1 : 0;
-    const double* qc = qring + s0_ * NV * QY * QX + qy * QX + qx;   // + n*QY*QX
-    double q[NV], dq[NDIM][NV], t0[NV];
-    const bool plane_flux = HZ ? (k >= z0 && k < z1) : true;        // x/y fluxes + update of this plane
-    if (need_tr) {
+    const bool col_own = (tx >= 1) && (tx <= BX - 2) && (cx < g.ox1);
+    const bool row_own = HY ? ((ty >= 1) && (ty <= BY - 2) && (cy < g.oy1)) : true;
+    const bool own = col_own && row_own;
+    const bool need_tr = (cx <= g.ox1) && (HY ? (cy <= g.oy1) : true);
+    const bool need_fx = (tx >= 1) && row_own && (cx <= g.ox1);
+    const bool need_fy = HY && (ty >= 1) && col_own && (cy <= g.oy1);
+
+    // (qx,qy) -> global offset of the plane-independent part; each thread owns cells i = tid, tid+NT, ...
+    auto cell_xy = [&](int i, int& xc, int& yc) {
+      const int qx = i % QX, qy = i / QX;
+      xc = wrap_or_clamp(x0 - 2 + qx, g.ncx, g.wrapx);
+      yc = HY ? wrap_or_clamp(y0 - 2 + qy, g.ncy, g.wrapy) : 0;
+    };
+    // ctoprim (hydro/umuscl.f90:861) of one cell into ring slot `slot`
+    auto to_ring = [&](const double* u, int slot, int i) {
+      double q[NV];
+      const double r = fmax(u[0], P.smallr);
+      const double oneoverrho = 1.0 / r;
+      q[0] = r;
+      double eken;
+      q[1] = u[1] * oneoverrho;
+      eken = 0.5 * q[1] * q[1];
+      if (NDIM > 1) { q[2] = u[2] * oneoverrho; eken = eken + 0.5 * q[2] * q[2]; }
+      if (NDIM > 2) { q[3] = u[3] * oneoverrho; eken = eken + 0.5 * q[3] * q[3]; }
+      const double eint = fmax(u[NDIM + 1] * oneoverrho - eken - 0.0, P.smalle);
+      q[NDIM + 1] = (P.gamma - 1.0) * r * eint;
+      q[1] = q[1] + 0.0;                       // gravity predictor with gloc = 0 (:932-938): -0 -> +0
+      if (NDIM > 1) q[2] = q[2] + 0.0;
+      if (NDIM > 2) q[3] = q[3] + 0.0;
+      double* qs = qring + (size_t)slot * NQ * PL + i;
 #pragma unroll
-      for (int n = 0; n < NV; n++) q[n] = qc[n * QY * QX];
-      // ---- uslope (hydro/umuscl.f90:970) ----
-      if (P.slope_type == 3 && NDIM > 1) {
-        // positivity preserving unsplit slope :1101-1144 (2-D), :1328-1391 (3-D)
+      for (int n = 0; n < NV; n++) qs[n * PL] = q[n];
+      qs[NV * PL] = oneoverrho;
+    };
+    auto load_plane_direct = [&](int z, int slot) {
+      const int zc = HZ ? wrap_or_clamp(z, g.ncz, g.wrapz) : 0;
+      for (int i = tid; i < PL; i += NT) {
+        int xc, yc;
+        cell_xy(i, xc, yc);
+        const long long off = cell_offset<NDIM>(g, xc, yc, zc);
+        double u[NV];
 #pragma unroll
-        for (int n = 0; n < NV; n++) {
-          const double* qn = qc + n * QY * QX;
-          double vmin = 0, vmax = 0;
-          bool first = true;
-          for (int cc = (HZ ? -1 : 0); cc <= (HZ ? 1 : 0); cc++) {
-            const double* qz = qring + (HZ ? (cc < 0 ? sm1 : (cc > 0 ? sp1 : s0_)) : 0) * NV * QY * QX + n * QY * QX + qy * QX + qx;
-            for (int aa = -1; aa <= 1; aa++)
-              for (int bb = -1; bb <= 1; bb++) {
-                const double d = qz[bb * QX + aa] - q[n];
-                if (first) { vmin = d; vmax = d; first = false; }
-                else { vmin = fmn(vmin, d); vmax = fmx(vmax, d); }
-              }
+        for (int n = 0; n < NV; n++) u[n] = __ldg(a.uin + n * vstride + off);
+        to_ring(u, slot, i);
+      }
+    };
+    auto stage_plane_async = [&](int z) {     // raw u of plane z -> staging buffer (cp.async, no registers)
+      const int zc = wrap_or_clamp(z, g.ncz, g.wrapz);
+      for (int i = tid; i < PL; i += NT) {
+        int xc, yc;
+        cell_xy(i, xc, yc);
+        const long long off = cell_offset<NDIM>(g, xc, yc, zc);
+#pragma unroll
+        for (int n = 0; n < NV; n++) cp_async8(stage + n * PL + i, a.uin + n * vstride + off);
+      }
+    };
+    auto stage_to_ring = [&](int slot) {       // each thread converts the cells it staged itself
+      cp_async_wait_all();
+      for (int i = tid; i < PL; i += NT) {
+        double u[NV];
+#pragma unroll
+        for (int n = 0; n < NV; n++) u[n] = stage[n * PL + i];
+        to_ring(u, slot, i);
+      }
+    };
+
+    __syncthreads();                           // previous segment done with shared memory
+    if (HZ) {
+      load_plane_direct(z0 - 2, 0);
+      load_plane_direct(z0 - 1, 1);
+      stage_plane_async(z0);
+    }
+    const int kbeg = HZ ? z0 - 1 : 0, kend = HZ ? z1 : 0;
+    for (int k = kbeg; k <= kend; k++) {
+      const int c = k - kbeg;
+      const int sm1 = HZ ? c % 3 : 0, sc = HZ ? (c + 1) % 3 : 0, sp1 = HZ ? (c + 2) % 3 : 0;
+      if (HZ) stage_to_ring(sp1); else load_plane_direct(0, 0);
+      __syncthreads();
+      if (HZ && k < kend) stage_plane_async(k + 2);
+
+      const int qx = tx + 1, qy = HY ? ty + 1 : 0;
+      const double* qc = qring + (size_t)sc * NQ * PL + qy * QX + qx;   // + n*PL
+      double q[NV], dq[NDIM][NV], t0[NV];
+      const bool plane_flux = HZ ? (k >= z0 && k < z1) : true;          // x/y fluxes + update of this plane
+      double qmx[NV];                                                   // left state of the +x face (to lane+1)
+#pragma unroll
+      for (int n = 0; n < NV; n++) { qmx[n] = 0.0; q[n] = 1.0; t0[n] = 0.0; }
+      if (need_tr) {
+#pragma unroll
+        for (int n = 0; n < NV; n++) q[n] = qc[n * PL];
+        const double rinv = qc[NV * PL];
+        // ---- uslope (hydro/umuscl.f90:970) ----
+        if (P.slope_type == 3 && NDIM > 1) {
+          // positivity preserving unsplit slope :1101-1144 (2-D), :1328-1391 (3-D)
+#pragma unroll
+          for (int n = 0; n < NV; n++) {
+            const double* qn = qc + n * PL;
+            double vmin = 0, vmax = 0;
+            bool first = true;
+            for (int cc = (HZ ? -1 : 0); cc <= (HZ ? 1 : 0); cc++) {
+              const double* qz = qring + (size_t)(HZ ? (cc < 0 ? sm1 : (cc > 0 ? sp1 : sc)) : 0) * NQ * PL + n * PL + qy * QX + qx;
+              for (int aa = -1; aa <= 1; aa++)
+                for (int bb = -1; bb <= 1; bb++) {
+                  const double d = qz[bb * QX + aa] - q[n];
+                  if (first) { vmin = d; vmax = d; first = false; }
+                  else { vmin = fmn(vmin, d); vmax = fmx(vmax, d); }
+                }
+            }
+            const double dfx = 0.5 * (qn[1] - qn[-1]);
+            const double dfy = 0.5 * (qn[QX] - qn[-QX]);
+            double dfz = 0, dff;
+            if (HZ) {
+              dfz = 0.5 * (qring[(size_t)sp1 * NQ * PL + n * PL + qy * QX + qx] - qring[(size_t)sm1 * NQ * PL + n * PL + qy * QX + qx]);
+              dff = 0.5 * (fabs(dfx) + fabs(dfy) + fabs(dfz));
+            } else dff = 0.5 * (fabs(dfx) + fabs(dfy));
+            double slop;
+            if (dff > 0.0) slop = fmn(1.0, fmn(fabs(vmin), fabs(vmax)) / dff);
+            else slop = 1.0;
+            dq[0][n] = slop * dfx;
+            dq[HY][n] = slop * dfy;
+            if (HZ) dq[NDIM - 1][n] = slop * dfz;
           }
-          const double dfx = 0.5 * (qn[1] - qn[-1]);
-          const double dfy = 0.5 * (qn[QX] - qn[-QX]);
-          double dfz = 0, dff;
-          if (HZ) {
-            dfz = 0.5 * (qring[sp1 * NV * QY * QX + n * QY * QX + qy * QX + qx] - qring[sm1 * NV * QY * QX + n * QY * QX + qy * QX + qx]);
-            dff = 0.5 * (fabs(dfx) + fabs(dfy) + fabs(dfz));
-          } else dff = 0.5 * (fabs(dfx) + fabs(dfy));
-          double slop;
-          if (dff > 0.0) slop = fmn(1.0, fmn(fabs(vmin), fabs(vmax)) / dff);
-          else slop = 1.0;
-          dq[0][n] = slop * dfx;
-          dq[1][n] = slop * dfy;
-          if (HZ) dq[NDIM - 1][n] = slop * dfz;
-        }
-      } else if (NDIM == 1 && P.slope_type >= 4 && P.slope_type <= 6) {
-        // 1-D only limiters :1021-1068
-        const double uvel = q[1];
+        } else if (NDIM == 1 && P.slope_type >= 4 && P.slope_type <= 6) {
+          // 1-D only limiters :1021-1068
+          const double uvel = q[1];
 #pragma unroll
-        for (int n = 0; n < NV; n++) {
-          const double* qn = qc + n * QY * QX;
-          const double qL = qn[-1], qC = qn[0], qR = qn[1];
-          double r;
-          if (P.slope_type == 4) {
-            double dcen = uvel * dt / a.dx;
-            const double dlft = 2.0 / (1.0 + dcen) * (qC - qL);
-            const double drgt = 2.0 / (1.0 - dcen) * (qR - qC);
-            const double dsgn = fsign1(dlft);
-            double dlim = fmn(fabs(dlft), fabs(drgt));
-            if ((dlft * drgt) <= 0.0) dlim = 0.0;
-            r = dsgn * dlim;
-          } else if (P.slope_type == 5) {
-            if (n == 0) {
-              const double dcen = uvel * dt / a.dx;
-              double dlft, drgt;
-              if (dcen >= 0) { dlft = 2.0 / (0.0 + dcen + 1e-10) * (qC - qL); drgt = 2.0 / (1.0 - dcen) * (qR - qC); }
-              else { dlft = 2.0 / (1.0 + dcen) * (qC - qL); drgt = 2.0 / (0.0 - dcen + 1e-10) * (qR - qC); }
+          for (int n = 0; n < NV; n++) {
+            const double* qn = qc + n * PL;
+            const double qL = qn[-1], qC = qn[0], qR = qn[1];
+            double r;
+            if (P.slope_type == 4) {
+              double dcen = uvel * dt / a.dx;
+              const double dlft = 2.0 / (1.0 + dcen) * (qC - qL);
+              const double drgt = 2.0 / (1.0 - dcen) * (qR - qC);
               const double dsgn = fsign1(dlft);
               double dlim = fmn(fabs(dlft), fabs(drgt));
               if ((dlft * drgt) <= 0.0) dlim = 0.0;
               r = dsgn * dlim;
-            } else r = 0;
-          } else {
-            if (n == 0) { const double dlft = qC - qL, drgt = qR - qC; r = 0.5 * (dlft + drgt); }
-            else r = 0;
+            } else if (P.slope_type == 5) {
+              if (n == 0) {
+                const double dcen = uvel * dt / a.dx;
+                double dlft, drgt;
+                if (dcen >= 0) { dlft = 2.0 / (0.0 + dcen + 1e-10) * (qC - qL); drgt = 2.0 / (1.0 - dcen) * (qR - qC); }
+                else { dlft = 2.0 / (1.0 + dcen) * (qC - qL); drgt = 2.0 / (0.0 - dcen + 1e-10) * (qR - qC); }
+                const double dsgn = fsign1(dlft);
+                double dlim = fmn(fabs(dlft), fabs(drgt));
+                if ((dlft * drgt) <= 0.0) dlim = 0.0;
+                r = dsgn * dlim;
+              } else r = 0;
+            } else {
+              if (n == 0) { const double dlft = qC - qL, drgt = qR - qC; r = 0.5 * (dlft + drgt); }
+              else r = 0;
+            }
+            dq[0][n] = r;
           }
-          dq[0][n] = r;
+        } else {
+#pragma unroll
+          for (int n = 0; n < NV; n++) {
+            const double* qn = qc + n * PL;
+            dq[0][n] = slope_lcr<NDIM>(qn[-1], q[n], qn[1], P);
+            if (HY) dq[HY][n] = slope_lcr<NDIM>(qn[-QX], q[n], qn[QX], P);
+            if (HZ) {
+              const double qb = qring[(size_t)sm1 * NQ * PL + n * PL + qy * QX + qx];
+              const double qf = qring[(size_t)sp1 * NQ * PL + n * PL + qy * QX + qx];
+              dq[NDIM - 1][n] = slope_lcr<NDIM>(qb, q[n], qf, P);
+            }
+          }
         }
-      } else {
+        // ---- trace (hydro/umuscl.f90:176/305/483): t0 = s0*dtdx*half ----
+        double s0[NV];
+        trace_sources<NDIM>(q, dq, rinv, s0, P);
+#pragma unroll
+        for (int n = 0; n < NV; n++) t0[n] = s0[n] * dtdx * 0.5;
 #pragma unroll
         for (int n = 0; n < NV; n++) {
-          const double* qn = qc + n * QY * QX;
-          dq[0][n] = slope_lcr<NDIM>(qn[-1], q[n], qn[1], P);
-          if (HY) dq[HY][n] = slope_lcr<NDIM>(qn[-QX], q[n], qn[QX], P);
-          if (HZ) {
-            const double qb = qring[sm1 * NV * QY * QX + n * QY * QX + qy * QX + qx];
-            const double qf = qring[sp1 * NV * QY * QX + n * QY * QX + qy * QX + qx];
-            dq[NDIM - 1][n] = slope_lcr<NDIM>(qb, q[n], qf, P);
-          }
-        }
-      }
-      // ---- trace (hydro/umuscl.f90:176/305/483): t0 = s0*dtdx*half ----
-      double s0[NV];
-      trace_sources<NDIM>(q, dq, s0, P);
-#pragma unroll
-      for (int n = 0; n < NV; n++) t0[n] = s0[n] * dtdx * 0.5;
-      // left states of the +x / +y faces go to shared memory
-      {
-        double qm;
-#pragma unroll
-        for (int n = 0; n < NV; n++) {
-          qm = q[n] + 0.5 * dq[0][n] + t0[n];
+          double qm = q[n] + 0.5 * dq[0][n] + t0[n];
           if (n == 0 && qm < P.smallr) qm = q[0];
-          exq[(n * BY + ty) * BX + tx] = qm;
+          qmx[n] = qm;
         }
         if (HY) {
 #pragma unroll
           for (int n = 0; n < NV; n++) {
-            qm = q[n] + 0.5 * dq[HY][n] + t0[n];
+            double qm = q[n] + 0.5 * dq[HY][n] + t0[n];
             if (n == 0 && qm < P.smallr) qm = q[0];
-            exq[((NV + n) * BY + ty) * BX + tx] = qm;
+            exq[n * NT + tid] = qm;
           }
         }
       }
-    }
-    __syncthreads();
+      // left state of my -x face comes from lane-1 (a warp is one x-row)
+      double qlx[NV];
+#pragma unroll
+      for (int n = 0; n < NV; n++) qlx[n] = __shfl_up_sync(0xffffffffu, qmx[n], 1);
+      __syncthreads();
 
-    double fx[NV], fy[NV], fz[NV];
-    // ---- X faces: cmpflxm(...,2,3,4) hydro/umuscl.f90:97 ----
-    if (need_fx && plane_flux) {
-      double ql[NV], qr[NV], fg[NV];
-      // cmpflxm order: (rho, u_n, P, u_t1, u_t2)
-      ql[0] = exq[(0 * BY + ty) * BX + tx - 1];
-      ql[1] = exq[(1 * BY + ty) * BX + tx - 1];
-      ql[2] = exq[((NDIM + 1) * BY + ty) * BX + tx - 1];
-      if (NDIM > 1) ql[3] = exq[(2 * BY + ty) * BX + tx - 1];
-      if (NDIM > 2) ql[4] = exq[(3 * BY + ty) * BX + tx - 1];
-      double qp[NV];
+      double fx[NV], fy[NV], fz[NV];
 #pragma unroll
-      for (int n = 0; n < NV; n++) qp[n] = q[n] - 0.5 * dq[0][n] + t0[n];
-      if (qp[0] < P.smallr) qp[0] = q[0];
-      qr[0] = qp[0]; qr[1] = qp[1]; qr[2] = qp[NDIM + 1];
-      if (NDIM > 1) qr[3] = qp[2];
-      if (NDIM > 2) qr[4] = qp[3];
-      riemann<NDIM, RIEMANN>(ql, qr, fg, P);
-      fx[0] = fg[0]; fx[1] = fg[1]; fx[NDIM + 1] = fg[2];
-      if (NDIM > 1) fx[2] = fg[3];
-      if (NDIM > 2) fx[3] = fg[4];
+      for (int n = 0; n < NV; n++) { fx[n] = 0.0; fy[n] = 0.0; fz[n] = 0.0; }
+      // ---- X faces: cmpflxm(...,2,3,4) hydro/umuscl.f90:97 ----
+      if (need_fx && plane_flux) {
+        double ql[NV], qr[NV], fg[NV];
+        ql[0] = qlx[0]; ql[1] = qlx[1]; ql[2] = qlx[NDIM + 1];
+        if (NDIM > 1) ql[3] = qlx[2];
+        if (NDIM > 2) ql[4] = qlx[3];
+        double qp[NV];
 #pragma unroll
-      for (int n = 0; n < NV; n++) {
-        fx[n] = scale_flux(fx[n], dt, a.dx, a.inv_dx, a.dx_pow2);
-        exf[(n * BY + ty) * BX + tx] = fx[n];
+        for (int n = 0; n < NV; n++) qp[n] = q[n] - 0.5 * dq[0][n] + t0[n];
+        if (qp[0] < P.smallr) qp[0] = q[0];
+        qr[0] = qp[0]; qr[1] = qp[1]; qr[2] = qp[NDIM + 1];
+        if (NDIM > 1) qr[3] = qp[2];
+        if (NDIM > 2) qr[4] = qp[3];
+        riemann<NDIM, RIEMANN>(ql, qr, fg, P);
+        fx[0] = fg[0]; fx[1] = fg[1]; fx[NDIM + 1] = fg[2];
+        if (NDIM > 1) fx[2] = fg[3];
+        if (NDIM > 2) fx[3] = fg[4];
+#pragma unroll
+        for (int n = 0; n < NV; n++) fx[n] = scale_flux(fx[n], dt, a.dx, a.inv_dx, a.dx_pow2);
       }
-    }
-    // ---- Y faces: cmpflxm(...,3,2,4) hydro/umuscl.f90:120 ----
-    if (HY && need_fy && plane_flux) {
-      double ql[NV], qr[NV], fg[NV];
-      ql[0] = exq[((NV + 0) * BY + ty - 1) * BX + tx];
-      ql[1] = exq[((NV + 2) * BY + ty - 1) * BX + tx];
-      ql[2] = exq[((NV + NDIM + 1) * BY + ty - 1) * BX + tx];
-      ql[3] = exq[((NV + 1) * BY + ty - 1) * BX + tx];
-      if (NDIM > 2) ql[4] = exq[((NV + 3) * BY + ty - 1) * BX + tx];
-      double qp[NV];
+      // ---- Y faces: cmpflxm(...,3,2,4) hydro/umuscl.f90:120 ----
+      if (HY && need_fy && plane_flux) {
+        double ql[NV], qr[NV], fg[NV];
+        const double* e = exq + tid - BX;        // row ty-1
+        ql[0] = e[0 * NT]; ql[1] = e[2 * NT]; ql[2] = e[(NDIM + 1) * NT]; ql[3] = e[1 * NT];
+        if (NDIM > 2) ql[4] = e[3 * NT];
+        double qp[NV];
 #pragma unroll
-      for (int n = 0; n < NV; n++) qp[n] = q[n] - 0.5 * dq[HY][n] + t0[n];
-      if (qp[0] < P.smallr) qp[0] = q[0];
-      qr[0] = qp[0]; qr[1] = qp[2]; qr[2] = qp[NDIM + 1]; qr[3] = qp[1];
-      if (NDIM > 2) qr[4] = qp[3];
-      riemann<NDIM, RIEMANN>(ql, qr, fg, P);
-      fy[0] = fg[0]; fy[2] = fg[1]; fy[NDIM + 1] = fg[2]; fy[1] = fg[3];
-      if (NDIM > 2) fy[3] = fg[4];
-#pragma unroll
-      for (int n = 0; n < NV; n++) {
-        fy[n] = scale_flux(fy[n], dt, a.dx, a.inv_dx, a.dx_pow2);
-        exf[((NV + n) * BY + ty) * BX + tx] = fy[n];
-      }
-    }
-    // ---- Z faces: cmpflxm(...,4,2,3) hydro/umuscl.f90:144; left state carried in registers ----
-    if (HZ && own && k >= z0) {
-      double ql[NV], qr[NV], fg[NV];
-      ql[0] = qmz_prev[0]; ql[1] = qmz_prev[3]; ql[2] = qmz_prev[NDIM + 1]; ql[3] = qmz_prev[1]; ql[4 % NV] = qmz_prev[2];
-      double qp[NV];
-#pragma unroll
-      for (int n = 0; n < NV; n++) qp[n] = q[n] - 0.5 * dq[NDIM - 1][n] + t0[n];
-      if (qp[0] < P.smallr) qp[0] = q[0];
-      qr[0] = qp[0]; qr[1] = qp[3 % NV]; qr[2] = qp[NDIM + 1]; qr[3] = qp[1]; qr[4 % NV] = qp[2];
-      riemann<NDIM, RIEMANN>(ql, qr, fg, P);
-      fz[0] = fg[0]; fz[3 % NV] = fg[1]; fz[NDIM + 1] = fg[2]; fz[1] = fg[3]; fz[2] = fg[4 % NV];
-#pragma unroll
-      for (int n = 0; n < NV; n++) fz[n] = scale_flux(fz[n], dt, a.dx, a.inv_dx, a.dx_pow2);
-    }
-    if (HZ && own) {
-#pragma unroll
-      for (int n = 0; n < NV; n++) {
-        double qm = q[n] + 0.5 * dq[NDIM - 1][n] + t0[n];
-        if (n == 0 && qm < P.smallr) qm = q[0];
-        qmz_prev[n] = qm;
-      }
-    }
-    __syncthreads();
-
-    // ---- conservative update (godfine1, hydro/godunov_fine.f90:751-792): x, then y, then z ----
-    if (own) {
-      double unew_[NV];
-      bool have = false;
-      if (HZ) {
-        if (k > z0) {   // finish plane k-1 with the z fluxes
-#pragma unroll
-          for (int n = 0; n < NV; n++) unew_[n] = acc_prev[n] + (fz_prev[n] - fz[n]);
-          have = true;
-        }
-        if (k >= z0) {
-#pragma unroll
-          for (int n = 0; n < NV; n++) fz_prev[n] = fz[n];
-        }
-      }
-      if (plane_flux) {
-        const long long off = cell_offset<NDIM>(g, cx, cy, HZ ? k : 0);
+        for (int n = 0; n < NV; n++) qp[n] = q[n] - 0.5 * dq[HY][n] + t0[n];
+        if (qp[0] < P.smallr) qp[0] = q[0];
+        qr[0] = qp[0]; qr[1] = qp[2]; qr[2] = qp[NDIM + 1]; qr[3] = qp[1];
+        if (NDIM > 2) qr[4] = qp[3];
+        riemann<NDIM, RIEMANN>(ql, qr, fg, P);
+        fy[0] = fg[0]; fy[2] = fg[1]; fy[NDIM + 1] = fg[2]; fy[1] = fg[3];
+        if (NDIM > 2) fy[3] = fg[4];
 #pragma unroll
         for (int n = 0; n < NV; n++) {
-          double u = __ldg(a.uin + n * vstride + off);          // set_unew: unew = uold
-          u = u + (fx[n] - exf[(n * BY + ty) * BX + tx + 1]);
-          if (HY) u = u + (fy[n] - exf[((NV + n) * BY + ty + 1) * BX + tx]);
-          if (HZ) acc_prev[n] = u; else unew_[n] = u;
+          fy[n] = scale_flux(fy[n], dt, a.dx, a.inv_dx, a.dx_pow2);
+          exf[n * NT + tid] = fy[n];
         }
-        if (!HZ) have = true;
       }
-      if (have) {
-        const long long off = cell_offset<NDIM>(g, cx, cy, HZ ? k - 1 : 0);
+      // ---- Z faces: cmpflxm(...,4,2,3) hydro/umuscl.f90:144; left state carried from the previous plane ----
+      if (HZ && own && k >= z0) {
+        double ql[NV], qr[NV], fg[NV];
+        const double* cq = carry + tid;          // qm_z of plane k-1
+        ql[0] = cq[0 * NT]; ql[1] = cq[3 * NT]; ql[2] = cq[(NDIM + 1) * NT]; ql[3] = cq[1 * NT]; ql[4 % NV] = cq[2 * NT];
+        double qp[NV];
 #pragma unroll
-        for (int n = 0; n < NV; n++) a.uout[n * vstride + off] = unew_[n];   // set_uold: uold = unew
-        // fused courant_fine of the new state (hydro/courant_fine.f90:96-123)
-        const double dtc = cmpdt_cell<NDIM>(unew_, a.dx, P);
-        my_dt = dtc < my_dt ? dtc : my_dt;
-        my_mass += unew_[0];
-        my_etot += unew_[NDIM + 1];
-        double ei = unew_[NDIM + 1];
+        for (int n = 0; n < NV; n++) qp[n] = q[n] - 0.5 * dq[NDIM - 1][n] + t0[n];
+        if (qp[0] < P.smallr) qp[0] = q[0];
+        qr[0] = qp[0]; qr[1] = qp[3 % NV]; qr[2] = qp[NDIM + 1]; qr[3] = qp[1]; qr[4 % NV] = qp[2];
+        riemann<NDIM, RIEMANN>(ql, qr, fg, P);
+        fz[0] = fg[0]; fz[3 % NV] = fg[1]; fz[NDIM + 1] = fg[2]; fz[1] = fg[3]; fz[2] = fg[4 % NV];
 #pragma unroll
-        for (int d = 0; d < NDIM; d++) ei = ei - 0.5 * (unew_[d + 1] * unew_[d + 1]) / fmx(unew_[0], P.smallr);
-        my_eint += ei;
+        for (int n = 0; n < NV; n++) fz[n] = scale_flux(fz[n], dt, a.dx, a.inv_dx, a.dx_pow2);
+      }
+      if (HZ && own) {
+#pragma unroll
+        for (int n = 0; n < NV; n++) {
+          double qm = q[n] + 0.5 * dq[NDIM - 1][n] + t0[n];
+          if (n == 0 && qm < P.smallr) qm = q[0];
+          carry[n * NT + tid] = qm;
+        }
+      }
+      // flux through my +x face comes from lane+1
+      double fxr[NV];
+#pragma unroll
+      for (int n = 0; n < NV; n++) fxr[n] = __shfl_down_sync(0xffffffffu, fx[n], 1);
+      __syncthreads();
+
+      // ---- conservative update (godfine1, hydro/godunov_fine.f90:751-792): x, then y, then z ----
+      if (own) {
+        double unew_[NV];
+        bool have = false;
+        if (HZ) {
+          if (k > z0) {   // finish plane k-1 with the z fluxes
+#pragma unroll
+            for (int n = 0; n < NV; n++) unew_[n] = carry[(2 * NV + n) * NT + tid] + (carry[(NV + n) * NT + tid] - fz[n]);
+            have = true;
+          }
+          if (k >= z0) {
+#pragma unroll
+            for (int n = 0; n < NV; n++) carry[(NV + n) * NT + tid] = fz[n];
+          }
+        }
+        if (plane_flux) {
+          const long long off = cell_offset<NDIM>(g, cx, cy, HZ ? k : 0);
+#pragma unroll
+          for (int n = 0; n < NV; n++) {
+            double u = __ldg(a.uin + n * vstride + off);          // set_unew: unew = uold
+            u = u + (fx[n] - fxr[n]);
+            if (HY) u = u + (fy[n] - exf[n * NT + tid + BX]);
+            if (HZ) carry[(2 * NV + n) * NT + tid] = u; else unew_[n] = u;
+          }
+          if (!HZ) have = true;
+        }
+        if (have) {
+          const long long off = cell_offset<NDIM>(g, cx, cy, HZ ? k - 1 : 0);
+#pragma unroll
+          for (int n = 0; n < NV; n++) a.uout[n * vstride + off] = unew_[n];   // set_uold: uold = unew
+          // fused courant_fine of the new state (hydro/courant_fine.f90:96-123)
+          double ei;
+          const double dtc = cmpdt_cell<NDIM>(unew_, a.dx, P, ei);
+          my_dt = dtc < my_dt ? dtc : my_dt;
+          my_mass += unew_[0];
+          my_etot += unew_[NDIM + 1];
+          my_eint += ei;
+        }
       }
     }
   }
@@ -378,6 +467,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
   my_dt = warp_min(my_dt);
   my_mass = warp_sum(my_mass); my_etot = warp_sum(my_etot); my_eint = warp_sum(my_eint);
   const int w = tid >> 5, l = tid & 31;
+  __syncthreads();
   if (l == 0) { red[0][w] = my_dt; red[1][w] = my_mass; red[2][w] = my_etot; red[3][w] = my_eint; }
   __syncthreads();
   if (w == 0) {
@@ -392,24 +482,17 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
   }
 }
 
-template <int NDIM, int BX, int BY>
-constexpr size_t sweep_smem_bytes() {
-  constexpr int NV = NDIM + 2, HY = NDIM > 1, HZ = NDIM > 2;
-  constexpr int QX = BX + 2, QY = HY ? BY + 2 : 1, NRING = HZ ? 3 : 1;
-  return sizeof(double) * ((size_t)NRING * NV * QY * QX + 2 * (size_t)(1 + HY) * NV * BY * BX);
-}
-
-// tile shapes per dimensionality
+// tile shapes per dimensionality (a warp = one x-row of 32 cells for NDIM>1)
 template <int NDIM> struct TileShape;
-template <> struct TileShape<1> { static constexpr int BX = 128, BY = 1; };
+template <> struct TileShape<1> { static constexpr int BX = 32, BY = 1; };
 template <> struct TileShape<2> { static constexpr int BX = 32, BY = 8; };
 template <> struct TileShape<3> { static constexpr int BX = 32, BY = 16; };
 
-// host launchers, one translation unit per (NDIM, RIEMANN)
+// host launchers, one translation unit per NDIM
 template <int NDIM, int RIEMANN>
 cudaError_t launch_sweep_dense(const SweepArgs& a, int nblocks, cudaStream_t st) {
   constexpr int BX = TileShape<NDIM>::BX, BY = TileShape<NDIM>::BY;
-  constexpr size_t smem = sweep_smem_bytes<NDIM, BX, BY>();
+  constexpr size_t smem = sizeof(double) * SweepSmem<NDIM, BX, BY>::doubles;
   auto kern = sweep_dense_kernel<NDIM, RIEMANN, BX, BY>;
   static bool configured = false;
   if (!configured) {

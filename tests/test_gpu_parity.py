@@ -184,3 +184,17 @@ def test_split_calls_match_fused(gpu):
     h.finalize()
     idx = c.active_cells()
     assert np.array_equal(a.uold[:, idx], ref.reshape(c.nvar, -1)[:, idx])
+
+
+def test_div_rn_matches_ieee(gpu):
+    """The shared-reciprocal quotient used in the kernels (rcp_rn + 3 FMA-type instructions) is bit-identical to
+    the IEEE division on 2^28 random / adversarial operand pairs."""
+    import ctypes as C
+    from ramses_b200.hydro import HydroGPU
+    c = Case(3, 2)
+    h = HydroGPU(c.amr_commons())
+    bad = C.c_longlong(-1)
+    from ramses_b200 import lib
+    lib.check(h.L.rgpu_selftest_div(1 << 28, 12345, C.byref(bad)))
+    h.finalize()
+    assert bad.value == 0
