@@ -85,6 +85,17 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active,
                     int nboundary, const int* boundary_type,
                     const int* ngrid_bound, const int* const* igrid_bound);
 
+/* Host-only dry run of rgpu_bind_level: computes the level plan (is it a dense box? extents, owned range, periodic
+ * wrap, slot numbering) from the tree and communicator lists without any CUDA call and without rgpu_init.
+ * slot_igrid_out (may be NULL, capacity slot_cap) receives the igrid of every lattice slot (0 = empty).           */
+int rgpu_plan_level(const rgpu_params* p, int myid, int ncoarse, int ngridmax, const int* father,
+                    int ilevel, int ngrid_active, const int* igrid_active,
+                    int ncpu, const int* ngrid_recv, const int* const* igrid_recv,
+                    const int* ngrid_emit, const int* const* igrid_emit,
+                    int nboundary, const int* boundary_type,
+                    const int* ngrid_bound, const int* const* igrid_bound,
+                    struct rgpu_level_info* info, int* slot_igrid_out, long long slot_cap);
+
 /* ---- Level-0 contract: host arrays in, host arrays out ------------------------
  * godunov_fine(ilevel) (hydro/godunov_fine.f90:5) on uold(1:ncell,1:nvar) ->
  * unew(1:ncell,1:nvar): for every active cell of the level

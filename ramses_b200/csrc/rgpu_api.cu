@@ -75,6 +75,8 @@ struct Level {
   int gmin = 0, gmax = 0;            // igrid range covered by the level (host mirror window)
   long long nslot = 0;
   std::vector<int> slot_igrid;       // igrid of every slot (0: empty)
+  std::vector<std::vector<int>> h_bslots, h_rslots, h_eslots;   // boundary / reception / emission octs as slots
+  std::vector<int> h_btype;
   int* d_slot_igrid = nullptr;
   double* d_mirror = nullptr;        // host-layout window [nvar][2^ndim][gmax-gmin+1]
   double* d_u[2] = {nullptr, nullptr};
@@ -360,7 +362,7 @@ int launch_sweep(Level& L) {
   a.P = G.phys;
   a.dt_dev = L.d_dt;
   a.dx = L.dx;
-  a.inv_dx = 1.0 / L.dx;
+  a.inv_dx = 1.0 / L.dx;   // correctly rounded reciprocal (IEEE division on the host)
   int ex;
   a.dx_pow2 = (std::frexp(L.dx, &ex) == 0.5) ? 1 : 0;
   a.ntx = L.ntx; a.nty = L.nty; a.nwork = L.nwork;
@@ -526,16 +528,12 @@ int rgpu_bind_tree(int ncoarse, int ngridmax, const int* son, const int* father,
   return RGPU_OK;
 }
 
-int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int ncpu, const int* ngrid_recv,
+// Host-only planning of a level: oct positions from the father chain, dense-box detection, slot numbering,
+// periodic unwrapping of ghost octs, boundary / reception / emission slot lists.  No CUDA call in here.
+static int plan_level(Level& L, int ilevel, int ngrid_active, const int* igrid_active, int ncpu, const int* ngrid_recv,
                     const int* const* igrid_recv, const int* ngrid_emit, const int* const* igrid_emit, int nboundary,
                     const int* boundary_type, const int* ngrid_bound, const int* const* igrid_bound) {
-  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
-  if (!G.son) return fail(RGPU_EINVAL, "rgpu_bind_tree has not been called");
-  if (ilevel < 1 || ilevel > MAXLEVEL) return fail(RGPU_EINVAL, "ilevel %d out of range", ilevel);
-  if (ngrid_active <= 0 || !igrid_active) return fail(RGPU_EINVAL, "level %d has no active oct", ilevel);
-  Level& L = G.lev[ilevel];
-  if (L.bound) free_level(L);
-  const int nd = G.p.ndim, T = T_();
+  const int nd = G.p.ndim;
   L.dx = level_dx(ilevel);
   // ---- collect every oct of the level with its position -------------------------------------
   struct Rec { int ig; int pos[3]; int kind; int sub; };  // kind 0 active, 1 recv(peer sub), 2 boundary(region sub)
@@ -572,7 +570,7 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
     }
   L.bound = true;
   L.dense = (avol == ngrid_active) && in_shell;
-  if (!L.dense) return RGPU_OK;   // bound, but only the AMR path (not built) could run it
+  if (!L.dense) return RGPU_OK;
   // every dimension must either be periodic over the whole level (no shell) or carry a shell on both sides
   int wrap[3] = {0, 0, 0};
   for (int d = 0; d < nd; d++) {
@@ -604,7 +602,9 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
     return s;
   };
   L.gmin = 1 << 30; L.gmax = 0;
-  std::vector<std::vector<int>> bslots(nboundary), rslots(ncpu > 1 ? ncpu : 0);
+  std::vector<std::vector<int>>& bslots = L.h_bslots; std::vector<std::vector<int>>& rslots = L.h_rslots;
+  bslots.assign(nboundary, {}); rslots.assign(ncpu > 1 ? ncpu : 0, {}); L.h_eslots.assign(ncpu > 1 ? ncpu : 0, {});
+  L.h_btype.assign(boundary_type, boundary_type + nboundary);
   for (auto& r : recs) {
     const long long s = slot_of(r.pos);
     if (L.slot_igrid[s] != 0) return fail(RGPU_EINVAL, "level %d: two octs (%d,%d) at the same lattice site", ilevel, L.slot_igrid[s], r.ig);
@@ -613,6 +613,39 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
     if (r.kind == 2) bslots[r.sub].push_back((int)s);
     if (r.kind == 1) rslots[r.sub].push_back((int)s);
   }
+  // emission octs as slots (the peer's reception list is sorted the same way by construction of build_comm)
+  if (ncpu > 1 && ngrid_emit && igrid_emit)
+    for (int c = 0; c < ncpu; c++) {
+      if (c == G.myid - 1) continue;
+      L.h_eslots[c].resize(ngrid_emit[c]);
+      for (int i = 0; i < ngrid_emit[c]; i++) {
+        int pos[3];
+        oct_pos(ilevel, igrid_emit[c][i], pos);
+        L.h_eslots[c][i] = (int)slot_of(pos);
+      }
+    }
+  return RGPU_OK;
+}
+
+int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int ncpu, const int* ngrid_recv,
+                    const int* const* igrid_recv, const int* ngrid_emit, const int* const* igrid_emit, int nboundary,
+                    const int* boundary_type, const int* ngrid_bound, const int* const* igrid_bound) {
+  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  if (!G.son) return fail(RGPU_EINVAL, "rgpu_bind_tree has not been called");
+  if (ilevel < 1 || ilevel > MAXLEVEL) return fail(RGPU_EINVAL, "ilevel %d out of range", ilevel);
+  if (ngrid_active <= 0 || !igrid_active) return fail(RGPU_EINVAL, "level %d has no active oct", ilevel);
+  Level& L = G.lev[ilevel];
+  if (L.bound) free_level(L);
+  {
+    const int rc = plan_level(L, ilevel, ngrid_active, igrid_active, ncpu, ngrid_recv, igrid_recv, ngrid_emit, igrid_emit, nboundary,
+                              boundary_type, ngrid_bound, igrid_bound);
+    if (rc) return rc;
+  }
+  if (!L.dense) return RGPU_OK;   // bound, but only the AMR path (not built) could run it
+  const int nd = G.p.ndim;
+  const long long nslot = L.nslot;
+  DenseGeom& g = L.g;
+  std::vector<std::vector<int>>& bslots = L.h_bslots; std::vector<std::vector<int>>& rslots = L.h_rslots;
   if (nslot >= (1LL << 31)) return fail(RGPU_EUNSUPPORTED, "level too large for 32-bit slots");
   const long long gspan = (long long)L.gmax - L.gmin + 1;
   const size_t np = nplanes_();
@@ -644,14 +677,9 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
         CUDA_OK(cudaMemcpy(P.d_recv, rslots[c].data(), sizeof(int) * P.nrecv, cudaMemcpyHostToDevice));
         CUDA_OK(cudaMalloc(&P.d_rbuf, sizeof(double) * np * P.nrecv));
       }
-      P.nemit = (ngrid_emit && igrid_emit) ? ngrid_emit[c] : 0;
+      P.nemit = (int)L.h_eslots[c].size();
       if (P.nemit) {
-        std::vector<int> es(P.nemit);
-        for (int i = 0; i < P.nemit; i++) {
-          int pos[3];
-          oct_pos(ilevel, igrid_emit[c][i], pos);
-          es[i] = (int)slot_of(pos);
-        }
+        const std::vector<int>& es = L.h_eslots[c];
         CUDA_OK(cudaMalloc(&P.d_emit, sizeof(int) * P.nemit));
         CUDA_OK(cudaMemcpy(P.d_emit, es.data(), sizeof(int) * P.nemit, cudaMemcpyHostToDevice));
         CUDA_OK(cudaMalloc(&P.d_sbuf, sizeof(double) * np * P.nemit));
@@ -660,7 +688,7 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
   }
   // ---- tile decomposition of the owned range ----------------------------------------------------
   const int bx = 32;
-  const int by = nd == 1 ? 1 : nd == 2 ? TileShape<2>::BY : TileShape<3>::BY;
+  const int by = tile_by(nd, G.p.riemann);
   const int txo = bx - 2, tyo = nd > 1 ? by - 2 : 1;
   L.ntx = (g.ox1 - g.ox0 + txo - 1) / txo;
   L.nty = nd > 1 ? (g.oy1 - g.oy0 + tyo - 1) / tyo : 1;
@@ -676,6 +704,36 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
   CUDA_OK(cudaMalloc(&L.d_dt, sizeof(double)));
   CUDA_OK(cudaMalloc(&L.d_out, sizeof(double) * 4));
   L.cur = 0; L.unew_valid = false;
+  return RGPU_OK;
+}
+
+// Host-only entry point: the level plan (dense-box geometry and slot numbering) without touching CUDA.
+// Used by the CPU test-suite and for dry runs of a new mesh; needs no rgpu_init.
+int rgpu_plan_level(const rgpu_params* p, int myid, int ncoarse, int ngridmax, const int* father, int ilevel, int ngrid_active, const int* igrid_active, int ncpu, const int* ngrid_recv,
+                    const int* const* igrid_recv, const int* ngrid_emit, const int* const* igrid_emit, int nboundary,
+                    const int* boundary_type, const int* ngrid_bound, const int* const* igrid_bound,
+                    rgpu_level_info* info, int* slot_igrid_out, long long slot_cap) {
+  if (!p || !father || !info) return fail(RGPU_EINVAL, "null argument");
+  if (G.init) return fail(RGPU_EINVAL, "rgpu_plan_level is a dry-run entry point: call it before rgpu_init or after rgpu_finalize");
+  G.p = *p; G.myid = myid; G.ncoarse = ncoarse; G.ngridmax = ngridmax; G.father = father;
+  Level L;
+  const int rc = plan_level(L, ilevel, ngrid_active, igrid_active, ncpu, ngrid_recv, igrid_recv, ngrid_emit, igrid_emit, nboundary,
+                            boundary_type, ngrid_bound, igrid_bound);
+  G.father = nullptr;
+  if (rc) return rc;
+  memset(info, 0, sizeof(*info));
+  info->dense = L.dense;
+  if (L.dense) {
+    info->ncell_box[0] = L.g.ncx; info->ncell_box[1] = L.g.ncy; info->ncell_box[2] = L.g.ncz;
+    info->own_lo[0] = L.g.ox0; info->own_lo[1] = L.g.oy0; info->own_lo[2] = L.g.oz0;
+    info->own_hi[0] = L.g.ox1; info->own_hi[1] = L.g.oy1; info->own_hi[2] = L.g.oz1;
+    info->wrap[0] = L.g.wrapx; info->wrap[1] = L.g.wrapy; info->wrap[2] = L.g.wrapz;
+    info->nslot = L.nslot;
+    if (slot_igrid_out) {
+      if (slot_cap < L.nslot) return fail(RGPU_EINVAL, "slot_igrid_out too small (%lld < %lld)", slot_cap, L.nslot);
+      memcpy(slot_igrid_out, L.slot_igrid.data(), sizeof(int) * L.nslot);
+    }
+  }
   return RGPU_OK;
 }
 

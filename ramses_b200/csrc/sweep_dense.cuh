@@ -81,10 +81,17 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// flux scaling of unsplit: flux = fx*dt/dx (hydro/umuscl.f90:106,129,153)
-__device__ __forceinline__ double scale_flux(double f, double dt, double dx, double inv_dx, int pow2) {
-  const double t = f * dt;
-  return pow2 ? t * inv_dx : t / dx;
+// flux scaling of unsplit: flux = fx*dt/dx (hydro/umuscl.f90:106,129,153).  dx a power of two: x/dx == x*(1/dx)
+// exactly; otherwise the shared-reciprocal quotient (inv_dx = correctly rounded 1/dx).
+template <int NV>
+__device__ __forceinline__ void scale_fluxes(double* f, double dt, double dx, double inv_dx, int pow2) {
+  if (pow2) {
+#pragma unroll
+    for (int n = 0; n < NV; n++) f[n] = (f[n] * dt) * inv_dx;
+  } else {
+#pragma unroll
+    for (int n = 0; n < NV; n++) f[n] = div_rn(f[n] * dt, dx, inv_dx);
+  }
 }
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
@@ -110,7 +117,7 @@ struct SweepSmem {
   static constexpr size_t doubles = ring + stage + exq + exf + carry;
 };
 
-template <int NDIM, int RIEMANN, int BX, int BY>
+template <int NDIM, int RIEMANN, int SLOPE, int BX, int BY>
 __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs a) {
   using S = SweepSmem<NDIM, BX, BY>;
   constexpr int NV = S::NV, HY = S::HY, HZ = S::HZ, QX = S::QX, QY = S::QY, NQ = S::NQ, NT = S::NT;
@@ -161,11 +168,22 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
     const bool need_fx = (tx >= 1) && row_own && (cx <= g.ox1);
     const bool need_fy = HY && (ty >= 1) && col_own && (cy <= g.oy1);
 
-    // (qx,qy) -> global offset of the plane-independent part; each thread owns cells i = tid, tid+NT, ...
-    auto cell_xy = [&](int i, int& xc, int& yc) {
-      const int qx = i % QX, qy = i / QX;
-      xc = wrap_or_clamp(x0 - 2 + qx, g.ncx, g.wrapx);
-      yc = HY ? wrap_or_clamp(y0 - 2 + qy, g.ncy, g.wrapy) : 0;
+    // each thread owns the q-tile cells i = tid, tid+NT, ...; their global offsets without the z part are
+    // plane independent and computed once per segment
+    constexpr int NOWN = (PL + NT - 1) / NT;
+    long long offxy[NOWN];
+#pragma unroll
+    for (int j = 0; j < NOWN; j++) {
+      const int i = tid + j * NT;
+      const int qx_ = i % QX, qy_ = i / QX;
+      const int xc = wrap_or_clamp(x0 - 2 + qx_, g.ncx, g.wrapx);
+      const int yc = HY ? wrap_or_clamp(y0 - 2 + qy_, g.ncy, g.wrapy) : 0;
+      offxy[j] = cell_offset<NDIM>(g, xc, yc, 0);
+    }
+    auto zoff = [&](int z) -> long long {     // z part of cell_offset
+      if (!HZ) return 0;
+      const int zc = wrap_or_clamp(z, g.ncz, g.wrapz);
+      return (long long)((zc & 1) << 2) * g.nslot + (long long)g.nox * g.noy * (zc >> 1);
     };
     // ctoprim (hydro/umuscl.f90:861) of one cell into ring slot `slot`
     auto to_ring = [&](const double* u, int slot, int i) {
@@ -189,11 +207,12 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
       qs[NV * PL] = oneoverrho;
     };
     auto load_plane_direct = [&](int z, int slot) {
-      const int zc = HZ ? wrap_or_clamp(z, g.ncz, g.wrapz) : 0;
-      for (int i = tid; i < PL; i += NT) {
-        int xc, yc;
-        cell_xy(i, xc, yc);
-        const long long off = cell_offset<NDIM>(g, xc, yc, zc);
+      const long long zo = zoff(z);
+#pragma unroll
+      for (int j = 0; j < NOWN; j++) {
+        const int i = tid + j * NT;
+        if (i >= PL) break;
+        const long long off = offxy[j] + zo;
         double u[NV];
 #pragma unroll
         for (int n = 0; n < NV; n++) u[n] = __ldg(a.uin + n * vstride + off);
@@ -201,11 +220,12 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
       }
     };
     auto stage_plane_async = [&](int z) {     // raw u of plane z -> staging buffer (cp.async, no registers)
-      const int zc = wrap_or_clamp(z, g.ncz, g.wrapz);
-      for (int i = tid; i < PL; i += NT) {
-        int xc, yc;
-        cell_xy(i, xc, yc);
-        const long long off = cell_offset<NDIM>(g, xc, yc, zc);
+      const long long zo = zoff(z);
+#pragma unroll
+      for (int j = 0; j < NOWN; j++) {
+        const int i = tid + j * NT;
+        if (i >= PL) break;
+        const long long off = offxy[j] + zo;
 #pragma unroll
         for (int n = 0; n < NV; n++) cp_async8(stage + n * PL + i, a.uin + n * vstride + off);
       }
@@ -246,7 +266,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
         for (int n = 0; n < NV; n++) q[n] = qc[n * PL];
         const double rinv = qc[NV * PL];
         // ---- uslope (hydro/umuscl.f90:970) ----
-        if (P.slope_type == 3 && NDIM > 1) {
+        if (SLOPE < 0 && P.slope_type == 3 && NDIM > 1) {
           // positivity preserving unsplit slope :1101-1144 (2-D), :1328-1391 (3-D)
 #pragma unroll
           for (int n = 0; n < NV; n++) {
@@ -276,7 +296,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
             dq[HY][n] = slop * dfy;
             if (HZ) dq[NDIM - 1][n] = slop * dfz;
           }
-        } else if (NDIM == 1 && P.slope_type >= 4 && P.slope_type <= 6) {
+        } else if (SLOPE < 0 && NDIM == 1 && P.slope_type >= 4 && P.slope_type <= 6) {
           // 1-D only limiters :1021-1068
           const double uvel = q[1];
 #pragma unroll
@@ -313,12 +333,12 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
 #pragma unroll
           for (int n = 0; n < NV; n++) {
             const double* qn = qc + n * PL;
-            dq[0][n] = slope_lcr<NDIM>(qn[-1], q[n], qn[1], P);
-            if (HY) dq[HY][n] = slope_lcr<NDIM>(qn[-QX], q[n], qn[QX], P);
+            dq[0][n] = slope_lcr<NDIM, SLOPE>(qn[-1], q[n], qn[1], P);
+            if (HY) dq[HY][n] = slope_lcr<NDIM, SLOPE>(qn[-QX], q[n], qn[QX], P);
             if (HZ) {
               const double qb = qring[(size_t)sm1 * NQ * PL + n * PL + qy * QX + qx];
               const double qf = qring[(size_t)sp1 * NQ * PL + n * PL + qy * QX + qx];
-              dq[NDIM - 1][n] = slope_lcr<NDIM>(qb, q[n], qf, P);
+              dq[NDIM - 1][n] = slope_lcr<NDIM, SLOPE>(qb, q[n], qf, P);
             }
           }
         }
@@ -348,9 +368,14 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
       for (int n = 0; n < NV; n++) qlx[n] = __shfl_up_sync(0xffffffffu, qmx[n], 1);
       __syncthreads();
 
-      double fx[NV], fy[NV], fz[NV];
+      double fx[NV], fy[NV], fz[NV], ucur[NV];
 #pragma unroll
-      for (int n = 0; n < NV; n++) { fx[n] = 0.0; fy[n] = 0.0; fz[n] = 0.0; }
+      for (int n = 0; n < NV; n++) { fx[n] = 0.0; fy[n] = 0.0; fz[n] = 0.0; ucur[n] = 0.0; }
+      if (own && plane_flux) {   // set_unew: unew = uold; issued early so the latency hides under the Riemann solves
+        const long long off = cell_offset<NDIM>(g, cx, cy, HZ ? k : 0);
+#pragma unroll
+        for (int n = 0; n < NV; n++) ucur[n] = __ldg(a.uin + n * vstride + off);
+      }
       // ---- X faces: cmpflxm(...,2,3,4) hydro/umuscl.f90:97 ----
       if (need_fx && plane_flux) {
         double ql[NV], qr[NV], fg[NV];
@@ -368,8 +393,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
         fx[0] = fg[0]; fx[1] = fg[1]; fx[NDIM + 1] = fg[2];
         if (NDIM > 1) fx[2] = fg[3];
         if (NDIM > 2) fx[3] = fg[4];
-#pragma unroll
-        for (int n = 0; n < NV; n++) fx[n] = scale_flux(fx[n], dt, a.dx, a.inv_dx, a.dx_pow2);
+        scale_fluxes<NV>(fx, dt, a.dx, a.inv_dx, a.dx_pow2);
       }
       // ---- Y faces: cmpflxm(...,3,2,4) hydro/umuscl.f90:120 ----
       if (HY && need_fy && plane_flux) {
@@ -386,11 +410,9 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
         riemann<NDIM, RIEMANN>(ql, qr, fg, P);
         fy[0] = fg[0]; fy[2] = fg[1]; fy[NDIM + 1] = fg[2]; fy[1] = fg[3];
         if (NDIM > 2) fy[3] = fg[4];
+        scale_fluxes<NV>(fy, dt, a.dx, a.inv_dx, a.dx_pow2);
 #pragma unroll
-        for (int n = 0; n < NV; n++) {
-          fy[n] = scale_flux(fy[n], dt, a.dx, a.inv_dx, a.dx_pow2);
-          exf[n * NT + tid] = fy[n];
-        }
+        for (int n = 0; n < NV; n++) exf[n * NT + tid] = fy[n];
       }
       // ---- Z faces: cmpflxm(...,4,2,3) hydro/umuscl.f90:144; left state carried from the previous plane ----
       if (HZ && own && k >= z0) {
@@ -404,8 +426,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
         qr[0] = qp[0]; qr[1] = qp[3 % NV]; qr[2] = qp[NDIM + 1]; qr[3] = qp[1]; qr[4 % NV] = qp[2];
         riemann<NDIM, RIEMANN>(ql, qr, fg, P);
         fz[0] = fg[0]; fz[3 % NV] = fg[1]; fz[NDIM + 1] = fg[2]; fz[1] = fg[3]; fz[2] = fg[4 % NV];
-#pragma unroll
-        for (int n = 0; n < NV; n++) fz[n] = scale_flux(fz[n], dt, a.dx, a.inv_dx, a.dx_pow2);
+        scale_fluxes<NV>(fz, dt, a.dx, a.inv_dx, a.dx_pow2);
       }
       if (HZ && own) {
 #pragma unroll
@@ -437,10 +458,9 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
           }
         }
         if (plane_flux) {
-          const long long off = cell_offset<NDIM>(g, cx, cy, HZ ? k : 0);
 #pragma unroll
           for (int n = 0; n < NV; n++) {
-            double u = __ldg(a.uin + n * vstride + off);          // set_unew: unew = uold
+            double u = ucur[n];
             u = u + (fx[n] - fxr[n]);
             if (HY) u = u + (fy[n] - exf[n * NT + tid + BX]);
             if (HZ) carry[(2 * NV + n) * NT + tid] = u; else unew_[n] = u;
@@ -482,18 +502,21 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
   }
 }
 
-// tile shapes per dimensionality (a warp = one x-row of 32 cells for NDIM>1)
-template <int NDIM> struct TileShape;
-template <> struct TileShape<1> { static constexpr int BX = 32, BY = 1; };
-template <> struct TileShape<2> { static constexpr int BX = 32, BY = 8; };
-template <> struct TileShape<3> { static constexpr int BX = 32, BY = 16; };
+// tile shapes (a warp = one x-row of 32 cells).  3-D: 32x12 threads (168 registers/thread, no spills) for the
+// algebraic solvers; the iterative 'exact' solver prefers 32x16 (more warps to cover its divergent Newton loop).
+// Measured on B200, 256^3: hllc 2.30 ms (32x12) vs 2.88 ms (32x16); exact 5.18 ms (32x16) vs 5.46 ms (32x12).
+template <int NDIM, int RIEMANN> struct TileShape { static constexpr int BX = 32, BY = (NDIM == 1) ? 1 : 8; };
+template <int RIEMANN> struct TileShape<3, RIEMANN> { static constexpr int BX = 32, BY = (RIEMANN == RIEMANN_EXACT) ? 16 : 12; };
+__host__ __device__ constexpr int tile_by(int ndim, int riemann) {
+  return ndim == 1 ? 1 : ndim == 2 ? 8 : (riemann == RIEMANN_EXACT ? 16 : 12);
+}
 
 // host launchers, one translation unit per NDIM
-template <int NDIM, int RIEMANN>
-cudaError_t launch_sweep_dense(const SweepArgs& a, int nblocks, cudaStream_t st) {
-  constexpr int BX = TileShape<NDIM>::BX, BY = TileShape<NDIM>::BY;
+template <int NDIM, int RIEMANN, int SLOPE>
+cudaError_t launch_sweep_dense_s(const SweepArgs& a, int nblocks, cudaStream_t st) {
+  constexpr int BX = TileShape<NDIM, RIEMANN>::BX, BY = TileShape<NDIM, RIEMANN>::BY;
   constexpr size_t smem = sizeof(double) * SweepSmem<NDIM, BX, BY>::doubles;
-  auto kern = sweep_dense_kernel<NDIM, RIEMANN, BX, BY>;
+  auto kern = sweep_dense_kernel<NDIM, RIEMANN, SLOPE, BX, BY>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -502,6 +525,13 @@ cudaError_t launch_sweep_dense(const SweepArgs& a, int nblocks, cudaStream_t st)
   }
   kern<<<nblocks, dim3(BX, BY, 1), smem, st>>>(a);
   return cudaGetLastError();
+}
+// slope_type 1 (minmod) and 2 (moncen) are compiled in; every other limiter goes through the runtime switch
+template <int NDIM, int RIEMANN>
+cudaError_t launch_sweep_dense(const SweepArgs& a, int nblocks, cudaStream_t st) {
+  if (a.P.slope_type == 1) return launch_sweep_dense_s<NDIM, RIEMANN, 1>(a, nblocks, st);
+  if (a.P.slope_type == 2) return launch_sweep_dense_s<NDIM, RIEMANN, 2>(a, nblocks, st);
+  return launch_sweep_dense_s<NDIM, RIEMANN, -1>(a, nblocks, st);
 }
 
 }  // namespace rgpu

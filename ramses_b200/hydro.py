@@ -73,29 +73,77 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+def make_params(amr):
+    """struct rgpu_params from the module variables (what the Fortran shim fills after read_params)."""
+    p = _lib.Params()
+    p.ndim, p.nvar, p.nvector = amr.ndim, amr.nvar, amr.nvector
+    p.slope_type, p.niter_riemann = amr.slope_type, amr.niter_riemann
+    if amr.scheme not in ("muscl", "plmde"):
+        raise ValueError("unknown scheme")
+    p.scheme = 0 if amr.scheme == "muscl" else 1
+    if amr.riemann not in _lib.RIEMANN:
+        raise ValueError("unknown Riemann solver")          # hydro/umuscl.f90:801-803
+    p.riemann = _lib.RIEMANN[amr.riemann]
+    p.pressure_fix = int(bool(amr.pressure_fix))
+    p.gamma, p.smallr, p.smallc = amr.gamma, amr.smallr, amr.smallc
+    p.slope_theta, p.difmag, p.courant_factor, p.boxlen = amr.slope_theta, amr.difmag, amr.courant_factor, amr.boxlen
+    p.nx, p.ny, p.nz = amr.nx, amr.ny, amr.nz
+    p.icoarse_min, p.icoarse_max = amr.icoarse_min, amr.icoarse_max
+    p.jcoarse_min, p.jcoarse_max = amr.jcoarse_min, amr.jcoarse_max
+    p.kcoarse_min, p.kcoarse_max = amr.kcoarse_min, amr.kcoarse_max
+    p.nlevelmax = amr.nlevelmax
+    return p
+
+
+def _level_lists(a, ilevel, keep):
+    """ctypes views of the communicator lists of one level, in the argument order of rgpu_bind_level."""
+    act = np.ascontiguousarray(a.active[ilevel], dtype=np.int32)
+    bl = [np.ascontiguousarray(x, dtype=np.int32) for x in a.boundary.get(ilevel, [])]
+    nb = len(bl)
+    btype = (C.c_int * max(nb, 1))(*a.boundary_type[:nb])
+    nbnd = (C.c_int * max(nb, 1))(*[len(x) for x in bl])
+    bptr = (C.POINTER(C.c_int) * max(nb, 1))(*[_ip(x) for x in bl])
+    ncpu = a.ncpu
+    if ncpu > 1:
+        rl = [np.ascontiguousarray(x, dtype=np.int32) for x in a.reception[ilevel]]
+        el = [np.ascontiguousarray(x, dtype=np.int32) for x in a.emission[ilevel]]
+        nr = (C.c_int * ncpu)(*[len(x) for x in rl])
+        ne = (C.c_int * ncpu)(*[len(x) for x in el])
+        rp = (C.POINTER(C.c_int) * ncpu)(*[_ip(x) for x in rl])
+        ep = (C.POINTER(C.c_int) * ncpu)(*[_ip(x) for x in el])
+        keep.append((rl, el))
+    else:
+        nr = ne = rp = ep = None
+    keep.append((act, bl))
+    return (len(act), _ip(act), ncpu, nr, rp, ne, ep, nb, btype, nbnd, bptr)
+
+
+def plan_level(amr, ilevel):
+    """Host-only dry run of bind_level (rgpu_plan_level): returns (LevelInfo, slot_igrid array).  No GPU needed."""
+    L = _lib.load()
+    p = make_params(amr)
+    keep = []
+    args = _level_lists(amr, ilevel, keep)
+    info = _lib.LevelInfo()
+    cap = 8 * max(len(amr.active[ilevel]), 1) + 64
+    for _ in range(2):
+        slots = np.zeros(cap, dtype=np.int32)
+        rc = L.rgpu_plan_level(C.byref(p), amr.myid, amr.ncoarse, amr.ngridmax, _ip(amr.father), ilevel, *args,
+                               C.byref(info), _ip(slots), cap)
+        if rc == 0 or info.nslot <= cap:
+            break
+        cap = int(info.nslot)
+    _lib.check(rc)
+    return info, slots[:info.nslot].copy()
+
+
 class HydroGPU:
     """The patched routines of hydro/godunov_fine.f90 & friends, running on the GPU through the C-ABI."""
 
     def __init__(self, amr: AmrCommons, device=-1):
         self.a = amr
         self.L = _lib.load()
-        p = _lib.Params()
-        p.ndim, p.nvar, p.nvector = amr.ndim, amr.nvar, amr.nvector
-        p.slope_type, p.niter_riemann = amr.slope_type, amr.niter_riemann
-        if amr.scheme not in ("muscl", "plmde"):
-            raise ValueError("unknown scheme")
-        p.scheme = 0 if amr.scheme == "muscl" else 1
-        if amr.riemann not in _lib.RIEMANN:
-            raise ValueError("unknown Riemann solver")          # hydro/umuscl.f90:801-803
-        p.riemann = _lib.RIEMANN[amr.riemann]
-        p.pressure_fix = int(bool(amr.pressure_fix))
-        p.gamma, p.smallr, p.smallc = amr.gamma, amr.smallr, amr.smallc
-        p.slope_theta, p.difmag, p.courant_factor, p.boxlen = amr.slope_theta, amr.difmag, amr.courant_factor, amr.boxlen
-        p.nx, p.ny, p.nz = amr.nx, amr.ny, amr.nz
-        p.icoarse_min, p.icoarse_max = amr.icoarse_min, amr.icoarse_max
-        p.jcoarse_min, p.jcoarse_max = amr.jcoarse_min, amr.jcoarse_max
-        p.kcoarse_min, p.kcoarse_max = amr.kcoarse_min, amr.kcoarse_max
-        p.nlevelmax = amr.nlevelmax
+        p = make_params(amr)
         self.params = p
         _lib.check(self.L.rgpu_init(C.byref(p), amr.myid, amr.ncpu, device))
         self._keep = []
@@ -109,26 +157,8 @@ class HydroGPU:
         _lib.check(self.L.rgpu_bind_tree(a.ncoarse, a.ngridmax, _ip(a.son), _ip(a.father), _ip(a.nbor)))
 
     def bind_level(self, ilevel):
-        a = self.a
-        act = np.ascontiguousarray(a.active[ilevel], dtype=np.int32)
-        bl = [np.ascontiguousarray(x, dtype=np.int32) for x in a.boundary.get(ilevel, [])]
-        nb = len(bl)
-        btype = (C.c_int * max(nb, 1))(*a.boundary_type[:nb])
-        nbnd = (C.c_int * max(nb, 1))(*[len(x) for x in bl])
-        bptr = (C.POINTER(C.c_int) * max(nb, 1))(*[_ip(x) for x in bl])
-        ncpu = a.ncpu
-        if ncpu > 1:
-            rl = [np.ascontiguousarray(x, dtype=np.int32) for x in a.reception[ilevel]]
-            el = [np.ascontiguousarray(x, dtype=np.int32) for x in a.emission[ilevel]]
-            nr = (C.c_int * ncpu)(*[len(x) for x in rl])
-            ne = (C.c_int * ncpu)(*[len(x) for x in el])
-            rp = (C.POINTER(C.c_int) * ncpu)(*[_ip(x) for x in rl])
-            ep = (C.POINTER(C.c_int) * ncpu)(*[_ip(x) for x in el])
-            self._keep.append((rl, el))
-        else:
-            nr = ne = rp = ep = None
-        self._keep.append((act, bl))
-        _lib.check(self.L.rgpu_bind_level(ilevel, len(act), _ip(act), ncpu, nr, rp, ne, ep, nb, btype, nbnd, bptr))
+        args = _level_lists(self.a, ilevel, self._keep)
+        _lib.check(self.L.rgpu_bind_level(ilevel, *args))
 
     def level_info(self, ilevel):
         info = _lib.LevelInfo()

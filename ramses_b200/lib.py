@@ -4,7 +4,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libramses_gpu.so")
+LIB_PATH = os.environ.get("RGPU_LIB", os.path.join(_HERE, "libramses_gpu.so"))   # RGPU_LIB: kernel-variant experiments
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "ramses_gpu.h")
 
 RIEMANN = {"llf": 0, "exact": 1, "acoustic": 2, "hllc": 3, "hll": 4}
@@ -60,6 +60,8 @@ def load():
     L.rgpu_init.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int]
     L.rgpu_bind_tree.argtypes = [C.c_int, C.c_int, ip, ip, ip]
     L.rgpu_bind_level.argtypes = [C.c_int, C.c_int, ip, C.c_int, ip, ipp, ip, ipp, C.c_int, ip, ip, ipp]
+    L.rgpu_plan_level.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, ip, C.c_int, C.c_int, ip, C.c_int, ip, ipp, ip, ipp,
+                                  C.c_int, ip, ip, ipp, C.POINTER(LevelInfo), ip, C.c_longlong]
     L.rgpu_godunov_fine.argtypes = [C.c_int, C.c_double, dp, dp]
     L.rgpu_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.rgpu_host_unregister.argtypes = [C.c_void_p]

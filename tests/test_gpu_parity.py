@@ -198,3 +198,21 @@ def test_div_rn_matches_ieee(gpu):
     lib.check(h.L.rgpu_selftest_div(1 << 28, 12345, C.byref(bad)))
     h.finalize()
     assert bad.value == 0
+
+
+def test_multi_gpu_bit_identical_to_single_gpu(gpu):
+    """2 (or more) GPUs with NCCL ghost-oct exchange == the same global problem on one GPU, bit for bit."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else (4 if n < 8 else 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", os.path.join(root, "tests", "mgpu_check.py"), "5", "6", "hllc"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "state identical=True" in r.stdout

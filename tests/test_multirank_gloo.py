@@ -1,0 +1,107 @@
+"""World-size-2 (and 8 in-process) CPU tests of the multi-GPU host logic: rank-local trees, communicator lists and the
+level plans are mutually consistent, so that the packed ncclSend/ncclRecv exchange of rgpu_make_virtual_fine fills
+every ghost oct with its owner's data.  The exchange itself is emulated with gloo."""
+import os
+
+import numpy as np
+import pytest
+
+
+def _global_key(a, l, igrids):
+    pos = a._pos[l][np.asarray(igrids, dtype=np.int64) - a._igrid0[l]]
+    ext = np.array([a.nx, a.ny, a.nz], dtype=np.int64) << (l - 1)
+    return pos[:, 0] + ext[0] * (pos[:, 1] + ext[1] * pos[:, 2])
+
+
+@pytest.mark.parametrize("ncpu", [2, 4, 8])
+def test_lists_consistent_in_process(ncpu):
+    from ramses_b200.tree import build_uniform_tree, coarse_dims_for_ranks
+    from ramses_b200.hydro import plan_level
+    l = 4
+    coarse = coarse_dims_for_ranks(3, ncpu)
+    ranks = [build_uniform_tree(3, l, coarse=coarse, myid=r + 1, ncpu=ncpu) for r in range(ncpu)]
+    for r, a in enumerate(ranks):
+        info, slots = plan_level(a, l)
+        assert info.dense == 1
+        n = 1 << l
+        for d in range(3):
+            assert info.own_hi[d] - info.own_lo[d] == n
+            assert info.wrap[d] == (1 if coarse[d] == 1 else 0)
+            assert info.ncell_box[d] == n + (0 if coarse[d] == 1 else 4)
+        for c, b in enumerate(ranks):
+            if c == r:
+                continue
+            # what r emits to c is exactly what c expects from r, in the same order
+            assert np.array_equal(_global_key(a, l, a.emission[l][c]), _global_key(b, l, b.reception[l][r]))
+        assert sum(len(x) for x in a.reception[l]) == (slots > 0).sum() - len(a.active[l])
+
+
+def _worker(rank, world, port, l, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ramses_b200.tree import build_uniform_tree, coarse_dims_for_ranks, fill_state
+    coarse = coarse_dims_for_ranks(3, world)
+    a = build_uniform_tree(3, l, coarse=coarse, myid=rank + 1, ncpu=world)
+
+    def fn(x, y, z):      # a global field that identifies every cell
+        u = np.zeros((5, len(x)))
+        for v in range(5):
+            u[v] = (v + 1) * 1000 + x * 17.0 + y * 3.0 + z * 0.25
+        return u
+    fill_state(a, l, fn)
+    # forward ghost fill (make_virtual_fine_dp semantics, all variables in one message per peer)
+    T, ng = a.twotondim, a.ngridmax
+    reqs, rbufs = [], {}
+    for c in range(world):
+        if c == rank:
+            continue
+        ig = a.emission[l][c].astype(np.int64)
+        cells = np.concatenate([a.ncoarse + ind * ng + ig - 1 for ind in range(T)])
+        sb = torch.from_numpy(np.ascontiguousarray(a.uold[:, cells]))
+        rb = torch.zeros((5, T * len(a.reception[l][c])), dtype=torch.float64)
+        rbufs[c] = rb
+        reqs.append(dist.isend(sb, c))
+        reqs.append(dist.irecv(rb, c))
+    for r_ in reqs:
+        r_.wait()
+    ok = True
+    for c, rb in rbufs.items():
+        ig = a.reception[l][c].astype(np.int64)
+        cells = np.concatenate([a.ncoarse + ind * ng + ig - 1 for ind in range(T)])
+        a.uold[:, cells] = rb.numpy()
+    # every ghost cell now holds fn(its own global position) modulo the periodic box
+    from ramses_b200.tree import cell_centers
+    pos = a._pos[l]
+    for c in range(world):
+        if c == rank:
+            continue
+        ig = a.reception[l][c].astype(np.int64)
+        p = pos[ig - a._igrid0[l]]
+        for ind in range(T):
+            b = np.array([(ind >> d) & 1 for d in range(3)])
+            cc = (2 * p + b[None, :] + 0.5) / (2 ** l)
+            expect = fn(cc[:, 0], cc[:, 1], cc[:, 2])
+            got = a.uold[:, a.ncoarse + ind * ng + ig - 1]
+            ok = ok and np.array_equal(got, expect)
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        q.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+def test_ghost_exchange_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 3, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == 1
