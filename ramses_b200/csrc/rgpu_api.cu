@@ -288,6 +288,9 @@ __global__ void selftest_div_kernel(long long n_per_thread, unsigned long long s
     const double q1 = div_rn(a, b, rcp_rn(b));
     const double q2 = a / b;
     if (__double_as_longlong(q1) != __double_as_longlong(q2)) bad++;
+    if (__double_as_longlong(rcp_rn(b)) != __double_as_longlong(1.0 / b)) bad++;
+    const double aa = fabs(a);
+    if (__double_as_longlong(sqrt_rn(aa)) != __double_as_longlong(sqrt(aa))) bad++;
   }
   if (bad) atomicAdd(mismatches, bad);
 }

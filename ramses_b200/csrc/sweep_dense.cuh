@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
     auto to_ring = [&](const double* u, int slot, int i) {
       double q[NV];
       const double r = fmax(u[0], P.smallr);
-      const double oneoverrho = 1.0 / r;
+      const double oneoverrho = rcp_rn(r);
       q[0] = r;
       double eken;
       q[1] = u[1] * oneoverrho;
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
               dff = 0.5 * (fabs(dfx) + fabs(dfy) + fabs(dfz));
             } else dff = 0.5 * (fabs(dfx) + fabs(dfy));
             double slop;
-            if (dff > 0.0) slop = fmn(1.0, fmn(fabs(vmin), fabs(vmax)) / dff);
+            if (dff > 0.0) slop = fmn(1.0, fdiv(fmn(fabs(vmin), fabs(vmax)), dff));
             else slop = 1.0;
             dq[0][n] = slop * dfx;
             dq[HY][n] = slop * dfy;

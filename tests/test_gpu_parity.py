@@ -186,9 +186,9 @@ def test_split_calls_match_fused(gpu):
     assert np.array_equal(a.uold[:, idx], ref.reshape(c.nvar, -1)[:, idx])
 
 
-def test_div_rn_matches_ieee(gpu):
-    """The shared-reciprocal quotient used in the kernels (rcp_rn + 3 FMA-type instructions) is bit-identical to
-    the IEEE division on 2^28 random / adversarial operand pairs."""
+def test_fast_div_sqrt_match_ieee(gpu):
+    """The branch-free reciprocal / shared-reciprocal quotient / square root used in the kernels are bit-identical to
+    the IEEE `1/b`, `a/b`, sqrt(a) on 2^28 random / adversarial operand pairs (exponents within 2^+-100)."""
     import ctypes as C
     from ramses_b200.hydro import HydroGPU
     c = Case(3, 2)
