@@ -20,8 +20,8 @@
 
 namespace rgpu {
 // launchers instantiated in sweep_inst_*.cu
-template <int NDIM, int RIEMANN> cudaError_t launch_sweep_dense(const SweepArgs& a, int nblocks, cudaStream_t st);
-#define DECL(ND, R) extern template cudaError_t launch_sweep_dense<ND, R>(const SweepArgs&, int, cudaStream_t);
+template <int NDIM, int RIEMANN> cudaError_t launch_sweep_dense(const SweepArgs& a, int nblocks, cudaStream_t st, int by);
+#define DECL(ND, R) extern template cudaError_t launch_sweep_dense<ND, R>(const SweepArgs&, int, cudaStream_t, int);
 DECL(1, 0) DECL(1, 1) DECL(1, 2) DECL(1, 3) DECL(1, 4)
 DECL(2, 0) DECL(2, 1) DECL(2, 2) DECL(2, 3) DECL(2, 4)
 DECL(3, 0) DECL(3, 1) DECL(3, 2) DECL(3, 3) DECL(3, 4)
@@ -84,7 +84,7 @@ struct Level {
   bool unew_valid = false;
   std::vector<BoundRegion> regions;
   std::vector<PeerList> peers;
-  int ntx = 0, nty = 0, nblocks = 0;
+  int ntx = 0, nty = 0, nblocks = 0, by = 1;
   long long nwork = 0;
   double* d_part = nullptr;          // [4][nblocks_max]
   int part_cap = 0;
@@ -347,13 +347,13 @@ int check_level(int ilevel, Level** out) {
 }
 
 template <int ND>
-cudaError_t dispatch_sweep_nd(int riemann, const SweepArgs& a, int nb, cudaStream_t st) {
+cudaError_t dispatch_sweep_nd(int riemann, const SweepArgs& a, int nb, cudaStream_t st, int by) {
   switch (riemann) {
-    case RGPU_RIEMANN_LLF: return launch_sweep_dense<ND, RIEMANN_LLF>(a, nb, st);
-    case RGPU_RIEMANN_EXACT: return launch_sweep_dense<ND, RIEMANN_EXACT>(a, nb, st);
-    case RGPU_RIEMANN_ACOUSTIC: return launch_sweep_dense<ND, RIEMANN_ACOUSTIC>(a, nb, st);
-    case RGPU_RIEMANN_HLLC: return launch_sweep_dense<ND, RIEMANN_HLLC>(a, nb, st);
-    default: return launch_sweep_dense<ND, RIEMANN_HLL>(a, nb, st);
+    case RGPU_RIEMANN_LLF: return launch_sweep_dense<ND, RIEMANN_LLF>(a, nb, st, by);
+    case RGPU_RIEMANN_EXACT: return launch_sweep_dense<ND, RIEMANN_EXACT>(a, nb, st, by);
+    case RGPU_RIEMANN_ACOUSTIC: return launch_sweep_dense<ND, RIEMANN_ACOUSTIC>(a, nb, st, by);
+    case RGPU_RIEMANN_HLLC: return launch_sweep_dense<ND, RIEMANN_HLLC>(a, nb, st, by);
+    default: return launch_sweep_dense<ND, RIEMANN_HLL>(a, nb, st, by);
   }
 }
 
@@ -372,9 +372,9 @@ int launch_sweep(Level& L) {
   a.part = L.d_part;
   if (G.timing) cudaEventRecord(G.ev0, G.stream);
   cudaError_t e;
-  if (G.p.ndim == 1) e = dispatch_sweep_nd<1>(G.p.riemann, a, L.nblocks, G.stream);
-  else if (G.p.ndim == 2) e = dispatch_sweep_nd<2>(G.p.riemann, a, L.nblocks, G.stream);
-  else e = dispatch_sweep_nd<3>(G.p.riemann, a, L.nblocks, G.stream);
+  if (G.p.ndim == 1) e = dispatch_sweep_nd<1>(G.p.riemann, a, L.nblocks, G.stream, L.by);
+  else if (G.p.ndim == 2) e = dispatch_sweep_nd<2>(G.p.riemann, a, L.nblocks, G.stream, L.by);
+  else e = dispatch_sweep_nd<3>(G.p.riemann, a, L.nblocks, G.stream, L.by);
   if (e != cudaSuccess) return fail(RGPU_ECUDA, "sweep launch: %s", cudaGetErrorString(e));
   if (G.timing) {
     cudaEventRecord(G.ev1, G.stream);
@@ -691,7 +691,9 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
   }
   // ---- tile decomposition of the owned range ----------------------------------------------------
   const int bx = 32;
-  const int by = tile_by(nd, G.p.riemann);
+  int by = tile_by_default(nd, G.p.riemann);
+  if (nd == 3) { const char* e = getenv("RGPU_BY3"); if (e) { const int v = atoi(e); if (v == 8 || v == 12 || v == 16) by = v; } }
+  L.by = by;
   const int txo = bx - 2, tyo = nd > 1 ? by - 2 : 1;
   L.ntx = (g.ox1 - g.ox0 + txo - 1) / txo;
   L.nty = nd > 1 ? (g.oy1 - g.oy0 + tyo - 1) / tyo : 1;

@@ -502,19 +502,16 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
   }
 }
 
-// tile shapes (a warp = one x-row of 32 cells).  3-D: 32x12 threads (168 registers/thread, no spills) for the
-// algebraic solvers; the iterative 'exact' solver prefers 32x16 (more warps to cover its divergent Newton loop).
-// Measured on B200, 256^3: hllc 2.30 ms (32x12) vs 2.88 ms (32x16); exact 5.18 ms (32x16) vs 5.46 ms (32x12).
-template <int NDIM, int RIEMANN> struct TileShape { static constexpr int BX = 32, BY = (NDIM == 1) ? 1 : 8; };
-template <int RIEMANN> struct TileShape<3, RIEMANN> { static constexpr int BX = 32, BY = (RIEMANN == RIEMANN_EXACT) ? 16 : 12; };
-__host__ __device__ constexpr int tile_by(int ndim, int riemann) {
-  return ndim == 1 ? 1 : ndim == 2 ? 8 : (riemann == RIEMANN_EXACT ? 16 : 12);
+// tile shapes (a warp = one x-row of 32 cells): BX = 32, BY = tile height in rows (threads = 32*BY).
+// 3-D default: 12 rows (384 threads, 168 registers/thread): measured best of 8/12/16 for every solver on B200;
+// RGPU_BY3=8|12|16 overrides at bind time (tuning experiments).
+__host__ __device__ constexpr int tile_by_default(int ndim, int riemann) {
+  return ndim == 1 ? 1 : ndim == 2 ? 8 : 12;   // measured best for every solver (riemann unused)
 }
 
-// host launchers, one translation unit per NDIM
-template <int NDIM, int RIEMANN, int SLOPE>
-cudaError_t launch_sweep_dense_s(const SweepArgs& a, int nblocks, cudaStream_t st) {
-  constexpr int BX = TileShape<NDIM, RIEMANN>::BX, BY = TileShape<NDIM, RIEMANN>::BY;
+template <int NDIM, int RIEMANN, int SLOPE, int BY>
+cudaError_t launch_sweep_dense_sb(const SweepArgs& a, int nblocks, cudaStream_t st) {
+  constexpr int BX = 32;
   constexpr size_t smem = sizeof(double) * SweepSmem<NDIM, BX, BY>::doubles;
   auto kern = sweep_dense_kernel<NDIM, RIEMANN, SLOPE, BX, BY>;
   static bool configured = false;
@@ -526,12 +523,20 @@ cudaError_t launch_sweep_dense_s(const SweepArgs& a, int nblocks, cudaStream_t s
   kern<<<nblocks, dim3(BX, BY, 1), smem, st>>>(a);
   return cudaGetLastError();
 }
+template <int NDIM, int RIEMANN, int SLOPE>
+cudaError_t launch_sweep_dense_s(const SweepArgs& a, int nblocks, cudaStream_t st, int by) {
+  if (NDIM == 1) return launch_sweep_dense_sb<NDIM, RIEMANN, SLOPE, 1>(a, nblocks, st);
+  if (NDIM == 2) return launch_sweep_dense_sb<NDIM, RIEMANN, SLOPE, (NDIM == 2 ? 8 : 1)>(a, nblocks, st);
+  if (by == 8) return launch_sweep_dense_sb<NDIM, RIEMANN, SLOPE, (NDIM == 3 ? 8 : 1)>(a, nblocks, st);
+  if (by == 16) return launch_sweep_dense_sb<NDIM, RIEMANN, SLOPE, (NDIM == 3 ? 16 : 1)>(a, nblocks, st);
+  return launch_sweep_dense_sb<NDIM, RIEMANN, SLOPE, (NDIM == 3 ? 12 : 1)>(a, nblocks, st);
+}
 // slope_type 1 (minmod) and 2 (moncen) are compiled in; every other limiter goes through the runtime switch
 template <int NDIM, int RIEMANN>
-cudaError_t launch_sweep_dense(const SweepArgs& a, int nblocks, cudaStream_t st) {
-  if (a.P.slope_type == 1) return launch_sweep_dense_s<NDIM, RIEMANN, 1>(a, nblocks, st);
-  if (a.P.slope_type == 2) return launch_sweep_dense_s<NDIM, RIEMANN, 2>(a, nblocks, st);
-  return launch_sweep_dense_s<NDIM, RIEMANN, -1>(a, nblocks, st);
+cudaError_t launch_sweep_dense(const SweepArgs& a, int nblocks, cudaStream_t st, int by) {
+  if (a.P.slope_type == 1) return launch_sweep_dense_s<NDIM, RIEMANN, 1>(a, nblocks, st, by);
+  if (a.P.slope_type == 2) return launch_sweep_dense_s<NDIM, RIEMANN, 2>(a, nblocks, st, by);
+  return launch_sweep_dense_s<NDIM, RIEMANN, -1>(a, nblocks, st, by);
 }
 
 }  // namespace rgpu
