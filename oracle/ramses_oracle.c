@@ -14,12 +14,13 @@
  *   The reference is Fortran 90; neither gfortran nor MPI exists in the build
  *   image, so the reference itself cannot be compiled or run here
  *   (oracle/_ref is therefore absent).  What pins this oracle:
- *    1. tests/golden/sod_tube_ref.json  <- tests/hydro/sod-tube/sod-tube-ref.dat:
- *       the reference's own golden sums (tolerance 3e-13) for the 1-D AMR Sod
- *       tube; reproduced by tests/test_oracle_golden.py through the AMR driver
- *       oracle/amr1d.py which calls THIS library for every numerical kernel.
- *       (status is recorded in DESIGN.md; if that test is marked xfail the
- *       pin is only partial.)
+ *    1. PINNED (tolerance 3e-13, the reference's own): tests/golden/sod_tube_ref.json
+ *       <- tests/hydro/sod-tube/sod-tube-ref.dat.  tests/test_oracle_golden.py runs
+ *       the 1-D AMR Sod tube (levelmin 3, levelmax 10, hllc, moncen, sub-cycling,
+ *       interpol_type 2) through oracle/amr.py, which calls THIS library for every
+ *       floating-point routine, and reproduces all golden sums (density and pressure
+ *       log-sums to 16 digits, velocity to 3e-16, time to 2e-15, ncells/level/x
+ *       exactly) plus the mesh structure and step counts of doc/wiki/Start.md:158-187.
  *    2. tests/golden/sod_tube_ana.json  <- tests/hydro/sod-tube/sod-tube-ana.dat
  *       (exact Sod solution, 1024 points): discretisation-level check of every
  *       Riemann solver on a uniform grid.
@@ -27,8 +28,9 @@
  *       lll/mmm neighbour tables) against the generated tables below.
  *    4. invariants: conservation to round-off on periodic runs, x<->y<->z
  *       permutation symmetry, dt parity.
- *   3-D runs, riemann='exact'/'acoustic'/'hll'/'llf' have NO golden file in the
- *   reference -> for those "parity unpinned" beyond 2-4.
+ *   UNPINNED at the 3e-13 level (no golden file exists in the reference):
+ *   2-D/3-D runs, riemann='exact'/'acoustic'/'hll'/'llf', slope types other than 2 --
+ *   those rest on 2-4 and on sharing the generic-NDIM code paths pinned by 1.
  *
  * Citations are reference file:line.
  */
@@ -1403,10 +1405,101 @@ void orc_set_uold(const orc_params* p, const orc_mesh* m, int ilevel, double* uo
   }
 }
 
-/* interpol_hydro hydro/interpol_hydro.f90:268-444, interpol_var=0 and
- * interpol_type 0/1/2/3 (limiters :449-500,:618-637)                            */
-static int g_interpol_type = 1;
-void orc_set_interpol_type(int t) { g_interpol_type = t; }
+
+/* ------------------------------------------------------------------------- */
+/*                AMR pieces: getnborfather, interpol_hydro, upl              */
+/* ------------------------------------------------------------------------- */
+static int g_interpol_type = 1, g_interpol_var = 0;   /* hydro_parameters.f90:88-89 */
+void orc_set_interpol(int type, int var) { g_interpol_type = type; g_interpol_var = var; }
+
+/* getnborfather amr/nbors_utils.f90:404-525 for ONE cell of level ilevel-1 (ilevel==1: a coarse cell):
+ * ind_father[0] = the cell, ind_father[1..2*ndim] = its neighbours at the same level, or the coarser
+ * neighbouring father cell where that neighbour oct does not exist.                                   */
+void orc_getnborfather(const orc_mesh* m, int ind_cell, int ilevel, int* ind_father) {
+  const int ndim = m->ndim, nx = m->nx, ny = m->ny, nz = m->nz, nxny = nx * ny;
+  ind_father[0] = ind_cell;
+  if (ilevel == 1) {
+    const int ibound[3] = {nx - 1, ny - 1, nz - 1};
+    const int iskip1[3] = {1, nx, nxny}, iskip2[3] = {nx - 1, (ny - 1) * nx, (nz - 1) * nxny};
+    int ix[3];
+    ix[2] = (ind_cell - 1) / nxny;
+    ix[1] = (ind_cell - 1 - ix[2] * nxny) / nx;
+    ix[0] = (ind_cell - 1 - ix[1] * nx - ix[2] * nxny);
+    for (int d = 0; d < ndim; d++) {
+      ind_father[2 * d + 1] = ix[d] > 0 ? ind_cell - iskip1[d] : ind_cell + iskip2[d];
+      ind_father[2 * d + 2] = ix[d] < ibound[d] ? ind_cell + iskip1[d] : ind_cell - iskip2[d];
+    }
+    return;
+  }
+  const int pos = (ind_cell - m->ncoarse - 1) / m->ngridmax;             /* 0-based cell position */
+  const int gf = ind_cell - m->ncoarse - pos * m->ngridmax;
+  for (int d = 0; d < ndim; d++)
+    for (int s = 0; s < 2; s++) {
+      const int j = 2 * d + s + 1;
+      const int bit = (pos >> d) & 1, pos2 = pos ^ (1 << d);
+      int g;                                                               /* getnborgrids / getnborcells :363,:530 */
+      if (bit != s) g = gf; else g = m->son[NBOR(m, gf, j)];
+      ind_father[j] = g > 0 ? m->ncoarse + pos2 * m->ngridmax + g : NBOR(m, gf, j);
+    }
+}
+
+/* interpol_hydro hydro/interpol_hydro.f90:268-444 for one father cell: u1[(2*ndim+1)][nvar] -> u2[2^ndim][nvar].
+ * interpol_var 0 (conservative) only; interpol_type 0,1,2,3.                                                     */
+void orc_interpol_hydro(const orc_params* p, const double* u1, double* u2) {
+  const int ndim = p->ndim, nvar = p->nvar, twotondim = ipow2(ndim), twondim = 2 * ndim;
+  if (g_interpol_var != 0) { fprintf(stderr, "orc: interpol_var=%d not restated\n", g_interpol_var); abort(); }
+  double xc[8][3];
+  for (int ind = 0; ind < twotondim; ind++) {
+    xc[ind][0] = (double)(ind & 1) - 0.5; xc[ind][1] = (double)((ind >> 1) & 1) - 0.5; xc[ind][2] = (double)((ind >> 2) & 1) - 0.5;
+  }
+  for (int iv = 0; iv < nvar; iv++) {
+    double a[7], w[3] = {0, 0, 0};
+    for (int j = 0; j <= twondim; j++) a[j] = u1[j * nvar + iv];
+    if (g_interpol_type == 1) { /* compute_limiter_minmod :449-470 */
+      for (int d = 0; d < ndim; d++) {
+        double dl = 0.5 * (a[2 * d + 2] - a[0]), dr = 0.5 * (a[0] - a[2 * d + 1]), mm;
+        if (dl * dr <= 0.0) mm = 0; else mm = FMIN(fabs(dl), fabs(dr)) * dl / fabs(dl);
+        w[d] = mm;
+      }
+    } else if (g_interpol_type == 2) { /* compute_limiter_central :481-613 */
+      double ac[8];
+      for (int d = 0; d < ndim; d++) w[d] = 0.25 * (a[2 * d + 2] - a[2 * d + 1]);
+      for (int ind = 0; ind < twotondim; ind++) ac[ind] = a[0];
+      for (int d = 0; d < ndim; d++)
+        for (int ind = 0; ind < twotondim; ind++) ac[ind] = ac[ind] + 2.0 * w[d] * xc[ind][d];
+      double corner = ac[0], kernel = a[1];
+      for (int j = 1; j < twotondim; j++) corner = FMAX(corner, ac[j]);
+      for (int j = 2; j <= twondim; j++) kernel = FMAX(kernel, a[j]);
+      double dk = a[0] - kernel, dc = a[0] - corner, maxl = 0.0, minl = 0.0;
+      if (dk * dc > 0.0) maxl = FMIN(1.0, dk / dc);
+      corner = ac[0]; kernel = a[1];
+      for (int j = 1; j < twotondim; j++) corner = FMIN(corner, ac[j]);
+      for (int j = 2; j <= twondim; j++) kernel = FMIN(kernel, a[j]);
+      dk = a[0] - kernel; dc = a[0] - corner;
+      if (dk * dc > 0.0) minl = FMIN(1.0, dk / dc);
+      const double lim = FMIN(minl, maxl);
+      for (int d = 0; d < ndim; d++) w[d] = w[d] * lim;
+    } else if (g_interpol_type == 3) { /* compute_central :618-637 */
+      for (int d = 0; d < ndim; d++) w[d] = 0.25 * (a[2 * d + 2] - a[2 * d + 1]);
+    }
+    for (int ind = 0; ind < twotondim; ind++) { /* :372-379 */
+      double v = a[0];
+      for (int d = 0; d < ndim; d++) v = v + w[d] * xc[ind][d];
+      u2[ind * nvar + iv] = v;
+    }
+  }
+}
+
+/* prolongation of one father cell from the coarse state: what godfine1 (:583-593) and make_grid_fine
+ * (amr/refine_utils.f90:136-167) do for a missing / newly created oct                                            */
+void orc_interpol_cell(const orc_params* p, const orc_mesh* m, int ind_cell, int ilevel, const double* uold, double* u2) {
+  int fa[7];
+  double u1[7 * 16];
+  orc_getnborfather(m, ind_cell, ilevel, fa);
+  for (int j = 0; j <= 2 * p->ndim; j++)
+    for (int iv = 1; iv <= p->nvar; iv++) u1[j * p->nvar + iv - 1] = uold[(size_t)(iv - 1) * m->ncell + fa[j] - 1];
+  orc_interpol_hydro(p, u1, u2);
+}
 
 /* godfine1 hydro/godunov_fine.f90:486-911 for one batch of octs */
 static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const int* ind_grid, int ncache, int ilevel,
@@ -1427,11 +1520,8 @@ static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const 
         for (int i1 = 0; i1 <= i1max; i1++) {
           int ind_father = i1 + 3 * j1 + 9 * k1;
           int igrid_nbor = m->son[nfc[ind_father]];
-          if (igrid_nbor <= 0) {
-            fprintf(stderr, "orc godfine1: missing neighbour oct (AMR interpolation path) not restated in C; "
-                            "use oracle/amr1d.py for AMR\n");
-            abort();
-          }
+          double u2[8 * 16];
+          if (igrid_nbor <= 0) orc_interpol_cell(p, m, nfc[ind_father], ilevel, uold, u2);   /* :583-593 */
           for (int k2 = 0; k2 <= k2max; k2++)
             for (int j2 = 0; j2 <= j2max; j2++)
               for (int i2 = 0; i2 <= i2max; i2++) {
@@ -1441,8 +1531,13 @@ static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const 
                 if (ndim > 1) j3 = 1 + 2 * (j1 - 1) + j2;
                 if (ndim > 2) k3 = 1 + 2 * (k1 - 1) + k2;
                 size_t x = PIX(w, i, i3, j3, k3);
-                for (int iv = 1; iv <= nvar; iv++) w->uloc[(iv - 1) * np + x] = UO(ic, iv);
-                w->ok[x] = m->son[ic] > 0; /* :661-663 */
+                if (igrid_nbor > 0) {
+                  for (int iv = 1; iv <= nvar; iv++) w->uloc[(iv - 1) * np + x] = UO(ic, iv);
+                  w->ok[x] = m->son[ic] > 0; /* :661-663 */
+                } else {
+                  for (int iv = 1; iv <= nvar; iv++) w->uloc[(iv - 1) * np + x] = u2[ind_son * nvar + iv - 1];
+                  w->ok[x] = 0;               /* :664-666 */
+                }
               }
         }
   }
@@ -1632,6 +1727,67 @@ void orc_run_uniform(const orc_params* p, const orc_mesh* m, int ilevel, int nst
   if (t_io) *t_io = t;
 }
 
+/* upload_fine hydro/interpol_hydro.f90:5-68 + upl :73-263 (interpol_var=0) */
 void orc_upload_fine(const orc_params* p, const orc_mesh* m, int ilevel, double* uold) {
-  (void)p; (void)m; (void)ilevel; (void)uold; /* restriction: AMR only; see oracle/amr1d.py */
+  const int twotondim = ipow2(p->ndim), nvar = p->nvar;
+  if (ilevel == m->nlevelmax) return;
+  for (int a = 0; a < m->nactive[ilevel]; a++)
+    for (int ind = 0; ind < twotondim; ind++) {
+      const int ic = m->ncoarse + ind * m->ngridmax + m->active[ilevel][a];
+      const int gs = m->son[ic];
+      if (gs <= 0) continue;
+      double getx = 0.0;
+      for (int is = 0; is < twotondim; is++) getx = getx + FMAX(UO(m->ncoarse + is * m->ngridmax + gs, 1), p->smallr);
+      UO(ic, 1) = getx / (double)twotondim;
+      for (int iv = 2; iv <= nvar; iv++) {
+        getx = 0.0;
+        for (int is = 0; is < twotondim; is++) getx = getx + UO(m->ncoarse + is * m->ngridmax + gs, iv);
+        UO(ic, iv) = getx / (double)twotondim;
+      }
+    }
+}
+
+/* an empty mesh (coarse grid only) whose tree arrays the AMR driver (oracle/amr.py) fills in like
+ * amr/refine_utils.f90 does; lists are pushed with orc_mesh_set_list                                 */
+orc_mesh* orc_mesh_new(int ndim, const int bt[6], int ngridmax, int nlevelmax) {
+  orc_mesh* m = (orc_mesh*)calloc(1, sizeof(orc_mesh));
+  m->ndim = ndim; m->nlevelmax = nlevelmax;
+  int nn[3] = {1, 1, 1}, cmin[3] = {0, 0, 0}, cmax[3] = {0, 0, 0};
+  for (int d = 0; d < ndim; d++)
+    for (int s2 = 0; s2 < 2; s2++)
+      if (bt[2 * d + s2] > 0) {
+        nn[d]++;
+        if (s2 == 0) { cmin[d]++; cmax[d]++; }
+        m->boundary_type[m->nboundary] = (bt[2 * d + s2] - 1) * 10 + (2 * d + s2 + 1);
+        m->nboundary++;
+      }
+  m->nx = nn[0]; m->ny = nn[1]; m->nz = nn[2];
+  m->icoarse_min = cmin[0]; m->icoarse_max = cmax[0]; m->jcoarse_min = cmin[1]; m->jcoarse_max = cmax[1];
+  m->kcoarse_min = cmin[2]; m->kcoarse_max = cmax[2];
+  m->ncoarse = nn[0] * nn[1] * nn[2];
+  m->ngridmax = ngridmax;
+  m->ncell = m->ncoarse + ipow2(ndim) * ngridmax;
+  m->son = (int*)calloc((size_t)m->ncell + 1, sizeof(int));
+  m->cpu_map = (int*)calloc((size_t)m->ncell + 1, sizeof(int));
+  m->father = (int*)calloc((size_t)ngridmax + 1, sizeof(int));
+  m->nbor = (int*)calloc((size_t)2 * ndim * (ngridmax + 1), sizeof(int));
+  m->xg = (double*)calloc((size_t)ndim * (ngridmax + 1), sizeof(double));
+  m->nactive = (int*)calloc(nlevelmax + 2, sizeof(int));
+  m->active = (int**)calloc(nlevelmax + 2, sizeof(int*));
+  m->nrecv = (int*)calloc(nlevelmax + 2, sizeof(int));
+  m->recv = (int**)calloc(nlevelmax + 2, sizeof(int*));
+  for (int b = 0; b < ORC_MAXBOUND; b++) {
+    m->nbound[b] = (int*)calloc(nlevelmax + 2, sizeof(int));
+    m->bound[b] = (int**)calloc(nlevelmax + 2, sizeof(int*));
+  }
+  return m;
+}
+/* kind 0: active(ilevel), kind 1: boundary(b,ilevel) */
+void orc_mesh_set_list(orc_mesh* m, int kind, int b, int ilevel, int n, const int* igrid) {
+  int** slot = kind == 0 ? &m->active[ilevel] : &m->bound[b][ilevel];
+  int* cnt = kind == 0 ? &m->nactive[ilevel] : &m->nbound[b][ilevel];
+  free(*slot);
+  *slot = (int*)malloc(sizeof(int) * (size_t)(n + 1));
+  memcpy(*slot, igrid, sizeof(int) * (size_t)n);
+  *cnt = n;
 }

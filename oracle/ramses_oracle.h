@@ -125,6 +125,14 @@ void orc_upload_fine(const orc_params*, const orc_mesh*, int ilevel, double* uol
 void orc_run_uniform(const orc_params*, const orc_mesh*, int ilevel, int nstep,
                      double* uold, double* unew, double* dt_hist, double* t_io, int nthreads);
 
+/* AMR pieces (hydro/interpol_hydro.f90, amr/nbors_utils.f90:404) */
+void orc_set_interpol(int interpol_type, int interpol_var);
+void orc_getnborfather(const orc_mesh*, int ind_cell, int ilevel, int* ind_father /*[2*ndim+1]*/);
+void orc_interpol_hydro(const orc_params*, const double* u1 /*[2*ndim+1][nvar]*/, double* u2 /*[2^ndim][nvar]*/);
+void orc_interpol_cell(const orc_params*, const orc_mesh*, int ind_cell, int ilevel, const double* uold, double* u2);
+orc_mesh* orc_mesh_new(int ndim, const int bound_type[6], int ngridmax, int nlevelmax);
+void orc_mesh_set_list(orc_mesh*, int kind, int b, int ilevel, int n, const int* igrid);
+
 int orc_abi_version(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,44 @@
+"""The oracle reproduces the reference's own golden sums (tests/hydro/sod-tube/sod-tube-ref.dat, tolerance 3e-13 as in
+tests/visu/visu_ramses.py:497) for the 1-D AMR Sod tube: levelmin=3, levelmax=10, hllc, moncen, reflexive walls,
+sub-cycling nsubcycle=3*1,2, interpol_type=2, err_grad_{d,u,p}=0.05 -- every floating-point routine of the C oracle on
+the path (ctoprim, uslope, trace1d, cmpflxm, riemann_hllc, godfine1 gather + interpol_hydro + coarse refluxing, cmpdt /
+courant_fine, set_unew / set_uold, upload_fine, make_boundary_hydro, condinit) is exercised by oracle/amr.py."""
+import json
+import os
+
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SOD = [dict(type="square", x_center=0.25, length_x=0.5, d=1.0, p=1.0),
+       dict(type="square", x_center=0.75, length_x=0.5, d=0.125, p=0.1)]       # tests/hydro/sod-tube/sod-tube.nml
+
+
+@pytest.fixture(scope="module")
+def sod_run(orc):
+    from oracle.amr import AmrRun
+    r = AmrRun(1, 3, 10, (1, 1, 0, 0, 0, 0), 1.0, nsubcycle=[1, 1, 1, 2], nexpand=1, ngridmax=2000, riemann="hllc",
+               slope_type=2, gamma=1.4, courant_factor=0.8, err_grad_d=0.05, err_grad_u=0.05, err_grad_p=0.05,
+               interpol_type=2, interpol_var=0, regions=SOD, tout=[0.245])
+    snap = r.run()
+    return r, snap
+
+
+def test_sod_tube_golden_sums(sod_run):
+    from oracle.amr import check_sums
+    r, snap = sod_run
+    ref = json.load(open(os.path.join(GOLD, "sod_tube_ref.json")))
+    sums = check_sums(snap["rows"], 1)
+    sums["time"] = snap["t"]
+    tol = 3.0e-13                                 # var_tol["all"], tests/visu/visu_ramses.py:497
+    for key in ("ncells", "level", "x", "density", "pressure", "velocity_x", "time"):
+        err = abs(sums[key] - ref[key]) / min(abs(sums[key]), abs(ref[key]))
+        assert err <= tol, (key, sums[key], ref[key], err)
+
+
+def test_sod_tube_mesh_structure_and_step_counts(sod_run):
+    """doc/wiki/Start.md:158-187: initial and final mesh structure, 43 main steps, 688 fine steps of the same run."""
+    r, snap = sod_run
+    assert [r.initial_grids[l] for l in range(1, 9)] == [1, 2, 4, 8, 8, 8, 8, 8]
+    assert [snap["grids"][l] for l in range(1, 11)] == [1, 2, 4, 8, 16, 27, 37, 17, 16, 13]
+    assert snap["nstep_coarse"] == 43 and snap["nstep"] == 688
+    assert abs(snap["t"] - 2.45047e-01) < 5e-7
