@@ -73,6 +73,13 @@ int rgpu_abi_version(void);
  * rgpu_bind_tree (the library reads them inside rgpu_bind_level only).         */
 int rgpu_bind_tree(int ncoarse, int ngridmax, const int* son, const int* father, const int* nbor);
 
+/* AMR mode (levelmin < nlevelmax): call once after rgpu_init and before rgpu_bind_tree.  The device then mirrors
+ * son/father/nbor and the whole uold/unew arrays; every level is processed as a list of octs by the oct-batch kernel
+ * (godfine1 with interpol_hydro ghost prolongation, flux masking and coarse refluxing, hydro/godunov_fine.f90:486-911).
+ * interpol_type / interpol_var: &REFINE_PARAMS (hydro/hydro_parameters.f90:88-89); interpol_var must be 0.
+ * In this mode rgpu_upload_state / rgpu_download_state move the WHOLE arrays (ilevel ignored).                       */
+int rgpu_set_amr(int on, int interpol_type, int interpol_var);
+
 /* ---- per-level communicator lists (amr/amr_commons.f90:108-119,170-180; built
  * by build_comm, amr/virtual_boundaries.f90:1286) ------------------------------
  * igrid_* are the %igrid arrays (1-based oct indices).  recv/emit are indexed by
@@ -121,6 +128,7 @@ int rgpu_courant_fine(int ilevel, double* dt_io, double sums[3]);
 int rgpu_make_boundary_hydro(int ilevel);                  /* hydro/hydro_boundary.f90:5       */
 int rgpu_make_virtual_fine(int ilevel);                    /* amr/virtual_boundaries.f90:373, all nvar at once */
 int rgpu_make_virtual_reverse(int ilevel);                 /* amr/virtual_boundaries.f90:693   */
+int rgpu_upload_fine(int ilevel);                          /* hydro/interpol_hydro.f90:5 (restriction of split cells) */
 
 /* ---- fused fast path --------------------------------------------------------------
  * nstep level steps of a levelmin=levelmax run in amr_step order

@@ -70,6 +70,7 @@ class AmrRun:
         self.snapshot = None
         self.iout = 0
         self.log = []
+        self.static = False      # static=.true. (amr_parameters): no regridding inside amr_step
 
     # ------------------------------------------------------------------ helpers
     def cell(self, ind, ig):
@@ -518,7 +519,7 @@ class AmrRun:
         """amr/amr_step.f90"""
         if self.numbtot(l) == 0 or self.done:
             return
-        if self.levelmin < self.nlevelmax:
+        if self.levelmin < self.nlevelmax and not self.static:
             if l == self.levelmin or icount > 1:
                 for i in range(l, self.nlevelmax + 1):
                     if i > self.levelmin:
@@ -552,7 +553,8 @@ class AmrRun:
         self.L.orc_set_uold(C.byref(self.p), self.mp, l, orc.dptr(self.uold), orc.dptr(self.unew))          # :423
         self.upload_fine(l)                                                                                  # :441
         self.make_boundary_hydro(l)                                                                          # :514
-        self.flag_fine(l, icount)                                                                            # :531
+        if not self.static:
+            self.flag_fine(l, icount)                                                                        # :531
         if l > self.levelmin:
             if self.nsubcycle[l - 1] == 1:
                 self.dtnew[l - 1] = self.dtnew[l]

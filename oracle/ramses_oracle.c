@@ -1571,27 +1571,37 @@ static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const 
             }
         }
   }
-  /* conservative update at level ilevel-1 :798-908 */
+  /* conservative update at level ilevel-1 :798-908.  Loop order of the reference: variable, then face, then the
+   * octs of the batch that sit at a coarse-fine boundary (several octs may reflux into the same coarse cell). */
   for (int idim = 0; idim < ndim; idim++) {
     int i0 = idim == 0, j0 = idim == 1, k0 = idim == 2;
-    for (int i = 0; i < ncache; i++) { /* left :811-829 */
+    int nb_noneigh = 0;
+    int* ind_buffer = (int*)malloc(sizeof(int) * (size_t)(ncache + 1));
+    int* ind_cell = (int*)malloc(sizeof(int) * (size_t)(ncache + 1));
+    for (int i = 0; i < ncache; i++) { /* left :811-817 */
       int nb = NBOR(m, ind_grid[i], 2 * idim + 1);
-      if (m->son[nb] == 0)
-        for (int iv = 1; iv <= nvar; iv++)
-          for (int k3 = k3min; k3 <= k3max - k0; k3++)
-            for (int j3 = j3min; j3 <= j3max - j0; j3++)
-              for (int i3 = i3min; i3 <= i3max - i0; i3++)
-                UN(nb, iv) = UN(nb, iv) - w->flux[((iv - 1) + (size_t)idim * nvar) * nfp + FIX(w, i, i3, j3, k3)] * oneontwotondim;
+      if (m->son[nb] == 0) { ind_buffer[nb_noneigh] = nb; ind_cell[nb_noneigh] = i; nb_noneigh++; }
     }
-    for (int i = 0; i < ncache; i++) { /* right :863-881 */
+    for (int iv = 1; iv <= nvar; iv++)
+      for (int k3 = k3min; k3 <= k3max - k0; k3++)
+        for (int j3 = j3min; j3 <= j3max - j0; j3++)
+          for (int i3 = i3min; i3 <= i3max - i0; i3++)
+            for (int i = 0; i < nb_noneigh; i++)
+              UN(ind_buffer[i], iv) = UN(ind_buffer[i], iv) -
+                  w->flux[((iv - 1) + (size_t)idim * nvar) * nfp + FIX(w, ind_cell[i], i3, j3, k3)] * oneontwotondim;
+    nb_noneigh = 0;
+    for (int i = 0; i < ncache; i++) { /* right :863-869 */
       int nb = NBOR(m, ind_grid[i], 2 * idim + 2);
-      if (m->son[nb] == 0)
-        for (int iv = 1; iv <= nvar; iv++)
-          for (int k3 = k3min + k0; k3 <= k3max; k3++)
-            for (int j3 = j3min + j0; j3 <= j3max; j3++)
-              for (int i3 = i3min + i0; i3 <= i3max; i3++)
-                UN(nb, iv) = UN(nb, iv) + w->flux[((iv - 1) + (size_t)idim * nvar) * nfp + FIX(w, i, i3 + i0, j3 + j0, k3 + k0)] * oneontwotondim;
+      if (m->son[nb] == 0) { ind_buffer[nb_noneigh] = nb; ind_cell[nb_noneigh] = i; nb_noneigh++; }
     }
+    for (int iv = 1; iv <= nvar; iv++)
+      for (int k3 = k3min + k0; k3 <= k3max; k3++)
+        for (int j3 = j3min + j0; j3 <= j3max; j3++)
+          for (int i3 = i3min + i0; i3 <= i3max; i3++)
+            for (int i = 0; i < nb_noneigh; i++)
+              UN(ind_buffer[i], iv) = UN(ind_buffer[i], iv) +
+                  w->flux[((iv - 1) + (size_t)idim * nvar) * nfp + FIX(w, ind_cell[i], i3 + i0, j3 + j0, k3 + k0)] * oneontwotondim;
+    free(ind_buffer); free(ind_cell);
   }
 }
 

@@ -1,0 +1,557 @@
+// amr_kernels.cuh -- oct-batch kernels for levels that are NOT dense boxes (levelmin < levelmax runs).
+//
+// In AMR mode the device mirrors the reference's own arrays: son(1:ncell), father(1:ngridmax),
+// nbor(1:ngridmax,1:2*ndim) (amr/amr_commons.f90:68-79) and uold/unew(1:ncell,1:nvar) in the Fortran
+// layout (hydro/hydro_commons.f90:4), so every index below is the reference's cell / oct index
+// (icell = ncoarse + (ind-1)*ngridmax + igrid).  One group of 64 threads reproduces godfine1
+// (hydro/godunov_fine.f90:486-911) for one oct:
+//   get3cubefather (amr/nbors_utils.f90:5) -> 6^ndim patch gather, with interpol_hydro
+//   (hydro/interpol_hydro.f90:268) prolongation of missing neighbour octs from the coarser level ->
+//   ctoprim / uslope / trace / cmpflxm+Riemann on the patch (same device functions as the dense sweep) ->
+//   flux masking at refined faces (:720-747) -> update of the oct's own cells (:751-792); the fluxes through
+//   the oct's outer faces are stored, and a second kernel refluxes them into the coarser level (:798-908) in the
+//   reference's accumulation order (deterministic, no atomics).
+#pragma once
+#include "hydro_device.cuh"
+
+namespace rgpu {
+
+struct AmrTree {
+  const int* son;      // 1-based: son[icell]
+  const int* father;   // 1-based: father[igrid]
+  const int* nbor;     // nbor[(j-1)*ngridmax + igrid-1], j = 1..2*ndim
+  int ncoarse, ngridmax, nx, ny, nz;
+  long long ncell;
+};
+
+__device__ __forceinline__ int amr_nbor(const AmrTree& t, int igrid, int j) { return t.nbor[(size_t)(j - 1) * t.ngridmax + igrid - 1]; }
+__device__ __forceinline__ int amr_cell(const AmrTree& t, int ind0, int igrid) { return t.ncoarse + ind0 * t.ngridmax + igrid; }
+
+// getnborfather (amr/nbors_utils.f90:404-525) for one cell of level ilevel-1
+template <int NDIM>
+__device__ void amr_getnborfather(const AmrTree& t, int ind_cell, int ilevel, int* fa) {
+  fa[0] = ind_cell;
+  if (ilevel == 1) {
+    const int nn[3] = {t.nx, t.ny, t.nz};
+    const int s1[3] = {1, t.nx, t.nx * t.ny};
+    int ix[3];
+    ix[2] = (ind_cell - 1) / (t.nx * t.ny);
+    ix[1] = (ind_cell - 1 - ix[2] * t.nx * t.ny) / t.nx;
+    ix[0] = ind_cell - 1 - ix[1] * t.nx - ix[2] * t.nx * t.ny;
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) {
+      fa[2 * d + 1] = ix[d] > 0 ? ind_cell - s1[d] : ind_cell + (nn[d] - 1) * s1[d];
+      fa[2 * d + 2] = ix[d] < nn[d] - 1 ? ind_cell + s1[d] : ind_cell - (nn[d] - 1) * s1[d];
+    }
+    return;
+  }
+  const int pos = (ind_cell - t.ncoarse - 1) / t.ngridmax;
+  const int gf = ind_cell - t.ncoarse - pos * t.ngridmax;
+#pragma unroll
+  for (int d = 0; d < NDIM; d++)
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      const int j = 2 * d + s + 1;
+      const int bit = (pos >> d) & 1, pos2 = pos ^ (1 << d);
+      const int nb = amr_nbor(t, gf, j);
+      const int g = (bit != s) ? gf : t.son[nb];
+      fa[j] = g > 0 ? amr_cell(t, pos2, g) : nb;
+    }
+}
+
+// interpol_hydro (hydro/interpol_hydro.f90:268-444, interpol_var = 0) for ONE variable: a[0..2*ndim] -> u2[2^ndim]
+template <int NDIM>
+__device__ void amr_interpol_var(const double* a, int interpol_type, double* u2) {
+  constexpr int T = 1 << NDIM, TW = 2 * NDIM;
+  double w[3] = {0, 0, 0};
+  if (interpol_type == 1) {            // compute_limiter_minmod :449
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) {
+      const double dl = 0.5 * (a[2 * d + 2] - a[0]), dr = 0.5 * (a[0] - a[2 * d + 1]);
+      double mm;
+      if (dl * dr <= 0.0) mm = 0; else mm = fmn(fabs(dl), fabs(dr)) * dl / fabs(dl);
+      w[d] = mm;
+    }
+  } else if (interpol_type == 2) {     // compute_limiter_central :481
+    double ac[T];
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) w[d] = 0.25 * (a[2 * d + 2] - a[2 * d + 1]);
+#pragma unroll
+    for (int i = 0; i < T; i++) ac[i] = a[0];
+#pragma unroll
+    for (int d = 0; d < NDIM; d++)
+#pragma unroll
+      for (int i = 0; i < T; i++) ac[i] = ac[i] + 2.0 * w[d] * ((double)((i >> d) & 1) - 0.5);
+    double corner = ac[0], kernel = a[1];
+#pragma unroll
+    for (int j = 1; j < T; j++) corner = fmx(corner, ac[j]);
+#pragma unroll
+    for (int j = 2; j <= TW; j++) kernel = fmx(kernel, a[j]);
+    double dk = a[0] - kernel, dc = a[0] - corner, maxl = 0.0, minl = 0.0;
+    if (dk * dc > 0.0) maxl = fmn(1.0, dk / dc);
+    corner = ac[0]; kernel = a[1];
+#pragma unroll
+    for (int j = 1; j < T; j++) corner = fmn(corner, ac[j]);
+#pragma unroll
+    for (int j = 2; j <= TW; j++) kernel = fmn(kernel, a[j]);
+    dk = a[0] - kernel; dc = a[0] - corner;
+    if (dk * dc > 0.0) minl = fmn(1.0, dk / dc);
+    const double lim = fmn(minl, maxl);
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) w[d] = w[d] * lim;
+  } else if (interpol_type == 3) {     // compute_central :618
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) w[d] = 0.25 * (a[2 * d + 2] - a[2 * d + 1]);
+  }
+#pragma unroll
+  for (int i = 0; i < T; i++) {
+    double v = a[0];
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) v = v + w[d] * ((double)((i >> d) & 1) - 0.5);
+    u2[i] = v;
+  }
+}
+
+struct AmrSweepArgs {
+  AmrTree t;
+  const int* active;      // active(ilevel)%igrid
+  int nact, ilevel;
+  const double* uold;     // [nvar][ncell]
+  double* unew;
+  double* rflux;          // [nact][2*ndim sides][2^(ndim-1) faces][nvar]: scaled, masked fluxes through the oct's outer faces
+  Phys P;
+  double dt, dx, inv_dx;
+  int dx_pow2, interpol_type;
+};
+
+constexpr int AMR_TPO = 64;   // threads per oct
+constexpr int AMR_OPB = 1;    // octs per block (26 KB of static shared memory per oct in 3-D)
+
+template <int NDIM, int RIEMANN>
+__global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const AmrSweepArgs a) {
+  constexpr int NV = NDIM + 2, T = 1 << NDIM, TW = 2 * NDIM;
+  constexpr int N3 = (NDIM == 1) ? 3 : (NDIM == 2 ? 9 : 27);
+  constexpr int HY = NDIM > 1, HZ = NDIM > 2;
+  constexpr int PJ = HY ? 6 : 1, PK = HZ ? 6 : 1;          // patch extents (i: 6)
+  constexpr int NP = 6 * PJ * PK;                          // patch cells
+  constexpr int TJ = HY ? 4 : 1, TK = HZ ? 4 : 1;          // trace region 0..3
+  constexpr int NTR = 4 * TJ * TK;
+  constexpr int FJ = HY ? 2 : 1, FK = HZ ? 2 : 1;          // faces per direction: 3 * 2^(ndim-1)
+  constexpr int NF = 3 * FJ * FK;
+  constexpr int NSF = FJ * FK;                             // faces per side
+  struct Sm {
+    double q[NV][NP];           // uloc, then primitive variables
+    unsigned char ok[NP];
+    double qm[NDIM][NV][NTR], qp[NDIM][NV][NTR];
+    double flux[NDIM][NV][NF];
+    int nfc[27], gnb[27], ng[8];
+  };
+  __shared__ Sm sm_[AMR_OPB];
+  const int grp = threadIdx.x / AMR_TPO, tl = threadIdx.x % AMR_TPO;
+  const int io = blockIdx.x * AMR_OPB + grp;
+  const bool live = io < a.nact;
+  Sm& s = sm_[grp];
+  const AmrTree& t = a.t;
+  const Phys& P = a.P;
+  const size_t NC = (size_t)t.ncell;
+  const int igrid = live ? a.active[io] : 0;
+  auto UO = [&](int icell, int iv) -> double { return a.uold[(size_t)iv * NC + icell - 1]; };
+
+  // ---- get3cubefather (amr/nbors_utils.f90:5-194, get3cubepos :199) ----
+  if (live && tl == 0) {
+    const int fc = t.father[igrid];
+    if (a.ilevel == 1) {
+      const int nxny = t.nx * t.ny;
+      const int iz = (fc - 1) / nxny, iy = (fc - 1 - iz * nxny) / t.nx, ix = fc - 1 - iy * t.nx - iz * nxny;
+      for (int j = 0; j < N3; j++) {
+        int o[3] = {j % 3 - 1, (j / 3) % 3 - 1, (j / 9) % 3 - 1};
+        int iix = ix + o[0], iiy = iy, iiz = iz;
+        if (iix < 0) iix = t.nx - 1; if (iix > t.nx - 1) iix = 0;
+        if (NDIM > 1) { iiy = iy + o[1]; if (iiy < 0) iiy = t.ny - 1; if (iiy > t.ny - 1) iiy = 0; }
+        if (NDIM > 2) { iiz = iz + o[2]; if (iiz < 0) iiz = t.nz - 1; if (iiz > t.nz - 1) iiz = 0; }
+        s.nfc[j] = 1 + iix + iiy * t.nx + iiz * nxny;
+      }
+    } else {
+      const int pos = (fc - t.ncoarse - 1) / t.ngridmax;
+      const int gf = fc - t.ncoarse - pos * t.ngridmax;
+      const int dirx = (pos & 1) ? 2 : 1, diry = ((pos >> 1) & 1) ? 4 : 3, dirz = ((pos >> 2) & 1) ? 6 : 5;
+      for (int kk = 0; kk <= HZ; kk++) {
+        int g1 = gf;
+        if (kk > 0 && gf > 0) g1 = t.son[amr_nbor(t, gf, dirz)];
+        for (int jj = 0; jj <= HY; jj++) {
+          int g2 = g1;
+          if (jj > 0 && g1 > 0) g2 = t.son[amr_nbor(t, g1, diry)];
+          for (int ii = 0; ii <= 1; ii++) {
+            int g3 = g2;
+            if (ii > 0 && g2 > 0) g3 = t.son[amr_nbor(t, g2, dirx)];
+            s.ng[ii + 2 * jj + 4 * kk] = g3;
+          }
+        }
+      }
+      const int c[3] = {pos & 1, (pos >> 1) & 1, (pos >> 2) & 1};
+      for (int j = 0; j < N3; j++) {
+        const int o[3] = {j % 3 - 1, (j / 3) % 3 - 1, (j / 9) % 3 - 1};
+        int gi = 0, cp = 0;
+        for (int d = 0; d < NDIM; d++) {
+          const int tt = c[d] + o[d];
+          gi += ((tt < 0 || tt > 1) ? 1 : 0) << d;
+          cp += (tt & 1) << d;
+        }
+        const int g = s.ng[gi];
+        s.nfc[j] = g > 0 ? amr_cell(t, cp, g) : 0;
+      }
+    }
+    for (int j = 0; j < N3; j++) s.gnb[j] = s.nfc[j] > 0 ? t.son[s.nfc[j]] : 0;
+  }
+  __syncthreads();
+
+  // ---- gather the 6^ndim patch (hydro/godunov_fine.f90:562-675) ----
+  if (live) {
+    // existing neighbour octs: straight copy
+    for (int e = tl; e < N3 * T; e += AMR_TPO) {
+      const int jf = e / T, is = e % T;
+      const int g = s.gnb[jf];
+      if (g <= 0) continue;
+      const int i1 = jf % 3, j1 = (jf / 3) % 3, k1 = jf / 9;
+      const int i3 = 1 + 2 * (i1 - 1) + (is & 1), j3 = HY ? 1 + 2 * (j1 - 1) + ((is >> 1) & 1) : 1, k3 = HZ ? 1 + 2 * (k1 - 1) + ((is >> 2) & 1) : 1;
+      const int pc = (i3 + 1) + 6 * ((HY ? j3 + 1 : 0) + PJ * (HZ ? k3 + 1 : 0));
+      const int ic = amr_cell(t, is, g);
+#pragma unroll
+      for (int n = 0; n < NV; n++) s.q[n][pc] = UO(ic, n);
+      s.ok[pc] = t.son[ic] > 0;
+    }
+    // missing neighbour octs: interpol_hydro from the coarser level, one thread per (father, variable)
+    for (int e = tl; e < N3 * NV; e += AMR_TPO) {
+      const int jf = e / NV, n = e % NV;
+      if (s.gnb[jf] > 0) continue;
+      int fa[7];
+      amr_getnborfather<NDIM>(t, s.nfc[jf], a.ilevel, fa);
+      double av[7], u2[T];
+#pragma unroll
+      for (int j = 0; j <= TW; j++) av[j] = UO(fa[j], n);
+      amr_interpol_var<NDIM>(av, a.interpol_type, u2);
+      const int i1 = jf % 3, j1 = (jf / 3) % 3, k1 = jf / 9;
+#pragma unroll
+      for (int is = 0; is < T; is++) {
+        const int i3 = 1 + 2 * (i1 - 1) + (is & 1), j3 = HY ? 1 + 2 * (j1 - 1) + ((is >> 1) & 1) : 1, k3 = HZ ? 1 + 2 * (k1 - 1) + ((is >> 2) & 1) : 1;
+        const int pc = (i3 + 1) + 6 * ((HY ? j3 + 1 : 0) + PJ * (HZ ? k3 + 1 : 0));
+        s.q[n][pc] = u2[is];
+        if (n == 0) s.ok[pc] = 0;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- ctoprim on the whole patch (hydro/umuscl.f90:861) ----
+  if (live)
+    for (int pc = tl; pc < NP; pc += AMR_TPO) {
+      double u[NV], q[NV];
+#pragma unroll
+      for (int n = 0; n < NV; n++) u[n] = s.q[n][pc];
+      const double r = fmax(u[0], P.smallr);
+      const double oneoverrho = rcp_rn(r);
+      q[0] = r;
+      double eken;
+      q[1] = u[1] * oneoverrho;
+      eken = 0.5 * q[1] * q[1];
+      if (NDIM > 1) { q[2] = u[2] * oneoverrho; eken = eken + 0.5 * q[2] * q[2]; }
+      if (NDIM > 2) { q[3] = u[3] * oneoverrho; eken = eken + 0.5 * q[3] * q[3]; }
+      const double eint = fmax(u[NDIM + 1] * oneoverrho - eken - 0.0, P.smalle);
+      q[NDIM + 1] = (P.gamma - 1.0) * r * eint;
+      q[1] = q[1] + 0.0;
+      if (NDIM > 1) q[2] = q[2] + 0.0;
+      if (NDIM > 2) q[3] = q[3] + 0.0;
+#pragma unroll
+      for (int n = 0; n < NV; n++) s.q[n][pc] = q[n];
+    }
+  __syncthreads();
+  // ---- uslope + trace on cells 0..3 (hydro/umuscl.f90:970, :176/:305/:483) ----
+  const double dtdx = a.dt / a.dx;
+  if (live)
+    for (int tc = tl; tc < NTR; tc += AMR_TPO) {
+      const int i = tc % 4, j = HY ? (tc / 4) % 4 : 1, k = HZ ? tc / 16 : 1;        // patch coordinates 0..3 (1-D/2-D: fixed 1)
+      const int pc = (i + 1) + 6 * ((HY ? j + 1 : 0) + PJ * (HZ ? k + 1 : 0));
+      constexpr int SJ = 6, SK = 6 * PJ;
+      double q[NV], dq[NDIM][NV];
+#pragma unroll
+      for (int n = 0; n < NV; n++) q[n] = s.q[n][pc];
+      if (P.slope_type == 3 && NDIM > 1) {
+#pragma unroll
+        for (int n = 0; n < NV; n++) {
+          const double* qn = &s.q[n][pc];
+          double vmin = 0, vmax = 0;
+          bool first = true;
+          for (int cc = (HZ ? -1 : 0); cc <= (HZ ? 1 : 0); cc++)
+            for (int aa = -1; aa <= 1; aa++)
+              for (int bb = -1; bb <= 1; bb++) {
+                const double d = qn[aa + bb * SJ + cc * SK] - q[n];
+                if (first) { vmin = d; vmax = d; first = false; }
+                else { vmin = fmn(vmin, d); vmax = fmx(vmax, d); }
+              }
+          const double dfx = 0.5 * (qn[1] - qn[-1]);
+          const double dfy = 0.5 * (qn[SJ] - qn[-SJ]);
+          double dfz = 0, dff;
+          if (HZ) { dfz = 0.5 * (qn[SK] - qn[-SK]); dff = 0.5 * (fabs(dfx) + fabs(dfy) + fabs(dfz)); }
+          else dff = 0.5 * (fabs(dfx) + fabs(dfy));
+          double slop;
+          if (dff > 0.0) slop = fmn(1.0, fdiv(fmn(fabs(vmin), fabs(vmax)), dff));
+          else slop = 1.0;
+          dq[0][n] = slop * dfx;
+          dq[HY][n] = slop * dfy;
+          if (HZ) dq[NDIM - 1][n] = slop * dfz;
+        }
+      } else if (NDIM == 1 && P.slope_type >= 4 && P.slope_type <= 6) {
+        const double uvel = q[1];
+#pragma unroll
+        for (int n = 0; n < NV; n++) {
+          const double qL = s.q[n][pc - 1], qC = q[n], qR = s.q[n][pc + 1];
+          double r;
+          if (P.slope_type == 4) {
+            const double dcen = uvel * a.dt / a.dx;
+            const double dlft = 2.0 / (1.0 + dcen) * (qC - qL), drgt = 2.0 / (1.0 - dcen) * (qR - qC);
+            double dlim = fmn(fabs(dlft), fabs(drgt));
+            if ((dlft * drgt) <= 0.0) dlim = 0.0;
+            r = fsign1(dlft) * dlim;
+          } else if (P.slope_type == 5) {
+            if (n == 0) {
+              const double dcen = uvel * a.dt / a.dx;
+              double dlft, drgt;
+              if (dcen >= 0) { dlft = 2.0 / (0.0 + dcen + 1e-10) * (qC - qL); drgt = 2.0 / (1.0 - dcen) * (qR - qC); }
+              else { dlft = 2.0 / (1.0 + dcen) * (qC - qL); drgt = 2.0 / (0.0 - dcen + 1e-10) * (qR - qC); }
+              double dlim = fmn(fabs(dlft), fabs(drgt));
+              if ((dlft * drgt) <= 0.0) dlim = 0.0;
+              r = fsign1(dlft) * dlim;
+            } else r = 0;
+          } else {
+            if (n == 0) r = 0.5 * ((qC - qL) + (qR - qC)); else r = 0;
+          }
+          dq[0][n] = r;
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < NV; n++) {
+          const double* qn = &s.q[n][pc];
+          dq[0][n] = slope_lcr<NDIM, -1>(qn[-1], q[n], qn[1], P);
+          if (HY) dq[HY][n] = slope_lcr<NDIM, -1>(qn[-SJ], q[n], qn[SJ], P);
+          if (HZ) dq[NDIM - 1][n] = slope_lcr<NDIM, -1>(qn[-SK], q[n], qn[SK], P);
+        }
+      }
+      double s0[NV];
+      trace_sources<NDIM>(q, dq, rcp_rn(q[0]), s0, P);
+#pragma unroll
+      for (int d = 0; d < NDIM; d++) {
+#pragma unroll
+        for (int n = 0; n < NV; n++) {
+          const double tt = s0[n] * dtdx * 0.5;
+          double vp = q[n] - 0.5 * dq[d][n] + tt, vm = q[n] + 0.5 * dq[d][n] + tt;
+          if (n == 0) { if (vp < P.smallr) vp = q[0]; if (vm < P.smallr) vm = q[0]; }
+          s.qp[d][n][tc] = vp;
+          s.qm[d][n][tc] = vm;
+        }
+      }
+    }
+  __syncthreads();
+  // ---- cmpflxm: 3*2^(ndim-1) faces per direction (hydro/umuscl.f90:97,120,144), flux = fx*dt/dx, masking :720-747 ----
+  if (live)
+    for (int e = tl; e < NDIM * NF; e += AMR_TPO) {
+      const int d = e / NF, f = e % NF;
+      // face coordinates: along d: 1..3, transverse: 1..2
+      int c3[3] = {1, 1, 1};
+      int rem = f;
+      for (int dd = 0; dd < NDIM; dd++) {
+        const int ext = (dd == d) ? 3 : 2;
+        c3[dd] = 1 + rem % ext;
+        rem /= ext;
+      }
+      int cl[3] = {c3[0], c3[1], c3[2]};
+      cl[d] -= 1;
+      const int tR = c3[0] + 4 * ((HY ? c3[1] : 0) + 4 * (HZ ? c3[2] : 0));
+      const int tL = cl[0] + 4 * ((HY ? cl[1] : 0) + 4 * (HZ ? cl[2] : 0));
+      const int ln = d + 1, lt1 = (d == 0) ? 2 : 1, lt2 = (d == 2) ? 2 : 3;       // cmpflxm(…,ln,lt1,lt2) as 0-based variable indices
+      double ql[NV], qr[NV], fg[NV], fl[NV];
+      ql[0] = s.qm[d][0][tL]; ql[1] = s.qm[d][ln][tL]; ql[2] = s.qm[d][NDIM + 1][tL];
+      qr[0] = s.qp[d][0][tR]; qr[1] = s.qp[d][ln][tR]; qr[2] = s.qp[d][NDIM + 1][tR];
+      if (NDIM > 1) { ql[3] = s.qm[d][lt1 % NV][tL]; qr[3] = s.qp[d][lt1 % NV][tR]; }
+      if (NDIM > 2) { ql[4 % NV] = s.qm[d][lt2 % NV][tL]; qr[4 % NV] = s.qp[d][lt2 % NV][tR]; }
+      riemann<NDIM, RIEMANN>(ql, qr, fg, P);
+      fl[0] = fg[0]; fl[ln] = fg[1]; fl[NDIM + 1] = fg[2];
+      if (NDIM > 1) fl[lt1 % NV] = fg[3];
+      if (NDIM > 2) fl[lt2 % NV] = fg[4 % NV];
+      const int pR = (c3[0] + 1) + 6 * ((HY ? c3[1] + 1 : 0) + PJ * (HZ ? c3[2] + 1 : 0));
+      const int pL = (cl[0] + 1) + 6 * ((HY ? cl[1] + 1 : 0) + PJ * (HZ ? cl[2] + 1 : 0));
+      const bool masked = s.ok[pL] || s.ok[pR];
+#pragma unroll
+      for (int n = 0; n < NV; n++) {
+        double v = a.dx_pow2 ? (fl[n] * a.dt) * a.inv_dx : div_rn(fl[n] * a.dt, a.dx, a.inv_dx);
+        if (masked) v = 0.0;
+        s.flux[d][n][f] = v;
+      }
+    }
+  __syncthreads();
+  // ---- conservative update of the oct's own cells (:751-792), x then y then z ----
+  if (live) {
+    for (int e = tl; e < T * NV; e += AMR_TPO) {
+      const int is = e % T, n = e / T;
+      const int c3[3] = {1 + (is & 1), 1 + ((is >> 1) & 1), 1 + ((is >> 2) & 1)};
+      const int ic = amr_cell(t, is, igrid);
+      double u = a.unew[(size_t)n * NC + ic - 1];
+#pragma unroll
+      for (int d = 0; d < NDIM; d++) {
+        int fl_ = 0, fr_ = 0, mul = 1;
+        for (int dd = 0; dd < NDIM; dd++) {
+          const int ext = (dd == d) ? 3 : 2;
+          fl_ += (c3[dd] - 1) * mul;
+          fr_ += (c3[dd] - 1 + (dd == d ? 1 : 0)) * mul;
+          mul *= ext;
+        }
+        u = u + (s.flux[d][n][fl_] - s.flux[d][n][fr_]);
+      }
+      a.unew[(size_t)n * NC + ic - 1] = u;
+    }
+    // fluxes through the outer faces, for the coarse reflux pass: side = 2*d + (0 left | 1 right)
+    for (int e = tl; e < TW * NSF * NV; e += AMR_TPO) {
+      const int n = e % NV, fs = (e / NV) % NSF, side = e / (NV * NSF);
+      const int d = side / 2, right = side % 2;
+      int f = 0, mul = 1, rem = fs;
+      for (int dd = 0; dd < NDIM; dd++) {
+        const int ext = (dd == d) ? 3 : 2;
+        int c;
+        if (dd == d) c = right ? 2 : 0;
+        else { c = rem % 2; rem /= 2; }
+        f += c * mul;
+        mul *= ext;
+      }
+      a.rflux[(((size_t)io * TW + side) * NSF + fs) * NV + n] = s.flux[d][n][f];
+    }
+  }
+}
+
+// coarse reflux (hydro/godunov_fine.f90:798-908) in the reference's accumulation order: entries are grouped per target
+// (cell), each with its contributions (oct, side, face) in the order the reference visits them.
+struct RefluxArgs {
+  int nent;                 // target cells
+  const int* cell;          // [nent] coarse cell index
+  const int* start;         // [nent+1]
+  const int* src;           // [ncontrib] packed: oct*64 + side*8 + face
+  const double* rflux;
+  double* unew;
+  long long ncell;
+  int nvar, nsides, nsf;
+  double oneontwotondim;
+};
+__global__ void amr_reflux_kernel(const RefluxArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.nent * a.nvar) return;
+  const int e = i / a.nvar, n = i % a.nvar;
+  const size_t idx = (size_t)n * a.ncell + a.cell[e] - 1;
+  double u = a.unew[idx];
+  for (int k = a.start[e]; k < a.start[e + 1]; k++) {
+    const int sr = a.src[k];
+    const int oct = sr >> 6, side = (sr >> 3) & 7, face = sr & 7;
+    const double f = a.rflux[(((size_t)oct * a.nsides + side) * a.nsf + face) * a.nvar + n] * a.oneontwotondim;
+    if (side & 1) u = u + f; else u = u - f;
+  }
+  a.unew[idx] = u;
+}
+
+// list-based passes on the mirrored arrays ------------------------------------------------------------------------------
+// set_unew (hydro/godunov_fine.f90:40): unew = uold on the cells of the listed octs
+__global__ void amr_copy_octs_kernel(const double* __restrict__ src, double* __restrict__ dst, const int* __restrict__ igrid, int n,
+                                     int ncoarse, int ngridmax, long long ncell, int T, int nvar) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n * T * nvar) return;
+  const int o = (int)(i % n), ind = (int)((i / n) % T), iv = (int)(i / ((long long)n * T));
+  const size_t c = (size_t)iv * ncell + ncoarse + (size_t)ind * ngridmax + igrid[o] - 1;
+  dst[c] = src[c];
+}
+// upload_fine (hydro/interpol_hydro.f90:5, upl :73): split cells <- mean of their sons
+__global__ void amr_upload_kernel(double* __restrict__ u, const int* __restrict__ son1, const int* __restrict__ igrid, int n, int ncoarse,
+                                  int ngridmax, long long ncell, int T, int nvar, double smallr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * T) return;
+  const int o = i % n, ind = i / n;
+  const int ic = ncoarse + ind * ngridmax + igrid[o];
+  const int gs = son1[ic];
+  if (gs <= 0) return;
+  double getx = 0.0;
+  for (int is = 0; is < T; is++) getx = getx + fmax(u[(size_t)ncoarse + (size_t)is * ngridmax + gs - 1], smallr);
+  u[ic - 1] = getx / (double)T;
+  for (int iv = 1; iv < nvar; iv++) {
+    getx = 0.0;
+    for (int is = 0; is < T; is++) getx = getx + u[(size_t)iv * ncell + ncoarse + (size_t)is * ngridmax + gs - 1];
+    u[(size_t)iv * ncell + ic - 1] = getx / (double)T;
+  }
+}
+// make_boundary_hydro (hydro/hydro_boundary.f90:5) on the mirrored arrays
+struct AmrBoundArgs {
+  int n; const int* igrid; int inbor; int ind_ref[8]; double gs[3]; int kind; int ndim, nvar; double smallr;
+};
+__global__ void amr_boundary_kernel(double* __restrict__ u, const AmrTree t, const AmrBoundArgs b) {
+  const int T = 1 << b.ndim;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n * T) return;
+  const int o = i / T, ind = i % T;
+  const int ig = b.igrid[o];
+  const int gref = t.son[amr_nbor(t, ig, b.inbor)];
+  const int ic = amr_cell(t, ind, ig), icr = amr_cell(t, b.ind_ref[ind] - 1, gref);
+  const size_t NC = (size_t)t.ncell;
+  double uu[8];
+  for (int iv = 0; iv < b.nvar; iv++) uu[iv] = u[(size_t)iv * NC + icr - 1];
+  if (b.kind == 0) {
+    for (int iv = 0; iv < b.nvar; iv++) {
+      double sw = 1.0;
+      if (iv >= 1 && iv <= b.ndim) sw = b.gs[iv - 1];
+      u[(size_t)iv * NC + ic - 1] = uu[iv] * sw;
+    }
+  } else {
+    double ekin = 0.0, d = fmx(uu[0], b.smallr);
+    for (int idim = 0; idim < b.ndim; idim++) { const double v = uu[idim + 1] / d; ekin = ekin + 0.5 * d * (v * v); }
+    uu[b.ndim + 1] = uu[b.ndim + 1] - ekin;
+    ekin = 0.0; d = fmx(uu[0], b.smallr);
+    for (int idim = 0; idim < b.ndim; idim++) { const double v = uu[idim + 1] / d; ekin = ekin + 0.5 * d * (v * v); }
+    uu[b.ndim + 1] = uu[b.ndim + 1] + ekin;
+    for (int iv = 0; iv < b.nvar; iv++) u[(size_t)iv * NC + ic - 1] = uu[iv];
+  }
+}
+// courant_fine over the LEAF cells of the listed octs (hydro/courant_fine.f90:61)
+template <int NDIM>
+__global__ void amr_courant_kernel(const double* __restrict__ u, const AmrTree t, const int* __restrict__ igrid, int n, Phys P, double dx,
+                                   double* __restrict__ part) {
+  constexpr int NV = NDIM + 2, T = 1 << NDIM;
+  __shared__ double red[4][32];
+  double my_dt = 1e300, m0 = 0, m1 = 0, m2 = 0;
+  const size_t NC = (size_t)t.ncell;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n * T; i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % n), ind = (int)(i / n);
+    const int ic = amr_cell(t, ind, igrid[o]);
+    if (t.son[ic] != 0) continue;
+    double uu[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) uu[k] = u[(size_t)k * NC + ic - 1];
+    double ei;
+    const double dtc = cmpdt_cell<NDIM>(uu, dx, P, ei);
+    my_dt = dtc < my_dt ? dtc : my_dt;
+    m0 += uu[0]; m1 += uu[NDIM + 1]; m2 += ei;
+  }
+  my_dt = warp_min(my_dt); m0 = warp_sum(m0); m1 = warp_sum(m1); m2 = warp_sum(m2);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = my_dt; red[1][w] = m0; red[2][w] = m1; red[3][w] = m2; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    double v0 = l < nw ? red[0][l] : 1e300, v1 = l < nw ? red[1][l] : 0, v2 = l < nw ? red[2][l] : 0, v3 = l < nw ? red[3][l] : 0;
+    v0 = warp_min(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+    if (l == 0) {
+      const size_t nb = gridDim.x;
+      part[0 * nb + blockIdx.x] = v0; part[1 * nb + blockIdx.x] = v1; part[2 * nb + blockIdx.x] = v2; part[3 * nb + blockIdx.x] = v3;
+    }
+  }
+}
+
+template <int NDIM, int RIEMANN>
+cudaError_t launch_amr_godfine(const AmrSweepArgs& a, cudaStream_t st) {
+  const int nb = (a.nact + AMR_OPB - 1) / AMR_OPB;
+  amr_godfine_kernel<NDIM, RIEMANN><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace rgpu

@@ -17,6 +17,7 @@
 #include <vector>
 #include "../../include/ramses_gpu.h"
 #include "sweep_dense.cuh"
+#include "amr_kernels.cuh"
 
 namespace rgpu {
 // launchers instantiated in sweep_inst_*.cu
@@ -97,8 +98,29 @@ struct Level {
   double dx = 0;
 };
 
+// AMR mode (levelmin < levelmax): the device mirrors the reference arrays, every level is a list of octs
+struct AmrRegion { int type = 0, n = 0; int* d_igrid = nullptr; };
+struct AmrLevel {
+  bool bound = false;
+  int nact = 0;
+  int* d_active = nullptr;
+  std::vector<AmrRegion> regions;
+  double* d_rflux = nullptr;
+  int nent = 0;                       // coarse cells that receive refluxes from this level
+  int *d_rcell = nullptr, *d_rstart = nullptr, *d_rsrc = nullptr;
+  double* d_part = nullptr; double* d_out = nullptr; double* d_dt = nullptr;
+  long long launches = 0;
+  double dx = 0;
+};
+
 struct Context {
   bool init = false;
+  bool amr = false;
+  int* d_son = nullptr; int* d_father = nullptr; int* d_nbor = nullptr;
+  double* d_uold = nullptr; double* d_unew = nullptr;
+  long long ncell = 0;
+  int interpol_type = 1;
+  AmrLevel alev[MAXLEVEL + 1];
   rgpu_params p{};
   Phys phys{};
   int myid = 1, ncpu = 1, device = 0;
@@ -436,6 +458,166 @@ int launch_boundaries(Level& L, double* u) {
   return RGPU_OK;
 }
 
+
+// ----------------------------------------------------------------------------- AMR mode host glue
+AmrTree amr_tree() {
+  AmrTree t{};
+  t.son = G.d_son - 1;         // 1-based indexing like the Fortran arrays
+  t.father = G.d_father - 1;
+  t.nbor = G.d_nbor;
+  t.ncoarse = G.ncoarse; t.ngridmax = G.ngridmax; t.nx = G.p.nx; t.ny = G.p.ny; t.nz = G.p.nz;
+  t.ncell = G.ncell;
+  return t;
+}
+void free_amr_level(AmrLevel& A) {
+  cudaFree(A.d_active); cudaFree(A.d_rflux); cudaFree(A.d_rcell); cudaFree(A.d_rstart); cudaFree(A.d_rsrc);
+  cudaFree(A.d_part); cudaFree(A.d_out); cudaFree(A.d_dt);
+  for (auto& r : A.regions) cudaFree(r.d_igrid);
+  A = AmrLevel();
+}
+int check_amr_level(int ilevel, AmrLevel** out) {
+  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  if (ilevel < 1 || ilevel > MAXLEVEL) return fail(RGPU_EINVAL, "ilevel %d out of range", ilevel);
+  if (!G.d_son) return fail(RGPU_EINVAL, "AMR mode: rgpu_bind_tree has not been called");
+  AmrLevel& A = G.alev[ilevel];
+  if (!A.bound) return fail(RGPU_EINVAL, "level %d is not bound (rgpu_bind_level)", ilevel);
+  *out = &A;
+  return RGPU_OK;
+}
+int amr_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int ncpu, int nboundary, const int* boundary_type,
+                   const int* ngrid_bound, const int* const* igrid_bound) {
+  if (ncpu > 1) return fail(RGPU_EUNSUPPORTED, "AMR mode is single-rank for now (ghost-oct exchange on oct lists not built)");
+  AmrLevel& A = G.alev[ilevel];
+  if (A.bound) free_amr_level(A);
+  const int nd = G.p.ndim, nvar = G.p.nvar, TW = 2 * nd, NSF = 1 << (nd - 1);
+  A.dx = level_dx(ilevel);
+  A.nact = ngrid_active;
+  CUDA_OK(cudaMalloc(&A.d_active, sizeof(int) * std::max(1, ngrid_active)));
+  CUDA_OK(cudaMemcpy(A.d_active, igrid_active, sizeof(int) * ngrid_active, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&A.d_rflux, sizeof(double) * (size_t)std::max(1, ngrid_active) * TW * NSF * nvar));
+  A.regions.resize(nboundary);
+  for (int b = 0; b < nboundary; b++) {
+    A.regions[b].type = boundary_type[b];
+    A.regions[b].n = ngrid_bound[b];
+    if (ngrid_bound[b] > 0) {
+      CUDA_OK(cudaMalloc(&A.regions[b].d_igrid, sizeof(int) * ngrid_bound[b]));
+      CUDA_OK(cudaMemcpy(A.regions[b].d_igrid, igrid_bound[b], sizeof(int) * ngrid_bound[b], cudaMemcpyHostToDevice));
+    }
+  }
+  // reflux schedule (hydro/godunov_fine.f90:798-908): contributions in the order the reference visits them --
+  // batch of nvector octs, direction, left then right, face, oct of the batch with son(nbor)==0
+  {
+    const int nv = std::max(1, G.p.nvector);
+    std::vector<int> tgt, src;
+    for (int i0 = 0; i0 < ngrid_active; i0 += nv) {
+      const int ng = std::min(nv, ngrid_active - i0);
+      for (int d = 0; d < nd; d++)
+        for (int s = 0; s < 2; s++)
+          for (int f = 0; f < NSF; f++)
+            for (int i = 0; i < ng; i++) {
+              const int ig = igrid_active[i0 + i];
+              const int nb = G.nbor[(size_t)(2 * d + s) * G.ngridmax + ig - 1];
+              if (nb > 0 && G.son[nb - 1] == 0) { tgt.push_back(nb); src.push_back(((i0 + i) << 6) | ((2 * d + s) << 3) | f); }
+            }
+    }
+    // group by target cell, keeping the visiting order inside each group (stable)
+    std::vector<int> order(tgt.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tgt[x] < tgt[y]; });
+    std::vector<int> cells, start, srcs;
+    for (size_t k = 0; k < order.size(); k++) {
+      if (k == 0 || tgt[order[k]] != tgt[order[k - 1]]) { cells.push_back(tgt[order[k]]); start.push_back((int)k); }
+      srcs.push_back(src[order[k]]);
+    }
+    start.push_back((int)order.size());
+    A.nent = (int)cells.size();
+    if (A.nent > 0) {
+      if (ngrid_active >= (1 << 25)) return fail(RGPU_EUNSUPPORTED, "too many octs for the packed reflux schedule");
+      CUDA_OK(cudaMalloc(&A.d_rcell, sizeof(int) * cells.size()));
+      CUDA_OK(cudaMalloc(&A.d_rstart, sizeof(int) * start.size()));
+      CUDA_OK(cudaMalloc(&A.d_rsrc, sizeof(int) * srcs.size()));
+      CUDA_OK(cudaMemcpy(A.d_rcell, cells.data(), sizeof(int) * cells.size(), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(A.d_rstart, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(A.d_rsrc, srcs.data(), sizeof(int) * srcs.size(), cudaMemcpyHostToDevice));
+    }
+  }
+  CUDA_OK(cudaMalloc(&A.d_part, sizeof(double) * 4 * 148 * 8));
+  CUDA_OK(cudaMalloc(&A.d_out, sizeof(double) * 4));
+  CUDA_OK(cudaMalloc(&A.d_dt, sizeof(double)));
+  A.bound = true;
+  return RGPU_OK;
+}
+template <int ND>
+cudaError_t dispatch_amr_nd(int riemann, const AmrSweepArgs& a, cudaStream_t st) {
+  switch (riemann) {
+    case RGPU_RIEMANN_LLF: return launch_amr_godfine<ND, RIEMANN_LLF>(a, st);
+    case RGPU_RIEMANN_EXACT: return launch_amr_godfine<ND, RIEMANN_EXACT>(a, st);
+    case RGPU_RIEMANN_ACOUSTIC: return launch_amr_godfine<ND, RIEMANN_ACOUSTIC>(a, st);
+    case RGPU_RIEMANN_HLLC: return launch_amr_godfine<ND, RIEMANN_HLLC>(a, st);
+    default: return launch_amr_godfine<ND, RIEMANN_HLL>(a, st);
+  }
+}
+int amr_godunov(AmrLevel& A, int ilevel, double dt) {
+  if (A.nact == 0) return RGPU_OK;
+  AmrSweepArgs a{};
+  a.t = amr_tree();
+  a.active = A.d_active; a.nact = A.nact; a.ilevel = ilevel;
+  a.uold = G.d_uold; a.unew = G.d_unew; a.rflux = A.d_rflux;
+  a.P = G.phys; a.dt = dt; a.dx = A.dx; a.inv_dx = 1.0 / A.dx;
+  int ex;
+  a.dx_pow2 = (std::frexp(A.dx, &ex) == 0.5) ? 1 : 0;
+  a.interpol_type = G.interpol_type;
+  cudaError_t e;
+  if (G.p.ndim == 1) e = dispatch_amr_nd<1>(G.p.riemann, a, G.stream);
+  else if (G.p.ndim == 2) e = dispatch_amr_nd<2>(G.p.riemann, a, G.stream);
+  else e = dispatch_amr_nd<3>(G.p.riemann, a, G.stream);
+  if (e != cudaSuccess) return fail(RGPU_ECUDA, "amr sweep launch: %s", cudaGetErrorString(e));
+  A.launches++;
+  if (A.nent > 0) {
+    RefluxArgs r{};
+    r.nent = A.nent; r.cell = A.d_rcell; r.start = A.d_rstart; r.src = A.d_rsrc; r.rflux = A.d_rflux; r.unew = G.d_unew;
+    r.ncell = G.ncell; r.nvar = G.p.nvar; r.nsides = 2 * G.p.ndim; r.nsf = 1 << (G.p.ndim - 1);
+    r.oneontwotondim = 1.0 / (double)(1 << G.p.ndim);
+    const int n = A.nent * G.p.nvar;
+    amr_reflux_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(r);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  return RGPU_OK;
+}
+int amr_copy(AmrLevel& A, const double* src, double* dst) {
+  if (A.nact == 0) return RGPU_OK;
+  const long long n = (long long)A.nact * T_() * G.p.nvar;
+  amr_copy_octs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, G.stream>>>(src, dst, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar);
+  CUDA_OK(cudaGetLastError());
+  A.launches++;
+  return RGPU_OK;
+}
+int amr_boundaries(AmrLevel& A) {
+  static const int ref_x[8] = {2, 1, 4, 3, 6, 5, 8, 7}, ref_y[8] = {3, 4, 1, 2, 7, 8, 5, 6}, ref_z[8] = {5, 6, 7, 8, 1, 2, 3, 4};
+  static const int fre[6][8] = {{1, 1, 3, 3, 5, 5, 7, 7}, {2, 2, 4, 4, 6, 6, 8, 8}, {1, 2, 1, 2, 5, 6, 5, 6},
+                                {3, 4, 3, 4, 7, 8, 7, 8}, {1, 2, 3, 4, 1, 2, 3, 4}, {5, 6, 7, 8, 5, 6, 7, 8}};
+  static const int inb[7] = {0, 2, 1, 4, 3, 6, 5};
+  for (auto& r : A.regions) {
+    if (r.n == 0) continue;
+    const int bt = r.type, dir = bt - 10 * (bt / 10);
+    if (bt / 10 > 1) return fail(RGPU_EUNSUPPORTED, "imposed boundary (boundana) type %d not supported", bt);
+    AmrBoundArgs b{};
+    b.n = r.n; b.igrid = r.d_igrid; b.inbor = inb[dir];
+    const int d = (dir - 1) / 2;
+    const int* ir = (bt / 10 == 0) ? (d == 0 ? ref_x : d == 1 ? ref_y : ref_z) : fre[dir - 1];
+    for (int i = 0; i < 8; i++) b.ind_ref[i] = ir[i];
+    b.gs[0] = b.gs[1] = b.gs[2] = 1.0;
+    if (bt >= 1 && bt <= 6) b.gs[d] = -1.0;
+    b.kind = bt / 10; b.ndim = G.p.ndim; b.nvar = G.p.nvar; b.smallr = G.p.smallr;
+    const int nthr = r.n * T_();
+    amr_boundary_kernel<<<(nthr + 127) / 128, 128, 0, G.stream>>>(G.d_uold, amr_tree(), b);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  return RGPU_OK;
+}
+
 int exchange_ghosts(Level& L, double* u, bool reverse);
 
 // set_uold only touches the active cells: the boundary / ghost shells keep their uold values until the next
@@ -516,10 +698,22 @@ int rgpu_finalize(void) {
   if (!G.init) return RGPU_OK;
   cudaStreamSynchronize(G.stream);
   for (int l = 0; l <= MAXLEVEL; l++) if (G.lev[l].bound) free_level(G.lev[l]);
+  for (int l = 0; l <= MAXLEVEL; l++) if (G.alev[l].bound) free_amr_level(G.alev[l]);
+  cudaFree(G.d_son); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew);
+  G.d_son = G.d_father = G.d_nbor = nullptr; G.d_uold = G.d_unew = nullptr; G.ncell = 0; G.amr = false;
   if (G.comm) { ncclCommDestroy(G.comm); G.comm = nullptr; }
   cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); cudaEventDestroy(G.ev2); cudaEventDestroy(G.ev3);
   cudaStreamDestroy(G.stream);
   G.init = false;
+  return RGPU_OK;
+}
+
+int rgpu_set_amr(int on, int interpol_type, int interpol_var) {
+  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  if (on && interpol_var != 0) return fail(RGPU_EUNSUPPORTED, "interpol_var=%d not supported (0 only)", interpol_var);
+  if (on && (interpol_type < 0 || interpol_type > 3)) return fail(RGPU_EUNSUPPORTED, "interpol_type=%d not supported", interpol_type);
+  G.amr = on != 0;
+  G.interpol_type = interpol_type;
   return RGPU_OK;
 }
 
@@ -528,6 +722,24 @@ int rgpu_bind_tree(int ncoarse, int ngridmax, const int* son, const int* father,
   if (!son || !father || !nbor) return fail(RGPU_EINVAL, "null tree array");
   if (ncoarse != G.p.nx * G.p.ny * G.p.nz) return fail(RGPU_EINVAL, "ncoarse=%d != nx*ny*nz", ncoarse);
   G.ncoarse = ncoarse; G.ngridmax = ngridmax; G.son = son; G.father = father; G.nbor = nbor;
+  if (G.amr) {   // mirror the tree (read-only during a step; re-bind after every regrid)
+    const long long ncell = (long long)ncoarse + (long long)T_() * ngridmax;
+    if (ncell != G.ncell) {
+      cudaFree(G.d_son); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew);
+      G.d_son = G.d_father = G.d_nbor = nullptr; G.d_uold = G.d_unew = nullptr;
+      CUDA_OK(cudaMalloc(&G.d_son, sizeof(int) * ncell));
+      CUDA_OK(cudaMalloc(&G.d_father, sizeof(int) * ngridmax));
+      CUDA_OK(cudaMalloc(&G.d_nbor, sizeof(int) * (size_t)2 * G.p.ndim * ngridmax));
+      CUDA_OK(cudaMalloc(&G.d_uold, sizeof(double) * G.p.nvar * ncell));
+      CUDA_OK(cudaMalloc(&G.d_unew, sizeof(double) * G.p.nvar * ncell));
+      CUDA_OK(cudaMemset(G.d_uold, 0, sizeof(double) * G.p.nvar * ncell));
+      CUDA_OK(cudaMemset(G.d_unew, 0, sizeof(double) * G.p.nvar * ncell));
+      G.ncell = ncell;
+    }
+    CUDA_OK(cudaMemcpy(G.d_son, son, sizeof(int) * ncell, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(G.d_father, father, sizeof(int) * ngridmax, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(G.d_nbor, nbor, sizeof(int) * (size_t)2 * G.p.ndim * ngridmax, cudaMemcpyHostToDevice));
+  }
   return RGPU_OK;
 }
 
@@ -637,6 +849,7 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
   if (!G.son) return fail(RGPU_EINVAL, "rgpu_bind_tree has not been called");
   if (ilevel < 1 || ilevel > MAXLEVEL) return fail(RGPU_EINVAL, "ilevel %d out of range", ilevel);
   if (ngrid_active <= 0 || !igrid_active) return fail(RGPU_EINVAL, "level %d has no active oct", ilevel);
+  if (G.amr) return amr_bind_level(ilevel, ngrid_active, igrid_active, ncpu, nboundary, boundary_type, ngrid_bound, igrid_bound);
   Level& L = G.lev[ilevel];
   if (L.bound) free_level(L);
   {
@@ -798,6 +1011,12 @@ static int download_from(Level& L, double* host, const double* srcdev, bool owne
 }
 
 int rgpu_upload_state(int ilevel, const double* uold) {
+  if (G.amr) {   // AMR mode: the whole uold array (all levels) is mirrored; ilevel is ignored
+    if (!G.d_uold || !uold) return fail(RGPU_EINVAL, "AMR mode: bind the tree first / null uold");
+    CUDA_OK(cudaMemcpyAsync(G.d_uold, uold, sizeof(double) * G.p.nvar * G.ncell, cudaMemcpyHostToDevice, G.stream));
+    CUDA_OK(cudaStreamSynchronize(G.stream));
+    return RGPU_OK;
+  }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (!uold) return fail(RGPU_EINVAL, "null uold");
   rc = upload_into(*L, uold, L->d_u[L->cur]); if (rc) return rc;
@@ -805,12 +1024,19 @@ int rgpu_upload_state(int ilevel, const double* uold) {
   return RGPU_OK;
 }
 int rgpu_download_state(int ilevel, double* uold) {
+  if (G.amr) {
+    if (!G.d_uold || !uold) return fail(RGPU_EINVAL, "AMR mode: bind the tree first / null uold");
+    CUDA_OK(cudaMemcpyAsync(uold, G.d_uold, sizeof(double) * G.p.nvar * G.ncell, cudaMemcpyDeviceToHost, G.stream));
+    CUDA_OK(cudaStreamSynchronize(G.stream));
+    return RGPU_OK;
+  }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (!uold) return fail(RGPU_EINVAL, "null uold");
   return download_from(*L, uold, L->d_u[L->cur], false);
 }
 
 int rgpu_set_unew(int ilevel) {
+  if (G.amr) { AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc; return amr_copy(*A, G.d_uold, G.d_unew); }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   const size_t n = nplanes_() * (size_t)L->nslot;
   copy_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, G.stream>>>(L->d_u[L->cur], L->d_u[1 - L->cur], n);
@@ -827,6 +1053,11 @@ int rgpu_set_unew(int ilevel) {
 }
 
 int rgpu_godunov_fine_dev(int ilevel, double dt) {
+  if (G.amr) {
+    AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
+    if (!(dt > 0)) return fail(RGPU_EINVAL, "dt=%g", dt);
+    return amr_godunov(*A, ilevel, dt);
+  }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (!(dt > 0)) return fail(RGPU_EINVAL, "dt=%g", dt);
   CUDA_OK(cudaMemcpyAsync(L->d_dt, &dt, sizeof(double), cudaMemcpyHostToDevice, G.stream));
@@ -838,6 +1069,7 @@ int rgpu_godunov_fine_dev(int ilevel, double dt) {
 }
 
 int rgpu_set_uold(int ilevel) {
+  if (G.amr) { AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc; return amr_copy(*A, G.d_unew, G.d_uold); }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (!L->unew_valid) return fail(RGPU_EINVAL, "set_uold before set_unew/godunov_fine");
   // uold <- unew on the active cells (godunov_fine.f90:193-197); shells keep their uold values
@@ -848,6 +1080,26 @@ int rgpu_set_uold(int ilevel) {
 }
 
 int rgpu_courant_fine(int ilevel, double* dt_io, double sums[3]) {
+  if (G.amr) {
+    AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
+    if (!dt_io) return fail(RGPU_EINVAL, "null dt");
+    if (A->nact == 0) return RGPU_OK;
+    const int nb = 148 * 8;
+    if (G.p.ndim == 1) amr_courant_kernel<1><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A->d_active, A->nact, G.phys, A->dx, A->d_part);
+    else if (G.p.ndim == 2) amr_courant_kernel<2><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A->d_active, A->nact, G.phys, A->dx, A->d_part);
+    else amr_courant_kernel<3><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A->d_active, A->nact, G.phys, A->dx, A->d_part);
+    CUDA_OK(cudaGetLastError());
+    const double vol = std::pow(A->dx, G.p.ndim), dt0 = G.p.courant_factor * A->dx / G.p.smallc;
+    courant_reduce_kernel<<<1, 1024, 0, G.stream>>>(A->d_part, nb, *dt_io, dt0, vol, A->d_out, A->d_dt, nullptr);
+    CUDA_OK(cudaGetLastError());
+    A->launches += 2;
+    double out[4];
+    CUDA_OK(cudaMemcpyAsync(out, A->d_out, sizeof(out), cudaMemcpyDeviceToHost, G.stream));
+    CUDA_OK(cudaStreamSynchronize(G.stream));
+    *dt_io = std::min(*dt_io, out[0]);
+    if (sums) { sums[0] += out[1]; sums[1] += out[2]; sums[2] += out[3]; }
+    return RGPU_OK;
+  }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (!dt_io) return fail(RGPU_EINVAL, "null dt");
   rc = launch_courant(*L, *dt_io, nullptr); if (rc) return rc;
@@ -868,21 +1120,36 @@ int rgpu_courant_fine(int ilevel, double* dt_io, double sums[3]) {
 }
 
 int rgpu_make_boundary_hydro(int ilevel) {
+  if (G.amr) { AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc; return amr_boundaries(*A); }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   return launch_boundaries(*L, L->d_u[L->cur]);
 }
 
 int rgpu_make_virtual_fine(int ilevel) {
+  if (G.amr) return RGPU_OK;   // single rank: no virtual boundaries
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   return exchange_ghosts(*L, L->d_u[L->cur], false);
 }
 int rgpu_make_virtual_reverse(int ilevel) {
+  if (G.amr) return RGPU_OK;
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (!L->unew_valid) return fail(RGPU_EINVAL, "make_virtual_reverse before godunov_fine");
   return exchange_ghosts(*L, L->d_u[1 - L->cur], true);
 }
 
 int rgpu_godunov_fine(int ilevel, double dt, const double* uold, double* unew) {
+  if (G.amr) {   // Level-0 in AMR mode: uold and unew (it carries the refluxes of finer levels) both travel
+    AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
+    if (!uold || !unew) return fail(RGPU_EINVAL, "null state array");
+    if (!(dt > 0)) return fail(RGPU_EINVAL, "dt=%g", dt);
+    const size_t bytes = sizeof(double) * G.p.nvar * G.ncell;
+    CUDA_OK(cudaMemcpyAsync(G.d_uold, uold, bytes, cudaMemcpyHostToDevice, G.stream));
+    CUDA_OK(cudaMemcpyAsync(G.d_unew, unew, bytes, cudaMemcpyHostToDevice, G.stream));
+    rc = amr_godunov(*A, ilevel, dt); if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(unew, G.d_unew, bytes, cudaMemcpyDeviceToHost, G.stream));
+    CUDA_OK(cudaStreamSynchronize(G.stream));
+    return RGPU_OK;
+  }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (!uold || !unew) return fail(RGPU_EINVAL, "null state array");
   if (!(dt > 0)) return fail(RGPU_EINVAL, "dt=%g", dt);
@@ -894,6 +1161,7 @@ int rgpu_godunov_fine(int ilevel, double dt, const double* uold, double* unew) {
 }
 
 int rgpu_level_steps(int ilevel, int nstep, double* dt_hist, double sums_last[3]) {
+  if (G.amr) return fail(RGPU_EUNSUPPORTED, "rgpu_level_steps is the levelmin=levelmax fast path; in AMR mode call the per-level routines in amr_step order");
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (nstep < 1) return fail(RGPU_EINVAL, "nstep=%d", nstep);
   if (L->hist_cap < nstep + 1) {
@@ -930,6 +1198,17 @@ int rgpu_level_steps(int ilevel, int nstep, double* dt_hist, double sums_last[3]
   return RGPU_OK;
 }
 
+int rgpu_upload_fine(int ilevel) {
+  if (!G.amr) return RGPU_OK;   // a dense (levelmin=levelmax) level has no split cells: upload_fine is a no-op
+  AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
+  if (A->nact == 0 || ilevel >= G.p.nlevelmax) return RGPU_OK;
+  const int n = A->nact * T_();
+  amr_upload_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_son - 1, A->d_active, A->nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar, G.p.smallr);
+  CUDA_OK(cudaGetLastError());
+  A->launches++;
+  return RGPU_OK;
+}
+
 int rgpu_comm_unique_id(void* unique_id_128) {
   if (!unique_id_128) return fail(RGPU_EINVAL, "null id");
   ncclUniqueId id;
@@ -949,6 +1228,11 @@ int rgpu_comm_init(int nranks, int rank, const void* unique_id_128) {
 }
 
 int rgpu_get_level_info(int ilevel, rgpu_level_info* o) {
+  if (G.init && G.amr && o && ilevel >= 1 && ilevel <= MAXLEVEL && G.alev[ilevel].bound) {
+    memset(o, 0, sizeof(*o));
+    o->nslot = G.alev[ilevel].nact; o->kernel_launches = G.alev[ilevel].launches;
+    return RGPU_OK;
+  }
   if (!G.init || ilevel < 1 || ilevel > MAXLEVEL || !G.lev[ilevel].bound || !o) return fail(RGPU_EINVAL, "level %d not bound", ilevel);
   Level& L = G.lev[ilevel];
   o->dense = L.dense;

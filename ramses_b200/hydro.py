@@ -140,12 +140,14 @@ def plan_level(amr, ilevel):
 class HydroGPU:
     """The patched routines of hydro/godunov_fine.f90 & friends, running on the GPU through the C-ABI."""
 
-    def __init__(self, amr: AmrCommons, device=-1):
+    def __init__(self, amr: AmrCommons, device=-1, amr_mode=False, interpol_type=1, interpol_var=0):
         self.a = amr
         self.L = _lib.load()
         p = make_params(amr)
         self.params = p
         _lib.check(self.L.rgpu_init(C.byref(p), amr.myid, amr.ncpu, device))
+        if amr_mode:      # levelmin < nlevelmax: oct-list kernels on mirrored arrays
+            _lib.check(self.L.rgpu_set_amr(1, interpol_type, interpol_var))
         self._keep = []
         self.bind_tree()
 
@@ -199,6 +201,9 @@ class HydroGPU:
 
     def make_boundary_hydro(self, ilevel):
         _lib.check(self.L.rgpu_make_boundary_hydro(ilevel))
+
+    def upload_fine(self, ilevel):
+        _lib.check(self.L.rgpu_upload_fine(ilevel))
 
     def make_virtual_fine(self, ilevel):
         _lib.check(self.L.rgpu_make_virtual_fine(ilevel))

@@ -1,0 +1,140 @@
+"""AMR levels on the GPU (oct-batch kernels: godfine1 with interpol_hydro ghost prolongation, flux masking, coarse
+refluxing; upload_fine; boundaries; leaf-cell Courant scan) against the pinned oracle on meshes produced by the oracle's
+AMR driver (oracle/amr.py).  One coarse step in amr_step order with sub-cycling, mesh kept static on both sides."""
+import numpy as np
+import pytest
+
+from ramses_b200.hydro import AmrCommons
+
+pytestmark = pytest.mark.gpu
+
+SOD = [dict(type="square", x_center=0.25, length_x=0.5, d=1.0, p=1.0),
+       dict(type="square", x_center=0.75, length_x=0.5, d=0.125, p=0.1)]
+
+
+def commons_from_run(r, riemann, slope_type):
+    m = r.m
+    a = AmrCommons(r.ndim, r.nvar, m.ncoarse, m.ngridmax, m.nx, m.ny, m.nz, (m.icoarse_min, m.icoarse_max),
+                   (m.jcoarse_min, m.jcoarse_max), (m.kcoarse_min, m.kcoarse_max), nlevelmax=r.nlevelmax, boxlen=r.p.boxlen)
+    a.son[:] = r.son[1:]
+    a.father[:] = r.father[1:]
+    a.nbor[:, :] = r.nbor[:, 1:]
+    a.uold[:, :] = r.uold.reshape(r.nvar, m.ncell)
+    for l in range(1, r.nlevelmax + 1):
+        a.active[l] = np.array(r.active[l], dtype=np.int32)
+        a.boundary[l] = [np.array(r.bound[b][l], dtype=np.int32) for b in range(m.nboundary)]
+    a.boundary_type = [m.boundary_type[b] for b in range(m.nboundary)]
+    a.gamma, a.courant_factor = r.p.gamma, r.p.courant_factor
+    a.slope_type, a.riemann, a.nvector = slope_type, riemann, r.nvector
+    return a
+
+
+def gpu_amr_step(h, a, r, l, icount, dtnew, dtold):
+    """amr/amr_step.f90 on a static mesh, every pass through the C-ABI"""
+    if len(a.active[l]) == 0:
+        return
+    dtold[l] = dtnew[l]
+    a.dtnew[l] = a.boxlen / a.smallc               # pm/newdt_fine.f90:51
+    dtnew[l] = h.courant_fine(l)
+    if l > r.levelmin:
+        dtnew[l] = min(dtnew[l - 1] / float(r.nsubcycle[l - 1]), dtnew[l])
+    a.dtnew[l] = dtnew[l]
+    h.set_unew(l)
+    if l < r.nlevelmax and len(a.active.get(l + 1, [])) > 0:
+        if r.nsubcycle[l] == 2:
+            gpu_amr_step(h, a, r, l + 1, 1, dtnew, dtold)
+            gpu_amr_step(h, a, r, l + 1, 2, dtnew, dtold)
+        else:
+            gpu_amr_step(h, a, r, l + 1, 1, dtnew, dtold)
+    elif l < r.nlevelmax:
+        dtold[l + 1] = dtnew[l] / float(r.nsubcycle[l])
+        dtnew[l + 1] = dtnew[l] / float(r.nsubcycle[l])
+    a.dtnew[l] = dtnew[l]
+    h.godunov_fine_dev(l)
+    h.set_uold(l)
+    h.upload_fine(l)
+    h.make_boundary_hydro(l)
+    if l > r.levelmin:
+        if r.nsubcycle[l - 1] == 1:
+            dtnew[l - 1] = dtnew[l]
+        if icount == 2:
+            dtnew[l - 1] = dtold[l] + dtnew[l]
+
+
+def run_case(ndim, levelmin, levelmax, bound, regions, riemann, slope_type, ncoarse_dev, interpol_type, nsub, boxlen=1.0,
+             err=0.05, nexpand=1):
+    from oracle.amr import AmrRun
+    from ramses_b200.hydro import HydroGPU
+    r = AmrRun(ndim, levelmin, levelmax, bound, boxlen, nsubcycle=nsub, nexpand=nexpand, ngridmax=20000, riemann=riemann,
+               slope_type=slope_type, err_grad_d=err, err_grad_u=err, err_grad_p=err, interpol_type=interpol_type,
+               regions=regions, tout=[1e9])
+    r.flag_coarse(); r.init_refine(); r.init_refine_2()
+    for _ in range(ncoarse_dev):                   # develop the flow with the full (regridding) driver
+        r.refine_coarse(); r.push_lists(1)
+        for l in range(1, levelmin + 1):
+            r.make_boundary_hydro(l)
+            if l < levelmin:
+                r.refine_fine(l)
+        r.amr_step(levelmin, 1)
+        for l in range(levelmin - 1, 0, -1):
+            r.upload_fine(l); r.make_boundary_hydro(l)
+        for l in range(levelmin - 1, 0, -1):
+            r.flag_fine(l, 2)
+        r.flag_coarse()
+        r.nstep_coarse += 1
+    # regrid once more like the head of amr_step, then freeze the mesh
+    for i in range(levelmin, levelmax + 1):
+        if i > levelmin:
+            r.make_boundary_hydro(i)
+        r.refine_fine(i)
+    nlev = [len(r.active[l]) for l in range(1, levelmax + 1)]
+    assert sum(1 for n in nlev[levelmin:] if n > 0) >= 1, nlev      # a genuinely refined mesh
+    a = commons_from_run(r, riemann, slope_type)
+    h = HydroGPU(a, amr_mode=True, interpol_type=interpol_type)
+    for l in range(1, levelmax + 1):
+        if len(a.active[l]):
+            h.bind_level(l)
+    h.upload_state(0)
+    for l in range(1, levelmax + 1):
+        if len(a.active[l]):
+            h.make_boundary_hydro(l)
+    dtnew = {l: r.dtnew[l] for l in range(0, levelmax + 2)}
+    dtold = {l: r.dtold[l] for l in range(0, levelmax + 2)}
+    gpu_amr_step(h, a, r, levelmin, 1, dtnew, dtold)
+    h.download_state(0)
+    h.finalize()
+    # oracle: the same coarse step on the frozen mesh
+    r.static = True
+    for l in range(1, levelmax + 1):
+        r.make_boundary_hydro(l)
+    r.amr_step(levelmin, 1)
+    ref = r.uold.reshape(r.nvar, -1)
+    cells = np.concatenate([[r.cell(ind, ig) - 1 for ig in r.active[l] for ind in range(r.T)] for l in range(1, levelmax + 1) if r.active[l]]).astype(np.int64)
+    return a.uold[:, cells], ref[:, cells], dtnew, r, nlev
+
+
+@pytest.mark.parametrize("riemann,slope_type,interpol_type", [("hllc", 2, 2), ("llf", 1, 1), ("hll", 7, 3), ("acoustic", 8, 0)])
+def test_amr_1d_sod_bitwise(riemann, slope_type, interpol_type):
+    got, ref, dtnew, r, nlev = run_case(1, 3, 8, (1, 1, 0, 0, 0, 0), SOD, riemann, slope_type, 6, interpol_type, [1, 1, 1, 2])
+    assert dtnew[3] == r.dtnew[3]
+    assert np.array_equal(got, ref), (np.abs(got - ref).max(), nlev)
+
+
+def test_amr_2d_bitwise():
+    regs = [dict(type="square", x_center=0.5, y_center=0.5, length_x=10, length_y=10, exp_region=10, d=1.0, p=0.1),
+            dict(type="square", x_center=0.3, y_center=0.4, length_x=0.3, length_y=0.25, exp_region=2, d=2.0, u=0.3, v=-0.2, p=1.0)]
+    got, ref, dtnew, r, nlev = run_case(2, 3, 5, (1, 1, 2, 2, 0, 0), regs, "hllc", 2, 2, 2, [1, 2])
+    assert dtnew[3] == r.dtnew[3]
+    assert np.array_equal(got, ref), (np.abs(got - ref).max(), nlev)
+
+
+@pytest.mark.parametrize("riemann", ["hllc", "exact"])
+def test_amr_3d_sedov_like(riemann):
+    regs = [dict(type="square", x_center=0.5, y_center=0.5, z_center=0.5, length_x=10, length_y=10, length_z=10, exp_region=10, d=1.0, p=0.1),
+            dict(type="square", x_center=0.4, y_center=0.45, z_center=0.55, length_x=0.3, length_y=0.3, length_z=0.3, exp_region=2, d=1.5, p=2.0)]
+    got, ref, dtnew, r, nlev = run_case(3, 3, 4, (0,) * 6, regs, riemann, 1, 1, 1, [2, 2])
+    if riemann == "exact":
+        scale = np.abs(ref).max(axis=1, keepdims=True)
+        assert (np.abs(got - ref) / scale).max() <= 1e-12
+    else:
+        assert np.array_equal(got, ref), (np.abs(got - ref).max(), nlev)
