@@ -46,6 +46,10 @@
 
 int orc_abi_version(void) { return 1; }
 
+/* host threads for the per-level passes (the reference spreads every pass over its MPI ranks) */
+static int g_nthreads = 1;
+void orc_set_threads(int n) { g_nthreads = n < 1 ? 1 : n; }
+
 /* module const (hydro/hydro_commons.f90:14-27) */
 static const double zero = 0.0, one = 1.0, two = 2.0, half = 0.5;
 
@@ -1372,8 +1376,12 @@ void orc_set_unew(const orc_params* p, const orc_mesh* m, int ilevel, const doub
   const int twotondim = ipow2(p->ndim);
   for (int ind = 0; ind < twotondim; ind++) {
     int iskip = m->ncoarse + ind * m->ngridmax;
-    for (int iv = 1; iv <= p->nvar; iv++)
+    for (int iv = 1; iv <= p->nvar; iv++) {
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(g_nthreads) schedule(static)
+#endif
       for (int a = 0; a < m->nactive[ilevel]; a++) UN(m->active[ilevel][a] + iskip, iv) = UO(m->active[ilevel][a] + iskip, iv);
+    }
   }
   for (int ind = 0; ind < twotondim; ind++) { /* :93-126 */
     int iskip = m->ncoarse + ind * m->ngridmax;
@@ -1400,8 +1408,12 @@ void orc_set_uold(const orc_params* p, const orc_mesh* m, int ilevel, double* uo
         }
       }
     }
-    for (int iv = 1; iv <= nvar; iv++)
+    for (int iv = 1; iv <= nvar; iv++) {
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(g_nthreads) schedule(static)
+#endif
       for (int a = 0; a < m->nactive[ilevel]; a++) UO(m->active[ilevel][a] + iskip, iv) = UN(m->active[ilevel][a] + iskip, iv);
+    }
   }
 }
 
@@ -1637,36 +1649,46 @@ double orc_courant_fine(const orc_params* p, const orc_mesh* m, int ilevel, doub
   double vol = 1;
   for (int d = 0; d < ndim; d++) vol *= dx; /* dx**ndim */
   double mass_loc = 0, ekin_loc = 0, eint_loc = 0, dt_loc = dt_in;
-  double* uu = (double*)calloc((size_t)nv * nvar, 8);
-  int* ind_leaf = (int*)calloc(nv, sizeof(int));
   const int ncache = m->nactive[ilevel];
-  for (int igrid = 0; igrid < ncache; igrid += nv) {
-    int ngrid = IMIN(nv, ncache - igrid);
-    for (int ind = 0; ind < twotondim; ind++) {
-      int iskip = m->ncoarse + ind * m->ngridmax;
-      int nleaf = 0;
-      for (int i = 0; i < ngrid; i++) {
-        int ic = m->active[ilevel][igrid + i] + iskip;
-        if (m->son[ic] == 0) ind_leaf[nleaf++] = ic;
-      }
-      for (int iv = 1; iv <= nvar; iv++)
-        for (int i = 0; i < nleaf; i++) uu[i + (size_t)nv * (iv - 1)] = UO(ind_leaf[i], iv);
-      for (int i = 0; i < nleaf; i++) mass_loc = mass_loc + uu[i] * vol;
-      for (int i = 0; i < nleaf; i++) ekin_loc = ekin_loc + uu[i + (size_t)nv * (ndim + 1)] * vol;
-      for (int i = 0; i < nleaf; i++) eint_loc = eint_loc + uu[i + (size_t)nv * (ndim + 1)] * vol;
-      for (int iv = 1; iv <= ndim; iv++)
-        for (int i = 0; i < nleaf; i++) {
-          double mo = uu[i + (size_t)nv * iv];
-          eint_loc = eint_loc - 0.5 * (mo * mo) / FMAX(uu[i], p->smallr) * vol;
+  const int nbatch = (ncache + nv - 1) / nv;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(g_nthreads) reduction(+ : mass_loc, ekin_loc, eint_loc) reduction(min : dt_loc)
+#endif
+  {
+    double* uu = (double*)calloc((size_t)nv * nvar, 8);
+    int* ind_leaf = (int*)calloc(nv, sizeof(int));
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+    for (int b = 0; b < nbatch; b++) {
+      const int igrid = b * nv;
+      int ngrid = IMIN(nv, ncache - igrid);
+      for (int ind = 0; ind < twotondim; ind++) {
+        int iskip = m->ncoarse + ind * m->ngridmax;
+        int nleaf = 0;
+        for (int i = 0; i < ngrid; i++) {
+          int ic = m->active[ilevel][igrid + i] + iskip;
+          if (m->son[ic] == 0) ind_leaf[nleaf++] = ic;
         }
-      if (nleaf > 0) {
-        double dt_lev;
-        orc_cmpdt(p, uu, NULL, dx, &dt_lev, nleaf);
-        dt_loc = FMIN(dt_loc, dt_lev);
+        for (int iv = 1; iv <= nvar; iv++)
+          for (int i = 0; i < nleaf; i++) uu[i + (size_t)nv * (iv - 1)] = UO(ind_leaf[i], iv);
+        for (int i = 0; i < nleaf; i++) mass_loc = mass_loc + uu[i] * vol;
+        for (int i = 0; i < nleaf; i++) ekin_loc = ekin_loc + uu[i + (size_t)nv * (ndim + 1)] * vol;
+        for (int i = 0; i < nleaf; i++) eint_loc = eint_loc + uu[i + (size_t)nv * (ndim + 1)] * vol;
+        for (int iv = 1; iv <= ndim; iv++)
+          for (int i = 0; i < nleaf; i++) {
+            double mo = uu[i + (size_t)nv * iv];
+            eint_loc = eint_loc - 0.5 * (mo * mo) / FMAX(uu[i], p->smallr) * vol;
+          }
+        if (nleaf > 0) {
+          double dt_lev;
+          orc_cmpdt(p, uu, NULL, dx, &dt_lev, nleaf);
+          dt_loc = FMIN(dt_loc, dt_lev);
+        }
       }
     }
+    free(uu); free(ind_leaf);
   }
-  free(uu); free(ind_leaf);
   if (sums) { sums[0] += mass_loc; sums[1] += ekin_loc; sums[2] += eint_loc; }
   return FMIN(dt_in, dt_loc);
 }
@@ -1723,6 +1745,7 @@ void orc_make_boundary_hydro(const orc_params* p, const orc_mesh* m, int ilevel,
 void orc_run_uniform(const orc_params* p, const orc_mesh* m, int ilevel, int nstep, double* uold, double* unew,
                      double* dt_hist, double* t_io, int nthreads) {
   double t = t_io ? *t_io : 0.0;
+  orc_set_threads(nthreads);
   orc_make_boundary_hydro(p, m, ilevel, uold);
   for (int s = 0; s < nstep; s++) {
     double sums[3] = {0, 0, 0};

@@ -133,6 +133,7 @@ void orc_interpol_cell(const orc_params*, const orc_mesh*, int ind_cell, int ile
 orc_mesh* orc_mesh_new(int ndim, const int bound_type[6], int ngridmax, int nlevelmax);
 void orc_mesh_set_list(orc_mesh*, int kind, int b, int ilevel, int n, const int* igrid);
 
+void orc_set_threads(int n);
 int orc_abi_version(void);
 
 #ifdef __cplusplus
