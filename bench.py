@@ -10,6 +10,8 @@ A "step" is one level step of a levelmin=levelmax run: courant_fine -> set_unew 
 With N ranks every rank owns one 256^3 coarse cell of an (nx,ny,nz) periodic coarse grid (weak scaling, 512^3 at
 N=8), ghost octs exchanged with ncclSend/ncclRecv.  Prints ONE JSON line on rank 0.
 """
+import os
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # CPU baseline: idle OpenMP threads must not spin on a shared host
 import argparse
 import ctypes as C
 import json
@@ -123,21 +125,37 @@ def host_threads():
 
 def cpu_reference_run(workload, steps, warmup, sample_level=7):
     """The reference algorithm on the host cores: oracle/ (C restatement of RAMSES, reference-shaped per-oct
-    6^3 patches, nvector=32 batches, OpenMP over batches).  The F90 itself cannot be built (no gfortran/MPI)."""
+    6^3 patches, nvector=32 batches, OpenMP over batches).  The F90 itself cannot be built (no gfortran/MPI).
+    The thread count is calibrated (8, 16, ... up to all host threads) on a 64^3 step and the fastest is used:
+    the GPU hosts are shared, oversubscribed thread teams run slower than smaller ones."""
     from oracle import orc
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import SEDOV3D_REGIONS, smooth_state
     w = WORKLOADS[workload]
-    nthr = host_threads()
     p = orc.make_params(ndim=3, riemann=w["riemann"], slope_type=w["slope_type"], boxlen=0.5, gamma=GAMMA,
                         courant_factor=0.8)
-    m = orc.Mesh(3, sample_level, order=0)
-    u = m.new_state(5)
-    if w["ic"] == "sedov":
-        from helpers import SEDOV3D_REGIONS
-        orc.condinit_regions(p, m, sample_level, u, SEDOV3D_REGIONS)
-    else:
-        from helpers import smooth_state
-        m.dense_to_level(smooth_state(3, 1 << sample_level), u, sample_level, 5)
+
+    def setup(level):
+        m = orc.Mesh(3, level, order=0)
+        u = m.new_state(5)
+        if w["ic"] == "sedov":
+            orc.condinit_regions(p, m, level, u, SEDOV3D_REGIONS)
+        else:
+            m.dense_to_level(smooth_state(3, 1 << level), u, level, 5)
+        return m, u
+    nmax = host_threads()
+    cands = sorted({min(nmax, c) for c in (8, 16, 32, 64, 128, nmax)})
+    mc, uc = setup(6)
+    best, best_rate = cands[0], 0.0
+    for c in cands:
+        orc.run_uniform(p, mc, 6, 1, uc, nthreads=c)
+        t0 = time.perf_counter()
+        orc.run_uniform(p, mc, 6, 2, uc, nthreads=c)
+        rate = 2 * 64 ** 3 / (time.perf_counter() - t0)
+        if rate > best_rate:
+            best, best_rate = c, rate
+    nthr = best
+    m, u = setup(sample_level)
     ncell = (1 << sample_level) ** 3
     if warmup:
         orc.run_uniform(p, m, sample_level, warmup, u, nthreads=nthr)
@@ -148,7 +166,8 @@ def cpu_reference_run(workload, steps, warmup, sample_level=7):
     return {"value": ncell * steps / el, "unit": "cell-updates/s", "cores": nthr, "kind": "port",
             "sample": f"{w['ic']} {n}^3 periodic, riemann={w['riemann']}, {steps} level steps "
                       f"(courant_fine+set_unew+godunov_fine+set_uold), C restatement of the RAMSES algorithm "
-                      f"(oracle/ramses_oracle.c, gcc -O2 -ffp-contract=off, OpenMP over nvector=32 oct batches)",
+                      f"(oracle/ramses_oracle.c, gcc -O2 -ffp-contract=off, OpenMP over nvector=32 oct batches); "
+                      f"{nthr} of {nmax} host threads (fastest of a calibration sweep)",
             "seconds": el}, el / steps
 
 

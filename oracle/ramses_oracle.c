@@ -1374,13 +1374,18 @@ void orc_condinit_regions(const orc_params* p, const orc_mesh* m, int ilevel, do
 /* set_unew hydro/godunov_fine.f90:40-130 */
 void orc_set_unew(const orc_params* p, const orc_mesh* m, int ilevel, const double* uold, double* unew) {
   const int twotondim = ipow2(p->ndim);
+  const int na = m->nactive[ilevel];
+  const int* act = m->active[ilevel];
+#ifdef _OPENMP
+#pragma omp parallel num_threads(g_nthreads) if (g_nthreads > 1)
+#endif
   for (int ind = 0; ind < twotondim; ind++) {
-    int iskip = m->ncoarse + ind * m->ngridmax;
+    const int iskip = m->ncoarse + ind * m->ngridmax;
     for (int iv = 1; iv <= p->nvar; iv++) {
 #ifdef _OPENMP
-#pragma omp parallel for num_threads(g_nthreads) schedule(static)
+#pragma omp for schedule(static) nowait
 #endif
-      for (int a = 0; a < m->nactive[ilevel]; a++) UN(m->active[ilevel][a] + iskip, iv) = UO(m->active[ilevel][a] + iskip, iv);
+      for (int a = 0; a < na; a++) UN(act[a] + iskip, iv) = UO(act[a] + iskip, iv);
     }
   }
   for (int ind = 0; ind < twotondim; ind++) { /* :93-126 */
@@ -1408,9 +1413,12 @@ void orc_set_uold(const orc_params* p, const orc_mesh* m, int ilevel, double* uo
         }
       }
     }
+#ifdef _OPENMP
+#pragma omp parallel num_threads(g_nthreads) if (g_nthreads > 1)
+#endif
     for (int iv = 1; iv <= nvar; iv++) {
 #ifdef _OPENMP
-#pragma omp parallel for num_threads(g_nthreads) schedule(static)
+#pragma omp for schedule(static) nowait
 #endif
       for (int a = 0; a < m->nactive[ilevel]; a++) UO(m->active[ilevel][a] + iskip, iv) = UN(m->active[ilevel][a] + iskip, iv);
     }
@@ -1652,7 +1660,7 @@ double orc_courant_fine(const orc_params* p, const orc_mesh* m, int ilevel, doub
   const int ncache = m->nactive[ilevel];
   const int nbatch = (ncache + nv - 1) / nv;
 #ifdef _OPENMP
-#pragma omp parallel num_threads(g_nthreads) reduction(+ : mass_loc, ekin_loc, eint_loc) reduction(min : dt_loc)
+#pragma omp parallel num_threads(g_nthreads) reduction(+ : mass_loc, ekin_loc, eint_loc) reduction(min : dt_loc) if (g_nthreads > 1)
 #endif
   {
     double* uu = (double*)calloc((size_t)nv * nvar, 8);

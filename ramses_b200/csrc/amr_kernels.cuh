@@ -463,6 +463,25 @@ __global__ void amr_copy_octs_kernel(const double* __restrict__ src, double* __r
   const size_t c = (size_t)iv * ncell + ncoarse + (size_t)ind * ngridmax + igrid[o] - 1;
   dst[c] = src[c];
 }
+// ghost-oct exchange buffers on the mirrored arrays: all variables and all cells of the listed octs in one message
+// (make_virtual_fine_dp / make_virtual_reverse_dp, amr/virtual_boundaries.f90:373,693)
+__global__ void amr_pack_kernel(const double* __restrict__ u, const int* __restrict__ igrid, int n, int ncoarse, int ngridmax,
+                                long long ncell, int T, int nvar, double* __restrict__ buf) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n * T * nvar) return;
+  const int o = (int)(i % n), ind = (int)((i / n) % T), iv = (int)(i / ((long long)n * T));
+  buf[i] = u[(size_t)iv * ncell + ncoarse + (size_t)ind * ngridmax + igrid[o] - 1];
+}
+__global__ void amr_unpack_kernel(double* __restrict__ u, const int* __restrict__ igrid, int n, int ncoarse, int ngridmax, long long ncell,
+                                  int T, int nvar, const double* __restrict__ buf, int mode /*0 copy, 1 accumulate, 2 zero*/) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n * T * nvar) return;
+  const int o = (int)(i % n), ind = (int)((i / n) % T), iv = (int)(i / ((long long)n * T));
+  const size_t c = (size_t)iv * ncell + ncoarse + (size_t)ind * ngridmax + igrid[o] - 1;
+  if (mode == 0) u[c] = buf[i];
+  else if (mode == 1) u[c] = u[c] + buf[i];
+  else u[c] = 0.0;
+}
 // upload_fine (hydro/interpol_hydro.f90:5, upl :73): split cells <- mean of their sons
 __global__ void amr_upload_kernel(double* __restrict__ u, const int* __restrict__ son1, const int* __restrict__ igrid, int n, int ncoarse,
                                   int ngridmax, long long ncell, int T, int nvar, double smallr) {

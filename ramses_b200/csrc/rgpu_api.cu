@@ -100,11 +100,13 @@ struct Level {
 
 // AMR mode (levelmin < levelmax): the device mirrors the reference arrays, every level is a list of octs
 struct AmrRegion { int type = 0, n = 0; int* d_igrid = nullptr; };
+struct AmrPeer { int nrecv = 0, nemit = 0; int *d_recv = nullptr, *d_emit = nullptr; double *d_sbuf = nullptr, *d_rbuf = nullptr; };
 struct AmrLevel {
   bool bound = false;
   int nact = 0;
   int* d_active = nullptr;
   std::vector<AmrRegion> regions;
+  std::vector<AmrPeer> peers;
   double* d_rflux = nullptr;
   int nent = 0;                       // coarse cells that receive refluxes from this level
   int *d_rcell = nullptr, *d_rstart = nullptr, *d_rsrc = nullptr;
@@ -473,6 +475,7 @@ void free_amr_level(AmrLevel& A) {
   cudaFree(A.d_active); cudaFree(A.d_rflux); cudaFree(A.d_rcell); cudaFree(A.d_rstart); cudaFree(A.d_rsrc);
   cudaFree(A.d_part); cudaFree(A.d_out); cudaFree(A.d_dt);
   for (auto& r : A.regions) cudaFree(r.d_igrid);
+  for (auto& p : A.peers) { cudaFree(p.d_recv); cudaFree(p.d_emit); cudaFree(p.d_sbuf); cudaFree(p.d_rbuf); }
   A = AmrLevel();
 }
 int check_amr_level(int ilevel, AmrLevel** out) {
@@ -484,16 +487,35 @@ int check_amr_level(int ilevel, AmrLevel** out) {
   *out = &A;
   return RGPU_OK;
 }
-int amr_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int ncpu, int nboundary, const int* boundary_type,
+int amr_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int ncpu, const int* ngrid_recv, const int* const* igrid_recv,
+                   const int* ngrid_emit, const int* const* igrid_emit, int nboundary, const int* boundary_type,
                    const int* ngrid_bound, const int* const* igrid_bound) {
-  if (ncpu > 1) return fail(RGPU_EUNSUPPORTED, "AMR mode is single-rank for now (ghost-oct exchange on oct lists not built)");
   AmrLevel& A = G.alev[ilevel];
   if (A.bound) free_amr_level(A);
+  if (ncpu > 1 && ngrid_recv && igrid_recv && ngrid_emit && igrid_emit) {
+    const size_t per = (size_t)G.p.nvar * T_();
+    A.peers.resize(ncpu);
+    for (int cpu = 0; cpu < ncpu; cpu++) {
+      if (cpu == G.myid - 1) continue;
+      AmrPeer& P = A.peers[cpu];
+      P.nrecv = ngrid_recv[cpu]; P.nemit = ngrid_emit[cpu];
+      if (P.nrecv) {
+        CUDA_OK(cudaMalloc(&P.d_recv, sizeof(int) * P.nrecv));
+        CUDA_OK(cudaMemcpy(P.d_recv, igrid_recv[cpu], sizeof(int) * P.nrecv, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&P.d_rbuf, sizeof(double) * per * P.nrecv));
+      }
+      if (P.nemit) {
+        CUDA_OK(cudaMalloc(&P.d_emit, sizeof(int) * P.nemit));
+        CUDA_OK(cudaMemcpy(P.d_emit, igrid_emit[cpu], sizeof(int) * P.nemit, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&P.d_sbuf, sizeof(double) * per * P.nemit));
+      }
+    }
+  }
   const int nd = G.p.ndim, nvar = G.p.nvar, TW = 2 * nd, NSF = 1 << (nd - 1);
   A.dx = level_dx(ilevel);
   A.nact = ngrid_active;
   CUDA_OK(cudaMalloc(&A.d_active, sizeof(int) * std::max(1, ngrid_active)));
-  CUDA_OK(cudaMemcpy(A.d_active, igrid_active, sizeof(int) * ngrid_active, cudaMemcpyHostToDevice));
+  if (ngrid_active > 0) CUDA_OK(cudaMemcpy(A.d_active, igrid_active, sizeof(int) * ngrid_active, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&A.d_rflux, sizeof(double) * (size_t)std::max(1, ngrid_active) * TW * NSF * nvar));
   A.regions.resize(nboundary);
   for (int b = 0; b < nboundary; b++) {
@@ -593,6 +615,51 @@ int amr_copy(AmrLevel& A, const double* src, double* dst) {
   A.launches++;
   return RGPU_OK;
 }
+// make_virtual_fine_dp (forward: emission octs -> peers' reception octs, copy) / make_virtual_reverse_dp (reverse:
+// reception octs -> owners' emission octs, accumulate in peer order) on the mirrored arrays, one NCCL group per call
+int amr_exchange(AmrLevel& A, double* u, bool reverse) {
+  if (A.peers.empty()) return RGPU_OK;
+  if (!G.comm) return fail(RGPU_EINVAL, "ghost exchange needs rgpu_comm_init");
+  const int T = T_(), nvar = G.p.nvar;
+  const long long per = (long long)T * nvar;
+  for (auto& P : A.peers) {
+    const int n = reverse ? P.nrecv : P.nemit;
+    if (!n) continue;
+    amr_pack_kernel<<<(unsigned)((n * per + 255) / 256), 256, 0, G.stream>>>(u, reverse ? P.d_recv : P.d_emit, n, G.ncoarse, G.ngridmax, G.ncell, T, nvar,
+                                                                            reverse ? P.d_rbuf : P.d_sbuf);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  NCCL_OK(ncclGroupStart());
+  for (int cpu = 0; cpu < (int)A.peers.size(); cpu++) {
+    AmrPeer& P = A.peers[cpu];
+    const int nsend = reverse ? P.nrecv : P.nemit, nrecv = reverse ? P.nemit : P.nrecv;
+    if (nsend) NCCL_OK(ncclSend(reverse ? P.d_rbuf : P.d_sbuf, (size_t)nsend * per, ncclDouble, cpu, G.comm, G.stream));
+    if (nrecv) NCCL_OK(ncclRecv(reverse ? P.d_sbuf : P.d_rbuf, (size_t)nrecv * per, ncclDouble, cpu, G.comm, G.stream));
+  }
+  NCCL_OK(ncclGroupEnd());
+  for (auto& P : A.peers) {
+    const int n = reverse ? P.nemit : P.nrecv;
+    if (!n) continue;
+    amr_unpack_kernel<<<(unsigned)((n * per + 255) / 256), 256, 0, G.stream>>>(u, reverse ? P.d_emit : P.d_recv, n, G.ncoarse, G.ngridmax, G.ncell, T, nvar,
+                                                                              reverse ? P.d_sbuf : P.d_rbuf, reverse ? 1 : 0);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  return RGPU_OK;
+}
+int amr_zero_ghost_unew(AmrLevel& A) {   // set_unew: unew = 0 in the reception octs (godunov_fine.f90:93-100)
+  const long long per = (long long)T_() * G.p.nvar;
+  for (auto& P : A.peers)
+    if (P.nrecv) {
+      amr_unpack_kernel<<<(unsigned)((P.nrecv * per + 255) / 256), 256, 0, G.stream>>>(G.d_unew, P.d_recv, P.nrecv, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar,
+                                                                                   nullptr, 2);
+      CUDA_OK(cudaGetLastError());
+      A.launches++;
+    }
+  return RGPU_OK;
+}
+
 int amr_boundaries(AmrLevel& A) {
   static const int ref_x[8] = {2, 1, 4, 3, 6, 5, 8, 7}, ref_y[8] = {3, 4, 1, 2, 7, 8, 5, 6}, ref_z[8] = {5, 6, 7, 8, 1, 2, 3, 4};
   static const int fre[6][8] = {{1, 1, 3, 3, 5, 5, 7, 7}, {2, 2, 4, 4, 6, 6, 8, 8}, {1, 2, 1, 2, 5, 6, 5, 6},
@@ -848,8 +915,8 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
   if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
   if (!G.son) return fail(RGPU_EINVAL, "rgpu_bind_tree has not been called");
   if (ilevel < 1 || ilevel > MAXLEVEL) return fail(RGPU_EINVAL, "ilevel %d out of range", ilevel);
-  if (ngrid_active <= 0 || !igrid_active) return fail(RGPU_EINVAL, "level %d has no active oct", ilevel);
-  if (G.amr) return amr_bind_level(ilevel, ngrid_active, igrid_active, ncpu, nboundary, boundary_type, ngrid_bound, igrid_bound);
+  if (!G.amr && (ngrid_active <= 0 || !igrid_active)) return fail(RGPU_EINVAL, "level %d has no active oct", ilevel);
+  if (G.amr) return amr_bind_level(ilevel, ngrid_active, igrid_active, ncpu, ngrid_recv, igrid_recv, ngrid_emit, igrid_emit, nboundary, boundary_type, ngrid_bound, igrid_bound);
   Level& L = G.lev[ilevel];
   if (L.bound) free_level(L);
   {
@@ -1036,7 +1103,7 @@ int rgpu_download_state(int ilevel, double* uold) {
 }
 
 int rgpu_set_unew(int ilevel) {
-  if (G.amr) { AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc; return amr_copy(*A, G.d_uold, G.d_unew); }
+  if (G.amr) { AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc; rc = amr_copy(*A, G.d_uold, G.d_unew); if (rc) return rc; return amr_zero_ghost_unew(*A); }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   const size_t n = nplanes_() * (size_t)L->nslot;
   copy_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, G.stream>>>(L->d_u[L->cur], L->d_u[1 - L->cur], n);
@@ -1083,7 +1150,6 @@ int rgpu_courant_fine(int ilevel, double* dt_io, double sums[3]) {
   if (G.amr) {
     AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
     if (!dt_io) return fail(RGPU_EINVAL, "null dt");
-    if (A->nact == 0) return RGPU_OK;
     const int nb = 148 * 8;
     if (G.p.ndim == 1) amr_courant_kernel<1><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A->d_active, A->nact, G.phys, A->dx, A->d_part);
     else if (G.p.ndim == 2) amr_courant_kernel<2><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A->d_active, A->nact, G.phys, A->dx, A->d_part);
@@ -1093,6 +1159,10 @@ int rgpu_courant_fine(int ilevel, double* dt_io, double sums[3]) {
     courant_reduce_kernel<<<1, 1024, 0, G.stream>>>(A->d_part, nb, *dt_io, dt0, vol, A->d_out, A->d_dt, nullptr);
     CUDA_OK(cudaGetLastError());
     A->launches += 2;
+    if (G.comm && G.nranks > 1) {   // MPI_ALLREDUCE MIN(1) + SUM(3), courant_fine.f90:138-141
+      NCCL_OK(ncclAllReduce(A->d_out, A->d_out, 1, ncclDouble, ncclMin, G.comm, G.stream));
+      NCCL_OK(ncclAllReduce(A->d_out + 1, A->d_out + 1, 3, ncclDouble, ncclSum, G.comm, G.stream));
+    }
     double out[4];
     CUDA_OK(cudaMemcpyAsync(out, A->d_out, sizeof(out), cudaMemcpyDeviceToHost, G.stream));
     CUDA_OK(cudaStreamSynchronize(G.stream));
@@ -1126,12 +1196,12 @@ int rgpu_make_boundary_hydro(int ilevel) {
 }
 
 int rgpu_make_virtual_fine(int ilevel) {
-  if (G.amr) return RGPU_OK;   // single rank: no virtual boundaries
+  if (G.amr) { AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc; return amr_exchange(*A, G.d_uold, false); }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   return exchange_ghosts(*L, L->d_u[L->cur], false);
 }
 int rgpu_make_virtual_reverse(int ilevel) {
-  if (G.amr) return RGPU_OK;
+  if (G.amr) { AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc; return amr_exchange(*A, G.d_unew, true); }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (!L->unew_valid) return fail(RGPU_EINVAL, "make_virtual_reverse before godunov_fine");
   return exchange_ghosts(*L, L->d_u[1 - L->cur], true);
