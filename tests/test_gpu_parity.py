@@ -216,3 +216,19 @@ def test_multi_gpu_bit_identical_to_single_gpu(gpu):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "state identical=True" in r.stdout
+
+
+def test_multi_gpu_amr_matches_single_gpu(gpu):
+    """AMR mode with NCCL ghost-oct exchange (forward copy + reverse reflux accumulation) on 2 GPUs == one GPU
+    (<= 1e-13: refluxes arriving from different ranks are summed in a different order)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(root, "tests", "mgpu_amr_check.py"), "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
