@@ -232,3 +232,50 @@ def test_multi_gpu_amr_matches_single_gpu(gpu):
            "--master-port", "29641", os.path.join(root, "tests", "mgpu_amr_check.py"), "2"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_full_size_256_properties(gpu):
+    """BASELINE config 2 at full size (sedov3d 256^3, exact Riemann, 10 level steps) through size-independent
+    properties: mass and energy conserved to round-off on the periodic box (mcons/econs of doc/wiki/Start.md), the
+    x<->y<->z permutation symmetry of the corner blast, positivity, and dt of the first step equal to the oracle's
+    closed form for the initial state."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import sedov_ic
+    from ramses_b200.hydro import HydroGPU
+    from ramses_b200.tree import build_uniform_tree, fill_state
+    level, n = 8, 256
+    a = build_uniform_tree(3, level, order="creation", boxlen=0.5)
+    a.gamma, a.courant_factor, a.slope_type, a.riemann = 1.4, 0.8, 1, "exact"
+    fill_state(a, level, sedov_ic(0.5, 1, level))
+    ig = a.active[level].astype(np.int64)
+    cells = np.concatenate([a.ncoarse + ind * a.ngridmax + ig - 1 for ind in range(8)])
+    m0, e0 = a.uold[0, cells].sum(), a.uold[4, cells].sum()
+    h = HydroGPU(a)
+    h.bind_level(level)
+    h.upload_state(level)
+    dts, sums = h.level_steps(level, 10)
+    h.download_state(level)
+    h.finalize()
+    u = a.uold[:, cells]
+    assert abs(u[0].sum() - m0) <= 1e-13 * m0
+    assert abs(u[4].sum() - e0) <= 1e-12 * e0
+    assert u[0].min() > 0 and np.isfinite(u).all()
+    # dt of step 1: the hottest cell (the one holding the blast energy) sets it, cmpdt (godunov_utils.f90:5-120)
+    dx = 0.5 / n
+    pmax = 1e-5 + 0.4 * 0.125 / dx ** 3
+    ws = 3 * np.sqrt(1.4 * pmax / 1.0)
+    g = 1e-4
+    assert abs(dts[0] - dx / ws * (np.sqrt(1 + 2 * 0.8 * g) - 1) / g) <= 1e-14 * dts[0]
+    assert np.all(np.diff(dts) != 0)
+    # permutation symmetry: gather a 16^3 corner block (the blast has not left it after 10 steps)
+    pos = a._pos[level][ig - a._igrid0[level]]
+    dense = np.zeros((5, 16, 16, 16))
+    for ind in range(8):
+        c = 2 * pos + np.array([(ind >> d) & 1 for d in range(3)])[None, :]
+        sel = (c < 16).all(axis=1)
+        dense[:, c[sel, 2], c[sel, 1], c[sel, 0]] = a.uold[:, a.ncoarse + ind * a.ngridmax + ig[sel] - 1]
+    assert np.abs(dense[0] - dense[0].transpose(0, 2, 1)).max() <= 1e-12 * dense[0].max()
+    assert np.abs(dense[0] - dense[0].transpose(2, 1, 0)).max() <= 1e-12 * dense[0].max()
+    assert np.abs(dense[1] - dense[2].transpose(0, 2, 1)).max() <= 1e-11 * np.abs(dense[1]).max()
+    assert dense[0].max() > 1.05          # the blast is there
