@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RGPU_ABI_VERSION 1
+#define RGPU_ABI_VERSION 2
 
 enum {
   RGPU_OK = 0,
@@ -56,7 +56,16 @@ typedef struct rgpu_params {
   int nx, ny, nz;      /* coarse grid incl. boundary cells (amr_parameters)   */
   int icoarse_min, icoarse_max, jcoarse_min, jcoarse_max, kcoarse_min, kcoarse_max;
   int nlevelmax;
+  /* ideal-MHD build (SOLVER=mhd, bin/Makefile:20; mhd/ shadows hydro/ through VPATH): NDIM=3, nvar=8; the state arrays
+   * then hold nvar+3 = 11 variables (left-face B in 6:8, right-face B in nvar+1:nvar+3, mhd/hydro_parameters.f90:15-30). */
+  int mhd;             /* 0: hydro build, 1: MHD build                          */
+  int riemann2d;       /* RGPU_MHD2D_* (mhd/hydro_parameters.f90:104)           */
+  int slope_mag_type;  /* mhd/hydro_parameters.f90:93; -1 = slope_type (hydro/read_hydro_params.f90:528) */
+  int pad_;
 } rgpu_params;
+/* `riemann` / `riemann2d` of the MHD build: iriemann, iriemann2d (hydro/read_hydro_params.f90:190-220) */
+enum { RGPU_MHD_LLF = 0, RGPU_MHD_ROE = 1, RGPU_MHD_HLL = 2, RGPU_MHD_HLLD = 3, RGPU_MHD_UPWIND = 4, RGPU_MHD_HYDRO = 5 };
+enum { RGPU_MHD2D_LLF = 0, RGPU_MHD2D_ROE = 1, RGPU_MHD2D_UPWIND = 2, RGPU_MHD2D_HLL = 3, RGPU_MHD2D_HLLA = 4, RGPU_MHD2D_HLLD = 5 };
 
 /* ---- life cycle -------------------------------------------------------------
  * rgpu_init: once, after read_params (amr/read_params.f90:1).  device<0 picks
@@ -123,7 +132,8 @@ int rgpu_set_unew(int ilevel);                             /* hydro/godunov_fine
 int rgpu_godunov_fine_dev(int ilevel, double dt);          /* hydro/godunov_fine.f90:5         */
 int rgpu_set_uold(int ilevel);                             /* hydro/godunov_fine.f90:135       */
 /* courant_fine (hydro/courant_fine.f90:1): *dt_io = min(*dt_io, CFL dt over the leaf
- * cells of the level [over all ranks]); sums[3] += (mass, total E, internal E)      */
+ * cells of the level [over all ranks]); sums[3] += (mass, total E, internal E).
+ * MHD build (mhd/courant_fine.f90:1): sums must hold 4 values, sums[3] += magnetic E */
 int rgpu_courant_fine(int ilevel, double* dt_io, double sums[3]);
 int rgpu_make_boundary_hydro(int ilevel);                  /* hydro/hydro_boundary.f90:5       */
 int rgpu_make_virtual_fine(int ilevel);                    /* amr/virtual_boundaries.f90:373, all nvar at once */

@@ -16,8 +16,8 @@ MAXBOUND = 6
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "ramses_oracle.c")
-    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("ramses_oracle.c", "ramses_oracle.h", "ramses_oracle_mhd.c", "ramses_oracle_mhd.h")]
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libramses_oracle.so"])
     return _LIB
 
@@ -44,6 +44,16 @@ class MeshS(C.Structure):
                 ("bound", C.POINTER(C.POINTER(C.c_int)) * MAXBOUND),
                 ("ngrid_used", C.c_int)]
 
+
+class MhdParams(C.Structure):
+    _fields_ = [("slope_type", C.c_int), ("slope_mag_type", C.c_int), ("riemann", C.c_int), ("riemann2d", C.c_int),
+                ("gamma", C.c_double), ("smallr", C.c_double), ("smallc", C.c_double), ("slope_theta", C.c_double),
+                ("courant_factor", C.c_double), ("boxlen", C.c_double)]
+
+
+MHD_RIEMANN = {"llf": 0, "roe": 1, "hll": 2, "hlld": 3, "upwind": 4, "hydro": 5}
+MHD_RIEMANN2D = {"llf": 0, "roe": 1, "upwind": 2, "hll": 3, "hlla": 4, "hlld": 5}
+MHD_NVAR = 8          # nvar of the MHD build; 11 = nvar+3 variables are stored (right-face B in 9..11)
 
 _lib = None
 
@@ -80,6 +90,29 @@ def lib():
         L.orc_work_new.argtypes = [pp]
         L.orc_work_free.argtypes = [C.c_void_p]
         L.orc_unsplit.argtypes = [pp, C.c_void_p, dp, dp, dp, dp] + [C.c_double] * 4 + [C.c_int]
+        # ideal-MHD variant (oracle/ramses_oracle_mhd.c)
+        mpp = C.POINTER(MhdParams)
+        L.orc_mhd_work_new.restype = C.c_void_p
+        L.orc_mhd_work_free.argtypes = [C.c_void_p]
+        for nm in ("uloc", "flux"):
+            getattr(L, "orc_mhd_work_" + nm).restype = dp
+            getattr(L, "orc_mhd_work_" + nm).argtypes = [C.c_void_p]
+        L.orc_mhd_work_emf.restype = dp
+        L.orc_mhd_work_emf.argtypes = [C.c_void_p, C.c_int]
+        L.orc_mhd_riemann.argtypes = [mpp, dp, dp, dp]
+        L.orc_mhd_emf.restype = C.c_double
+        L.orc_mhd_emf.argtypes = [mpp, dp, dp, dp, dp, C.c_int]
+        L.orc_mhd_unsplit.argtypes = [mpp, C.c_void_p, C.c_double, C.c_double]
+        L.orc_mhd_cmpdt_cell.restype = C.c_double
+        L.orc_mhd_cmpdt_cell.argtypes = [mpp, dp, C.c_double]
+        L.orc_mhd_set_unew.argtypes = [mp, C.c_int, dp, dp]
+        L.orc_mhd_set_uold.argtypes = [mp, C.c_int, dp, dp]
+        L.orc_mhd_godunov_fine.argtypes = [mpp, mp, C.c_int, C.c_double, dp, dp, C.c_int]
+        L.orc_mhd_courant_fine.restype = C.c_double
+        L.orc_mhd_courant_fine.argtypes = [mpp, mp, C.c_int, C.c_double, dp, dp]
+        L.orc_mhd_make_boundary_hydro.argtypes = [mpp, mp, C.c_int, dp]
+        L.orc_mhd_run_uniform.argtypes = [mpp, mp, C.c_int, C.c_int, dp, dp, dp, dp, C.c_int]
+        L.orc_mhd_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -226,3 +259,43 @@ def run_uniform(p, mesh, l, nstep, uold, nthreads=1):
     t = C.c_double(0.0)
     lib().orc_run_uniform(C.byref(p), mesh.ptr, l, nstep, dptr(uold), dptr(unew), dptr(dts), C.byref(t), nthreads)
     return dts, t.value
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ideal MHD (NDIM=3, nvar=8 stored as 11)
+def make_mhd_params(slope_type=1, slope_mag_type=-1, riemann="llf", riemann2d="llf", gamma=1.4, smallr=1e-10, smallc=1e-10,
+                    slope_theta=1.5, courant_factor=0.8, boxlen=1.0):
+    p = MhdParams()
+    p.slope_type = slope_type
+    p.slope_mag_type = slope_type if slope_mag_type == -1 else slope_mag_type     # hydro/read_hydro_params.f90:528
+    p.riemann = MHD_RIEMANN[riemann] if isinstance(riemann, str) else riemann
+    p.riemann2d = MHD_RIEMANN2D[riemann2d] if isinstance(riemann2d, str) else riemann2d
+    p.gamma, p.smallr, p.smallc = gamma, smallr, smallc
+    p.slope_theta, p.courant_factor, p.boxlen = slope_theta, courant_factor, boxlen
+    return p
+
+
+def mhd_run_uniform(p, mesh, l, nstep, uold, nthreads=1):
+    unew = np.zeros_like(uold)
+    dts = np.zeros(nstep)
+    t = C.c_double(0.0)
+    lib().orc_mhd_run_uniform(C.byref(p), mesh.ptr, l, nstep, dptr(uold), dptr(unew), dptr(dts), C.byref(t), nthreads)
+    return dts, t.value
+
+
+def mhd_state_from_primitives(d, vel, P, bface, gamma):
+    """Dense conservative MHD state [11][nz][ny][nx] from cell primitives and the three staggered face fields.
+    bface[c] has one extra layer along axis c: bface[0] is [nz][ny][nx+1] etc. (left face of cell i = index i).
+    E includes 0.5*B_c^2 with B_c the face average (mhd/condinit.f90:60-75)."""
+    nz, ny, nx = d.shape
+    u = np.zeros((11, nz, ny, nx))
+    u[0] = d
+    for c in range(3):
+        u[1 + c] = d * vel[c]
+    u[5] = bface[0][:, :, :-1]; u[8] = bface[0][:, :, 1:]
+    u[6] = bface[1][:, :-1, :]; u[9] = bface[1][:, 1:, :]
+    u[7] = bface[2][:-1, :, :]; u[10] = bface[2][1:, :, :]
+    ekin = 0.5 * d * (vel[0] ** 2 + vel[1] ** 2 + vel[2] ** 2)
+    emag = 0.125 * ((u[5] + u[8]) ** 2 + (u[6] + u[9]) ** 2 + (u[7] + u[10]) ** 2)
+    u[4] = P / (gamma - 1.0) + ekin + emag
+    return u

@@ -18,6 +18,7 @@
 #include "../../include/ramses_gpu.h"
 #include "sweep_dense.cuh"
 #include "amr_kernels.cuh"
+#include "mhd_dense.cuh"
 
 namespace rgpu {
 // launchers instantiated in sweep_inst_*.cu
@@ -87,10 +88,12 @@ struct Level {
   std::vector<PeerList> peers;
   int ntx = 0, nty = 0, nblocks = 0, by = 1;
   long long nwork = 0;
-  double* d_part = nullptr;          // [4][nblocks_max]
+  double* d_part = nullptr;          // [5][part_cap]
+  double* d_mhdw = nullptr;          // MHD work arrays [MW_NCOMP][ncell_box]
+  int mhd_nb = 0;                    // CTAs of the MHD update kernel
   int part_cap = 0;
   double* d_dt = nullptr;            // [1] dt used by the next sweep
-  double* d_out = nullptr;           // [4] dt, mass, etot, eint of the last scan
+  double* d_out = nullptr;           // [5] dt, mass, etot, eint (, emag) of the last scan
   double* d_hist = nullptr; int hist_cap = 0;
   long long launches = 0;
   double last_sweep_ms = 0;
@@ -125,6 +128,8 @@ struct Context {
   AmrLevel alev[MAXLEVEL + 1];
   rgpu_params p{};
   Phys phys{};
+  MPhys mphys{};
+  int nvs = 0;                       // stored variables per cell: nvar (hydro) or nvar+3 (MHD)
   int myid = 1, ncpu = 1, device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -252,24 +257,25 @@ __global__ void courant_kernel(const double* __restrict__ u, DenseGeom g, Phys P
 // final reduction of the per-CTA partials: dt = min(dt_cap, courant_factor*dx/smallc, min dtcell)
 // (cmpdt godunov_utils.f90:113-118, courant_fine.f90:121-123,155); fixed summation order.
 __global__ void courant_reduce_kernel(const double* __restrict__ part, int nb, double dt_cap, double dt_floor0, double vol,
-                                      double* __restrict__ out /*[4]*/, double* __restrict__ dt_dev, double* __restrict__ hist) {
-  __shared__ double red[4][32];
-  double v0 = 1e300, v1 = 0, v2 = 0, v3 = 0;
+                                      double* __restrict__ out /*[5]*/, double* __restrict__ dt_dev, double* __restrict__ hist, int has_emag = 0) {
+  __shared__ double red[5][32];
+  double v0 = 1e300, v1 = 0, v2 = 0, v3 = 0, v4 = 0;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) {
     v0 = part[i] < v0 ? part[i] : v0; v1 += part[(size_t)nb + i]; v2 += part[2 * (size_t)nb + i]; v3 += part[3 * (size_t)nb + i];
+    if (has_emag) v4 += part[4 * (size_t)nb + i];
   }
-  v0 = warp_min(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+  v0 = warp_min(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3); v4 = warp_sum(v4);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { red[0][w] = v0; red[1][w] = v1; red[2][w] = v2; red[3][w] = v3; }
+  if (l == 0) { red[0][w] = v0; red[1][w] = v1; red[2][w] = v2; red[3][w] = v3; red[4][w] = v4; }
   __syncthreads();
   if (w == 0) {
     const int nw = blockDim.x >> 5;
-    v0 = l < nw ? red[0][l] : 1e300; v1 = l < nw ? red[1][l] : 0; v2 = l < nw ? red[2][l] : 0; v3 = l < nw ? red[3][l] : 0;
-    v0 = warp_min(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+    v0 = l < nw ? red[0][l] : 1e300; v1 = l < nw ? red[1][l] : 0; v2 = l < nw ? red[2][l] : 0; v3 = l < nw ? red[3][l] : 0; v4 = l < nw ? red[4][l] : 0;
+    v0 = warp_min(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3); v4 = warp_sum(v4);
     if (l == 0) {
       double dt = dt_floor0 < v0 ? dt_floor0 : v0;
       dt = dt_cap < dt ? dt_cap : dt;
-      out[0] = dt; out[1] = v1 * vol; out[2] = v2 * vol; out[3] = v3 * vol;
+      out[0] = dt; out[1] = v1 * vol; out[2] = v2 * vol; out[3] = v3 * vol; out[4] = v4 * vol;
       if (dt_dev) *dt_dev = dt;
       if (hist) *hist = dt;
     }
@@ -321,7 +327,7 @@ __global__ void selftest_div_kernel(long long n_per_thread, unsigned long long s
 
 // ----------------------------------------------------------------------------- helpers
 inline int T_() { return 1 << G.p.ndim; }
-inline size_t nplanes_() { return (size_t)G.p.nvar * T_(); }
+inline size_t nplanes_() { return (size_t)G.nvs * T_(); }
 
 double level_dx(int ilevel) {  // godunov_fine.f90:532-534
   const int nx_loc = G.p.icoarse_max - G.p.icoarse_min + 1;
@@ -354,7 +360,7 @@ void oct_pos(int ilevel, int igrid, int pos[3]) {
 
 void free_level(Level& L) {
   cudaFree(L.d_slot_igrid); cudaFree(L.d_mirror); cudaFree(L.d_u[0]); cudaFree(L.d_u[1]);
-  cudaFree(L.d_part); cudaFree(L.d_dt); cudaFree(L.d_out); cudaFree(L.d_hist);
+  cudaFree(L.d_part); cudaFree(L.d_dt); cudaFree(L.d_out); cudaFree(L.d_hist); cudaFree(L.d_mhdw);
   for (auto& r : L.regions) cudaFree(r.d_slots);
   for (auto& p : L.peers) { cudaFree(p.d_recv); cudaFree(p.d_emit); cudaFree(p.d_sbuf); cudaFree(p.d_rbuf); }
   L = Level();
@@ -382,6 +388,24 @@ cudaError_t dispatch_sweep_nd(int riemann, const SweepArgs& a, int nb, cudaStrea
 }
 
 int launch_sweep(Level& L) {
+  if (G.p.mhd) {
+    MhdArgs m{};
+    m.uin = L.d_u[L.cur]; m.uout = L.d_u[1 - L.cur]; m.g = L.g; m.P = G.mphys; m.dt_dev = L.d_dt; m.dx = L.dx;
+    m.W = L.d_mhdw; m.nc = (long long)L.g.ncx * L.g.ncy * L.g.ncz; m.part = L.d_part;
+    if (G.timing) cudaEventRecord(G.ev0, G.stream);
+    const bool sl = !(G.mphys.slope_type == 0 && G.mphys.slope_mag_type == 0);
+    cudaError_t e = launch_mhd_sweep(m, G.p.riemann, G.p.riemann2d, sl, L.mhd_nb, G.stream);
+    if (e != cudaSuccess) return fail(RGPU_ECUDA, "MHD sweep launch: %s", cudaGetErrorString(e));
+    if (G.timing) {
+      cudaEventRecord(G.ev1, G.stream);
+      cudaEventSynchronize(G.ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, G.ev0, G.ev1);
+      L.last_sweep_ms = ms;
+    }
+    L.launches += 6;
+    return RGPU_OK;
+  }
   SweepArgs a{};
   a.uin = L.d_u[L.cur];
   a.uout = L.d_u[1 - L.cur];
@@ -415,7 +439,7 @@ int launch_sweep(Level& L) {
 int launch_reduce(Level& L, int nb, double dt_cap, double* hist_slot) {
   const double vol = std::pow(L.dx, G.p.ndim);
   const double dt0 = G.p.courant_factor * L.dx / G.p.smallc;   // cmpdt: dt = courant_factor*dx/smallc
-  courant_reduce_kernel<<<1, 1024, 0, G.stream>>>(L.d_part, nb, dt_cap, dt0, vol, L.d_out, L.d_dt, hist_slot);
+  courant_reduce_kernel<<<1, 1024, 0, G.stream>>>(L.d_part, nb, dt_cap, dt0, vol, L.d_out, L.d_dt, hist_slot, G.p.mhd ? 1 : 0);
   CUDA_OK(cudaGetLastError());
   L.launches++;
   return RGPU_OK;
@@ -423,6 +447,12 @@ int launch_reduce(Level& L, int nb, double dt_cap, double* hist_slot) {
 
 int launch_courant(Level& L, double dt_cap, double* hist_slot) {
   const int nb = std::min(L.part_cap, 148 * 8);
+  if (G.p.mhd) {
+    cudaError_t e = launch_mhd_courant(L.d_u[L.cur], L.g, G.mphys, L.dx, L.d_part, nb, G.stream);
+    if (e != cudaSuccess) return fail(RGPU_ECUDA, "MHD courant launch: %s", cudaGetErrorString(e));
+    L.launches++;
+    return launch_reduce(L, nb, dt_cap, hist_slot);
+  }
   if (G.p.ndim == 1) courant_kernel<1><<<nb, 256, 0, G.stream>>>(L.d_u[L.cur], L.g, G.phys, L.dx, L.d_part);
   else if (G.p.ndim == 2) courant_kernel<2><<<nb, 256, 0, G.stream>>>(L.d_u[L.cur], L.g, G.phys, L.dx, L.d_part);
   else courant_kernel<3><<<nb, 256, 0, G.stream>>>(L.d_u[L.cur], L.g, G.phys, L.dx, L.d_part);
@@ -441,10 +471,28 @@ int launch_boundaries(Level& L, double* u) {
     if (r.n == 0) continue;
     const int bt = r.type, dir = bt - 10 * (bt / 10);
     if (bt / 10 > 1) return fail(RGPU_EUNSUPPORTED, "imposed boundary (boundana) type %d not supported", bt);
-    BoundArgs b{};
-    b.n = r.n; b.slots = r.d_slots; b.nslot = L.nslot;
     const long long str[3] = {1, L.g.nox, (long long)L.g.nox * L.g.noy};
     const int d = (dir - 1) / 2;
+    if (G.p.mhd) {   // mhd/hydro_boundary.f90:53-139
+      static const int alt_[6][8] = {{-2, -1, -2, -1, -2, -1, -2, -1}, {1, 2, 1, 2, 1, 2, 1, 2}, {-2, -2, -1, -1, -2, -2, -1, -1},
+                                     {1, 1, 2, 2, 1, 1, 2, 2}, {-2, -2, -2, -2, -1, -1, -1, -1}, {1, 1, 1, 1, 2, 2, 2, 2}};
+      MhdBoundArgs m{};
+      m.n = r.n; m.slots = r.d_slots; m.nslot = L.nslot;
+      m.nbr_off = (dir % 2 == 1) ? str[d] : -str[d];
+      const int* ir = (bt / 10 == 0) ? (d == 0 ? ref_x : d == 1 ? ref_y : ref_z) : fre[dir - 1];
+      for (int i = 0; i < 8; i++) { m.ind_ref[i] = ir[i]; m.ind_normal[i] = fre[dir - 1][i]; m.alt[i] = alt_[dir - 1][i]; }
+      m.gs[0] = m.gs[1] = m.gs[2] = 1.0;
+      if (bt >= 1 && bt <= 6) m.gs[d] = -1.0;
+      m.kind = bt / 10; m.gdim = d + 1;
+      m.iperp1 = (dir % 2 == 1) ? 4 + m.gdim : 7 + m.gdim;   // left-face (6..8) / right-face (nvar+1..) component, 0-based
+      m.smallr = G.p.smallr;
+      cudaError_t e = launch_mhd_boundary(u, m, G.stream);
+      if (e != cudaSuccess) return fail(RGPU_ECUDA, "MHD boundary launch: %s", cudaGetErrorString(e));
+      L.launches++;
+      continue;
+    }
+    BoundArgs b{};
+    b.n = r.n; b.slots = r.d_slots; b.nslot = L.nslot;
     b.nbr_off = (dir % 2 == 1) ? str[d] : -str[d];   // boundary at the min face looks towards +d
     const int* ir = (bt / 10 == 0) ? (d == 0 ? ref_x : d == 1 ? ref_y : ref_z) : fre[dir - 1];
     for (int i = 0; i < 8; i++) b.ind_ref[i] = ir[i];
@@ -564,7 +612,7 @@ int amr_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int nc
     }
   }
   CUDA_OK(cudaMalloc(&A.d_part, sizeof(double) * 4 * 148 * 8));
-  CUDA_OK(cudaMalloc(&A.d_out, sizeof(double) * 4));
+  CUDA_OK(cudaMalloc(&A.d_out, sizeof(double) * 5));
   CUDA_OK(cudaMalloc(&A.d_dt, sizeof(double)));
   A.bound = true;
   return RGPU_OK;
@@ -718,9 +766,20 @@ const char* rgpu_last_error(void) { return g_err; }
 int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device) {
   if (!p) return fail(RGPU_EINVAL, "null params");
   if (p->ndim < 1 || p->ndim > 3) return fail(RGPU_EINVAL, "ndim=%d", p->ndim);
+  if (p->mhd) {
+    if (p->ndim != 3) return fail(RGPU_EUNSUPPORTED, "MHD build: NDIM=%d not supported (3 only)", p->ndim);
+    if (p->nvar != 8) return fail(RGPU_EUNSUPPORTED, "MHD build: nvar=%d: passive scalars / NENER not supported (need nvar=8)", p->nvar);
+    if (p->riemann < 0 || p->riemann > 5) return fail(RGPU_EINVAL, "unknown riemann solver");     // mhd/umuscl.f90:1435
+    if (p->riemann2d < 0 || p->riemann2d > 5) return fail(RGPU_EINVAL, "unknown 2D riemann solver"); // mhd/umuscl.f90:1886
+    const int smt = p->slope_mag_type == -1 ? p->slope_type : p->slope_mag_type;
+    if (!(smt == 0 || smt == 1 || smt == 2)) return fail(RGPU_EINVAL, "Unknown mag. slope type %d", smt);   // mhd/umuscl.f90:2655
+    if (!(p->slope_type == 0 || p->slope_type == 1 || p->slope_type == 2 || p->slope_type == 3 || p->slope_type == 7 || p->slope_type == 8))
+      return fail(RGPU_EINVAL, "Unknown slope type %d", p->slope_type);                                      // mhd/umuscl.f90:2562
+  } else {
   if (p->nvar != p->ndim + 2) return fail(RGPU_EUNSUPPORTED, "nvar=%d: passive scalars / NENER not supported (need nvar=ndim+2)", p->nvar);
-  if (p->scheme != RGPU_SCHEME_MUSCL) return fail(RGPU_EUNSUPPORTED, "scheme='plmde' not supported");
   if (p->riemann < 0 || p->riemann > 4) return fail(RGPU_EINVAL, "unknown Riemann solver %d", p->riemann);
+  }
+  if (p->scheme != RGPU_SCHEME_MUSCL) return fail(RGPU_EUNSUPPORTED, "scheme='plmde' not supported");
   if (p->pressure_fix) return fail(RGPU_EUNSUPPORTED, "pressure_fix not supported");
   if (p->difmag > 0.0) return fail(RGPU_EUNSUPPORTED, "difmag>0 not supported");
   {
@@ -757,6 +816,11 @@ int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device) {
   P.cfl_rg = 1.0 / P.cfl_g;
   P.cfl_k = std::sqrt(1.0 + 2.0 * p->courant_factor * P.cfl_g) - 1.0;
   P.slope_type = p->slope_type; P.niter_riemann = p->niter_riemann;
+  G.nvs = p->mhd ? p->nvar + 3 : p->nvar;
+  MPhys& M = G.mphys;
+  M.gamma = p->gamma; M.smallr = p->smallr; M.smallc = p->smallc; M.slope_theta = p->slope_theta; M.courant_factor = p->courant_factor;
+  M.smallp = p->smallr * (p->smallc * p->smallc) / p->gamma;
+  M.slope_type = p->slope_type; M.slope_mag_type = p->slope_mag_type == -1 ? p->slope_type : p->slope_mag_type;
   G.init = true;
   return RGPU_OK;
 }
@@ -777,6 +841,7 @@ int rgpu_finalize(void) {
 
 int rgpu_set_amr(int on, int interpol_type, int interpol_var) {
   if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  if (on && G.p.mhd) return fail(RGPU_EUNSUPPORTED, "MHD build: AMR mode (divergence-free prolongation, EMF refluxing) not supported; levelmin=levelmax only");
   if (on && interpol_var != 0) return fail(RGPU_EUNSUPPORTED, "interpol_var=%d not supported (0 only)", interpol_var);
   if (on && (interpol_type < 0 || interpol_type > 3)) return fail(RGPU_EUNSUPPORTED, "interpol_type=%d not supported", interpol_type);
   G.amr = on != 0;
@@ -985,9 +1050,17 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
     L.nblocks = (int)std::min<long long>(nsm, L.nwork);
   }
   L.part_cap = std::max(L.nblocks, 148 * 8);
-  CUDA_OK(cudaMalloc(&L.d_part, sizeof(double) * 4 * L.part_cap));
+  if (G.p.mhd) {
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, G.device);
+    L.mhd_nb = nsm * 8;
+    L.nblocks = L.mhd_nb;   // CTAs that write Courant partials in the sweep
+    L.part_cap = std::max(L.part_cap, L.mhd_nb);
+    CUDA_OK(cudaMalloc(&L.d_mhdw, sizeof(double) * (size_t)MW_NCOMP * (size_t)g.ncx * g.ncy * g.ncz));
+  }
+  CUDA_OK(cudaMalloc(&L.d_part, sizeof(double) * 5 * L.part_cap));
   CUDA_OK(cudaMalloc(&L.d_dt, sizeof(double)));
-  CUDA_OK(cudaMalloc(&L.d_out, sizeof(double) * 4));
+  CUDA_OK(cudaMalloc(&L.d_out, sizeof(double) * 5));
   L.cur = 0; L.unew_valid = false;
   return RGPU_OK;
 }
@@ -1036,7 +1109,7 @@ static int upload_into(Level& L, const double* host, double* dst) {
   const int T = T_();
   const long long gspan = (long long)L.gmax - L.gmin + 1;
   const size_t ncell = (size_t)G.ncoarse + (size_t)T * G.ngridmax;
-  for (int iv = 0; iv < G.p.nvar; iv++)
+  for (int iv = 0; iv < G.nvs; iv++)
     for (int ind = 0; ind < T; ind++) {
       const double* src = host + (size_t)iv * ncell + G.ncoarse + (size_t)ind * G.ngridmax + (L.gmin - 1);
       CUDA_OK(cudaMemcpyAsync(L.d_mirror + ((size_t)iv * T + ind) * gspan, src, sizeof(double) * gspan, cudaMemcpyHostToDevice, G.stream));
@@ -1058,7 +1131,7 @@ static int download_from(Level& L, double* host, const double* srcdev, bool owne
   if (G.p.ndim > 2) nown *= (L.g.oz1 - L.g.oz0) / 2;
   const bool preload = (gspan != L.nslot) || (owned_only && nown != L.nslot);
   if (preload)
-    for (int iv = 0; iv < G.p.nvar; iv++)
+    for (int iv = 0; iv < G.nvs; iv++)
       for (int ind = 0; ind < T; ind++) {
         const double* src = host + (size_t)iv * ncell + G.ncoarse + (size_t)ind * G.ngridmax + (L.gmin - 1);
         CUDA_OK(cudaMemcpyAsync(L.d_mirror + ((size_t)iv * T + ind) * gspan, src, sizeof(double) * gspan, cudaMemcpyHostToDevice, G.stream));
@@ -1068,7 +1141,7 @@ static int download_from(Level& L, double* host, const double* srcdev, bool owne
                                                                                   (int)nplanes_(), owned_only ? 1 : 0, L.g);
   CUDA_OK(cudaGetLastError());
   L.launches++;
-  for (int iv = 0; iv < G.p.nvar; iv++)
+  for (int iv = 0; iv < G.nvs; iv++)
     for (int ind = 0; ind < T; ind++) {
       double* dst = host + (size_t)iv * ncell + G.ncoarse + (size_t)ind * G.ngridmax + (L.gmin - 1);
       CUDA_OK(cudaMemcpyAsync(dst, L.d_mirror + ((size_t)iv * T + ind) * gspan, sizeof(double) * gspan, cudaMemcpyDeviceToHost, G.stream));
@@ -1173,19 +1246,19 @@ int rgpu_courant_fine(int ilevel, double* dt_io, double sums[3]) {
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (!dt_io) return fail(RGPU_EINVAL, "null dt");
   rc = launch_courant(*L, *dt_io, nullptr); if (rc) return rc;
-  double out[4];
+  double out[5];
   CUDA_OK(cudaMemcpyAsync(out, L->d_out, sizeof(out), cudaMemcpyDeviceToHost, G.stream));
   CUDA_OK(cudaStreamSynchronize(G.stream));
   if (G.comm && G.nranks > 1) {
-    // MPI_ALLREDUCE SUM(3) + MIN(1) of courant_fine.f90:138-141, carried by NCCL
+    // MPI_ALLREDUCE SUM(3 or 4) + MIN(1) of courant_fine.f90:138-141, carried by NCCL
     double* d = L->d_out;
     NCCL_OK(ncclAllReduce(d, d, 1, ncclDouble, ncclMin, G.comm, G.stream));
-    NCCL_OK(ncclAllReduce(d + 1, d + 1, 3, ncclDouble, ncclSum, G.comm, G.stream));
+    NCCL_OK(ncclAllReduce(d + 1, d + 1, 4, ncclDouble, ncclSum, G.comm, G.stream));
     CUDA_OK(cudaMemcpyAsync(out, L->d_out, sizeof(out), cudaMemcpyDeviceToHost, G.stream));
     CUDA_OK(cudaStreamSynchronize(G.stream));
   }
   *dt_io = std::min(*dt_io, out[0]);
-  if (sums) { sums[0] += out[1]; sums[1] += out[2]; sums[2] += out[3]; }
+  if (sums) { sums[0] += out[1]; sums[1] += out[2]; sums[2] += out[3]; if (G.p.mhd) sums[3] += out[4]; }
   return RGPU_OK;
 }
 
@@ -1260,10 +1333,10 @@ int rgpu_level_steps(int ilevel, int nstep, double* dt_hist, double sums_last[3]
   L->unew_valid = false;
   CUDA_OK(cudaEventRecord(G.ev3, G.stream));
   if (dt_hist) CUDA_OK(cudaMemcpyAsync(dt_hist, L->d_hist, sizeof(double) * nstep, cudaMemcpyDeviceToHost, G.stream));
-  double out[4];
+  double out[5];
   CUDA_OK(cudaMemcpyAsync(out, L->d_out, sizeof(out), cudaMemcpyDeviceToHost, G.stream));
   CUDA_OK(cudaStreamSynchronize(G.stream));
-  if (sums_last) { sums_last[0] = out[1]; sums_last[1] = out[2]; sums_last[2] = out[3]; }
+  if (sums_last) { sums_last[0] = out[1]; sums_last[1] = out[2]; sums_last[2] = out[3]; if (G.p.mhd) sums_last[3] = out[4]; }
   { float ms = 0; cudaEventElapsedTime(&ms, G.ev2, G.ev3); L->last_steps_ms = ms; }
   return RGPU_OK;
 }

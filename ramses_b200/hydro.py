@@ -28,8 +28,10 @@ class AmrCommons:
     """
 
     def __init__(self, ndim, nvar, ncoarse, ngridmax, nx, ny, nz, icoarse=(0, 0), jcoarse=(0, 0), kcoarse=(0, 0),
-                 nlevelmax=1, boxlen=1.0, myid=1, ncpu=1):
+                 nlevelmax=1, boxlen=1.0, myid=1, ncpu=1, mhd=False):
         self.ndim, self.nvar = ndim, nvar
+        self.mhd = bool(mhd)                     # SOLVER=mhd build: uold(1:ncell,1:nvar+3), mhd/hydro_commons.f90
+        self.nvar_store = nvar + 3 if mhd else nvar
         self.ncoarse, self.ngridmax = ncoarse, ngridmax
         self.twotondim, self.twondim = 1 << ndim, 2 * ndim
         self.ncell = ncoarse + self.twotondim * ngridmax
@@ -42,8 +44,8 @@ class AmrCommons:
         self.son = np.zeros(self.ncell, dtype=np.int32)
         self.father = np.zeros(ngridmax, dtype=np.int32)
         self.nbor = np.zeros((self.twondim, ngridmax), dtype=np.int32)   # Fortran nbor(1:ngridmax,1:twondim)
-        self.uold = np.zeros((nvar, self.ncell), dtype=np.float64)
-        self.unew = np.zeros((nvar, self.ncell), dtype=np.float64)
+        self.uold = np.zeros((self.nvar_store, self.ncell), dtype=np.float64)
+        self.unew = np.zeros((self.nvar_store, self.ncell), dtype=np.float64)
         self.active = {}       # ilevel -> int32 array of igrid
         self.boundary = {}     # ilevel -> list of int32 arrays, one per ibound
         self.boundary_type = []
@@ -58,7 +60,8 @@ class AmrCommons:
         self.scheme, self.riemann = "muscl", "llf"
         self.nvector = 32
         self.pressure_fix = False
-        self.mass_tot = self.ekin_tot = self.eint_tot = 0.0
+        self.mass_tot = self.ekin_tot = self.eint_tot = self.emag_tot = 0.0
+        self.riemann2d, self.slope_mag_type = "llf", -1          # mhd/hydro_parameters.f90:93,104
 
     def dx(self, ilevel):
         nx_loc = self.icoarse_max - self.icoarse_min + 1
@@ -81,9 +84,17 @@ def make_params(amr):
     if amr.scheme not in ("muscl", "plmde"):
         raise ValueError("unknown scheme")
     p.scheme = 0 if amr.scheme == "muscl" else 1
-    if amr.riemann not in _lib.RIEMANN:
-        raise ValueError("unknown Riemann solver")          # hydro/umuscl.f90:801-803
-    p.riemann = _lib.RIEMANN[amr.riemann]
+    if getattr(amr, "mhd", False):
+        if amr.riemann not in _lib.MHD_RIEMANN:
+            raise ValueError("unknown riemann solver")      # mhd/umuscl.f90:1435
+        if amr.riemann2d not in _lib.MHD_RIEMANN2D:
+            raise ValueError("unknown 2D riemann solver")   # mhd/umuscl.f90:1886
+        p.riemann, p.riemann2d = _lib.MHD_RIEMANN[amr.riemann], _lib.MHD_RIEMANN2D[amr.riemann2d]
+        p.mhd, p.slope_mag_type = 1, amr.slope_mag_type
+    else:
+        if amr.riemann not in _lib.RIEMANN:
+            raise ValueError("unknown Riemann solver")      # hydro/umuscl.f90:801-803
+        p.riemann = _lib.RIEMANN[amr.riemann]
     p.pressure_fix = int(bool(amr.pressure_fix))
     p.gamma, p.smallr, p.smallc = amr.gamma, amr.smallr, amr.smallc
     p.slope_theta, p.difmag, p.courant_factor, p.boxlen = amr.slope_theta, amr.difmag, amr.courant_factor, amr.boxlen
@@ -193,10 +204,10 @@ class HydroGPU:
         """courant_fine(ilevel): dtnew(ilevel) = min(dtnew(ilevel), CFL dt); mass_tot etc. accumulated."""
         a = self.a
         dt = C.c_double(a.dtnew[ilevel])
-        sums = (C.c_double * 3)(0.0, 0.0, 0.0)
+        sums = (C.c_double * 4)(0.0, 0.0, 0.0, 0.0)
         _lib.check(self.L.rgpu_courant_fine(ilevel, C.byref(dt), sums))
         a.dtnew[ilevel] = dt.value
-        a.mass_tot += sums[0]; a.ekin_tot += sums[1]; a.eint_tot += sums[2]
+        a.mass_tot += sums[0]; a.ekin_tot += sums[1]; a.eint_tot += sums[2]; a.emag_tot += sums[3]
         return dt.value
 
     def make_boundary_hydro(self, ilevel):
@@ -214,7 +225,7 @@ class HydroGPU:
     def level_steps(self, ilevel, nstep):
         """nstep fused level steps (courant -> set_unew -> godunov_fine -> set_uold -> ghosts -> boundaries)."""
         dts = np.zeros(nstep)
-        sums = (C.c_double * 3)()
+        sums = (C.c_double * 4)()
         _lib.check(self.L.rgpu_level_steps(ilevel, nstep, _dp(dts), sums))
         return dts, list(sums)
 

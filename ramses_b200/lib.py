@@ -8,6 +8,9 @@ LIB_PATH = os.environ.get("RGPU_LIB", os.path.join(_HERE, "libramses_gpu.so"))  
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "ramses_gpu.h")
 
 RIEMANN = {"llf": 0, "exact": 1, "acoustic": 2, "hllc": 3, "hll": 4}
+# MHD build: iriemann / iriemann2d (hydro/read_hydro_params.f90:190-220)
+MHD_RIEMANN = {"llf": 0, "roe": 1, "hll": 2, "hlld": 3, "upwind": 4, "hydro": 5}
+MHD_RIEMANN2D = {"llf": 0, "roe": 1, "upwind": 2, "hll": 3, "hlla": 4, "hlld": 5}
 
 
 class RgpuError(RuntimeError):
@@ -24,7 +27,8 @@ class Params(C.Structure):
                 ("difmag", C.c_double), ("courant_factor", C.c_double), ("boxlen", C.c_double),
                 ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
                 ("icoarse_min", C.c_int), ("icoarse_max", C.c_int), ("jcoarse_min", C.c_int), ("jcoarse_max", C.c_int),
-                ("kcoarse_min", C.c_int), ("kcoarse_max", C.c_int), ("nlevelmax", C.c_int)]
+                ("kcoarse_min", C.c_int), ("kcoarse_max", C.c_int), ("nlevelmax", C.c_int),
+                ("mhd", C.c_int), ("riemann2d", C.c_int), ("slope_mag_type", C.c_int), ("pad_", C.c_int)]
 
 
 class LevelInfo(C.Structure):

@@ -6,6 +6,9 @@ Run in the build container only; the GPU box has no /root/reference and uses the
   sod_tube_ana.json   <- tests/hydro/sod-tube/sod-tube-ana.dat   (exact Sod solution at t=0.245, 1024 points)
   indices3cube.json   <- amr/nbors_utils.f90:305-358             (lll/mmm neighbour lookup tables)
   implosion_ref.json  <- tests/hydro/implosion/implosion-ref.dat (golden sums, 2-D AMR; kept for later rounds)
+  imhd_tube_ref.json  <- tests/mhd/imhd-tube/imhd-tube-ref.dat   (golden sums of the 1-D AMR MHD tube, hlld)
+  imhd_tube_ana.json  <- tests/mhd/imhd-tube/imhd-tube-ana.dat   (exact solution at t=0.4, 2014 points)
+  orszag_tang_ref.json <- tests/mhd/orszag-tang/orszag-tang-ref.dat (golden sums, 2-D AMR; kept for later rounds)
 """
 import json
 import os
@@ -28,6 +31,11 @@ def main():
     json.dump(ref_dat(f"{REF}/tests/hydro/implosion/implosion-ref.dat"), open(f"{OUT}/implosion_ref.json", "w"), indent=1)
     rows = [[float(x) for x in l.split()] for l in open(f"{REF}/tests/hydro/sod-tube/sod-tube-ana.dat") if l.strip()]
     json.dump({"columns": ["idx", "x", "u", "rho", "P", "e"], "rows": rows}, open(f"{OUT}/sod_tube_ana.json", "w"))
+    json.dump(ref_dat(f"{REF}/tests/mhd/imhd-tube/imhd-tube-ref.dat"), open(f"{OUT}/imhd_tube_ref.json", "w"), indent=1)
+    json.dump(ref_dat(f"{REF}/tests/mhd/orszag-tang/orszag-tang-ref.dat"), open(f"{OUT}/orszag_tang_ref.json", "w"), indent=1)
+    rows = [[float(x) for x in l.split()] for l in open(f"{REF}/tests/mhd/imhd-tube/imhd-tube-ana.dat") if l.strip()]
+    json.dump({"columns": ["x", "rho", "u", "v", "w", "Bx", "By", "Bz", "P"], "rows": rows},
+              open(f"{OUT}/imhd_tube_ana.json", "w"))
     src = open(f"{REF}/amr/nbors_utils.f90").read()
     tab = {"lll": {}, "mmm": {}}
     for name in ("lll", "mmm"):

@@ -129,3 +129,123 @@ def max_rel_err(a, b):
             scale = 1.0
         out = max(out, np.abs(a[v] - b[v]).max() / scale)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# ideal MHD (NDIM=3, nvar=8 stored as 11)
+def mhd_smooth_state(n, gamma=5.0 / 3.0, b0=(0.5, 0.3, 0.2), amp=0.1, periodic=(True, True, True)):
+    """Smooth periodic MHD state with a divergence-free staggered field built from an edge-centred vector potential.
+    Face values shared by two cells (incl. the periodic wrap) are the same number on both sides.
+    Returns the dense conservative array [11][n][n][n]."""
+    h = 1.0 / n
+    xc = (np.arange(n) + 0.5) * h
+    xe = np.arange(n) * h                       # low edges / faces; the high one wraps onto index 0
+    tw = 2 * np.pi
+    Z, Y, X = np.meshgrid(xc, xc, xc, indexing="ij")
+    d = 1 + 0.2 * np.sin(tw * X) * np.cos(tw * Y)
+    vel = [0.3 * np.sin(tw * Y), 0.2 * np.cos(tw * Z), 0.1 * np.sin(tw * X)]
+    P = 1 + 0.1 * np.cos(tw * Z) * np.sin(tw * (X + Y))
+    # vector potential on the low edges of every cell
+    ze, ye, x_ = np.meshgrid(xe, xe, xc, indexing="ij"); Ax = amp * np.sin(tw * ye) * np.cos(tw * ze)
+    ze, y_, xe_ = np.meshgrid(xe, xc, xe, indexing="ij"); Ay = amp * np.sin(tw * ze + 1.0) * np.cos(tw * xe_)
+    z_, ye, xe_ = np.meshgrid(xc, xe, xe, indexing="ij"); Az = amp * np.cos(tw * xe_) * np.sin(tw * ye + 0.3)
+    up = lambda a, ax: np.roll(a, -1, axis=ax)
+    # left-face fields of every cell (curl of A), axis order (z,y,x)
+    bx = (up(Az, 1) - Az) / h - (up(Ay, 0) - Ay) / h + b0[0]
+    by = (up(Ax, 0) - Ax) / h - (up(Az, 2) - Az) / h + b0[1]
+    bz = (up(Ay, 2) - Ay) / h - (up(Ax, 1) - Ax) / h + b0[2]
+    u = np.zeros((11, n, n, n))
+    u[0] = d
+    for c in range(3):
+        u[1 + c] = d * vel[c]
+    u[5], u[6], u[7] = bx, by, bz
+    u[8], u[9], u[10] = up(bx, 2), up(by, 1), up(bz, 0)
+    ekin = 0.5 * d * (vel[0] ** 2 + vel[1] ** 2 + vel[2] ** 2)
+    emag = 0.125 * ((u[5] + u[8]) ** 2 + (u[6] + u[9]) ** 2 + (u[7] + u[10]) ** 2)
+    u[4] = P / (gamma - 1.0) + ekin + emag
+    return u
+
+
+def mhd_tube_state(n, left, right, x0, boxlen, gamma):
+    """Shock tube along x (mhd/condinit.f90 with two 'square' regions spanning y,z): left/right = (d,u,v,w,P,A,B,C)."""
+    xc = (np.arange(n) + 0.5) * boxlen / n
+    u = np.zeros((11, n, n, n))
+    for sel, s in ((xc < x0, left), (xc >= x0, right)):
+        d, vx, vy, vz, P, A, B, C = s
+        u[0][:, :, sel] = d
+        u[1][:, :, sel] = d * vx; u[2][:, :, sel] = d * vy; u[3][:, :, sel] = d * vz
+        u[5][:, :, sel] = A; u[8][:, :, sel] = A
+        u[6][:, :, sel] = B; u[9][:, :, sel] = B
+        u[7][:, :, sel] = C; u[10][:, :, sel] = C
+        u[4][:, :, sel] = P / (gamma - 1.0) + 0.5 * d * (vx * vx + vy * vy + vz * vz) + 0.5 * (A * A + B * B + C * C)
+    return u
+
+
+def mhd_divb(u, n_per_len):
+    """cell-wise div(B) of a dense [11][nz][ny][nx] state from the two face copies"""
+    return ((u[8] - u[5]) + (u[9] - u[6]) + (u[10] - u[7])) * n_per_len
+
+
+class MhdCase:
+    """MHD run set-up: oracle mesh + MHD params + the Fortran-side arrays (AmrCommons of an MHD build)."""
+
+    def __init__(self, level, riemann="hlld", riemann2d="llf", slope_type=1, slope_mag_type=-1, bound=(0,) * 6, order=0, seed=1,
+                 boxlen=1.0, gamma=5.0 / 3.0, courant_factor=0.8, slope_theta=1.5):
+        self.ndim, self.level, self.nvar, self.nvs = 3, level, 8, 11
+        self.mesh = orc.Mesh(3, level, bound, order, seed)
+        self.p = orc.make_mhd_params(slope_type=slope_type, slope_mag_type=slope_mag_type, riemann=riemann, riemann2d=riemann2d,
+                                     gamma=gamma, courant_factor=courant_factor, boxlen=boxlen, slope_theta=slope_theta)
+        self.riemann, self.riemann2d, self.slope_type, self.slope_mag_type = riemann, riemann2d, slope_type, slope_mag_type
+        self.u = self.mesh.new_state(11)
+
+    def init_dense(self, dense):
+        self.mesh.dense_to_level(dense, self.u, self.level, 11)
+        orc.lib().orc_mhd_make_boundary_hydro(C.byref(self.p), self.mesh.ptr, self.level, orc.dptr(self.u))
+
+    def dense(self, u=None):
+        return self.mesh.level_to_dense(self.u if u is None else u, self.level, 11)
+
+    def oracle_courant(self, u=None, dt_in=None):
+        u = self.u if u is None else u
+        sums = np.zeros(4)
+        dt_in = self.p.boxlen / self.p.smallc if dt_in is None else dt_in
+        dt = orc.lib().orc_mhd_courant_fine(C.byref(self.p), self.mesh.ptr, self.level, dt_in, orc.dptr(u), orc.dptr(sums))
+        return dt, sums
+
+    def oracle_godunov(self, dt, u=None, nthreads=4):
+        u = self.u if u is None else u
+        unew = np.zeros_like(u)
+        L = orc.lib()
+        L.orc_mhd_set_unew(self.mesh.ptr, self.level, orc.dptr(u), orc.dptr(unew))
+        L.orc_mhd_godunov_fine(C.byref(self.p), self.mesh.ptr, self.level, dt, orc.dptr(u), orc.dptr(unew), nthreads)
+        return unew
+
+    def oracle_steps(self, nstep, u=None, nthreads=4):
+        u = (self.u if u is None else u).copy()
+        dts, t = orc.mhd_run_uniform(self.p, self.mesh, self.level, nstep, u, nthreads=nthreads)
+        return u, dts
+
+    def amr_commons(self, u=None):
+        m, s = self.mesh, self.mesh.s
+        a = AmrCommons(3, 8, s.ncoarse, s.ngridmax, s.nx, s.ny, s.nz,
+                       (s.icoarse_min, s.icoarse_max), (s.jcoarse_min, s.jcoarse_max), (s.kcoarse_min, s.kcoarse_max),
+                       nlevelmax=self.level, boxlen=self.p.boxlen, mhd=True)
+        a.son[:] = m.son()[1:]
+        a.father[:] = m.father()[1:]
+        a.nbor[:, :] = m.nbor()[:, 1:]
+        a.uold[:, :] = (self.u if u is None else u).reshape(11, s.ncell)
+        a.unew[:, :] = 0.0
+        for l in range(1, self.level + 1):
+            a.active[l] = m.active(l).copy()
+            a.boundary[l] = [m.bound(b, l).copy() for b in range(s.nboundary)]
+        a.boundary_type = m.boundary_types()
+        a.gamma, a.courant_factor = self.p.gamma, self.p.courant_factor
+        a.smallr, a.smallc = self.p.smallr, self.p.smallc
+        a.slope_type, a.slope_theta = self.p.slope_type, self.p.slope_theta
+        a.riemann, a.riemann2d, a.slope_mag_type = self.riemann, self.riemann2d, self.slope_mag_type
+        return a
+
+    def active_cells(self):
+        s = self.mesh.s
+        ig = self.mesh.active(self.level).astype(np.int64)
+        return np.concatenate([s.ncoarse + ind * s.ngridmax + ig - 1 for ind in range(8)])

@@ -1,0 +1,176 @@
+"""CPU tests of the MHD oracle (oracle/ramses_oracle_mhd.c).  The reference's MHD golden files are 1-D / 2-D AMR runs the
+restatement cannot reproduce yet (see the file header), so what is checked here is what the scheme guarantees: consistency
+of every 1-D / 2-D solver, conservation, div(B) at round-off, bitwise agreement of the two copies of every face field,
+covariance under a cyclic permutation of the axes (catches index slips in the direction-dependent code paths), the B=0 limit
+against the pinned hydro oracle, and the exact solution of tests/mhd/imhd-tube (committed fixture)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import MhdCase, mhd_smooth_state, mhd_tube_state, mhd_divb
+from oracle import orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SOLVERS1D = ["llf", "roe", "hll", "hlld", "upwind", "hydro"]
+SOLVERS2D = ["llf", "roe", "upwind", "hll", "hlla", "hlld"]
+
+
+def phys_flux(q, gamma):
+    d, P, u, A, v, B, w, Cc = q
+    entho = 1.0 / (gamma - 1.0)
+    emag = 0.5 * (A * A + B * B + Cc * Cc)
+    etot = P * entho + 0.5 * d * (u * u + v * v + w * w) + emag
+    Ptot = P + emag
+    return np.array([d * u, (etot + Ptot) * u - A * (A * u + B * v + Cc * w), d * u * u + Ptot - A * A, 0.0, d * u * v - A * B,
+                     B * u - A * v, d * u * w - A * Cc, Cc * u - A * w, P * entho * u])
+
+
+@pytest.mark.parametrize("riemann", SOLVERS1D)
+def test_riemann1d_consistency(riemann):
+    p = orc.make_mhd_params(riemann=riemann, gamma=5.0 / 3.0)
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        q = np.array([rng.uniform(0.1, 2), rng.uniform(0.1, 2), rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-1, 1),
+                      rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-1, 1)])
+        fg = np.zeros(9)
+        orc.lib().orc_mhd_riemann(C.byref(p), orc.dptr(q), orc.dptr(q.copy()), orc.dptr(fg))
+        ref = phys_flux(q, 5.0 / 3.0)
+        n = 8 if riemann == "roe" else 9          # athena_roe leaves the internal-energy flux unset
+        assert np.allclose(fg[:n], ref[:n], rtol=1e-12, atol=1e-13), (riemann, fg, ref)
+
+
+@pytest.mark.parametrize("riemann", ["llf", "hll", "hlld", "roe"])
+def test_riemann1d_mirror_symmetry(riemann):
+    """Mirroring the problem (swap states, flip normal components) flips the sign of the even-parity fluxes."""
+    p = orc.make_mhd_params(riemann=riemann, gamma=5.0 / 3.0)
+    rng = np.random.default_rng(5)
+    flip = np.array([1, 1, -1, -1, 1, 1, 1, 1.0])
+    sgn = np.array([-1, -1, 1, 1, -1, -1, -1, -1.0])       # only the normal-momentum flux is even under the mirror
+    for _ in range(20):
+        ql = np.array([rng.uniform(0.5, 2), rng.uniform(0.5, 2)] + list(rng.uniform(-0.5, 0.5, 6)))
+        qr = np.array([rng.uniform(0.5, 2), rng.uniform(0.5, 2)] + list(rng.uniform(-0.5, 0.5, 6)))
+        f1, f2 = np.zeros(9), np.zeros(9)
+        orc.lib().orc_mhd_riemann(C.byref(p), orc.dptr(ql), orc.dptr(qr), orc.dptr(f1))
+        orc.lib().orc_mhd_riemann(C.byref(p), orc.dptr(qr * flip), orc.dptr(ql * flip), orc.dptr(f2))
+        assert np.allclose(f2[:8], sgn * f1[:8], rtol=1e-11, atol=1e-12), (riemann, f1, f2)
+
+
+@pytest.mark.parametrize("riemann2d", SOLVERS2D)
+def test_riemann2d_uniform_state_gives_ideal_emf(riemann2d):
+    p = orc.make_mhd_params(riemann2d=riemann2d, gamma=5.0 / 3.0)
+    rng = np.random.default_rng(7)
+    for _ in range(20):
+        s = np.array([rng.uniform(0.5, 2)] + list(rng.uniform(-1, 1, 3)) + [rng.uniform(0.5, 2)] + list(rng.uniform(-1, 1, 3)))
+        r, u, v, w, P, A, B, Cc = s
+        E = {0: v * Cc - w * B, 1: w * A - u * Cc, 2: u * B - v * A}
+        for d in range(3):
+            e = orc.lib().orc_mhd_emf(C.byref(p), orc.dptr(s), orc.dptr(s.copy()), orc.dptr(s.copy()), orc.dptr(s.copy()), d)
+            assert abs(e - E[d]) < 1e-12, (riemann2d, d, e, E[d])
+
+
+def _run(case, u0, nstep):
+    case.init_dense(u0)
+    u, dts = case.oracle_steps(nstep)
+    return case.dense(u), dts
+
+
+@pytest.mark.parametrize("riemann,riemann2d", [("llf", "llf"), ("hll", "hll"), ("hlld", "hlld"), ("roe", "roe"), ("roe", "llf"),
+                                               ("hlld", "hlla"), ("upwind", "upwind"), ("hydro", "llf")])
+@pytest.mark.parametrize("slope_type", [0, 1, 2, 3])
+def test_conservation_divb_and_face_copies(riemann, riemann2d, slope_type):
+    n = 8
+    c = MhdCase(3, riemann=riemann, riemann2d=riemann2d, slope_type=slope_type, slope_mag_type=min(slope_type, 2) if slope_type != 3 else 1)
+    u0 = mhd_smooth_state(n)
+    u1, dts = _run(c, u0, 4)
+    assert np.isfinite(u1).all() and (dts > 0).all()
+    for iv in range(5):
+        assert abs(u1[iv].sum() - u0[iv].sum()) <= 1e-13 * max(np.abs(u0[iv]).sum(), 1.0)
+    # mean field is conserved, div B stays at round-off, both copies of a face are the same number
+    for iv in (5, 6, 7):
+        assert abs(u1[iv].sum() - u0[iv].sum()) <= 1e-12 * n ** 3
+    assert np.abs(mhd_divb(u1, n)).max() < 5e-14 * n
+    assert np.array_equal(np.roll(u1[5], -1, axis=2), u1[8])
+    assert np.array_equal(np.roll(u1[6], -1, axis=1), u1[9])
+    assert np.array_equal(np.roll(u1[7], -1, axis=0), u1[10])
+
+
+def _cycle(u):
+    """f'(x',y',z') = f(x=y', y=z', z=x'): old x axis -> new y axis; vector components follow."""
+    t = lambda a: np.ascontiguousarray(np.transpose(a, (1, 2, 0)))
+    o = np.zeros_like(u)
+    o[0], o[4] = t(u[0]), t(u[4])
+    o[1], o[2], o[3] = t(u[3]), t(u[1]), t(u[2])          # v'_x = v_z, v'_y = v_x, v'_z = v_y
+    o[5], o[6], o[7] = t(u[7]), t(u[5]), t(u[6])
+    o[8], o[9], o[10] = t(u[10]), t(u[8]), t(u[9])
+    return o
+
+
+@pytest.mark.parametrize("riemann,riemann2d,slope_type", [("llf", "llf", 1), ("hlld", "hlld", 2), ("roe", "roe", 1), ("hll", "hlla", 3),
+                                                          ("roe", "upwind", 0)])
+def test_covariance_under_cyclic_axis_permutation(riemann, riemann2d, slope_type):
+    n = 8
+    u0 = mhd_smooth_state(n)
+    smt = 1 if slope_type == 3 else -1
+    a = MhdCase(3, riemann=riemann, riemann2d=riemann2d, slope_type=slope_type, slope_mag_type=smt)
+    b = MhdCase(3, riemann=riemann, riemann2d=riemann2d, slope_type=slope_type, slope_mag_type=smt)
+    ua, dta = _run(a, u0, 3)
+    ub, dtb = _run(b, _cycle(u0), 3)
+    assert np.allclose(dta, dtb, rtol=1e-13)
+    assert np.abs(_cycle(ua) - ub).max() < 1e-12
+
+
+def test_zero_field_limit_matches_hydro_oracle():
+    """B = 0: the MHD llf / hll solvers reduce to the hydro ones; the update must agree with the (golden-pinned) hydro oracle
+    up to the different algebraic form of the solvers (round-off)."""
+    from helpers import Case, smooth_state
+    n = 8
+    for riemann in ("llf", "hll"):
+        for st in (1, 2):
+            h = Case(3, 3, riemann=riemann, slope_type=st, gamma=1.4)
+            uh0 = smooth_state(3, n)
+            h.init_dense(uh0)
+            uh, dth = h.oracle_steps(3)
+            uh = h.dense(uh)
+            m = MhdCase(3, riemann=riemann, riemann2d="llf", slope_type=st, gamma=1.4)
+            um0 = np.zeros((11, n, n, n))
+            um0[:5] = uh0
+            um, dtm = _run(m, um0, 3)
+            assert np.allclose(dtm, dth, rtol=1e-12)
+            assert np.abs(um[:5] - uh).max() < 1e-11
+            assert np.abs(um[5:]).max() == 0.0
+
+
+def _tube_errors(level, nstep, rows, nthreads=8):
+    n, boxlen, gamma, x0 = 1 << level, 3.5, 1.6666667, 1.5
+    L = (1.0, 0.0, 0.0, 0.0, 1.0, 1.0, 1.0, 0.0)                 # imhd-tube.nml INIT_PARAMS
+    R = (0.2, 0.0, 0.0, 0.0, 0.2, 1.0, -0.989992, 0.141120)
+    c = MhdCase(level, riemann="hlld", riemann2d="llf", slope_type=1, bound=(2, 2, 0, 0, 0, 0), boxlen=boxlen, gamma=gamma)
+    c.init_dense(mhd_tube_state(n, L, R, x0, boxlen, gamma))
+    u, dts = c.oracle_steps(nstep, nthreads=nthreads)
+    t = dts.sum()
+    assert 0.3 < t < 0.5
+    u = c.dense(u)
+    assert np.abs(u - u[:, :1, :1, :]).max() < 1e-12              # stays uniform in y, z
+    assert np.abs(u[5] - 1.0).max() < 1e-13                       # the normal field of a 1-D problem never changes
+    xc = (np.arange(n) + 0.5) * boxlen / n
+    xs = (xc - x0) * 0.4 / t                                      # self-similar coordinate mapped to the fixture's t = 0.4
+    d = u[0, 0, 0]
+    prof = {1: d, 2: u[1, 0, 0] / d, 3: u[2, 0, 0] / d, 6: 0.5 * (u[6, 0, 0] + u[9, 0, 0]), 7: 0.5 * (u[7, 0, 0] + u[10, 0, 0])}
+    sel = (xs > rows[0, 0]) & (xs < rows[-1, 0])
+    return {k: float(np.abs(a[sel] - np.interp(xs[sel], rows[:, 0], rows[:, k])).mean()) for k, a in prof.items()}
+
+
+def test_imhd_tube_exact_solution():
+    """tests/mhd/imhd-tube (Ryu & Jones tube, all seven MHD waves; hlld): the 3-D restatement on uniform 32^3 and 64^3 grids
+    against the exact solution shipped with the reference (self-similar in (x-x0)/t).  L1 errors are at the level of a TVD
+    scheme on 32 / 64 cells and shrink with resolution (128^3: 0.018, 0.034, 0.042, 0.026, 0.006)."""
+    rows = np.array(json.load(open(os.path.join(GOLD, "imhd_tube_ana.json")))["rows"])
+    e32 = _tube_errors(5, 45, rows)
+    e64 = _tube_errors(6, 90, rows)
+    lim = {1: 0.035, 2: 0.065, 3: 0.075, 6: 0.05, 7: 0.011}      # rho, u, v, By, Bz
+    for k in lim:
+        assert e64[k] < lim[k], (k, e64)
+        assert e64[k] < 0.9 * e32[k], (k, e32, e64)
