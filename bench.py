@@ -36,7 +36,16 @@ WORKLOADS = {
     "smooth_256_llf": dict(level=8, riemann="llf", slope_type=1, ic="smooth"),
     "sedov3d_128_exact": dict(level=7, riemann="exact", slope_type=1, ic="sedov"),
     "sedov3d_64_exact": dict(level=6, riemann="exact", slope_type=1, ic="sedov"),
+    # BASELINE.json configs[4] (M4): namelist/tube_mhd.nml on 256^3, ideal MHD, riemann='roe', riemann2d='llf', slope_type=0
+    "tube_mhd_256_roe": dict(level=8, riemann="roe", riemann2d="llf", slope_type=0, ic="tube_mhd", mhd=True),
+    "tube_mhd_256_hlld": dict(level=8, riemann="hlld", riemann2d="hlld", slope_type=1, ic="tube_mhd", mhd=True),
+    "tube_mhd_128_roe": dict(level=7, riemann="roe", riemann2d="llf", slope_type=0, ic="tube_mhd", mhd=True),
+    "tube_mhd_64_roe": dict(level=6, riemann="roe", riemann2d="llf", slope_type=0, ic="tube_mhd", mhd=True),
 }
+MHD_GAMMA = 1.6666667
+TUBE_L = (1.0, 0.0, 0.0, 0.0, 2.0, 1.0, 0.0, 0.0)               # namelist/tube_mhd.nml:25-38 (d,u,v,w,P,A,B,C)
+TUBE_R = (0.2, 1.186, 2.967, 0.0, 0.1368, 1.0, 1.6405, 0.0)
+MHD_BYTES_PER_CELL = 176.0   # 2 * 11 stored variables * 8 B
 BYTES_PER_CELL = 80.0   # algorithmic: read uold once + write unew once = 2*nvar*8 B
 
 
@@ -69,6 +78,24 @@ def smooth_ic(nxyz):
         u[0] = rho
         u[1], u[2], u[3] = rho * vx, rho * vy, rho * vz
         u[4] = p / (GAMMA - 1) + 0.5 * rho * (vx ** 2 + vy ** 2 + vz ** 2)
+        return u
+    return fn
+
+
+def tube_mhd_ic(x_lo, x_mid, x_hi):
+    """namelist/tube_mhd.nml INIT_PARAMS: two 'square' regions spanning y,z (mhd/condinit.f90); x in coarse-cell units.
+    Cells outside [x_lo, x_hi) (periodic multi-rank variant) repeat the pattern."""
+    def fn(x, y, z):
+        left = ((x - x_lo) % (x_hi - x_lo)) < (x_mid - x_lo)
+        u = np.zeros((11, len(x)))
+        for sel, st in ((left, TUBE_L), (~left, TUBE_R)):
+            d, vx, vy, vz, P, A, B, Cc = st
+            u[0][sel] = d
+            u[1][sel], u[2][sel], u[3][sel] = d * vx, d * vy, d * vz
+            u[5][sel] = A; u[8][sel] = A
+            u[6][sel] = B; u[9][sel] = B
+            u[7][sel] = Cc; u[10][sel] = Cc
+            u[4][sel] = P / (MHD_GAMMA - 1.0) + 0.5 * d * (vx * vx + vy * vy + vz * vz) + 0.5 * (A * A + B * B + Cc * Cc)
         return u
     return fn
 
@@ -132,6 +159,8 @@ def cpu_reference_run(workload, steps, warmup, sample_level=7):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import SEDOV3D_REGIONS, smooth_state
     w = WORKLOADS[workload]
+    if w.get("mhd"):
+        return cpu_reference_run_mhd(workload, steps, warmup, sample_level=6)
     p = orc.make_params(ndim=3, riemann=w["riemann"], slope_type=w["slope_type"], boxlen=0.5, gamma=GAMMA,
                         courant_factor=0.8)
 
@@ -171,6 +200,48 @@ def cpu_reference_run(workload, steps, warmup, sample_level=7):
             "seconds": el}, el / steps
 
 
+def cpu_reference_run_mhd(workload, steps, warmup, sample_level=6):
+    """MHD workloads: oracle/ramses_oracle_mhd.c (per-oct 6^3 patches like mag_unsplit, OpenMP over octs)."""
+    from oracle import orc
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import mhd_tube_state
+    w = WORKLOADS[workload]
+    p = orc.make_mhd_params(slope_type=w["slope_type"], riemann=w["riemann"], riemann2d=w["riemann2d"], gamma=MHD_GAMMA,
+                            courant_factor=0.8, boxlen=2.0)
+
+    def setup(level):
+        m = orc.Mesh(3, level, (2, 2, 0, 0, 0, 0), 0, 1)
+        u = m.new_state(11)
+        n = 1 << level
+        m.dense_to_level(mhd_tube_state(n, TUBE_L, TUBE_R, 1.0, 2.0, MHD_GAMMA), u, level, 11)
+        return m, u
+    nmax = host_threads()
+    cands = sorted({min(nmax, c) for c in (8, 16, 32, 64, 128, nmax)})
+    mc, uc = setup(5)
+    best, best_rate = cands[0], 0.0
+    for c in cands:
+        orc.mhd_run_uniform(p, mc, 5, 1, uc, nthreads=c)
+        t0 = time.perf_counter()
+        orc.mhd_run_uniform(p, mc, 5, 2, uc, nthreads=c)
+        rate = 2 * 32 ** 3 / (time.perf_counter() - t0)
+        if rate > best_rate:
+            best, best_rate = c, rate
+    nthr = best
+    m, u = setup(sample_level)
+    n = 1 << sample_level
+    if warmup:
+        orc.mhd_run_uniform(p, m, sample_level, warmup, u, nthreads=nthr)
+    t0 = time.perf_counter()
+    orc.mhd_run_uniform(p, m, sample_level, steps, u, nthreads=nthr)
+    el = time.perf_counter() - t0
+    return {"value": n ** 3 * steps / el, "unit": "cell-updates/s", "cores": nthr, "kind": "port",
+            "sample": f"tube_mhd {n}^3 (x zero-gradient, y/z periodic), riemann={w['riemann']}, riemann2d={w['riemann2d']}, "
+                      f"slope_type={w['slope_type']}, {steps} level steps (courant_fine+set_unew+godunov_fine+set_uold+"
+                      f"make_boundary_hydro), C restatement of the RAMSES MHD algorithm (oracle/ramses_oracle_mhd.c, gcc -O2 "
+                      f"-ffp-contract=off, OpenMP over octs); {nthr} of {nmax} host threads (fastest of a calibration sweep)",
+            "seconds": el}, el / steps
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -196,7 +267,7 @@ def main():
         line = {"impl": "reference", "metric": "cell_updates_per_s", "value": cb["value"], "unit": "cell-updates/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec_per_step * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload, "note": "each step is a bounded 128^3 sample of the workload"},
+                "config": {"workload": args.workload, "note": "each step is a bounded sample of the workload (cpu_baseline.sample)"},
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -213,10 +284,22 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     level = w["level"]
     coarse = coarse_dims_for_ranks(3, world)
-    boxlen = 0.5
-    a = build_uniform_tree(3, level, coarse=coarse, myid=rank + 1, ncpu=world, order=args.order, boxlen=boxlen)
-    a.gamma, a.courant_factor, a.slope_type, a.riemann = GAMMA, 0.8, w["slope_type"], w["riemann"]
-    fill_state(a, level, sedov_ic(boxlen, coarse[0], level) if w["ic"] == "sedov" else smooth_ic(coarse))
+    mhd = bool(w.get("mhd"))
+    nvs = 11 if mhd else 5
+    bpc = MHD_BYTES_PER_CELL if mhd else BYTES_PER_CELL
+    if mhd:
+        # single rank: the namelist's own box (x zero-gradient boundaries, boxlen=2); several ranks: the periodic
+        # image of the same tube (one coarse cell per rank, no physical boundary) -- same work per cell
+        boxlen = 2.0
+        xb = (2, 2) if world == 1 else None
+        a = build_uniform_tree(3, level, coarse=coarse, myid=rank + 1, ncpu=world, order=args.order, boxlen=boxlen, mhd=True, xbound=xb)
+        a.gamma, a.courant_factor, a.slope_type, a.riemann, a.riemann2d = MHD_GAMMA, 0.8, w["slope_type"], w["riemann"], w["riemann2d"]
+        fill_state(a, level, tube_mhd_ic(1.0, 1.5, 2.0) if world == 1 else tube_mhd_ic(0.0, 0.5 * coarse[0], float(coarse[0])))
+    else:
+        boxlen = 0.5
+        a = build_uniform_tree(3, level, coarse=coarse, myid=rank + 1, ncpu=world, order=args.order, boxlen=boxlen)
+        a.gamma, a.courant_factor, a.slope_type, a.riemann = GAMMA, 0.8, w["slope_type"], w["riemann"]
+        fill_state(a, level, sedov_ic(boxlen, coarse[0], level) if w["ic"] == "sedov" else smooth_ic(coarse))
     h = HydroGPU(a, device=local_rank)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8)
@@ -281,19 +364,21 @@ def main():
         peak, peak_src = json.load(open(peaks_file))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = BYTES_PER_CELL * ncell_rank / (k_ms * 1e-3) / 1e9
+    achieved = bpc * ncell_rank / (k_ms * 1e-3) / 1e9
     traffic = None
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tf):
         traffic = json.load(open(tf)).get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "sweep_dense_kernel<3,%s>" % w["riemann"], "kernel_ms": k_ms,
-                "algorithmic_bytes_per_launch": BYTES_PER_CELL * ncell_rank, "peak_source": peak_src,
+                "traffic": traffic, "kernel": ("MHD sweep: 6 kernels (prim, efield, trace, flux<%s>, emf<%s>, update)" % (w["riemann"], w["riemann2d"]))
+                if mhd else "sweep_dense_kernel<3,%s>" % w["riemann"], "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": bpc * ncell_rank, "peak_source": peak_src,
                 "note": "FP64 issue rate, not HBM, is the binding roof for this kernel (DESIGN.md)"}
 
     # end-to-end through the reference-facing call godunov_fine(ilevel) on HOST arrays (H2D + sweep + D2H per step)
     h.download_state(level)
     a.dtnew[level] = float(dts[-1])      # a CFL-limited dt of this run
+    a.unew[:, :] = a.uold                # boundary / ghost cells of the second host array hold valid states too
     h.godunov_fine(level)           # warm
     barrier()
     t0 = time.perf_counter()
@@ -309,7 +394,7 @@ def main():
     info = h.level_info(level)
     gspan = info.nslot        # contiguous igrid window of the level on this rank
     e2e = {"value": ncell_total * args.e2e_steps / e2e_t, "unit": "cell-updates/s",
-           "h2d_bytes_per_step": int(5 * 8 * gspan * 8), "d2h_bytes_per_step": int(5 * 8 * gspan * 8),
+           "h2d_bytes_per_step": int(nvs * 8 * gspan * 8), "d2h_bytes_per_step": int(nvs * 8 * gspan * 8),
            "steps": args.e2e_steps, "api": "rgpu_godunov_fine(ilevel, dt, uold_host, unew_host), pinned host arrays"}
 
     cpu_baseline = None
@@ -326,10 +411,10 @@ def main():
                 "steps": steps, "warmup": warmup, "ms_per_step": t_dev / steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "grid_per_gpu": f"{n}^3", "global_grid":
-                           f"{n * coarse[0]}x{n * coarse[1]}x{n * coarse[2]}", "riemann": w["riemann"],
+                           f"{n * coarse[0]}x{n * coarse[1]}x{n * coarse[2]}", "riemann": w["riemann"], "riemann2d": w.get("riemann2d"),
                            "slope_type": w["slope_type"], "decomposition": f"{coarse[0]}x{coarse[1]}x{coarse[2]} coarse cells, one per rank",
                            "oct_order": args.order,
-                           "l2": "inputs larger than L2 (state %.2f GB per rank vs 126 MB L2), no flush" % (5 * 8 * ncell_rank / 1e9)},
+                           "l2": "inputs larger than L2 (state %.2f GB per rank vs 126 MB L2), no flush" % (nvs * 8 * ncell_rank / 1e9)},
                 "wall_ms_per_step": wall / steps * 1e3, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))

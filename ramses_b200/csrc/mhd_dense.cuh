@@ -79,14 +79,15 @@ __global__ void __launch_bounds__(256) mhd_prim_kernel(const MhdArgs a) {
   for (int n = 0; n < 11; n++) u[n] = __ldg(a.uin + n * vs + off);
   double q[8];
   q[0] = fmx(u[0], a.P.smallr);
-  q[1] = u[1] / q[0]; q[2] = u[2] / q[0]; q[3] = u[3] / q[0];
+  const double rq0 = rcp_rn(q[0]);   // shared reciprocal, same bits as the four IEEE divisions (hydro_device.cuh div_rn)
+  q[1] = div_rn(u[1], q[0], rq0); q[2] = div_rn(u[2], q[0], rq0); q[3] = div_rn(u[3], q[0], rq0);
   q[5] = (u[5] + u[8]) * 0.5;
   q[6] = (u[6] + u[9]) * 0.5;
   q[7] = (u[7] + u[10]) * 0.5;
   const double eken = 0.5 * (q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   const double emag = 0.5 * (q[5] * q[5] + q[6] * q[6] + q[7] * q[7]);
   const double etot = u[4] - emag - 0.0;
-  const double eint = etot / q[0] - eken;
+  const double eint = div_rn(etot, q[0], rq0) - eken;
   q[4] = fmx((a.P.gamma - 1.0) * q[0] * eint, a.P.smallp);
   double* W = a.W;
 #pragma unroll
@@ -139,10 +140,11 @@ __global__ void __launch_bounds__(256) mhd_efield_kernel(const MhdArgs a) {
 
 #endif  // MHD_DEFINE_KERNELS (passes 1, 2)
 // ---------------------------------------------------------------------------------------------------- pass 3
+__device__ __forceinline__ double slope_mmd(double st, double ql, double qc, double qr) { return slope_mm(st, ql, qc, qr).v; }
 // one limited slope of the cell-centred variables (all slope types of the NDIM=3 MHD build except type 3, which needs the
 // whole 3^3 neighbourhood and is handled by the caller)
 __device__ __forceinline__ double mhd_slope1(int st, double theta, double ql, double qc, double qr) {
-  if (st == 1 || st == 2) return slope_mm((double)st, ql, qc, qr);
+  if (st == 1 || st == 2) return slope_mm((double)st, ql, qc, qr).v;
   const double dlft = qc - ql, drgt = qr - qc;
   if (st == 7) return ((dlft * drgt) <= 0.0) ? 0.0 : (2 * dlft * drgt / (dlft + drgt));
   // st == 8
@@ -221,18 +223,18 @@ __global__ void __launch_bounds__(256) mhd_trace_kernel(const MhdArgs a) {
       const double* Bx = BF;
       const double* By = BF + nc;
       const double* Bz = BF + 2 * nc;
-      fs[0] = 0.5 * slope_mm(s, Bx[cym], Bx[c], Bx[cyp]);                                                     // dALy
-      fs[1] = 0.5 * slope_mm(s, Bx[cidx(g, xp, ym, p.z)], Bx[cxp], Bx[cidx(g, xp, yp, p.z)]);                 // dARy
-      fs[2] = 0.5 * slope_mm(s, Bx[czm], Bx[c], Bx[czp]);                                                     // dALz
-      fs[3] = 0.5 * slope_mm(s, Bx[cidx(g, xp, p.y, zm)], Bx[cxp], Bx[cidx(g, xp, p.y, zp)]);                 // dARz
-      fs[4] = 0.5 * slope_mm(s, By[cxm], By[c], By[cxp]);                                                     // dBLx
-      fs[5] = 0.5 * slope_mm(s, By[cidx(g, xm, yp, p.z)], By[cyp], By[cidx(g, xp, yp, p.z)]);                 // dBRx
-      fs[6] = 0.5 * slope_mm(s, By[czm], By[c], By[czp]);                                                     // dBLz
-      fs[7] = 0.5 * slope_mm(s, By[cidx(g, p.x, yp, zm)], By[cyp], By[cidx(g, p.x, yp, zp)]);                 // dBRz
-      fs[8] = 0.5 * slope_mm(s, Bz[cxm], Bz[c], Bz[cxp]);                                                     // dCLx
-      fs[9] = 0.5 * slope_mm(s, Bz[cidx(g, xm, p.y, zp)], Bz[czp], Bz[cidx(g, xp, p.y, zp)]);                 // dCRx
-      fs[10] = 0.5 * slope_mm(s, Bz[cym], Bz[c], Bz[cyp]);                                                    // dCLy
-      fs[11] = 0.5 * slope_mm(s, Bz[cidx(g, p.x, ym, zp)], Bz[czp], Bz[cidx(g, p.x, yp, zp)]);                // dCRy
+      fs[0] = 0.5 * slope_mmd(s, Bx[cym], Bx[c], Bx[cyp]);                                                     // dALy
+      fs[1] = 0.5 * slope_mmd(s, Bx[cidx(g, xp, ym, p.z)], Bx[cxp], Bx[cidx(g, xp, yp, p.z)]);                 // dARy
+      fs[2] = 0.5 * slope_mmd(s, Bx[czm], Bx[c], Bx[czp]);                                                     // dALz
+      fs[3] = 0.5 * slope_mmd(s, Bx[cidx(g, xp, p.y, zm)], Bx[cxp], Bx[cidx(g, xp, p.y, zp)]);                 // dARz
+      fs[4] = 0.5 * slope_mmd(s, By[cxm], By[c], By[cxp]);                                                     // dBLx
+      fs[5] = 0.5 * slope_mmd(s, By[cidx(g, xm, yp, p.z)], By[cyp], By[cidx(g, xp, yp, p.z)]);                 // dBRx
+      fs[6] = 0.5 * slope_mmd(s, By[czm], By[c], By[czp]);                                                     // dBLz
+      fs[7] = 0.5 * slope_mmd(s, By[cidx(g, p.x, yp, zm)], By[cyp], By[cidx(g, p.x, yp, zp)]);                 // dBRz
+      fs[8] = 0.5 * slope_mmd(s, Bz[cxm], Bz[c], Bz[cxp]);                                                     // dCLx
+      fs[9] = 0.5 * slope_mmd(s, Bz[cidx(g, xm, p.y, zp)], Bz[czp], Bz[cidx(g, xp, p.y, zp)]);                 // dCRx
+      fs[10] = 0.5 * slope_mmd(s, Bz[cym], Bz[c], Bz[cyp]);                                                    // dCLy
+      fs[11] = 0.5 * slope_mmd(s, Bz[cidx(g, p.x, ym, zp)], Bz[czp], Bz[cidx(g, p.x, yp, zp)]);                // dCRy
     }
   }
   // CT half-step of the face fields :905-947
@@ -255,9 +257,12 @@ __global__ void __launch_bounds__(256) mhd_trace_kernel(const MhdArgs a) {
     const double drz = sz[0], duz = sz[1], dvz = sz[2], dwz = sz[3], dpz = sz[4], dAz = sz[5], dBz = sz[6];
     const double gamma = P.gamma;
     const double sr0 = (-u * drx - dux * r) * dtdx + (-v * dry - dvy * r) * dtdy + (-w * drz - dwz * r) * dtdz;
-    const double su0 = (-u * dux - (dpx + B * dBx + C * dCx) / r) * dtdx + (-v * duy + B * dAy / r) * dtdy + (-w * duz + C * dAz / r) * dtdz;
-    const double sv0 = (-u * dvx + A * dBx / r) * dtdx + (-v * dvy - (dpy + A * dAy + C * dCy) / r) * dtdy + (-w * dvz + C * dBz / r) * dtdz;
-    const double sw0 = (-u * dwx + A * dCx / r) * dtdx + (-v * dwy + B * dCy / r) * dtdy + (-w * dwz - (dpz + A * dAz + B * dBz) / r) * dtdz;
+    const double rr = rcp_rn(r);   // r >= smallr; the nine quotients share the reciprocal (same bits as IEEE `/`)
+#define DR(x) div_rn((x), r, rr)
+    const double su0 = (-u * dux - DR(dpx + B * dBx + C * dCx)) * dtdx + (-v * duy + DR(B * dAy)) * dtdy + (-w * duz + DR(C * dAz)) * dtdz;
+    const double sv0 = (-u * dvx + DR(A * dBx)) * dtdx + (-v * dvy - DR(dpy + A * dAy + C * dCy)) * dtdy + (-w * dvz + DR(C * dBz)) * dtdz;
+    const double sw0 = (-u * dwx + DR(A * dCx)) * dtdx + (-v * dwy + DR(B * dCy)) * dtdy + (-w * dwz - DR(dpz + A * dAz + B * dBz)) * dtdz;
+#undef DR
     const double sp0 = (-u * dpx - dux * gamma * pp) * dtdx + (-v * dpy - dvy * gamma * pp) * dtdy + (-w * dpz - dwz * gamma * pp) * dtdz;
     r = r + sr0; u = u + su0; v = v + sv0; w = w + sw0; pp = pp + sp0;
   }
@@ -365,20 +370,22 @@ __device__ __forceinline__ void face_flux(const MhdArgs& a, const double* TR, lo
   // ln,lt1,lt2,bn,bt1,bt2 (0-based variable numbers) :51,:84,:117
   constexpr int ln = DIR == 0 ? 1 : DIR == 1 ? 2 : 3, lt1 = DIR == 0 ? 2 : 1, lt2 = DIR == 2 ? 2 : 3;
   constexpr int bn = DIR == 0 ? 5 : DIR == 1 ? 6 : 7, bt1 = DIR == 0 ? 6 : 5, bt2 = DIR == 2 ? 6 : 7;
-  double ql[8], qr[8], fg[9];
+  real ql[8], qr[8], fg[9];
   const double bn_mean = 0.5 * (sm[bn] + sp[bn]);
   ql[0] = sm[0]; ql[1] = sm[4]; ql[2] = sm[ln]; ql[3] = bn_mean; ql[4] = sm[lt1]; ql[5] = sm[bt1]; ql[6] = sm[lt2]; ql[7] = sm[bt2];
   qr[0] = sp[0]; qr[1] = sp[4]; qr[2] = sp[ln]; qr[3] = bn_mean; qr[4] = sp[lt1]; qr[5] = sp[bt1]; qr[6] = sp[lt2]; qr[7] = sp[bt2];
   riemann1d<R1D>(a.P, ql, qr, fg);
   double f[5];   // (rho, mx, my, mz, E); the induction fluxes are dropped (flux(:,6:8)=0, godunov_fine.f90:778-879)
-  f[0] = fg[0]; f[4] = fg[1]; f[ln] = fg[2]; f[lt1] = fg[4]; f[lt2] = fg[6];
+  f[0] = fg[0].v; f[4] = fg[1].v; f[ln] = fg[2].v; f[lt1] = fg[4].v; f[lt2] = fg[6].v;
   double* F = a.W + (MW_F + 5 * DIR) * nc;
 #pragma unroll
-  for (int n = 0; n < 5; n++) F[n * nc + c] = f[n] * dt / a.dx;   // flux = fx*dt/dx :83
+  const double rdx = rcp_rn(a.dx);
+#pragma unroll
+  for (int n = 0; n < 5; n++) F[n * nc + c] = div_rn(f[n] * dt, a.dx, rdx);   // flux = fx*dt/dx :83
 }
 
-template <int R1D, bool SL>
-__global__ void __launch_bounds__(128) mhd_flux_kernel(const MhdArgs a) {
+template <int R1D, bool SL, int MINB>
+__global__ void __launch_bounds__(128, MINB) mhd_flux_kernel(const MhdArgs a) {
   const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (c >= a.nc) return;
   const DenseGeom& g = a.g;
@@ -401,7 +408,7 @@ __global__ void __launch_bounds__(128) mhd_flux_kernel(const MhdArgs a) {
 template <int R2D>
 __device__ __forceinline__ double emf_corners(const MPhys& P, const double* RT, const double* RB, const double* LT, const double* LB,
                                               int lp1, int lp2, int lor, int bp1, int bp2, int bor) {
-  double qLL[8], qRL[8], qLR[8], qRR[8];   // :1506-1541 (qLL<-qRT, qRL<-qLT, qLR<-qRB, qRR<-qLB)
+  real qLL[8], qRL[8], qLR[8], qRR[8];   // :1506-1541 (qLL<-qRT, qRL<-qLT, qLR<-qRB, qRR<-qLB)
   qLL[0] = RT[0]; qRL[0] = LT[0]; qLR[0] = RB[0]; qRR[0] = LB[0];
   qLL[1] = RT[4]; qRL[1] = LT[4]; qLR[1] = RB[4]; qRR[1] = LB[4];
   qLL[2] = RT[lp1]; qRL[2] = LT[lp1]; qLR[2] = RB[lp1]; qRR[2] = LB[lp1];
@@ -412,11 +419,11 @@ __device__ __forceinline__ double emf_corners(const MPhys& P, const double* RT, 
   qLR[6] = 0.5 * (RT[bp2] + RB[bp2]); qRR[6] = 0.5 * (LT[bp2] + LB[bp2]);
   qLL[4] = RT[lor]; qRL[4] = LT[lor]; qLR[4] = RB[lor]; qRR[4] = LB[lor];
   qLL[7] = RT[bor]; qRL[7] = LT[bor]; qLR[7] = RB[bor]; qRR[7] = LB[bor];
-  return emf_edge<R2D>(P, qLL, qRL, qLR, qRR);
+  return emf_edge<R2D>(P, qLL, qRL, qLR, qRR).v;
 }
 
-template <int R2D, bool SL>
-__global__ void __launch_bounds__(128) mhd_emf_kernel(const MhdArgs a) {
+template <int R2D, bool SL, int MINB>
+__global__ void __launch_bounds__(128, MINB) mhd_emf_kernel(const MhdArgs a) {
   const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (c >= a.nc) return;
   const DenseGeom& g = a.g;
@@ -429,6 +436,7 @@ __global__ void __launch_bounds__(128) mhd_emf_kernel(const MhdArgs a) {
   const double* TR = a.W + MW_TR * nc;
   double* EM = a.W + MW_EM * nc;
   const double dt = *a.dt_dev;
+  const double rdx = rcp_rn(a.dx);
   const int xm = wm(p.x, g.ncx, g.wrapx), ym = wm(p.y, g.ncy, g.wrapy), zm = wm(p.z, g.ncz, g.wrapz);
   const MPhys& P = a.P;
   double RT[8], RB[8], LT[8], LB[8];
@@ -438,21 +446,21 @@ __global__ void __launch_bounds__(128) mhd_emf_kernel(const MhdArgs a) {
     load_tc<SL>(TR, nc, cidx(g, xm, p.y, p.z), t); edge_state<2, +1, -1>(P, t, RB);
     load_tc<SL>(TR, nc, cidx(g, p.x, ym, p.z), t); edge_state<2, -1, +1>(P, t, LT);
     load_tc<SL>(TR, nc, c, t); edge_state<2, -1, -1>(P, t, LB);
-    EM[2 * nc + c] = emf_corners<R2D>(P, RT, RB, LT, LB, 1, 2, 3, 5, 6, 7) * dt / a.dx;
+    EM[2 * nc + c] = div_rn(emf_corners<R2D>(P, RT, RB, LT, LB, 1, 2, 3, 5, 6, 7) * dt, a.dx, rdx);
   }
   if (ex && oy && ez) {   // emfy: (qRT(i-1,k-1), qLT(i,k-1), qRB(i-1,k), qLB(i,k)) component 2, permutation 4,2,3,8,6,7
     load_tc<SL>(TR, nc, cidx(g, xm, p.y, zm), t); edge_state<1, +1, +1>(P, t, RT);
     load_tc<SL>(TR, nc, cidx(g, p.x, p.y, zm), t); edge_state<1, -1, +1>(P, t, RB);   // dummy qRB <- actual qLT
     load_tc<SL>(TR, nc, cidx(g, xm, p.y, p.z), t); edge_state<1, +1, -1>(P, t, LT);   // dummy qLT <- actual qRB
     load_tc<SL>(TR, nc, c, t); edge_state<1, -1, -1>(P, t, LB);
-    EM[1 * nc + c] = emf_corners<R2D>(P, RT, RB, LT, LB, 3, 1, 2, 7, 5, 6) * dt / a.dx;
+    EM[1 * nc + c] = div_rn(emf_corners<R2D>(P, RT, RB, LT, LB, 3, 1, 2, 7, 5, 6) * dt, a.dx, rdx);
   }
   if (ox && ey && ez) {   // emfx: (qRT(j-1,k-1), qRB(j-1,k), qLT(j,k-1), qLB(j,k)) component 1, permutation 3,4,2,7,8,6
     load_tc<SL>(TR, nc, cidx(g, p.x, ym, zm), t); edge_state<0, +1, +1>(P, t, RT);
     load_tc<SL>(TR, nc, cidx(g, p.x, ym, p.z), t); edge_state<0, +1, -1>(P, t, RB);
     load_tc<SL>(TR, nc, cidx(g, p.x, p.y, zm), t); edge_state<0, -1, +1>(P, t, LT);
     load_tc<SL>(TR, nc, c, t); edge_state<0, -1, -1>(P, t, LB);
-    EM[0 * nc + c] = emf_corners<R2D>(P, RT, RB, LT, LB, 2, 3, 1, 6, 7, 5) * dt / a.dx;
+    EM[0 * nc + c] = div_rn(emf_corners<R2D>(P, RT, RB, LT, LB, 2, 3, 1, 6, 7, 5) * dt, a.dx, rdx);
   }
 }
 
@@ -500,10 +508,13 @@ __global__ void __launch_bounds__(256) mhd_update_kernel(const MhdArgs a) {
     for (int d = 1; d <= 3; d++) {
       const double b2 = 0.125 * SQ(u[4 + d] + u[7 + d]);
       em = em + b2;
-      ei = ei - 0.5 * (u[d] * u[d]) / u[0] - b2;
+      ei = ei - fdiv(0.5 * (u[d] * u[d]), u[0]) - b2;
     }
     m2 += ei; m3 += em;
-    const double dtc = mhd_cmpdt_cell(a.P, u, a.dx);
+    real uu[11];
+#pragma unroll
+    for (int n = 0; n < 11; n++) uu[n] = u[n];
+    const double dtc = mhd_cmpdt_cell(a.P, uu, a.dx).v;
     my_dt = dtc < my_dt ? dtc : my_dt;
   }
   __shared__ double red[5][32];
@@ -542,10 +553,13 @@ __global__ void __launch_bounds__(256) mhd_courant_kernel(const double* __restri
     for (int d = 1; d <= 3; d++) {
       const double b2 = 0.125 * SQ(u[4 + d] + u[7 + d]);
       em = em + b2;
-      ei = ei - 0.5 * (u[d] * u[d]) / u[0] - b2;
+      ei = ei - fdiv(0.5 * (u[d] * u[d]), u[0]) - b2;
     }
     m2 += ei; m3 += em;
-    const double dtc = mhd_cmpdt_cell(P, u, dx);
+    real uu[11];
+#pragma unroll
+    for (int n = 0; n < 11; n++) uu[n] = u[n];
+    const double dtc = mhd_cmpdt_cell(P, uu, dx).v;
     my_dt = dtc < my_dt ? dtc : my_dt;
   }
   __shared__ double red[5][32];

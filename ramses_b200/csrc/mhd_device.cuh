@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "hydro_device.cuh"
+#include "real64.cuh"
 
 namespace rgpu {
 
@@ -21,22 +22,23 @@ struct MPhys {
   int slope_type, slope_mag_type;
 };
 
-__device__ __forceinline__ double fmx4(double a, double b, double c, double d) { return fmx(fmx(fmx(a, b), c), d); }
-__device__ __forceinline__ double fmn4(double a, double b, double c, double d) { return fmn(fmn(fmn(a, b), c), d); }
-__device__ __forceinline__ double SQ(double a) { return a * a; }
+using real = R64;   // see real64.cuh: IEEE-identical, branch-free `/` and sqrt
+template <class T> __device__ __forceinline__ T fmx4(T a, T b, T c, T d) { return fmx(fmx(fmx(a, b), c), d); }
+template <class T> __device__ __forceinline__ T fmn4(T a, T b, T c, T d) { return fmn(fmn(fmn(a, b), c), d); }
+template <class T> __device__ __forceinline__ T SQ(T a) { return a * a; }
 #define zero 0.0
 #define one 1.0
 #define two 2.0
 #define half 0.5
 #define forth 0.25
 
-__device__ __forceinline__ void find_mhd_flux(const MPhys& M, const double* q, double* c, double* ff) { /* :704 */
-  double entho = one / (M.gamma - one);
-  double d = q[0], P = q[1], u = q[2], A = q[3], v = q[4], B = q[5], w = q[6], C = q[7];
-  double ecin = half * (u * u + v * v + w * w) * d;
-  double emag = half * (A * A + B * B + C * C);
-  double etot = P * entho + ecin + emag;
-  double Ptot = P + emag;
+__device__ __forceinline__ void find_mhd_flux(const MPhys& M, const real* q, real* c, real* ff) { /* :704 */
+  real entho = one / (M.gamma - one);
+  real d = q[0], P = q[1], u = q[2], A = q[3], v = q[4], B = q[5], w = q[6], C = q[7];
+  real ecin = half * (u * u + v * v + w * w) * d;
+  real emag = half * (A * A + B * B + C * C);
+  real etot = P * entho + ecin + emag;
+  real Ptot = P + emag;
   c[0] = d; c[1] = etot; c[2] = d * u; c[3] = A; c[4] = d * v; c[5] = B; c[6] = d * w; c[7] = C;
   c[8] = P * entho;
   ff[0] = d * u;
@@ -50,128 +52,135 @@ __device__ __forceinline__ void find_mhd_flux(const MPhys& M, const double* q, d
   ff[8] = P * entho * u;
 }
 
-__device__ __forceinline__ double find_speed_fast(const MPhys& M, const double* q) { /* :823 */
-  double d = q[0], P = q[1], A = q[3], B = q[5], C = q[7];
-  double B2 = A * A + B * B + C * C;
-  double c2 = M.gamma * P / d;
-  double d2 = half * (B2 / d + c2);
-  return sqrt(d2 + sqrt(d2 * d2 - c2 * A * A / d));
+__device__ __forceinline__ real find_speed_fast(const MPhys& M, const real* q) { /* :823 */
+  real d = q[0], P = q[1], A = q[3], B = q[5], C = q[7];
+  const RcpD rd(d);
+  real B2 = A * A + B * B + C * C;
+  real c2 = M.gamma * P / rd;
+  real d2 = half * (B2 / rd + c2);
+  return rsqrt64(d2 + rsqrt64(d2 * d2 - c2 * A * A / rd));
 }
-__device__ __forceinline__ double find_speed_info(const MPhys& M, const double* q) { return find_speed_fast(M, q) + fabs(q[2]); } /* :787 */
-__device__ __forceinline__ double find_speed_alfven(const double* q) { return sqrt(q[3] * q[3] / q[0]); }                                /* :857 */
+__device__ __forceinline__ real find_speed_info(const MPhys& M, const real* q) { return find_speed_fast(M, q) + rabs(q[2]); } /* :787 */
+__device__ __forceinline__ real find_speed_alfven(const real* q) { return rsqrt64(q[3] * q[3] / q[0]); }                                /* :857 */
 
-__device__ __forceinline__ void mean_bn(double* ql, double* qr) { double bx = half * (ql[3] + qr[3]); ql[3] = bx; qr[3] = bx; }
+__device__ __forceinline__ void mean_bn(real* ql, real* qr) { real bx = half * (ql[3] + qr[3]); ql[3] = bx; qr[3] = bx; }
 
-__device__ __forceinline__ void lax_friedrich(const MPhys& M, double* ql, double* qr, double* fg, double zero_flux) { /* :352 */
-  double ul[9], ur[9], fl[9], fr[9];
+__device__ __forceinline__ void lax_friedrich(const MPhys& M, real* ql, real* qr, real* fg, real zero_flux) { /* :352 */
+  real ul[9], ur[9], fl[9], fr[9];
   mean_bn(ql, qr);
   find_mhd_flux(M, ql, ul, fl);
   find_mhd_flux(M, qr, ur, fr);
-  double vl = find_speed_info(M, ql), vr = find_speed_info(M, qr);
-  double vm = fmx(vl, vr);
+  real vl = find_speed_info(M, ql), vr = find_speed_info(M, qr);
+  real vm = fmx(vl, vr);
   for (int n = 0; n < 9; n++) {
-    double fmean = half * (fr[n] + fl[n]) * zero_flux;
-    double udiff = half * (ur[n] - ul[n]);
+    real fmean = half * (fr[n] + fl[n]) * zero_flux;
+    real udiff = half * (ur[n] - ul[n]);
     fg[n] = fmean - vm * udiff;
   }
 }
 
-__device__ __forceinline__ void upwind(const MPhys& M, double* ql, double* qr, double* fg, double zero_flux) { /* :313 */
-  double ul[9], ur[9], fl[9], fr[9];
+__device__ __forceinline__ void upwind(const MPhys& M, real* ql, real* qr, real* fg, real zero_flux) { /* :313 */
+  real ul[9], ur[9], fl[9], fr[9];
   mean_bn(ql, qr);
   find_mhd_flux(M, ql, ul, fl);
   find_mhd_flux(M, qr, ur, fr);
-  double vleft = half * (ql[2] + qr[2]);
+  real vleft = half * (ql[2] + qr[2]);
   for (int n = 0; n < 9; n++) {
-    double fmean = half * (fr[n] + fl[n]) * zero_flux;
-    double udiff = half * (ur[n] - ul[n]);
-    fg[n] = fmean - fabs(vleft) * udiff;
+    real fmean = half * (fr[n] + fl[n]) * zero_flux;
+    real udiff = half * (ur[n] - ul[n]);
+    fg[n] = fmean - rabs(vleft) * udiff;
   }
 }
 
-__device__ __forceinline__ void hll(const MPhys& M, double* ql, double* qr, double* fg) { /* :391 */
-  double ul[9], ur[9], fl[9], fr[9];
+__device__ __forceinline__ void hll(const MPhys& M, real* ql, real* qr, real* fg) { /* :391 */
+  real ul[9], ur[9], fl[9], fr[9];
   mean_bn(ql, qr);
   find_mhd_flux(M, ql, ul, fl);
   find_mhd_flux(M, qr, ur, fr);
-  double cfl = find_speed_fast(M, ql), cfr = find_speed_fast(M, qr);
-  double vl = ql[2], vr = qr[2];
-  double SL = fmn(fmn(vl, vr) - fmx(cfl, cfr), zero);
-  double SR = fmx(fmx(vl, vr) + fmx(cfl, cfr), zero);
-  for (int n = 0; n < 9; n++) fg[n] = (SR * fl[n] - SL * fr[n] + SR * SL * (ur[n] - ul[n])) / (SR - SL);
+  real cfl = find_speed_fast(M, ql), cfr = find_speed_fast(M, qr);
+  real vl = ql[2], vr = qr[2];
+  real SL = fmn(fmn(vl, vr) - fmx(cfl, cfr), zero);
+  real SR = fmx(fmx(vl, vr) + fmx(cfl, cfr), zero);
+  const RcpD rs(SR - SL);
+#pragma unroll
+  for (int n = 0; n < 9; n++) fg[n] = (SR * fl[n] - SL * fr[n] + SR * SL * (ur[n] - ul[n])) / rs;
 }
 
-__device__ __forceinline__ void hlld(const MPhys& M, double* ql, double* qr, double* fg) { /* :426 */
-  double entho = one / (M.gamma - one);
-  double A = half * (ql[3] + qr[3]);
-  double sgnm = copysign(1.0, A);
+__device__ __forceinline__ void hlld(const MPhys& M, real* ql, real* qr, real* fg) { /* :426 */
+  real entho = one / (M.gamma - one);
+  real A = half * (ql[3] + qr[3]);
+  real sgnm = rsign(1.0, A);
   ql[3] = A; qr[3] = A;
-  double rl = ql[0], Pl = ql[1], ul = ql[2], vl = ql[4], Bl = ql[5], wl = ql[6], Cl = ql[7];
-  double ecinl = half * (ul * ul + vl * vl + wl * wl) * rl;
-  double emagl = half * (A * A + Bl * Bl + Cl * Cl);
-  double etotl = Pl * entho + ecinl + emagl;
-  double Ptotl = Pl + emagl;
-  double vdotBl = ul * A + vl * Bl + wl * Cl;
-  double eintl = Pl * entho;
-  double rr = qr[0], Pr = qr[1], ur = qr[2], vr = qr[4], Br = qr[5], wr = qr[6], Cr = qr[7];
-  double ecinr = half * (ur * ur + vr * vr + wr * wr) * rr;
-  double emagr = half * (A * A + Br * Br + Cr * Cr);
-  double etotr = Pr * entho + ecinr + emagr;
-  double Ptotr = Pr + emagr;
-  double vdotBr = ur * A + vr * Br + wr * Cr;
-  double eintr = Pr * entho;
-  double cfastl = find_speed_fast(M, ql), cfastr = find_speed_fast(M, qr);
-  double SL = fmn(ul, ur) - fmx(cfastl, cfastr);
-  double SR = fmx(ul, ur) + fmx(cfastl, cfastr);
-  double rcl = rl * (ul - SL), rcr = rr * (SR - ur);
-  double ustar = (rcr * ur + rcl * ul + (Ptotl - Ptotr)) / (rcr + rcl);
-  double Ptotstar = (rcr * Ptotl + rcl * Ptotr + rcl * rcr * (ul - ur)) / (rcr + rcl);
+  real rl = ql[0], Pl = ql[1], ul = ql[2], vl = ql[4], Bl = ql[5], wl = ql[6], Cl = ql[7];
+  real ecinl = half * (ul * ul + vl * vl + wl * wl) * rl;
+  real emagl = half * (A * A + Bl * Bl + Cl * Cl);
+  real etotl = Pl * entho + ecinl + emagl;
+  real Ptotl = Pl + emagl;
+  real vdotBl = ul * A + vl * Bl + wl * Cl;
+  real eintl = Pl * entho;
+  real rr = qr[0], Pr = qr[1], ur = qr[2], vr = qr[4], Br = qr[5], wr = qr[6], Cr = qr[7];
+  real ecinr = half * (ur * ur + vr * vr + wr * wr) * rr;
+  real emagr = half * (A * A + Br * Br + Cr * Cr);
+  real etotr = Pr * entho + ecinr + emagr;
+  real Ptotr = Pr + emagr;
+  real vdotBr = ur * A + vr * Br + wr * Cr;
+  real eintr = Pr * entho;
+  real cfastl = find_speed_fast(M, ql), cfastr = find_speed_fast(M, qr);
+  real SL = fmn(ul, ur) - fmx(cfastl, cfastr);
+  real SR = fmx(ul, ur) + fmx(cfastl, cfastr);
+  real rcl = rl * (ul - SL), rcr = rr * (SR - ur);
+  const RcpD rrc(rcr + rcl);
+  real ustar = (rcr * ur + rcl * ul + (Ptotl - Ptotr)) / rrc;
+  real Ptotstar = (rcr * Ptotl + rcl * Ptotr + rcl * rcr * (ul - ur)) / rrc;
+  const RcpD rsl(SL - ustar), rsr(SR - ustar);
   /* left star region */
-  double rstarl = rl * (SL - ul) / (SL - ustar);
-  double estar = rl * (SL - ul) * (SL - ustar) - A * A;
-  double el = rl * (SL - ul) * (SL - ul) - A * A;
-  double eintstarl = eintl * (SL - ul) / (SL - ustar);
-  double vstarl, Bstarl, wstarl, Cstarl;
-  if (fabs(estar) < (double)1e-4f * (A * A)) /* `1e-4` is a default-real literal */ { vstarl = vl; Bstarl = Bl; wstarl = wl; Cstarl = Cl; }
+  real rstarl = rl * (SL - ul) / rsl;
+  real estar = rl * (SL - ul) * (SL - ustar) - A * A;
+  real el = rl * (SL - ul) * (SL - ul) - A * A;
+  real eintstarl = eintl * (SL - ul) / rsl;
+  real vstarl, Bstarl, wstarl, Cstarl;
+  if (rabs(estar) < (real)1e-4f * (A * A)) /* `1e-4` is a default-real literal */ { vstarl = vl; Bstarl = Bl; wstarl = wl; Cstarl = Cl; }
   else {
-    vstarl = vl - A * Bl * (ustar - ul) / estar;
-    Bstarl = Bl * el / estar;
-    wstarl = wl - A * Cl * (ustar - ul) / estar;
-    Cstarl = Cl * el / estar;
+    const RcpD re(estar);
+    vstarl = vl - A * Bl * (ustar - ul) / re;
+    Bstarl = Bl * el / re;
+    wstarl = wl - A * Cl * (ustar - ul) / re;
+    Cstarl = Cl * el / re;
   }
-  double vdotBstarl = ustar * A + vstarl * Bstarl + wstarl * Cstarl;
-  double etotstarl = ((SL - ul) * etotl - Ptotl * ul + Ptotstar * ustar + A * (vdotBl - vdotBstarl)) / (SL - ustar);
-  double sqrrstarl = sqrt(rstarl);
-  double calfvenl = fabs(A) / sqrrstarl;
-  double SAL = ustar - calfvenl;
+  real vdotBstarl = ustar * A + vstarl * Bstarl + wstarl * Cstarl;
+  real etotstarl = ((SL - ul) * etotl - Ptotl * ul + Ptotstar * ustar + A * (vdotBl - vdotBstarl)) / rsl;
+  real sqrrstarl = rsqrt64(rstarl);
+  real calfvenl = rabs(A) / sqrrstarl;
+  real SAL = ustar - calfvenl;
   /* right star region */
-  double rstarr = rr * (SR - ur) / (SR - ustar);
+  real rstarr = rr * (SR - ur) / rsr;
   estar = rr * (SR - ur) * (SR - ustar) - A * A;
-  double er = rr * (SR - ur) * (SR - ur) - A * A;
-  double eintstarr = eintr * (SR - ur) / (SR - ustar);
-  double vstarr, Bstarr, wstarr, Cstarr;
-  if (fabs(estar) < (double)1e-4f * (A * A)) /* `1e-4` is a default-real literal */ { vstarr = vr; Bstarr = Br; wstarr = wr; Cstarr = Cr; }
+  real er = rr * (SR - ur) * (SR - ur) - A * A;
+  real eintstarr = eintr * (SR - ur) / rsr;
+  real vstarr, Bstarr, wstarr, Cstarr;
+  if (rabs(estar) < (real)1e-4f * (A * A)) /* `1e-4` is a default-real literal */ { vstarr = vr; Bstarr = Br; wstarr = wr; Cstarr = Cr; }
   else {
-    vstarr = vr - A * Br * (ustar - ur) / estar;
-    Bstarr = Br * er / estar;
-    wstarr = wr - A * Cr * (ustar - ur) / estar;
-    Cstarr = Cr * er / estar;
+    const RcpD re(estar);
+    vstarr = vr - A * Br * (ustar - ur) / re;
+    Bstarr = Br * er / re;
+    wstarr = wr - A * Cr * (ustar - ur) / re;
+    Cstarr = Cr * er / re;
   }
-  double vdotBstarr = ustar * A + vstarr * Bstarr + wstarr * Cstarr;
-  double etotstarr = ((SR - ur) * etotr - Ptotr * ur + Ptotstar * ustar + A * (vdotBr - vdotBstarr)) / (SR - ustar);
-  double sqrrstarr = sqrt(rstarr);
-  double calfvenr = fabs(A) / sqrrstarr;
-  double SAR = ustar + calfvenr;
-  /* double star region */
-  double den = sqrrstarl + sqrrstarr;
-  double vstarstar = (sqrrstarl * vstarl + sqrrstarr * vstarr + sgnm * (Bstarr - Bstarl)) / den;
-  double wstarstar = (sqrrstarl * wstarl + sqrrstarr * wstarr + sgnm * (Cstarr - Cstarl)) / den;
-  double Bstarstar = (sqrrstarl * Bstarr + sqrrstarr * Bstarl + sgnm * sqrrstarl * sqrrstarr * (vstarr - vstarl)) / den;
-  double Cstarstar = (sqrrstarl * Cstarr + sqrrstarr * Cstarl + sgnm * sqrrstarl * sqrrstarr * (wstarr - wstarl)) / den;
-  double vdotBstarstar = ustar * A + vstarstar * Bstarstar + wstarstar * Cstarstar;
-  double etotstarstarl = etotstarl - sgnm * sqrrstarl * (vdotBstarl - vdotBstarstar);
-  double etotstarstarr = etotstarr + sgnm * sqrrstarr * (vdotBstarr - vdotBstarstar);
-  double ro, uo, vo, wo, Bo, Co, Ptoto, etoto, vdotBo, einto;
+  real vdotBstarr = ustar * A + vstarr * Bstarr + wstarr * Cstarr;
+  real etotstarr = ((SR - ur) * etotr - Ptotr * ur + Ptotstar * ustar + A * (vdotBr - vdotBstarr)) / rsr;
+  real sqrrstarr = rsqrt64(rstarr);
+  real calfvenr = rabs(A) / sqrrstarr;
+  real SAR = ustar + calfvenr;
+  /* real star region */
+  const RcpD den(sqrrstarl + sqrrstarr);
+  real vstarstar = (sqrrstarl * vstarl + sqrrstarr * vstarr + sgnm * (Bstarr - Bstarl)) / den;
+  real wstarstar = (sqrrstarl * wstarl + sqrrstarr * wstarr + sgnm * (Cstarr - Cstarl)) / den;
+  real Bstarstar = (sqrrstarl * Bstarr + sqrrstarr * Bstarl + sgnm * sqrrstarl * sqrrstarr * (vstarr - vstarl)) / den;
+  real Cstarstar = (sqrrstarl * Cstarr + sqrrstarr * Cstarl + sgnm * sqrrstarl * sqrrstarr * (wstarr - wstarl)) / den;
+  real vdotBstarstar = ustar * A + vstarstar * Bstarstar + wstarstar * Cstarstar;
+  real etotstarstarl = etotstarl - sgnm * sqrrstarl * (vdotBstarl - vdotBstarstar);
+  real etotstarstarr = etotstarr + sgnm * sqrrstarr * (vdotBstarr - vdotBstarstar);
+  real ro, uo, vo, wo, Bo, Co, Ptoto, etoto, vdotBo, einto;
   if (SL > 0.0) { ro = rl; uo = ul; vo = vl; wo = wl; Bo = Bl; Co = Cl; Ptoto = Ptotl; etoto = etotl; vdotBo = vdotBl; einto = eintl; }
   else if (SAL > 0.0) { ro = rstarl; uo = ustar; vo = vstarl; wo = wstarl; Bo = Bstarl; Co = Cstarl; Ptoto = Ptotstar; etoto = etotstarl; vdotBo = vdotBstarl; einto = eintstarl; }
   else if (ustar > 0.0) { ro = rstarl; uo = ustar; vo = vstarstar; wo = wstarstar; Bo = Bstarstar; Co = Cstarstar; Ptoto = Ptotstar; etoto = etotstarstarl; vdotBo = vdotBstarstar; einto = eintstarl; }
@@ -189,103 +198,183 @@ __device__ __forceinline__ void hlld(const MPhys& M, double* ql, double* qr, dou
   fg[8] = uo * einto;
 }
 
-__device__ __forceinline__ void hydro_acoustic(const MPhys& M, double* ql, double* qr, double* fg) { /* :1092 */
-  double smallp = M.smallr * (M.smallc * M.smallc);
+__device__ __forceinline__ void hydro_acoustic(const MPhys& M, real* ql, real* qr, real* fg) { /* :1092 */
+  real smallp = M.smallr * (M.smallc * M.smallc);
   mean_bn(ql, qr);
-  double rl = fmx(ql[0], M.smallr), rr = fmx(qr[0], M.smallr);
-  double pl = fmx(ql[1], smallp), pr = fmx(qr[1], smallp);
-  double ul = ql[2], ur = qr[2];
-  double cl = sqrt(M.gamma * pl / rl), cr = sqrt(M.gamma * pr / rr);
-  double wl = cl * rl, wr = cr * rr;
-  double pstar = ((wr * pl + wl * pr) + wl * wr * (ul - ur)) / (wl + wr);
-  double ustar = ((wr * ur + wl * ul) + (pl - pr)) / (wl + wr);
-  double sgnm = copysign(1.0, ustar);
-  double ro, uo, po, co;
+  real rl = fmx(ql[0], M.smallr), rr = fmx(qr[0], M.smallr);
+  real pl = fmx(ql[1], smallp), pr = fmx(qr[1], smallp);
+  real ul = ql[2], ur = qr[2];
+  real cl = rsqrt64(M.gamma * pl / rl), cr = rsqrt64(M.gamma * pr / rr);
+  real wl = cl * rl, wr = cr * rr;
+  real pstar = ((wr * pl + wl * pr) + wl * wr * (ul - ur)) / (wl + wr);
+  real ustar = ((wr * ur + wl * ul) + (pl - pr)) / (wl + wr);
+  real sgnm = rsign(1.0, ustar);
+  real ro, uo, po, co;
   if (sgnm == one) { ro = rl; uo = ul; po = pl; co = cl; } else { ro = rr; uo = ur; po = pr; co = cr; }
-  double rstar = ro + (pstar - po) / (co * co);
+  real rstar = ro + (pstar - po) / (co * co);
   rstar = fmx(rstar, M.smallr);
-  double cstar = sqrt(fabs(M.gamma * pstar / rstar));
+  real cstar = rsqrt64(rabs(M.gamma * pstar / rstar));
   cstar = fmx(cstar, M.smallc);
-  double spout = co - sgnm * uo;
-  double spin = cstar - sgnm * ustar;
-  double ushock = half * (spin + spout);
+  real spout = co - sgnm * uo;
+  real spin = cstar - sgnm * ustar;
+  real ushock = half * (spin + spout);
   ushock = fmx(ushock, -sgnm * ustar);
   if (pstar >= po) { spout = ushock; spin = spout; }
-  double qg[8];
+  real qg[8];
   if (spout < zero) { qg[0] = ro; qg[1] = po; qg[2] = uo; }
   else if (spin >= zero) { qg[0] = rstar; qg[1] = pstar; qg[2] = ustar; }
   else {
-    double frac = spout / (spout - spin);
+    real frac = spout / (spout - spin);
     qg[0] = frac * rstar + (one - frac) * ro;
     qg[1] = frac * pstar + (one - frac) * po;
     qg[2] = frac * ustar + (one - frac) * uo;
   }
   for (int n = 3; n < 8; n++) qg[n] = (sgnm == one) ? ql[n] : qr[n];
-  double ug[9];
+  real ug[9];
   find_mhd_flux(M, qg, ug, fg);
 }
 
-__device__ __forceinline__ void eigenvalues(const MPhys& M, double d, double vx, double pr, double bx, double by, double bz, double* lambda) { /* :1207 */
-  double btsq = by * by + bz * bz;
-  double vaxsq = bx * bx / d;
-  double vax = sqrt(vaxsq);
-  double asq = M.gamma * pr / d;
-  asq = fmx(asq, M.smallc * M.smallc);
-  double astarsq = asq + vaxsq + btsq / d;
-  double disc = sqrt(astarsq * astarsq - 4.0 * asq * vaxsq);
-  double cfsq = .5 * (astarsq + disc);
-  double cfast = sqrt(cfsq);
-  double cssq = .5 * (astarsq - disc);
+__device__ __forceinline__ void eigenvalues(const MPhys& M, real d, real vx, real pr, real bx, real by, real bz, real* lambda) { /* :1207 */
+  const RcpD rd(d);
+  real btsq = by * by + bz * bz;
+  real vaxsq = bx * bx / rd;
+  real vax = rsqrt64(vaxsq);
+  real asq = M.gamma * pr / rd;
+  asq = fmx(asq, real(M.smallc * M.smallc));
+  real astarsq = asq + vaxsq + btsq / rd;
+  real disc = rsqrt64(astarsq * astarsq - 4.0 * asq * vaxsq);
+  real cfsq = .5 * (astarsq + disc);
+  real cfast = rsqrt64(cfsq);
+  real cssq = .5 * (astarsq - disc);
   if (cssq <= 0.) cssq = 0.;
-  double cslow = sqrt(cssq);
+  real cslow = rsqrt64(cssq);
   lambda[0] = vx - cfast; lambda[1] = vx - vax; lambda[2] = vx - cslow; lambda[3] = vx;
   lambda[4] = vx + cslow; lambda[5] = vx + vax; lambda[6] = vx + cfast;
 }
 
-/* eigen_cons :1266.  rem[n][m] = rem(n+1,m+1), lem[n][m] = lem(n+1,m+1).  The literal `.5*sqrt(2.)` of the reference is a
- * default-real (single precision) expression.                                                                        */
-__device__ __forceinline__ void eigen_cons(const MPhys& M, double d, double vx, double vy, double vz, double h, double Bx, double by,
-                       double bz, double Xfac, double Yfac, double* lambda, double rem[7][7], double lem[7][7]) {
-  const double gamma = M.gamma;
-  const double hsq2 = 0.707106769084930419921875 /* (double)(0.5f*sqrtf(2.0f)) */;
-  double vsq = vx * vx + vy * vy + vz * vz;
-  double btsq = by * by + bz * bz;
-  double bt_starsq = (gamma - 1. - (gamma - 2.) * Yfac) * btsq;
-  double bt = sqrt(btsq);
-  double bt_star = sqrt(bt_starsq);
-  double vaxsq = Bx * Bx / d;
-  double vax = sqrt(vaxsq);
-  double hp = h - (vaxsq + btsq / d);
-  double twid_asq = ((gamma - 1.) * (hp - .5 * vsq) - (gamma - 2.) * Xfac);
-  twid_asq = fmx(twid_asq, M.smallc * M.smallc);
-  double q_starsq = twid_asq + (vaxsq + bt_starsq / d);
-  double disc = sqrt(q_starsq * q_starsq - 4.0 * twid_asq * vaxsq);
-  double cfsq = .5 * (q_starsq + disc);
-  double cfast = sqrt(cfsq);
-  double cssq = .5 * (q_starsq - disc);
+/* athena_roe :878 with eigen_cons :1266 written out in place.  Every entry of the eigenvector matrices keeps the reference's
+ * expression; only the ORDER in which independent entries are evaluated differs: the left eigenvectors are formed column
+ * by column and consumed at once by the wave strengths a(n) (:985-994), before the right eigenvectors are formed, which
+ * halves the live register set (the 7x7 matrices never coexist).  Quotients with a common divisor share one reciprocal
+ * (RcpD, real64.cuh; same bits).  fm[8] (the internal-energy flux) is never set by the reference on the Roe branch
+ * (godunov_utils.f90:1069-1088); it is only read when pressure_fix=.true., which is out of scope: 0 here. */
+__device__ __forceinline__ void athena_roe(const MPhys& M, real* ql, real* qr, real* fm, real zero_flux) {
+  real ul_[9], ur_[9], fl[9], fr[9];
+  real lambda[7], lambdal[7], lambdar[7], a[7];
+  mean_bn(ql, qr);
+  find_mhd_flux(M, ql, ul_, fl);
+  find_mhd_flux(M, qr, ur_, fr);
+  real dl = ql[0], dr = qr[0], pl = ql[1], pr = qr[1], vxl = ql[2], vxr = qr[2], vyl = ql[4], vyr = qr[4];
+  real byl = ql[5], byr = qr[5], vzl = ql[6], vzr = qr[6], bzl = ql[7], bzr = qr[7];
+  real bx = 0.5 * (ql[3] + qr[3]);
+  real el = ul_[1], er = ur_[1], mxl = ul_[2], mxr = ur_[2], myl = ul_[4], myr = ur_[4], mzl = ul_[6], mzr = ur_[6];
+  real pbl = half * (bx * bx + byl * byl + bzl * bzl);
+  real pbr = half * (bx * bx + byr * byr + bzr * bzr);
+  real hl = (el + pl + pbl) / dl;
+  real hr = (er + pr + pbr) / dr;
+  real sqrtdl = rsqrt64(dl), sqrtdr = rsqrt64(dr);
+  real droe = sqrtdl * sqrtdr;
+  const RcpD ssum(sqrtdl + sqrtdr);
+  real vx = (sqrtdl * vxl + sqrtdr * vxr) / ssum;
+  real vy = (sqrtdl * vyl + sqrtdr * vyr) / ssum;
+  real vz = (sqrtdl * vzl + sqrtdr * vzr) / ssum;
+  real by = (sqrtdr * byl + sqrtdl * byr) / ssum;
+  real bz = (sqrtdr * bzl + sqrtdl * bzr) / ssum;
+  real h = (sqrtdl * hl + sqrtdr * hr) / ssum;
+  const RcpD droe2(2 * droe);
+  real Xfac = ((by * by - byl * byr) + (bz * bz - bzl * bzr)) / droe2;
+  real Yfac = (dl + dr) / droe2;
+  real d = droe, Bx = bx;
+  /* ---- eigen_cons(droe,vxroe,vyroe,vzroe,hroe,bx,byroe,bzroe,Xfactor,Yfactor,...) :1266-1330 ---- */
+  const real gamma = M.gamma;
+  const real hsq2 = 0.707106769084930419921875 /* the default-real (single precision) expression .5*sqrt(2.) */;
+  const RcpD rd(d);
+  real vsq = vx * vx + vy * vy + vz * vz;
+  real btsq = by * by + bz * bz;
+  real bt_starsq = (gamma - 1. - (gamma - 2.) * Yfac) * btsq;
+  real bt = rsqrt64(btsq);
+  real bt_star = rsqrt64(bt_starsq);
+  real vaxsq = Bx * Bx / rd;
+  real vax = rsqrt64(vaxsq);
+  real hp = h - (vaxsq + btsq / rd);
+  real twid_asq = ((gamma - 1.) * (hp - .5 * vsq) - (gamma - 2.) * Xfac);
+  twid_asq = fmx(twid_asq, real(M.smallc * M.smallc));
+  real q_starsq = twid_asq + (vaxsq + bt_starsq / rd);
+  real disc = rsqrt64(q_starsq * q_starsq - 4.0 * twid_asq * vaxsq);
+  real cfsq = .5 * (q_starsq + disc);
+  real cfast = rsqrt64(cfsq);
+  real cssq = .5 * (q_starsq - disc);
   if (cssq <= 0.) cssq = 0.;
-  double cslow = sqrt(cssq);
-  double beta_y, beta_z, beta_ystar, beta_zstar;
+  real cslow = rsqrt64(cssq);
+  real beta_y, beta_z, beta_ystar, beta_zstar;
   if (bt == 0) { beta_y = hsq2; beta_z = hsq2; beta_ystar = hsq2; beta_zstar = hsq2; }
-  else { beta_y = by / bt; beta_z = bz / bt; beta_ystar = by / bt_star; beta_zstar = bz / bt_star; }
-  double beta_starsq = beta_ystar * beta_ystar + beta_zstar * beta_zstar;
-  double vbeta = vy * beta_ystar + vz * beta_zstar;
-  double alpha_f, alpha_s;
+  else {
+    const RcpD rbt(bt), rbts(bt_star);
+    beta_y = by / rbt; beta_z = bz / rbt; beta_ystar = by / rbts; beta_zstar = bz / rbts;
+  }
+  real beta_starsq = beta_ystar * beta_ystar + beta_zstar * beta_zstar;
+  real vbeta = vy * beta_ystar + vz * beta_zstar;
+  real alpha_f, alpha_s;
   if ((cfsq - cssq) == 0.) { alpha_f = 1.0; alpha_s = 0.0; }
   else if ((twid_asq - cssq) <= 0.) { alpha_f = 0.0; alpha_s = 1.0; }
   else if ((cfsq - twid_asq) <= 0.) { alpha_f = 1.0; alpha_s = 0.0; }
-  else { alpha_f = sqrt((twid_asq - cssq) / (cfsq - cssq)); alpha_s = sqrt((cfsq - twid_asq) / (cfsq - cssq)); }
-  double droot = sqrt(d);
-  double s = copysign(1.0, Bx);
-  double twid_a = sqrt(twid_asq);
-  double Qfast = s * cfast * alpha_f;
-  double Qslow = s * cslow * alpha_s;
-  double af_prime = twid_a * alpha_f / droot;
-  double as_prime = twid_a * alpha_s / droot;
-  double Afpbb = af_prime * bt_star * beta_starsq;
-  double Aspbb = as_prime * bt_star * beta_starsq;
+  else {
+    const RcpD rcc(cfsq - cssq);
+    alpha_f = rsqrt64((twid_asq - cssq) / rcc); alpha_s = rsqrt64((cfsq - twid_asq) / rcc);
+  }
+  real droot = rsqrt64(d);
+  const RcpD rdroot(droot);
+  real s = rsign(1.0, Bx);
+  real twid_a = rsqrt64(twid_asq);
+  real Qfast = s * cfast * alpha_f;
+  real Qslow = s * cslow * alpha_s;
+  real af_prime = twid_a * alpha_f / rdroot;
+  real as_prime = twid_a * alpha_s / rdroot;
+  real Afpbb = af_prime * bt_star * beta_starsq;
+  real Aspbb = as_prime * bt_star * beta_starsq;
   lambda[0] = vx - cfast; lambda[1] = vx - vax; lambda[2] = vx - cslow; lambda[3] = vx;
   lambda[4] = vx + cslow; lambda[5] = vx + vax; lambda[6] = vx + cfast;
+  /* ---- left eigenvectors :1390-1470, column by column, and the wave strengths a(n) :985-994 ---- */
+  {
+    real na = 0.5 / twid_asq;
+    real cff = na * alpha_f * cfast;
+    real css = na * alpha_s * cslow;
+    real Qfl = Qfast * na;
+    real Qsl = Qslow * na;
+    real af = na * af_prime * d;
+    real as = na * as_prime * d;
+    real Afpb = na * af_prime * bt_star;
+    real Aspb = na * as_prime * bt_star;
+    real alf = (gamma - 1.) * na * alpha_f;
+    real als = (gamma - 1.) * na * alpha_s;
+    const RcpD rbss(beta_starsq);
+    real Q_ystar = beta_ystar / rbss;
+    real Q_zstar = beta_zstar / rbss;
+    real vqstr = (vy * Q_ystar + vz * Q_zstar);
+    real norm = (gamma - 1.) * 2. * na;
+    const real du0 = dr - dl, du1 = mxr - mxl, du2 = myr - myl, du3 = mzr - mzl, du4 = er - el, du5 = byr - byl, du6 = bzr - bzl;
+#define WAVE(n, L0, L1, L2, L3, L4, L5, L6)                                                                  \
+  a[n] = 0.0; a[n] = a[n] + du0 * (L0); a[n] = a[n] + du1 * (L1); a[n] = a[n] + du2 * (L2);                  \
+  a[n] = a[n] + du3 * (L3); a[n] = a[n] + du4 * (L4); a[n] = a[n] + du5 * (L5); a[n] = a[n] + du6 * (L6);
+    const real lem61 = as * Q_ystar - alf * by, lem71 = as * Q_zstar - alf * bz;
+    WAVE(0, alf * (vsq - hp) + cff * (cfast + vx) - Qsl * vqstr - Aspb, -alf * vx - cff, -alf * vy + Qsl * Q_ystar, -alf * vz + Qsl * Q_zstar,
+         alf, lem61, lem71)
+    const real lem12 = 0.5 * (vy * beta_z - vz * beta_y), lem32 = -0.5 * beta_z, lem42 = 0.5 * beta_y;
+    const real lem62 = -0.5 * droot * beta_z * s, lem72 = 0.5 * droot * beta_y * s;
+    WAVE(1, lem12, real(0.), lem32, lem42, real(0.), lem62, lem72)
+    const real lem63 = -af * Q_ystar - als * by, lem73 = -af * Q_zstar - als * bz;
+    WAVE(2, als * (vsq - hp) + css * (cslow + vx) + Qfl * vqstr + Afpb, -als * vx - css, -als * vy - Qfl * Q_ystar, -als * vz - Qfl * Q_zstar,
+         als, lem63, lem73)
+    WAVE(3, 1. - norm * (.5 * vsq - (gamma - 2.) * Xfac / (gamma - 1.)), norm * vx, norm * vy, norm * vz, -norm, norm * by, norm * bz)
+    WAVE(4, als * (vsq - hp) + css * (cslow - vx) - Qfl * vqstr + Afpb, -als * vx + css, -als * vy + Qfl * Q_ystar, -als * vz + Qfl * Q_zstar,
+         als, lem63, lem73)
+    WAVE(5, -lem12, real(0.), -lem32, -lem42, real(0.), lem62, lem72)
+    WAVE(6, alf * (vsq - hp) + cff * (cfast - vx) + Qsl * vqstr - Aspb, -alf * vx + cff, -alf * vy - Qsl * Q_ystar, -alf * vz - Qsl * Q_zstar,
+         alf, lem61, lem71)
+#undef WAVE
+  }
+  /* ---- right eigenvectors :1332-1388 ---- */
+  real rem[7][7];
   rem[0][0] = alpha_f;
   rem[0][1] = alpha_f * (vx - cfast);
   rem[0][2] = alpha_f * vy + Qslow * beta_ystar;
@@ -297,8 +386,8 @@ __device__ __forceinline__ void eigen_cons(const MPhys& M, double d, double vx, 
   rem[1][2] = -beta_z;
   rem[1][3] = beta_y;
   rem[1][4] = -(vy * beta_z - vz * beta_y);
-  rem[1][5] = -s * beta_z / droot;
-  rem[1][6] = s * beta_y / droot;
+  rem[1][5] = -s * beta_z / rdroot;
+  rem[1][6] = s * beta_y / rdroot;
   rem[2][0] = alpha_s;
   rem[2][1] = alpha_s * (vx - cslow);
   rem[2][2] = alpha_s * vy - Qfast * beta_ystar;
@@ -329,114 +418,12 @@ __device__ __forceinline__ void eigen_cons(const MPhys& M, double d, double vx, 
   rem[6][4] = alpha_f * (hp + vx * cfast) - Qslow * vbeta + Aspbb;
   rem[6][5] = rem[0][5];
   rem[6][6] = rem[0][6];
-  /* left eigenvectors */
-  double na = 0.5 / twid_asq;
-  double cff = na * alpha_f * cfast;
-  double css = na * alpha_s * cslow;
-  Qfast = Qfast * na;
-  Qslow = Qslow * na;
-  double af = na * af_prime * d;
-  double as = na * as_prime * d;
-  double Afpb = na * af_prime * bt_star;
-  double Aspb = na * as_prime * bt_star;
-  alpha_f = (gamma - 1.) * na * alpha_f;
-  alpha_s = (gamma - 1.) * na * alpha_s;
-  double Q_ystar = beta_ystar / beta_starsq;
-  double Q_zstar = beta_zstar / beta_starsq;
-  double vqstr = (vy * Q_ystar + vz * Q_zstar);
-  double norm = (gamma - 1.) * 2. * na;
-  lem[0][0] = alpha_f * (vsq - hp) + cff * (cfast + vx) - Qslow * vqstr - Aspb;
-  lem[1][0] = -alpha_f * vx - cff;
-  lem[2][0] = -alpha_f * vy + Qslow * Q_ystar;
-  lem[3][0] = -alpha_f * vz + Qslow * Q_zstar;
-  lem[4][0] = alpha_f;
-  lem[5][0] = as * Q_ystar - alpha_f * by;
-  lem[6][0] = as * Q_zstar - alpha_f * bz;
-  lem[0][1] = 0.5 * (vy * beta_z - vz * beta_y);
-  lem[1][1] = 0.;
-  lem[2][1] = -0.5 * beta_z;
-  lem[3][1] = 0.5 * beta_y;
-  lem[4][1] = 0.;
-  lem[5][1] = -0.5 * droot * beta_z * s;
-  lem[6][1] = 0.5 * droot * beta_y * s;
-  lem[0][2] = alpha_s * (vsq - hp) + css * (cslow + vx) + Qfast * vqstr + Afpb;
-  lem[1][2] = -alpha_s * vx - css;
-  lem[2][2] = -alpha_s * vy - Qfast * Q_ystar;
-  lem[3][2] = -alpha_s * vz - Qfast * Q_zstar;
-  lem[4][2] = alpha_s;
-  lem[5][2] = -af * Q_ystar - alpha_s * by;
-  lem[6][2] = -af * Q_zstar - alpha_s * bz;
-  lem[0][3] = 1. - norm * (.5 * vsq - (gamma - 2.) * Xfac / (gamma - 1.));
-  lem[1][3] = norm * vx;
-  lem[2][3] = norm * vy;
-  lem[3][3] = norm * vz;
-  lem[4][3] = -norm;
-  lem[5][3] = norm * by;
-  lem[6][3] = norm * bz;
-  lem[0][4] = alpha_s * (vsq - hp) + css * (cslow - vx) - Qfast * vqstr + Afpb;
-  lem[1][4] = -alpha_s * vx + css;
-  lem[2][4] = -alpha_s * vy + Qfast * Q_ystar;
-  lem[3][4] = -alpha_s * vz + Qfast * Q_zstar;
-  lem[4][4] = alpha_s;
-  lem[5][4] = lem[5][2];
-  lem[6][4] = lem[6][2];
-  lem[0][5] = -lem[0][1];
-  lem[1][5] = 0.;
-  lem[2][5] = -lem[2][1];
-  lem[3][5] = -lem[3][1];
-  lem[4][5] = 0.;
-  lem[5][5] = lem[5][1];
-  lem[6][5] = lem[6][1];
-  lem[0][6] = alpha_f * (vsq - hp) + cff * (cfast - vx) + Qslow * vqstr - Aspb;
-  lem[1][6] = -alpha_f * vx + cff;
-  lem[2][6] = -alpha_f * vy - Qslow * Q_ystar;
-  lem[3][6] = -alpha_f * vz - Qslow * Q_zstar;
-  lem[4][6] = alpha_f;
-  lem[5][6] = lem[5][0];
-  lem[6][6] = lem[6][0];
-}
-
-/* athena_roe :878.  fg[8] (the internal-energy flux) is never set by the reference on the Roe branch
- * (godunov_utils.f90:1069-1088); it is only read when pressure_fix=.true., which is out of scope: 0 here. */
-__device__ __forceinline__ void athena_roe(const MPhys& M, double* ql, double* qr, double* fm, double zero_flux) {
-  double ul_[9], ur_[9], fl[9], fr[9];
-  double lem[7][7], rem[7][7], lambda[7], lambdal[7], lambdar[7], a[7];
-  mean_bn(ql, qr);
-  find_mhd_flux(M, ql, ul_, fl);
-  find_mhd_flux(M, qr, ur_, fr);
-  double dl = ql[0], dr = qr[0], pl = ql[1], pr = qr[1], vxl = ql[2], vxr = qr[2], vyl = ql[4], vyr = qr[4];
-  double byl = ql[5], byr = qr[5], vzl = ql[6], vzr = qr[6], bzl = ql[7], bzr = qr[7];
-  double bx = 0.5 * (ql[3] + qr[3]);
-  double el = ul_[1], er = ur_[1], mxl = ul_[2], mxr = ur_[2], myl = ul_[4], myr = ur_[4], mzl = ul_[6], mzr = ur_[6];
-  double pbl = half * (bx * bx + byl * byl + bzl * bzl);
-  double pbr = half * (bx * bx + byr * byr + bzr * bzr);
-  double hl = (el + pl + pbl) / dl;
-  double hr = (er + pr + pbr) / dr;
-  double sqrtdl = sqrt(dl), sqrtdr = sqrt(dr);
-  double droe = sqrtdl * sqrtdr;
-  double vxroe = (sqrtdl * vxl + sqrtdr * vxr) / (sqrtdl + sqrtdr);
-  double vyroe = (sqrtdl * vyl + sqrtdr * vyr) / (sqrtdl + sqrtdr);
-  double vzroe = (sqrtdl * vzl + sqrtdr * vzr) / (sqrtdl + sqrtdr);
-  double byroe = (sqrtdr * byl + sqrtdl * byr) / (sqrtdl + sqrtdr);
-  double bzroe = (sqrtdr * bzl + sqrtdl * bzr) / (sqrtdl + sqrtdr);
-  double hroe = (sqrtdl * hl + sqrtdr * hr) / (sqrtdl + sqrtdr);
-  double Xfactor = ((byroe * byroe - byl * byr) + (bzroe * bzroe - bzl * bzr)) / (2 * droe);
-  double Yfactor = (dl + dr) / (2 * droe);
-  eigen_cons(M, droe, vxroe, vyroe, vzroe, hroe, bx, byroe, bzroe, Xfactor, Yfactor, lambda, rem, lem);
   eigenvalues(M, dl, vxl, pl, bx, byl, bzl, lambdal);
   eigenvalues(M, dr, vxr, pr, bx, byr, bzr, lambdar);
-  for (int n = 0; n < 7; n++) {
-    a[n] = 0.0;
-    a[n] = a[n] + (dr - dl) * lem[0][n];
-    a[n] = a[n] + (mxr - mxl) * lem[1][n];
-    a[n] = a[n] + (myr - myl) * lem[2][n];
-    a[n] = a[n] + (mzr - mzl) * lem[3][n];
-    a[n] = a[n] + (er - el) * lem[4][n];
-    a[n] = a[n] + (byr - byl) * lem[5][n];
-    a[n] = a[n] + (bzr - bzl) * lem[6][n];
-  }
-  int llf = 0;
-  double dim = dl, mxm = mxl, mym = myl, mzm = mzl, eim = el, bym = byl, bzm = bzl;
+  /* ---- intermediate states: fall back to LLF when one of them is unphysical :996-1033 ---- */
+  bool llf = false;
+  real dim = dl, mxm = mxl, mym = myl, mzm = mzl, eim = el, bym = byl, bzm = bzl;
+#pragma unroll
   for (int n = 0; n < 7; n++) {
     dim = dim + a[n] * rem[n][0];
     mxm = mxm + a[n] * rem[n][1];
@@ -445,29 +432,33 @@ __device__ __forceinline__ void athena_roe(const MPhys& M, double* ql, double* q
     eim = eim + a[n] * rem[n][4];
     bym = bym + a[n] * rem[n][5];
     bzm = bzm + a[n] * rem[n][6];
-    double etm = eim - 0.5 * (mxm * mxm + mym * mym + mzm * mzm) / dim - 0.5 * (bx * bx + bym * bym + bzm * bzm);
-    if (dim <= zero || etm <= zero) llf = 1;
+    real etm = eim - 0.5 * (mxm * mxm + mym * mym + mzm * mzm) / dim - 0.5 * (bx * bx + bym * bym + bzm * bzm);
+    if (dim <= zero || etm <= zero) llf = true;
   }
   if (llf) {
-    double vl = find_speed_info(M, ql), vr = find_speed_info(M, qr);
-    double vm = fmx(vl, vr);
+    real vl = find_speed_info(M, ql), vr = find_speed_info(M, qr);
+    real vm = fmx(vl, vr);
+#pragma unroll
     for (int n = 0; n < 9; n++) {
-      double fmean = half * (fr[n] + fl[n]) * zero_flux;
-      double udiff = half * (ur_[n] - ul_[n]);
+      real fmean = half * (fr[n] + fl[n]) * zero_flux;
+      real udiff = half * (ur_[n] - ul_[n]);
       fm[n] = fmean - vm * udiff;
     }
     return;
   }
+#pragma unroll
   for (int n = 0; n < 7; n += 2) {
-    double l1 = fmn(lambdal[n], lambda[n]);
-    double l2 = fmx(lambdar[n], lambda[n]);
+    real l1 = fmn(lambdal[n], lambda[n]);
+    real l2 = fmx(lambdar[n], lambda[n]);
     if (l1 < zero && l2 > zero) lambda[n] = (lambda[n] * (l2 + l1) - two * l2 * l1) / (l2 - l1);
   }
+#pragma unroll
   for (int n = 0; n < 9; n++) { fl[n] = fl[n] * zero_flux; fr[n] = fr[n] * zero_flux; }
-  double fluxd = fl[0] + fr[0], fluxe = fl[1] + fr[1], fluxmx = fl[2] + fr[2], fluxmy = fl[4] + fr[4];
-  double fluxby = fl[5] + fr[5], fluxmz = fl[6] + fr[6], fluxbz = fl[7] + fr[7];
+  real fluxd = fl[0] + fr[0], fluxe = fl[1] + fr[1], fluxmx = fl[2] + fr[2], fluxmy = fl[4] + fr[4];
+  real fluxby = fl[5] + fr[5], fluxmz = fl[6] + fr[6], fluxbz = fl[7] + fr[7];
+#pragma unroll
   for (int n = 0; n < 7; n++) {
-    double coef = fabs(lambda[n]) * a[n];
+    real coef = rabs(lambda[n]) * a[n];
     fluxd = fluxd - coef * rem[n][0];
     fluxe = fluxe - coef * rem[n][4];
     fluxmx = fluxmx - coef * rem[n][1];
@@ -485,103 +476,105 @@ __device__ __forceinline__ void athena_roe(const MPhys& M, double* ql, double* q
  * permuted: s[0]=rho s[1]=P s[2]=v_p1 s[3]=v_p2 s[4]=v_or s[5]=B_p1 s[6]=B_p2 s[7]=B_or  (B_p1, B_p2 already replaced
  * by the pair means :1517-1528).
  * ====================================================================================================== */
-__device__ __forceinline__ double fast_xy(const MPhys& M, const double* s, int y) {
-  double qt[8];
+__device__ __forceinline__ real fast_xy(const MPhys& M, const real* s, int y) {
+  real qt[8];
   qt[0] = s[0]; qt[1] = s[1]; qt[6] = s[4]; qt[7] = s[7];
   if (!y) { qt[2] = s[2]; qt[3] = s[5]; qt[4] = s[3]; qt[5] = s[6]; }
   else { qt[2] = s[3]; qt[3] = s[6]; qt[4] = s[2]; qt[5] = s[5]; }
   return find_speed_fast(M, qt);
 }
-__device__ __forceinline__ double alfven_xy(const double* s, int y) {
-  double qt[8];
+__device__ __forceinline__ real alfven_xy(const real* s, int y) {
+  real qt[8];
   qt[0] = s[0]; qt[3] = y ? s[6] : s[5];
   return find_speed_alfven(qt);
 }
 
 template <int R2D>
-__device__ __forceinline__ double emf_edge(const MPhys& M, const double* qLL, const double* qRL, const double* qLR, const double* qRR) {
-  double ELL = qLL[2] * qLL[6] - qLL[3] * qLL[5];
-  double ERL = qRL[2] * qRL[6] - qRL[3] * qRL[5];
-  double ELR = qLR[2] * qLR[6] - qLR[3] * qLR[5];
-  double ERR = qRR[2] * qRR[6] - qRR[3] * qRR[5];
+__device__ __forceinline__ real emf_edge(const MPhys& M, const real* qLL, const real* qRL, const real* qLR, const real* qRR) {
+  real ELL = qLL[2] * qLL[6] - qLL[3] * qLL[5];
+  real ERL = qRL[2] * qRL[6] - qRL[3] * qRL[5];
+  real ELR = qLR[2] * qLR[6] - qLR[3] * qLR[5];
+  real ERR = qRR[2] * qRR[6] - qRR[3] * qRR[5];
   constexpr int r2d = R2D;
   if (r2d == MHD2D_HLLD) { /* :1567-1735 */
-    double rLL = qLL[0], pLL = qLL[1], uLL = qLL[2], vLL = qLL[3], ALL = qLL[5], BLL = qLL[6], CLL = qLL[7];
-    double rLR = qLR[0], pLR = qLR[1], uLR = qLR[2], vLR = qLR[3], ALR = qLR[5], BLR = qLR[6], CLR = qLR[7];
-    double rRL = qRL[0], pRL = qRL[1], uRL = qRL[2], vRL = qRL[3], ARL = qRL[5], BRL = qRL[6], CRL = qRL[7];
-    double rRR = qRR[0], pRR = qRR[1], uRR = qRR[2], vRR = qRR[3], ARR = qRR[5], BRR = qRR[6], CRR = qRR[7];
-    double cfastLLx = fast_xy(M, qLL, 0), cfastLRx = fast_xy(M, qLR, 0), cfastRLx = fast_xy(M, qRL, 0), cfastRRx = fast_xy(M, qRR, 0);
-    double cfastLLy = fast_xy(M, qLL, 1), cfastLRy = fast_xy(M, qLR, 1), cfastRLy = fast_xy(M, qRL, 1), cfastRRy = fast_xy(M, qRR, 1);
-    double cmx = fmx4(cfastLLx, cfastLRx, cfastRLx, cfastRRx), cmy = fmx4(cfastLLy, cfastLRy, cfastRLy, cfastRRy);
-    double SL = fmn4(uLL, uLR, uRL, uRR) - cmx;
-    double SR = fmx4(uLL, uLR, uRL, uRR) + cmx;
-    double SB = fmn4(vLL, vLR, vRL, vRR) - cmy;
-    double ST = fmx4(vLL, vLR, vRL, vRR) + cmy;
+    real rLL = qLL[0], pLL = qLL[1], uLL = qLL[2], vLL = qLL[3], ALL = qLL[5], BLL = qLL[6], CLL = qLL[7];
+    real rLR = qLR[0], pLR = qLR[1], uLR = qLR[2], vLR = qLR[3], ALR = qLR[5], BLR = qLR[6], CLR = qLR[7];
+    real rRL = qRL[0], pRL = qRL[1], uRL = qRL[2], vRL = qRL[3], ARL = qRL[5], BRL = qRL[6], CRL = qRL[7];
+    real rRR = qRR[0], pRR = qRR[1], uRR = qRR[2], vRR = qRR[3], ARR = qRR[5], BRR = qRR[6], CRR = qRR[7];
+    real cfastLLx = fast_xy(M, qLL, 0), cfastLRx = fast_xy(M, qLR, 0), cfastRLx = fast_xy(M, qRL, 0), cfastRRx = fast_xy(M, qRR, 0);
+    real cfastLLy = fast_xy(M, qLL, 1), cfastLRy = fast_xy(M, qLR, 1), cfastRLy = fast_xy(M, qRL, 1), cfastRRy = fast_xy(M, qRR, 1);
+    real cmx = fmx4(cfastLLx, cfastLRx, cfastRLx, cfastRRx), cmy = fmx4(cfastLLy, cfastLRy, cfastRLy, cfastRRy);
+    real SL = fmn4(uLL, uLR, uRL, uRR) - cmx;
+    real SR = fmx4(uLL, uLR, uRL, uRR) + cmx;
+    real SB = fmn4(vLL, vLR, vRL, vRR) - cmy;
+    real ST = fmx4(vLL, vLR, vRL, vRR) + cmy;
     ELL = uLL * BLL - vLL * ALL;
     ELR = uLR * BLR - vLR * ALR;
     ERL = uRL * BRL - vRL * ARL;
     ERR = uRR * BRR - vRR * ARR;
-    double PtotLL = pLL + half * (ALL * ALL + BLL * BLL + CLL * CLL);
-    double PtotLR = pLR + half * (ALR * ALR + BLR * BLR + CLR * CLR);
-    double PtotRL = pRL + half * (ARL * ARL + BRL * BRL + CRL * CRL);
-    double PtotRR = pRR + half * (ARR * ARR + BRR * BRR + CRR * CRR);
-    double rcLLx = rLL * (uLL - SL), rcRLx = rRL * (SR - uRL);
-    double rcLRx = rLR * (uLR - SL), rcRRx = rRR * (SR - uRR);
-    double rcLLy = rLL * (vLL - SB), rcLRy = rLR * (ST - vLR);
-    double rcRLy = rRL * (vRL - SB), rcRRy = rRR * (ST - vRR);
-    double ustar = (rcLLx * uLL + rcLRx * uLR + rcRLx * uRL + rcRRx * uRR + (PtotLL - PtotRL + PtotLR - PtotRR)) / (rcLLx + rcLRx + rcRLx + rcRRx);
-    double vstar = (rcLLy * vLL + rcLRy * vLR + rcRLy * vRL + rcRRy * vRR + (PtotLL - PtotLR + PtotRL - PtotRR)) / (rcLLy + rcLRy + rcRLy + rcRRy);
-    double rstarLLx = rLL * (SL - uLL) / (SL - ustar), BstarLL = BLL * (SL - uLL) / (SL - ustar);
-    double rstarLLy = rLL * (SB - vLL) / (SB - vstar), AstarLL = ALL * (SB - vLL) / (SB - vstar);
-    double rstarLL = rLL * (SL - uLL) / (SL - ustar) * (SB - vLL) / (SB - vstar);
-    double EstarLLx = ustar * BstarLL - vLL * ALL;
-    double EstarLLy = uLL * BLL - vstar * AstarLL;
-    double EstarLL = ustar * BstarLL - vstar * AstarLL;
-    double rstarLRx = rLR * (SL - uLR) / (SL - ustar), BstarLR = BLR * (SL - uLR) / (SL - ustar);
-    double rstarLRy = rLR * (ST - vLR) / (ST - vstar), AstarLR = ALR * (ST - vLR) / (ST - vstar);
-    double rstarLR = rLR * (SL - uLR) / (SL - ustar) * (ST - vLR) / (ST - vstar);
-    double EstarLRx = ustar * BstarLR - vLR * ALR;
-    double EstarLRy = uLR * BLR - vstar * AstarLR;
-    double EstarLR = ustar * BstarLR - vstar * AstarLR;
-    double rstarRLx = rRL * (SR - uRL) / (SR - ustar), BstarRL = BRL * (SR - uRL) / (SR - ustar);
-    double rstarRLy = rRL * (SB - vRL) / (SB - vstar), AstarRL = ARL * (SB - vRL) / (SB - vstar);
-    double rstarRL = rRL * (SR - uRL) / (SR - ustar) * (SB - vRL) / (SB - vstar);
-    double EstarRLx = ustar * BstarRL - vRL * ARL;
-    double EstarRLy = uRL * BRL - vstar * AstarRL;
-    double EstarRL = ustar * BstarRL - vstar * AstarRL;
-    double rstarRRx = rRR * (SR - uRR) / (SR - ustar), BstarRR = BRR * (SR - uRR) / (SR - ustar);
-    double rstarRRy = rRR * (ST - vRR) / (ST - vstar), AstarRR = ARR * (ST - vRR) / (ST - vstar);
-    double rstarRR = rRR * (SR - uRR) / (SR - ustar) * (ST - vRR) / (ST - vstar);
-    double EstarRRx = ustar * BstarRR - vRR * ARR;
-    double EstarRRy = uRR * BRR - vstar * AstarRR;
-    double EstarRR = ustar * BstarRR - vstar * AstarRR;
-    double sc = M.smallc;
-    double calfvenL = fmx(fmx4(fabs(ALR) / sqrt(rstarLRx), fabs(AstarLR) / sqrt(rstarLR), fabs(ALL) / sqrt(rstarLLx), fabs(AstarLL) / sqrt(rstarLL)), sc);
-    double calfvenR = fmx(fmx4(fabs(ARR) / sqrt(rstarRRx), fabs(AstarRR) / sqrt(rstarRR), fabs(ARL) / sqrt(rstarRLx), fabs(AstarRL) / sqrt(rstarRL)), sc);
-    double calfvenB = fmx(fmx4(fabs(BLL) / sqrt(rstarLLy), fabs(BstarLL) / sqrt(rstarLL), fabs(BRL) / sqrt(rstarRLy), fabs(BstarRL) / sqrt(rstarRL)), sc);
-    double calfvenT = fmx(fmx4(fabs(BLR) / sqrt(rstarLRy), fabs(BstarLR) / sqrt(rstarLR), fabs(BRR) / sqrt(rstarRRy), fabs(BstarRR) / sqrt(rstarRR)), sc);
-    double SAL = fmn(ustar - calfvenL, zero), SAR = fmx(ustar + calfvenR, zero);
-    double SAB = fmn(vstar - calfvenB, zero), SAT = fmx(vstar + calfvenT, zero);
-    double AstarT = (SAR * AstarRR - SAL * AstarLR) / (SAR - SAL), AstarB = (SAR * AstarRL - SAL * AstarLL) / (SAR - SAL);
-    double BstarR = (SAT * BstarRR - SAB * BstarRL) / (SAT - SAB), BstarL = (SAT * BstarLR - SAB * BstarLL) / (SAT - SAB);
-    double E;
+    real PtotLL = pLL + half * (ALL * ALL + BLL * BLL + CLL * CLL);
+    real PtotLR = pLR + half * (ALR * ALR + BLR * BLR + CLR * CLR);
+    real PtotRL = pRL + half * (ARL * ARL + BRL * BRL + CRL * CRL);
+    real PtotRR = pRR + half * (ARR * ARR + BRR * BRR + CRR * CRR);
+    real rcLLx = rLL * (uLL - SL), rcRLx = rRL * (SR - uRL);
+    real rcLRx = rLR * (uLR - SL), rcRRx = rRR * (SR - uRR);
+    real rcLLy = rLL * (vLL - SB), rcLRy = rLR * (ST - vLR);
+    real rcRLy = rRL * (vRL - SB), rcRRy = rRR * (ST - vRR);
+    real ustar = (rcLLx * uLL + rcLRx * uLR + rcRLx * uRL + rcRRx * uRR + (PtotLL - PtotRL + PtotLR - PtotRR)) / (rcLLx + rcLRx + rcRLx + rcRRx);
+    real vstar = (rcLLy * vLL + rcLRy * vLR + rcRLy * vRL + rcRRy * vRR + (PtotLL - PtotLR + PtotRL - PtotRR)) / (rcLLy + rcLRy + rcRLy + rcRRy);
+    const RcpD dSL(SL - ustar), dSR(SR - ustar), dSB(SB - vstar), dST(ST - vstar);
+    real rstarLLx = rLL * (SL - uLL) / dSL, BstarLL = BLL * (SL - uLL) / dSL;
+    real rstarLLy = rLL * (SB - vLL) / dSB, AstarLL = ALL * (SB - vLL) / dSB;
+    real rstarLL = rLL * (SL - uLL) / dSL * (SB - vLL) / dSB;
+    real EstarLLx = ustar * BstarLL - vLL * ALL;
+    real EstarLLy = uLL * BLL - vstar * AstarLL;
+    real EstarLL = ustar * BstarLL - vstar * AstarLL;
+    real rstarLRx = rLR * (SL - uLR) / dSL, BstarLR = BLR * (SL - uLR) / dSL;
+    real rstarLRy = rLR * (ST - vLR) / dST, AstarLR = ALR * (ST - vLR) / dST;
+    real rstarLR = rLR * (SL - uLR) / dSL * (ST - vLR) / dST;
+    real EstarLRx = ustar * BstarLR - vLR * ALR;
+    real EstarLRy = uLR * BLR - vstar * AstarLR;
+    real EstarLR = ustar * BstarLR - vstar * AstarLR;
+    real rstarRLx = rRL * (SR - uRL) / dSR, BstarRL = BRL * (SR - uRL) / dSR;
+    real rstarRLy = rRL * (SB - vRL) / dSB, AstarRL = ARL * (SB - vRL) / dSB;
+    real rstarRL = rRL * (SR - uRL) / dSR * (SB - vRL) / dSB;
+    real EstarRLx = ustar * BstarRL - vRL * ARL;
+    real EstarRLy = uRL * BRL - vstar * AstarRL;
+    real EstarRL = ustar * BstarRL - vstar * AstarRL;
+    real rstarRRx = rRR * (SR - uRR) / dSR, BstarRR = BRR * (SR - uRR) / dSR;
+    real rstarRRy = rRR * (ST - vRR) / dST, AstarRR = ARR * (ST - vRR) / dST;
+    real rstarRR = rRR * (SR - uRR) / dSR * (ST - vRR) / dST;
+    real EstarRRx = ustar * BstarRR - vRR * ARR;
+    real EstarRRy = uRR * BRR - vstar * AstarRR;
+    real EstarRR = ustar * BstarRR - vstar * AstarRR;
+    real sc = M.smallc;
+    real calfvenL = fmx(fmx4(rabs(ALR) / rsqrt64(rstarLRx), rabs(AstarLR) / rsqrt64(rstarLR), rabs(ALL) / rsqrt64(rstarLLx), rabs(AstarLL) / rsqrt64(rstarLL)), sc);
+    real calfvenR = fmx(fmx4(rabs(ARR) / rsqrt64(rstarRRx), rabs(AstarRR) / rsqrt64(rstarRR), rabs(ARL) / rsqrt64(rstarRLx), rabs(AstarRL) / rsqrt64(rstarRL)), sc);
+    real calfvenB = fmx(fmx4(rabs(BLL) / rsqrt64(rstarLLy), rabs(BstarLL) / rsqrt64(rstarLL), rabs(BRL) / rsqrt64(rstarRLy), rabs(BstarRL) / rsqrt64(rstarRL)), sc);
+    real calfvenT = fmx(fmx4(rabs(BLR) / rsqrt64(rstarLRy), rabs(BstarLR) / rsqrt64(rstarLR), rabs(BRR) / rsqrt64(rstarRRy), rabs(BstarRR) / rsqrt64(rstarRR)), sc);
+    real SAL = fmn(ustar - calfvenL, zero), SAR = fmx(ustar + calfvenR, zero);
+    real SAB = fmn(vstar - calfvenB, zero), SAT = fmx(vstar + calfvenT, zero);
+    const RcpD dA(SAR - SAL), dB(SAT - SAB);
+    real AstarT = (SAR * AstarRR - SAL * AstarLR) / dA, AstarB = (SAR * AstarRL - SAL * AstarLL) / dA;
+    real BstarR = (SAT * BstarRR - SAB * BstarRL) / dB, BstarL = (SAT * BstarLR - SAB * BstarLL) / dB;
+    real E;
     if (SB > 0.0) {
       if (SL > 0.0) E = ELL;
       else if (SR < 0.0) E = ERL;
-      else E = (SAR * EstarLLx - SAL * EstarRLx + SAR * SAL * (BRL - BLL)) / (SAR - SAL);
+      else E = (SAR * EstarLLx - SAL * EstarRLx + SAR * SAL * (BRL - BLL)) / dA;
     } else if (ST < 0.0) {
       if (SL > 0.0) E = ELR;
       else if (SR < 0.0) E = ERR;
-      else E = (SAR * EstarLRx - SAL * EstarRRx + SAR * SAL * (BRR - BLR)) / (SAR - SAL);
-    } else if (SL > 0.0) E = (SAT * EstarLLy - SAB * EstarLRy - SAT * SAB * (ALR - ALL)) / (SAT - SAB);
-    else if (SR < 0.0) E = (SAT * EstarRLy - SAB * EstarRRy - SAT * SAB * (ARR - ARL)) / (SAT - SAB);
+      else E = (SAR * EstarLRx - SAL * EstarRRx + SAR * SAL * (BRR - BLR)) / dA;
+    } else if (SL > 0.0) E = (SAT * EstarLLy - SAB * EstarLRy - SAT * SAB * (ALR - ALL)) / dB;
+    else if (SR < 0.0) E = (SAT * EstarRLy - SAB * EstarRRy - SAT * SAB * (ARR - ARL)) / dB;
     else
-      E = (SAL * SAB * EstarRR - SAL * SAT * EstarRL - SAR * SAB * EstarLR + SAR * SAT * EstarLL) / (SAR - SAL) / (SAT - SAB) -
-          SAT * SAB / (SAT - SAB) * (AstarT - AstarB) + SAR * SAL / (SAR - SAL) * (BstarR - BstarL);
+      E = (SAL * SAB * EstarRR - SAL * SAT * EstarRL - SAR * SAB * EstarLR + SAR * SAT * EstarLL) / dA / dB -
+          SAT * SAB / dB * (AstarT - AstarB) + SAR * SAL / dA * (BstarR - BstarL);
     return E;
   }
   if (r2d == MHD2D_HLL || r2d == MHD2D_HLLA) { /* :1737-1850 */
-    double cLLx, cLRx, cRLx, cRRx, cLLy, cLRy, cRLy, cRRy;
+    real cLLx, cLRx, cRLx, cRRx, cLLy, cLRy, cRLy, cRRy;
     if (r2d == MHD2D_HLL) {
       cLLx = fast_xy(M, qLL, 0); cLRx = fast_xy(M, qLR, 0); cRLx = fast_xy(M, qRL, 0); cRRx = fast_xy(M, qRR, 0);
       cLLy = fast_xy(M, qLL, 1); cLRy = fast_xy(M, qLR, 1); cRLy = fast_xy(M, qRL, 1); cRRy = fast_xy(M, qRR, 1);
@@ -589,16 +582,16 @@ __device__ __forceinline__ double emf_edge(const MPhys& M, const double* qLL, co
       cLLx = alfven_xy(qLL, 0); cLRx = alfven_xy(qLR, 0); cRLx = alfven_xy(qRL, 0); cRRx = alfven_xy(qRR, 0);
       cLLy = alfven_xy(qLL, 1); cLRy = alfven_xy(qLR, 1); cRLy = alfven_xy(qRL, 1); cRRy = alfven_xy(qRR, 1);
     }
-    double SL = fmn(fmn4(qLL[2], qLR[2], qRL[2], qRR[2]) - fmx4(cLLx, cLRx, cRLx, cRRx), zero);
-    double SR = fmx(fmx4(qLL[2], qLR[2], qRL[2], qRR[2]) + fmx4(cLLx, cLRx, cRLx, cRRx), zero);
-    double SB = fmn(fmn4(qLL[3], qLR[3], qRL[3], qRR[3]) - fmx4(cLLy, cLRy, cRLy, cRRy), zero);
-    double ST = fmx(fmx4(qLL[3], qLR[3], qRL[3], qRR[3]) + fmx4(cLLy, cLRy, cRLy, cRRy), zero);
+    real SL = fmn(fmn4(qLL[2], qLR[2], qRL[2], qRR[2]) - fmx4(cLLx, cLRx, cRLx, cRRx), zero);
+    real SR = fmx(fmx4(qLL[2], qLR[2], qRL[2], qRR[2]) + fmx4(cLLx, cLRx, cRLx, cRRx), zero);
+    real SB = fmn(fmn4(qLL[3], qLR[3], qRL[3], qRR[3]) - fmx4(cLLy, cLRy, cRLy, cRRy), zero);
+    real ST = fmx(fmx4(qLL[3], qLR[3], qRL[3], qRR[3]) + fmx4(cLLy, cLRy, cRLy, cRRy), zero);
     return (SL * SB * ERR - SL * ST * ERL - SR * SB * ELR + SR * ST * ELL) / (SR - SL) / (ST - SB) -
            ST * SB / (ST - SB) * (qRR[5] - qLL[5]) + SR * SL / (SR - SL) * (qRR[6] - qLL[6]);
   }
   /* llf / roe / upwind: two 1-D problems on pair-averaged states :1852-1925 */
-  double E = forth * (ELL + ERL + ELR + ERR);
-  double ql[8], qr[8], fmean_x[9], fmean_y[9];
+  real E = forth * (ELL + ERL + ELR + ERR);
+  real ql[8], qr[8], fmean_x[9], fmean_y[9];
   const int mapx[8] = {0, 1, 2, 5, 3, 6, 4, 7}; /* qleft(1..8) <- s(1,2,3,6,4,7,5,8) */
   const int mapy[8] = {0, 1, 3, 6, 2, 5, 4, 7}; /* qleft(1..8) <- s(1,2,4,7,3,6,5,8) */
   for (int n = 0; n < 8; n++) {
@@ -621,7 +614,7 @@ __device__ __forceinline__ double emf_edge(const MPhys& M, const double* qLL, co
 
 // 1-D solver dispatch of cmpflxm (mhd/umuscl.f90:1411-1437), allow_switch_solver=.false.
 template <int R1D>
-__device__ __forceinline__ void riemann1d(const MPhys& M, double* ql, double* qr, double* fg) {
+__device__ __forceinline__ void riemann1d(const MPhys& M, real* ql, real* qr, real* fg) {
   if (R1D == MHD_ROE) athena_roe(M, ql, qr, fg, 1.0);
   else if (R1D == MHD_LLF || R1D == MHD_UPWIND) lax_friedrich(M, ql, qr, fg, 1.0);   // CASE (4) also calls lax_friedrich
   else if (R1D == MHD_HLL) hll(M, ql, qr, fg);
@@ -630,39 +623,40 @@ __device__ __forceinline__ void riemann1d(const MPhys& M, double* ql, double* qr
 }
 
 // minmod / moncen limiter in the algebraic form of the MHD build (mhd/umuscl.f90:2367-2376)
-__device__ __forceinline__ double slope_mm(double st, double ql, double qc, double qr) {
-  const double dlft = st * (qc - ql);
-  const double drgt = st * (qr - qc);
-  const double dcen = half * (dlft + drgt) / st;
-  const double dsgn = copysign(1.0, dcen);
-  double dlim = fmn(fabs(dlft), fabs(drgt));
+__device__ __forceinline__ real slope_mm(real st, real ql, real qc, real qr) {
+  const real dlft = st * (qc - ql);
+  const real drgt = st * (qr - qc);
+  const real dcen = half * (dlft + drgt) * real(1.0 / st.v);   // st is 1 or 2: x/st == x*(1/st) exactly
+  const real dsgn = rsign(1.0, dcen);
+  real dlim = fmn(rabs(dlft), rabs(drgt));
   if ((dlft * drgt) <= zero) dlim = zero;
-  return dsgn * fmn(dlim, fabs(dcen));
+  return dsgn * fmn(dlim, rabs(dcen));
 }
 
 // cmpdt for one cell (mhd/godunov_utils.f90:5-111, no gravity); uu[11] is destroyed like in the reference
-__device__ __forceinline__ double mhd_cmpdt_cell(const MPhys& M, double* uu, double dx) {
-  uu[0] = fmx(uu[0], M.smallr);
-  const double rho = uu[0];
-  for (int d = 1; d <= 3; d++) uu[d] = uu[d] / rho;
-  double B2 = zero;
+__device__ __forceinline__ real mhd_cmpdt_cell(const MPhys& M, real* uu, real dx) {
+  uu[0] = fmx(uu[0], real(M.smallr));
+  const real rho = uu[0];
+  const RcpD rrho(rho);
+  for (int d = 1; d <= 3; d++) uu[d] = uu[d] / rrho;
+  real B2 = zero;
   for (int d = 1; d <= 3; d++) {
-    const double Bc = half * (uu[4 + d] + uu[7 + d]);
+    const real Bc = half * (uu[4 + d] + uu[7 + d]);
     B2 = B2 + Bc * Bc;
     uu[4] = uu[4] - half * uu[0] * (uu[d] * uu[d]) - half * (Bc * Bc);
   }
   uu[4] = fmx((M.gamma - one) * uu[4], M.smallp);
-  const double a2 = M.gamma * uu[4] / uu[0];
-  double ctot = zero;
+  const real a2 = M.gamma * uu[4] / rrho;
+  real ctot = zero;
   for (int d = 1; d <= 3; d++) {
-    const double cc = half * (B2 / rho + a2);
-    const double BN = half * (uu[4 + d] + uu[7 + d]);
-    const double cf = sqrt(cc + sqrt(cc * cc - a2 * (BN * BN) / rho));
-    ctot = ctot + fabs(uu[d]) + cf;
+    const real cc = half * (B2 / rrho + a2);
+    const real BN = half * (uu[4 + d] + uu[7 + d]);
+    const real cf = rsqrt64(cc + rsqrt64(cc * cc - a2 * (BN * BN) / rrho));
+    ctot = ctot + rabs(uu[d]) + cf;
   }
-  double r = zero * dx / (ctot * ctot);
+  real r = zero * dx / (ctot * ctot);
   r = fmx(r, 0.0001);
-  return dx / ctot * (sqrt(one + two * M.courant_factor * r) - one) / r;
+  return dx / ctot * (rsqrt64(one + two * M.courant_factor * r) - one) / r;
 }
 
 #undef zero

@@ -1,10 +1,23 @@
 // pass 4 of the MHD sweep (1-D Riemann problems): one instantiation per solver and slope mode
+#include <cstdlib>
 #include "mhd_dense.cuh"
 namespace rgpu {
+// MINB = resident CTAs per SM the register allocation is bounded for (2: up to 255 registers, 3: 168, 4: 128).
+// Measured on B200 (profiles/r1_mhd_*): see DESIGN.md; RGPU_MHD_MINB overrides the default.
+static int minb_choice(int r1d) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("RGPU_MHD_MINB"); env = e ? atoi(e) : 0; }
+  if (env >= 2 && env <= 4) return env;
+  return r1d == MHD_ROE ? 4 : 2;
+}
 template <int R1D, bool SL>
 static cudaError_t go(const MhdArgs& a, cudaStream_t st) {
   const int nt = 128;
-  mhd_flux_kernel<R1D, SL><<<(unsigned)((a.nc + nt - 1) / nt), nt, 0, st>>>(a);
+  const unsigned nb = (unsigned)((a.nc + nt - 1) / nt);
+  const int mb = minb_choice(R1D);
+  if (mb == 4) mhd_flux_kernel<R1D, SL, 4><<<nb, nt, 0, st>>>(a);
+  else if (mb == 3) mhd_flux_kernel<R1D, SL, 3><<<nb, nt, 0, st>>>(a);
+  else mhd_flux_kernel<R1D, SL, 2><<<nb, nt, 0, st>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_mhd_flux(const MhdArgs& a, int r1d, bool sl, cudaStream_t st) {

@@ -31,11 +31,18 @@ def coarse_dims_for_ranks(ndim, ncpu):
 
 
 def build_uniform_tree(ndim, levelmax, nvar=None, coarse=(1, 1, 1), myid=1, ncpu=1, order="creation", seed=1,
-                       boxlen=1.0):
+                       boxlen=1.0, mhd=False, xbound=None):
     """Returns an AmrCommons with the tree of rank `myid` (1-based).  order: 'creation' (the order in which the
-    reference's refine pass creates octs: cell position outermost, amr/refine_utils.f90), 'lattice' or 'random'."""
-    nvar = nvar or ndim + 2
+    reference's refine pass creates octs: cell position outermost, amr/refine_utils.f90), 'lattice' or 'random'.
+    xbound=(bound_type_min, bound_type_max) (single rank only; 1 reflexive, 2 zero gradient): the run has
+    &BOUNDARY_PARAMS ibound_min=-1,+1 like namelist/tube_mhd.nml:17-22, i.e. a 3x1x1 coarse grid whose outer
+    cells are boundary cells (icoarse_min=icoarse_max=1) carrying one layer of boundary octs per level."""
+    nvar = nvar or (8 if mhd else ndim + 2)
     nx, ny, nz = coarse
+    if xbound is not None:
+        if ncpu != 1 or tuple(coarse) != (1, 1, 1):
+            raise ValueError("xbound needs a single rank and a single domain coarse cell")
+        nx = 3
     nc = np.array([nx, ny, nz], dtype=np.int64)
     if ncpu > 1 and nx * ny * nz != ncpu:
         raise ValueError("one coarse cell per rank is required")
@@ -58,6 +65,8 @@ def build_uniform_tree(ndim, levelmax, nvar=None, coarse=(1, 1, 1), myid=1, ncpu
     n1 = 1 << (L - 1)
     if ncpu == 1:
         rng = [np.arange(ext[d]) for d in range(3)]
+        if xbound is not None:
+            rng[0] = np.arange(n1 - 1, 2 * n1 + 1)       # the domain [n1, 2 n1) plus one boundary oct on each side
     else:
         rng = []
         for d in range(3):
@@ -113,8 +122,10 @@ def build_uniform_tree(ndim, levelmax, nvar=None, coarse=(1, 1, 1), myid=1, ncpu
         ok = ks[i] == k
         return np.where(ok, igrid0[l] + srt[i], 0)
 
-    a = AmrCommons(ndim, nvar, ncoarse, ngridmax, nx, ny, nz, (0, nx - 1), (0, ny - 1), (0, nz - 1), nlevelmax=L,
-                   boxlen=boxlen, myid=myid, ncpu=ncpu)
+    a = AmrCommons(ndim, nvar, ncoarse, ngridmax, nx, ny, nz, (1, 1) if xbound is not None else (0, nx - 1), (0, ny - 1),
+                   (0, nz - 1), nlevelmax=L, boxlen=boxlen, myid=myid, ncpu=ncpu, mhd=mhd)
+    if xbound is not None:
+        a.boundary_type = [(0 if t == 1 else 10) + k + 1 for k, t in enumerate(xbound)]    # hydro/read_hydro_params.f90:316-420
     # icoarse_min/max: the reference keeps nx_loc = icoarse_max-icoarse_min+1 = 1 for boxlen scaling unless the
     # user box spans several coarse cells; here the physical box spans the whole coarse grid in x
     for l in range(1, L + 1):
@@ -152,8 +163,11 @@ def build_uniform_tree(ndim, levelmax, nvar=None, coarse=(1, 1, 1), myid=1, ncpu
         cc = p >> (l - 1)                                # coarse cell containing the oct
         owner = cc[:, 0] + nx * (cc[:, 1] + ny * cc[:, 2])
         mine = owner == r0 if ncpu > 1 else np.ones(len(p), dtype=bool)
-        a.active[l] = ig[mine]
         a.boundary[l] = []
+        if xbound is not None:
+            mine = cc[:, 0] == 1
+            a.boundary[l] = [ig[cc[:, 0] == 0], ig[cc[:, 0] == 2]]
+        a.active[l] = ig[mine]
         if ncpu > 1:
             kk = key(p, l)
             rec, emi = [], []
