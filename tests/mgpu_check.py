@@ -35,6 +35,27 @@ def state_fn(coarse):
     return fn
 
 
+def mhd_state_fn(coarse):
+    """Smooth periodic MHD state; B_x depends on (y,z) only etc.: divergence-free and the two copies of a face agree."""
+    def fn(x, y, z):
+        tw = 2 * np.pi
+        xs, ys, zs = x / coarse[0], y / coarse[1], z / coarse[2]
+        rho = 1 + 0.2 * np.sin(tw * xs) * np.cos(tw * ys)
+        vx, vy, vz = 0.3 * np.sin(tw * ys), 0.2 * np.cos(tw * zs), 0.1 * np.sin(tw * xs)
+        p = 1 + 0.1 * np.cos(tw * zs) * np.sin(tw * (xs + ys))
+        bx = 0.5 + 0.2 * np.sin(tw * ys) * np.cos(tw * zs)
+        by = 0.3 + 0.2 * np.sin(tw * zs + 1.0) * np.cos(tw * xs)
+        bz = 0.2 + 0.2 * np.cos(tw * xs) * np.sin(tw * ys + 0.3)
+        u = np.zeros((11, len(x)))
+        u[0] = rho
+        u[1], u[2], u[3] = rho * vx, rho * vy, rho * vz
+        u[5], u[6], u[7] = bx, by, bz
+        u[8], u[9], u[10] = bx, by, bz
+        u[4] = p * 1.5 + 0.5 * rho * (vx ** 2 + vy ** 2 + vz ** 2) + 0.5 * (bx ** 2 + by ** 2 + bz ** 2)
+        return u
+    return fn
+
+
 def keys_and_state(a, l):
     """(global cell key, state) of the active cells."""
     ig = a.active[l].astype(np.int64)
@@ -57,9 +78,18 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     coarse = coarse_dims_for_ranks(3, world)
-    a = build_uniform_tree(3, level, coarse=coarse, myid=rank + 1, ncpu=world, order="random", seed=rank + 5)
-    a.riemann, a.slope_type, a.courant_factor = riemann, 1, 0.8
-    fill_state(a, level, state_fn(coarse))
+    mhd = riemann.startswith("mhd:")          # e.g. mhd:hlld:hlld = MHD build, riemann='hlld', riemann2d='hlld'
+
+    def configure(t):
+        if mhd:
+            _, t.riemann, t.riemann2d = riemann.split(":")
+            t.gamma = 5.0 / 3.0
+        else:
+            t.riemann = riemann
+        t.slope_type, t.courant_factor = 1, 0.8
+        fill_state(t, level, mhd_state_fn(coarse) if mhd else state_fn(coarse))
+    a = build_uniform_tree(3, level, coarse=coarse, myid=rank + 1, ncpu=world, order="random", seed=rank + 5, mhd=mhd)
+    configure(a)
     h = HydroGPU(a, device=lr)
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
@@ -89,9 +119,8 @@ def main():
         uu = torch.cat(us, dim=1).cpu().numpy()
         order = np.argsort(kk)
         kk, uu = kk[order], uu[:, order]
-        g = build_uniform_tree(3, level, coarse=coarse, myid=1, ncpu=1, order="creation")
-        g.riemann, g.slope_type, g.courant_factor = riemann, 1, 0.8
-        fill_state(g, level, state_fn(coarse))
+        g = build_uniform_tree(3, level, coarse=coarse, myid=1, ncpu=1, order="creation", mhd=mhd)
+        configure(g)
         hg = HydroGPU(g, device=lr)
         hg.bind_level(level)
         hg.upload_state(level)
