@@ -52,6 +52,7 @@ typedef struct rgpu_params {
   int riemann;         /* RGPU_RIEMANN_*                                       */
   int pressure_fix;    /* must be 0 (tmp/divu/enew path not built)            */
   double gamma, smallr, smallc, slope_theta, difmag, courant_factor;
+                       /* difmag>0 (cmpdivu/consup, hydro/uplmde.f90:702,769): oct-batch kernel only, i.e. after rgpu_set_amr(1,..) */
   double boxlen;
   int nx, ny, nz;      /* coarse grid incl. boundary cells (amr_parameters)   */
   int icoarse_min, icoarse_max, jcoarse_min, jcoarse_max, kcoarse_min, kcoarse_max;

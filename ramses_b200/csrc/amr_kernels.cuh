@@ -122,12 +122,14 @@ struct AmrSweepArgs {
   Phys P;
   double dt, dx, inv_dx;
   int dx_pow2, interpol_type;
+  double difmag;          // hydro_parameters.f90:81
 };
 
 constexpr int AMR_TPO = 64;   // threads per oct
 constexpr int AMR_OPB = 1;    // octs per block (26 KB of static shared memory per oct in 3-D)
 
-template <int NDIM, int RIEMANN>
+// DIF: artificial diffusion difmag>0 (cmpdivu hydro/uplmde.f90:702 + consup :769, called from unsplit hydro/umuscl.f90:160-168)
+template <int NDIM, int RIEMANN, bool DIF>
 __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const AmrSweepArgs a) {
   constexpr int NV = NDIM + 2, T = 1 << NDIM, TW = 2 * NDIM;
   constexpr int N3 = (NDIM == 1) ? 3 : (NDIM == 2 ? 9 : 27);
@@ -145,6 +147,8 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
     double qm[NDIM][NV][NTR], qp[NDIM][NV][NTR];
     double flux[NDIM][NV][NF];
     int nfc[27], gnb[27], ng[8];
+    double uc[DIF ? NV : 1][DIF ? NP : 1];   // conservative patch (consup needs uin next to the primitives)
+    double div[DIF ? 27 : 1];                // velocity divergence on the 3^ndim vertex lattice if1:if2 x jf1:jf2 x kf1:kf2
   };
   __shared__ Sm sm_[AMR_OPB];
   const int grp = threadIdx.x / AMR_TPO, tl = threadIdx.x % AMR_TPO;
@@ -247,6 +251,10 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
       double u[NV], q[NV];
 #pragma unroll
       for (int n = 0; n < NV; n++) u[n] = s.q[n][pc];
+      if (DIF) {
+#pragma unroll
+        for (int n = 0; n < NV; n++) s.uc[DIF ? n : 0][DIF ? pc : 0] = u[n];
+      }
       const double r = fmax(u[0], P.smallr);
       const double oneoverrho = rcp_rn(r);
       q[0] = r;
@@ -264,6 +272,29 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
       for (int n = 0; n < NV; n++) s.q[n][pc] = q[n];
     }
   __syncthreads();
+  if (DIF && live) {   // cmpdivu :702-764 on the vertices (i,j,k) = low corner of patch cell (i,j,k), i,j,k = 1..3
+    constexpr int VJ = HY ? 3 : 1, VK = HZ ? 3 : 1;
+    double hp = 1.0;
+    for (int d = 1; d < NDIM; d++) hp = hp * 0.5;       // half**(ndim-1)
+    const double factorx = hp / a.dx, factory = factorx, factorz = factorx;
+    for (int e = tl; e < 3 * VJ * VK; e += AMR_TPO) {
+      const int i = 1 + e % 3, j = HY ? 1 + (e / 3) % 3 : 1, k = HZ ? 1 + e / 9 : 1;
+      auto Q = [&](int ii, int jj, int kk, int n) -> double { return s.q[n][(ii + 1) + 6 * ((HY ? jj + 1 : 0) + PJ * (HZ ? kk + 1 : 0))]; };
+      double ux = 0.0, vy = 0.0, wz = 0.0;
+      ux = ux + factorx * (Q(i, j, k, 1) - Q(i - 1, j, k, 1));
+      if (NDIM > 1) {
+        ux = ux + factorx * (Q(i, j - 1, k, 1) - Q(i - 1, j - 1, k, 1));
+        vy = vy + factory * (Q(i, j, k, 2 % NV) - Q(i, j - 1, k, 2 % NV) + Q(i - 1, j, k, 2 % NV) - Q(i - 1, j - 1, k, 2 % NV));
+      }
+      if (NDIM > 2) {
+        ux = ux + factorx * (Q(i, j, k - 1, 1) - Q(i - 1, j, k - 1, 1) + Q(i, j - 1, k - 1, 1) - Q(i - 1, j - 1, k - 1, 1));
+        vy = vy + factory * (Q(i, j, k - 1, 2 % NV) - Q(i, j - 1, k - 1, 2 % NV) + Q(i - 1, j, k - 1, 2 % NV) - Q(i - 1, j - 1, k - 1, 2 % NV));
+        wz = wz + factorz * (Q(i, j, k, 3 % NV) - Q(i, j, k - 1, 3 % NV) + Q(i, j - 1, k, 3 % NV) - Q(i, j - 1, k - 1, 3 % NV) +
+                             Q(i - 1, j, k, 3 % NV) - Q(i - 1, j, k - 1, 3 % NV) + Q(i - 1, j - 1, k, 3 % NV) - Q(i - 1, j - 1, k - 1, 3 % NV));
+      }
+      s.div[DIF ? e : 0] = ux + vy + wz;
+    }
+  }
   // ---- uslope + trace on cells 0..3 (hydro/umuscl.f90:970, :176/:305/:483) ----
   const double dtdx = a.dt / a.dx;
   if (live)
@@ -379,9 +410,31 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
       const int pR = (c3[0] + 1) + 6 * ((HY ? c3[1] + 1 : 0) + PJ * (HZ ? c3[2] + 1 : 0));
       const int pL = (cl[0] + 1) + 6 * ((HY ? cl[1] + 1 : 0) + PJ * (HZ ? cl[2] + 1 : 0));
       const bool masked = s.ok[pL] || s.ok[pR];
+      double div1 = 0.0;
+      if (DIF) {   // consup :769-869: vertices of the face, difmag*min(0, mean divergence)
+        constexpr int VJ = HY ? 3 : 1;
+        auto DV = [&](int ii, int jj, int kk) -> double { return s.div[DIF ? (ii - 1) + 3 * ((HY ? jj - 1 : 0) + VJ * (HZ ? kk - 1 : 0)) : 0]; };
+        double hp = 1.0;
+        for (int dd = 1; dd < NDIM; dd++) hp = hp * 0.5;
+        const double factor = hp;
+        const int i = c3[0], j = c3[1], k = c3[2];
+        if (d == 0) {
+          div1 = factor * DV(i, j, k);
+          if (NDIM > 1) div1 = div1 + factor * DV(i, j + 1, k);
+          if (NDIM > 2) div1 = div1 + factor * (DV(i, j, k + 1) + DV(i, j + 1, k + 1));
+        } else if (d == 1) {
+          div1 = 0.0;
+          div1 = div1 + factor * (DV(i, j, k) + DV(i + 1, j, k));
+          if (NDIM > 2) div1 = div1 + factor * (DV(i, j, k + 1) + DV(i + 1, j, k + 1));
+        } else {
+          div1 = factor * (DV(i, j, k) + DV(i + 1, j, k) + DV(i, j + 1, k) + DV(i + 1, j + 1, k));
+        }
+        div1 = a.difmag * ((div1 < 0.0) ? div1 : 0.0);
+      }
 #pragma unroll
       for (int n = 0; n < NV; n++) {
         double v = a.dx_pow2 ? (fl[n] * a.dt) * a.inv_dx : div_rn(fl[n] * a.dt, a.dx, a.inv_dx);
+        if (DIF) v = v + a.dt * div1 * (s.uc[DIF ? n : 0][DIF ? pR : 0] - s.uc[DIF ? n : 0][DIF ? pL : 0]);
         if (masked) v = 0.0;
         s.flux[d][n][f] = v;
       }
@@ -569,7 +622,8 @@ __global__ void amr_courant_kernel(const double* __restrict__ u, const AmrTree t
 template <int NDIM, int RIEMANN>
 cudaError_t launch_amr_godfine(const AmrSweepArgs& a, cudaStream_t st) {
   const int nb = (a.nact + AMR_OPB - 1) / AMR_OPB;
-  amr_godfine_kernel<NDIM, RIEMANN><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);
+  if (a.difmag > 0.0) amr_godfine_kernel<NDIM, RIEMANN, true><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);
+  else amr_godfine_kernel<NDIM, RIEMANN, false><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);
   return cudaGetLastError();
 }
 

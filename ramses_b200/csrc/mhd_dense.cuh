@@ -357,33 +357,12 @@ __device__ __forceinline__ void edge_state(const MPhys& P, const TC& t, double* 
 }
 
 // ---------------------------------------------------------------------------------------------------- pass 4
-// cmpflxm for the low face of cell c in direction DIR; left state from cell cl (the cell below), right state from c
-template <int DIR, int R1D, bool SL>
-__device__ __forceinline__ void face_flux(const MhdArgs& a, const double* TR, long long c, long long cl, double dt) {
-  const long long nc = a.nc;
-  TC tl, tr;
-  load_tc<SL>(TR, nc, cl, tl);
-  load_tc<SL>(TR, nc, c, tr);
-  double sm[8], sp[8];
-  face_state<DIR, +1>(a.P, tl, sm);   // qm of the left cell
-  face_state<DIR, -1>(a.P, tr, sp);   // qp of the right cell
-  // ln,lt1,lt2,bn,bt1,bt2 (0-based variable numbers) :51,:84,:117
-  constexpr int ln = DIR == 0 ? 1 : DIR == 1 ? 2 : 3, lt1 = DIR == 0 ? 2 : 1, lt2 = DIR == 2 ? 2 : 3;
-  constexpr int bn = DIR == 0 ? 5 : DIR == 1 ? 6 : 7, bt1 = DIR == 0 ? 6 : 5, bt2 = DIR == 2 ? 6 : 7;
-  real ql[8], qr[8], fg[9];
-  const double bn_mean = 0.5 * (sm[bn] + sp[bn]);
-  ql[0] = sm[0]; ql[1] = sm[4]; ql[2] = sm[ln]; ql[3] = bn_mean; ql[4] = sm[lt1]; ql[5] = sm[bt1]; ql[6] = sm[lt2]; ql[7] = sm[bt2];
-  qr[0] = sp[0]; qr[1] = sp[4]; qr[2] = sp[ln]; qr[3] = bn_mean; qr[4] = sp[lt1]; qr[5] = sp[bt1]; qr[6] = sp[lt2]; qr[7] = sp[bt2];
-  riemann1d<R1D>(a.P, ql, qr, fg);
-  double f[5];   // (rho, mx, my, mz, E); the induction fluxes are dropped (flux(:,6:8)=0, godunov_fine.f90:778-879)
-  f[0] = fg[0].v; f[4] = fg[1].v; f[ln] = fg[2].v; f[lt1] = fg[4].v; f[lt2] = fg[6].v;
-  double* F = a.W + (MW_F + 5 * DIR) * nc;
-#pragma unroll
-  const double rdx = rcp_rn(a.dx);
-#pragma unroll
-  for (int n = 0; n < 5; n++) F[n * nc + c] = div_rn(f[n] * dt, a.dx, rdx);   // flux = fx*dt/dx :83
-}
+__device__ __forceinline__ double sel3(int dir, double x, double y, double z) { return dir == 0 ? x : (dir == 1 ? y : z); }
 
+// cmpflxm for the three low faces of a cell.  For Roe the direction loop is a real loop (`#pragma unroll 1`): the solver is
+// inlined ONCE, so that the kernel (2700 instructions per solve) stays inside the instruction cache -- with three
+// inlined copies the top stall reason was `no_instruction` (profiles/r1_ncu_full_mhd_flux_roe.txt).  The variable
+// permutations ln,lt1,lt2,bn,bt1,bt2 of the three cmpflxm calls (mhd/umuscl.f90:51,84,117) become selects.
 template <int R1D, bool SL, int MINB>
 __global__ void __launch_bounds__(128, MINB) mhd_flux_kernel(const MhdArgs a) {
   const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -395,30 +374,83 @@ __global__ void __launch_bounds__(128, MINB) mhd_flux_kernel(const MhdArgs a) {
              oz = in_range(p.z, g.oz0, g.oz1, g.ncz, g.wrapz, 0, 0);
   const bool ex = in_range(p.x, g.ox0, g.ox1, g.ncx, g.wrapx, 0, 1), ey = in_range(p.y, g.oy0, g.oy1, g.ncy, g.wrapy, 0, 1),
              ez = in_range(p.z, g.oz0, g.oz1, g.ncz, g.wrapz, 0, 1);
-  const double* TR = a.W + MW_TR * a.nc;
+  const long long nc = a.nc;
+  const double* TR = a.W + MW_TR * nc;
   const double dt = *a.dt_dev;
-  if (ex && oy && oz) face_flux<0, R1D, SL>(a, TR, c, cidx(g, wm(p.x, g.ncx, g.wrapx), p.y, p.z), dt);
-  if (ox && ey && oz) face_flux<1, R1D, SL>(a, TR, c, cidx(g, p.x, wm(p.y, g.ncy, g.wrapy), p.z), dt);
-  if (ox && oy && ez) face_flux<2, R1D, SL>(a, TR, c, cidx(g, p.x, p.y, wm(p.z, g.ncz, g.wrapz)), dt);
+  const double rdx = rcp_rn(a.dx);
+  TC tr;
+  load_tc<SL>(TR, nc, c, tr);
+  auto one_face = [&](const int dir) {
+    const bool need = dir == 0 ? (ex && oy && oz) : dir == 1 ? (ox && ey && oz) : (ox && oy && ez);
+    if (!need) return;
+    const long long cl = dir == 0 ? cidx(g, wm(p.x, g.ncx, g.wrapx), p.y, p.z)
+                       : dir == 1 ? cidx(g, p.x, wm(p.y, g.ncy, g.wrapy), p.z) : cidx(g, p.x, p.y, wm(p.z, g.ncz, g.wrapz));
+    TC tl;
+    load_tc<SL>(TR, nc, cl, tl);
+    double sm[8], sp[8];   // qm of the cell below, qp of this cell
+    if (dir == 0) { face_state<0, +1>(a.P, tl, sm); face_state<0, -1>(a.P, tr, sp); }
+    else if (dir == 1) { face_state<1, +1>(a.P, tl, sm); face_state<1, -1>(a.P, tr, sp); }
+    else { face_state<2, +1>(a.P, tl, sm); face_state<2, -1>(a.P, tr, sp); }
+    real ql[8], qr[8], fg[9];
+    const double bnl = sel3(dir, sm[5], sm[6], sm[7]), bnr = sel3(dir, sp[5], sp[6], sp[7]);
+    const double bn_mean = 0.5 * (bnl + bnr);
+    ql[0] = sm[0]; ql[1] = sm[4]; ql[2] = sel3(dir, sm[1], sm[2], sm[3]); ql[3] = bn_mean;
+    ql[4] = sel3(dir, sm[2], sm[1], sm[1]); ql[5] = sel3(dir, sm[6], sm[5], sm[5]);
+    ql[6] = sel3(dir, sm[3], sm[3], sm[2]); ql[7] = sel3(dir, sm[7], sm[7], sm[6]);
+    qr[0] = sp[0]; qr[1] = sp[4]; qr[2] = sel3(dir, sp[1], sp[2], sp[3]); qr[3] = bn_mean;
+    qr[4] = sel3(dir, sp[2], sp[1], sp[1]); qr[5] = sel3(dir, sp[6], sp[5], sp[5]);
+    qr[6] = sel3(dir, sp[3], sp[3], sp[2]); qr[7] = sel3(dir, sp[7], sp[7], sp[6]);
+    riemann1d<R1D>(a.P, ql, qr, fg);
+    // (rho, mx, my, mz, E); the induction fluxes are dropped (flux(:,6:8)=0, godunov_fine.f90:778-879)
+    double f[5];
+    f[0] = fg[0].v; f[4] = fg[1].v;
+    f[1] = sel3(dir, fg[2].v, fg[4].v, fg[4].v);
+    f[2] = sel3(dir, fg[4].v, fg[2].v, fg[6].v);
+    f[3] = sel3(dir, fg[6].v, fg[6].v, fg[2].v);
+    double* F = a.W + (MW_F + 5 * dir) * nc;
+#pragma unroll
+    for (int n = 0; n < 5; n++) F[n * nc + c] = div_rn(f[n] * dt, a.dx, rdx);   // flux = fx*dt/dx :83
+  };
+  if (R1D == MHD_ROE) {   // measured: one copy wins for Roe (10.8 -> 10.5 ms/step), three copies for the small solvers
+#pragma unroll 1
+    for (int dir = 0; dir < 3; dir++) one_face(dir);
+  } else {
+    one_face(0); one_face(1); one_face(2);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------- pass 5
-// cmp_mag_flx at the low edge along DIR of cell c.  c1 = neighbour below along the first transverse axis, c2 = along the
-// second, c12 = diagonal.  Argument order and variable permutation of the three calls in mag_unsplit :147-240.
+// cmp_mag_flx at the three low edges of a cell, one inlined copy of the 2-D solver (see pass 4).  The four corner states
+// arrive in cell-variable order (r,u,v,w,p,A,B,C) under the dummy-argument names of cmp_mag_flx; the variable permutation
+// lp1,lp2,lor,bp1,bp2,bor of the three calls in mag_unsplit :147-240 -- emfz (2,3,4,6,7,8), emfy (4,2,3,8,6,7),
+// emfx (3,4,2,7,8,6) -- is applied with selects.  dir = direction of the edge (0: emfx, 1: emfy, 2: emfz).
 template <int R2D>
-__device__ __forceinline__ double emf_corners(const MPhys& P, const double* RT, const double* RB, const double* LT, const double* LB,
-                                              int lp1, int lp2, int lor, int bp1, int bp2, int bor) {
+__device__ __forceinline__ double emf_corners(const MPhys& P, const double* RT, const double* RB, const double* LT, const double* LB, int dir) {
   real qLL[8], qRL[8], qLR[8], qRR[8];   // :1506-1541 (qLL<-qRT, qRL<-qLT, qLR<-qRB, qRR<-qLB)
+#define VP1(s) sel3(dir, s[2], s[3], s[1])
+#define VP2(s) sel3(dir, s[3], s[1], s[2])
+#define VOR(s) sel3(dir, s[1], s[2], s[3])
+#define BP1(s) sel3(dir, s[6], s[7], s[5])
+#define BP2(s) sel3(dir, s[7], s[5], s[6])
+#define BOR(s) sel3(dir, s[5], s[6], s[7])
   qLL[0] = RT[0]; qRL[0] = LT[0]; qLR[0] = RB[0]; qRR[0] = LB[0];
   qLL[1] = RT[4]; qRL[1] = LT[4]; qLR[1] = RB[4]; qRR[1] = LB[4];
-  qLL[2] = RT[lp1]; qRL[2] = LT[lp1]; qLR[2] = RB[lp1]; qRR[2] = LB[lp1];
-  qLL[3] = RT[lp2]; qRL[3] = LT[lp2]; qLR[3] = RB[lp2]; qRR[3] = LB[lp2];
-  qLL[5] = 0.5 * (RT[bp1] + LT[bp1]); qRL[5] = 0.5 * (RT[bp1] + LT[bp1]);
-  qLR[5] = 0.5 * (RB[bp1] + LB[bp1]); qRR[5] = 0.5 * (RB[bp1] + LB[bp1]);
-  qLL[6] = 0.5 * (RT[bp2] + RB[bp2]); qRL[6] = 0.5 * (LT[bp2] + LB[bp2]);
-  qLR[6] = 0.5 * (RT[bp2] + RB[bp2]); qRR[6] = 0.5 * (LT[bp2] + LB[bp2]);
-  qLL[4] = RT[lor]; qRL[4] = LT[lor]; qLR[4] = RB[lor]; qRR[4] = LB[lor];
-  qLL[7] = RT[bor]; qRL[7] = LT[bor]; qLR[7] = RB[bor]; qRR[7] = LB[bor];
+  qLL[2] = VP1(RT); qRL[2] = VP1(LT); qLR[2] = VP1(RB); qRR[2] = VP1(LB);
+  qLL[3] = VP2(RT); qRL[3] = VP2(LT); qLR[3] = VP2(RB); qRR[3] = VP2(LB);
+  const double b1RT = BP1(RT), b1LT = BP1(LT), b1RB = BP1(RB), b1LB = BP1(LB);
+  const double b2RT = BP2(RT), b2LT = BP2(LT), b2RB = BP2(RB), b2LB = BP2(LB);
+  qLL[5] = 0.5 * (b1RT + b1LT); qRL[5] = 0.5 * (b1RT + b1LT);
+  qLR[5] = 0.5 * (b1RB + b1LB); qRR[5] = 0.5 * (b1RB + b1LB);
+  qLL[6] = 0.5 * (b2RT + b2RB); qRL[6] = 0.5 * (b2LT + b2LB);
+  qLR[6] = 0.5 * (b2RT + b2RB); qRR[6] = 0.5 * (b2LT + b2LB);
+  qLL[4] = VOR(RT); qRL[4] = VOR(LT); qLR[4] = VOR(RB); qRR[4] = VOR(LB);
+  qLL[7] = BOR(RT); qRL[7] = BOR(LT); qLR[7] = BOR(RB); qRR[7] = BOR(LB);
+#undef VP1
+#undef VP2
+#undef VOR
+#undef BP1
+#undef BP2
+#undef BOR
   return emf_edge<R2D>(P, qLL, qRL, qLR, qRR).v;
 }
 
@@ -439,28 +471,34 @@ __global__ void __launch_bounds__(128, MINB) mhd_emf_kernel(const MhdArgs a) {
   const double rdx = rcp_rn(a.dx);
   const int xm = wm(p.x, g.ncx, g.wrapx), ym = wm(p.y, g.ncy, g.wrapy), zm = wm(p.z, g.ncz, g.wrapz);
   const MPhys& P = a.P;
-  double RT[8], RB[8], LT[8], LB[8];
-  TC t;
-  if (ex && ey && oz) {   // emfz: (qRT(i-1,j-1), qRB(i-1,j), qLT(i,j-1), qLB(i,j)) component 3, permutation 2,3,4,6,7,8
-    load_tc<SL>(TR, nc, cidx(g, xm, ym, p.z), t); edge_state<2, +1, +1>(P, t, RT);
-    load_tc<SL>(TR, nc, cidx(g, xm, p.y, p.z), t); edge_state<2, +1, -1>(P, t, RB);
-    load_tc<SL>(TR, nc, cidx(g, p.x, ym, p.z), t); edge_state<2, -1, +1>(P, t, LT);
-    load_tc<SL>(TR, nc, c, t); edge_state<2, -1, -1>(P, t, LB);
-    EM[2 * nc + c] = div_rn(emf_corners<R2D>(P, RT, RB, LT, LB, 1, 2, 3, 5, 6, 7) * dt, a.dx, rdx);
-  }
-  if (ex && oy && ez) {   // emfy: (qRT(i-1,k-1), qLT(i,k-1), qRB(i-1,k), qLB(i,k)) component 2, permutation 4,2,3,8,6,7
-    load_tc<SL>(TR, nc, cidx(g, xm, p.y, zm), t); edge_state<1, +1, +1>(P, t, RT);
-    load_tc<SL>(TR, nc, cidx(g, p.x, p.y, zm), t); edge_state<1, -1, +1>(P, t, RB);   // dummy qRB <- actual qLT
-    load_tc<SL>(TR, nc, cidx(g, xm, p.y, p.z), t); edge_state<1, +1, -1>(P, t, LT);   // dummy qLT <- actual qRB
-    load_tc<SL>(TR, nc, c, t); edge_state<1, -1, -1>(P, t, LB);
-    EM[1 * nc + c] = div_rn(emf_corners<R2D>(P, RT, RB, LT, LB, 3, 1, 2, 7, 5, 6) * dt, a.dx, rdx);
-  }
-  if (ox && ey && ez) {   // emfx: (qRT(j-1,k-1), qRB(j-1,k), qLT(j,k-1), qLB(j,k)) component 1, permutation 3,4,2,7,8,6
-    load_tc<SL>(TR, nc, cidx(g, p.x, ym, zm), t); edge_state<0, +1, +1>(P, t, RT);
-    load_tc<SL>(TR, nc, cidx(g, p.x, ym, p.z), t); edge_state<0, +1, -1>(P, t, RB);
-    load_tc<SL>(TR, nc, cidx(g, p.x, p.y, zm), t); edge_state<0, -1, +1>(P, t, LT);
-    load_tc<SL>(TR, nc, c, t); edge_state<0, -1, -1>(P, t, LB);
-    EM[0 * nc + c] = div_rn(emf_corners<R2D>(P, RT, RB, LT, LB, 2, 3, 1, 6, 7, 5) * dt, a.dx, rdx);
+  auto one_edge = [&](const int dir) {
+    const bool need = dir == 2 ? (ex && ey && oz) : dir == 1 ? (ex && oy && ez) : (ox && ey && ez);
+    if (!need) return;
+    double RT[8], RB[8], LT[8], LB[8];
+    TC t;
+    if (dir == 2) {          // emfz: (qRT(i-1,j-1), qRB(i-1,j), qLT(i,j-1), qLB(i,j)) component 3
+      load_tc<SL>(TR, nc, cidx(g, xm, ym, p.z), t); edge_state<2, +1, +1>(P, t, RT);
+      load_tc<SL>(TR, nc, cidx(g, xm, p.y, p.z), t); edge_state<2, +1, -1>(P, t, RB);
+      load_tc<SL>(TR, nc, cidx(g, p.x, ym, p.z), t); edge_state<2, -1, +1>(P, t, LT);
+      load_tc<SL>(TR, nc, c, t); edge_state<2, -1, -1>(P, t, LB);
+    } else if (dir == 1) {   // emfy: (qRT(i-1,k-1), qLT(i,k-1), qRB(i-1,k), qLB(i,k)) component 2
+      load_tc<SL>(TR, nc, cidx(g, xm, p.y, zm), t); edge_state<1, +1, +1>(P, t, RT);
+      load_tc<SL>(TR, nc, cidx(g, p.x, p.y, zm), t); edge_state<1, -1, +1>(P, t, RB);   // dummy qRB <- actual qLT
+      load_tc<SL>(TR, nc, cidx(g, xm, p.y, p.z), t); edge_state<1, +1, -1>(P, t, LT);   // dummy qLT <- actual qRB
+      load_tc<SL>(TR, nc, c, t); edge_state<1, -1, -1>(P, t, LB);
+    } else {                 // emfx: (qRT(j-1,k-1), qRB(j-1,k), qLT(j,k-1), qLB(j,k)) component 1
+      load_tc<SL>(TR, nc, cidx(g, p.x, ym, zm), t); edge_state<0, +1, +1>(P, t, RT);
+      load_tc<SL>(TR, nc, cidx(g, p.x, ym, p.z), t); edge_state<0, +1, -1>(P, t, RB);
+      load_tc<SL>(TR, nc, cidx(g, p.x, p.y, zm), t); edge_state<0, -1, +1>(P, t, LT);
+      load_tc<SL>(TR, nc, c, t); edge_state<0, -1, -1>(P, t, LB);
+    }
+    EM[dir * nc + c] = div_rn(emf_corners<R2D>(P, RT, RB, LT, LB, dir) * dt, a.dx, rdx);
+  };
+  if (R2D == MHD2D_ROE) {
+#pragma unroll 1
+    for (int dir = 2; dir >= 0; dir--) one_edge(dir);
+  } else {
+    one_edge(2); one_edge(1); one_edge(0);
   }
 }
 

@@ -637,6 +637,7 @@ int amr_godunov(AmrLevel& A, int ilevel, double dt) {
   int ex;
   a.dx_pow2 = (std::frexp(A.dx, &ex) == 0.5) ? 1 : 0;
   a.interpol_type = G.interpol_type;
+  a.difmag = G.p.difmag;
   cudaError_t e;
   if (G.p.ndim == 1) e = dispatch_amr_nd<1>(G.p.riemann, a, G.stream);
   else if (G.p.ndim == 2) e = dispatch_amr_nd<2>(G.p.riemann, a, G.stream);
@@ -781,7 +782,8 @@ int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device) {
   }
   if (p->scheme != RGPU_SCHEME_MUSCL) return fail(RGPU_EUNSUPPORTED, "scheme='plmde' not supported");
   if (p->pressure_fix) return fail(RGPU_EUNSUPPORTED, "pressure_fix not supported");
-  if (p->difmag > 0.0) return fail(RGPU_EUNSUPPORTED, "difmag>0 not supported");
+  if (p->difmag > 0.0 && p->mhd) return fail(RGPU_EUNSUPPORTED, "MHD build: difmag>0 not supported");
+  if (p->difmag < 0.0) return fail(RGPU_EINVAL, "difmag=%g", p->difmag);
   {
     const int st = p->slope_type;
     const bool ok = st == 0 || st == 1 || st == 2 || st == 3 || st == 7 || st == 8 || (p->ndim == 1 && st >= 4 && st <= 6);
@@ -982,6 +984,9 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
   if (ilevel < 1 || ilevel > MAXLEVEL) return fail(RGPU_EINVAL, "ilevel %d out of range", ilevel);
   if (!G.amr && (ngrid_active <= 0 || !igrid_active)) return fail(RGPU_EINVAL, "level %d has no active oct", ilevel);
   if (G.amr) return amr_bind_level(ilevel, ngrid_active, igrid_active, ncpu, ngrid_recv, igrid_recv, ngrid_emit, igrid_emit, nboundary, boundary_type, ngrid_bound, igrid_bound);
+  if (G.p.difmag > 0.0)
+    return fail(RGPU_EUNSUPPORTED, "difmag>0 (cmpdivu/consup) is built in the oct-batch kernel only: call rgpu_set_amr(1, interpol_type, 0) after rgpu_init "
+                                   "(works for levelmin=levelmax runs too)");
   Level& L = G.lev[ilevel];
   if (L.bound) free_level(L);
   {

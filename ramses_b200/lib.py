@@ -49,6 +49,24 @@ def build(verbose=False):
 _lib = None
 
 
+def _preload_bundled_nccl():
+    """libramses_gpu.so needs `libnccl.so.2`.  When the Python environment ships its own NCCL (the `nvidia-nccl-cu12` wheel
+    PyTorch links against), load THAT copy first: the dynamic loader then binds both this library and a later
+    `import torch` to the same, newer NCCL.  Otherwise the system libnccl would be bound first and a subsequent
+    `import torch` fails with an undefined NCCL symbol.  No torch import happens here."""
+    try:
+        import glob
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            for f in sorted(glob.glob(os.path.join(d, "lib", "libnccl.so*"))):
+                C.CDLL(f, mode=C.RTLD_GLOBAL)
+                return f
+    except Exception:
+        pass
+    return None
+
+
 def load():
     """Load the C-ABI library.  Fails loudly if it has not been built: there is no fallback path."""
     global _lib
@@ -57,6 +75,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(ramses_b200 has no CPU fallback)")
+    _preload_bundled_nccl()
     L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
     ipp = C.POINTER(ip)

@@ -26,6 +26,7 @@ def commons_from_run(r, riemann, slope_type):
     a.boundary_type = [m.boundary_type[b] for b in range(m.nboundary)]
     a.gamma, a.courant_factor = r.p.gamma, r.p.courant_factor
     a.slope_type, a.riemann, a.nvector = slope_type, riemann, r.nvector
+    a.difmag = r.p.difmag
     return a
 
 
@@ -62,12 +63,13 @@ def gpu_amr_step(h, a, r, l, icount, dtnew, dtold):
 
 
 def run_case(ndim, levelmin, levelmax, bound, regions, riemann, slope_type, ncoarse_dev, interpol_type, nsub, boxlen=1.0,
-             err=0.05, nexpand=1):
+             err=0.05, nexpand=1, difmag=0.0):
     from oracle.amr import AmrRun
     from ramses_b200.hydro import HydroGPU
     r = AmrRun(ndim, levelmin, levelmax, bound, boxlen, nsubcycle=nsub, nexpand=nexpand, ngridmax=20000, riemann=riemann,
                slope_type=slope_type, err_grad_d=err, err_grad_u=err, err_grad_p=err, interpol_type=interpol_type,
                regions=regions, tout=[1e9])
+    r.p.difmag = difmag                            # hydro_parameters.f90:81 (cmpdivu + consup in unsplit)
     r.flag_coarse(); r.init_refine(); r.init_refine_2()
     for _ in range(ncoarse_dev):                   # develop the flow with the full (regridding) driver
         r.refine_coarse(); r.push_lists(1)
@@ -138,3 +140,54 @@ def test_amr_3d_sedov_like(riemann):
         assert (np.abs(got - ref) / scale).max() <= 1e-12
     else:
         assert np.array_equal(got, ref), (np.abs(got - ref).max(), nlev)
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_amr_difmag_bitwise(ndim):
+    """difmag>0: cmpdivu + consup (hydro/uplmde.f90:702,769) inside the oct-batch kernel, refined meshes in 1-D/2-D/3-D."""
+    if ndim == 1:
+        got, ref, dtnew, r, nlev = run_case(1, 3, 8, (1, 1, 0, 0, 0, 0), SOD, "hllc", 2, 6, 2, [1, 1, 1, 2], difmag=0.3)
+    elif ndim == 2:
+        regs = [dict(type="square", x_center=0.5, y_center=0.5, length_x=10, length_y=10, exp_region=10, d=1.0, p=0.1),
+                dict(type="square", x_center=0.3, y_center=0.4, length_x=0.3, length_y=0.25, exp_region=2, d=2.0, u=0.3, v=-0.2, p=1.0)]
+        got, ref, dtnew, r, nlev = run_case(2, 3, 5, (1, 1, 2, 2, 0, 0), regs, "hllc", 2, 2, 2, [1, 2], difmag=0.2)
+    else:
+        regs = [dict(type="square", x_center=0.5, y_center=0.5, z_center=0.5, length_x=10, length_y=10, length_z=10, exp_region=10, d=1.0, p=0.1),
+                dict(type="square", x_center=0.4, y_center=0.45, z_center=0.55, length_x=0.3, length_y=0.3, length_z=0.3, exp_region=2, d=1.5, p=2.0)]
+        got, ref, dtnew, r, nlev = run_case(3, 3, 4, (0,) * 6, regs, "llf", 1, 1, 1, [2, 2], difmag=0.25)
+    assert dtnew[3] == r.dtnew[3]
+    assert np.array_equal(got, ref), (np.abs(got - ref).max(), nlev)
+
+
+def test_difmag_uniform_grid_through_amr_mode_and_dense_path_rejects():
+    """levelmin=levelmax run with difmag>0: the dense fast path refuses, the oct-batch kernel (AMR mode) runs it bit-exactly."""
+    from helpers import Case, smooth_state
+    from ramses_b200 import lib as _l
+    from ramses_b200.hydro import HydroGPU
+    c = Case(3, 3, riemann="hllc", slope_type=1)
+    c.p.difmag = 0.4
+    u0 = smooth_state(3, 8)
+    u0[1] += u0[0] * 0.8 * np.sin(2 * np.pi * (np.arange(8) + 0.5) / 8)[None, None, :]   # compression around x = 0.5: min(0, div u) is active
+    c.init_dense(u0)
+    dt, _ = c.oracle_courant()
+    exp = c.oracle_godunov(dt).reshape(5, -1)
+    c0 = Case(3, 3, riemann="hllc", slope_type=1)
+    c0.init_dense(u0)
+    assert not np.array_equal(c0.oracle_godunov(dt).reshape(5, -1), exp)      # the term is active
+    a = c.amr_commons()
+    a.difmag = 0.4
+    h = HydroGPU(a)
+    with pytest.raises(_l.RgpuError):
+        h.bind_level(3)
+    h.finalize()
+    a = c.amr_commons()
+    a.difmag = 0.4
+    a.unew[:, :] = a.uold
+    a.dtnew[3] = dt
+    h = HydroGPU(a, amr_mode=True)
+    for l in (1, 2, 3):
+        h.bind_level(l)
+    h.godunov_fine(3)
+    h.finalize()
+    act = c.active_cells()
+    assert np.array_equal(a.unew[:, act], exp[:, act])
