@@ -363,59 +363,69 @@ __device__ __forceinline__ double sel3(int dir, double x, double y, double z) { 
 // inlined ONCE, so that the kernel (2700 instructions per solve) stays inside the instruction cache -- with three
 // inlined copies the top stall reason was `no_instruction` (profiles/r1_ncu_full_mhd_flux_roe.txt).  The variable
 // permutations ln,lt1,lt2,bn,bt1,bt2 of the three cmpflxm calls (mhd/umuscl.f90:51,84,117) become selects.
+struct FaceCtx {
+  bool ox, oy, oz, ex, ey, ez;
+  int x, y, z, xm, ym, zm;
+  long long c;
+  double dt, rdx;
+};
+template <int R1D, bool SL>
+__device__ __forceinline__ void one_face(const MhdArgs& a, const FaceCtx& k, const TC& tr, const int dir) {
+  const DenseGeom& g = a.g;
+  const long long nc = a.nc, c = k.c;
+  const double* TR = a.W + MW_TR * nc;
+  const bool need = dir == 0 ? (k.ex && k.oy && k.oz) : dir == 1 ? (k.ox && k.ey && k.oz) : (k.ox && k.oy && k.ez);
+  if (!need) return;
+  const long long cl = dir == 0 ? cidx(g, k.xm, k.y, k.z) : dir == 1 ? cidx(g, k.x, k.ym, k.z) : cidx(g, k.x, k.y, k.zm);
+  TC tl;
+  load_tc<SL>(TR, nc, cl, tl);
+  double sm[8], sp[8];   // qm of the cell below, qp of this cell
+  if (dir == 0) { face_state<0, +1>(a.P, tl, sm); face_state<0, -1>(a.P, tr, sp); }
+  else if (dir == 1) { face_state<1, +1>(a.P, tl, sm); face_state<1, -1>(a.P, tr, sp); }
+  else { face_state<2, +1>(a.P, tl, sm); face_state<2, -1>(a.P, tr, sp); }
+  real ql[8], qr[8], fg[9];
+  const double bnl = sel3(dir, sm[5], sm[6], sm[7]), bnr = sel3(dir, sp[5], sp[6], sp[7]);
+  const double bn_mean = 0.5 * (bnl + bnr);
+  ql[0] = sm[0]; ql[1] = sm[4]; ql[2] = sel3(dir, sm[1], sm[2], sm[3]); ql[3] = bn_mean;
+  ql[4] = sel3(dir, sm[2], sm[1], sm[1]); ql[5] = sel3(dir, sm[6], sm[5], sm[5]);
+  ql[6] = sel3(dir, sm[3], sm[3], sm[2]); ql[7] = sel3(dir, sm[7], sm[7], sm[6]);
+  qr[0] = sp[0]; qr[1] = sp[4]; qr[2] = sel3(dir, sp[1], sp[2], sp[3]); qr[3] = bn_mean;
+  qr[4] = sel3(dir, sp[2], sp[1], sp[1]); qr[5] = sel3(dir, sp[6], sp[5], sp[5]);
+  qr[6] = sel3(dir, sp[3], sp[3], sp[2]); qr[7] = sel3(dir, sp[7], sp[7], sp[6]);
+  riemann1d<R1D>(a.P, ql, qr, fg);
+  // (rho, mx, my, mz, E); the induction fluxes are dropped (flux(:,6:8)=0, godunov_fine.f90:778-879)
+  double f[5];
+  f[0] = fg[0].v; f[4] = fg[1].v;
+  f[1] = sel3(dir, fg[2].v, fg[4].v, fg[4].v);
+  f[2] = sel3(dir, fg[4].v, fg[2].v, fg[6].v);
+  f[3] = sel3(dir, fg[6].v, fg[6].v, fg[2].v);
+  double* F = a.W + (MW_F + 5 * dir) * nc;
+#pragma unroll
+  for (int n = 0; n < 5; n++) F[n * nc + c] = div_rn(f[n] * k.dt, a.dx, k.rdx);   // flux = fx*dt/dx :83
+}
+
 template <int R1D, bool SL, int MINB>
 __global__ void __launch_bounds__(128, MINB) mhd_flux_kernel(const MhdArgs a) {
   const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (c >= a.nc) return;
   const DenseGeom& g = a.g;
   const Cxyz p = cell_xyz(g, c);
+  FaceCtx k;
   // low faces are needed for the owned cells and for the first cell above the owned range (= high face of the last one)
-  const bool ox = in_range(p.x, g.ox0, g.ox1, g.ncx, g.wrapx, 0, 0), oy = in_range(p.y, g.oy0, g.oy1, g.ncy, g.wrapy, 0, 0),
-             oz = in_range(p.z, g.oz0, g.oz1, g.ncz, g.wrapz, 0, 0);
-  const bool ex = in_range(p.x, g.ox0, g.ox1, g.ncx, g.wrapx, 0, 1), ey = in_range(p.y, g.oy0, g.oy1, g.ncy, g.wrapy, 0, 1),
-             ez = in_range(p.z, g.oz0, g.oz1, g.ncz, g.wrapz, 0, 1);
-  const long long nc = a.nc;
-  const double* TR = a.W + MW_TR * nc;
-  const double dt = *a.dt_dev;
-  const double rdx = rcp_rn(a.dx);
+  k.ox = in_range(p.x, g.ox0, g.ox1, g.ncx, g.wrapx, 0, 0); k.oy = in_range(p.y, g.oy0, g.oy1, g.ncy, g.wrapy, 0, 0);
+  k.oz = in_range(p.z, g.oz0, g.oz1, g.ncz, g.wrapz, 0, 0);
+  k.ex = in_range(p.x, g.ox0, g.ox1, g.ncx, g.wrapx, 0, 1); k.ey = in_range(p.y, g.oy0, g.oy1, g.ncy, g.wrapy, 0, 1);
+  k.ez = in_range(p.z, g.oz0, g.oz1, g.ncz, g.wrapz, 0, 1);
+  k.x = p.x; k.y = p.y; k.z = p.z;
+  k.xm = wm(p.x, g.ncx, g.wrapx); k.ym = wm(p.y, g.ncy, g.wrapy); k.zm = wm(p.z, g.ncz, g.wrapz);
+  k.c = c; k.dt = *a.dt_dev; k.rdx = rcp_rn(a.dx);
   TC tr;
-  load_tc<SL>(TR, nc, c, tr);
-  auto one_face = [&](const int dir) {
-    const bool need = dir == 0 ? (ex && oy && oz) : dir == 1 ? (ox && ey && oz) : (ox && oy && ez);
-    if (!need) return;
-    const long long cl = dir == 0 ? cidx(g, wm(p.x, g.ncx, g.wrapx), p.y, p.z)
-                       : dir == 1 ? cidx(g, p.x, wm(p.y, g.ncy, g.wrapy), p.z) : cidx(g, p.x, p.y, wm(p.z, g.ncz, g.wrapz));
-    TC tl;
-    load_tc<SL>(TR, nc, cl, tl);
-    double sm[8], sp[8];   // qm of the cell below, qp of this cell
-    if (dir == 0) { face_state<0, +1>(a.P, tl, sm); face_state<0, -1>(a.P, tr, sp); }
-    else if (dir == 1) { face_state<1, +1>(a.P, tl, sm); face_state<1, -1>(a.P, tr, sp); }
-    else { face_state<2, +1>(a.P, tl, sm); face_state<2, -1>(a.P, tr, sp); }
-    real ql[8], qr[8], fg[9];
-    const double bnl = sel3(dir, sm[5], sm[6], sm[7]), bnr = sel3(dir, sp[5], sp[6], sp[7]);
-    const double bn_mean = 0.5 * (bnl + bnr);
-    ql[0] = sm[0]; ql[1] = sm[4]; ql[2] = sel3(dir, sm[1], sm[2], sm[3]); ql[3] = bn_mean;
-    ql[4] = sel3(dir, sm[2], sm[1], sm[1]); ql[5] = sel3(dir, sm[6], sm[5], sm[5]);
-    ql[6] = sel3(dir, sm[3], sm[3], sm[2]); ql[7] = sel3(dir, sm[7], sm[7], sm[6]);
-    qr[0] = sp[0]; qr[1] = sp[4]; qr[2] = sel3(dir, sp[1], sp[2], sp[3]); qr[3] = bn_mean;
-    qr[4] = sel3(dir, sp[2], sp[1], sp[1]); qr[5] = sel3(dir, sp[6], sp[5], sp[5]);
-    qr[6] = sel3(dir, sp[3], sp[3], sp[2]); qr[7] = sel3(dir, sp[7], sp[7], sp[6]);
-    riemann1d<R1D>(a.P, ql, qr, fg);
-    // (rho, mx, my, mz, E); the induction fluxes are dropped (flux(:,6:8)=0, godunov_fine.f90:778-879)
-    double f[5];
-    f[0] = fg[0].v; f[4] = fg[1].v;
-    f[1] = sel3(dir, fg[2].v, fg[4].v, fg[4].v);
-    f[2] = sel3(dir, fg[4].v, fg[2].v, fg[6].v);
-    f[3] = sel3(dir, fg[6].v, fg[6].v, fg[2].v);
-    double* F = a.W + (MW_F + 5 * dir) * nc;
-#pragma unroll
-    for (int n = 0; n < 5; n++) F[n * nc + c] = div_rn(f[n] * dt, a.dx, rdx);   // flux = fx*dt/dx :83
-  };
-  if (R1D == MHD_ROE) {   // measured: one copy wins for Roe (10.8 -> 10.5 ms/step), three copies for the small solvers
+  load_tc<SL>(a.W + MW_TR * a.nc, a.nc, c, tr);
+  if (R1D == MHD_ROE) {   // measured: one copy wins for Roe (10.8 -> 10.35 ms/step), three copies for the small solvers
 #pragma unroll 1
-    for (int dir = 0; dir < 3; dir++) one_face(dir);
+    for (int dir = 0; dir < 3; dir++) one_face<R1D, SL>(a, k, tr, dir);
   } else {
-    one_face(0); one_face(1); one_face(2);
+    one_face<R1D, SL>(a, k, tr, 0); one_face<R1D, SL>(a, k, tr, 1); one_face<R1D, SL>(a, k, tr, 2);
   }
 }
 
@@ -454,51 +464,55 @@ __device__ __forceinline__ double emf_corners(const MPhys& P, const double* RT, 
   return emf_edge<R2D>(P, qLL, qRL, qLR, qRR).v;
 }
 
+template <int R2D, bool SL>
+__device__ __forceinline__ void one_edge(const MhdArgs& a, const FaceCtx& k, const int dir) {
+  const DenseGeom& g = a.g;
+  const long long nc = a.nc, c = k.c;
+  const double* TR = a.W + MW_TR * nc;
+  const MPhys& P = a.P;
+  const bool need = dir == 2 ? (k.ex && k.ey && k.oz) : dir == 1 ? (k.ex && k.oy && k.ez) : (k.ox && k.ey && k.ez);
+  if (!need) return;
+  double RT[8], RB[8], LT[8], LB[8];
+  TC t;
+  if (dir == 2) {          // emfz: (qRT(i-1,j-1), qRB(i-1,j), qLT(i,j-1), qLB(i,j)) component 3
+    load_tc<SL>(TR, nc, cidx(g, k.xm, k.ym, k.z), t); edge_state<2, +1, +1>(P, t, RT);
+    load_tc<SL>(TR, nc, cidx(g, k.xm, k.y, k.z), t); edge_state<2, +1, -1>(P, t, RB);
+    load_tc<SL>(TR, nc, cidx(g, k.x, k.ym, k.z), t); edge_state<2, -1, +1>(P, t, LT);
+    load_tc<SL>(TR, nc, c, t); edge_state<2, -1, -1>(P, t, LB);
+  } else if (dir == 1) {   // emfy: (qRT(i-1,k-1), qLT(i,k-1), qRB(i-1,k), qLB(i,k)) component 2
+    load_tc<SL>(TR, nc, cidx(g, k.xm, k.y, k.zm), t); edge_state<1, +1, +1>(P, t, RT);
+    load_tc<SL>(TR, nc, cidx(g, k.x, k.y, k.zm), t); edge_state<1, -1, +1>(P, t, RB);   // dummy qRB <- actual qLT
+    load_tc<SL>(TR, nc, cidx(g, k.xm, k.y, k.z), t); edge_state<1, +1, -1>(P, t, LT);   // dummy qLT <- actual qRB
+    load_tc<SL>(TR, nc, c, t); edge_state<1, -1, -1>(P, t, LB);
+  } else {                 // emfx: (qRT(j-1,k-1), qRB(j-1,k), qLT(j,k-1), qLB(j,k)) component 1
+    load_tc<SL>(TR, nc, cidx(g, k.x, k.ym, k.zm), t); edge_state<0, +1, +1>(P, t, RT);
+    load_tc<SL>(TR, nc, cidx(g, k.x, k.ym, k.z), t); edge_state<0, +1, -1>(P, t, RB);
+    load_tc<SL>(TR, nc, cidx(g, k.x, k.y, k.zm), t); edge_state<0, -1, +1>(P, t, LT);
+    load_tc<SL>(TR, nc, c, t); edge_state<0, -1, -1>(P, t, LB);
+  }
+  double* EM = a.W + MW_EM * nc;
+  EM[dir * nc + c] = div_rn(emf_corners<R2D>(P, RT, RB, LT, LB, dir) * k.dt, a.dx, k.rdx);
+}
+
 template <int R2D, bool SL, int MINB>
 __global__ void __launch_bounds__(128, MINB) mhd_emf_kernel(const MhdArgs a) {
   const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (c >= a.nc) return;
   const DenseGeom& g = a.g;
   const Cxyz p = cell_xyz(g, c);
-  const bool ox = in_range(p.x, g.ox0, g.ox1, g.ncx, g.wrapx, 0, 0), oy = in_range(p.y, g.oy0, g.oy1, g.ncy, g.wrapy, 0, 0),
-             oz = in_range(p.z, g.oz0, g.oz1, g.ncz, g.wrapz, 0, 0);
-  const bool ex = in_range(p.x, g.ox0, g.ox1, g.ncx, g.wrapx, 0, 1), ey = in_range(p.y, g.oy0, g.oy1, g.ncy, g.wrapy, 0, 1),
-             ez = in_range(p.z, g.oz0, g.oz1, g.ncz, g.wrapz, 0, 1);
-  const long long nc = a.nc;
-  const double* TR = a.W + MW_TR * nc;
-  double* EM = a.W + MW_EM * nc;
-  const double dt = *a.dt_dev;
-  const double rdx = rcp_rn(a.dx);
-  const int xm = wm(p.x, g.ncx, g.wrapx), ym = wm(p.y, g.ncy, g.wrapy), zm = wm(p.z, g.ncz, g.wrapz);
-  const MPhys& P = a.P;
-  auto one_edge = [&](const int dir) {
-    const bool need = dir == 2 ? (ex && ey && oz) : dir == 1 ? (ex && oy && ez) : (ox && ey && ez);
-    if (!need) return;
-    double RT[8], RB[8], LT[8], LB[8];
-    TC t;
-    if (dir == 2) {          // emfz: (qRT(i-1,j-1), qRB(i-1,j), qLT(i,j-1), qLB(i,j)) component 3
-      load_tc<SL>(TR, nc, cidx(g, xm, ym, p.z), t); edge_state<2, +1, +1>(P, t, RT);
-      load_tc<SL>(TR, nc, cidx(g, xm, p.y, p.z), t); edge_state<2, +1, -1>(P, t, RB);
-      load_tc<SL>(TR, nc, cidx(g, p.x, ym, p.z), t); edge_state<2, -1, +1>(P, t, LT);
-      load_tc<SL>(TR, nc, c, t); edge_state<2, -1, -1>(P, t, LB);
-    } else if (dir == 1) {   // emfy: (qRT(i-1,k-1), qLT(i,k-1), qRB(i-1,k), qLB(i,k)) component 2
-      load_tc<SL>(TR, nc, cidx(g, xm, p.y, zm), t); edge_state<1, +1, +1>(P, t, RT);
-      load_tc<SL>(TR, nc, cidx(g, p.x, p.y, zm), t); edge_state<1, -1, +1>(P, t, RB);   // dummy qRB <- actual qLT
-      load_tc<SL>(TR, nc, cidx(g, xm, p.y, p.z), t); edge_state<1, +1, -1>(P, t, LT);   // dummy qLT <- actual qRB
-      load_tc<SL>(TR, nc, c, t); edge_state<1, -1, -1>(P, t, LB);
-    } else {                 // emfx: (qRT(j-1,k-1), qRB(j-1,k), qLT(j,k-1), qLB(j,k)) component 1
-      load_tc<SL>(TR, nc, cidx(g, p.x, ym, zm), t); edge_state<0, +1, +1>(P, t, RT);
-      load_tc<SL>(TR, nc, cidx(g, p.x, ym, p.z), t); edge_state<0, +1, -1>(P, t, RB);
-      load_tc<SL>(TR, nc, cidx(g, p.x, p.y, zm), t); edge_state<0, -1, +1>(P, t, LT);
-      load_tc<SL>(TR, nc, c, t); edge_state<0, -1, -1>(P, t, LB);
-    }
-    EM[dir * nc + c] = div_rn(emf_corners<R2D>(P, RT, RB, LT, LB, dir) * dt, a.dx, rdx);
-  };
+  FaceCtx k;
+  k.ox = in_range(p.x, g.ox0, g.ox1, g.ncx, g.wrapx, 0, 0); k.oy = in_range(p.y, g.oy0, g.oy1, g.ncy, g.wrapy, 0, 0);
+  k.oz = in_range(p.z, g.oz0, g.oz1, g.ncz, g.wrapz, 0, 0);
+  k.ex = in_range(p.x, g.ox0, g.ox1, g.ncx, g.wrapx, 0, 1); k.ey = in_range(p.y, g.oy0, g.oy1, g.ncy, g.wrapy, 0, 1);
+  k.ez = in_range(p.z, g.oz0, g.oz1, g.ncz, g.wrapz, 0, 1);
+  k.x = p.x; k.y = p.y; k.z = p.z;
+  k.xm = wm(p.x, g.ncx, g.wrapx); k.ym = wm(p.y, g.ncy, g.wrapy); k.zm = wm(p.z, g.ncz, g.wrapz);
+  k.c = c; k.dt = *a.dt_dev; k.rdx = rcp_rn(a.dx);
   if (R2D == MHD2D_ROE) {
 #pragma unroll 1
-    for (int dir = 2; dir >= 0; dir--) one_edge(dir);
+    for (int dir = 2; dir >= 0; dir--) one_edge<R2D, SL>(a, k, dir);
   } else {
-    one_edge(2); one_edge(1); one_edge(0);
+    one_edge<R2D, SL>(a, k, 2); one_edge<R2D, SL>(a, k, 1); one_edge<R2D, SL>(a, k, 0);
   }
 }
 

@@ -8,7 +8,7 @@ static int minb_choice(int r1d) {
   static int env = -1;
   if (env < 0) { const char* e = getenv("RGPU_MHD_MINB"); env = e ? atoi(e) : 0; }
   if (env >= 2 && env <= 4) return env;
-  return r1d == MHD_ROE ? 4 : 2;
+  return r1d == MHD_ROE ? 4 : (r1d == MHD_HLLD ? 3 : 2);
 }
 template <int R1D, bool SL>
 static cudaError_t go(const MhdArgs& a, cudaStream_t st) {
