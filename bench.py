@@ -41,6 +41,9 @@ WORKLOADS = {
     "tube_mhd_256_hlld": dict(level=8, riemann="hlld", riemann2d="hlld", slope_type=1, ic="tube_mhd", mhd=True),
     "tube_mhd_128_roe": dict(level=7, riemann="roe", riemann2d="llf", slope_type=0, ic="tube_mhd", mhd=True),
     "tube_mhd_64_roe": dict(level=6, riemann="roe", riemann2d="llf", slope_type=0, ic="tube_mhd", mhd=True),
+    # BASELINE.json configs[3]: sedov3d AMR levelmin=7 levelmax=10 (statically nested refinement around the blast, oct-batch kernel)
+    "sedov3d_amr_7_10_hllc": dict(level=10, levelmin=7, half_width=16, riemann="hllc", slope_type=1, ic="sedov_centre", amr=True),
+    "sedov3d_amr_5_8_hllc": dict(level=8, levelmin=5, half_width=8, riemann="hllc", slope_type=1, ic="sedov_centre", amr=True),
 }
 MHD_GAMMA = 1.6666667
 TUBE_L = (1.0, 0.0, 0.0, 0.0, 2.0, 1.0, 0.0, 0.0)               # namelist/tube_mhd.nml:25-38 (d,u,v,w,P,A,B,C)
@@ -80,6 +83,89 @@ def smooth_ic(nxyz):
         u[4] = p / (GAMMA - 1) + 0.5 * rho * (vx ** 2 + vy ** 2 + vz ** 2)
         return u
     return fn
+
+
+def amr_bench(args, w, rank, world, local_rank):
+    """configs[3]: one GPU, AMR mode.  A `step` is one coarse step of amr_step (levelmin .. levelmax with sub-cycling 2 per
+    level: 1+2+4+8 level steps), every per-level routine through the C-ABI in the reference's order (hydro.amr_step)."""
+    import torch
+    from ramses_b200.hydro import HydroGPU, amr_step
+    from ramses_b200.tree import build_nested_tree, cell_centers
+    if world > 1:
+        raise SystemExit("the AMR workloads are single-GPU in this round (multi-rank AMR is covered by tests/mgpu_amr_check.py)")
+    levelmin, levelmax = w["levelmin"], w["level"]
+    a = build_nested_tree(levelmin, levelmax, half_width=w["half_width"], boxlen=1.0)
+    a.gamma, a.courant_factor, a.slope_type, a.riemann = GAMMA, 0.8, w["slope_type"], w["riemann"]
+    dxf = 0.5 ** levelmax
+    for l in range(levelmin, levelmax + 1):       # sedov3d.nml regions with the point source moved to the box centre
+        ig, cc = cell_centers(a, l)
+        for ind in range(8):
+            x, y, z = cc[ind][:, 0] - 0.5, cc[ind][:, 1] - 0.5, cc[ind][:, 2] - 0.5
+            r = (np.maximum(1.0 - np.abs(x) / dxf, 0.0) * np.maximum(1.0 - np.abs(y) / dxf, 0.0) * np.maximum(1.0 - np.abs(z) / dxf, 0.0))
+            u = np.zeros((5, len(x)))
+            u[0] = 1.0
+            u[4] = (1e-5 + 0.4 * r / dxf ** 3) / (GAMMA - 1.0)
+            a.uold[:, a.ncoarse + ind * a.ngridmax + ig - 1] = u
+    h = HydroGPU(a, device=local_rank, amr_mode=True, interpol_type=1)
+    for l in range(1, levelmax + 1):
+        h.bind_level(l)
+    h.host_register(a.uold)
+    h.upload_state(0)
+    for l in range(levelmax - 1, 0, -1):
+        h.upload_fine(l)
+    nsub = [1] * (levelmin + 1) + [2] * 64
+    dtnew = {l: 0.0 for l in range(0, levelmax + 2)}
+    dtold = {l: 0.0 for l in range(0, levelmax + 2)}
+    ncell = {l: 8 * len(a.active[l]) for l in range(levelmin, levelmax + 1)}
+    updates = sum(ncell[l] * 2 ** (l - levelmin) for l in ncell)
+    launches0 = lambda: sum(h.level_info(l).kernel_launches for l in range(1, levelmax + 1))
+    steps, warmup = args.steps, max(args.warmup, 3)
+    for _ in range(warmup):
+        amr_step(h, levelmin, 1, levelmin, nsub, dtnew, dtold)
+    h.synchronize(); torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start(); time.sleep(0.3)
+    l0 = launches0()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h.synchronize(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        amr_step(h, levelmin, 1, levelmin, nsub, dtnew, dtold)
+    h.synchronize(); torch.cuda.synchronize()
+    wall = time.perf_counter() - t0           # the library's stream is synchronised on both sides: device time + host driver
+    launches = launches0() - l0
+    clocks = sampler.stop()
+    # end to end: host arrays in, host arrays out around every coarse step
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        h.upload_state(0)
+        amr_step(h, levelmin, 1, levelmin, nsub, dtnew, dtold)
+        h.download_state(0)
+    h.synchronize()
+    e2e_t = time.perf_counter() - t0
+    nbytes = a.uold.nbytes
+    h.finalize()
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(peaks_file))["hbm_gbs"] if os.path.exists(peaks_file) else 6650.0
+    achieved = BYTES_PER_CELL * updates / (wall / steps) / 1e9
+    line = {"metric": "cell_updates_per_s", "value": updates * steps / wall, "unit": "cell-updates/s", "n_gpus": 1, "steps": steps,
+            "warmup": warmup, "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "levelmin": levelmin, "levelmax": levelmax, "cells_per_level": ncell,
+                       "level_steps_per_coarse_step": {l: 2 ** (l - levelmin) for l in ncell}, "riemann": w["riemann"],
+                       "mesh": "static nested refinement (ramses_b200.tree.build_nested_tree), periodic box",
+                       "timing": "wall clock around K coarse steps with the stream synchronised on both sides (host-driven per-level calls)",
+                       "l2": "state %.2f GB vs 126 MB L2" % (nbytes / 1e9)},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": updates * args.e2e_steps / e2e_t, "unit": "cell-updates/s", "h2d_bytes_per_step": int(nbytes),
+                    "d2h_bytes_per_step": int(nbytes), "steps": args.e2e_steps,
+                    "api": "rgpu_upload_state + amr_step order of per-level rgpu_* calls + rgpu_download_state"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "whole coarse step (amr_godfine_kernel + reflux + list passes)", "kernel_ms": wall / steps * 1e3,
+                         "algorithmic_bytes_per_launch": BYTES_PER_CELL * updates},
+            "cpu_baseline": None}
+    print(json.dumps(line))
+    return 0
 
 
 def tube_mhd_ic(x_lo, x_mid, x_hi):
@@ -282,6 +368,8 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if w.get("amr"):
+        return amr_bench(args, w, rank, world, local_rank)
     level = w["level"]
     coarse = coarse_dims_for_ranks(3, world)
     mhd = bool(w.get("mhd"))

@@ -243,3 +243,40 @@ class HydroGPU:
 
     def finalize(self):
         _lib.check(self.L.rgpu_finalize())
+
+
+def amr_step(h, ilevel, icount, levelmin, nsubcycle, dtnew, dtold, multi_rank=False):
+    """amr_step(ilevel, icount) of amr/amr_step.f90 for the hydro solver on a frozen mesh (no flag/refine pass): the
+    recursion and the sub-cycling stay on the host exactly like in the Fortran driver, every per-level routine is the
+    `HydroGPU` call of the same name.  dtnew/dtold: dicts indexed by level (amr_commons dtnew/dtold); nsubcycle: list
+    indexed by level (amr_parameters.f90:nsubcycle, 1 or 2).  Line numbers refer to amr/amr_step.f90."""
+    a = h.a
+    if len(a.active.get(ilevel, [])) == 0:                       # numbtot(1,ilevel)==0 :37
+        return
+    dtold[ilevel] = dtnew[ilevel]
+    a.dtnew[ilevel] = a.boxlen / a.smallc                        # newdt_fine :326 (pm/newdt_fine.f90:47-51)
+    dtnew[ilevel] = h.courant_fine(ilevel)
+    if ilevel > levelmin:
+        dtnew[ilevel] = min(dtnew[ilevel - 1] / float(nsubcycle[ilevel - 1]), dtnew[ilevel])
+    a.dtnew[ilevel] = dtnew[ilevel]
+    h.set_unew(ilevel)                                           # :333
+    if ilevel < a.nlevelmax and len(a.active.get(ilevel + 1, [])) > 0:     # recursive call :345-361
+        for ic in ((1, 2) if nsubcycle[ilevel] == 2 else (1,)):
+            amr_step(h, ilevel + 1, ic, levelmin, nsubcycle, dtnew, dtold, multi_rank)
+    elif ilevel < a.nlevelmax:
+        dtold[ilevel + 1] = dtnew[ilevel] / float(nsubcycle[ilevel])
+        dtnew[ilevel + 1] = dtnew[ilevel] / float(nsubcycle[ilevel])
+    a.dtnew[ilevel] = dtnew[ilevel]
+    h.godunov_fine_dev(ilevel)                                   # :388
+    if multi_rank:
+        h.make_virtual_reverse(ilevel)                           # :397
+    h.set_uold(ilevel)                                           # :423
+    h.upload_fine(ilevel)                                        # :441
+    if multi_rank:
+        h.make_virtual_fine(ilevel)                              # :505
+    h.make_boundary_hydro(ilevel)                                # :514
+    if ilevel > levelmin:                                        # :567-577
+        if nsubcycle[ilevel - 1] == 1:
+            dtnew[ilevel - 1] = dtnew[ilevel]
+        if icount == 2:
+            dtnew[ilevel - 1] = dtold[ilevel] + dtnew[ilevel]

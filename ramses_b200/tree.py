@@ -218,3 +218,84 @@ def fill_state(a, ilevel, fn):
     for ind in range(a.twotondim):
         u = fn(cc[ind][:, 0], cc[ind][:, 1], cc[ind][:, 2])
         a.uold[:, a.ncoarse + ind * a.ngridmax + ig - 1] = u
+
+
+def build_nested_tree(levelmin, levelmax, half_width=8, boxlen=1.0, nvar=None, mhd=False):
+    """A statically refined 3-D periodic tree (single rank): levels 1..levelmin cover the box, every level
+    levelmin < l <= levelmax refines the centred cube of (2*half_width)^3 cells of level l-1 (so each fine level holds
+    (2*half_width)^3 octs).  With half_width >= 2 every refined cell keeps its 3^3 neighbours at its own level, the
+    rule the reference enforces through smooth_fine / nexpand (amr/flag_utils.f90:117-188), and a fine oct's six
+    neighbouring father cells always exist.  Produces the arrays of amr/amr_commons.f90:68-79 like build_uniform_tree;
+    oct numbering is lattice order level by level."""
+    ndim, nx, ny, nz = 3, 1, 1, 1
+    nvar = nvar or (8 if mhd else 5)
+    if half_width < 2:
+        raise ValueError("half_width must be >= 2")
+    pos = {}
+    for l in range(1, levelmax + 1):
+        n = 1 << (l - 1)                                  # octs per dimension if the level were full
+        if l <= levelmin:
+            r = np.arange(n)
+        else:
+            c = n // 2                                    # father cells at level l-1: n per dimension
+            if 2 * half_width > n:
+                raise ValueError("refined cube larger than the box")
+            r = np.arange(c - half_width, c + half_width)
+        gz, gy, gx = np.meshgrid(r, r, r, indexing="ij")
+        pos[l] = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], axis=1).astype(np.int64)
+    igrid0, nxt = {}, 1
+    for l in range(1, levelmax + 1):
+        igrid0[l] = nxt
+        nxt += len(pos[l])
+    ngridmax = nxt - 1 + 8
+    ncoarse = 1
+
+    def lookup(l, p):
+        n = 1 << (l - 1)
+        p = np.mod(p, n)
+        if l <= levelmin:
+            return igrid0[l] + p[:, 0] + n * (p[:, 1] + n * p[:, 2])
+        c, h = n // 2, half_width
+        q = p - (c - h)
+        ok = np.all((q >= 0) & (q < 2 * h), axis=1)
+        return np.where(ok, igrid0[l] + q[:, 0] + 2 * h * (q[:, 1] + 2 * h * q[:, 2]), 0)
+
+    a = AmrCommons(ndim, nvar, ncoarse, ngridmax, nx, ny, nz, (0, 0), (0, 0), (0, 0), nlevelmax=levelmax, boxlen=boxlen, mhd=mhd)
+    for l in range(1, levelmax + 1):
+        p = pos[l]
+        ig = igrid0[l] + np.arange(len(p))
+        if l == 1:
+            fcell = np.ones(len(p), dtype=np.int64)
+        else:
+            par = lookup(l - 1, p >> 1)
+            ind = (p[:, 0] & 1) + 2 * (p[:, 1] & 1) + 4 * (p[:, 2] & 1)
+            fcell = ncoarse + ind * ngridmax + par
+        a.father[ig - 1] = fcell
+        a.son[fcell - 1] = ig
+        for d in range(3):
+            for s, sh in ((0, -1), (1, +1)):
+                if l == 1:
+                    nb = np.ones(len(p), dtype=np.int64)
+                else:
+                    q = p.copy()
+                    q[:, d] += sh
+                    par = lookup(l - 1, np.mod(q, 1 << (l - 1)) >> 1)
+                    if (par <= 0).any():
+                        raise RuntimeError("nested tree violates the 2:1 rule")
+                    q = np.mod(q, 1 << (l - 1))
+                    ind = (q[:, 0] & 1) + 2 * (q[:, 1] & 1) + 4 * (q[:, 2] & 1)
+                    nb = ncoarse + ind * ngridmax + par
+                a.nbor[2 * d + s, ig - 1] = nb
+        a.active[l] = ig.astype(np.int32)
+        a.boundary[l] = []
+    a._pos = pos
+    a._igrid0 = igrid0
+    a.levelmin = levelmin
+    return a
+
+
+def leaf_cells(a, ilevel):
+    """0-based indices (into the ncell axis) of the leaf cells of a level (son == 0)."""
+    ig = a.active[ilevel].astype(np.int64)
+    c = np.concatenate([a.ncoarse + ind * a.ngridmax + ig - 1 for ind in range(a.twotondim)])
+    return c[a.son[c] == 0]
