@@ -53,6 +53,10 @@ struct SweepArgs {
   int ntx, nty;               // column tiles of the owned range
   long long nwork;            // ntx*nty*(owned planes): plane-tiles to distribute
   double* part;               // per-CTA partials [4][gridDim.x]: min dt, mass, etot, eint of the new state
+  // AMR variant (fully refined level inside an AMR run, godfine1 hydro/godunov_fine.f90:661-666,720-747,751-792):
+  const unsigned char* refined;  // [2^ndim][nslot] son(cell)>0: fluxes through faces of refined cells are reset to zero
+                                 // and the update ACCUMULATES into uout (= unew, which already holds the refluxes of the
+                                 // finer level) instead of starting from uin
 };
 
 __device__ __forceinline__ int wrap_or_clamp(int c, int n, int wrap) {
@@ -117,7 +121,7 @@ struct SweepSmem {
   static constexpr size_t doubles = ring + stage + exq + exf + carry;
 };
 
-template <int NDIM, int RIEMANN, int SLOPE, int BX, int BY>
+template <int NDIM, int RIEMANN, int SLOPE, int BX, int BY, bool AMRV = false>
 __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs a) {
   using S = SweepSmem<NDIM, BX, BY>;
   constexpr int NV = S::NV, HY = S::HY, HZ = S::HZ, QX = S::QX, QY = S::QY, NQ = S::NQ, NT = S::NT;
@@ -133,6 +137,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
   double* exf = exq + S::exq;                  // [NV][NT] Fy
   double* carry = exf + S::exf;                // [3][NV][NT]: qm_z, Fz, partial update of the previous plane
   __shared__ double red[4][NT / 32];
+  __shared__ unsigned char exm[AMRV ? NT : 1];   // AMRV: refined flag of every thread's cell (y exchange)
 
   const DenseGeom& g = a.g;
   const Phys& P = a.P;
@@ -247,6 +252,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
       stage_plane_async(z0);
     }
     const int kbeg = HZ ? z0 - 1 : 0, kend = HZ ? z1 : 0;
+    int mprev = 0;                             // AMRV: refined flag of my cell in the previous plane
     for (int k = kbeg; k <= kend; k++) {
       const int c = k - kbeg;
       const int sm1 = HZ ? c % 3 : 0, sc = HZ ? (c + 1) % 3 : 0, sp1 = HZ ? (c + 2) % 3 : 0;
@@ -366,6 +372,16 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
       double qlx[NV];
 #pragma unroll
       for (int n = 0; n < NV; n++) qlx[n] = __shfl_up_sync(0xffffffffu, qmx[n], 1);
+      int mc = 0, mlx = 0;                     // AMRV: ok(cell) = son(cell)>0 of my cell / of the cell at lane-1
+      if (AMRV) {
+        if (need_tr) {
+          const long long offm = cell_offset<NDIM>(g, wrap_or_clamp(cx, g.ncx, g.wrapx), HY ? wrap_or_clamp(cy, g.ncy, g.wrapy) : 0,
+                                                   HZ ? wrap_or_clamp(k, g.ncz, g.wrapz) : 0);
+          mc = a.refined[offm];
+        }
+        mlx = __shfl_up_sync(0xffffffffu, mc, 1);
+        exm[AMRV ? tid : 0] = (unsigned char)mc;
+      }
       __syncthreads();
 
       double fx[NV], fy[NV], fz[NV], ucur[NV];
@@ -373,8 +389,13 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
       for (int n = 0; n < NV; n++) { fx[n] = 0.0; fy[n] = 0.0; fz[n] = 0.0; ucur[n] = 0.0; }
       if (own && plane_flux) {   // set_unew: unew = uold; issued early so the latency hides under the Riemann solves
         const long long off = cell_offset<NDIM>(g, cx, cy, HZ ? k : 0);
+        if (AMRV) {              // unew already holds uold + the refluxes of the finer level (godunov_fine.f90:751-792 adds to it)
 #pragma unroll
-        for (int n = 0; n < NV; n++) ucur[n] = __ldg(a.uin + n * vstride + off);
+          for (int n = 0; n < NV; n++) ucur[n] = a.uout[n * vstride + off];
+        } else {
+#pragma unroll
+          for (int n = 0; n < NV; n++) ucur[n] = __ldg(a.uin + n * vstride + off);
+        }
       }
       // ---- X faces: cmpflxm(...,2,3,4) hydro/umuscl.f90:97 ----
       if (need_fx && plane_flux) {
@@ -394,6 +415,10 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
         if (NDIM > 1) fx[2] = fg[3];
         if (NDIM > 2) fx[3] = fg[4];
         scale_fluxes<NV>(fx, dt, a.dx, a.inv_dx, a.dx_pow2);
+        if (AMRV && (mlx | mc)) {   // reset flux along direction at refined interface :720-747
+#pragma unroll
+          for (int n = 0; n < NV; n++) fx[n] = 0.0;
+        }
       }
       // ---- Y faces: cmpflxm(...,3,2,4) hydro/umuscl.f90:120 ----
       if (HY && need_fy && plane_flux) {
@@ -411,6 +436,10 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
         fy[0] = fg[0]; fy[2] = fg[1]; fy[NDIM + 1] = fg[2]; fy[1] = fg[3];
         if (NDIM > 2) fy[3] = fg[4];
         scale_fluxes<NV>(fy, dt, a.dx, a.inv_dx, a.dx_pow2);
+        if (AMRV && (exm[AMRV ? tid - BX : 0] | mc)) {
+#pragma unroll
+          for (int n = 0; n < NV; n++) fy[n] = 0.0;
+        }
 #pragma unroll
         for (int n = 0; n < NV; n++) exf[n * NT + tid] = fy[n];
       }
@@ -427,7 +456,12 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
         riemann<NDIM, RIEMANN>(ql, qr, fg, P);
         fz[0] = fg[0]; fz[3 % NV] = fg[1]; fz[NDIM + 1] = fg[2]; fz[1] = fg[3]; fz[2] = fg[4 % NV];
         scale_fluxes<NV>(fz, dt, a.dx, a.inv_dx, a.dx_pow2);
+        if (AMRV && (mprev | mc)) {
+#pragma unroll
+          for (int n = 0; n < NV; n++) fz[n] = 0.0;
+        }
       }
+      mprev = mc;
       if (HZ && own) {
 #pragma unroll
         for (int n = 0; n < NV; n++) {
@@ -532,6 +566,21 @@ cudaError_t launch_sweep_dense_s(const SweepArgs& a, int nblocks, cudaStream_t s
   return launch_sweep_dense_sb<NDIM, RIEMANN, SLOPE, (NDIM == 3 ? 12 : 1)>(a, nblocks, st);
 }
 // slope_type 1 (minmod) and 2 (moncen) are compiled in; every other limiter goes through the runtime switch
+// AMR variant: one instantiation per solver (runtime slope switch, 12-row tiles), 3-D only
+template <int NDIM, int RIEMANN>
+cudaError_t launch_sweep_dense_amr(const SweepArgs& a, int nblocks, cudaStream_t st) {
+  constexpr int BX = 32, BY = (NDIM == 3 ? 12 : (NDIM == 2 ? 8 : 1));
+  constexpr size_t smem = sizeof(double) * SweepSmem<NDIM, BX, BY>::doubles;
+  auto kern = sweep_dense_kernel<NDIM, RIEMANN, -1, BX, BY, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<nblocks, dim3(BX, BY, 1), smem, st>>>(a);
+  return cudaGetLastError();
+}
 template <int NDIM, int RIEMANN>
 cudaError_t launch_sweep_dense(const SweepArgs& a, int nblocks, cudaStream_t st, int by) {
   if (a.P.slope_type == 1) return launch_sweep_dense_s<NDIM, RIEMANN, 1>(a, nblocks, st, by);

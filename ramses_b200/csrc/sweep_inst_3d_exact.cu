@@ -2,4 +2,5 @@
 #include "sweep_dense.cuh"
 namespace rgpu {
 template cudaError_t launch_sweep_dense<3, RIEMANN_EXACT>(const SweepArgs&, int, cudaStream_t, int);
+template cudaError_t launch_sweep_dense_amr<3, RIEMANN_EXACT>(const SweepArgs&, int, cudaStream_t);
 }
