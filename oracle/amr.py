@@ -374,8 +374,7 @@ class AmrRun:
                 raise RuntimeError("Fatal error in make_grid_fine")          # :612-626
         (self.active[lnew] if b < 0 else self.bound[b][lnew]).append(ig)
         if not self.init:
-            u2 = np.zeros(self.T * self.nvar)
-            self.L.orc_interpol_cell(C.byref(self.p), self.mp, c, lnew, orc.dptr(self.uold), orc.dptr(u2))
+            u2 = self.c_interpol_cell(c, lnew)
             U = self.uold.reshape(self.nvar, self.ncell)
             for j in range(self.T):
                 U[:, self.cell(j, ig) - 1] = u2[j * self.nvar:(j + 1) * self.nvar]
@@ -424,6 +423,21 @@ class AmrRun:
             self.refine_fine(l)
 
     # ------------------------------------------------------------------ hydro passes (C oracle)
+    # ---- the floating-point routines (C oracle); the MHD driver (oracle/amr_mhd.py) overrides these -------------------
+    def c_set_unew(self, l):
+        self.L.orc_set_unew(C.byref(self.p), self.mp, l, orc.dptr(self.uold), orc.dptr(self.unew))
+
+    def c_godunov_fine(self, l):
+        self.L.orc_godunov_fine(C.byref(self.p), self.mp, l, self.dtnew[l], orc.dptr(self.uold), orc.dptr(self.unew), 1)
+
+    def c_set_uold(self, l):
+        self.L.orc_set_uold(C.byref(self.p), self.mp, l, orc.dptr(self.uold), orc.dptr(self.unew))
+
+    def c_interpol_cell(self, c, lnew):
+        u2 = np.zeros(self.T * self.nvar)
+        self.L.orc_interpol_cell(C.byref(self.p), self.mp, c, lnew, orc.dptr(self.uold), orc.dptr(u2))
+        return u2
+
     def make_boundary_hydro(self, l):
         self.L.orc_make_boundary_hydro(C.byref(self.p), self.mp, l, orc.dptr(self.uold))
 
@@ -533,7 +547,7 @@ class AmrRun:
         self.newdt_fine(l)                                         # :326
         if l > self.levelmin:
             self.dtnew[l] = min(self.dtnew[l - 1] / float(self.nsubcycle[l - 1]), self.dtnew[l])
-        self.L.orc_set_unew(C.byref(self.p), self.mp, l, orc.dptr(self.uold), orc.dptr(self.unew))     # :333
+        self.c_set_unew(l)                                         # :333
         if l < self.nlevelmax:
             if self.numbtot(l + 1) > 0:
                 if self.nsubcycle[l] == 2:
@@ -549,8 +563,8 @@ class AmrRun:
             self.update_time(l)
         if self.done:
             return
-        self.L.orc_godunov_fine(C.byref(self.p), self.mp, l, self.dtnew[l], orc.dptr(self.uold), orc.dptr(self.unew), 1)  # :388
-        self.L.orc_set_uold(C.byref(self.p), self.mp, l, orc.dptr(self.uold), orc.dptr(self.unew))          # :423
+        self.c_godunov_fine(l)                                     # :388
+        self.c_set_uold(l)                                         # :423
         self.upload_fine(l)                                                                                  # :441
         self.make_boundary_hydro(l)                                                                          # :514
         if not self.static:

@@ -12,15 +12,20 @@
  *   mhd/courant_fine.f90  courant_fine:1
  *   mhd/hydro_boundary.f90 make_boundary_hydro:1 (reflexive :141-222, zero-gradient :223-296)
  *
- * Scope: NDIM=3, nvar=8 (no passive scalars, NENER=0), levelmin=levelmax (every neighbouring oct exists, so the
- * AMR prolongation mhd/interpol_hydro.f90 is never entered), no gravity, ischeme=muscl, pressure_fix=.false.,
- * allow_switch_solver=.false.
+ * Scope: NDIM=3 on uniform grids (levelmin=levelmax: every neighbouring oct exists) and NDIM=1 with AMR (end of the file);
+ * nvar=8 (no passive scalars, NENER=0), no gravity, ischeme=muscl, pressure_fix=.false., allow_switch_solver=.false.
  *
- * PARITY PINNING STATUS: UNPINNED.  The reference's only MHD golden files (tests/mhd/imhd-tube: NDIM=1 AMR 5-15,
- * tests/mhd/orszag-tang: NDIM=2 AMR 5-9) need trace1d/trace2d and the divergence-free AMR prolongation, which this
- * restatement does not cover yet, and the Fortran reference cannot be built here (no gfortran in the image).  What
- * pins it today: the analytic Brio-Wu-like tube (namelist/tube_mhd.nml) keeps its plateau states, div(B) stays at
- * round-off, conservation to round-off, and the B=0 limit reproduces the (pinned) hydro oracle's LLF/HLL fluxes.
+ * PARITY PINNING STATUS: PINNED for the 1-D AMR hlld path against the reference's golden file, at the reference's tolerance.
+ *   tests/mhd/imhd-tube/imhd-tube-ref.dat (NDIM=1, AMR levels 5..15, riemann='hlld', slope_type=0, zero-gradient ends,
+ *   interpol_type=2) is reproduced by oracle/amr_mhd.py + the NDIM=1 routines at the end of this file: ncells=437, level
+ *   and x sums exact, every other sum (density, pressure, three velocities, six face fields, time) to <= 1.8e-15 relative
+ *   (tolerance of the reference's check_solution: 3e-13) after 259 coarse / 16576 fine steps -- tests/test_oracle_golden.py.
+ *   That run exercises find_mhd_flux, hlld, find_speed_fast, cmpdt, the shared limiter, the MHD prolongation / restriction
+ *   / refluxing and boundary code.  NOT covered by a golden file (the reference has none): the NDIM=3 specific parts
+ *   (trace3d, cmp_mag_flx and the 2-D solvers, the CT update) and roe / hll / llf; those rest on the exact Ryu-Jones
+ *   solution shipped with the reference (3-D run converges to it), axis-permutation covariance, div B = 0, conservation
+ *   and the B=0 limit against the golden-pinned hydro oracle (tests/test_oracle_mhd.py).  tests/mhd/orszag-tang (NDIM=2
+ *   AMR) needs trace2d and the 2-D divergence-free prolongation: not restated.
  */
 #include "ramses_oracle_mhd.h"
 
@@ -1250,4 +1255,342 @@ void orc_mhd_run_uniform(const orc_mhd_params* p, const orc_mesh* m, int ilevel,
     if (dt_hist) dt_hist[s] = dt;
   }
   if (t_io) *t_io = t;
+}
+
+/* ======================================================================================================
+ * NDIM = 1 (tests/mhd/imhd-tube): mag_unsplit with trace1d (mhd/umuscl.f90:244), godfine1 with the coarse-fine pieces
+ * (AMR prolongation mhd/interpol_hydro.f90:612 + interpol_mag:990, flux reset at refined faces, coarse refluxing
+ * mhd/godunov_fine.f90:997-1168), upload_fine (mhd/interpol_hydro.f90:5,233), courant_fine, make_boundary_hydro.
+ * In one dimension B_x never changes (flux(:,6)=0, no EMF), B_y and B_z advance with the ordinary fluxes 7,8 and both of
+ * their copies receive the same increment.
+ * ====================================================================================================== */
+typedef struct { double uloc[6][NVS]; int ok[6]; double flux[3][NV]; } mhd1_patch;   /* faces i3 = 1..3 */
+
+static void mhd1_unsplit(const orc_mhd_params* p, mhd1_patch* w, double dx, double dt) {
+  double q[6][NV], dq[6][NV], qm[6][NV], qp[6][NV];
+  const double smallp = p->smallr * (p->smallc * p->smallc) / p->gamma;
+  for (int i = 0; i < 6; i++) { /* ctoprim :2029 */
+    const double* u = w->uloc[i];
+    q[i][0] = FMAX(u[0], p->smallr);
+    q[i][1] = u[1] / q[i][0]; q[i][2] = u[2] / q[i][0]; q[i][3] = u[3] / q[i][0];
+    q[i][5] = (u[5] + u[NV + 0]) * half;
+    q[i][6] = (u[6] + u[NV + 1]) * half;
+    q[i][7] = (u[7] + u[NV + 2]) * half;
+    double eken = half * (q[i][1] * q[i][1] + q[i][2] * q[i][2] + q[i][3] * q[i][3]);
+    double emag = half * (q[i][5] * q[i][5] + q[i][6] * q[i][6] + q[i][7] * q[i][7]);
+    double etot = u[4] - emag - zero;
+    double eint = etot / q[i][0] - eken;
+    q[i][4] = FMAX((p->gamma - one) * q[i][0] * eint, smallp);
+  }
+  memset(dq, 0, sizeof dq);
+  if (p->slope_type == 1 || p->slope_type == 2) { /* uslope NDIM==1 :2222-2245 */
+    for (int n = 0; n < NV; n++)
+      for (int i = 1; i <= 4; i++) dq[i][n] = slope_mm((double)p->slope_type, q[i - 1][n], q[i][n], q[i + 1][n]);
+  } else if (p->slope_type != 0) { fprintf(stderr, "oracle(mhd 1-D): Unknown slope type\n"); abort(); }
+  const double dtdx = dt / dx;
+  for (int i = 1; i <= 4; i++) { /* trace1d :244 (Fortran i = 0..3) */
+    double r = q[i][0], u = q[i][1], v = q[i][2], ww = q[i][3], pp = q[i][4], A = q[i][5], B = q[i][6], C = q[i][7];
+    double drx = half * dq[i][0], dux = half * dq[i][1], dvx = half * dq[i][2], dwx = half * dq[i][3], dpx = half * dq[i][4];
+    double dBx = half * dq[i][6], dCx = half * dq[i][7];
+    double sr0 = -u * drx - r * dux;
+    double su0 = -u * dux - (dpx + B * dBx + C * dCx) / r;
+    double sv0 = -u * dvx + (A * dBx) / r;
+    double sw0 = -u * dwx + (A * dCx) / r;
+    double sp0 = -u * dpx - p->gamma * pp * dux;
+    double sB0 = -u * dBx + A * dvx - B * dux;
+    double sC0 = -u * dCx + A * dwx - C * dux;
+    r = r + sr0 * dtdx; u = u + su0 * dtdx; v = v + sv0 * dtdx; ww = ww + sw0 * dtdx; pp = pp + sp0 * dtdx;
+    B = B + sB0 * dtdx; C = C + sC0 * dtdx;
+    qp[i][0] = r - drx; qp[i][1] = u - dux; qp[i][2] = v - dvx; qp[i][3] = ww - dwx; qp[i][4] = pp - dpx;
+    qp[i][5] = A; qp[i][6] = B - dBx; qp[i][7] = C - dCx;
+    if (qp[i][0] < p->smallr) qp[i][0] = r;
+    qm[i][0] = r + drx; qm[i][1] = u + dux; qm[i][2] = v + dvx; qm[i][3] = ww + dwx; qm[i][4] = pp + dpx;
+    qm[i][5] = A; qm[i][6] = B + dBx; qm[i][7] = C + dCx;
+    if (qm[i][0] < p->smallr) qm[i][0] = r;
+  }
+  for (int i3 = 1; i3 <= 3; i3++) { /* cmpflxm(…,2,3,4,6,7,8) :51; face i3 between patch cells i3-1 and i3 (Fortran) */
+    const double* m_ = qm[i3]; /* Fortran cell i3-1 = C index i3 */
+    const double* p_ = qp[i3 + 1];
+    double ql[8], qr[8], fg[9];
+    double bn_mean = half * (m_[5] + p_[5]);
+    ql[0] = m_[0]; ql[1] = m_[4]; ql[2] = m_[1]; ql[3] = bn_mean; ql[4] = m_[2]; ql[5] = m_[6]; ql[6] = m_[3]; ql[7] = m_[7];
+    qr[0] = p_[0]; qr[1] = p_[4]; qr[2] = p_[1]; qr[3] = bn_mean; qr[4] = p_[2]; qr[5] = p_[6]; qr[6] = p_[3]; qr[7] = p_[7];
+    riemann1d(p, ql, qr, fg);
+    double* f = w->flux[i3 - 1];
+    f[0] = fg[0]; f[4] = fg[1]; f[1] = fg[2]; f[5] = fg[3]; f[2] = fg[4]; f[6] = fg[5]; f[3] = fg[6]; f[7] = fg[7];
+    for (int n = 0; n < NV; n++) f[n] = f[n] * dt / dx;
+  }
+}
+
+static const orc_params* hydro_like_params(int ndim) {   /* orc_interpol_hydro / orc_getnborfather only read ndim, nvar */
+  static orc_params hp;
+  memset(&hp, 0, sizeof hp);
+  hp.ndim = ndim; hp.nvar = NVS;
+  return &hp;
+}
+
+/* interpol_hydro mhd/interpol_hydro.f90:612 for one father cell, NDIM=1, interpol_var=0: variables 1..5,7,8 with the
+ * scalar limiter, B_x from interpol_mag (:990; face values, fine faces where a neighbour is refined :1246, centre = mean
+ * :1354), the right copies of B_y,B_z equal to the left ones (:712-718).  u2[2][11].                                    */
+void orc_mhd1_interpol_cell(const orc_mesh* m, int ind_cell, int ilevel, const double* uold, double* u2) {
+  int fa[3];
+  double u1[3 * NVS], t2[2 * NVS];
+  orc_getnborfather(m, ind_cell, ilevel, fa);
+  for (int j = 0; j < 3; j++)
+    for (int iv = 1; iv <= NVS; iv++) u1[j * NVS + iv - 1] = UO(fa[j], iv);
+  orc_interpol_hydro(hydro_like_params(1), u1, t2);
+  for (int ind = 0; ind < 2; ind++) {
+    for (int iv = 0; iv < NVS; iv++) u2[ind * NVS + iv] = t2[ind * NVS + iv];
+    u2[ind * NVS + NV + 1] = u2[ind * NVS + 6];
+    u2[ind * NVS + NV + 2] = u2[ind * NVS + 7];
+  }
+  double um1 = u1[0 * NVS + 5] + 0.5 * 0.0 * (0.0 - 0.5) + 0.5 * 0.0 * (0.0 - 0.5);       /* interpol_faces :1091 (s = 0 in 1-D) */
+  double up1 = u1[0 * NVS + NV + 0] + 0.5 * 0.0 * (0.0 - 0.5) + 0.5 * 0.0 * (0.0 - 0.5);
+  const int s1 = m->son[fa[1]], s2 = m->son[fa[2]];
+  if (s1 > 0) um1 = UO(m->ncoarse + 1 * m->ngridmax + s1, NV + 1);   /* right face of the right son of the left neighbour */
+  if (s2 > 0) up1 = UO(m->ncoarse + 0 * m->ngridmax + s2, 6);        /* left face of the left son of the right neighbour */
+  const double u0 = 0.5 * (um1 + up1);                               /* cmp_central_faces :1354 (no transverse terms in 1-D) */
+  u2[0 * NVS + 5] = um1; u2[0 * NVS + NV + 0] = u0;
+  u2[1 * NVS + 5] = u0;  u2[1 * NVS + NV + 0] = up1;
+}
+
+/* godfine1 for one batch of ncache <= nvector octs: like the reference, all fluxes of the batch first, then the update of the
+ * octs' own cells, then per direction the refluxes through the LEFT faces of every oct of the batch, then through the RIGHT
+ * faces (several octs may reflux into the same coarse cell: the order of these additions is the reference's).               */
+static void mhd1_godfine1(const orc_mhd_params* p, const orc_mesh* m, const int* ind_grid, int ncache, int ilevel, int levelmin,
+                          double dt, const double* uold, double* unew) {
+  const double dx = level_dx(p, m, ilevel);
+  mhd1_patch* W = (mhd1_patch*)malloc(sizeof(mhd1_patch) * (size_t)ncache);
+  for (int i = 0; i < ncache; i++) {
+    const int ig = ind_grid[i];
+    mhd1_patch* w = &W[i];
+    int nfc[3];
+    orc_get3cubefather(m, m->father[ig], ilevel, nfc, NULL);
+    for (int i1 = 0; i1 <= 2; i1++) {
+      const int igrid_nbor = m->son[nfc[i1]];
+      double u2[2 * NVS];
+      if (igrid_nbor <= 0) orc_mhd1_interpol_cell(m, nfc[i1], ilevel, uold, u2);
+      for (int i2 = 0; i2 <= 1; i2++) {
+        const int i3 = 1 + 2 * (i1 - 1) + i2;      /* Fortran -1..4 */
+        if (igrid_nbor > 0) {
+          const int ic = m->ncoarse + i2 * m->ngridmax + igrid_nbor;
+          for (int iv = 1; iv <= NVS; iv++) w->uloc[i3 + 1][iv - 1] = UO(ic, iv);
+          w->ok[i3 + 1] = m->son[ic] > 0;
+        } else {
+          for (int iv = 0; iv < NVS; iv++) w->uloc[i3 + 1][iv] = u2[i2 * NVS + iv];
+          w->ok[i3 + 1] = 0;
+        }
+      }
+    }
+    mhd1_unsplit(p, w, dx, dt);
+    for (int i3 = 1; i3 <= 3; i3++) {
+      if (w->ok[i3] || w->ok[i3 + 1])      /* ok(i3-1) .or. ok(i3) :742-747 */
+        for (int n = 0; n < NV; n++) w->flux[i3 - 1][n] = 0.0;
+      w->flux[i3 - 1][5] = 0.0;            /* flux(:,6,idim)=0 :778 (7 and 8 only for NDIM>1, NDIM>2) */
+    }
+  }
+  for (int i2 = 0; i2 <= 1; i2++)          /* :883-956 */
+    for (int i = 0; i < ncache; i++) {
+      const mhd1_patch* w = &W[i];
+      const int ic = m->ncoarse + i2 * m->ngridmax + ind_grid[i];
+      for (int iv = 1; iv <= NV; iv++) UN(ic, iv) = UN(ic, iv) + (w->flux[i2][iv - 1] - w->flux[i2 + 1][iv - 1]);
+      for (int iv = 1; iv <= 3; iv++) UN(ic, NV + iv) = UN(ic, NV + iv) + (w->flux[i2][5 + iv - 1] - w->flux[i2 + 1][5 + iv - 1]);
+    }
+  for (int i2 = 0; i2 <= 1; i2++)          /* :943-956 with emfy = emfz = 0 in one dimension */
+    for (int i = 0; i < ncache; i++) {
+      const int ic = m->ncoarse + i2 * m->ngridmax + ind_grid[i];
+      const double dflux_x = (0.0 - 0.0) - (0.0 - 0.0);
+      UN(ic, 6) = UN(ic, 6) + dflux_x;
+      UN(ic, NV + 1) = UN(ic, NV + 1) + dflux_x;
+    }
+  if (ilevel > levelmin) {                 /* :997-1168 */
+    const double oneontwotondim = 0.5;
+    for (int iv = 1; iv <= NV; iv++)
+      for (int i = 0; i < ncache; i++) {
+        const int nb = NBOR(m, ind_grid[i], 1);
+        if (m->son[nb] == 0) UN(nb, iv) = UN(nb, iv) - W[i].flux[0][iv - 1] * oneontwotondim;
+      }
+    for (int iv = 1; iv <= 3; iv++)
+      for (int i = 0; i < ncache; i++) {
+        const int nb = NBOR(m, ind_grid[i], 1);
+        if (m->son[nb] == 0) UN(nb, NV + iv) = UN(nb, NV + iv) - W[i].flux[0][5 + iv - 1] * oneontwotondim;
+      }
+    for (int iv = 1; iv <= NV; iv++)
+      for (int i = 0; i < ncache; i++) {
+        const int nb = NBOR(m, ind_grid[i], 2);
+        if (m->son[nb] == 0) UN(nb, iv) = UN(nb, iv) + W[i].flux[2][iv - 1] * oneontwotondim;
+      }
+    for (int iv = 1; iv <= 3; iv++)
+      for (int i = 0; i < ncache; i++) {
+        const int nb = NBOR(m, ind_grid[i], 2);
+        if (m->son[nb] == 0) UN(nb, NV + iv) = UN(nb, NV + iv) + W[i].flux[2][5 + iv - 1] * oneontwotondim;
+      }
+  }
+  free(W);
+}
+
+void orc_mhd1_godunov_fine(const orc_mhd_params* p, const orc_mesh* m, int ilevel, int levelmin, int nvector, double dt,
+                           const double* uold, double* unew) {
+  if (m->ndim != 1) { fprintf(stderr, "oracle(mhd 1-D): NDIM=%d\n", m->ndim); abort(); }
+  const int ncache = m->nactive[ilevel];
+  for (int ig = 0; ig < ncache; ig += nvector) {
+    const int ngrid = (nvector < ncache - ig) ? nvector : ncache - ig;
+    mhd1_godfine1(p, m, m->active[ilevel] + ig, ngrid, ilevel, levelmin, dt, uold, unew);
+  }
+}
+
+/* set_unew / set_uold mhd/godunov_fine.f90:40,172 for any NDIM */
+void orc_mhdn_set_unew(const orc_mesh* m, int ilevel, const double* uold, double* unew) {
+  const int T = 1 << m->ndim;
+  for (int ind = 0; ind < T; ind++) {
+    int iskip = m->ncoarse + ind * m->ngridmax;
+    for (int iv = 1; iv <= NVS; iv++)
+      for (int a = 0; a < m->nactive[ilevel]; a++) UN(m->active[ilevel][a] + iskip, iv) = UO(m->active[ilevel][a] + iskip, iv);
+  }
+}
+void orc_mhdn_set_uold(const orc_mesh* m, int ilevel, double* uold, const double* unew) {
+  const int T = 1 << m->ndim;
+  for (int ind = 0; ind < T; ind++) {
+    int iskip = m->ncoarse + ind * m->ngridmax;
+    for (int iv = 1; iv <= NVS; iv++)
+      for (int a = 0; a < m->nactive[ilevel]; a++) UO(m->active[ilevel][a] + iskip, iv) = UN(m->active[ilevel][a] + iskip, iv);
+  }
+}
+
+/* courant_fine mhd/courant_fine.f90 + cmpdt (godunov_utils.f90:5), NDIM=1: leaf cells, ctot sums idim = 1..ndim */
+double orc_mhd1_courant_fine(const orc_mhd_params* p, const orc_mesh* m, int ilevel, double dt_in, const double* uold) {
+  const double dx = level_dx(p, m, ilevel);
+  const double smallp = p->smallr * (p->smallc * p->smallc) / p->gamma;
+  double dt_loc = dt_in;
+  for (int a = 0; a < m->nactive[ilevel]; a++)
+    for (int ind = 0; ind < 2; ind++) {
+      int ic = m->active[ilevel][a] + m->ncoarse + ind * m->ngridmax;
+      if (m->son[ic] != 0) continue;
+      double uu[NVS];
+      for (int iv = 1; iv <= NVS; iv++) uu[iv - 1] = UO(ic, iv);
+      uu[0] = FMAX(uu[0], p->smallr);
+      double rho = uu[0];
+      for (int d = 1; d <= 3; d++) uu[d] = uu[d] / rho;
+      double B2 = zero;
+      for (int d = 1; d <= 3; d++) {
+        double Bc = half * (uu[4 + d] + uu[NV + d - 1]);
+        B2 = B2 + Bc * Bc;
+        uu[4] = uu[4] - half * uu[0] * (uu[d] * uu[d]) - half * (Bc * Bc);
+      }
+      uu[4] = FMAX((p->gamma - one) * uu[4], smallp);
+      double a2 = p->gamma * uu[4] / uu[0];
+      double ctot = zero;
+      for (int d = 1; d <= 1; d++) { /* WARNING: ndim instead of 3 */
+        double cc = half * (B2 / rho + a2);
+        double BN = half * (uu[4 + d] + uu[NV + d - 1]);
+        double cf = sqrt(cc + sqrt(cc * cc - a2 * (BN * BN) / rho));
+        ctot = ctot + fabs(uu[d]) + cf;
+      }
+      double r = zero * dx / (ctot * ctot);
+      r = FMAX(r, 0.0001);
+      double dt = p->courant_factor * dx / p->smallc;
+      double dtcell = dx / ctot * (sqrt(one + two * p->courant_factor * r) - one) / r;
+      dt = FMIN(dt, dtcell);
+      dt_loc = FMIN(dt_loc, dt);
+    }
+  return FMIN(dt_in, dt_loc);
+}
+
+/* make_boundary_hydro mhd/hydro_boundary.f90, NDIM=1 (boundary_dir 1,2; reflexive and zero gradient) */
+void orc_mhd1_make_boundary_hydro(const orc_mhd_params* p, const orc_mesh* m, int ilevel, double* uold) {
+  for (int ib = 0; ib < m->nboundary; ib++) {
+    const int bt = m->boundary_type[ib];
+    const int dir = bt - 10 * (bt / 10);
+    const int inbor = dir == 1 ? 2 : 1;
+    static const int ref_x[2] = {2, 1}, free1[2] = {1, 1}, free2[2] = {2, 2};
+    static const int alt1[2] = {-2, -1}, alt2[2] = {1, 2};
+    const int* ind_ref = (bt / 10 == 0) ? ref_x : (dir == 1 ? free1 : free2);
+    const int* ind_normal = dir == 1 ? free1 : free2;
+    const int* alt = dir == 1 ? alt1 : alt2;
+    const int iperp1 = dir == 1 ? 6 : NV + 1;
+    const int gdim = 1;
+    for (int a = 0; a < m->nbound[ib][ilevel]; a++) {
+      const int ig = m->bound[ib][ilevel][a];
+      const int igr = m->son[NBOR(m, ig, inbor)];
+      for (int ind = 0; ind < 2; ind++) {
+        const int ic = m->ncoarse + ind * m->ngridmax + ig;
+        const int icr = m->ncoarse + (ind_ref[ind] - 1) * m->ngridmax + igr;
+        double uu[NVS + 1];
+        for (int iv = 1; iv <= NVS; iv++) uu[iv] = UO(icr, iv);
+        if (bt / 10 == 0) {
+          const int icn = m->ncoarse + (ind_normal[ind] - 1) * m->ngridmax + igr;
+          double emag = 0.125 * (SQ(uu[6] + uu[NV + 1]) + SQ(uu[7] + uu[NV + 2]) + SQ(uu[8] + uu[NV + 3]));
+          uu[5] = uu[5] - emag;
+          const double B_normal = UO(icn, iperp1);
+          for (int iv = 1; iv <= NVS; iv++) {
+            double sw = 1;
+            if (iv == 2) sw = -1;          /* gs(1) = -1 for boundary types 1,2 */
+            if (iv != 5 + gdim && iv != NV + gdim) UO(ic, iv) = uu[iv] * sw;
+            if (iv == 5 + gdim) UO(ic, 5 + gdim) = 2 * B_normal - uu[NV + gdim];
+            if (iv == NV + gdim) UO(ic, NV + gdim) = 2 * B_normal - uu[5 + gdim];
+          }
+          emag = 0.125 * (SQ(UO(ic, 6) + UO(ic, NV + 1)) + SQ(UO(ic, 7) + UO(ic, NV + 2)) + SQ(UO(ic, 8) + UO(ic, NV + 3)));
+          UO(ic, 5) = UO(ic, 5) + emag;
+        } else if (bt / 10 == 1) {
+          double emag = 0.125 * (SQ(uu[6] + uu[NV + 1]) + SQ(uu[7] + uu[NV + 2]) + SQ(uu[8] + uu[NV + 3]));
+          double ekin = 0.0, d = FMAX(uu[1], p->smallr);
+          for (int idim = 1; idim <= 1; idim++) { double v = uu[idim + 1] / d; ekin = ekin + 0.5 * d * (v * v); }   /* idim=1,ndim */
+          uu[5] = uu[5] - emag - ekin;
+          for (int iv = 1; iv <= NVS; iv++) {
+            if (iv != 5 + gdim && iv != NV + gdim) UO(ic, iv) = uu[iv];
+            if (iv == 5 + gdim) UO(ic, 5 + gdim) = uu[5 + gdim] + (uu[NV + gdim] - uu[5 + gdim]) * (double)alt[ind];
+            if (iv == NV + gdim) UO(ic, NV + gdim) = uu[NV + gdim] + (uu[NV + gdim] - uu[5 + gdim]) * (double)alt[ind];
+          }
+          emag = 0.125 * (SQ(UO(ic, 6) + UO(ic, NV + 1)) + SQ(UO(ic, 7) + UO(ic, NV + 2)) + SQ(UO(ic, 8) + UO(ic, NV + 3)));
+          ekin = 0.0; d = FMAX(UO(ic, 1), p->smallr);
+          for (int idim = 1; idim <= 1; idim++) { double v = UO(ic, idim + 1) / d; ekin = ekin + 0.5 * d * (v * v); }
+          UO(ic, 5) = UO(ic, 5) + emag + ekin;
+        } else { fprintf(stderr, "oracle(mhd 1-D): imposed boundary not restated\n"); abort(); }
+      }
+    }
+  }
+}
+
+/* upload_fine mhd/interpol_hydro.f90:5-68 + upl :233, NDIM=1, interpol_var=0.  The second half of upload_fine (:70-231,
+ * upl_left/upl_right: the normal face field of a leaf cell next to a refined cell takes the fine value) only touches B_x,
+ * which is one constant in a one-dimensional run; it is applied all the same. */
+void orc_mhd1_upload_fine(const orc_mhd_params* p, const orc_mesh* m, int ilevel, double* uold) {
+  if (ilevel == m->nlevelmax) return;
+  for (int a = 0; a < m->nactive[ilevel]; a++)
+    for (int ind = 0; ind < 2; ind++) {
+      const int ic = m->ncoarse + ind * m->ngridmax + m->active[ilevel][a];
+      const int gs = m->son[ic];
+      if (gs <= 0) continue;
+      const int c1 = m->ncoarse + 0 * m->ngridmax + gs, c2 = m->ncoarse + 1 * m->ngridmax + gs;
+      double getx = 0.0;
+      getx = getx + FMAX(UO(c1, 1), p->smallr);
+      getx = getx + FMAX(UO(c2, 1), p->smallr);
+      UO(ic, 1) = getx / 2.0;
+      for (int iv = 2; iv <= NV; iv++) {
+        if (iv <= 5 || iv > 5 + 1) {
+          getx = 0.0;
+          getx = getx + UO(c1, iv);
+          getx = getx + UO(c2, iv);
+          UO(ic, iv) = getx / 2.0;
+        }
+      }
+      UO(ic, NV + 2) = UO(ic, 7);
+      UO(ic, NV + 3) = UO(ic, 8);
+      getx = 0.0; getx = getx + UO(c1, 6); UO(ic, 6) = getx / 1.0;
+      getx = 0.0; getx = getx + UO(c2, NV + 1); UO(ic, NV + 1) = getx / 1.0;
+    }
+  /* :70-231: leaf cells whose neighbouring cell (same level) is refined */
+  for (int a = 0; a < m->nactive[ilevel]; a++) {
+    const int ig = m->active[ilevel][a];
+    const int gl = m->son[NBOR(m, ig, 1)], gr = m->son[NBOR(m, ig, 2)];
+    for (int ind = 0; ind < 2; ind++) {
+      const int ic = m->ncoarse + ind * m->ngridmax + ig;
+      if (m->son[ic] != 0) continue;
+      /* left neighbour cell: ind=0 -> cell 2 of the left oct, ind=1 -> cell 1 of this oct (iii/jjj tables :75-80) */
+      const int gL = ind == 0 ? gl : ig, cL = m->ncoarse + (ind == 0 ? 1 : 0) * m->ngridmax + gL;
+      if (gL > 0 && m->son[cL] > 0) UO(ic, 6) = UO(m->ncoarse + 1 * m->ngridmax + m->son[cL], NV + 1);      /* upl_left :516 */
+      const int gR = ind == 1 ? gr : ig, cR = m->ncoarse + (ind == 1 ? 0 : 1) * m->ngridmax + gR;
+      if (gR > 0 && m->son[cR] > 0) UO(ic, NV + 1) = UO(m->ncoarse + 0 * m->ngridmax + m->son[cR], 6);      /* upl_right :564 */
+    }
+  }
 }

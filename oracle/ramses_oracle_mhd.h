@@ -45,6 +45,15 @@ void orc_mhd_run_uniform(const orc_mhd_params*, const orc_mesh*, int ilevel, int
                          double* dt_hist, double* t_io, int nthreads);
 void orc_mhd_set_threads(int n);
 
+/* NDIM = 1 with AMR (tests/mhd/imhd-tube) */
+void orc_mhd1_interpol_cell(const orc_mesh*, int ind_cell, int ilevel, const double* uold, double* u2 /*[2][11]*/);
+void orc_mhd1_godunov_fine(const orc_mhd_params*, const orc_mesh*, int ilevel, int levelmin, int nvector, double dt, const double* uold, double* unew);
+void orc_mhdn_set_unew(const orc_mesh*, int ilevel, const double* uold, double* unew);
+void orc_mhdn_set_uold(const orc_mesh*, int ilevel, double* uold, const double* unew);
+double orc_mhd1_courant_fine(const orc_mhd_params*, const orc_mesh*, int ilevel, double dt_in, const double* uold);
+void orc_mhd1_make_boundary_hydro(const orc_mhd_params*, const orc_mesh*, int ilevel, double* uold);
+void orc_mhd1_upload_fine(const orc_mhd_params*, const orc_mesh*, int ilevel, double* uold);
+
 #ifdef __cplusplus
 }
 #endif
