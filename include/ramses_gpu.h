@@ -44,7 +44,7 @@ enum { RGPU_SCHEME_MUSCL = 0, RGPU_SCHEME_PLMDE = 1 };
  * path reads (hydro/read_hydro_params.f90:43-54).                            */
 typedef struct rgpu_params {
   int ndim;            /* NDIM 1,2,3                                          */
-  int nvar;            /* NVAR (= ndim+2; passive scalars not yet supported)  */
+  int nvar;            /* NVAR = ndim+2 (+ up to 2 passive scalars: NDIM=3, oct-batch kernel, i.e. after rgpu_set_amr) */
   int nvector;         /* NVECTOR: accepted for interface parity, unused      */
   int slope_type;      /* 0,1,2,3,7,8 (+4,5,6 in 1-D)                          */
   int niter_riemann;   /* Newton iterations of riemann='exact'                */

@@ -123,15 +123,18 @@ struct AmrSweepArgs {
   double dt, dx, inv_dx;
   int dx_pow2, interpol_type;
   double difmag;          // hydro_parameters.f90:81
+  int nps;                // passive scalars: nvar - (ndim+2)
 };
 
 constexpr int AMR_TPO = 64;   // threads per oct
 constexpr int AMR_OPB = 1;    // octs per block (26 KB of static shared memory per oct in 3-D)
 
 // DIF: artificial diffusion difmag>0 (cmpdivu hydro/uplmde.f90:702 + consup :769, called from unsplit hydro/umuscl.f90:160-168)
-template <int NDIM, int RIEMANN, bool DIF>
+// NPS: passive scalars (NVAR = NDIM+2+NPS): q = u/rho in ctoprim (umuscl.f90:948-961), advected in trace (:680-704), carried
+// through cmpflxm like the transverse velocities (:781-789,:835-842), every solver upwinds them with the mass flux
+template <int NDIM, int RIEMANN, bool DIF, int NPS = 0>
 __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const AmrSweepArgs a) {
-  constexpr int NV = NDIM + 2, T = 1 << NDIM, TW = 2 * NDIM;
+  constexpr int NV = NDIM + 2 + NPS, NH = NDIM + 2, T = 1 << NDIM, TW = 2 * NDIM;
   constexpr int N3 = (NDIM == 1) ? 3 : (NDIM == 2 ? 9 : 27);
   constexpr int HY = NDIM > 1, HZ = NDIM > 2;
   constexpr int PJ = HY ? 6 : 1, PK = HZ ? 6 : 1;          // patch extents (i: 6)
@@ -269,6 +272,8 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
       if (NDIM > 1) q[2] = q[2] + 0.0;
       if (NDIM > 2) q[3] = q[3] + 0.0;
 #pragma unroll
+      for (int n = NH; n < NV; n++) q[n] = u[n] * oneoverrho;
+#pragma unroll
       for (int n = 0; n < NV; n++) s.q[n][pc] = q[n];
     }
   __syncthreads();
@@ -367,7 +372,7 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
         }
       }
       double s0[NV];
-      trace_sources<NDIM>(q, dq, rcp_rn(q[0]), s0, P);
+      trace_sources<NDIM, NPS>(q, dq, rcp_rn(q[0]), s0, P);
 #pragma unroll
       for (int d = 0; d < NDIM; d++) {
 #pragma unroll
@@ -403,10 +408,14 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
       qr[0] = s.qp[d][0][tR]; qr[1] = s.qp[d][ln][tR]; qr[2] = s.qp[d][NDIM + 1][tR];
       if (NDIM > 1) { ql[3] = s.qm[d][lt1 % NV][tL]; qr[3] = s.qp[d][lt1 % NV][tR]; }
       if (NDIM > 2) { ql[4 % NV] = s.qm[d][lt2 % NV][tL]; qr[4 % NV] = s.qp[d][lt2 % NV][tR]; }
-      riemann<NDIM, RIEMANN>(ql, qr, fg, P);
+#pragma unroll
+      for (int n = NH; n < NV; n++) { ql[n] = s.qm[d][n][tL]; qr[n] = s.qp[d][n][tR]; }
+      riemann<NDIM, RIEMANN, NPS>(ql, qr, fg, P);
       fl[0] = fg[0]; fl[ln] = fg[1]; fl[NDIM + 1] = fg[2];
       if (NDIM > 1) fl[lt1 % NV] = fg[3];
       if (NDIM > 2) fl[lt2 % NV] = fg[4 % NV];
+#pragma unroll
+      for (int n = NH; n < NV; n++) fl[n] = fg[n];
       const int pR = (c3[0] + 1) + 6 * ((HY ? c3[1] + 1 : 0) + PJ * (HZ ? c3[2] + 1 : 0));
       const int pL = (cl[0] + 1) + 6 * ((HY ? cl[1] + 1 : 0) + PJ * (HZ ? cl[2] + 1 : 0));
       const bool masked = s.ok[pL] || s.ok[pR];
@@ -516,6 +525,21 @@ __global__ void amr_copy_octs_kernel(const double* __restrict__ src, double* __r
   const size_t c = (size_t)iv * ncell + ncoarse + (size_t)ind * ngridmax + igrid[o] - 1;
   dst[c] = src[c];
 }
+// set_uold, passive scalars only (hydro/godunov_fine.f90:176-190): cells whose density crosses the floor smallr keep their
+// concentration -- inflow into a floored cell / outflow below the floor
+__global__ void amr_scalar_floor_kernel(const double* __restrict__ uold, double* __restrict__ unew, const int* __restrict__ igrid, int n,
+                                        int ncoarse, int ngridmax, long long ncell, int T, int nhydro, int nvar, double smallr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * T) return;
+  const int o = i % n, ind = i / n;
+  const size_t c = (size_t)ncoarse + (size_t)ind * ngridmax + igrid[o] - 1;
+  const double dold = uold[c], dnew = unew[c];
+  if (dold < smallr && dnew > dold) {
+    for (int iv = nhydro; iv < nvar; iv++) unew[(size_t)iv * ncell + c] = uold[(size_t)iv * ncell + c] * fmax(dnew, smallr) / smallr;
+  } else if (dnew < smallr && dold > dnew) {
+    for (int iv = nhydro; iv < nvar; iv++) unew[(size_t)iv * ncell + c] = uold[(size_t)iv * ncell + c] * smallr / fmax(dold, smallr);
+  }
+}
 // ghost-oct exchange buffers on the mirrored arrays: all variables and all cells of the listed octs in one message
 // (make_virtual_fine_dp / make_virtual_reverse_dp, amr/virtual_boundaries.f90:373,693)
 __global__ void amr_pack_kernel(const double* __restrict__ u, const int* __restrict__ igrid, int n, int ncoarse, int ngridmax,
@@ -622,8 +646,14 @@ __global__ void amr_courant_kernel(const double* __restrict__ u, const AmrTree t
 template <int NDIM, int RIEMANN>
 cudaError_t launch_amr_godfine(const AmrSweepArgs& a, cudaStream_t st) {
   const int nb = (a.nact + AMR_OPB - 1) / AMR_OPB;
-  if (a.difmag > 0.0) amr_godfine_kernel<NDIM, RIEMANN, true><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);
-  else amr_godfine_kernel<NDIM, RIEMANN, false><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);
+  if (a.nps == 0) {
+    if (a.difmag > 0.0) amr_godfine_kernel<NDIM, RIEMANN, true><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);
+    else amr_godfine_kernel<NDIM, RIEMANN, false><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);
+  } else if (NDIM == 3 && a.nps == 1) {      // passive scalars: NDIM=3, up to 2, without difmag (checked by rgpu_init)
+    amr_godfine_kernel<NDIM, RIEMANN, false, (NDIM == 3 ? 1 : 0)><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);
+  } else if (NDIM == 3 && a.nps == 2) {
+    amr_godfine_kernel<NDIM, RIEMANN, false, (NDIM == 3 ? 2 : 0)><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);
+  } else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

@@ -710,6 +710,7 @@ int amr_godunov(AmrLevel& A, int ilevel, double dt) {
   a.dx_pow2 = (std::frexp(A.dx, &ex) == 0.5) ? 1 : 0;
   a.interpol_type = G.interpol_type;
   a.difmag = G.p.difmag;
+  a.nps = G.p.nvar - (G.p.ndim + 2);
   cudaError_t e;
   if (G.p.ndim == 1) e = dispatch_amr_nd<1>(G.p.riemann, a, G.stream);
   else if (G.p.ndim == 2) e = dispatch_amr_nd<2>(G.p.riemann, a, G.stream);
@@ -849,7 +850,12 @@ int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device) {
     if (!(p->slope_type == 0 || p->slope_type == 1 || p->slope_type == 2 || p->slope_type == 3 || p->slope_type == 7 || p->slope_type == 8))
       return fail(RGPU_EINVAL, "Unknown slope type %d", p->slope_type);                                      // mhd/umuscl.f90:2562
   } else {
-  if (p->nvar != p->ndim + 2) return fail(RGPU_EUNSUPPORTED, "nvar=%d: passive scalars / NENER not supported (need nvar=ndim+2)", p->nvar);
+  {
+    const int nps = p->nvar - (p->ndim + 2);
+    if (nps < 0) return fail(RGPU_EINVAL, "nvar=%d < ndim+2", p->nvar);
+    if (nps > 0 && !(p->ndim == 3 && nps <= 2 && !(p->difmag > 0.0)))
+      return fail(RGPU_EUNSUPPORTED, "nvar=%d: passive scalars are built for NDIM=3, at most 2 of them, difmag=0 (NENER not supported)", p->nvar);
+  }
   if (p->riemann < 0 || p->riemann > 4) return fail(RGPU_EINVAL, "unknown Riemann solver %d", p->riemann);
   }
   if (p->scheme != RGPU_SCHEME_MUSCL) return fail(RGPU_EUNSUPPORTED, "scheme='plmde' not supported");
@@ -1141,7 +1147,8 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
     Level& L = G.lev[ilevel];
     if (L.bound) free_level(L);
     const char* env = getenv("RGPU_AMR_DENSE");
-    const bool want = !(env && atoi(env) == 0) && G.p.ndim == 3 && !G.p.mhd && !(G.p.difmag > 0.0) && A.nent == 0 && ngrid_active > 0;
+    const bool want = !(env && atoi(env) == 0) && G.p.ndim == 3 && !G.p.mhd && !(G.p.difmag > 0.0) && G.p.nvar == G.p.ndim + 2 && A.nent == 0 &&
+                      ngrid_active > 0;
     if (want) {
       rc = plan_level(L, ilevel, ngrid_active, igrid_active, ncpu, ngrid_recv, igrid_recv, ngrid_emit, igrid_emit, nboundary,
                       boundary_type, ngrid_bound, igrid_bound);
@@ -1159,9 +1166,9 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
     }
     return RGPU_OK;
   }
-  if (G.p.difmag > 0.0)
-    return fail(RGPU_EUNSUPPORTED, "difmag>0 (cmpdivu/consup) is built in the oct-batch kernel only: call rgpu_set_amr(1, interpol_type, 0) after rgpu_init "
-                                   "(works for levelmin=levelmax runs too)");
+  if (G.p.difmag > 0.0 || (!G.p.mhd && G.p.nvar != G.p.ndim + 2))
+    return fail(RGPU_EUNSUPPORTED, "difmag>0 (cmpdivu/consup) and passive scalars (nvar>ndim+2) are built in the oct-batch kernel only: call "
+                                   "rgpu_set_amr(1, interpol_type, 0) after rgpu_init (works for levelmin=levelmax runs too)");
   Level& L = G.lev[ilevel];
   if (L.bound) free_level(L);
   {
@@ -1317,7 +1324,18 @@ int rgpu_godunov_fine_dev(int ilevel, double dt) {
 }
 
 int rgpu_set_uold(int ilevel) {
-  if (G.amr) { AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc; return amr_copy(*A, G.d_unew, G.d_uold); }
+  if (G.amr) {
+    AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
+    const int nps = G.p.nvar - (G.p.ndim + 2);
+    if (nps > 0 && A->nact > 0) {   // passive-scalar fix for floored densities, before the copy (godunov_fine.f90:176-190)
+      const int n = A->nact * T_();
+      amr_scalar_floor_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_unew, A->d_active, A->nact, G.ncoarse, G.ngridmax, G.ncell, T_(),
+                                                                  G.p.ndim + 2, G.p.nvar, G.p.smallr);
+      CUDA_OK(cudaGetLastError());
+      A->launches++;
+    }
+    return amr_copy(*A, G.d_unew, G.d_uold);
+  }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (!L->unew_valid) return fail(RGPU_EINVAL, "set_uold before set_unew/godunov_fine");
   // uold <- unew on the active cells (godunov_fine.f90:193-197); shells keep their uold values

@@ -47,10 +47,10 @@ class Case:
     """One run set-up: oracle mesh + params + the Fortran-side arrays (AmrCommons)."""
 
     def __init__(self, ndim, level, riemann="hllc", slope_type=1, bound=(0,) * 6, order=0, seed=1, boxlen=1.0,
-                 gamma=1.4, courant_factor=0.8, niter_riemann=10, slope_theta=1.5, nvector=32):
-        self.ndim, self.level, self.nvar = ndim, level, ndim + 2
+                 gamma=1.4, courant_factor=0.8, niter_riemann=10, slope_theta=1.5, nvector=32, nvar=None):
+        self.ndim, self.level, self.nvar = ndim, level, (nvar or ndim + 2)      # nvar > ndim+2: passive scalars
         self.mesh = orc.Mesh(ndim, level, bound, order, seed)
-        self.p = orc.make_params(ndim=ndim, riemann=riemann, slope_type=slope_type, boxlen=boxlen, gamma=gamma,
+        self.p = orc.make_params(ndim=ndim, nvar=self.nvar, riemann=riemann, slope_type=slope_type, boxlen=boxlen, gamma=gamma,
                                  courant_factor=courant_factor, niter_riemann=niter_riemann, slope_theta=slope_theta,
                                  nvector=nvector)
         self.riemann, self.slope_type = riemann, slope_type

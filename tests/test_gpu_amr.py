@@ -280,3 +280,104 @@ def test_amr_full_size_conservation_levelmin7_levelmax10():
         assert abs(t1[iv] - t0[iv]) < 1e-13, (iv, t0, t1)
     # the solution moved
     assert np.abs(a.uold - u0).max() > 1e-3
+
+
+@pytest.mark.parametrize("riemann", ["llf", "hll", "hllc", "acoustic"])
+def test_passive_scalars_uniform_grid_bitwise(riemann):
+    """NVAR = 7 (two passive scalars) on a levelmin=levelmax run through the oct-batch kernel: three level steps in amr_step
+    order (courant, set_unew, godunov_fine, set_uold incl. the floor fix, boundaries) == the oracle."""
+    from helpers import Case, smooth_state
+    from ramses_b200.hydro import HydroGPU
+    n = 8
+    u7 = np.zeros((7, n, n, n))
+    u7[:5] = smooth_state(3, n)
+    u7[5] = 0.3 * u7[0]
+    u7[6] = u7[0] * (0.5 + 0.4 * np.sin(2 * np.pi * (np.arange(n) + 0.5) / n))[None, :, None]
+    c = Case(3, 3, riemann=riemann, slope_type=2, nvar=7, bound=(1, 1, 2, 2, 0, 0))
+    c.init_dense(u7)
+    ref, dts_ref = c.oracle_steps(3)
+    a = c.amr_commons()
+    h = HydroGPU(a, amr_mode=True)
+    for l in (1, 2, 3):
+        h.bind_level(l)
+    h.upload_state(0)
+    h.make_boundary_hydro(3)
+    dts = []
+    for _ in range(3):
+        a.dtnew[3] = a.boxlen / a.smallc
+        dts.append(h.courant_fine(3))
+        h.set_unew(3); h.godunov_fine_dev(3); h.set_uold(3); h.make_boundary_hydro(3)
+    h.download_state(0)
+    h.finalize()
+    act = c.active_cells()
+    assert np.array_equal(np.array(dts), dts_ref)
+    assert np.array_equal(a.uold[:, act], ref.reshape(7, -1)[:, act])
+
+
+def test_passive_scalars_refined_mesh_bitwise():
+    """Two passive scalars on the 3-level nested tree (prolongation, refluxing and restriction of all 7 variables)."""
+    from oracle.amr import AmrRun
+    from ramses_b200.tree import build_nested_tree, cell_centers
+    from ramses_b200.hydro import HydroGPU, amr_step
+    levelmin, levelmax = 4, 6
+    a = build_nested_tree(levelmin, levelmax, half_width=3, boxlen=1.0, nvar=7)
+    a.gamma, a.courant_factor, a.slope_type, a.riemann = 1.4, 0.8, 1, "hllc"
+    for l in range(levelmin, levelmax + 1):
+        ig, cc = cell_centers(a, l)
+        for ind in range(8):
+            x, y, z = cc[ind][:, 0], cc[ind][:, 1], cc[ind][:, 2]
+            r2 = (x - 0.5) ** 2 + (y - 0.5) ** 2 + (z - 0.5) ** 2
+            u = np.zeros((7, len(x)))
+            u[0] = 1.0 + 0.5 * np.exp(-r2 / 0.01)
+            u[1] = 0.1 * u[0] * np.sin(2 * np.pi * y)
+            u[4] = (0.1 + 2.0 * np.exp(-r2 / 0.005)) / 0.4 + 0.5 * u[1] ** 2 / u[0]
+            u[5] = u[0] * (0.2 + 0.1 * np.cos(2 * np.pi * x))
+            u[6] = u[0] * np.exp(-r2 / 0.02)
+            a.uold[:, a.ncoarse + ind * a.ngridmax + ig - 1] = u
+    h = HydroGPU(a, amr_mode=True, interpol_type=1)
+    for l in range(1, levelmax + 1):
+        h.bind_level(l)
+    h.upload_state(0)
+    for l in range(levelmax - 1, 0, -1):
+        h.upload_fine(l)
+    h.download_state(0)
+    u0 = a.uold.copy()
+    nsub = [1] * (levelmin + 1) + [2] * 64
+    dtnew = {l: 0.0 for l in range(0, levelmax + 2)}
+    dtold = {l: 0.0 for l in range(0, levelmax + 2)}
+    amr_step(h, levelmin, 1, levelmin, nsub, dtnew, dtold)
+    h.download_state(0)
+    h.finalize()
+    r = AmrRun(3, levelmin, levelmax, (0,) * 6, 1.0, nsubcycle=[1, 2, 2], ngridmax=a.ngridmax, riemann="hllc", slope_type=1,
+               interpol_type=1, tout=[1e9])
+    r.p.nvar = 7; r.nvar = 7
+    r.uold = u0.ravel().copy(); r.unew = np.zeros_like(r.uold)
+    r.son[1:] = a.son; r.father[1:] = a.father; r.nbor[:, 1:] = a.nbor
+    for l in range(1, levelmax + 1):
+        r.active[l] = [int(g) for g in a.active[l]]
+    r.push_all()
+    r.static = True
+    r.amr_step(levelmin, 1)
+    ref = r.uold.reshape(7, -1)
+    assert dtnew[levelmin] == r.dtnew[levelmin]
+    cells = np.concatenate([[a.ncoarse + ind * a.ngridmax + int(g) - 1 for g in a.active[l] for ind in range(8)] for l in range(1, levelmax + 1)])
+    assert np.array_equal(a.uold[:, cells], ref[:, cells]), float(np.abs(a.uold[:, cells] - ref[:, cells]).max())
+    assert np.abs(a.uold[5:, cells] - u0[5:, cells]).max() > 1e-4
+
+
+def test_passive_scalars_rejected_where_not_built():
+    from helpers import Case
+    from ramses_b200 import lib as _l
+    from ramses_b200.hydro import HydroGPU
+    c = Case(3, 2, nvar=7)
+    a = c.amr_commons()
+    h = HydroGPU(a)                      # fused dense path: refuses at bind time, pointing to rgpu_set_amr
+    with pytest.raises(_l.RgpuError):
+        h.bind_level(2)
+    h.finalize()
+    c = Case(3, 2, nvar=9)
+    with pytest.raises(_l.RgpuError):
+        HydroGPU(c.amr_commons(), amr_mode=True)
+    c = Case(2, 2, nvar=5)
+    with pytest.raises(_l.RgpuError):
+        HydroGPU(c.amr_commons(), amr_mode=True)
