@@ -113,3 +113,84 @@ def test_tree_builder_matches_oracle_builder():
         na, nm = split(a.nbor[j, :n], a.ngridmax, a.ncoarse), split(m.nbor()[j, 1:n + 1], m.ngridmax, m.ncoarse)
         assert np.array_equal(na[0], nm[0]) and np.array_equal(na[1], nm[1])
     assert np.array_equal(a.active[4], m.active(4))
+
+
+def test_nested_tree_fabricator_invariants():
+    """ramses_b200.tree.build_nested_tree: son/father/nbor are mutually consistent, the refined cubes are nested 2:1 and the
+    oracle's neighbour walk (get3cubefather) finds an existing father cell for every neighbour of every oct."""
+    import ctypes as C
+    from oracle import orc
+    from ramses_b200.tree import build_nested_tree, leaf_cells
+    levelmin, levelmax, hw = 4, 6, 3
+    a = build_nested_tree(levelmin, levelmax, half_width=hw)
+    assert [len(a.active[l]) for l in range(1, levelmax + 1)] == [1, 8, 64, 512, (2 * hw) ** 3, (2 * hw) ** 3]
+    for l in range(2, levelmax + 1):
+        ig = a.active[l].astype(np.int64)
+        f = a.father[ig - 1].astype(np.int64)
+        assert (a.son[f - 1] == ig).all()                                   # son(father(igrid)) == igrid
+        for d in range(3):                                                   # nbor(nbor) symmetry through the sons
+            left, right = a.nbor[2 * d, ig - 1], a.nbor[2 * d + 1, ig - 1]
+            assert (left > 0).all() and (right > 0).all()
+    leaves = sum(len(leaf_cells(a, l)) for l in range(1, levelmax + 1))
+    assert leaves == (8 * 512 - (2 * hw) ** 3) + 7 * (2 * hw) ** 3 + 8 * (2 * hw) ** 3
+    # the oracle's tree walk agrees with the fabricated arrays
+    L = orc.lib()
+    L.orc_mesh_new.restype = C.POINTER(orc.MeshS)
+    L.orc_mesh_new.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]
+    m = L.orc_mesh_new(3, (C.c_int * 6)(0, 0, 0, 0, 0, 0), a.ngridmax, levelmax)
+    s = m.contents
+    np.ctypeslib.as_array(s.son, shape=(s.ncell + 1,))[1:] = a.son
+    np.ctypeslib.as_array(s.father, shape=(s.ngridmax + 1,))[1:] = a.father
+    np.ctypeslib.as_array(s.nbor, shape=(6, s.ngridmax + 1))[:, 1:] = a.nbor
+    nfc = (C.c_int * 27)()
+    for l in range(2, levelmax + 1):
+        for g in a.active[l][:: max(1, len(a.active[l]) // 50)]:
+            L.orc_get3cubefather(m, int(a.father[g - 1]), l, nfc, None)
+            assert all(c > 0 for c in nfc)
+            assert nfc[13] == a.father[g - 1]
+
+
+def test_xbound_tree_matches_the_oracle_mesh_plan():
+    """ramses_b200.tree.build_uniform_tree(xbound=...) (3x1x1 coarse grid, boundary octs at the x ends, namelist/tube_mhd.nml
+    BOUNDARY_PARAMS) is planned as the same dense box as the oracle's mesh with the same boundary types."""
+    from helpers import MhdCase
+    from ramses_b200.hydro import plan_level
+    from ramses_b200.tree import build_uniform_tree
+    a = build_uniform_tree(3, 4, mhd=True, xbound=(2, 2), boxlen=2.0)
+    ia, _ = plan_level(a, 4)
+    b = MhdCase(4, bound=(2, 2, 0, 0, 0, 0), boxlen=2.0).amr_commons()
+    ib, _ = plan_level(b, 4)
+    assert ia.dense == 1 and ib.dense == 1
+    for f in ("ncell_box", "own_lo", "own_hi", "wrap"):
+        assert list(getattr(ia, f)) == list(getattr(ib, f))
+    assert ia.nslot == ib.nslot and a.boundary_type == b.boundary_type == [11, 12]
+    assert a.uold.shape[0] == 11 and (a.icoarse_min, a.icoarse_max) == (1, 1)
+
+
+def test_host_amr_step_mirror_call_order():
+    """ramses_b200.hydro.amr_step issues the per-level calls in the order of amr/amr_step.f90 (recursion, sub-cycling 1,2,2)."""
+    from ramses_b200.hydro import amr_step
+
+    class Rec:
+        def __init__(self, a):
+            self.a, self.log = a, []
+
+        def __getattr__(self, name):
+            def f(l):
+                self.log.append((name, l))
+                return 0.125 / l if name == "courant_fine" else None
+            return f
+
+    class A:
+        pass
+    a = A()
+    a.active = {3: [1], 4: [1], 5: [1]}
+    a.nlevelmax, a.boxlen, a.smallc, a.dtnew = 5, 1.0, 1e-10, {}
+    h = Rec(a)
+    dtnew, dtold = {l: 0.0 for l in range(8)}, {l: 0.0 for l in range(8)}
+    amr_step(h, 3, 1, 3, [1, 1, 1, 2, 2, 2, 2], dtnew, dtold)
+    god = [l for n, l in h.log if n == "godunov_fine_dev"]
+    assert god == [5, 5, 4, 5, 5, 4, 3]                               # post-order: 2 fine steps per coarser step
+    per = [n for n, l in h.log if l == 3]
+    assert per == ["courant_fine", "set_unew", "godunov_fine_dev", "set_uold", "upload_fine", "make_boundary_hydro"]
+    assert dtnew[4] <= dtnew[3] / 2 + 1e-18 and dtnew[5] <= dtnew[4] / 2 + 1e-18
