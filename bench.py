@@ -461,7 +461,8 @@ def main():
                 "traffic": traffic, "kernel": ("MHD sweep: 6 kernels (prim, efield, trace, flux<%s>, emf<%s>, update)" % (w["riemann"], w["riemann2d"]))
                 if mhd else "sweep_dense_kernel<3,%s>" % w["riemann"], "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": bpc * ncell_rank, "peak_source": peak_src,
-                "note": "FP64 issue rate, not HBM, is the binding roof for this kernel (DESIGN.md)"}
+                "note": "FP64 issue rate, not HBM, is the binding roof for this kernel (DESIGN.md)"
+                        + ("; kernel_ms spans the six passes of the sweep, traffic is the dominant pass (flux)" if mhd else "")}
 
     # end-to-end through the reference-facing call godunov_fine(ilevel) on HOST arrays (H2D + sweep + D2H per step)
     h.download_state(level)
