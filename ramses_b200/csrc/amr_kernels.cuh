@@ -112,6 +112,56 @@ __device__ void amr_interpol_var(const double* a, int interpol_type, double* u2)
   }
 }
 
+// get3cubefather (amr/nbors_utils.f90:5-194, get3cubepos :199): the 3^ndim father cells around the father cell of an oct
+template <int NDIM>
+__device__ __forceinline__ void amr_get3cubefather(const AmrTree& t, int igrid, int ilevel, int* nfc /*[3^ndim]*/, int* ng /*[8]*/) {
+  constexpr int N3 = (NDIM == 1) ? 3 : (NDIM == 2 ? 9 : 27);
+  constexpr int HY = NDIM > 1, HZ = NDIM > 2;
+
+    const int fc = t.father[igrid];
+    if (ilevel == 1) {
+      const int nxny = t.nx * t.ny;
+      const int iz = (fc - 1) / nxny, iy = (fc - 1 - iz * nxny) / t.nx, ix = fc - 1 - iy * t.nx - iz * nxny;
+      for (int j = 0; j < N3; j++) {
+        int o[3] = {j % 3 - 1, (j / 3) % 3 - 1, (j / 9) % 3 - 1};
+        int iix = ix + o[0], iiy = iy, iiz = iz;
+        if (iix < 0) iix = t.nx - 1; if (iix > t.nx - 1) iix = 0;
+        if (NDIM > 1) { iiy = iy + o[1]; if (iiy < 0) iiy = t.ny - 1; if (iiy > t.ny - 1) iiy = 0; }
+        if (NDIM > 2) { iiz = iz + o[2]; if (iiz < 0) iiz = t.nz - 1; if (iiz > t.nz - 1) iiz = 0; }
+        nfc[j] = 1 + iix + iiy * t.nx + iiz * nxny;
+      }
+    } else {
+      const int pos = (fc - t.ncoarse - 1) / t.ngridmax;
+      const int gf = fc - t.ncoarse - pos * t.ngridmax;
+      const int dirx = (pos & 1) ? 2 : 1, diry = ((pos >> 1) & 1) ? 4 : 3, dirz = ((pos >> 2) & 1) ? 6 : 5;
+      for (int kk = 0; kk <= HZ; kk++) {
+        int g1 = gf;
+        if (kk > 0 && gf > 0) g1 = t.son[amr_nbor(t, gf, dirz)];
+        for (int jj = 0; jj <= HY; jj++) {
+          int g2 = g1;
+          if (jj > 0 && g1 > 0) g2 = t.son[amr_nbor(t, g1, diry)];
+          for (int ii = 0; ii <= 1; ii++) {
+            int g3 = g2;
+            if (ii > 0 && g2 > 0) g3 = t.son[amr_nbor(t, g2, dirx)];
+            ng[ii + 2 * jj + 4 * kk] = g3;
+          }
+        }
+      }
+      const int c[3] = {pos & 1, (pos >> 1) & 1, (pos >> 2) & 1};
+      for (int j = 0; j < N3; j++) {
+        const int o[3] = {j % 3 - 1, (j / 3) % 3 - 1, (j / 9) % 3 - 1};
+        int gi = 0, cp = 0;
+        for (int d = 0; d < NDIM; d++) {
+          const int tt = c[d] + o[d];
+          gi += ((tt < 0 || tt > 1) ? 1 : 0) << d;
+          cp += (tt & 1) << d;
+        }
+        const int g = ng[gi];
+        nfc[j] = g > 0 ? amr_cell(t, cp, g) : 0;
+      }
+    }
+}
+
 struct AmrSweepArgs {
   AmrTree t;
   const int* active;      // active(ilevel)%igrid
@@ -124,6 +174,10 @@ struct AmrSweepArgs {
   int dx_pow2, interpol_type;
   double difmag;          // hydro_parameters.f90:81
   int nps;                // passive scalars: nvar - (ndim+2)
+  // patch mode: the level's own cells are updated by the dense kernel; this launch only evaluates the scaled, masked fluxes
+  // through the outer faces of the octs at the surface of the patch (coarse refluxing)
+  int flux_only;
+  const int* rflux_index; // list position -> oct index of rflux (NULL: identity)
 };
 
 constexpr int AMR_TPO = 64;   // threads per oct
@@ -166,48 +220,7 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
 
   // ---- get3cubefather (amr/nbors_utils.f90:5-194, get3cubepos :199) ----
   if (live && tl == 0) {
-    const int fc = t.father[igrid];
-    if (a.ilevel == 1) {
-      const int nxny = t.nx * t.ny;
-      const int iz = (fc - 1) / nxny, iy = (fc - 1 - iz * nxny) / t.nx, ix = fc - 1 - iy * t.nx - iz * nxny;
-      for (int j = 0; j < N3; j++) {
-        int o[3] = {j % 3 - 1, (j / 3) % 3 - 1, (j / 9) % 3 - 1};
-        int iix = ix + o[0], iiy = iy, iiz = iz;
-        if (iix < 0) iix = t.nx - 1; if (iix > t.nx - 1) iix = 0;
-        if (NDIM > 1) { iiy = iy + o[1]; if (iiy < 0) iiy = t.ny - 1; if (iiy > t.ny - 1) iiy = 0; }
-        if (NDIM > 2) { iiz = iz + o[2]; if (iiz < 0) iiz = t.nz - 1; if (iiz > t.nz - 1) iiz = 0; }
-        s.nfc[j] = 1 + iix + iiy * t.nx + iiz * nxny;
-      }
-    } else {
-      const int pos = (fc - t.ncoarse - 1) / t.ngridmax;
-      const int gf = fc - t.ncoarse - pos * t.ngridmax;
-      const int dirx = (pos & 1) ? 2 : 1, diry = ((pos >> 1) & 1) ? 4 : 3, dirz = ((pos >> 2) & 1) ? 6 : 5;
-      for (int kk = 0; kk <= HZ; kk++) {
-        int g1 = gf;
-        if (kk > 0 && gf > 0) g1 = t.son[amr_nbor(t, gf, dirz)];
-        for (int jj = 0; jj <= HY; jj++) {
-          int g2 = g1;
-          if (jj > 0 && g1 > 0) g2 = t.son[amr_nbor(t, g1, diry)];
-          for (int ii = 0; ii <= 1; ii++) {
-            int g3 = g2;
-            if (ii > 0 && g2 > 0) g3 = t.son[amr_nbor(t, g2, dirx)];
-            s.ng[ii + 2 * jj + 4 * kk] = g3;
-          }
-        }
-      }
-      const int c[3] = {pos & 1, (pos >> 1) & 1, (pos >> 2) & 1};
-      for (int j = 0; j < N3; j++) {
-        const int o[3] = {j % 3 - 1, (j / 3) % 3 - 1, (j / 9) % 3 - 1};
-        int gi = 0, cp = 0;
-        for (int d = 0; d < NDIM; d++) {
-          const int tt = c[d] + o[d];
-          gi += ((tt < 0 || tt > 1) ? 1 : 0) << d;
-          cp += (tt & 1) << d;
-        }
-        const int g = s.ng[gi];
-        s.nfc[j] = g > 0 ? amr_cell(t, cp, g) : 0;
-      }
-    }
+    amr_get3cubefather<NDIM>(t, igrid, a.ilevel, s.nfc, s.ng);
     for (int j = 0; j < N3; j++) s.gnb[j] = s.nfc[j] > 0 ? t.son[s.nfc[j]] : 0;
   }
   __syncthreads();
@@ -451,7 +464,7 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
   __syncthreads();
   // ---- conservative update of the oct's own cells (:751-792), x then y then z ----
   if (live) {
-    for (int e = tl; e < T * NV; e += AMR_TPO) {
+    for (int e = tl; e < (a.flux_only ? 0 : T * NV); e += AMR_TPO) {
       const int is = e % T, n = e / T;
       const int c3[3] = {1 + (is & 1), 1 + ((is >> 1) & 1), 1 + ((is >> 2) & 1)};
       const int ic = amr_cell(t, is, igrid);
@@ -482,7 +495,8 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
         f += c * mul;
         mul *= ext;
       }
-      a.rflux[(((size_t)io * TW + side) * NSF + fs) * NV + n] = s.flux[d][n][f];
+      const int ro = a.rflux_index ? a.rflux_index[io] : io;
+      a.rflux[(((size_t)ro * TW + side) * NSF + fs) * NV + n] = s.flux[d][n][f];
     }
   }
 }
@@ -641,6 +655,40 @@ __global__ void amr_courant_kernel(const double* __restrict__ u, const AmrTree t
       part[0 * nb + blockIdx.x] = v0; part[1 * nb + blockIdx.x] = v1; part[2 * nb + blockIdx.x] = v2; part[3 * nb + blockIdx.x] = v3;
     }
   }
+}
+
+// ---- patch mode (a refined level whose octs form a Cartesian box): ghost shell of the level store ------------------------
+// father cell (level l-1) of every empty shell slot around the box: the neighbours of the surface octs that have no son
+__global__ void amr_shell_father_kernel(const AmrTree t, const int* __restrict__ active, const int* __restrict__ act_slot, int nact, int ilevel,
+                                        int nox, int noy, long long nslot, int* __restrict__ shell_father) {
+  const int io = blockIdx.x * blockDim.x + threadIdx.x;
+  if (io >= nact) return;
+  int nfc[27], ng[8];
+  amr_get3cubefather<3>(t, active[io], ilevel, nfc, ng);
+  const long long s0 = act_slot[io];
+  for (int j = 0; j < 27; j++) {
+    if (nfc[j] <= 0 || t.son[nfc[j]] > 0) continue;
+    const long long s = s0 + (j % 3 - 1) + (long long)nox * ((j / 3) % 3 - 1) + (long long)nox * noy * (j / 9 - 1);
+    if (s >= 0 && s < nslot) shell_father[s] = nfc[j];     // every writer stores the same value
+  }
+}
+// prolongation of the shell octs from level l-1 (interpol_hydro, hydro/interpol_hydro.f90:268) into the level store
+__global__ void amr_fill_shell_kernel(const AmrTree t, const double* __restrict__ uold, double* __restrict__ u, const int* __restrict__ shell_father,
+                                      long long nslot, int ilevel, int nvar, int interpol_type) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nslot * nvar) return;
+  const long long s = i % nslot;
+  const int n = (int)(i / nslot);
+  const int fc = shell_father[s];
+  if (fc <= 0) return;
+  int fa[7];
+  amr_getnborfather<3>(t, fc, ilevel, fa);
+  double av[7], u2[8];
+#pragma unroll
+  for (int j = 0; j < 7; j++) av[j] = uold[(size_t)n * t.ncell + fa[j] - 1];
+  amr_interpol_var<3>(av, interpol_type, u2);
+#pragma unroll
+  for (int is = 0; is < 8; is++) u[((size_t)n * 8 + is) * nslot + s] = u2[is];
 }
 
 template <int NDIM, int RIEMANN>

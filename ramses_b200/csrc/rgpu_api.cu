@@ -121,7 +121,11 @@ struct AmrLevel {
   double* d_part = nullptr; double* d_out = nullptr; double* d_dt = nullptr;
   long long launches = 0;
   double dx = 0;
-  bool dense_sweep = false;           // fully refined box without coarse refluxes: godunov_fine runs the dense kernel (AMR variant)
+  bool dense_sweep = false;           // the level is a Cartesian box: godunov_fine runs the dense kernel (AMR variant)
+  bool patch = false;                 // ... with a prolongated ghost shell and coarse refluxes (refined patch)
+  int nsurf = 0;                      // octs at the surface of the patch (they own the refluxed faces)
+  int *d_surf_igrid = nullptr, *d_surf_io = nullptr, *d_act_slot = nullptr, *d_shell_father = nullptr;
+  std::vector<int> h_surf_io;
 };
 
 struct Context {
@@ -562,6 +566,7 @@ AmrTree amr_tree() {
 void free_amr_level(AmrLevel& A) {
   cudaFree(A.d_active); cudaFree(A.d_rflux); cudaFree(A.d_rcell); cudaFree(A.d_rstart); cudaFree(A.d_rsrc);
   cudaFree(A.d_part); cudaFree(A.d_out); cudaFree(A.d_dt);
+  cudaFree(A.d_surf_igrid); cudaFree(A.d_surf_io); cudaFree(A.d_act_slot); cudaFree(A.d_shell_father);
   for (auto& r : A.regions) cudaFree(r.d_igrid);
   for (auto& p : A.peers) { cudaFree(p.d_recv); cudaFree(p.d_emit); cudaFree(p.d_sbuf); cudaFree(p.d_rbuf); }
   A = AmrLevel();
@@ -641,6 +646,12 @@ int amr_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int nc
     }
     start.push_back((int)order.size());
     A.nent = (int)cells.size();
+    {   // octs that own at least one refluxed face, in active-list order
+      std::vector<char> mark((size_t)std::max(1, ngrid_active), 0);
+      for (int sv : src) mark[(size_t)(sv >> 6)] = 1;
+      A.h_surf_io.clear();
+      for (int i = 0; i < ngrid_active; i++) if (mark[i]) A.h_surf_io.push_back(i);
+    }
     if (A.nent > 0) {
       if (ngrid_active >= (1 << 25)) return fail(RGPU_EUNSUPPORTED, "too many octs for the packed reflux schedule");
       CUDA_OK(cudaMalloc(&A.d_rcell, sizeof(int) * cells.size()));
@@ -676,10 +687,15 @@ int amr_godunov_dense(AmrLevel& A, int ilevel, double dt) {
   amr_gather_slots_kernel<<<nb, nthr, 0, G.stream>>>(G.d_uold, L.d_u[0], L.d_slot_igrid, L.nslot, G.ncoarse, G.ngridmax, G.ncell, G.p.nvar, T_());
   amr_gather_slots_kernel<<<nb, nthr, 0, G.stream>>>(G.d_unew, L.d_u[1], L.d_slot_igrid, L.nslot, G.ncoarse, G.ngridmax, G.ncell, G.p.nvar, T_());
   CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaMemcpyAsync(L.d_dt, &dt, sizeof(double), cudaMemcpyHostToDevice, G.stream));
-  CUDA_OK(cudaStreamSynchronize(G.stream));   // dt is a stack variable
+  if (A.patch) {   // ghost shell: prolongation from level l-1 (what godfine1 does for every missing neighbour oct, :583-593)
+    const long long n = L.nslot * G.p.nvar;
+    amr_fill_shell_kernel<<<(unsigned)((n + nthr - 1) / nthr), nthr, 0, G.stream>>>(amr_tree(), G.d_uold, L.d_u[0], A.d_shell_father, L.nslot, ilevel,
+                                                                                G.p.nvar, G.interpol_type);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
   SweepArgs a{};
-  a.uin = L.d_u[0]; a.uout = L.d_u[1]; a.g = L.g; a.P = G.phys; a.dt_dev = L.d_dt; a.dx = L.dx; a.inv_dx = 1.0 / L.dx;
+  a.uin = L.d_u[0]; a.uout = L.d_u[1]; a.g = L.g; a.P = G.phys; a.dt_dev = nullptr; a.dt_val = dt; a.dx = L.dx; a.inv_dx = 1.0 / L.dx;
   int ex;
   a.dx_pow2 = (std::frexp(L.dx, &ex) == 0.5) ? 1 : 0;
   a.ntx = L.ntx; a.nty = L.nty; a.nwork = L.nwork; a.part = nullptr; a.refined = L.d_refined;
@@ -695,6 +711,28 @@ int amr_godunov_dense(AmrLevel& A, int ilevel, double dt) {
   amr_scatter_slots_kernel<<<nb, nthr, 0, G.stream>>>(G.d_unew, L.d_u[1], L.d_slot_igrid, L.nslot, G.ncoarse, G.ngridmax, G.ncell, G.p.nvar, T_(), L.g);
   CUDA_OK(cudaGetLastError());
   A.launches += 4;
+  if (A.patch && A.nsurf > 0) {   // fluxes through the outer faces of the surface octs, then the coarse reflux pass
+    AmrSweepArgs s{};
+    s.t = amr_tree();
+    s.active = A.d_surf_igrid; s.nact = A.nsurf; s.ilevel = ilevel;
+    s.uold = G.d_uold; s.unew = G.d_unew; s.rflux = A.d_rflux;
+    s.P = G.phys; s.dt = dt; s.dx = A.dx; s.inv_dx = 1.0 / A.dx; s.dx_pow2 = a.dx_pow2;
+    s.interpol_type = G.interpol_type; s.difmag = 0.0; s.nps = 0;
+    s.flux_only = 1; s.rflux_index = A.d_surf_io;
+    e = dispatch_amr_nd<3>(G.p.riemann, s, G.stream);
+    if (e != cudaSuccess) return fail(RGPU_ECUDA, "patch surface flux launch: %s", cudaGetErrorString(e));
+    A.launches++;
+  }
+  if (A.nent > 0) {
+    RefluxArgs r{};
+    r.nent = A.nent; r.cell = A.d_rcell; r.start = A.d_rstart; r.src = A.d_rsrc; r.rflux = A.d_rflux; r.unew = G.d_unew;
+    r.ncell = G.ncell; r.nvar = G.p.nvar; r.nsides = 2 * G.p.ndim; r.nsf = 1 << (G.p.ndim - 1);
+    r.oneontwotondim = 1.0 / (double)(1 << G.p.ndim);
+    const int n = A.nent * G.p.nvar;
+    amr_reflux_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(r);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
   return RGPU_OK;
 }
 
@@ -959,7 +997,7 @@ int rgpu_bind_tree(int ncoarse, int ngridmax, const int* son, const int* father,
 // periodic unwrapping of ghost octs, boundary / reception / emission slot lists.  No CUDA call in here.
 static int plan_level(Level& L, int ilevel, int ngrid_active, const int* igrid_active, int ncpu, const int* ngrid_recv,
                     const int* const* igrid_recv, const int* ngrid_emit, const int* const* igrid_emit, int nboundary,
-                    const int* boundary_type, const int* ngrid_bound, const int* const* igrid_bound) {
+                    const int* boundary_type, const int* ngrid_bound, const int* const* igrid_bound, bool isolated = false) {
   const int nd = G.p.ndim;
   L.dx = level_dx(ilevel);
   // ---- collect every oct of the level with its position -------------------------------------
@@ -995,6 +1033,9 @@ static int plan_level(Level& L, int ilevel, int ngrid_active, const int* igrid_a
       lo[d] = std::min(lo[d], recs[i].pos[d]); hi[d] = std::max(hi[d], recs[i].pos[d]);
       if (recs[i].pos[d] < alo[d] - 1 || recs[i].pos[d] > ahi[d] + 1) in_shell = false;
     }
+  if (isolated)   // a refined patch: one layer of (mostly empty) shell slots wherever the box does not span the level
+    for (int d = 0; d < nd; d++)
+      if (!((long long)(ahi[d] - alo[d] + 1) == ext[d] && alo[d] == 0)) { lo[d] = std::min(lo[d], alo[d] - 1); hi[d] = std::max(hi[d], ahi[d] + 1); }
   L.bound = true;
   L.dense = (avol == ngrid_active) && in_shell;
   if (!L.dense) return RGPU_OK;
@@ -1147,11 +1188,16 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
     Level& L = G.lev[ilevel];
     if (L.bound) free_level(L);
     const char* env = getenv("RGPU_AMR_DENSE");
-    const bool want = !(env && atoi(env) == 0) && G.p.ndim == 3 && !G.p.mhd && !(G.p.difmag > 0.0) && G.p.nvar == G.p.ndim + 2 && A.nent == 0 &&
-                      ngrid_active > 0;
-    if (want) {
+    const char* envp = getenv("RGPU_AMR_PATCH");
+    const bool eligible = !(env && atoi(env) == 0) && G.p.ndim == 3 && !G.p.mhd && !(G.p.difmag > 0.0) && G.p.nvar == G.p.ndim + 2 &&
+                          ngrid_active > 0;
+    const bool base = eligible && A.nent == 0 && ncpu == 1;   // multi-rank AMR keeps the oct-batch kernel (tested path)
+    // a refined level whose octs form a Cartesian box (nested / zoom refinement): dense kernel on the box + a prolongated
+    // ghost shell; the octs at its surface go through the oct-batch kernel once more for the refluxed faces only
+    const bool patch = eligible && A.nent > 0 && ncpu == 1 && nboundary == 0 && !(envp && atoi(envp) == 0);
+    if (base || patch) {
       rc = plan_level(L, ilevel, ngrid_active, igrid_active, ncpu, ngrid_recv, igrid_recv, ngrid_emit, igrid_emit, nboundary,
-                      boundary_type, ngrid_bound, igrid_bound);
+                      boundary_type, ngrid_bound, igrid_bound, patch);
       if (rc == RGPU_OK && L.dense && L.nslot < (1LL << 31)) {
         rc = alloc_dense_store(L, ncpu, nboundary, boundary_type);
         if (rc) return rc;
@@ -1159,6 +1205,28 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
         amr_refined_mask_kernel<<<(unsigned)((L.nslot + 255) / 256), 256, 0, G.stream>>>(G.d_son, L.d_refined, L.d_slot_igrid, L.nslot, G.ncoarse,
                                                                                        G.ngridmax, T_());
         CUDA_OK(cudaGetLastError());
+        if (patch) {
+          std::vector<int> slot_of((size_t)G.ngridmax + 1, -1);
+          for (long long s = 0; s < L.nslot; s++) if (L.slot_igrid[s] > 0) slot_of[L.slot_igrid[s]] = (int)s;
+          std::vector<int> act_slot(ngrid_active), surf_ig(A.h_surf_io.size());
+          for (int i = 0; i < ngrid_active; i++) act_slot[i] = slot_of[igrid_active[i]];
+          for (size_t i = 0; i < A.h_surf_io.size(); i++) surf_ig[i] = igrid_active[A.h_surf_io[i]];
+          A.nsurf = (int)A.h_surf_io.size();
+          CUDA_OK(cudaMalloc(&A.d_act_slot, sizeof(int) * ngrid_active));
+          CUDA_OK(cudaMemcpy(A.d_act_slot, act_slot.data(), sizeof(int) * ngrid_active, cudaMemcpyHostToDevice));
+          CUDA_OK(cudaMalloc(&A.d_shell_father, sizeof(int) * L.nslot));
+          CUDA_OK(cudaMemset(A.d_shell_father, 0, sizeof(int) * L.nslot));
+          if (A.nsurf > 0) {
+            CUDA_OK(cudaMalloc(&A.d_surf_igrid, sizeof(int) * A.nsurf));
+            CUDA_OK(cudaMalloc(&A.d_surf_io, sizeof(int) * A.nsurf));
+            CUDA_OK(cudaMemcpy(A.d_surf_igrid, surf_ig.data(), sizeof(int) * A.nsurf, cudaMemcpyHostToDevice));
+            CUDA_OK(cudaMemcpy(A.d_surf_io, A.h_surf_io.data(), sizeof(int) * A.nsurf, cudaMemcpyHostToDevice));
+          }
+          amr_shell_father_kernel<<<(ngrid_active + 127) / 128, 128, 0, G.stream>>>(amr_tree(), A.d_active, A.d_act_slot, ngrid_active, ilevel, L.g.nox,
+                                                                                L.g.noy, L.nslot, A.d_shell_father);
+          CUDA_OK(cudaGetLastError());
+          A.patch = true;
+        }
         A.dense_sweep = true;
       } else {
         L = Level();   // not a box: the oct-batch kernel runs the level

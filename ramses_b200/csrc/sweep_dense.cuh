@@ -47,7 +47,8 @@ struct SweepArgs {
   double* uout;               // state at t^n+1 (unew after set_uold)
   DenseGeom g;
   Phys P;
-  const double* dt_dev;       // time step, device resident (written by the Courant reduce)
+  const double* dt_dev;       // time step, device resident (written by the Courant reduce); NULL: use dt_val
+  double dt_val;              // time step passed by value (host-driven per-level calls)
   double dx, inv_dx;
   int dx_pow2;                // dx is a power of two: x/dx == x*inv_dx exactly
   int ntx, nty;               // column tiles of the owned range
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
   const Phys& P = a.P;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * BX + tx;
-  const double dt = *a.dt_dev;
+  const double dt = a.dt_dev ? *a.dt_dev : a.dt_val;
   const double dtdx = dt / a.dx;               // trace3d: dtdx = dt/dx (hydro/umuscl.f90:516)
   const size_t vstride = (size_t)TWOTONDIM * g.nslot;
   const int nzo = HZ ? g.oz1 - g.oz0 : 1;
