@@ -85,6 +85,48 @@ def smooth_ic(nxyz):
     return fn
 
 
+def cpu_reference_run_amr(workload, steps, warmup):
+    """AMR workloads on the host cores: the oracle's amr_step (oracle/amr.py driving oracle/ramses_oracle.c, one thread: the
+    reference's serial build) on a bounded sample of the same statically nested mesh (levelmin=5, levelmax=8, 16^3-oct cubes)."""
+    from oracle.amr import AmrRun
+    from ramses_b200.tree import build_nested_tree, cell_centers
+    w = WORKLOADS[workload]
+    levelmin, levelmax, hw = 5, 8, 8
+    a = build_nested_tree(levelmin, levelmax, half_width=hw, boxlen=1.0)
+    dxf = 0.5 ** levelmax
+    for l in range(levelmin, levelmax + 1):
+        ig, cc = cell_centers(a, l)
+        for ind in range(8):
+            x, y, z = cc[ind][:, 0] - 0.5, cc[ind][:, 1] - 0.5, cc[ind][:, 2] - 0.5
+            r = (np.maximum(1.0 - np.abs(x) / dxf, 0.0) * np.maximum(1.0 - np.abs(y) / dxf, 0.0) * np.maximum(1.0 - np.abs(z) / dxf, 0.0))
+            u = np.zeros((5, len(x)))
+            u[0] = 1.0
+            u[4] = (1e-5 + 0.4 * r / dxf ** 3) / (GAMMA - 1.0)
+            a.uold[:, a.ncoarse + ind * a.ngridmax + ig - 1] = u
+    r = AmrRun(3, levelmin, levelmax, (0,) * 6, 1.0, nsubcycle=[1, 2, 2, 2], ngridmax=a.ngridmax, riemann=w["riemann"],
+               slope_type=w["slope_type"], gamma=GAMMA, interpol_type=1, tout=[1e9])
+    r.son[1:] = a.son; r.father[1:] = a.father; r.nbor[:, 1:] = a.nbor
+    for l in range(1, levelmax + 1):
+        r.active[l] = [int(g) for g in a.active[l]]
+    r.push_all()
+    r.uold[:] = a.uold.ravel()
+    for l in range(levelmax - 1, 0, -1):
+        r.upload_fine(l)
+    r.static = True
+    updates = sum(8 * len(a.active[l]) * 2 ** (l - levelmin) for l in range(levelmin, levelmax + 1))
+    for _ in range(warmup):
+        r.amr_step(levelmin, 1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r.amr_step(levelmin, 1)
+    el = time.perf_counter() - t0
+    return {"value": updates * steps / el, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+            "sample": f"statically nested AMR mesh levelmin={levelmin} levelmax={levelmax} ({(2 * hw) ** 3} octs per refined level), "
+                      f"riemann={w['riemann']}, {steps} coarse steps with sub-cycling (1+2+4+8 level steps), the oracle's amr_step "
+                      f"(oracle/amr.py + oracle/ramses_oracle.c: godfine1 with interpol_hydro, refluxing, upload_fine), 1 host thread",
+            "seconds": el}, el / steps
+
+
 def amr_bench(args, w, rank, world, local_rank):
     """configs[3]: one GPU, AMR mode.  A `step` is one coarse step of amr_step (levelmin .. levelmax with sub-cycling 2 per
     level: 1+2+4+8 level steps), every per-level routine through the C-ABI in the reference's order (hydro.amr_step)."""
@@ -164,6 +206,13 @@ def amr_bench(args, w, rank, world, local_rank):
                          "kernel": "whole coarse step (amr_godfine_kernel + reflux + list passes)", "kernel_ms": wall / steps * 1e3,
                          "algorithmic_bytes_per_launch": BYTES_PER_CELL * updates},
             "cpu_baseline": None}
+    if not args.no_cpu_baseline:
+        try:
+            cb, _ = cpu_reference_run_amr(args.workload, 2, 1)
+            cb.pop("seconds", None)
+            line["cpu_baseline"] = cb
+        except Exception as e:
+            line["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line))
     return 0
 
@@ -247,6 +296,8 @@ def cpu_reference_run(workload, steps, warmup, sample_level=7):
     w = WORKLOADS[workload]
     if w.get("mhd"):
         return cpu_reference_run_mhd(workload, steps, warmup, sample_level=6)
+    if w.get("amr"):
+        return cpu_reference_run_amr(workload, steps, warmup)
     p = orc.make_params(ndim=3, riemann=w["riemann"], slope_type=w["slope_type"], boxlen=0.5, gamma=GAMMA,
                         courant_factor=0.8)
 
