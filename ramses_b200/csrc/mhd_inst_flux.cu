@@ -7,7 +7,7 @@ namespace rgpu {
 static int minb_choice(int r1d) {
   static int env = -1;
   if (env < 0) { const char* e = getenv("RGPU_MHD_MINB"); env = e ? atoi(e) : 0; }
-  if (env >= 2 && env <= 4) return env;
+  if (env >= 2 && env <= 6) return env;
   return r1d == MHD_ROE ? 4 : (r1d == MHD_HLLD ? 3 : 2);
 }
 template <int R1D, bool SL>
@@ -15,7 +15,9 @@ static cudaError_t go(const MhdArgs& a, cudaStream_t st) {
   const int nt = 128;
   const unsigned nb = (unsigned)((a.nc + nt - 1) / nt);
   const int mb = minb_choice(R1D);
-  if (mb == 4) mhd_flux_kernel<R1D, SL, 4><<<nb, nt, 0, st>>>(a);
+  if (mb == 6 && R1D == MHD_ROE) mhd_flux_kernel<R1D, SL, (R1D == MHD_ROE ? 6 : 4)><<<nb, nt, 0, st>>>(a);
+  else if (mb == 5 && R1D == MHD_ROE) mhd_flux_kernel<R1D, SL, (R1D == MHD_ROE ? 5 : 4)><<<nb, nt, 0, st>>>(a);
+  else if (mb >= 4) mhd_flux_kernel<R1D, SL, 4><<<nb, nt, 0, st>>>(a);
   else if (mb == 3) mhd_flux_kernel<R1D, SL, 3><<<nb, nt, 0, st>>>(a);
   else mhd_flux_kernel<R1D, SL, 2><<<nb, nt, 0, st>>>(a);
   return cudaGetLastError();
