@@ -162,19 +162,17 @@ def amr_bench(args, w, rank, world, local_rank):
     updates = sum(ncell[l] * 2 ** (l - levelmin) for l in ncell)
     launches0 = lambda: sum(h.level_info(l).kernel_launches for l in range(1, levelmax + 1))
     steps, warmup = args.steps, max(args.warmup, 3)
-    for _ in range(warmup):
-        amr_step(h, levelmin, 1, levelmin, nsub, dtnew, dtold)
+    h.amr_steps(levelmin, nsub, warmup)
     h.synchronize(); torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start(); time.sleep(0.3)
     l0 = launches0()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h.synchronize(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        amr_step(h, levelmin, 1, levelmin, nsub, dtnew, dtold)
+    h.amr_steps(levelmin, nsub, steps)        # rgpu_amr_steps: time steps stay on the device, one host sync at the end
     h.synchronize(); torch.cuda.synchronize()
-    wall = time.perf_counter() - t0           # the library's stream is synchronised on both sides: device time + host driver
+    wall_host = time.perf_counter() - t0
+    wall = h.level_info(levelmin).last_steps_ms * 1e-3      # CUDA events on the launching stream around the K coarse steps
     launches = launches0() - l0
     clocks = sampler.stop()
     # end to end: host arrays in, host arrays out around every coarse step
@@ -196,7 +194,8 @@ def amr_bench(args, w, rank, world, local_rank):
             "config": {"workload": args.workload, "levelmin": levelmin, "levelmax": levelmax, "cells_per_level": ncell,
                        "level_steps_per_coarse_step": {l: 2 ** (l - levelmin) for l in ncell}, "riemann": w["riemann"],
                        "mesh": "static nested refinement (ramses_b200.tree.build_nested_tree), periodic box",
-                       "timing": "wall clock around K coarse steps with the stream synchronised on both sides (host-driven per-level calls)",
+                       "timing": "CUDA events on the launching stream around K coarse steps of rgpu_amr_steps (device-resident time steps)",
+                       "wall_ms_per_step": wall_host / steps * 1e3,
                        "l2": "state %.2f GB vs 126 MB L2" % (nbytes / 1e9)},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": updates * args.e2e_steps / e2e_t, "unit": "cell-updates/s", "h2d_bytes_per_step": int(nbytes),

@@ -148,6 +148,12 @@ int rgpu_upload_fine(int ilevel);                          /* hydro/interpol_hyd
  * dt_hist (nstep doubles, may be NULL) receives the dt of every step; sums_last[3]
  * (may be NULL) the courant_fine sums of the final state.                         */
 int rgpu_level_steps(int ilevel, int nstep, double* dt_hist, double sums_last[3]);
+/* AMR mode: ncoarse_steps calls of amr_step(levelmin, 1) (amr/amr_step.f90: recursion over the bound levels, sub-cycling
+ * nsubcycle(l) = 1 or 2 indexed by level like amr_parameters.f90:nsubcycle, :326 courant, :333 set_unew, :388 godunov_fine,
+ * :397/:505 ghost exchanges, :423 set_uold, :441 upload_fine, :514 boundaries, :567-577 dt synchronisation) on a frozen mesh,
+ * with dtnew/dtold device resident: no host round trip inside a coarse step.  dt_hist (may be NULL) receives dtnew(levelmin)
+ * of every coarse step.                                                                                              */
+int rgpu_amr_steps(int levelmin, const int* nsubcycle, int ncoarse_steps, double* dt_hist);
 
 /* ---- multi-GPU: NCCL communicator replacing MPI_COMM_WORLD ----------------------
  * unique_id: the 128-byte ncclUniqueId produced by rgpu_comm_unique_id on rank 0 and

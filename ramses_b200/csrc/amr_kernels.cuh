@@ -178,6 +178,7 @@ struct AmrSweepArgs {
   // through the outer faces of the octs at the surface of the patch (coarse refluxing)
   int flux_only;
   const int* rflux_index; // list position -> oct index of rflux (NULL: identity)
+  const double* dt_dev;   // device-resident dtnew(ilevel) (rgpu_amr_steps); NULL: use dt
 };
 
 constexpr int AMR_TPO = 64;   // threads per oct
@@ -314,7 +315,8 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
     }
   }
   // ---- uslope + trace on cells 0..3 (hydro/umuscl.f90:970, :176/:305/:483) ----
-  const double dtdx = a.dt / a.dx;
+  const double dt_ = a.dt_dev ? *a.dt_dev : a.dt;
+  const double dtdx = dt_ / a.dx;
   if (live)
     for (int tc = tl; tc < NTR; tc += AMR_TPO) {
       const int i = tc % 4, j = HY ? (tc / 4) % 4 : 1, k = HZ ? tc / 16 : 1;        // patch coordinates 0..3 (1-D/2-D: fixed 1)
@@ -355,14 +357,14 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
           const double qL = s.q[n][pc - 1], qC = q[n], qR = s.q[n][pc + 1];
           double r;
           if (P.slope_type == 4) {
-            const double dcen = uvel * a.dt / a.dx;
+            const double dcen = uvel * dt_ / a.dx;
             const double dlft = 2.0 / (1.0 + dcen) * (qC - qL), drgt = 2.0 / (1.0 - dcen) * (qR - qC);
             double dlim = fmn(fabs(dlft), fabs(drgt));
             if ((dlft * drgt) <= 0.0) dlim = 0.0;
             r = fsign1(dlft) * dlim;
           } else if (P.slope_type == 5) {
             if (n == 0) {
-              const double dcen = uvel * a.dt / a.dx;
+              const double dcen = uvel * dt_ / a.dx;
               double dlft, drgt;
               if (dcen >= 0) { dlft = 2.0 / (0.0 + dcen + 1e-10) * (qC - qL); drgt = 2.0 / (1.0 - dcen) * (qR - qC); }
               else { dlft = 2.0 / (1.0 + dcen) * (qC - qL); drgt = 2.0 / (0.0 - dcen + 1e-10) * (qR - qC); }
@@ -455,8 +457,8 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
       }
 #pragma unroll
       for (int n = 0; n < NV; n++) {
-        double v = a.dx_pow2 ? (fl[n] * a.dt) * a.inv_dx : div_rn(fl[n] * a.dt, a.dx, a.inv_dx);
-        if (DIF) v = v + a.dt * div1 * (s.uc[DIF ? n : 0][DIF ? pR : 0] - s.uc[DIF ? n : 0][DIF ? pL : 0]);
+        double v = a.dx_pow2 ? (fl[n] * dt_) * a.inv_dx : div_rn(fl[n] * dt_, a.dx, a.inv_dx);
+        if (DIF) v = v + dt_ * div1 * (s.uc[DIF ? n : 0][DIF ? pR : 0] - s.uc[DIF ? n : 0][DIF ? pL : 0]);
         if (masked) v = 0.0;
         s.flux[d][n][f] = v;
       }
@@ -654,6 +656,23 @@ __global__ void amr_courant_kernel(const double* __restrict__ u, const AmrTree t
       const size_t nb = gridDim.x;
       part[0 * nb + blockIdx.x] = v0; part[1 * nb + blockIdx.x] = v1; part[2 * nb + blockIdx.x] = v2; part[3 * nb + blockIdx.x] = v3;
     }
+  }
+}
+
+// the time-step bookkeeping of amr_step on device-resident dtnew / dtold (amr/amr_step.f90:326-331,:346-361,:567-577)
+enum { DT_SAVE_OLD = 0, DT_AFTER_COURANT = 1, DT_NO_FINER = 2, DT_SYNC_COARSE = 3 };
+__global__ void amr_dt_op_kernel(int op, double* dtnew, double* dtold, const double* courant_dt, int l, int levelmin, double nsub_coarse,
+                                 double nsub_l, int icount) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (op == DT_SAVE_OLD) dtold[l] = dtnew[l];
+  else if (op == DT_AFTER_COURANT) {
+    double dt = *courant_dt;
+    if (l > levelmin) { const double c = dtnew[l - 1] / nsub_coarse; dt = (c < dt) ? c : dt; }   // MIN(dtnew(l-1)/nsubcycle(l-1), dtnew(l))
+    dtnew[l] = dt;
+  } else if (op == DT_NO_FINER) { dtold[l + 1] = dtnew[l] / nsub_l; dtnew[l + 1] = dtnew[l] / nsub_l; }
+  else if (op == DT_SYNC_COARSE) {
+    if (nsub_coarse == 1.0) dtnew[l - 1] = dtnew[l];
+    if (icount == 2) dtnew[l - 1] = dtold[l] + dtnew[l];
   }
 }
 

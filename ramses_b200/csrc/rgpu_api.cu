@@ -121,6 +121,7 @@ struct AmrLevel {
   double* d_part = nullptr; double* d_out = nullptr; double* d_dt = nullptr;
   long long launches = 0;
   double dx = 0;
+  double last_steps_ms = 0;           // CUDA-event duration of the last rgpu_amr_steps call (recorded on the levelmin entry)
   bool dense_sweep = false;           // the level is a Cartesian box: godunov_fine runs the dense kernel (AMR variant)
   bool patch = false;                 // ... with a prolongated ghost shell and coarse refluxes (refined patch)
   int nsurf = 0;                      // octs at the surface of the patch (they own the refluxed faces)
@@ -136,6 +137,7 @@ struct Context {
   long long ncell = 0;
   int interpol_type = 1;
   AmrLevel alev[MAXLEVEL + 1];
+  double* d_dtn = nullptr; double* d_dto = nullptr;   // device-resident dtnew/dtold(0:MAXLEVEL+1) of rgpu_amr_steps
   rgpu_params p{};
   Phys phys{};
   MPhys mphys{};
@@ -680,7 +682,7 @@ cudaError_t dispatch_amr_nd(int riemann, const AmrSweepArgs& a, cudaStream_t st)
 }
 // godunov_fine of a fully refined level inside an AMR run through the dense kernel: gather uold (all octs of the box) and
 // unew (it carries the refluxes of the finer level) into the level store, masked sweep, scatter unew of the active octs
-int amr_godunov_dense(AmrLevel& A, int ilevel, double dt) {
+int amr_godunov_dense(AmrLevel& A, int ilevel, double dt, const double* dt_dev) {
   Level& L = G.lev[ilevel];
   const int nthr = 256;
   const unsigned nb = (unsigned)((L.nslot + nthr - 1) / nthr);
@@ -695,7 +697,7 @@ int amr_godunov_dense(AmrLevel& A, int ilevel, double dt) {
     A.launches++;
   }
   SweepArgs a{};
-  a.uin = L.d_u[0]; a.uout = L.d_u[1]; a.g = L.g; a.P = G.phys; a.dt_dev = nullptr; a.dt_val = dt; a.dx = L.dx; a.inv_dx = 1.0 / L.dx;
+  a.uin = L.d_u[0]; a.uout = L.d_u[1]; a.g = L.g; a.P = G.phys; a.dt_dev = dt_dev; a.dt_val = dt; a.dx = L.dx; a.inv_dx = 1.0 / L.dx;
   int ex;
   a.dx_pow2 = (std::frexp(L.dx, &ex) == 0.5) ? 1 : 0;
   a.ntx = L.ntx; a.nty = L.nty; a.nwork = L.nwork; a.part = nullptr; a.refined = L.d_refined;
@@ -716,7 +718,7 @@ int amr_godunov_dense(AmrLevel& A, int ilevel, double dt) {
     s.t = amr_tree();
     s.active = A.d_surf_igrid; s.nact = A.nsurf; s.ilevel = ilevel;
     s.uold = G.d_uold; s.unew = G.d_unew; s.rflux = A.d_rflux;
-    s.P = G.phys; s.dt = dt; s.dx = A.dx; s.inv_dx = 1.0 / A.dx; s.dx_pow2 = a.dx_pow2;
+    s.P = G.phys; s.dt = dt; s.dt_dev = dt_dev; s.dx = A.dx; s.inv_dx = 1.0 / A.dx; s.dx_pow2 = a.dx_pow2;
     s.interpol_type = G.interpol_type; s.difmag = 0.0; s.nps = 0;
     s.flux_only = 1; s.rflux_index = A.d_surf_io;
     e = dispatch_amr_nd<3>(G.p.riemann, s, G.stream);
@@ -736,10 +738,11 @@ int amr_godunov_dense(AmrLevel& A, int ilevel, double dt) {
   return RGPU_OK;
 }
 
-int amr_godunov(AmrLevel& A, int ilevel, double dt) {
+int amr_godunov(AmrLevel& A, int ilevel, double dt, const double* dt_dev = nullptr) {
   if (A.nact == 0) return RGPU_OK;
-  if (A.dense_sweep) return amr_godunov_dense(A, ilevel, dt);
+  if (A.dense_sweep) return amr_godunov_dense(A, ilevel, dt, dt_dev);
   AmrSweepArgs a{};
+  a.dt_dev = dt_dev;
   a.t = amr_tree();
   a.active = A.d_active; a.nact = A.nact; a.ilevel = ilevel;
   a.uold = G.d_uold; a.unew = G.d_unew; a.rflux = A.d_rflux;
@@ -948,8 +951,8 @@ int rgpu_finalize(void) {
   cudaStreamSynchronize(G.stream);
   for (int l = 0; l <= MAXLEVEL; l++) if (G.lev[l].bound) free_level(G.lev[l]);
   for (int l = 0; l <= MAXLEVEL; l++) if (G.alev[l].bound) free_amr_level(G.alev[l]);
-  cudaFree(G.d_son); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew);
-  G.d_son = G.d_father = G.d_nbor = nullptr; G.d_uold = G.d_unew = nullptr; G.ncell = 0; G.amr = false;
+  cudaFree(G.d_son); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew); cudaFree(G.d_dtn); cudaFree(G.d_dto);
+  G.d_son = G.d_father = G.d_nbor = nullptr; G.d_uold = G.d_unew = nullptr; G.d_dtn = G.d_dto = nullptr; G.ncell = 0; G.amr = false;
   if (G.comm) { ncclCommDestroy(G.comm); G.comm = nullptr; }
   cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); cudaEventDestroy(G.ev2); cudaEventDestroy(G.ev3);
   cudaStreamDestroy(G.stream);
@@ -1535,6 +1538,94 @@ int rgpu_level_steps(int ilevel, int nstep, double* dt_hist, double sums_last[3]
   return RGPU_OK;
 }
 
+// amr_step(levelmin, 1) x ncoarse with every time step kept on the device: the recursion and the sub-cycling run on the host
+// (they only depend on which levels hold octs), but no value travels back -- courant_fine's reduction, the MIN with the coarser
+// level's dt/nsubcycle and the dtnew(l-1) = dtold(l) + dtnew(l) synchronisation are tiny kernels on device-resident
+// dtnew/dtold, so the ~90 launches of a coarse step queue back to back.  Same arithmetic, same order as the host-driven
+// sequence (ramses_b200.hydro.amr_step): bit-identical state and time steps.
+static int amr_step_dev(int l, int icount, int levelmin, const int* nsub) {
+  AmrLevel& A = G.alev[l];
+  if (!A.bound || A.nact == 0) return RGPU_OK;
+  const int nlev = G.p.nlevelmax;
+  int rc;
+  auto op = [&](int o, int lev, double nsc, double nsl, int ic) {
+    amr_dt_op_kernel<<<1, 32, 0, G.stream>>>(o, G.d_dtn, G.d_dto, A.d_dt, lev, levelmin, nsc, nsl, ic);
+  };
+  op(DT_SAVE_OLD, l, 1.0, 1.0, icount);
+  {   // courant_fine :326 (newdt_fine: dtnew = boxlen/smallc, then the CFL scan)
+    const int nb = 148 * 8;
+    if (G.p.ndim == 1) amr_courant_kernel<1><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.phys, A.dx, A.d_part);
+    else if (G.p.ndim == 2) amr_courant_kernel<2><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.phys, A.dx, A.d_part);
+    else amr_courant_kernel<3><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.phys, A.dx, A.d_part);
+    const double vol = std::pow(A.dx, G.p.ndim), dt0 = G.p.courant_factor * A.dx / G.p.smallc;
+    courant_reduce_kernel<<<1, 1024, 0, G.stream>>>(A.d_part, nb, G.p.boxlen / G.p.smallc, dt0, vol, A.d_out, A.d_dt, nullptr);
+    CUDA_OK(cudaGetLastError());
+    if (G.comm && G.nranks > 1) NCCL_OK(ncclAllReduce(A.d_dt, A.d_dt, 1, ncclDouble, ncclMin, G.comm, G.stream));
+    A.launches += 2;
+  }
+  op(DT_AFTER_COURANT, l, l > levelmin ? (double)nsub[l - 1] : 1.0, 1.0, icount);
+  rc = amr_copy(A, G.d_uold, G.d_unew); if (rc) return rc;           // set_unew :333
+  rc = amr_zero_ghost_unew(A); if (rc) return rc;
+  if (l < nlev && G.alev[l + 1].bound && G.alev[l + 1].nact > 0) {     // :345-361
+    rc = amr_step_dev(l + 1, 1, levelmin, nsub); if (rc) return rc;
+    if (nsub[l] == 2) { rc = amr_step_dev(l + 1, 2, levelmin, nsub); if (rc) return rc; }
+  } else if (l < nlev) {
+    op(DT_NO_FINER, l, 1.0, (double)nsub[l], icount);
+  }
+  rc = amr_godunov(A, l, 0.0, G.d_dtn + l); if (rc) return rc;         // :388
+  if (G.comm && G.nranks > 1) { rc = amr_exchange(A, G.d_unew, true); if (rc) return rc; }     // :397
+  {   // set_uold :423 (+ passive-scalar floor fix)
+    const int nps = G.p.nvar - (G.p.ndim + 2);
+    if (nps > 0) {
+      const int n = A.nact * T_();
+      amr_scalar_floor_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_unew, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(),
+                                                                  G.p.ndim + 2, G.p.nvar, G.p.smallr);
+      A.launches++;
+    }
+    rc = amr_copy(A, G.d_unew, G.d_uold); if (rc) return rc;
+  }
+  if (l < nlev) {                                                       // upload_fine :441
+    const int n = A.nact * T_();
+    amr_upload_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_son - 1, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar, G.p.smallr);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  if (G.comm && G.nranks > 1) { rc = amr_exchange(A, G.d_uold, false); if (rc) return rc; }    // :505
+  rc = amr_boundaries(A); if (rc) return rc;                           // :514
+  if (l > levelmin) op(DT_SYNC_COARSE, l, (double)nsub[l - 1], 1.0, icount);   // :567-577
+  A.launches += 4;
+  return RGPU_OK;
+}
+
+int rgpu_amr_steps(int levelmin, const int* nsubcycle, int ncoarse_steps, double* dt_hist) {
+  if (!G.init || !G.amr) return fail(RGPU_EINVAL, "rgpu_amr_steps needs AMR mode (rgpu_set_amr)");
+  if (levelmin < 1 || levelmin > G.p.nlevelmax || !nsubcycle || ncoarse_steps < 1) return fail(RGPU_EINVAL, "bad argument");
+  for (int l = levelmin; l <= G.p.nlevelmax; l++)
+    if (nsubcycle[l] != 1 && nsubcycle[l] != 2) return fail(RGPU_EINVAL, "nsubcycle(%d)=%d (1 or 2)", l, nsubcycle[l]);   // amr/read_params.f90:441
+  if (!G.d_dtn) {
+    CUDA_OK(cudaMalloc(&G.d_dtn, sizeof(double) * (MAXLEVEL + 2)));
+    CUDA_OK(cudaMalloc(&G.d_dto, sizeof(double) * (MAXLEVEL + 2)));
+    CUDA_OK(cudaMemset(G.d_dtn, 0, sizeof(double) * (MAXLEVEL + 2)));
+    CUDA_OK(cudaMemset(G.d_dto, 0, sizeof(double) * (MAXLEVEL + 2)));
+  }
+  std::vector<double> hist(ncoarse_steps);
+  double* d_hist = nullptr;
+  CUDA_OK(cudaMalloc(&d_hist, sizeof(double) * ncoarse_steps));
+  CUDA_OK(cudaEventRecord(G.ev2, G.stream));
+  for (int s = 0; s < ncoarse_steps; s++) {
+    const int rc = amr_step_dev(levelmin, 1, levelmin, nsubcycle);
+    if (rc) { cudaFree(d_hist); return rc; }
+    CUDA_OK(cudaMemcpyAsync(d_hist + s, G.d_dtn + levelmin, sizeof(double), cudaMemcpyDeviceToDevice, G.stream));
+  }
+  CUDA_OK(cudaEventRecord(G.ev3, G.stream));
+  CUDA_OK(cudaMemcpyAsync(hist.data(), d_hist, sizeof(double) * ncoarse_steps, cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  cudaFree(d_hist);
+  if (dt_hist) memcpy(dt_hist, hist.data(), sizeof(double) * ncoarse_steps);
+  { float ms = 0; cudaEventElapsedTime(&ms, G.ev2, G.ev3); G.alev[levelmin].last_steps_ms = ms; }
+  return RGPU_OK;
+}
+
 int rgpu_upload_fine(int ilevel) {
   if (!G.amr) return RGPU_OK;   // a dense (levelmin=levelmax) level has no split cells: upload_fine is a no-op
   AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
@@ -1567,7 +1658,7 @@ int rgpu_comm_init(int nranks, int rank, const void* unique_id_128) {
 int rgpu_get_level_info(int ilevel, rgpu_level_info* o) {
   if (G.init && G.amr && o && ilevel >= 1 && ilevel <= MAXLEVEL && G.alev[ilevel].bound) {
     memset(o, 0, sizeof(*o));
-    o->nslot = G.alev[ilevel].nact; o->kernel_launches = G.alev[ilevel].launches;
+    o->nslot = G.alev[ilevel].nact; o->kernel_launches = G.alev[ilevel].launches; o->last_steps_ms = G.alev[ilevel].last_steps_ms;
     return RGPU_OK;
   }
   if (!G.init || ilevel < 1 || ilevel > MAXLEVEL || !G.lev[ilevel].bound || !o) return fail(RGPU_EINVAL, "level %d not bound", ilevel);

@@ -229,6 +229,13 @@ class HydroGPU:
         _lib.check(self.L.rgpu_level_steps(ilevel, nstep, _dp(dts), sums))
         return dts, list(sums)
 
+    def amr_steps(self, levelmin, nsubcycle, ncoarse_steps):
+        """ncoarse_steps x amr_step(levelmin, 1) with device-resident time steps (rgpu_amr_steps); returns dtnew(levelmin) per step."""
+        ns = np.ascontiguousarray(list(nsubcycle) + [2] * 64, dtype=np.int32)[: self.a.nlevelmax + 2]
+        dts = np.zeros(ncoarse_steps)
+        _lib.check(self.L.rgpu_amr_steps(levelmin, _ip(ns), ncoarse_steps, _dp(dts)))
+        return dts
+
     def host_register(self, arr):
         _lib.check(self.L.rgpu_host_register(arr.ctypes.data, arr.nbytes))
 

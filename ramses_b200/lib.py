@@ -99,6 +99,7 @@ def load():
     L.rgpu_make_virtual_reverse.argtypes = [C.c_int]
     L.rgpu_level_steps.argtypes = [C.c_int, C.c_int, dp, dp]
     L.rgpu_upload_fine.argtypes = [C.c_int]
+    L.rgpu_amr_steps.argtypes = [C.c_int, ip, C.c_int, dp]
     L.rgpu_set_amr.argtypes = [C.c_int, C.c_int, C.c_int]
     L.rgpu_comm_unique_id.argtypes = [C.c_void_p]
     L.rgpu_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p]

@@ -381,3 +381,35 @@ def test_passive_scalars_rejected_where_not_built():
     c = Case(2, 2, nvar=5)
     with pytest.raises(_l.RgpuError):
         HydroGPU(c.amr_commons(), amr_mode=True)
+
+
+def test_amr_steps_device_resident_dt_equals_host_driven():
+    """rgpu_amr_steps (recursion on the host, every time step on the device, no round trip) == the host-driven amr_step
+    sequence: same state, same dtnew(levelmin), over 3 coarse steps of the nested tree (oct-batch, dense-base and patch paths)."""
+    levelmin, levelmax = 4, 6
+    from ramses_b200.hydro import HydroGPU, amr_step
+    res = []
+    for mode in ("host", "device"):
+        a = _nested_case(levelmin, levelmax, 3)
+        h = HydroGPU(a, amr_mode=True, interpol_type=1)
+        for l in range(1, levelmax + 1):
+            h.bind_level(l)
+        h.upload_state(0)
+        for l in range(levelmax - 1, 0, -1):
+            h.upload_fine(l)
+        nsub = [1] * (levelmin + 1) + [2] * 64
+        if mode == "host":
+            dtnew = {l: 0.0 for l in range(0, levelmax + 2)}
+            dtold = {l: 0.0 for l in range(0, levelmax + 2)}
+            dts = []
+            for _ in range(3):
+                amr_step(h, levelmin, 1, levelmin, nsub, dtnew, dtold)
+                dts.append(dtnew[levelmin])
+        else:
+            dts = list(h.amr_steps(levelmin, nsub, 3))
+        h.download_state(0)
+        h.finalize()
+        res.append((np.array(dts), a.uold.copy()))
+    assert np.array_equal(res[0][0], res[1][0]), (res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1])
+    assert (res[0][0] > 0).all()
