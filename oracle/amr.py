@@ -21,7 +21,7 @@ class AmrRun:
     def __init__(self, ndim, levelmin, levelmax, bound_type, boxlen, nsubcycle, nexpand=1, ngridmax=2000,
                  riemann="hllc", slope_type=2, gamma=1.4, courant_factor=0.8, err_grad_d=-1.0, err_grad_u=-1.0,
                  err_grad_p=-1.0, interpol_type=1, interpol_var=0, regions=(), tout=(), nvector=32,
-                 floor_d=1e-10, floor_u=1e-10, floor_p=1e-10):
+                 floor_d=1e-10, floor_u=1e-10, floor_p=1e-10, bound_regions=None):
         self.ndim, self.levelmin, self.nlevelmax = ndim, levelmin, levelmax
         self.T, self.twondim = 1 << ndim, 2 * ndim
         L = self.L = orc.lib()
@@ -56,7 +56,20 @@ class AmrRun:
         # level dependent arrays rearranged like amr/read_params.f90:441-470
         ns = list(nsubcycle) + [2] * 64
         self.nsubcycle = {l: (ns[l - levelmin] if l >= levelmin else 1) for l in range(1, levelmax + 2)}
-        self.nexpand = {l: nexpand for l in range(1, levelmax + 2)}
+        # a scalar applies to every level; a list is the namelist array (`nexpand=4` in a namelist sets element 1 only,
+        # i.e. pass [4]): level l >= levelmin takes element l-levelmin+1, missing elements and coarser levels are 1
+        ne = (list(nexpand) + [1] * 64) if hasattr(nexpand, "__len__") else [nexpand] * 64
+        self.nexpand = {l: (ne[l - levelmin] if l >= levelmin else 1) for l in range(1, levelmax + 2)}
+        # boundary regions in the coarse-cell ranges of hydro/read_hydro_params.f90:316-407.  Default: one region per
+        # non-periodic face covering that face only (no edge/corner cells).  bound_regions = [(boundary_type, (imin,
+        # imax), (jmin, jmax), (kmin, kmax)), ...] in namelist order restates BOUNDARY_PARAMS blocks whose regions include
+        # the corner cells (tests/hydro/implosion/implosion.nml:17-24); ranges are coarse-grid indices incl. boundary cells
+        self.bound_regions = None
+        if bound_regions is not None:
+            assert len(bound_regions) == m.nboundary
+            self.bound_regions = [(int(t), tuple(ri), tuple(rj), tuple(rk)) for t, ri, rj, rk in bound_regions]
+            for b, reg in enumerate(self.bound_regions):
+                m.boundary_type[b] = reg[0]
         self.err_grad_d, self.err_grad_u, self.err_grad_p = err_grad_d, err_grad_u, err_grad_p
         self.floor_d, self.floor_u, self.floor_p = floor_d, floor_u, floor_p
         self.regions = list(regions)
@@ -342,7 +355,7 @@ class AmrRun:
                     dom.add(ind)
                     if self.flag1[ind] == 1 and self.son[ind] == 0:
                         self.make_grid_coarse(ind, -1)
-        # boundary regions: one coarse cell per boundary face in this builder
+        # boundary regions (:93-150): by default one slab of coarse cells per boundary face
         for b in range(m.nboundary):
             bt = m.boundary_type[b]
             bdir = bt - 10 * (bt // 10)
@@ -351,6 +364,8 @@ class AmrRun:
             cmax = [m.icoarse_max, m.jcoarse_max, m.kcoarse_max]
             rng = [range(cmin[x], cmax[x] + 1) for x in range(3)]
             rng[d] = [cmin[d] - 1] if s == 0 else [cmax[d] + 1]
+            if self.bound_regions is not None:
+                rng = [range(lo, hi + 1) for lo, hi in self.bound_regions[b][1:]]
             for k in rng[2]:
                 for j in rng[1]:
                     for i in rng[0]:
@@ -604,6 +619,70 @@ class AmrRun:
         return self.snapshot
 
 
+class FastAmrRun(AmrRun):
+    """AmrRun with the per-cell flag / scan passes done by oracle/ramses_oracle_amr.c (same passes, same visiting order; the
+    Python methods of AmrRun remain the readable statement and the cross-check).  Needed for the 2-D golden run."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        L = self.L
+        MP, ip, dp = C.POINTER(orc.MeshS), C.POINTER(C.c_int), C.POINTER(C.c_double)
+        L.orc_amr_make_boundary_flag.argtypes = [MP, C.c_int, ip]
+        L.orc_amr_init_flag.argtypes = [MP, C.c_int, C.c_int, ip]
+        L.orc_amr_smooth_fine.argtypes = [MP, C.c_int, ip, ip]
+        L.orc_amr_hydro_flag.argtypes = [C.POINTER(orc.Params), MP, C.c_int, dp, ip, dp, dp]
+        L.orc_amr_ensure_ref_rules.argtypes = [MP, C.c_int, ip]
+        L.orc_amr_authorize_fine.argtypes = [MP, C.c_int, ip, ip]
+        L.orc_amr_refine_scan.argtypes = [MP, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, ip, C.c_int]
+        self._f1, self._f2 = orc.iptr(self.flag1), orc.iptr(self.flag2)
+        self._scan = np.zeros(2 * self.T * (self.ngridmax + 1), dtype=np.int32)
+
+    def make_boundary_flag(self, l):
+        self.L.orc_amr_make_boundary_flag(self.mp, l, self._f1)
+
+    def init_flag(self, l):
+        self.L.orc_amr_init_flag(self.mp, l, self.levelmin, self._f1)
+
+    def smooth_fine(self, l):
+        if l == self.nlevelmax or self.numbtot(l) == 0:
+            return
+        self.L.orc_amr_smooth_fine(self.mp, l, self._f1, self._f2)
+
+    def hydro_flag(self, l):
+        if l == self.nlevelmax or self.numbtot(l) == 0:
+            return
+        if self.err_grad_d == -1.0 and self.err_grad_p == -1.0 and self.err_grad_u == -1.0:
+            return
+        err = np.array([self.err_grad_d, self.err_grad_u, self.err_grad_p])
+        flo = np.array([self.floor_d, self.floor_u, self.floor_p])
+        self.L.orc_amr_hydro_flag(C.byref(self.p), self.mp, l, orc.dptr(self.uold), self._f1, orc.dptr(err), orc.dptr(flo))
+
+    def ensure_ref_rules(self, l):
+        self.L.orc_amr_ensure_ref_rules(self.mp, l, self._f1)
+
+    def authorize_fine(self, l):
+        if l == self.nlevelmax:
+            return
+        self.L.orc_amr_authorize_fine(self.mp, l, self._f1, self._f2)
+
+    def refine_fine(self, l):
+        if l == self.nlevelmax or self.numbtot(l) == 0:
+            return
+        self.authorize_fine(l)
+        cap = len(self._scan) // 2
+        for mode in (0, 1):
+            for kind, b, lst in self.all_lists(l):
+                n = self.L.orc_amr_refine_scan(self.mp, l, kind, max(b, 0), self.nvector, self._f1, self._f2, mode,
+                                               orc.iptr(self._scan), cap)
+                assert n <= cap
+                for ig, ind in self._scan[:2 * n].reshape(n, 2).tolist():
+                    if mode == 0:
+                        self.make_grid_fine(ig, ind, l + 1, b)
+                    else:
+                        self.kill_grid(self.cell(ind, ig), l + 1, b)
+        self.push_lists(l + 1)
+
+
 class _MeshView:
     """duck-typed stand-in for orc.Mesh in orc.condinit_regions"""
 
@@ -611,23 +690,25 @@ class _MeshView:
         self.ptr = run.mp
 
 
-def check_sums(rows, ndim):
-    """tests/visu/visu_ramses.py:495-557 check_solution sums for the hydro fields"""
-    dens = np.array([r[2] for r in rows])
-    pres = np.array([r[4] for r in rows])
+def check_sums(rows, ndim, boxlen=1.0):
+    """tests/visu/visu_ramses.py:495-557 check_solution sums for the hydro fields.  Vector components are thresholded
+    against 2e-14 x norm, where the norm is the vector length only if all three components exist in the snapshot (true
+    for x,y,z -- never binding -- and for NDIM=3 velocities) and 1 otherwise."""
     lev = np.array([r[0] for r in rows], dtype=float)
-    x = np.array([r[1][0] for r in rows])
-    vx = np.array([r[3][0] for r in rows])
 
     def filt(a):
         av = np.average(a)
         if av == 0.0:
             return a
         return np.where(np.abs(a - av) / abs(av) < 1.0e-14, av, a)
-    out = {"ncells": float(len(rows)), "level": math.fsum(np.abs(filt(lev))), "x": math.fsum(np.abs(filt(x))),
+    dens = np.array([r[2] for r in rows])
+    pres = np.array([r[4] for r in rows])
+    out = {"ncells": float(len(rows)), "level": math.fsum(np.abs(filt(lev))), "dx": math.fsum(np.abs(filt(0.5 ** lev * boxlen))),
            "density": math.fsum(np.log10(np.abs(filt(dens)))), "pressure": math.fsum(np.log10(np.abs(filt(pres))))}
-    norm = np.abs(vx) if ndim == 1 else None
-    kd = filt(vx)
-    thr = 2.0e-14 * (1.0 if ndim == 1 else norm)
-    out["velocity_x"] = math.fsum(np.where(np.abs(kd) < thr, 0.0, np.abs(kd)))
+    vel = [np.array([r[3][k] for r in rows]) for k in range(ndim)]
+    norm = np.sqrt(sum(v * v for v in vel)) if ndim == 3 else 1.0
+    for k in range(ndim):
+        out["xyz"[k]] = math.fsum(np.abs(filt(np.array([r[1][k] for r in rows]))))
+        kd = filt(vel[k])
+        out["velocity_" + "xyz"[k]] = math.fsum(np.where(np.abs(kd) < 2.0e-14 * norm, 0.0, np.abs(kd)))
     return out

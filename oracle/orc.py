@@ -16,7 +16,8 @@ MAXBOUND = 6
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("ramses_oracle.c", "ramses_oracle.h", "ramses_oracle_mhd.c", "ramses_oracle_mhd.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("ramses_oracle.c", "ramses_oracle.h", "ramses_oracle_mhd.c", "ramses_oracle_mhd.h",
+                                              "ramses_oracle_amr.c")]
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libramses_oracle.so"])
     return _LIB

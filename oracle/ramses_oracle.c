@@ -21,6 +21,14 @@
  *       floating-point routine, and reproduces all golden sums (density and pressure
  *       log-sums to 16 digits, velocity to 3e-16, time to 2e-15, ncells/level/x
  *       exactly) plus the mesh structure and step counts of doc/wiki/Start.md:158-187.
+ *    1b. PINNED (tolerance 3e-13): tests/golden/implosion_ref.json
+ *       <- tests/hydro/implosion/implosion-ref.dat.  The 2-D AMR implosion (levels 5-8,
+ *       hllc, moncen, four reflexive walls with corner octs, nsubcycle 2, t=5: 1049
+ *       coarse / 8392 fine steps, 15 349 leaf cells) through oracle/amr.py::FastAmrRun:
+ *       ncells, level, dx, x, y exact; log-sums of density 4e-14, pressure 2.0e-13,
+ *       sum|v_x| 2.2e-13, sum|v_y| 1.8e-13, time 4e-15 -- all inside the reference's
+ *       tolerance; the golden file's own x<->y asymmetry is 1.5e-13, i.e. the residual is
+ *       the round-off amplification of that flow (it moves by 1e-14 with nvector).
  *    2. tests/golden/sod_tube_ana.json  <- tests/hydro/sod-tube/sod-tube-ana.dat
  *       (exact Sod solution, 1024 points): discretisation-level check of every
  *       Riemann solver on a uniform grid.
@@ -29,8 +37,8 @@
  *    4. invariants: conservation to round-off on periodic runs, x<->y<->z
  *       permutation symmetry, dt parity.
  *   UNPINNED at the 3e-13 level (no golden file exists in the reference):
- *   2-D/3-D runs, riemann='exact'/'acoustic'/'hll'/'llf', slope types other than 2 --
- *   those rest on 2-4 and on sharing the generic-NDIM code paths pinned by 1.
+ *   3-D runs, riemann='exact'/'acoustic'/'hll'/'llf', slope types other than 2 --
+ *   those rest on 2-4 and on sharing the generic-NDIM code paths pinned by 1 and 1b.
  *
  * Citations are reference file:line.
  */

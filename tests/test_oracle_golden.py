@@ -79,3 +79,55 @@ def test_imhd_tube_golden_sums(imhd_run):
         checked += 1
     assert checked >= 15
     assert sums["ncells"] == 437 and snap["nstep_coarse"] == 259
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2-D hydro: tests/hydro/implosion (NDIM=2, AMR levels 5..8, hllc, moncen, four reflexive walls whose y-regions include the
+# corner cells, nsubcycle=10*2, nexpand=4 (first level only), interpol_type=2, t=5: 1049 coarse / 8392 fine steps)
+IMPL = [dict(type="square", x_center=0.5, y_center=0.5, length_x=1.0, length_y=1.0, exp_region=10, d=1.0, p=1.0),
+        dict(type="square", x_center=0.0, y_center=0.0, length_x=1.0, length_y=1.0, exp_region=1, d=0.125, p=0.4)]
+# BOUNDARY_PARAMS of implosion.nml:17-24 after hydro/read_hydro_params.f90:316-407: (boundary_type, i-, j-, k-range)
+IMPL_BOUND = [(1, (0, 0), (1, 1), (0, 0)), (2, (2, 2), (1, 1), (0, 0)), (4, (0, 2), (2, 2), (0, 0)), (3, (0, 2), (0, 0), (0, 0))]
+
+
+@pytest.fixture(scope="module")
+def implosion_run(orc):
+    from oracle.amr import FastAmrRun
+    r = FastAmrRun(2, 5, 8, (1, 1, 1, 1, 0, 0), 1.0, nsubcycle=[2] * 10, nexpand=[4], ngridmax=100000, riemann="hllc",
+                   slope_type=2, gamma=1.4, courant_factor=0.8, err_grad_d=0.05, err_grad_u=0.05, err_grad_p=0.05,
+                   interpol_type=2, interpol_var=0, regions=IMPL, tout=[0.0, 5.0], bound_regions=IMPL_BOUND)
+    return r, r.run()
+
+
+def test_implosion_golden_sums(implosion_run):
+    """tests/hydro/implosion/implosion-ref.dat with the reference's own tolerance (3e-13): pins the NDIM=2 paths of the
+    oracle -- trace2d, 2-D slopes, cmpflxm in two directions, 2-D interpol_hydro / refluxing / flux masking, corner
+    boundary octs, cmpdt -- through 8392 fine steps of a flow that amplifies any 1-ulp slip."""
+    from oracle.amr import check_sums
+    r, snap = implosion_run
+    ref = json.load(open(os.path.join(GOLD, "implosion_ref.json")))
+    sums = check_sums(snap["rows"], 2)
+    sums["time"] = snap["t"]
+    tol = 3.0e-13
+    for key in ("ncells", "level", "dx", "x", "y", "density", "pressure", "velocity_x", "velocity_y", "time"):
+        err = abs(sums[key] - ref[key]) / min(abs(sums[key]), abs(ref[key]))
+        assert err <= tol, (key, sums[key], ref[key], err)
+    assert snap["nstep_coarse"] == 1049 and snap["nstep"] == 8392
+    assert [snap["grids"][l] for l in range(1, 9)] == [1, 4, 16, 64, 256, 781, 1288, 2706]
+
+
+def test_fast_amr_driver_equals_python_driver(orc):
+    """oracle/ramses_oracle_amr.c (flag / scan passes in C) against the pure-Python passes of AmrRun: identical state,
+    tree and time on the sod-tube golden case."""
+    import numpy as np
+    from oracle.amr import AmrRun, FastAmrRun
+    out = []
+    for cls in (AmrRun, FastAmrRun):
+        r = cls(1, 3, 10, (1, 1, 0, 0, 0, 0), 1.0, nsubcycle=[1, 1, 1, 2], nexpand=1, ngridmax=2000, riemann="hllc",
+                slope_type=2, gamma=1.4, courant_factor=0.8, err_grad_d=0.05, err_grad_u=0.05, err_grad_p=0.05,
+                interpol_type=2, interpol_var=0, regions=SOD, tout=[0.245])
+        snap = r.run()
+        out.append((snap["t"], snap["rows"], r.uold.copy(), r.son.copy(), r.nbor.copy()))
+    a, b = out
+    assert a[0] == b[0] and a[1] == b[1]
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
