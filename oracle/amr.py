@@ -623,9 +623,12 @@ class FastAmrRun(AmrRun):
     """AmrRun with the per-cell flag / scan passes done by oracle/ramses_oracle_amr.c (same passes, same visiting order; the
     Python methods of AmrRun remain the readable statement and the cross-check).  Needed for the 2-D golden run."""
 
-    def __init__(self, *a, **kw):
+    def __init__(self, *a, nthreads=None, **kw):
         super().__init__(*a, **kw)
         L = self.L
+        import os
+        L.orc_set_amr_threads.argtypes = [C.c_int]     # flux phase only; bit-identical to the serial routine for any count
+        L.orc_set_amr_threads(int(nthreads) if nthreads else min(8, os.cpu_count() or 1))
         MP, ip, dp = C.POINTER(orc.MeshS), C.POINTER(C.c_int), C.POINTER(C.c_double)
         L.orc_amr_make_boundary_flag.argtypes = [MP, C.c_int, ip]
         L.orc_amr_init_flag.argtypes = [MP, C.c_int, C.c_int, ip]

@@ -1530,8 +1530,10 @@ void orc_interpol_cell(const orc_params* p, const orc_mesh* m, int ind_cell, int
 }
 
 /* godfine1 hydro/godunov_fine.f90:486-911 for one batch of octs */
+/* phase 0: the whole routine; phase 1: gather + fluxes + flux reset only (reads uold, writes the work arrays);
+ * phase 2: the updates of unew only, from the work arrays left by phase 1                                        */
 static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const int* ind_grid, int ncache, int ilevel,
-                     double dt, const double* uold, double* unew) {
+                     double dt, const double* uold, double* unew, int phase) {
   const int ndim = p->ndim, nvar = p->nvar, twotondim = ipow2(ndim);
   const size_t np = w->np, nfp = w->nfp;
   const double oneontwotondim = 1.0 / (double)twotondim;
@@ -1539,6 +1541,7 @@ static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const 
   const int i1max = 2, j1max = ndim > 1 ? 2 : 0, k1max = ndim > 2 ? 2 : 0;
   const int i2max = 1, j2max = ndim > 1 ? 1 : 0, k2max = ndim > 2 ? 1 : 0;
   const int i3min = 1, i3max = 2, j3min = 1, j3max = ndim > 1 ? 2 : 1, k3min = 1, k3max = ndim > 2 ? 2 : 1;
+  if (phase != 2) {
   /* gather 3^ndim neighbouring father cells :553-556 and the 6^ndim stencil :562-675 */
   for (int i = 0; i < ncache; i++) {
     int nfc[27];
@@ -1582,6 +1585,8 @@ static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const 
               if (w->ok[PIX(w, i, i3 - i0, j3 - j0, k3 - k0)] || w->ok[PIX(w, i, i3, j3, k3)])
                 w->flux[(iv + (size_t)idim * nvar) * nfp + FIX(w, i, i3, j3, k3)] = 0.0;
   }
+  }
+  if (phase == 1) return;
   /* conservative update at level ilevel :751-792 */
   for (int idim = 0; idim < ndim; idim++) {
     int i0 = idim == 0, j0 = idim == 1, k0 = idim == 2;
@@ -1635,12 +1640,43 @@ static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const 
 
 /* godunov_fine hydro/godunov_fine.f90:5-35.  nthreads>1 splits the batches of a
  * level over OpenMP threads (the reference splits them over MPI ranks).          */
+static int g_amr_threads = 1;
+/* threads for the flux phase of orc_godunov_fine when it is called with nthreads=1 (the AMR drivers): batches are taken
+ * g_amr_threads at a time, their fluxes computed concurrently (phase 1 only reads uold), and their updates of unew --
+ * including the coarse refluxes -- applied serially in batch order, so the result is bit-identical to the serial routine */
+void orc_set_amr_threads(int n) { g_amr_threads = n < 1 ? 1 : n; }
+
 void orc_godunov_fine(const orc_params* p, const orc_mesh* m, int ilevel, double dt, const double* uold, double* unew,
                       int nthreads) {
   const int ncache = m->nactive[ilevel], nv = p->nvector;
   if (ncache == 0) return;
   int nbatch = (ncache + nv - 1) / nv;
   if (nthreads < 1) nthreads = 1;
+  if (nthreads == 1 && g_amr_threads > 1 && nbatch > 1) {
+    const int nt = IMIN(g_amr_threads, 64);
+    static orc_work* ws[64];                       /* kept between calls (thousands of level steps per run) */
+    static int ws_n = 0, ws_key[3] = {0, 0, 0};
+    if (ws_n != nt || ws_key[0] != p->ndim || ws_key[1] != p->nvar || ws_key[2] != p->nvector) {
+      for (int t = 0; t < ws_n; t++) orc_work_free(ws[t]);
+      for (int t = 0; t < nt; t++) ws[t] = orc_work_new(p);
+      ws_n = nt; ws_key[0] = p->ndim; ws_key[1] = p->nvar; ws_key[2] = p->nvector;
+    }
+    for (int b0 = 0; b0 < nbatch; b0 += nt) {
+      const int nb = IMIN(nt, nbatch - b0);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+#endif
+      for (int t = 0; t < nb; t++) {
+        const int ig = (b0 + t) * nv;
+        godfine1(p, m, ws[t], m->active[ilevel] + ig, IMIN(nv, ncache - ig), ilevel, dt, uold, unew, 1);
+      }
+      for (int t = 0; t < nb; t++) {
+        const int ig = (b0 + t) * nv;
+        godfine1(p, m, ws[t], m->active[ilevel] + ig, IMIN(nv, ncache - ig), ilevel, dt, uold, unew, 2);
+      }
+    }
+    return;
+  }
 #ifdef _OPENMP
 #pragma omp parallel num_threads(nthreads)
 #endif
@@ -1652,7 +1688,7 @@ void orc_godunov_fine(const orc_params* p, const orc_mesh* m, int ilevel, double
     for (int b = 0; b < nbatch; b++) {
       int ig = b * nv;
       int ngrid = IMIN(nv, ncache - ig);
-      godfine1(p, m, w, m->active[ilevel] + ig, ngrid, ilevel, dt, uold, unew);
+      godfine1(p, m, w, m->active[ilevel] + ig, ngrid, ilevel, dt, uold, unew, 0);
     }
     orc_work_free(w);
   }

@@ -134,6 +134,7 @@ orc_mesh* orc_mesh_new(int ndim, const int bound_type[6], int ngridmax, int nlev
 void orc_mesh_set_list(orc_mesh*, int kind, int b, int ilevel, int n, const int* igrid);
 
 void orc_set_threads(int n);
+void orc_set_amr_threads(int n);   /* flux phase of orc_godunov_fine(nthreads=1); results do not depend on it */
 int orc_abi_version(void);
 
 #ifdef __cplusplus

@@ -1323,7 +1323,7 @@ static void mhd1_unsplit(const orc_mhd_params* p, mhd1_patch* w, double dx, doub
 }
 
 static const orc_params* hydro_like_params(int ndim) {   /* orc_interpol_hydro / orc_getnborfather only read ndim, nvar */
-  static orc_params hp;
+  static _Thread_local orc_params hp;
   memset(&hp, 0, sizeof hp);
   hp.ndim = ndim; hp.nvar = NVS;
   return &hp;
@@ -1591,6 +1591,658 @@ void orc_mhd1_upload_fine(const orc_mhd_params* p, const orc_mesh* m, int ilevel
       if (gL > 0 && m->son[cL] > 0) UO(ic, 6) = UO(m->ncoarse + 1 * m->ngridmax + m->son[cL], NV + 1);      /* upl_left :516 */
       const int gR = ind == 1 ? gr : ig, cR = m->ncoarse + (ind == 1 ? 0 : 1) * m->ngridmax + gR;
       if (gR > 0 && m->son[cR] > 0) UO(ic, NV + 1) = UO(m->ncoarse + 0 * m->ngridmax + m->son[cR], 6);      /* upl_right :564 */
+    }
+  }
+}
+
+/* ======================================================================================================
+ * NDIM = 2 (tests/mhd/orszag-tang): mag_unsplit with trace2d (mhd/umuscl.f90:410) and one EMF component (E_z at the cell
+ * corners, cmp_mag_flx :1453), godfine1 with the coarse-fine pieces -- divergence-free prolongation (interpol_hydro
+ * mhd/interpol_hydro.f90:612, interpol_mag :990 = interpol_faces + copy_from_refined_faces + cmp_central_faces), flux and
+ * EMF reset at refined faces / edges, constrained-transport update of B_x, B_y, coarse refluxing of the Euler fluxes and of
+ * the four E_z edges (mhd/godunov_fine.f90:1025-1270) -- upload_fine with face-centred restriction (:5-231, upl :233),
+ * courant_fine.  B_z is a cell-centred quantity in two dimensions (both copies equal, advanced by the flux of variable 8).
+ * ====================================================================================================== */
+typedef struct {
+  double uloc[6][6][NVS];   /* [j][i], Fortran -1..4 -> 0..5 */
+  int ok[6][6];
+  double flux[2][3][3][NV]; /* [idim][j3-1][i3-1]: x faces i3=1..3, j3=1..2; y faces i3=1..2, j3=1..3 */
+  double emfz[3][3];        /* [j3-1][i3-1] corners i3,j3 = 1..3 */
+  int nfc[9];               /* get3cubefather cells (needed again by the EMF refluxing) */
+} mhd2_patch;
+
+static void mhd2_unsplit(const orc_mhd_params* p, mhd2_patch* w, double dx, double dt) {
+  double q[6][6][NV], bf[7][7][2], dq[6][6][NV][2], dbf[7][7][2], Ez[6][6];
+  double qm[6][6][NV][2], qp[6][6][NV][2], qRT[6][6][NV], qRB[6][6][NV], qLT[6][6][NV], qLB[6][6][NV];
+  const double smallp = p->smallr * (p->smallc * p->smallc) / p->gamma;
+  const double smallr = p->smallr, gamma = p->gamma;
+  enum { ir = 0, iu = 1, iv = 2, iw = 3, ip = 4, iA = 5, iB = 6, iC = 7 };
+  /* ctoprim :2029 */
+  for (int j = -1; j <= 4; j++)
+    for (int i = -1; i <= 5; i++) bf[X(j)][X(i)][0] = (i <= 4) ? w->uloc[X(j)][X(i)][5] : w->uloc[X(j)][X(i - 1)][NV + 0];
+  for (int j = -1; j <= 5; j++)
+    for (int i = -1; i <= 4; i++) bf[X(j)][X(i)][1] = (j <= 4) ? w->uloc[X(j)][X(i)][6] : w->uloc[X(j - 1)][X(i)][NV + 1];
+  for (int j = 0; j < 6; j++)
+    for (int i = 0; i < 6; i++) {
+      const double* u = w->uloc[j][i];
+      double* qq = q[j][i];
+      qq[0] = FMAX(u[0], smallr);
+      qq[1] = u[1] / qq[0]; qq[2] = u[2] / qq[0]; qq[3] = u[3] / qq[0];
+      qq[5] = (u[5] + u[NV + 0]) * half;
+      qq[6] = (u[6] + u[NV + 1]) * half;
+      qq[7] = (u[7] + u[NV + 2]) * half;
+      double eken = half * (qq[1] * qq[1] + qq[2] * qq[2] + qq[3] * qq[3]);
+      double emag = half * (qq[5] * qq[5] + qq[6] * qq[6] + qq[7] * qq[7]);
+      double etot = u[4] - emag - zero;
+      double eint = etot / qq[0] - eken;
+      qq[4] = FMAX((gamma - one) * qq[0] * eint, smallp);
+    }
+  /* uslope NDIM==2 :2253-2372 */
+  memset(dq, 0, sizeof dq);
+  memset(dbf, 0, sizeof dbf);
+  if (p->slope_type == 1 || p->slope_type == 2) {
+    const double s = (double)p->slope_type;
+    for (int n = 0; n < NV; n++)
+      for (int j = 0; j <= 3; j++)
+        for (int i = 0; i <= 3; i++) {
+          dq[X(j)][X(i)][n][0] = slope_mm(s, q[X(j)][X(i - 1)][n], q[X(j)][X(i)][n], q[X(j)][X(i + 1)][n]);
+          dq[X(j)][X(i)][n][1] = slope_mm(s, q[X(j - 1)][X(i)][n], q[X(j)][X(i)][n], q[X(j + 1)][X(i)][n]);
+        }
+  } else if (p->slope_type != 0) { fprintf(stderr, "oracle(mhd 2-D): slope_type %d not restated\n", p->slope_type); abort(); }
+  if (p->slope_mag_type == 1 || p->slope_mag_type == 2) {
+    const double s = (double)p->slope_mag_type;
+    for (int j = 0; j <= 3; j++)
+      for (int i = 0; i <= 4; i++) dbf[X(j)][X(i)][0] = slope_mm(s, bf[X(j - 1)][X(i)][0], bf[X(j)][X(i)][0], bf[X(j + 1)][X(i)][0]);
+    for (int j = 0; j <= 4; j++)
+      for (int i = 0; i <= 3; i++) dbf[X(j)][X(i)][1] = slope_mm(s, bf[X(j)][X(i - 1)][1], bf[X(j)][X(i)][1], bf[X(j)][X(i + 1)][1]);
+  } else if (p->slope_mag_type != 0) { fprintf(stderr, "oracle(mhd 2-D): slope_mag_type %d not restated\n", p->slope_mag_type); abort(); }
+  /* trace2d :410 */
+  const double dtdx = dt / dx, dtdy = dt / dx;
+  for (int j = 0; j <= 4; j++)
+    for (int i = 0; i <= 4; i++) {
+      double u = 0.25 * (q[X(j - 1)][X(i - 1)][iu] + q[X(j)][X(i - 1)][iu] + q[X(j - 1)][X(i)][iu] + q[X(j)][X(i)][iu]);
+      double v = 0.25 * (q[X(j - 1)][X(i - 1)][iv] + q[X(j)][X(i - 1)][iv] + q[X(j - 1)][X(i)][iv] + q[X(j)][X(i)][iv]);
+      double A = 0.5 * (bf[X(j - 1)][X(i)][0] + bf[X(j)][X(i)][0]);
+      double B = 0.5 * (bf[X(j)][X(i - 1)][1] + bf[X(j)][X(i)][1]);
+      Ez[X(j)][X(i)] = u * B - v * A;
+    }
+  for (int j = 0; j <= 3; j++)
+    for (int i = 0; i <= 3; i++) {
+      const double* qq = q[X(j)][X(i)];
+      double(*d)[2] = dq[X(j)][X(i)];
+      double r = qq[ir], u = qq[iu], v = qq[iv], ww = qq[iw], pp = qq[ip], A = qq[iA], B = qq[iB], C = qq[iC];
+      double AL = bf[X(j)][X(i)][0], AR = bf[X(j)][X(i + 1)][0], BL = bf[X(j)][X(i)][1], BR = bf[X(j + 1)][X(i)][1];
+      double drx = half * d[ir][0], dux = half * d[iu][0], dvx = half * d[iv][0], dwx = half * d[iw][0], dpx = half * d[ip][0];
+      double dBx = half * d[iB][0], dCx = half * d[iC][0];
+      double dry = half * d[ir][1], duy = half * d[iu][1], dvy = half * d[iv][1], dwy = half * d[iw][1], dpy = half * d[ip][1];
+      double dAy = half * d[iA][1], dCy = half * d[iC][1];
+      double dALy = half * dbf[X(j)][X(i)][0], dARy = half * dbf[X(j)][X(i + 1)][0];
+      double dBLx = half * dbf[X(j)][X(i)][1], dBRx = half * dbf[X(j + 1)][X(i)][1];
+      double ELL = Ez[X(j)][X(i)], ELR = Ez[X(j + 1)][X(i)], ERL = Ez[X(j)][X(i + 1)], ERR = Ez[X(j + 1)][X(i + 1)];
+      double sAL0 = +(ELR - ELL) * dtdy * half;
+      double sAR0 = +(ERR - ERL) * dtdy * half;
+      double sBL0 = -(ERL - ELL) * dtdx * half;
+      double sBR0 = -(ERR - ELR) * dtdx * half;
+      AL = AL + sAL0; AR = AR + sAR0; BL = BL + sBL0; BR = BR + sBR0;
+      double sr0 = (-u * drx - dux * r) * dtdx + (-v * dry - dvy * r) * dtdy;
+      double su0 = (-u * dux - (dpx + B * dBx + C * dCx) / r) * dtdx + (-v * duy + B * dAy / r) * dtdy;
+      double sv0 = (-u * dvx + A * dBx / r) * dtdx + (-v * dvy - (dpy + A * dAy + C * dCy) / r) * dtdy;
+      double sw0 = (-u * dwx + A * dCx / r) * dtdx + (-v * dwy + B * dCy / r) * dtdy;
+      double sp0 = (-u * dpx - dux * gamma * pp) * dtdx + (-v * dpy - dvy * gamma * pp) * dtdy;
+      double sC0 = (-u * dCx - C * dux + A * dwx) * dtdx + (-v * dCy - C * dvy + B * dwy) * dtdy;
+      r = r + sr0; u = u + su0; v = v + sv0; ww = ww + sw0; pp = pp + sp0; C = C + sC0;
+      A = 0.5 * (AL + AR); B = 0.5 * (BL + BR);
+#define SET2(arr, R, U, V, W, P_, A_, B_, C_)                          \
+  do {                                                               \
+    double* s_ = arr;                                                \
+    s_[ir] = (R); s_[iu] = (U); s_[iv] = (V); s_[iw] = (W);          \
+    s_[ip] = (P_); s_[iA] = (A_); s_[iB] = (B_); s_[iC] = (C_);      \
+    if (s_[ir] < smallr) s_[ir] = r;                                 \
+    s_[ip] = FMAX(smallp, s_[ip]);                                   \
+  } while (0)
+      double t[NV];
+#define PUT(arr, d_) for (int n_ = 0; n_ < NV; n_++) arr[X(j)][X(i)][n_][d_] = t[n_]
+      SET2(t, r - drx, u - dux, v - dvx, ww - dwx, pp - dpx, AL, B - dBx, C - dCx); PUT(qp, 0);
+      SET2(t, r + drx, u + dux, v + dvx, ww + dwx, pp + dpx, AR, B + dBx, C + dCx); PUT(qm, 0);
+      SET2(t, r - dry, u - duy, v - dvy, ww - dwy, pp - dpy, A - dAy, BL, C - dCy); PUT(qp, 1);
+      SET2(t, r + dry, u + duy, v + dvy, ww + dwy, pp + dpy, A + dAy, BR, C + dCy); PUT(qm, 1);
+      SET2(qRT[X(j)][X(i)], r + (+drx + dry), u + (+dux + duy), v + (+dvx + dvy), ww + (+dwx + dwy), pp + (+dpx + dpy), AR + (+dARy), BR + (+dBRx), C + (+dCx + dCy));
+      SET2(qRB[X(j)][X(i)], r + (+drx - dry), u + (+dux - duy), v + (+dvx - dvy), ww + (+dwx - dwy), pp + (+dpx - dpy), AR + (-dARy), BL + (+dBLx), C + (+dCx - dCy));
+      SET2(qLT[X(j)][X(i)], r + (-drx + dry), u + (-dux + duy), v + (-dvx + dvy), ww + (-dwx + dwy), pp + (-dpx + dpy), AL + (+dALy), BR + (-dBRx), C + (-dCx + dCy));
+      SET2(qLB[X(j)][X(i)], r + (-drx - dry), u + (-dux - duy), v + (-dvx - dvy), ww + (-dwx - dwy), pp + (-dpx - dpy), AL + (-dALy), BL + (-dBLx), C + (-dCx - dCy));
+#undef PUT
+#undef SET2
+    }
+  /* cmpflxm :1308 in x (2,3,4,6,7,8) and y (3,2,4,7,6,8); flux = fx*dt/dx */
+  static const int perm[2][6] = {{2, 3, 4, 6, 7, 8}, {3, 2, 4, 7, 6, 8}};
+  for (int idim = 0; idim < 2; idim++) {
+    const int ln = perm[idim][0] - 1, lt1 = perm[idim][1] - 1, lt2 = perm[idim][2] - 1;
+    const int bn = perm[idim][3] - 1, bt1 = perm[idim][4] - 1, bt2 = perm[idim][5] - 1;
+    const int i0 = idim == 0, j0 = idim == 1;
+    for (int j = 1; j <= 2 + j0; j++)
+      for (int i = 1; i <= 2 + i0; i++) {
+        double(*m_)[2] = qm[X(j - j0)][X(i - i0)];
+        double(*p_)[2] = qp[X(j)][X(i)];
+        double ql[8], qr[8], fg[9];
+        double bn_mean = half * (m_[bn][idim] + p_[bn][idim]);
+        ql[0] = m_[0][idim]; ql[1] = m_[4][idim]; ql[2] = m_[ln][idim]; ql[3] = bn_mean;
+        ql[4] = m_[lt1][idim]; ql[5] = m_[bt1][idim]; ql[6] = m_[lt2][idim]; ql[7] = m_[bt2][idim];
+        qr[0] = p_[0][idim]; qr[1] = p_[4][idim]; qr[2] = p_[ln][idim]; qr[3] = bn_mean;
+        qr[4] = p_[lt1][idim]; qr[5] = p_[bt1][idim]; qr[6] = p_[lt2][idim]; qr[7] = p_[bt2][idim];
+        riemann1d(p, ql, qr, fg);
+        double* f = w->flux[idim][j - 1][i - 1];
+        f[0] = fg[0]; f[4] = fg[1]; f[ln] = fg[2]; f[bn] = fg[3]; f[lt1] = fg[4]; f[bt1] = fg[5]; f[lt2] = fg[6]; f[bt2] = fg[7];
+        for (int n = 0; n < NV; n++) f[n] = f[n] * dt / dx;
+      }
+  }
+  /* cmp_mag_flx :1453 for E_z at the corners i,j = 1..3 */
+  for (int j = 1; j <= 3; j++)
+    for (int i = 1; i <= 3; i++)
+      w->emfz[j - 1][i - 1] = emf_from_corners(p, qRT[X(j - 1)][X(i - 1)], qRB[X(j)][X(i - 1)], qLT[X(j - 1)][X(i)], qLB[X(j)][X(i)],
+                                               2, 3, 4, 6, 7, 8) * dt / dx;
+}
+
+/* public hook for tests: mag_unsplit on one 6x6 patch uloc[j][i][11] -> flux[2][3][3][8], emfz[3][3] */
+void orc_mhd2_unsplit(const orc_mhd_params* p, const double* uloc, double dx, double dt, double* flux, double* emfz) {
+  mhd2_patch w;
+  memset(&w, 0, sizeof w);
+  memcpy(w.uloc, uloc, sizeof w.uloc);
+  mhd2_unsplit(p, &w, dx, dt);
+  memcpy(flux, w.flux, sizeof w.flux);
+  memcpy(emfz, w.emfz, sizeof w.emfz);
+}
+
+static inline double tvd1(int mt, double b0, double b1, double b2) { /* compute_1d_tvd mhd/interpol_hydro.f90:1532 */
+  if (mt == 3) { double dlft = half * (b0 - b1), drgt = half * (b2 - b0); return dlft + drgt; }
+  return slope_mm((double)mt, b1, b0, b2);
+}
+
+static int g_interpol_mag_type = 2, g_mhd_interpol_type = 2;
+void orc_mhd_set_interpol(int interpol_type, int interpol_mag_type) {
+  g_mhd_interpol_type = interpol_type;
+  g_interpol_mag_type = interpol_mag_type < 0 ? interpol_type : interpol_mag_type;   /* hydro/read_hydro_params.f90:531 */
+  orc_set_interpol(interpol_type, 0);
+}
+
+/* interpol_hydro mhd/interpol_hydro.f90:612 for one father cell, NDIM=2, interpol_var=0: u2[4][11] */
+void orc_mhd2_interpol_cell(const orc_mesh* m, int ind_cell, int ilevel, const double* uold, double* u2) {
+  int fa[5], ind1[5];
+  double u1[5 * NVS], t2[4 * NVS];
+  orc_getnborfather(m, ind_cell, ilevel, fa);
+  for (int j = 0; j < 5; j++) {
+    for (int iv = 1; iv <= NVS; iv++) u1[j * NVS + iv - 1] = UO(fa[j], iv);
+    ind1[j] = m->son[fa[j]];
+  }
+  orc_interpol_hydro(hydro_like_params(2), u1, t2);          /* variables 1..5 and 8 (cell centred); the rest is overwritten */
+  for (int ind = 0; ind < 4; ind++) {
+    for (int iv = 0; iv < NVS; iv++) u2[ind * NVS + iv] = t2[ind * NVS + iv];
+    u2[ind * NVS + NV + 2] = u2[ind * NVS + 7];              /* :712-718 */
+  }
+  /* interpol_mag :990: u[i+1][j] i=-1..1, v[i][j+1] j=-1..1 */
+  double u[3][2], v[2][3];
+  const int mt = g_interpol_mag_type;
+#define B1(j_, c_) u1[(j_)*NVS + ((c_) <= 3 ? 4 + (c_) : NV + (c_)-4)]   /* B1(j,1..3) = u1(j,6..8), B1(j,4..6) = u1(j,9..11) */
+  { /* interpol_faces :1052 */
+    double s1, s2 = 0.0;
+    s1 = 0.0; if (mt > 0) s1 = tvd1(mt, B1(0, 1), B1(3, 1), B1(4, 1));
+    for (int j = 0; j <= 1; j++) u[0][j] = B1(0, 1) + 0.5 * s1 * ((double)j - 0.5) + 0.5 * s2 * ((double)0 - 0.5);
+    s1 = 0.0; if (mt > 0) s1 = tvd1(mt, B1(0, 4), B1(3, 4), B1(4, 4));
+    for (int j = 0; j <= 1; j++) u[2][j] = B1(0, 4) + 0.5 * s1 * ((double)j - 0.5) + 0.5 * s2 * ((double)0 - 0.5);
+    s1 = 0.0; if (mt > 0) s1 = tvd1(mt, B1(0, 2), B1(1, 2), B1(2, 2));
+    for (int i = 0; i <= 1; i++) v[i][0] = B1(0, 2) + 0.5 * s1 * ((double)i - 0.5) + 0.5 * s2 * ((double)0 - 0.5);
+    s1 = 0.0; if (mt > 0) s1 = tvd1(mt, B1(0, 5), B1(1, 5), B1(2, 5));
+    for (int i = 0; i <= 1; i++) v[i][2] = B1(0, 5) + 0.5 * s1 * ((double)i - 0.5) + 0.5 * s2 * ((double)0 - 0.5);
+  }
+#undef B1
+  /* copy_from_refined_faces :1246 */
+  for (int j = 0; j <= 1; j++) {
+    if (ind1[1] > 0) u[0][j] = UO(m->ncoarse + (1 + j * 2) * m->ngridmax + ind1[1], NV + 1);
+    if (ind1[2] > 0) u[2][j] = UO(m->ncoarse + (0 + j * 2) * m->ngridmax + ind1[2], 6);
+  }
+  for (int i = 0; i <= 1; i++) {
+    if (ind1[3] > 0) v[i][0] = UO(m->ncoarse + (i + 1 * 2) * m->ngridmax + ind1[3], NV + 2);
+    if (ind1[4] > 0) v[i][2] = UO(m->ncoarse + (i + 0 * 2) * m->ngridmax + ind1[4], 7);
+  }
+  /* cmp_central_faces :1354, NDIM==2 */
+  double UXX = 0.0, VYY = 0.0;
+  for (int i = 0; i <= 1; i++)
+    for (int j = 0; j <= 1; j++) {
+      const int ii = 2 * i - 1, jj = 2 * j - 1;
+      UXX = UXX + ((double)(ii * jj) * v[i][jj + 1]) * 0.25;
+      VYY = VYY + ((double)(ii * jj) * u[ii + 1][j]) * 0.25;
+    }
+  for (int j = 0; j <= 1; j++) u[1][j] = 0.5 * (u[0][j] + u[2][j]) + UXX;
+  for (int i = 0; i <= 1; i++) v[i][1] = 0.5 * (v[i][0] + v[i][2]) + VYY;
+  for (int i = 0; i <= 1; i++)
+    for (int j = 0; j <= 1; j++) {
+      const int ind = i + 2 * j;
+      u2[ind * NVS + 5] = u[i][j];          /* B2(ind,1) = u(i-1,j) */
+      u2[ind * NVS + 6] = v[i][j];          /* B2(ind,2) = v(i,j-1) */
+      u2[ind * NVS + NV + 0] = u[i + 1][j]; /* B2(ind,4) = u(i,j)   */
+      u2[ind * NVS + NV + 1] = v[i][j + 1]; /* B2(ind,5) = v(i,j)   */
+    }
+}
+
+/* godfine1 mhd/godunov_fine.f90:538 for one batch of ncache <= nvector octs, NDIM=2 */
+static void mhd2_godfine1(const orc_mhd_params* p, const orc_mesh* m, const int* ind_grid, int ncache, int ilevel, int levelmin,
+                          double dt, const double* uold, double* unew) {
+  const double dx = level_dx(p, m, ilevel);
+  mhd2_patch* W = (mhd2_patch*)malloc(sizeof(mhd2_patch) * (size_t)ncache);
+  /* the fluxes of the octs of a batch are independent of each other (they read uold only): threads split them; every
+   * accumulation into unew below is serial and in the reference's order, so the result does not depend on the thread count */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(g_threads) if (g_threads > 1)
+#endif
+  for (int i = 0; i < ncache; i++) {
+    mhd2_patch* w = &W[i];
+    orc_get3cubefather(m, m->father[ind_grid[i]], ilevel, w->nfc, NULL);
+    for (int j1 = 0; j1 <= 2; j1++)
+      for (int i1 = 0; i1 <= 2; i1++) {
+        const int fc = w->nfc[i1 + 3 * j1];
+        const int igrid_nbor = m->son[fc];
+        double u2[4 * NVS];
+        if (igrid_nbor <= 0) orc_mhd2_interpol_cell(m, fc, ilevel, uold, u2);
+        for (int j2 = 0; j2 <= 1; j2++)
+          for (int i2 = 0; i2 <= 1; i2++) {
+            const int ind_son = i2 + 2 * j2;
+            const int i3 = 1 + 2 * (i1 - 1) + i2, j3 = 1 + 2 * (j1 - 1) + j2;
+            if (igrid_nbor > 0) {
+              const int ic = m->ncoarse + ind_son * m->ngridmax + igrid_nbor;
+              for (int iv = 1; iv <= NVS; iv++) w->uloc[X(j3)][X(i3)][iv - 1] = UO(ic, iv);
+              w->ok[X(j3)][X(i3)] = m->son[ic] > 0;
+            } else {
+              for (int iv = 0; iv < NVS; iv++) w->uloc[X(j3)][X(i3)][iv] = u2[ind_son * NVS + iv];
+              w->ok[X(j3)][X(i3)] = 0;
+            }
+          }
+      }
+    mhd2_unsplit(p, w, dx, dt);
+    /* reset flux along direction at refined interface :760-782, Euler fluxes of Bx, By :786-800,:823-837 */
+    for (int idim = 0; idim < 2; idim++) {
+      const int i0 = idim == 0, j0 = idim == 1;
+      for (int j3 = 1; j3 <= 2 + j0; j3++)
+        for (int i3 = 1; i3 <= 2 + i0; i3++) {
+          double* f = w->flux[idim][j3 - 1][i3 - 1];
+          if (w->ok[X(j3 - j0)][X(i3 - i0)] || w->ok[X(j3)][X(i3)])
+            for (int n = 0; n < NV; n++) f[n] = 0.0;
+          f[5] = 0.0;
+          f[6] = 0.0;
+        }
+    }
+    /* reset electromotive force along direction z at refined edges :805-818 */
+    for (int j3 = 1; j3 <= 3; j3++)
+      for (int i3 = 1; i3 <= 3; i3++)
+        if (w->ok[X(j3)][X(i3)] || w->ok[X(j3 - 1)][X(i3)] || w->ok[X(j3)][X(i3 - 1)] || w->ok[X(j3 - 1)][X(i3 - 1)]) w->emfz[j3 - 1][i3 - 1] = 0.0;
+  }
+  /* conservative update at level ilevel for the Euler system :886-934 */
+  for (int idim = 0; idim < 2; idim++) {
+    const int i0 = idim == 0, j0 = idim == 1;
+    for (int j2 = 0; j2 <= 1; j2++)
+      for (int i2 = 0; i2 <= 1; i2++) {
+        const int iskip = m->ncoarse + (i2 + 2 * j2) * m->ngridmax;
+        const int i3 = 1 + i2, j3 = 1 + j2;
+        for (int iv = 1; iv <= NV; iv++)
+          for (int i = 0; i < ncache; i++) {
+            const mhd2_patch* w = &W[i];
+            const int ic = iskip + ind_grid[i];
+            UN(ic, iv) = UN(ic, iv) + (w->flux[idim][j3 - 1][i3 - 1][iv - 1] - w->flux[idim][j3 + j0 - 1][i3 + i0 - 1][iv - 1]);
+          }
+        for (int iv = 1; iv <= 3; iv++)
+          for (int i = 0; i < ncache; i++) {
+            const mhd2_patch* w = &W[i];
+            const int ic = iskip + ind_grid[i];
+            UN(ic, NV + iv) = UN(ic, NV + iv) + (w->flux[idim][j3 - 1][i3 - 1][5 + iv - 1] - w->flux[idim][j3 + j0 - 1][i3 + i0 - 1][5 + iv - 1]);
+          }
+      }
+  }
+  /* conservative update at level ilevel for the induction system :939-976 (emfx = emfy = 0 in two dimensions) */
+  for (int j3 = 1; j3 <= 2; j3++)
+    for (int i3 = 1; i3 <= 2; i3++) {
+      const int iskip = m->ncoarse + ((i3 - 1) + 2 * (j3 - 1)) * m->ngridmax;
+      for (int i = 0; i < ncache; i++) {
+        const mhd2_patch* w = &W[i];
+        const int ic = iskip + ind_grid[i];
+        double dflux_x = (0.0 - 0.0) - (w->emfz[j3 - 1][i3 - 1] - w->emfz[j3][i3 - 1]);
+        UN(ic, 6) = UN(ic, 6) + dflux_x;
+        dflux_x = (0.0 - 0.0) - (w->emfz[j3 - 1][i3] - w->emfz[j3][i3]);
+        UN(ic, NV + 1) = UN(ic, NV + 1) + dflux_x;
+      }
+    }
+  for (int j3 = 1; j3 <= 2; j3++)
+    for (int i3 = 1; i3 <= 2; i3++) {
+      const int iskip = m->ncoarse + ((i3 - 1) + 2 * (j3 - 1)) * m->ngridmax;
+      for (int i = 0; i < ncache; i++) {
+        const mhd2_patch* w = &W[i];
+        const int ic = iskip + ind_grid[i];
+        double dflux_y = (w->emfz[j3 - 1][i3 - 1] - w->emfz[j3 - 1][i3]) - (0.0 - 0.0);
+        UN(ic, 7) = UN(ic, 7) + dflux_y;
+        dflux_y = (w->emfz[j3][i3 - 1] - w->emfz[j3][i3]) - (0.0 - 0.0);
+        UN(ic, NV + 2) = UN(ic, NV + 2) + dflux_y;
+      }
+    }
+  if (ilevel > levelmin) {
+    /* conservative update at level ilevel-1 for the Euler system :1030-1168 */
+    const double oneontwotondim = 0.25;
+    int* ind_buffer = (int*)malloc(sizeof(int) * (size_t)(ncache + 1));
+    int* ind_cell = (int*)malloc(sizeof(int) * (size_t)(ncache + 1));
+    for (int idim = 0; idim < 2; idim++) {
+      const int i0 = idim == 0, j0 = idim == 1;
+      for (int side = 0; side < 2; side++) {
+        int nb = 0;
+        for (int i = 0; i < ncache; i++) {
+          const int c = NBOR(m, ind_grid[i], 2 * idim + 1 + side);
+          if (m->son[c] == 0) { ind_buffer[nb] = c; ind_cell[nb] = i; nb++; }
+        }
+        const double sgn = side == 0 ? -1.0 : 1.0;
+        const int j3lo = side == 0 ? 1 : 1 + j0, j3hi = side == 0 ? 2 - j0 : 2;
+        const int i3lo = side == 0 ? 1 : 1 + i0, i3hi = side == 0 ? 2 - i0 : 2;
+        const int di = side == 0 ? 0 : i0, dj = side == 0 ? 0 : j0;
+        for (int pass = 0; pass < 2; pass++) {           /* variables 1..nvar, then nvar+1..nvar+3 <- fluxes 6..8 */
+          const int nv_ = pass == 0 ? NV : 3;
+          for (int iv = 1; iv <= nv_; iv++)
+            for (int j3 = j3lo; j3 <= j3hi; j3++)
+              for (int i3 = i3lo; i3 <= i3hi; i3++)
+                for (int i = 0; i < nb; i++) {
+                  const int dst = pass == 0 ? iv : NV + iv, src = pass == 0 ? iv - 1 : 5 + iv - 1;
+                  const double f = W[ind_cell[i]].flux[idim][j3 + dj - 1][i3 + di - 1][src] * oneontwotondim;
+                  if (side == 0) UN(ind_buffer[i], dst) = UN(ind_buffer[i], dst) - f;
+                  else UN(ind_buffer[i], dst) = UN(ind_buffer[i], dst) + f;
+                }
+        }
+        (void)sgn;
+      }
+    }
+    free(ind_buffer); free(ind_cell);
+    /* conservative update at level ilevel-1 for the induction system: the four EMFz edges :1176-1270.
+     * father-cell numbering ind_father = 1+i1+3*j1 with the centre at (1,1)                                              */
+    static const int fo[4][3][2] = {   /* (i1,j1) offsets of ind_father1,2,3 for the edges X0Y0, X0Y1, X1Y1, X1Y0 */
+        {{1, 0}, {0, 0}, {0, 1}}, {{0, 1}, {0, 2}, {1, 2}}, {{1, 2}, {2, 2}, {2, 1}}, {{2, 1}, {2, 0}, {1, 0}}};
+    static const int ec[4][2] = {{1, 1}, {1, 3}, {3, 3}, {3, 1}};   /* corner (i3,j3) of emfz */
+    for (int e = 0; e < 4; e++)
+      for (int i = 0; i < ncache; i++) {
+        const mhd2_patch* w = &W[i];
+        const int b1 = w->nfc[fo[e][0][0] + 3 * fo[e][0][1]], b2 = w->nfc[fo[e][1][0] + 3 * fo[e][1][1]],
+                  b3 = w->nfc[fo[e][2][0] + 3 * fo[e][2][1]];
+        double weight = 1.0;
+        if (m->son[b1] > 0 && m->son[b3] > 0) continue;
+        if (m->son[b1] > 0 || m->son[b2] > 0 || m->son[b3] > 0) weight = 0.5;
+        const double ez = w->emfz[ec[e][1] - 1][ec[e][0] - 1];
+        const double dflux = (ez + ez) * 0.25 * weight;            /* emfz(:,:,:,2) is a copy of emfz(:,:,:,1) umuscl.f90:190-199 */
+        const int all_leaf = m->son[b1] == 0 && m->son[b2] == 0 && m->son[b3] == 0;
+        if (e == 0) {
+          UN(b1, 6) = UN(b1, 6) + dflux;
+          UN(b2, NV + 1) = UN(b2, NV + 1) + dflux;
+          UN(b2, NV + 2) = UN(b2, NV + 2) - dflux;
+          UN(b3, 7) = UN(b3, 7) - dflux;
+          if (all_leaf) { UN(b3, NV + 1) = UN(b3, NV + 1) - dflux * 0.5; UN(b1, NV + 2) = UN(b1, NV + 2) + dflux * 0.5; }
+        } else if (e == 1) {
+          UN(b1, NV + 2) = UN(b1, NV + 2) - dflux;
+          UN(b2, 7) = UN(b2, 7) - dflux;
+          UN(b2, NV + 1) = UN(b2, NV + 1) - dflux;
+          UN(b3, 6) = UN(b3, 6) - dflux;
+          if (all_leaf) { UN(b3, 7) = UN(b3, 7) + dflux * 0.5; UN(b1, NV + 1) = UN(b1, NV + 1) + dflux * 0.5; }
+        } else if (e == 2) {
+          UN(b1, NV + 1) = UN(b1, NV + 1) - dflux;
+          UN(b2, 6) = UN(b2, 6) - dflux;
+          UN(b2, 7) = UN(b2, 7) + dflux;
+          UN(b3, NV + 2) = UN(b3, NV + 2) + dflux;
+          if (all_leaf) { UN(b3, 6) = UN(b3, 6) + dflux * 0.5; UN(b1, 7) = UN(b1, 7) - dflux * 0.5; }
+        } else {
+          UN(b1, 7) = UN(b1, 7) + dflux;
+          UN(b2, NV + 2) = UN(b2, NV + 2) + dflux;
+          UN(b2, 6) = UN(b2, 6) + dflux;
+          UN(b3, NV + 1) = UN(b3, NV + 1) + dflux;
+          if (all_leaf) { UN(b3, NV + 2) = UN(b3, NV + 2) - dflux * 0.5; UN(b1, 6) = UN(b1, 6) - dflux * 0.5; }
+        }
+      }
+  }
+  free(W);
+}
+
+void orc_mhd2_godunov_fine(const orc_mhd_params* p, const orc_mesh* m, int ilevel, int levelmin, int nvector, double dt,
+                           const double* uold, double* unew) {
+  if (m->ndim != 2) { fprintf(stderr, "oracle(mhd 2-D): NDIM=%d\n", m->ndim); abort(); }
+  const int ncache = m->nactive[ilevel];
+  for (int ig = 0; ig < ncache; ig += nvector) {
+    const int ngrid = (nvector < ncache - ig) ? nvector : ncache - ig;
+    mhd2_godfine1(p, m, m->active[ilevel] + ig, ngrid, ilevel, levelmin, dt, uold, unew);
+  }
+}
+
+/* courant_fine mhd/courant_fine.f90 + cmpdt mhd/godunov_utils.f90:5 for any NDIM (ctot sums idim = 1..ndim) */
+double orc_mhdn_courant_fine(const orc_mhd_params* p, const orc_mesh* m, int ilevel, double dt_in, const double* uold) {
+  const double dx = level_dx(p, m, ilevel);
+  const double smallp = p->smallr * (p->smallc * p->smallc) / p->gamma;
+  const int T = 1 << m->ndim;
+  double dt_loc = dt_in;
+  for (int a = 0; a < m->nactive[ilevel]; a++)
+    for (int ind = 0; ind < T; ind++) {
+      int ic = m->active[ilevel][a] + m->ncoarse + ind * m->ngridmax;
+      if (m->son[ic] != 0) continue;
+      double uu[NVS];
+      for (int iv = 1; iv <= NVS; iv++) uu[iv - 1] = UO(ic, iv);
+      uu[0] = FMAX(uu[0], p->smallr);
+      double rho = uu[0];
+      for (int d = 1; d <= 3; d++) uu[d] = uu[d] / rho;
+      double B2 = zero;
+      for (int d = 1; d <= 3; d++) {
+        double Bc = half * (uu[4 + d] + uu[NV + d - 1]);
+        B2 = B2 + Bc * Bc;
+        uu[4] = uu[4] - half * uu[0] * (uu[d] * uu[d]) - half * (Bc * Bc);
+      }
+      uu[4] = FMAX((p->gamma - one) * uu[4], smallp);
+      double a2 = p->gamma * uu[4] / uu[0];
+      double ctot = zero;
+      for (int d = 1; d <= m->ndim; d++) { /* WARNING: ndim instead of 3 */
+        double cc = half * (B2 / rho + a2);
+        double BN = half * (uu[4 + d] + uu[NV + d - 1]);
+        double cf = sqrt(cc + sqrt(cc * cc - a2 * (BN * BN) / rho));
+        ctot = ctot + fabs(uu[d]) + cf;
+      }
+      double r = zero * dx / (ctot * ctot);
+      r = FMAX(r, 0.0001);
+      double dt = p->courant_factor * dx / p->smallc;
+      double dtcell = dx / ctot * (sqrt(one + two * p->courant_factor * r) - one) / r;
+      dt = FMIN(dt, dtcell);
+      dt_loc = FMIN(dt_loc, dt);
+    }
+  return FMIN(dt_in, dt_loc);
+}
+
+/* upload_fine mhd/interpol_hydro.f90:5-231 + upl :233, upl_left :516, upl_right :564 for NDIM = 1,2,3, interpol_var=0.
+ * The reference applies upl batch by batch (cells of one position of nvector octs); the restriction of one cell only reads
+ * its own sons, and the face pass (:70-231) only reads fine cells, so the order is immaterial.                            */
+void orc_mhdn_upload_fine(const orc_mhd_params* p, const orc_mesh* m, int ilevel, double* uold) {
+  static const int hhh[6][4] = {{1, 3, 5, 7}, {2, 4, 6, 8}, {1, 2, 5, 6}, {3, 4, 7, 8}, {1, 2, 3, 4}, {5, 6, 7, 8}};
+  static const int iii[3][2][8] = {{{1, 0, 1, 0, 1, 0, 1, 0}, {0, 2, 0, 2, 0, 2, 0, 2}},
+                                   {{3, 3, 0, 0, 3, 3, 0, 0}, {0, 0, 4, 4, 0, 0, 4, 4}},
+                                   {{5, 5, 5, 5, 0, 0, 0, 0}, {0, 0, 0, 0, 6, 6, 6, 6}}};
+  static const int jjj[3][2][8] = {{{2, 1, 4, 3, 6, 5, 8, 7}, {2, 1, 4, 3, 6, 5, 8, 7}},
+                                   {{3, 4, 1, 2, 7, 8, 5, 6}, {3, 4, 1, 2, 7, 8, 5, 6}},
+                                   {{5, 6, 7, 8, 1, 2, 3, 4}, {5, 6, 7, 8, 1, 2, 3, 4}}};
+  const int ndim = m->ndim, T = 1 << ndim, Th = T / 2;
+  if (ilevel == m->nlevelmax) return;
+  for (int a = 0; a < m->nactive[ilevel]; a++)
+    for (int ind = 0; ind < T; ind++) {
+      const int ic = m->ncoarse + ind * m->ngridmax + m->active[ilevel][a];
+      const int gs = m->son[ic];
+      if (gs <= 0) continue;
+      double getx = 0.0;
+      for (int is = 0; is < T; is++) getx = getx + FMAX(UO(m->ncoarse + is * m->ngridmax + gs, 1), p->smallr);
+      UO(ic, 1) = getx / (double)T;
+      for (int iv = 2; iv <= NV; iv++)
+        if (iv <= 5 || iv > 5 + ndim) {
+          getx = 0.0;
+          for (int is = 0; is < T; is++) getx = getx + UO(m->ncoarse + is * m->ngridmax + gs, iv);
+          UO(ic, iv) = getx / (double)T;
+        }
+      if (ndim == 1) { UO(ic, NV + 2) = UO(ic, 7); UO(ic, NV + 3) = UO(ic, 8); }
+      if (ndim == 2) UO(ic, NV + 3) = UO(ic, 8);
+      for (int idim = 1; idim <= ndim; idim++) {
+        getx = 0.0;
+        for (int k = 0; k < Th; k++) getx = getx + UO(m->ncoarse + (hhh[2 * idim - 2][k] - 1) * m->ngridmax + gs, 5 + idim);
+        UO(ic, 5 + idim) = getx / (double)Th;
+        getx = 0.0;
+        for (int k = 0; k < Th; k++) getx = getx + UO(m->ncoarse + (hhh[2 * idim - 1][k] - 1) * m->ngridmax + gs, NV + idim);
+        UO(ic, NV + idim) = getx / (double)Th;
+      }
+    }
+  for (int a = 0; a < m->nactive[ilevel]; a++) {
+    const int ig = m->active[ilevel][a];
+    int igridn[7];
+    igridn[0] = ig;
+    for (int idim = 1; idim <= ndim; idim++) {
+      igridn[2 * idim - 1] = m->son[NBOR(m, ig, 2 * idim - 1)];
+      igridn[2 * idim] = m->son[NBOR(m, ig, 2 * idim)];
+    }
+    for (int ind = 0; ind < T; ind++) {
+      const int ic = m->ncoarse + ind * m->ngridmax + ig;
+      if (m->son[ic] != 0) continue;
+      for (int idim = 1; idim <= ndim; idim++) {
+        int g = igridn[iii[idim - 1][0][ind]];
+        if (g > 0) {
+          const int sc = m->son[g + m->ncoarse + (jjj[idim - 1][0][ind] - 1) * m->ngridmax];
+          if (sc > 0) {   /* upl_left: left B of the leaf = mean of the right B of the touching sons */
+            double getx = 0.0;
+            for (int k = 0; k < Th; k++) getx = getx + UO(m->ncoarse + (hhh[2 * idim - 1][k] - 1) * m->ngridmax + sc, NV + idim);
+            UO(ic, 5 + idim) = getx / (double)Th;
+          }
+        }
+        g = igridn[iii[idim - 1][1][ind]];
+        if (g > 0) {
+          const int sc = m->son[g + m->ncoarse + (jjj[idim - 1][1][ind] - 1) * m->ngridmax];
+          if (sc > 0) {   /* upl_right */
+            double getx = 0.0;
+            for (int k = 0; k < Th; k++) getx = getx + UO(m->ncoarse + (hhh[2 * idim - 2][k] - 1) * m->ngridmax + sc, 5 + idim);
+            UO(ic, NV + idim) = getx / (double)Th;
+          }
+        }
+      }
+    }
+  }
+}
+
+/* condinit of the Orszag-Tang patch (tests/mhd/orszag-tang/condinit.f90:5-82) for the active octs of a level, NDIM=2:
+ * face fields from the vector potential A_z, so that div B = 0 to round-off on every level.                              */
+void orc_mhd2_condinit_orszag_tang(const orc_mhd_params* p, const orc_mesh* m, int ilevel, double* uold) {
+  const int nx_loc = m->icoarse_max - m->icoarse_min + 1;
+  const double scale = p->boxlen / (double)nx_loc;
+  const double dxl = pow(0.5, ilevel);
+  const double dx = dxl * scale;                      /* dx_loc handed to condinit (mhd/init_flow_fine.f90) */
+  const double pi = acos(-1.0);
+  const double B0 = 1.0 / sqrt(4.0 * pi);
+  const double skip[2] = {(double)m->icoarse_min, (double)m->jcoarse_min};
+  for (int a = 0; a < m->nactive[ilevel]; a++) {
+    const int ig = m->active[ilevel][a];
+    for (int ind = 0; ind < 4; ind++) {
+      const double xcell[2] = {((double)(ind & 1) - 0.5) * dxl, ((double)((ind >> 1) & 1) - 0.5) * dxl};
+      double x[2];
+      for (int d = 0; d < 2; d++) x[d] = (m->xg[(size_t)d * (m->ngridmax + 1) + ig] + xcell[d] - skip[d]) * scale;
+      const double xl = x[0] - 0.5 * dx, xr = x[0] + 0.5 * dx, xc = x[0];
+      const double yl = x[1] - 0.5 * dx, yr = x[1] + 0.5 * dx, yc = x[1];
+      double q[NVS];
+      q[0] = 25.0 / (36.0 * pi);
+      q[1] = -sin(2.0 * pi * yc);
+      q[2] = +sin(2.0 * pi * xc);
+      q[3] = 0.0;
+      q[4] = 5.0 / (12.0 * pi);
+      double Ar, Al;
+      Ar = B0 * (cos(4.0 * pi * xl) / (4.0 * pi) + cos(2.0 * pi * yr) / (2.0 * pi));
+      Al = B0 * (cos(4.0 * pi * xl) / (4.0 * pi) + cos(2.0 * pi * yl) / (2.0 * pi));
+      q[5] = (Ar - Al) / dx;
+      Ar = B0 * (cos(4.0 * pi * xr) / (4.0 * pi) + cos(2.0 * pi * yr) / (2.0 * pi));
+      Al = B0 * (cos(4.0 * pi * xr) / (4.0 * pi) + cos(2.0 * pi * yl) / (2.0 * pi));
+      q[NV + 0] = (Ar - Al) / dx;
+      Ar = B0 * (cos(4.0 * pi * xr) / (4.0 * pi) + cos(2.0 * pi * yl) / (2.0 * pi));
+      Al = B0 * (cos(4.0 * pi * xl) / (4.0 * pi) + cos(2.0 * pi * yl) / (2.0 * pi));
+      q[6] = (Al - Ar) / dx;
+      Ar = B0 * (cos(4.0 * pi * xr) / (4.0 * pi) + cos(2.0 * pi * yr) / (2.0 * pi));
+      Al = B0 * (cos(4.0 * pi * xl) / (4.0 * pi) + cos(2.0 * pi * yr) / (2.0 * pi));
+      q[NV + 1] = (Al - Ar) / dx;
+      q[7] = 0.0;
+      q[NV + 2] = 0.0;
+      const int ic = m->ncoarse + ind * m->ngridmax + ig;
+      double e = 0.0;
+      e = e + 0.5 * q[0] * (q[1] * q[1]);
+      e = e + 0.5 * q[0] * (q[2] * q[2]);
+      e = e + 0.5 * q[0] * (q[3] * q[3]);
+      e = e + q[4] / (p->gamma - 1.0);
+      e = e + 0.125 * SQ(q[5] + q[NV + 0]);
+      e = e + 0.125 * SQ(q[6] + q[NV + 1]);
+      e = e + 0.125 * SQ(q[7] + q[NV + 2]);
+      UO(ic, 1) = q[0];
+      UO(ic, 2) = q[0] * q[1]; UO(ic, 3) = q[0] * q[2]; UO(ic, 4) = q[0] * q[3];
+      UO(ic, 5) = e;
+      for (int n = 0; n < 3; n++) { UO(ic, 6 + n) = q[5 + n]; UO(ic, NV + 1 + n) = q[NV + n]; }
+    }
+  }
+}
+
+/* hydro_flag hydro/hydro_flag.f90:1 with hydro_refine of the MHD build (mhd/godunov_utils.f90:113-310) */
+static int mhd_hydro_refine(const orc_mhd_params* p, const double* ug_, const double* um_, const double* ud_, const double err[7],
+                            const double flo[7]) {
+  double u[3][NVS], emag[3];
+  const double* src[3] = {ug_, um_, ud_};
+  for (int s = 0; s < 3; s++) {
+    for (int v = 0; v < NVS; v++) u[s][v] = src[s][v];
+    u[s][0] = FMAX(u[s][0], p->smallr);
+    for (int d = 1; d <= 3; d++) u[s][d] = u[s][d] / u[s][0];
+    double ek = 0.0, em = 0.0;
+    for (int d = 1; d <= 3; d++) ek = ek + half * u[s][0] * (u[s][d] * u[s][d]);
+    for (int d = 0; d < 3; d++) em = em + half * SQ(half * (u[s][5 + d] + u[s][NV + d]));
+    u[s][4] = (p->gamma - one) * (u[s][4] - ek - em);
+    emag[s] = em;
+  }
+  const double *g = u[0], *c = u[1], *d_ = u[2];
+  int ok = 0;
+#define ERR2(a_, b_, c_, fl_) (2.0 * FMAX(fabs(((c_) - (b_)) / ((c_) + (b_) + (fl_))), fabs(((b_) - (a_)) / ((b_) + (a_) + (fl_)))))
+  if (err[0] >= 0.0) ok = ok || ERR2(g[0], c[0], d_[0], flo[0]) > err[0];
+  if (err[1] >= 0.0) ok = ok || ERR2(g[4], c[4], d_[4], flo[1]) > err[1];
+  if (err[2] >= 0.0) ok = ok || ERR2(emag[0], emag[1], emag[2], flo[2]) > err[2];
+  for (int k = 0; k < 3; k++)
+    if (err[3 + k] >= 0.0) {
+      double vg = 0.5 * (g[5 + k] + g[NV + k]), vm = 0.5 * (c[5 + k] + c[NV + k]), vd = 0.5 * (d_[5 + k] + d_[NV + k]);
+      double cg = sqrt(emag[0]), cm = sqrt(emag[1]), cd = sqrt(emag[2]);
+      double e = 2.0 * FMAX(fabs((vd - vm) / (cd + cm + flo[3 + k])), fabs((vm - vg) / (cm + cg + flo[3 + k])));
+      ok = ok || e > err[3 + k];
+    }
+  if (err[6] >= 0.0) {
+    const double f2 = flo[6] * flo[6];
+    for (int k = 1; k <= 3; k++) {
+      double vg = g[k], vm = c[k], vd = d_[k];
+      double cg = sqrt(FMAX(p->gamma * g[4] / g[0], f2)), cm = sqrt(FMAX(p->gamma * c[4] / c[0], f2)), cd = sqrt(FMAX(p->gamma * d_[4] / d_[0], f2));
+      double e = 2.0 * FMAX(fabs((vd - vm) / (cd + cm + fabs(vd) + fabs(vm) + flo[6])), fabs((vm - vg) / (cm + cg + fabs(vm) + fabs(vg) + flo[6])));
+      ok = ok || e > err[6];
+    }
+  }
+#undef ERR2
+  return ok;
+}
+
+void orc_amr_mhd_hydro_flag(const orc_mhd_params* p, const orc_mesh* m, int l, const double* uold, int* flag1, const double err[7],
+                            const double flo[7]) {
+  const int ndim = m->ndim, T = 1 << ndim;
+  double ug[NVS], um[NVS], ud[NVS];
+  for (int a = 0; a < m->nactive[l]; a++) {
+    const int ig = m->active[l][a];
+    int gn[7];
+    gn[0] = ig;
+    for (int j = 1; j <= 2 * ndim; j++) { const int c = NBOR(m, ig, j); gn[j] = c > 0 ? m->son[c] : 0; }
+    for (int ind = 0; ind < T; ind++) {
+      const int c = m->ncoarse + ind * m->ngridmax + ig;
+      int nc[6];
+      for (int d = 0; d < ndim; d++)
+        for (int s = 0; s < 2; s++) {                 /* getnborcells amr/nbors_utils.f90:363 */
+          const int bit = (ind >> d) & 1, ind2 = ind ^ (1 << d);
+          const int g = bit != s ? gn[0] : gn[2 * d + s + 1];
+          nc[2 * d + s] = g > 0 ? m->ncoarse + ind2 * m->ngridmax + g : NBOR(m, ig, 2 * d + s + 1);
+        }
+      int ok = 0;
+      for (int d = 0; d < ndim; d++) {
+        for (int v = 1; v <= NVS; v++) { ug[v - 1] = UO(nc[2 * d], v); um[v - 1] = UO(c, v); ud[v - 1] = UO(nc[2 * d + 1], v); }
+        ok = ok || mhd_hydro_refine(p, ug, um, ud, err, flo);
+      }
+      if (ok) flag1[c] = 1;
     }
   }
 }

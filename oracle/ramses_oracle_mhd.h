@@ -54,6 +54,21 @@ double orc_mhd1_courant_fine(const orc_mhd_params*, const orc_mesh*, int ilevel,
 void orc_mhd1_make_boundary_hydro(const orc_mhd_params*, const orc_mesh*, int ilevel, double* uold);
 void orc_mhd1_upload_fine(const orc_mhd_params*, const orc_mesh*, int ilevel, double* uold);
 
+
+/* NDIM = 2 with AMR (tests/mhd/orszag-tang) and dimension-generic passes */
+void orc_mhd_set_interpol(int interpol_type, int interpol_mag_type);
+void orc_mhd2_unsplit(const orc_mhd_params*, const double* uloc /*[6][6][11] (j,i,ivar)*/, double dx, double dt,
+                      double* flux /*[2][3][3][8] (idim,j3,i3,ivar)*/, double* emfz /*[3][3] (j3,i3)*/);
+void orc_mhd2_interpol_cell(const orc_mesh*, int ind_cell, int ilevel, const double* uold, double* u2 /*[4][11]*/);
+void orc_mhd2_godunov_fine(const orc_mhd_params*, const orc_mesh*, int ilevel, int levelmin, int nvector, double dt, const double* uold, double* unew);
+double orc_mhdn_courant_fine(const orc_mhd_params*, const orc_mesh*, int ilevel, double dt_in, const double* uold);
+void orc_mhdn_upload_fine(const orc_mhd_params*, const orc_mesh*, int ilevel, double* uold);
+/* tests/mhd/orszag-tang/condinit.f90 on the active octs of a level */
+void orc_mhd2_condinit_orszag_tang(const orc_mhd_params*, const orc_mesh*, int ilevel, double* uold);
+/* hydro_flag (hydro/hydro_flag.f90, SOLVERmhd) + hydro_refine mhd/godunov_utils.f90:113; err/flo = (d, p, b2, A, B, C, u) */
+void orc_amr_mhd_hydro_flag(const orc_mhd_params*, const orc_mesh*, int ilevel, const double* uold, int* flag1,
+                            const double err[7], const double flo[7]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,3 +174,90 @@ def test_imhd_tube_exact_solution():
     for k in lim:
         assert e64[k] < lim[k], (k, e64)
         assert e64[k] < 0.9 * e32[k], (k, e32, e64)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# NDIM=2 restatement (pinned by the orszag-tang golden file) against the NDIM=3 restatement (the GPU kernels' oracle)
+def _patch_2d(gamma, with_z):
+    n, h = 6, 1 / 16.0
+    x = (np.arange(n) + 0.5) * h
+    X, Y = np.meshgrid(x, x, indexing="xy")        # [j][i]
+    az = lambda xx, yy: 0.3 * np.cos(2 * np.pi * xx) * np.sin(2 * np.pi * yy) + 0.1 * xx - 0.2 * yy
+    xl, xr, yl, yr = X - h / 2, X + h / 2, Y - h / 2, Y + h / 2
+    bxl = (az(xl, yr) - az(xl, yl)) / h
+    bxr = (az(xr, yr) - az(xr, yl)) / h
+    byl = -(az(xr, yl) - az(xl, yl)) / h
+    byr = -(az(xr, yr) - az(xl, yr)) / h
+    d = 1 + 0.3 * np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y)
+    u = 0.4 * np.sin(2 * np.pi * Y)
+    v = -0.3 * np.cos(2 * np.pi * X)
+    w = 0.2 * np.sin(2 * np.pi * (X + Y)) if with_z else 0.0 * X
+    bz = 0.25 * np.cos(2 * np.pi * (X - Y)) if with_z else 0.0 * X
+    P = 1 + 0.2 * np.cos(2 * np.pi * (X + 2 * Y))
+    e = P / (gamma - 1) + 0.5 * d * (u * u + v * v + w * w) + 0.125 * ((bxl + bxr) ** 2 + (byl + byr) ** 2 + (2 * bz) ** 2)
+    return np.ascontiguousarray(np.stack([d, d * u, d * v, d * w, e, bxl, byl, bz, bxr, byr, bz], axis=-1)), h
+
+
+@pytest.mark.parametrize("r1,r2,st", [("hlld", "hlld", 2), ("llf", "llf", 1), ("roe", "roe", 2), ("hll", "hll", 0), ("hlld", "hlla", 1),
+                                      ("upwind", "upwind", 2), ("roe", "llf", 0)])
+def test_unsplit_2d_equals_z_invariant_3d(orc, r1, r2, st):
+    """mag_unsplit of the NDIM=2 restatement (trace2d, E_z only) on a 6x6 patch == mag_unsplit of the NDIM=3 restatement on the
+    z-invariant 6x6x6 patch, BIT FOR BIT, for in-plane fields (w = B_z = 0): x and y fluxes of all eight variables and E_z.
+    The NDIM=2 code reproduces the reference's orszag-tang golden file; this carries that pin over to trace3d / cmpflxm /
+    cmp_mag_flx of the NDIM=3 code (the z paths are tied to x and y by the axis-permutation test above)."""
+    import ctypes as C
+    L = orc.lib()
+    pp, dp = C.POINTER(orc.MhdParams), C.POINTER(C.c_double)
+    L.orc_mhd2_unsplit.argtypes = [pp, dp, C.c_double, C.c_double, dp, dp]
+    L.orc_mhd_work_new.restype = C.c_void_p
+    L.orc_mhd_work_free.argtypes = [C.c_void_p]
+    for f in (L.orc_mhd_work_uloc, L.orc_mhd_work_flux):
+        f.restype, f.argtypes = dp, [C.c_void_p]
+    L.orc_mhd_work_emf.restype, L.orc_mhd_work_emf.argtypes = dp, [C.c_void_p, C.c_int]
+    L.orc_mhd_unsplit.argtypes = [pp, C.c_void_p, C.c_double, C.c_double]
+    pm = orc.make_mhd_params(slope_type=st, riemann=r1, riemann2d=r2, gamma=5 / 3.)
+    U2, h = _patch_2d(pm.gamma, with_z=False)
+    flux2, emfz2 = np.zeros((2, 3, 3, 8)), np.zeros((3, 3))
+    dx, dt = h, 0.3 * h
+    L.orc_mhd2_unsplit(C.byref(pm), orc.dptr(U2), dx, dt, orc.dptr(flux2), orc.dptr(emfz2))
+    w = L.orc_mhd_work_new()
+    U3 = np.ascontiguousarray(np.broadcast_to(U2[None], (6, 6, 6, 11)))
+    C.memmove(L.orc_mhd_work_uloc(w), U3.ctypes.data, U3.nbytes)
+    L.orc_mhd_unsplit(C.byref(pm), w, dx, dt)
+    f3 = np.ctypeslib.as_array(L.orc_mhd_work_flux(w), shape=(3, 3, 3, 3, 8)).copy()
+    ez3 = np.ctypeslib.as_array(L.orc_mhd_work_emf(w, 2), shape=(3, 3, 3)).copy()
+    ex3 = np.ctypeslib.as_array(L.orc_mhd_work_emf(w, 0), shape=(3, 3, 3)).copy()
+    ey3 = np.ctypeslib.as_array(L.orc_mhd_work_emf(w, 1), shape=(3, 3, 3)).copy()
+    L.orc_mhd_work_free(w)
+    assert np.abs(flux2).max() > 0.1 and np.abs(emfz2).max() > 0.05
+    for k3 in range(2):
+        assert np.array_equal(flux2[0, 0:2, 0:3], f3[0, k3, 0:2, 0:3])
+        assert np.array_equal(flux2[1, 0:3, 0:2], f3[1, k3, 0:3, 0:2])
+        assert np.array_equal(emfz2, ez3[k3])
+    if r2 != "hlla":          # (hlla divides by the in-plane Alfven speed, 0/0 for the x and y edges of an in-plane field)
+        assert np.abs(ex3).max() == 0.0 and np.abs(ey3).max() == 0.0      # no E_x, E_y for in-plane fields
+
+
+def test_orszag_tang_small_run_invariants(orc):
+    """a short 2-D AMR run (levels 4..6): div B = 0 to round-off on every leaf cell through prolongation, refluxing and
+    restriction; mass and total energy conserved to round-off; the run refines (three levels populated)."""
+    from oracle.amr_mhd import MhdAmrRun2D
+
+    def totals(r):
+        U = r.uold.reshape(11, r.ncell)
+        tot = np.zeros(5)
+        for l, ind, ig, c in r.leaf_cells():
+            tot += U[0:5, c - 1].sum(axis=1) * (0.5 ** l) ** 2
+        return tot
+    kw = dict(riemann="hlld", riemann2d="hlld", slope_type=2, gamma=1.6666667, courant_factor=0.8, err_grad_p=0.1,
+              interpol_type=2, tout=[0.1], nexpand=1, ngridmax=20000)
+    r0 = MhdAmrRun2D(4, 6, 1.0, nsubcycle=[1], **kw)
+    r0.flag_coarse(); r0.init_refine(); r0.init_refine_2()
+    t0 = totals(r0)
+    r = MhdAmrRun2D(4, 6, 1.0, nsubcycle=[1], **kw)
+    snap = r.run()
+    assert snap["grids"][5] > 0 and snap["grids"][6] > 0
+    assert r.divb_max() < 5e-15
+    t1 = totals(r)
+    assert abs(t1[0] - t0[0]) <= 2e-15 * t0[0] and abs(t1[4] - t0[4]) <= 2e-15 * t0[4]
+    assert abs(t1[1]) < 1e-14 and abs(t1[2]) < 1e-14
