@@ -12,20 +12,26 @@
  *   mhd/courant_fine.f90  courant_fine:1
  *   mhd/hydro_boundary.f90 make_boundary_hydro:1 (reflexive :141-222, zero-gradient :223-296)
  *
- * Scope: NDIM=3 on uniform grids (levelmin=levelmax: every neighbouring oct exists) and NDIM=1 with AMR (end of the file);
+ * Scope: NDIM=3 on uniform grids (levelmin=levelmax: every neighbouring oct exists), NDIM=1 and NDIM=2 with AMR (end of the
+ * file: trace1d / trace2d, interpol_hydro + interpol_mag, EMF refluxing, upload_fine with face-centred restriction);
  * nvar=8 (no passive scalars, NENER=0), no gravity, ischeme=muscl, pressure_fix=.false., allow_switch_solver=.false.
  *
- * PARITY PINNING STATUS: PINNED for the 1-D AMR hlld path against the reference's golden file, at the reference's tolerance.
- *   tests/mhd/imhd-tube/imhd-tube-ref.dat (NDIM=1, AMR levels 5..15, riemann='hlld', slope_type=0, zero-gradient ends,
- *   interpol_type=2) is reproduced by oracle/amr_mhd.py + the NDIM=1 routines at the end of this file: ncells=437, level
- *   and x sums exact, every other sum (density, pressure, three velocities, six face fields, time) to <= 1.8e-15 relative
- *   (tolerance of the reference's check_solution: 3e-13) after 259 coarse / 16576 fine steps -- tests/test_oracle_golden.py.
- *   That run exercises find_mhd_flux, hlld, find_speed_fast, cmpdt, the shared limiter, the MHD prolongation / restriction
- *   / refluxing and boundary code.  NOT covered by a golden file (the reference has none): the NDIM=3 specific parts
- *   (trace3d, cmp_mag_flx and the 2-D solvers, the CT update) and roe / hll / llf; those rest on the exact Ryu-Jones
- *   solution shipped with the reference (3-D run converges to it), axis-permutation covariance, div B = 0, conservation
- *   and the B=0 limit against the golden-pinned hydro oracle (tests/test_oracle_mhd.py).  tests/mhd/orszag-tang (NDIM=2
- *   AMR) needs trace2d and the 2-D divergence-free prolongation: not restated.
+ * PARITY PINNING STATUS: PINNED against BOTH golden files the reference holds for the MHD build, at the reference's tolerance
+ * (check_solution: 3e-13), tests/test_oracle_golden.py:
+ *   1. tests/mhd/imhd-tube/imhd-tube-ref.dat (NDIM=1, AMR levels 5..15, riemann='hlld', slope_type=0, zero-gradient ends,
+ *      interpol_type=2) by oracle/amr_mhd.py::MhdAmrRun + the NDIM=1 routines: ncells=437, level and x sums exact, every other
+ *      sum (density, pressure, three velocities, six face fields, time) to <= 1.8e-15 after 259 coarse / 16576 fine steps.
+ *   2. tests/mhd/orszag-tang/orszag-tang-ref.dat (NDIM=2, AMR levels 5..9, riemann='hlld', riemann2d='hlld', slope_type=2,
+ *      periodic, the patch's condinit.f90) by MhdAmrRun2D + the NDIM=2 routines: ncells=100066, level, dx, x, y exact; density,
+ *      pressure, velocities, the four in-plane face-field sums and time to <= 1.9e-15 after 174 coarse / 1236 fine steps; div B
+ *      stays at round-off.  This pins trace2d, the hlld 1-D solver, the hlld corner-EMF solver of cmp_mag_flx, the CT update,
+ *      the divergence-free prolongation, the EMF refluxing, the face-centred restriction, cmpdt and hydro_refine.
+ *   3. carried over to NDIM=3 (the code the GPU kernels are compared with): mag_unsplit of the NDIM=2 routines equals
+ *      mag_unsplit of the NDIM=3 routines on z-invariant patches BIT FOR BIT for in-plane fields, all solver pairs
+ *      (tests/test_oracle_mhd.py::test_unsplit_2d_equals_z_invariant_3d); the z paths are tied to x, y by the axis-permutation
+ *      covariance test.  roe / hll / llf / upwind have no golden file in the reference; they share everything but the solver
+ *      body with the pinned hlld path and are held by solver-consistency tests, the exact Ryu-Jones solution shipped with
+ *      the reference, div B = 0, conservation and the B=0 limit against the golden-pinned hydro oracle.
  */
 #include "ramses_oracle_mhd.h"
 
