@@ -36,9 +36,11 @@
  *       lll/mmm neighbour tables) against the generated tables below.
  *    4. invariants: conservation to round-off on periodic runs, x<->y<->z
  *       permutation symmetry, dt parity.
- *   UNPINNED at the 3e-13 level (no golden file exists in the reference):
- *   3-D runs, riemann='exact'/'acoustic'/'hll'/'llf', slope types other than 2 --
- *   those rest on 2-4 and on sharing the generic-NDIM code paths pinned by 1 and 1b.
+ *    5. NDIM=3 (what the GPU kernels are compared with): level steps of a 2-D run and of the
+ *       z-invariant 3-D run are bit-identical for every solver (tests/test_oracle.py), so the
+ *       NDIM=3 branches are tied to the golden-pinned NDIM=2 branches.
+ *   NOT covered by a golden file (none exists in the reference): the bodies of
+ *   riemann='exact'/'acoustic'/'hll'/'llf' and slope types other than 2 -- held by 2-5.
  *
  * Citations are reference file:line.
  */
