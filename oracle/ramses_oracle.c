@@ -1473,51 +1473,101 @@ void orc_getnborfather(const orc_mesh* m, int ind_cell, int ilevel, int* ind_fat
     }
 }
 
+/* the three slope routines of hydro/interpol_hydro.f90 for one variable: a[0..2*ndim] -> w[ndim] */
+static void interpol_slopes(int ndim, int type, const double* a, double* w, const double xc[8][3]) {
+  const int twotondim = ipow2(ndim), twondim = 2 * ndim;
+  for (int d = 0; d < ndim; d++) w[d] = 0.0;
+  if (type == 1) { /* compute_limiter_minmod :449-470 */
+    for (int d = 0; d < ndim; d++) {
+      double dl = 0.5 * (a[2 * d + 2] - a[0]), dr = 0.5 * (a[0] - a[2 * d + 1]), mm;
+      if (dl * dr <= 0.0) mm = 0; else mm = FMIN(fabs(dl), fabs(dr)) * dl / fabs(dl);
+      w[d] = mm;
+    }
+  } else if (type == 2) { /* compute_limiter_central :481-613 */
+    double ac[8];
+    for (int d = 0; d < ndim; d++) w[d] = 0.25 * (a[2 * d + 2] - a[2 * d + 1]);
+    for (int ind = 0; ind < twotondim; ind++) ac[ind] = a[0];
+    for (int d = 0; d < ndim; d++)
+      for (int ind = 0; ind < twotondim; ind++) ac[ind] = ac[ind] + 2.0 * w[d] * xc[ind][d];
+    double corner = ac[0], kernel = a[1];
+    for (int j = 1; j < twotondim; j++) corner = FMAX(corner, ac[j]);
+    for (int j = 2; j <= twondim; j++) kernel = FMAX(kernel, a[j]);
+    double dk = a[0] - kernel, dc = a[0] - corner, maxl = 0.0, minl = 0.0;
+    if (dk * dc > 0.0) maxl = FMIN(1.0, dk / dc);
+    corner = ac[0]; kernel = a[1];
+    for (int j = 1; j < twotondim; j++) corner = FMIN(corner, ac[j]);
+    for (int j = 2; j <= twondim; j++) kernel = FMIN(kernel, a[j]);
+    dk = a[0] - kernel; dc = a[0] - corner;
+    if (dk * dc > 0.0) minl = FMIN(1.0, dk / dc);
+    const double lim = FMIN(minl, maxl);
+    for (int d = 0; d < ndim; d++) w[d] = w[d] * lim;
+  } else if (type == 3) { /* compute_central :618-637 */
+    for (int d = 0; d < ndim; d++) w[d] = 0.25 * (a[2 * d + 2] - a[2 * d + 1]);
+  }
+}
+
 /* interpol_hydro hydro/interpol_hydro.f90:268-444 for one father cell: u1[(2*ndim+1)][nvar] -> u2[2^ndim][nvar].
- * interpol_var 0 (conservative) only; interpol_type 0,1,2,3.                                                     */
-void orc_interpol_hydro(const orc_params* p, const double* u1, double* u2) {
+ * interpol_var 0 (rho, rho u, E), 1 (rho, rho u, rho eps), 2 (rho, u, rho eps + momentum correction :393-415);
+ * interpol_type 0,1,2,3 and 4 (type 3 for the velocities, type 2 for the rest; needs interpol_var=2 :357-366).           */
+void orc_interpol_hydro(const orc_params* p, const double* u1_in, double* u2) {
   const int ndim = p->ndim, nvar = p->nvar, twotondim = ipow2(ndim), twondim = 2 * ndim;
-  if (g_interpol_var != 0) { fprintf(stderr, "orc: interpol_var=%d not restated\n", g_interpol_var); abort(); }
+  const int var = g_interpol_var, type = g_interpol_type;
+  if (var < 0 || var > 2 || type < 0 || type > 4 || (type == 4 && var != 2)) {
+    fprintf(stderr, "orc: interpol_var=%d interpol_type=%d not valid (type 4 is designed for interpol_var=2)\n", var, type);
+    abort();
+  }
+  const double oneover_twotondim = 1.0 / (double)twotondim;
   double xc[8][3];
   for (int ind = 0; ind < twotondim; ind++) {
     xc[ind][0] = (double)(ind & 1) - 0.5; xc[ind][1] = (double)((ind >> 1) & 1) - 0.5; xc[ind][2] = (double)((ind >> 2) & 1) - 0.5;
   }
-  for (int iv = 0; iv < nvar; iv++) {
-    double a[7], w[3] = {0, 0, 0};
-    for (int j = 0; j <= twondim; j++) a[j] = u1[j * nvar + iv];
-    if (g_interpol_type == 1) { /* compute_limiter_minmod :449-470 */
-      for (int d = 0; d < ndim; d++) {
-        double dl = 0.5 * (a[2 * d + 2] - a[0]), dr = 0.5 * (a[0] - a[2 * d + 1]), mm;
-        if (dl * dr <= 0.0) mm = 0; else mm = FMIN(fabs(dl), fabs(dr)) * dl / fabs(dl);
-        w[d] = mm;
-      }
-    } else if (g_interpol_type == 2) { /* compute_limiter_central :481-613 */
-      double ac[8];
-      for (int d = 0; d < ndim; d++) w[d] = 0.25 * (a[2 * d + 2] - a[2 * d + 1]);
-      for (int ind = 0; ind < twotondim; ind++) ac[ind] = a[0];
-      for (int d = 0; d < ndim; d++)
-        for (int ind = 0; ind < twotondim; ind++) ac[ind] = ac[ind] + 2.0 * w[d] * xc[ind][d];
-      double corner = ac[0], kernel = a[1];
-      for (int j = 1; j < twotondim; j++) corner = FMAX(corner, ac[j]);
-      for (int j = 2; j <= twondim; j++) kernel = FMAX(kernel, a[j]);
-      double dk = a[0] - kernel, dc = a[0] - corner, maxl = 0.0, minl = 0.0;
-      if (dk * dc > 0.0) maxl = FMIN(1.0, dk / dc);
-      corner = ac[0]; kernel = a[1];
-      for (int j = 1; j < twotondim; j++) corner = FMIN(corner, ac[j]);
-      for (int j = 2; j <= twondim; j++) kernel = FMIN(kernel, a[j]);
-      dk = a[0] - kernel; dc = a[0] - corner;
-      if (dk * dc > 0.0) minl = FMIN(1.0, dk / dc);
-      const double lim = FMIN(minl, maxl);
-      for (int d = 0; d < ndim; d++) w[d] = w[d] * lim;
-    } else if (g_interpol_type == 3) { /* compute_central :618-637 */
-      for (int d = 0; d < ndim; d++) w[d] = 0.25 * (a[2 * d + 2] - a[2 * d + 1]);
+  double u1[7 * 16];
+  for (int j = 0; j <= twondim; j++)
+    for (int iv = 0; iv < nvar; iv++) u1[j * nvar + iv] = u1_in[j * nvar + iv];
+#define U1(j, iv) u1[(j)*nvar + (iv)-1]
+#define U2(ind, iv) u2[(ind)*nvar + (iv)-1]
+  if (var == 1 || var == 2) { /* father total energy -> internal energy :318-345, momenta -> velocities for var 2 */
+    for (int j = 0; j <= twondim; j++) {
+      double ekin = 0.0;
+      for (int d = 1; d <= ndim; d++) ekin = ekin + 0.5 * (U1(j, d + 1) * U1(j, d + 1)) / FMAX(U1(j, 1), p->smallr);
+      const double erad = 0.0;
+      U1(j, ndim + 2) = U1(j, ndim + 2) - ekin - erad;
+      if (var == 2)
+        for (int d = 1; d <= ndim; d++) U1(j, d + 1) = U1(j, d + 1) / FMAX(U1(j, 1), p->smallr);
     }
+  }
+  for (int iv = 1; iv <= nvar; iv++) {
+    double a[7], w[3];
+    for (int j = 0; j <= twondim; j++) a[j] = U1(j, iv);
+    int t = type;
+    if (type == 4) t = (iv > 1 && iv <= 1 + ndim) ? 3 : 2;
+    interpol_slopes(ndim, t, a, w, xc);
     for (int ind = 0; ind < twotondim; ind++) { /* :372-379 */
       double v = a[0];
       for (int d = 0; d < ndim; d++) v = v + w[d] * xc[ind][d];
-      u2[ind * nvar + iv] = v;
+      U2(ind, iv) = v;
     }
   }
+  if (var == 1 || var == 2) {
+    if (var == 2) {
+      for (int ind = 0; ind < twotondim; ind++)
+        for (int d = 1; d <= ndim; d++) U2(ind, d + 1) = U2(ind, d + 1) * U2(ind, 1);
+      for (int d = 1; d <= ndim; d++) { /* correct the total momentum keeping the slope fixed :399-413 */
+        double mom = 0.0;
+        for (int ind = 0; ind < twotondim; ind++) mom = mom + U2(ind, d + 1) * oneover_twotondim;
+        mom = mom - U1(0, d + 1) * U1(0, 1);
+        for (int ind = 0; ind < twotondim; ind++) U2(ind, d + 1) = U2(ind, d + 1) - mom;
+      }
+    }
+    for (int ind = 0; ind < twotondim; ind++) { /* children internal energy -> total energy :418-440 */
+      double ekin = 0.0;
+      for (int d = 1; d <= ndim; d++) ekin = ekin + 0.5 * (U2(ind, d + 1) * U2(ind, d + 1)) / FMAX(U2(ind, 1), p->smallr);
+      const double erad = 0.0;
+      U2(ind, ndim + 2) = U2(ind, ndim + 2) + ekin + erad;
+    }
+  }
+#undef U1
+#undef U2
 }
 
 /* prolongation of one father cell from the coarse state: what godfine1 (:583-593) and make_grid_fine
@@ -1830,6 +1880,19 @@ void orc_upload_fine(const orc_params* p, const orc_mesh* m, int ilevel, double*
         getx = 0.0;
         for (int is = 0; is < twotondim; is++) getx = getx + UO(m->ncoarse + is * m->ngridmax + gs, iv);
         UO(ic, iv) = getx / (double)twotondim;
+      }
+      if (g_interpol_var == 1 || g_interpol_var == 2) { /* average internal energy instead of total energy :204-261 */
+        const int ndim = p->ndim;
+        getx = 0.0;
+        for (int is = 0; is < twotondim; is++) {
+          const int cs = m->ncoarse + is * m->ngridmax + gs;
+          double ekin = 0.0;
+          for (int d = 1; d <= ndim; d++) ekin = ekin + 0.5 * (UO(cs, 1 + d) * UO(cs, 1 + d)) / FMAX(UO(cs, 1), p->smallr);
+          getx = getx + UO(cs, ndim + 2) - ekin - 0.0;
+        }
+        double ekin = 0.0;
+        for (int d = 1; d <= ndim; d++) ekin = ekin + 0.5 * (UO(ic, 1 + d) * UO(ic, 1 + d)) / FMAX(UO(ic, 1), p->smallr);
+        UO(ic, ndim + 2) = getx / (double)twotondim + ekin + 0.0;
       }
     }
 }

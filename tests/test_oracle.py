@@ -235,3 +235,45 @@ def test_oracle_passive_scalars_keep_uniform_concentration_and_are_conserved():
         assert np.abs(d7[5] / d7[0] - 0.3).max() < 1e-14
         assert abs(d7[6].sum() - u7[6].sum()) < 1e-12 * u7[6].sum()
         assert np.abs(d7[6] - u7[6]).max() > 1e-3
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+@pytest.mark.parametrize("ivar,itype", [(0, 0), (0, 1), (0, 2), (0, 3), (1, 1), (1, 2), (1, 3), (2, 1), (2, 2), (2, 3), (2, 4)])
+def test_interpol_hydro_variants(orc, ndim, ivar, itype):
+    """interpol_hydro (hydro/interpol_hydro.f90:268) for every interpol_var / interpol_type: the children average back to the
+    father for mass and momentum (interpol_var 2 through its explicit momentum correction :393-415); total energy for
+    interpol_var=0, internal energy for interpol_var=1; a uniform neighbourhood is reproduced exactly; the limited types keep
+    every child inside the range of the father's neighbourhood for the limited variables."""
+    import ctypes as C
+    L = orc.lib()
+    L.orc_set_interpol.argtypes = [C.c_int, C.c_int]
+    L.orc_interpol_hydro.argtypes = [C.POINTER(orc.Params), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    p = orc.make_params(ndim=ndim)
+    nvar, T, nn = ndim + 2, 1 << ndim, 2 * ndim + 1
+    rng = np.random.default_rng(10 * ndim + ivar + itype)
+    try:
+        L.orc_set_interpol(itype, ivar)
+        for trial in range(20):
+            u1 = np.zeros((nn, nvar))
+            u1[:, 0] = 1 + 0.5 * rng.random(nn)
+            vel = 0.4 * rng.standard_normal((nn, ndim))
+            u1[:, 1:1 + ndim] = u1[:, :1] * vel
+            eint = 1 + 0.5 * rng.random(nn)
+            u1[:, ndim + 1] = eint + 0.5 * u1[:, 0] * (vel ** 2).sum(axis=1)
+            if trial == 0:
+                u1[:] = u1[0]
+            u2 = np.zeros((T, nvar))
+            L.orc_interpol_hydro(C.byref(p), orc.dptr(np.ascontiguousarray(u1)), orc.dptr(u2))
+            if trial == 0:
+                assert np.allclose(u2, u1[0], rtol=0, atol=1e-15)
+            assert abs(u2[:, 0].mean() - u1[0, 0]) < 1e-14
+            assert np.abs(u2[:, 1:1 + ndim].mean(axis=0) - u1[0, 1:1 + ndim]).max() < 1e-14
+            ek = lambda u: 0.5 * (u[..., 1:1 + ndim] ** 2).sum(axis=-1) / u[..., 0]
+            if ivar == 0:
+                assert abs(u2[:, ndim + 1].mean() - u1[0, ndim + 1]) < 1e-14
+            else:
+                assert abs((u2[:, ndim + 1] - ek(u2)).mean() - (u1[0, ndim + 1] - ek(u1[0]))) < 1e-14
+            if itype in (1, 2):
+                assert u2[:, 0].min() >= u1[:, 0].min() - 1e-14 and u2[:, 0].max() <= u1[:, 0].max() + 1e-14
+    finally:
+        L.orc_set_interpol(1, 0)
