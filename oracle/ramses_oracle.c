@@ -1382,6 +1382,13 @@ void orc_condinit_regions(const orc_params* p, const orc_mesh* m, int ilevel, do
 }
 
 /* set_unew hydro/godunov_fine.f90:40-130 */
+/* pressure_fix (amr_parameters.f90:167,197): the two extra cell arrays of hydro_commons -- divu (= -div(u)*dt accumulated from
+ * the face velocities tmp(:,1)) and enew (internal energy advanced with the flux tmp(:,2) and the -pdV source) -- are owned by
+ * the caller; NULL switches the option off.  hexp = 0 (no cosmology).                                                       */
+static double *g_divu = NULL, *g_enew = NULL;
+static double g_beta_fix = 0.0, g_dt_level[64];
+void orc_set_pressure_fix(double* divu, double* enew, double beta_fix) { g_divu = divu; g_enew = enew; g_beta_fix = beta_fix; }
+
 void orc_set_unew(const orc_params* p, const orc_mesh* m, int ilevel, const double* uold, double* unew) {
   const int twotondim = ipow2(p->ndim);
   const int na = m->nactive[ilevel];
@@ -1398,10 +1405,68 @@ void orc_set_unew(const orc_params* p, const orc_mesh* m, int ilevel, const doub
       for (int a = 0; a < na; a++) UN(act[a] + iskip, iv) = UO(act[a] + iskip, iv);
     }
   }
+  if (g_divu)                                   /* pressure_fix :71-90 */
+    for (int ind = 0; ind < twotondim; ind++) {
+      const int iskip = m->ncoarse + ind * m->ngridmax, ndim = p->ndim;
+      for (int a = 0; a < na; a++) g_divu[act[a] + iskip - 1] = 0;
+      for (int a = 0; a < na; a++) {
+        const int ic = act[a] + iskip;
+        double d = FMAX(UO(ic, 1), p->smallr), u = 0, v = 0, w = 0;
+        if (ndim > 0) u = UO(ic, 2) / d;
+        if (ndim > 1) v = UO(ic, 3) / d;
+        if (ndim > 2) w = UO(ic, 4) / d;
+        g_enew[ic - 1] = UO(ic, ndim + 2) - 0.5 * d * (u * u + v * v + w * w);
+      }
+    }
   for (int ind = 0; ind < twotondim; ind++) { /* :93-126 */
     int iskip = m->ncoarse + ind * m->ngridmax;
     for (int iv = 1; iv <= p->nvar; iv++)
       for (int a = 0; a < m->nrecv[ilevel]; a++) UN(m->recv[ilevel][a] + iskip, iv) = 0;
+    if (g_divu)
+      for (int a = 0; a < m->nrecv[ilevel]; a++) { g_divu[m->recv[ilevel][a] + iskip - 1] = 0; g_enew[m->recv[ilevel][a] + iskip - 1] = 0; }
+  }
+}
+
+/* add_pdv_source_terms hydro/godunov_fine.f90:294-437 (pressure_fix part): enew -= (gamma-1) e_old div(u) dt with the
+ * velocity divergence from the face-neighbour cells of uold (the coarser father cell at 1.5 dx where no neighbour oct exists) */
+static void add_pdv_source_terms(const orc_params* p, const orc_mesh* m, int ilevel, const double* uold) {
+  static const int iii[3][2][8] = {{{1, 0, 1, 0, 1, 0, 1, 0}, {0, 2, 0, 2, 0, 2, 0, 2}},
+                                   {{3, 3, 0, 0, 3, 3, 0, 0}, {0, 0, 4, 4, 0, 0, 4, 4}},
+                                   {{5, 5, 5, 5, 0, 0, 0, 0}, {0, 0, 0, 0, 6, 6, 6, 6}}};
+  static const int jjj[3][2][8] = {{{2, 1, 4, 3, 6, 5, 8, 7}, {2, 1, 4, 3, 6, 5, 8, 7}},
+                                   {{3, 4, 1, 2, 7, 8, 5, 6}, {3, 4, 1, 2, 7, 8, 5, 6}},
+                                   {{5, 6, 7, 8, 1, 2, 3, 4}, {5, 6, 7, 8, 1, 2, 3, 4}}};
+  const int ndim = p->ndim, twotondim = ipow2(ndim);
+  const double dx_loc = orc_dx(p, m, ilevel);
+  const double dt = g_dt_level[ilevel];
+  for (int a = 0; a < m->nactive[ilevel]; a++) {
+    const int ig = m->active[ilevel][a];
+    int igridn[7], ind_left[3], ind_right[3];
+    igridn[0] = ig;
+    for (int d = 0; d < ndim; d++) {
+      ind_left[d] = NBOR(m, ig, 2 * d + 1); ind_right[d] = NBOR(m, ig, 2 * d + 2);
+      igridn[2 * d + 1] = m->son[ind_left[d]]; igridn[2 * d + 2] = m->son[ind_right[d]];
+    }
+    for (int ind = 0; ind < twotondim; ind++) {
+      const int ic = m->ncoarse + ind * m->ngridmax + ig;
+      double divu_loc = 0.0;
+      for (int d = 0; d < ndim; d++) {
+        double velg, veld, dx_g, dx_d;
+        const int g1 = igridn[iii[d][0][ind]], c1 = g1 > 0 ? g1 + m->ncoarse + (jjj[d][0][ind] - 1) * m->ngridmax : ind_left[d];
+        velg = UO(c1, d + 2) / FMAX(UO(c1, 1), p->smallr);
+        dx_g = g1 > 0 ? dx_loc : dx_loc * 1.5;
+        const int g2 = igridn[iii[d][1][ind]], c2 = g2 > 0 ? g2 + m->ncoarse + (jjj[d][1][ind] - 1) * m->ngridmax : ind_right[d];
+        veld = UO(c2, d + 2) / FMAX(UO(c2, 1), p->smallr);
+        dx_d = g2 > 0 ? dx_loc : dx_loc * 1.5;
+        divu_loc = divu_loc + (veld - velg) / (dx_g + dx_d);
+      }
+      double dd = FMAX(UO(ic, 1), p->smallr), u = 0, v = 0, w = 0;
+      if (ndim > 0) u = UO(ic, 2) / dd;
+      if (ndim > 1) v = UO(ic, 3) / dd;
+      if (ndim > 2) w = UO(ic, 4) / dd;
+      const double eold = UO(ic, ndim + 2) - 0.5 * dd * (u * u + v * v + w * w);
+      g_enew[ic - 1] = g_enew[ic - 1] - (p->gamma - 1.0) * eold * divu_loc * dt;
+    }
   }
 }
 
@@ -1409,6 +1474,7 @@ void orc_set_unew(const orc_params* p, const orc_mesh* m, int ilevel, const doub
 void orc_set_uold(const orc_params* p, const orc_mesh* m, int ilevel, double* uold, const double* unew) {
   const int twotondim = ipow2(p->ndim), ndim = p->ndim, nvar = p->nvar;
   const double smallr = p->smallr;
+  if (g_divu) add_pdv_source_terms(p, m, ilevel, uold);             /* :164-168 */
   for (int ind = 0; ind < twotondim; ind++) {
     int iskip = m->ncoarse + ind * m->ngridmax;
     if (nvar > ndim + 2) { /* :176-190 passive-scalar floor fix */
@@ -1431,6 +1497,23 @@ void orc_set_uold(const orc_params* p, const orc_mesh* m, int ilevel, double* uo
 #pragma omp for schedule(static) nowait
 #endif
       for (int a = 0; a < m->nactive[ilevel]; a++) UO(m->active[ilevel][a] + iskip, iv) = UN(m->active[ilevel][a] + iskip, iv);
+    }
+    if (g_divu) {                                                     /* correct total energy if internal energy is too small :203-227 */
+      const double dx = orc_dx(p, m, ilevel), hexp = 0.0;
+      for (int a = 0; a < m->nactive[ilevel]; a++) {
+        const int ic = m->active[ilevel][a] + iskip;
+        double d = FMAX(UO(ic, 1), smallr), u = 0, v = 0, w = 0;
+        if (ndim > 0) u = UO(ic, 2) / d;
+        if (ndim > 1) v = UO(ic, 3) / d;
+        if (ndim > 2) w = UO(ic, 4) / d;
+        const double e_kin = 0.5 * d * (u * u + v * v + w * w);
+        const double e_cons = UO(ic, ndim + 2) - e_kin;
+        const double e_prim = g_enew[ic - 1];
+        const double div = fabs(g_divu[ic - 1]) * dx / g_dt_level[ilevel];     /* divu = -div.u*dt */
+        const double mx = FMAX(div, 3.0 * hexp * dx);
+        const double e_trunc = g_beta_fix * d * (mx * mx);
+        if (e_cons < e_trunc) UO(ic, ndim + 2) = e_prim + e_kin;
+      }
     }
   }
 }
@@ -1636,6 +1719,14 @@ static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const 
             for (int i = 0; i < ncache; i++)
               if (w->ok[PIX(w, i, i3 - i0, j3 - j0, k3 - k0)] || w->ok[PIX(w, i, i3, j3, k3)])
                 w->flux[(iv + (size_t)idim * nvar) * nfp + FIX(w, i, i3, j3, k3)] = 0.0;
+    if (g_divu)                                                     /* pressure_fix :737-745 */
+      for (int k3 = k3min; k3 <= k3max + k0; k3++)
+        for (int j3 = j3min; j3 <= j3max + j0; j3++)
+          for (int i3 = i3min; i3 <= i3max + i0; i3++)
+            for (int iv = 0; iv < 2; iv++)
+              for (int i = 0; i < ncache; i++)
+                if (w->ok[PIX(w, i, i3 - i0, j3 - j0, k3 - k0)] || w->ok[PIX(w, i, i3, j3, k3)])
+                  w->tmp[(iv + (size_t)idim * 2) * nfp + FIX(w, i, i3, j3, k3)] = 0.0;
   }
   }
   if (phase == 1) return;
@@ -1654,6 +1745,18 @@ static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const 
               const double* f = &w->flux[((iv - 1) + (size_t)idim * nvar) * nfp];
               UN(ic, iv) = UN(ic, iv) + (f[FIX(w, i, i3, j3, k3)] - f[FIX(w, i, i3 + i0, j3 + j0, k3 + k0)]);
             }
+          if (g_divu) {                                             /* :773-786 */
+            const double* t1 = &w->tmp[(0 + (size_t)idim * 2) * nfp];
+            const double* t2 = &w->tmp[(1 + (size_t)idim * 2) * nfp];
+            for (int i = 0; i < ncache; i++) {
+              int ic = iskip + ind_grid[i];
+              g_divu[ic - 1] = g_divu[ic - 1] + (t1[FIX(w, i, i3, j3, k3)] - t1[FIX(w, i, i3 + i0, j3 + j0, k3 + k0)]);
+            }
+            for (int i = 0; i < ncache; i++) {
+              int ic = iskip + ind_grid[i];
+              g_enew[ic - 1] = g_enew[ic - 1] + (t2[FIX(w, i, i3, j3, k3)] - t2[FIX(w, i, i3 + i0, j3 + j0, k3 + k0)]);
+            }
+          }
         }
   }
   /* conservative update at level ilevel-1 :798-908.  Loop order of the reference: variable, then face, then the
@@ -1674,6 +1777,16 @@ static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const 
             for (int i = 0; i < nb_noneigh; i++)
               UN(ind_buffer[i], iv) = UN(ind_buffer[i], iv) -
                   w->flux[((iv - 1) + (size_t)idim * nvar) * nfp + FIX(w, ind_cell[i], i3, j3, k3)] * oneontwotondim;
+    if (g_divu)                                                     /* :830-851 */
+      for (int tv = 0; tv < 2; tv++) {
+        double* dst = tv == 0 ? g_divu : g_enew;
+        for (int k3 = k3min; k3 <= k3max - k0; k3++)
+          for (int j3 = j3min; j3 <= j3max - j0; j3++)
+            for (int i3 = i3min; i3 <= i3max - i0; i3++)
+              for (int i = 0; i < nb_noneigh; i++)
+                dst[ind_buffer[i] - 1] = dst[ind_buffer[i] - 1] -
+                    w->tmp[(tv + (size_t)idim * 2) * nfp + FIX(w, ind_cell[i], i3, j3, k3)] * oneontwotondim;
+      }
     nb_noneigh = 0;
     for (int i = 0; i < ncache; i++) { /* right :863-869 */
       int nb = NBOR(m, ind_grid[i], 2 * idim + 2);
@@ -1686,6 +1799,16 @@ static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const 
             for (int i = 0; i < nb_noneigh; i++)
               UN(ind_buffer[i], iv) = UN(ind_buffer[i], iv) +
                   w->flux[((iv - 1) + (size_t)idim * nvar) * nfp + FIX(w, ind_cell[i], i3 + i0, j3 + j0, k3 + k0)] * oneontwotondim;
+    if (g_divu)                                                     /* :882-903 */
+      for (int tv = 0; tv < 2; tv++) {
+        double* dst = tv == 0 ? g_divu : g_enew;
+        for (int k3 = k3min + k0; k3 <= k3max; k3++)
+          for (int j3 = j3min + j0; j3 <= j3max; j3++)
+            for (int i3 = i3min + i0; i3 <= i3max; i3++)
+              for (int i = 0; i < nb_noneigh; i++)
+                dst[ind_buffer[i] - 1] = dst[ind_buffer[i] - 1] +
+                    w->tmp[(tv + (size_t)idim * 2) * nfp + FIX(w, ind_cell[i], i3 + i0, j3 + j0, k3 + k0)] * oneontwotondim;
+      }
     free(ind_buffer); free(ind_cell);
   }
 }
@@ -1701,9 +1824,11 @@ void orc_set_amr_threads(int n) { g_amr_threads = n < 1 ? 1 : n; }
 void orc_godunov_fine(const orc_params* p, const orc_mesh* m, int ilevel, double dt, const double* uold, double* unew,
                       int nthreads) {
   const int ncache = m->nactive[ilevel], nv = p->nvector;
+  if (ilevel >= 0 && ilevel < 64) g_dt_level[ilevel] = dt;          /* dtnew(ilevel) for set_uold (pressure_fix) */
   if (ncache == 0) return;
   int nbatch = (ncache + nv - 1) / nv;
   if (nthreads < 1) nthreads = 1;
+  if (g_divu && nthreads > 1) nthreads = 1;                          /* divu/enew refluxes need the serial update order */
   if (nthreads == 1 && g_amr_threads > 1 && nbatch > 1) {
     const int nt = IMIN(g_amr_threads, 64);
     static orc_work* ws[64];                       /* kept between calls (thousands of level steps per run) */

@@ -133,6 +133,8 @@ void orc_interpol_cell(const orc_params*, const orc_mesh*, int ind_cell, int ile
 orc_mesh* orc_mesh_new(int ndim, const int bound_type[6], int ngridmax, int nlevelmax);
 void orc_mesh_set_list(orc_mesh*, int kind, int b, int ilevel, int n, const int* igrid);
 
+/* pressure_fix: caller-owned divu / enew cell arrays [ncell] (NULL = off) and beta_fix (amr_parameters.f90:167)      */
+void orc_set_pressure_fix(double* divu, double* enew, double beta_fix);
 void orc_set_threads(int n);
 void orc_set_amr_threads(int n);   /* flux phase of orc_godunov_fine(nthreads=1); results do not depend on it */
 int orc_abi_version(void);
