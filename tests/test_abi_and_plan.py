@@ -194,3 +194,26 @@ def test_host_amr_step_mirror_call_order():
     per = [n for n, l in h.log if l == 3]
     assert per == ["courant_fine", "set_unew", "godunov_fine_dev", "set_uold", "upload_fine", "make_boundary_hydro"]
     assert dtnew[4] <= dtnew[3] / 2 + 1e-18 and dtnew[5] <= dtnew[4] / 2 + 1e-18
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) prints ONE JSON line with the contract's keys,
+    needs no GPU, and times the oracle port on the host cores."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", "sedov3d_256_exact"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(line) == 1
+    j = json.loads(line[0])
+    assert j["impl"] == "reference" and j["metric"] == "cell_updates_per_s" and j["unit"] == "cell-updates/s"
+    assert j["higher_is_better"] is True and j["n_gpus"] == 1 and j["value"] > 1e5
+    assert j["config"]["workload"] == "sedov3d_256_exact"
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert j["gpu_launches"] == 0
