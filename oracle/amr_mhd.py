@@ -228,11 +228,13 @@ class MhdAmrRun2D(FastAmrRun):
     EMF, constrained transport, divergence-free prolongation (interpol_mag), EMF refluxing, face-centred restriction.  Exists to
     reproduce tests/mhd/orszag-tang/orszag-tang-ref.dat."""
 
+    NDIM = 2
+
     def __init__(self, levelmin, levelmax, boxlen, nsubcycle, riemann="hlld", riemann2d="hlld", slope_type=2, gamma=1.4,
                  courant_factor=0.8, err_grad_d=-1.0, err_grad_u=-1.0, err_grad_p=-1.0, err_grad_A=-1.0, err_grad_B=-1.0,
                  err_grad_C=-1.0, err_grad_B2=-1.0, interpol_type=2, tout=(), nexpand=1, ngridmax=100000, nvector=32,
                  ic="orszag_tang", nthreads=None):
-        super().__init__(2, levelmin, levelmax, (0, 0, 0, 0, 0, 0), boxlen, nsubcycle, nexpand=nexpand, ngridmax=ngridmax,
+        super().__init__(self.NDIM, levelmin, levelmax, (0, 0, 0, 0, 0, 0), boxlen, nsubcycle, nexpand=nexpand, ngridmax=ngridmax,
                          riemann="llf", slope_type=slope_type, gamma=gamma, courant_factor=courant_factor,
                          err_grad_d=err_grad_d, err_grad_u=err_grad_u, err_grad_p=err_grad_p, interpol_type=interpol_type,
                          interpol_var=0, regions=(), tout=tout, nvector=nvector, nthreads=nthreads)
@@ -259,20 +261,26 @@ class MhdAmrRun2D(FastAmrRun):
         L.orc_mhdn_upload_fine.argtypes = [pp, mp, C.c_int, dp]
         L.orc_mhd2_condinit_orszag_tang.argtypes = [pp, mp, C.c_int, dp]
         L.orc_amr_mhd_hydro_flag.argtypes = [pp, mp, C.c_int, dp, ip, dp, dp]
+        L.orc_mhd3_interpol_cell.argtypes = [mp, C.c_int, C.c_int, dp, dp]
+        L.orc_mhd3_godunov_fine.argtypes = [pp, mp, C.c_int, C.c_int, C.c_int, C.c_double, dp, dp]
+        L.orc_mhd3_condinit_orszag_tang.argtypes = [pp, mp, C.c_int, dp]
+        self._godunov = L.orc_mhd2_godunov_fine if self.NDIM == 2 else L.orc_mhd3_godunov_fine
+        self._interpol = L.orc_mhd2_interpol_cell if self.NDIM == 2 else L.orc_mhd3_interpol_cell
+        self._condinit = L.orc_mhd2_condinit_orszag_tang if self.NDIM == 2 else L.orc_mhd3_condinit_orszag_tang
 
     def c_set_unew(self, l):
         self.L.orc_mhdn_set_unew(self.mp, l, orc.dptr(self.uold), orc.dptr(self.unew))
 
     def c_godunov_fine(self, l):
-        self.L.orc_mhd2_godunov_fine(C.byref(self.pm), self.mp, l, self.levelmin, self.nvector, self.dtnew[l], orc.dptr(self.uold),
+        self._godunov(C.byref(self.pm), self.mp, l, self.levelmin, self.nvector, self.dtnew[l], orc.dptr(self.uold),
                                      orc.dptr(self.unew))
 
     def c_set_uold(self, l):
         self.L.orc_mhdn_set_uold(self.mp, l, orc.dptr(self.uold), orc.dptr(self.unew))
 
     def c_interpol_cell(self, c, lnew):
-        u2 = np.zeros(4 * NVS)
-        self.L.orc_mhd2_interpol_cell(self.mp, c, lnew, orc.dptr(self.uold), orc.dptr(u2))
+        u2 = np.zeros(self.T * NVS)
+        self._interpol(self.mp, c, lnew, orc.dptr(self.uold), orc.dptr(u2))
         return u2
 
     def make_boundary_hydro(self, l):
@@ -290,7 +298,7 @@ class MhdAmrRun2D(FastAmrRun):
         if self.numbtot(l) == 0:
             return
         assert self.ic == "orszag_tang"
-        self.L.orc_mhd2_condinit_orszag_tang(C.byref(self.pm), self.mp, l, orc.dptr(self.uold))
+        self._condinit(C.byref(self.pm), self.mp, l, orc.dptr(self.uold))
 
     def hydro_flag(self, l):
         if l == self.nlevelmax or self.numbtot(l) == 0:
@@ -307,7 +315,7 @@ class MhdAmrRun2D(FastAmrRun):
             act = np.asarray(self.active[l], dtype=np.int64)
             if len(act) == 0:
                 continue
-            for ind in range(4):
+            for ind in range(self.T):
                 c = self.ncoarse + ind * self.ngridmax + act
                 leaf = c[self.son[c] == 0]
                 if len(leaf):
@@ -332,7 +340,8 @@ class MhdAmrRun2D(FastAmrRun):
             cols["level"].append(np.full(n, float(l)))
             cols["x"].append((self.xg[0, ig] + ((ind & 1) - 0.5) * dx - self.m.icoarse_min) * scale)
             cols["y"].append((self.xg[1, ig] + (((ind >> 1) & 1) - 0.5) * dx - self.m.jcoarse_min) * scale)
-            cols["z"].append(np.zeros(n))
+            cols["z"].append(np.zeros(n) if self.NDIM == 2 else
+                             (self.xg[2, ig] + (((ind >> 2) & 1) - 0.5) * dx - self.m.kcoarse_min) * scale)
             cols["dx"].append(np.full(n, dx * scale))
             cols["density"].append(u_[0].copy())
             cols["velocity_x"].append(vx); cols["velocity_y"].append(vy); cols["velocity_z"].append(vz)
@@ -347,8 +356,29 @@ class MhdAmrRun2D(FastAmrRun):
         worst = 0.0
         for l, ind, ig, c in self.leaf_cells():
             u_ = U[:, c - 1]
-            worst = max(worst, float(np.max(np.abs((u_[8] - u_[5]) + (u_[9] - u_[6])))))
+            d = (u_[8] - u_[5]) + (u_[9] - u_[6])
+            if self.NDIM == 3:
+                d = d + (u_[10] - u_[7])
+            worst = max(worst, float(np.max(np.abs(d))))
         return worst
+
+
+class MhdAmrRun3D(MhdAmrRun2D):
+    """NDIM=3 ideal-MHD AMR driver on the NDIM=3 AMR routines of oracle/ramses_oracle_mhd.c (the initial condition is the
+    z-invariant Orszag-Tang state, so that a run can be compared with the golden-pinned NDIM=2 run)."""
+    NDIM = 3
+
+    def __init__(self, *a, courant_ndim=0, **kw):
+        super().__init__(*a, **kw)
+        self.courant_ndim = courant_ndim            # bit mask of the cmpdt directions (test hook; 0 = all three)
+
+    def newdt_fine(self, l):
+        self.L.orc_mhd_set_courant_ndim.argtypes = [C.c_int]
+        self.L.orc_mhd_set_courant_ndim(self.courant_ndim)
+        try:
+            super().newdt_fine(l)
+        finally:
+            self.L.orc_mhd_set_courant_ndim(0)
 
 
 def check_sums_cols(data, threshold=2.0e-14, norm_min=1.0e-30, min_variance=1.0e-14):

@@ -12,7 +12,7 @@
  *   mhd/courant_fine.f90  courant_fine:1
  *   mhd/hydro_boundary.f90 make_boundary_hydro:1 (reflexive :141-222, zero-gradient :223-296)
  *
- * Scope: NDIM=3 on uniform grids (levelmin=levelmax: every neighbouring oct exists), NDIM=1 and NDIM=2 with AMR (end of the
+ * Scope: NDIM=3 on uniform grids (levelmin=levelmax: every neighbouring oct exists), NDIM=1, 2 and 3 with AMR (end of the
  * file: trace1d / trace2d, interpol_hydro + interpol_mag, EMF refluxing, upload_fine with face-centred restriction);
  * nvar=8 (no passive scalars, NENER=0), no gravity, ischeme=muscl, pressure_fix=.false., allow_switch_solver=.false.
  *
@@ -29,7 +29,9 @@
  *   3. carried over to NDIM=3 (the code the GPU kernels are compared with): mag_unsplit of the NDIM=2 routines equals
  *      mag_unsplit of the NDIM=3 routines on z-invariant patches BIT FOR BIT for in-plane fields, all solver pairs
  *      (tests/test_oracle_mhd.py::test_unsplit_2d_equals_z_invariant_3d); the z paths are tied to x, y by the axis-permutation
- *      covariance test.  roe / hll / llf / upwind have no golden file in the reference; they share everything but the solver
+ *      covariance test.  The NDIM=3 AMR routines (3-D interpol_mag, the twelve EMF edges) give the NDIM=2 result for an
+ *      in-plane problem embedded in each of the three coordinate planes of a nested mesh, to 2e-13
+ *      (test_3d_amr_mhd_equals_golden_pinned_2d_on_embedded_problem).  roe / hll / llf / upwind have no golden file in the reference; they share everything but the solver
  *      body with the pinned hlld path and are held by solver-consistency tests, the exact Ryu-Jones solution shipped with
  *      the reference, div B = 0, conservation and the B=0 limit against the golden-pinned hydro oracle.
  */
@@ -2015,6 +2017,11 @@ void orc_mhd2_godunov_fine(const orc_mhd_params* p, const orc_mesh* m, int ileve
   }
 }
 
+/* test hook: bit mask of the directions summed in cmpdt (0 = directions 1..NDIM of the mesh, what the reference does); lets an
+ * NDIM=3 run of a problem that is invariant along one axis take the time steps of the NDIM=2 run it is compared with      */
+static int g_courant_mask = 0;
+void orc_mhd_set_courant_ndim(int mask) { g_courant_mask = mask; }
+
 /* courant_fine mhd/courant_fine.f90 + cmpdt mhd/godunov_utils.f90:5 for any NDIM (ctot sums idim = 1..ndim) */
 double orc_mhdn_courant_fine(const orc_mhd_params* p, const orc_mesh* m, int ilevel, double dt_in, const double* uold) {
   const double dx = level_dx(p, m, ilevel);
@@ -2040,6 +2047,7 @@ double orc_mhdn_courant_fine(const orc_mhd_params* p, const orc_mesh* m, int ile
       double a2 = p->gamma * uu[4] / uu[0];
       double ctot = zero;
       for (int d = 1; d <= m->ndim; d++) { /* WARNING: ndim instead of 3 */
+        if (g_courant_mask && !((g_courant_mask >> (d - 1)) & 1)) continue;
         double cc = half * (B2 / rho + a2);
         double BN = half * (uu[4 + d] + uu[NV + d - 1]);
         double cf = sqrt(cc + sqrt(cc * cc - a2 * (BN * BN) / rho));
@@ -2249,6 +2257,363 @@ void orc_amr_mhd_hydro_flag(const orc_mhd_params* p, const orc_mesh* m, int l, c
         ok = ok || mhd_hydro_refine(p, ug, um, ud, err, flo);
       }
       if (ok) flag1[c] = 1;
+    }
+  }
+}
+
+/* ======================================================================================================
+ * NDIM = 3 with AMR: godfine1 mhd/godunov_fine.f90:538-1459 on a refined mesh -- divergence-free prolongation of missing
+ * neighbour octs (interpol_hydro :612 + interpol_mag :990 with compute_2d_tvd and the NDIM=3 branch of cmp_central_faces),
+ * flux / EMF reset at refined faces and edges (:760-880), CT update, coarse refluxing of the Euler fluxes (:1030-1168) and of
+ * the twelve EMF edges (:1176-1455).  No golden file of the reference covers it; it is held by equality with the golden-pinned
+ * NDIM=2 routines on z-invariant runs (round-off level), div B = 0 and conservation (tests/test_oracle_mhd.py).
+ * ====================================================================================================== */
+typedef struct {
+  double flux[3][3][3][3][NV];
+  double emf[3][3][3][3];     /* [dir][k3-1][j3-1][i3-1], dir 0,1,2 = emfx, emfy, emfz */
+  int nfc[27];
+} mhd3_result;
+
+static inline double tvd2(int mt, double b0, double bl, double br) { /* one direction of compute_2d_tvd :1478 */
+  if (mt == 3) { double dlft = half * (b0 - bl), drgt = half * (br - b0); return dlft + drgt; }
+  return slope_mm((double)mt, bl, b0, br);
+}
+
+/* interpol_hydro mhd/interpol_hydro.f90:612 for one father cell, NDIM=3, interpol_var=0: u2[8][11] */
+void orc_mhd3_interpol_cell(const orc_mesh* m, int ind_cell, int ilevel, const double* uold, double* u2) {
+  int fa[7], ind1[7];
+  double u1[7 * NVS], t2[8 * NVS];
+  orc_getnborfather(m, ind_cell, ilevel, fa);
+  for (int j = 0; j < 7; j++) {
+    for (int iv = 1; iv <= NVS; iv++) u1[j * NVS + iv - 1] = UO(fa[j], iv);
+    ind1[j] = m->son[fa[j]];
+  }
+  orc_interpol_hydro(hydro_like_params(3), u1, t2);          /* variables 1..5 (cell centred); the face fields are overwritten */
+  for (int ind = 0; ind < 8; ind++)
+    for (int iv = 0; iv < NVS; iv++) u2[ind * NVS + iv] = t2[ind * NVS + iv];
+  double u[3][2][2], v[2][3][2], w[2][2][3];                 /* u[i+1][j][k], v[i][j+1][k], w[i][j][k+1] */
+  const int mt = g_interpol_mag_type;
+#define B1(j_, c_) u1[(j_)*NVS + ((c_) <= 3 ? 4 + (c_) : NV + (c_)-4)]
+  for (int side = 0; side < 2; side++) { /* interpol_faces :1052 */
+    const int cx = side == 0 ? 1 : 4, cy = side == 0 ? 2 : 5, cz = side == 0 ? 3 : 6, f = side == 0 ? 0 : 2;
+    double s1 = 0.0, s2 = 0.0;
+    if (mt > 0) { s1 = tvd2(mt, B1(0, cx), B1(3, cx), B1(4, cx)); s2 = tvd2(mt, B1(0, cx), B1(5, cx), B1(6, cx)); }
+    for (int j = 0; j <= 1; j++)
+      for (int k = 0; k <= 1; k++) u[f][j][k] = B1(0, cx) + 0.5 * s1 * ((double)j - 0.5) + 0.5 * s2 * ((double)k - 0.5);
+    s1 = s2 = 0.0;
+    if (mt > 0) { s1 = tvd2(mt, B1(0, cy), B1(1, cy), B1(2, cy)); s2 = tvd2(mt, B1(0, cy), B1(5, cy), B1(6, cy)); }
+    for (int i = 0; i <= 1; i++)
+      for (int k = 0; k <= 1; k++) v[i][f][k] = B1(0, cy) + 0.5 * s1 * ((double)i - 0.5) + 0.5 * s2 * ((double)k - 0.5);
+    s1 = s2 = 0.0;
+    if (mt > 0) { s1 = tvd2(mt, B1(0, cz), B1(1, cz), B1(2, cz)); s2 = tvd2(mt, B1(0, cz), B1(3, cz), B1(4, cz)); }
+    for (int i = 0; i <= 1; i++)
+      for (int j = 0; j <= 1; j++) w[i][j][f] = B1(0, cz) + 0.5 * s1 * ((double)i - 0.5) + 0.5 * s2 * ((double)j - 0.5);
+  }
+#undef B1
+  /* copy_from_refined_faces :1246 */
+  for (int a = 0; a <= 1; a++)
+    for (int b = 0; b <= 1; b++) {
+      if (ind1[1] > 0) u[0][a][b] = UO(m->ncoarse + (1 + a * 2 + b * 4) * m->ngridmax + ind1[1], NV + 1);
+      if (ind1[2] > 0) u[2][a][b] = UO(m->ncoarse + (0 + a * 2 + b * 4) * m->ngridmax + ind1[2], 6);
+      if (ind1[3] > 0) v[a][0][b] = UO(m->ncoarse + (a + 1 * 2 + b * 4) * m->ngridmax + ind1[3], NV + 2);
+      if (ind1[4] > 0) v[a][2][b] = UO(m->ncoarse + (a + 0 * 2 + b * 4) * m->ngridmax + ind1[4], 7);
+      if (ind1[5] > 0) w[a][b][0] = UO(m->ncoarse + (a + b * 2 + 1 * 4) * m->ngridmax + ind1[5], NV + 3);
+      if (ind1[6] > 0) w[a][b][2] = UO(m->ncoarse + (a + b * 2 + 0 * 4) * m->ngridmax + ind1[6], 8);
+    }
+  /* cmp_central_faces :1354, NDIM==3 */
+  double UXX = 0, VYY = 0, WZZ = 0, UXYZ = 0, VXYZ = 0, WXYZ = 0;
+  for (int i = 0; i <= 1; i++)
+    for (int j = 0; j <= 1; j++)
+      for (int k = 0; k <= 1; k++) {
+        const int ii = 2 * i - 1, jj = 2 * j - 1, kk = 2 * k - 1;
+        UXX = UXX + ((double)(ii * jj) * v[i][jj + 1][k] + (double)(ii * kk) * w[i][j][kk + 1]) * 0.125;
+        VYY = VYY + ((double)(jj * kk) * w[i][j][kk + 1] + (double)(ii * jj) * u[ii + 1][j][k]) * 0.125;
+        WZZ = WZZ + ((double)(ii * kk) * u[ii + 1][j][k] + (double)(jj * kk) * v[i][jj + 1][k]) * 0.125;
+        UXYZ = UXYZ + ((double)(ii * jj * kk) * u[ii + 1][j][k]) * 0.125;
+        VXYZ = VXYZ + ((double)(ii * jj * kk) * v[i][jj + 1][k]) * 0.125;
+        WXYZ = WXYZ + ((double)(ii * jj * kk) * w[i][j][kk + 1]) * 0.125;
+      }
+  for (int j = 0; j <= 1; j++)
+    for (int k = 0; k <= 1; k++)
+      u[1][j][k] = 0.5 * (u[0][j][k] + u[2][j][k]) + UXX + ((double)k - 0.5) * VXYZ + ((double)j - 0.5) * WXYZ;
+  for (int i = 0; i <= 1; i++)
+    for (int k = 0; k <= 1; k++)
+      v[i][1][k] = 0.5 * (v[i][0][k] + v[i][2][k]) + VYY + ((double)i - 0.5) * WXYZ + ((double)k - 0.5) * UXYZ;
+  for (int i = 0; i <= 1; i++)
+    for (int j = 0; j <= 1; j++)
+      w[i][j][1] = 0.5 * (w[i][j][0] + w[i][j][2]) + WZZ + ((double)j - 0.5) * UXYZ + ((double)i - 0.5) * VXYZ;
+  for (int i = 0; i <= 1; i++)
+    for (int j = 0; j <= 1; j++)
+      for (int k = 0; k <= 1; k++) {
+        const int ind = i + 2 * j + 4 * k;
+        u2[ind * NVS + 5] = u[i][j][k];      u2[ind * NVS + NV + 0] = u[i + 1][j][k];
+        u2[ind * NVS + 6] = v[i][j][k];      u2[ind * NVS + NV + 1] = v[i][j + 1][k];
+        u2[ind * NVS + 7] = w[i][j][k];      u2[ind * NVS + NV + 2] = w[i][j][k + 1];
+      }
+}
+
+/* the twelve EMF edges of the coarse refluxing :1176-1455.  Variables: 6,7,8 = left faces (1..3+neul), 9,10,11 = right faces */
+typedef struct { int f[3][3]; int dir; int c[2][3]; int upd[4][3]; int leaf[2][3]; } mhd_edge;   /* upd = {buffer 1..3, var, sign} */
+static const mhd_edge MHD_EDGES[12] = {
+    /* EMFz: X0Y0, X0Y1, X1Y1, X1Y0 */
+    {{{1, 0, 1}, {0, 0, 1}, {0, 1, 1}}, 2, {{1, 1, 1}, {1, 1, 2}}, {{1, 6, +1}, {2, 9, +1}, {2, 10, -1}, {3, 7, -1}}, {{3, 9, -1}, {1, 10, +1}}},
+    {{{0, 1, 1}, {0, 2, 1}, {1, 2, 1}}, 2, {{1, 3, 1}, {1, 3, 2}}, {{1, 10, -1}, {2, 7, -1}, {2, 9, -1}, {3, 6, -1}}, {{3, 7, +1}, {1, 9, +1}}},
+    {{{1, 2, 1}, {2, 2, 1}, {2, 1, 1}}, 2, {{3, 3, 1}, {3, 3, 2}}, {{1, 9, -1}, {2, 6, -1}, {2, 7, +1}, {3, 10, +1}}, {{3, 6, +1}, {1, 7, -1}}},
+    {{{2, 1, 1}, {2, 0, 1}, {1, 0, 1}}, 2, {{3, 1, 1}, {3, 1, 2}}, {{1, 7, +1}, {2, 10, +1}, {2, 6, +1}, {3, 9, +1}}, {{3, 10, -1}, {1, 6, -1}}},
+    /* EMFx: Y0Z0, Y0Z1, Y1Z1, Y1Z0 */
+    {{{1, 1, 0}, {1, 0, 0}, {1, 0, 1}}, 0, {{1, 1, 1}, {2, 1, 1}}, {{1, 7, +1}, {2, 10, +1}, {2, 11, -1}, {3, 8, -1}}, {{1, 11, +1}, {3, 10, -1}}},
+    {{{1, 0, 1}, {1, 0, 2}, {1, 1, 2}}, 0, {{1, 1, 3}, {2, 1, 3}}, {{1, 11, -1}, {2, 8, -1}, {2, 10, -1}, {3, 7, -1}}, {{1, 10, +1}, {3, 8, +1}}},
+    {{{1, 1, 2}, {1, 2, 2}, {1, 2, 1}}, 0, {{1, 3, 3}, {2, 3, 3}}, {{1, 10, -1}, {2, 7, -1}, {2, 8, +1}, {3, 11, +1}}, {{3, 7, +1}, {1, 8, -1}}},
+    {{{1, 2, 1}, {1, 2, 0}, {1, 1, 0}}, 0, {{1, 3, 1}, {2, 3, 1}}, {{1, 8, +1}, {2, 11, +1}, {2, 7, +1}, {3, 10, +1}}, {{3, 11, -1}, {1, 7, -1}}},
+    /* EMFy: X0Z0, X0Z1, X1Z1, X1Z0 */
+    {{{1, 1, 0}, {0, 1, 0}, {0, 1, 1}}, 1, {{1, 1, 1}, {1, 2, 1}}, {{1, 6, -1}, {2, 9, -1}, {2, 11, +1}, {3, 8, +1}}, {{3, 9, +1}, {1, 11, -1}}},
+    {{{0, 1, 1}, {0, 1, 2}, {1, 1, 2}}, 1, {{1, 1, 3}, {1, 2, 3}}, {{1, 11, +1}, {2, 8, +1}, {2, 9, +1}, {3, 6, +1}}, {{3, 8, -1}, {1, 9, -1}}},
+    {{{1, 1, 2}, {2, 1, 2}, {2, 1, 1}}, 1, {{3, 1, 3}, {3, 2, 3}}, {{1, 9, +1}, {2, 6, +1}, {2, 8, -1}, {3, 11, -1}}, {{3, 6, -1}, {1, 8, +1}}},
+    {{{2, 1, 1}, {2, 1, 0}, {1, 1, 0}}, 1, {{3, 1, 1}, {3, 2, 1}}, {{1, 8, -1}, {2, 11, -1}, {2, 6, -1}, {3, 9, -1}}, {{3, 11, +1}, {1, 6, +1}}}};
+
+static void mhd3_godfine1(const orc_mhd_params* p, const orc_mesh* m, const int* ind_grid, int ncache, int ilevel, int levelmin,
+                          double dt, const double* uold, double* unew) {
+  const double dx = level_dx(p, m, ilevel);
+  mhd3_result* R = (mhd3_result*)malloc(sizeof(mhd3_result) * (size_t)ncache);
+#ifdef _OPENMP
+#pragma omp parallel num_threads(g_threads) if (g_threads > 1)
+#endif
+  {
+    orc_mhd_work* w = orc_mhd_work_new();
+    int(*ok)[6][6] = (int(*)[6][6])malloc(sizeof(int) * 216);
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+    for (int i = 0; i < ncache; i++) {
+      mhd3_result* r = &R[i];
+      orc_get3cubefather(m, m->father[ind_grid[i]], ilevel, r->nfc, NULL);
+      for (int k1 = 0; k1 <= 2; k1++)
+        for (int j1 = 0; j1 <= 2; j1++)
+          for (int i1 = 0; i1 <= 2; i1++) {
+            const int fc = r->nfc[i1 + 3 * j1 + 9 * k1];
+            const int igrid_nbor = m->son[fc];
+            double u2[8 * NVS];
+            if (igrid_nbor <= 0) orc_mhd3_interpol_cell(m, fc, ilevel, uold, u2);
+            for (int k2 = 0; k2 <= 1; k2++)
+              for (int j2 = 0; j2 <= 1; j2++)
+                for (int i2 = 0; i2 <= 1; i2++) {
+                  const int ind_son = i2 + 2 * j2 + 4 * k2;
+                  const int i3 = 1 + 2 * (i1 - 1) + i2, j3 = 1 + 2 * (j1 - 1) + j2, k3 = 1 + 2 * (k1 - 1) + k2;
+                  if (igrid_nbor > 0) {
+                    const int ic = m->ncoarse + ind_son * m->ngridmax + igrid_nbor;
+                    for (int iv = 1; iv <= NVS; iv++) w->uloc[X(k3)][X(j3)][X(i3)][iv - 1] = UO(ic, iv);
+                    ok[X(k3)][X(j3)][X(i3)] = m->son[ic] > 0;
+                  } else {
+                    for (int iv = 0; iv < NVS; iv++) w->uloc[X(k3)][X(j3)][X(i3)][iv] = u2[ind_son * NVS + iv];
+                    ok[X(k3)][X(j3)][X(i3)] = 0;
+                  }
+                }
+          }
+      orc_mhd_unsplit(p, w, dx, dt);
+      memcpy(r->flux, w->flux, sizeof r->flux);
+      memcpy(r->emf[0], w->emfx, sizeof w->emfx);
+      memcpy(r->emf[1], w->emfy, sizeof w->emfy);
+      memcpy(r->emf[2], w->emfz, sizeof w->emfz);
+      /* reset flux along direction at refined interface :760-782; Euler fluxes of Bx, By, Bz :786-879 */
+      for (int idim = 0; idim < 3; idim++) {
+        const int i0 = idim == 0, j0 = idim == 1, k0 = idim == 2;
+        for (int k3 = 1; k3 <= 2 + k0; k3++)
+          for (int j3 = 1; j3 <= 2 + j0; j3++)
+            for (int i3 = 1; i3 <= 2 + i0; i3++) {
+              double* f = r->flux[idim][k3 - 1][j3 - 1][i3 - 1];
+              if (ok[X(k3 - k0)][X(j3 - j0)][X(i3 - i0)] || ok[X(k3)][X(j3)][X(i3)])
+                for (int n = 0; n < NV; n++) f[n] = 0.0;
+              f[5] = 0.0; f[6] = 0.0; f[7] = 0.0;
+            }
+      }
+      /* reset electromotive forces at refined edges :805-869 */
+      for (int k3 = 1; k3 <= 2; k3++)
+        for (int j3 = 1; j3 <= 3; j3++)
+          for (int i3 = 1; i3 <= 3; i3++)
+            if (ok[X(k3)][X(j3)][X(i3)] || ok[X(k3)][X(j3 - 1)][X(i3)] || ok[X(k3)][X(j3)][X(i3 - 1)] || ok[X(k3)][X(j3 - 1)][X(i3 - 1)])
+              r->emf[2][k3 - 1][j3 - 1][i3 - 1] = 0.0;
+      for (int k3 = 1; k3 <= 3; k3++)
+        for (int j3 = 1; j3 <= 2; j3++)
+          for (int i3 = 1; i3 <= 3; i3++)
+            if (ok[X(k3)][X(j3)][X(i3)] || ok[X(k3 - 1)][X(j3)][X(i3)] || ok[X(k3)][X(j3)][X(i3 - 1)] || ok[X(k3 - 1)][X(j3)][X(i3 - 1)])
+              r->emf[1][k3 - 1][j3 - 1][i3 - 1] = 0.0;
+      for (int k3 = 1; k3 <= 3; k3++)
+        for (int j3 = 1; j3 <= 3; j3++)
+          for (int i3 = 1; i3 <= 2; i3++)
+            if (ok[X(k3)][X(j3)][X(i3)] || ok[X(k3 - 1)][X(j3)][X(i3)] || ok[X(k3)][X(j3 - 1)][X(i3)] || ok[X(k3 - 1)][X(j3 - 1)][X(i3)])
+              r->emf[0][k3 - 1][j3 - 1][i3 - 1] = 0.0;
+    }
+    free(ok);
+    orc_mhd_work_free(w);
+  }
+  /* conservative update at level ilevel for the Euler system :886-934 */
+  for (int idim = 0; idim < 3; idim++) {
+    const int i0 = idim == 0, j0 = idim == 1, k0 = idim == 2;
+    for (int k2 = 0; k2 <= 1; k2++)
+      for (int j2 = 0; j2 <= 1; j2++)
+        for (int i2 = 0; i2 <= 1; i2++) {
+          const int iskip = m->ncoarse + (i2 + 2 * j2 + 4 * k2) * m->ngridmax;
+          for (int iv = 1; iv <= NV; iv++)
+            for (int i = 0; i < ncache; i++) {
+              const int ic = iskip + ind_grid[i];
+              UN(ic, iv) = UN(ic, iv) + (R[i].flux[idim][k2][j2][i2][iv - 1] - R[i].flux[idim][k2 + k0][j2 + j0][i2 + i0][iv - 1]);
+            }
+          for (int iv = 1; iv <= 3; iv++)
+            for (int i = 0; i < ncache; i++) {
+              const int ic = iskip + ind_grid[i];
+              UN(ic, NV + iv) = UN(ic, NV + iv) + (R[i].flux[idim][k2][j2][i2][5 + iv - 1] - R[i].flux[idim][k2 + k0][j2 + j0][i2 + i0][5 + iv - 1]);
+            }
+        }
+  }
+  /* constrained transport :939-995 */
+#define RX(i3, j3, k3) R[i].emf[0][(k3)-1][(j3)-1][(i3)-1]
+#define RY(i3, j3, k3) R[i].emf[1][(k3)-1][(j3)-1][(i3)-1]
+#define RZ(i3, j3, k3) R[i].emf[2][(k3)-1][(j3)-1][(i3)-1]
+  for (int comp = 0; comp < 3; comp++)
+    for (int k3 = 1; k3 <= 2; k3++)
+      for (int j3 = 1; j3 <= 2; j3++)
+        for (int i3 = 1; i3 <= 2; i3++) {
+          const int iskip = m->ncoarse + ((i3 - 1) + 2 * (j3 - 1) + 4 * (k3 - 1)) * m->ngridmax;
+          for (int i = 0; i < ncache; i++) {
+            const int ic = iskip + ind_grid[i];
+            double df;
+            if (comp == 0) {
+              df = (RY(i3, j3, k3) - RY(i3, j3, k3 + 1)) - (RZ(i3, j3, k3) - RZ(i3, j3 + 1, k3));
+              UN(ic, 6) = UN(ic, 6) + df;
+              df = (RY(i3 + 1, j3, k3) - RY(i3 + 1, j3, k3 + 1)) - (RZ(i3 + 1, j3, k3) - RZ(i3 + 1, j3 + 1, k3));
+              UN(ic, NV + 1) = UN(ic, NV + 1) + df;
+            } else if (comp == 1) {
+              df = (RZ(i3, j3, k3) - RZ(i3 + 1, j3, k3)) - (RX(i3, j3, k3) - RX(i3, j3, k3 + 1));
+              UN(ic, 7) = UN(ic, 7) + df;
+              df = (RZ(i3, j3 + 1, k3) - RZ(i3 + 1, j3 + 1, k3)) - (RX(i3, j3 + 1, k3) - RX(i3, j3 + 1, k3 + 1));
+              UN(ic, NV + 2) = UN(ic, NV + 2) + df;
+            } else {
+              df = (RX(i3, j3, k3) - RX(i3, j3 + 1, k3)) - (RY(i3, j3, k3) - RY(i3 + 1, j3, k3));
+              UN(ic, 8) = UN(ic, 8) + df;
+              df = (RX(i3, j3, k3 + 1) - RX(i3, j3 + 1, k3 + 1)) - (RY(i3, j3, k3 + 1) - RY(i3 + 1, j3, k3 + 1));
+              UN(ic, NV + 3) = UN(ic, NV + 3) + df;
+            }
+          }
+        }
+#undef RX
+#undef RY
+#undef RZ
+  if (ilevel > levelmin) {
+    /* conservative update at level ilevel-1 for the Euler system :1030-1168 */
+    const double oneontwotondim = 0.125;
+    int* ind_buffer = (int*)malloc(sizeof(int) * (size_t)(ncache + 1));
+    int* ind_cell = (int*)malloc(sizeof(int) * (size_t)(ncache + 1));
+    for (int idim = 0; idim < 3; idim++) {
+      const int i0 = idim == 0, j0 = idim == 1, k0 = idim == 2;
+      for (int side = 0; side < 2; side++) {
+        int nb = 0;
+        for (int i = 0; i < ncache; i++) {
+          const int c = NBOR(m, ind_grid[i], 2 * idim + 1 + side);
+          if (m->son[c] == 0) { ind_buffer[nb] = c; ind_cell[nb] = i; nb++; }
+        }
+        const int k3lo = side == 0 ? 1 : 1 + k0, k3hi = side == 0 ? 2 - k0 : 2;
+        const int j3lo = side == 0 ? 1 : 1 + j0, j3hi = side == 0 ? 2 - j0 : 2;
+        const int i3lo = side == 0 ? 1 : 1 + i0, i3hi = side == 0 ? 2 - i0 : 2;
+        const int di = side == 0 ? 0 : i0, dj = side == 0 ? 0 : j0, dk = side == 0 ? 0 : k0;
+        for (int pass = 0; pass < 2; pass++) {
+          const int nv_ = pass == 0 ? NV : 3;
+          for (int iv = 1; iv <= nv_; iv++)
+            for (int k3 = k3lo; k3 <= k3hi; k3++)
+              for (int j3 = j3lo; j3 <= j3hi; j3++)
+                for (int i3 = i3lo; i3 <= i3hi; i3++)
+                  for (int i = 0; i < nb; i++) {
+                    const int dst = pass == 0 ? iv : NV + iv, src = pass == 0 ? iv - 1 : 5 + iv - 1;
+                    const double f = R[ind_cell[i]].flux[idim][k3 + dk - 1][j3 + dj - 1][i3 + di - 1][src] * oneontwotondim;
+                    if (side == 0) UN(ind_buffer[i], dst) = UN(ind_buffer[i], dst) - f;
+                    else UN(ind_buffer[i], dst) = UN(ind_buffer[i], dst) + f;
+                  }
+        }
+      }
+    }
+    free(ind_buffer); free(ind_cell);
+    /* conservative update at level ilevel-1 for the induction system :1176-1455 */
+    for (int e = 0; e < 12; e++) {
+      const mhd_edge* E = &MHD_EDGES[e];
+      for (int i = 0; i < ncache; i++) {
+        const mhd3_result* r = &R[i];
+        int b[4];
+        for (int q = 0; q < 3; q++) b[q + 1] = r->nfc[E->f[q][0] + 3 * E->f[q][1] + 9 * E->f[q][2]];
+        double weight = 1.0;
+        if (m->son[b[1]] > 0 && m->son[b[3]] > 0) continue;
+        if (m->son[b[1]] > 0 || m->son[b[2]] > 0 || m->son[b[3]] > 0) weight = 0.5;
+        const double dflux = (r->emf[E->dir][E->c[0][2] - 1][E->c[0][1] - 1][E->c[0][0] - 1] +
+                              r->emf[E->dir][E->c[1][2] - 1][E->c[1][1] - 1][E->c[1][0] - 1]) * 0.25 * weight;
+        for (int q = 0; q < 4; q++) {
+          const int c = b[E->upd[q][0]], var = E->upd[q][1];
+          if (E->upd[q][2] > 0) UN(c, var) = UN(c, var) + dflux; else UN(c, var) = UN(c, var) - dflux;
+        }
+        if (m->son[b[1]] == 0 && m->son[b[2]] == 0 && m->son[b[3]] == 0)
+          for (int q = 0; q < 2; q++) {
+            const int c = b[E->leaf[q][0]], var = E->leaf[q][1];
+            if (E->leaf[q][2] > 0) UN(c, var) = UN(c, var) + dflux * 0.5; else UN(c, var) = UN(c, var) - dflux * 0.5;
+          }
+      }
+    }
+  }
+  free(R);
+}
+
+void orc_mhd3_godunov_fine(const orc_mhd_params* p, const orc_mesh* m, int ilevel, int levelmin, int nvector, double dt,
+                           const double* uold, double* unew) {
+  if (m->ndim != 3) { fprintf(stderr, "oracle(mhd 3-D AMR): NDIM=%d\n", m->ndim); abort(); }
+  const int ncache = m->nactive[ilevel];
+  for (int ig = 0; ig < ncache; ig += nvector) {
+    const int ngrid = (nvector < ncache - ig) ? nvector : ncache - ig;
+    mhd3_godfine1(p, m, m->active[ilevel] + ig, ngrid, ilevel, levelmin, dt, uold, unew);
+  }
+}
+
+/* a z-invariant Orszag-Tang state for NDIM=3 (the NDIM=2 condinit applied to every z) */
+void orc_mhd3_condinit_orszag_tang(const orc_mhd_params* p, const orc_mesh* m, int ilevel, double* uold) {
+  const int nx_loc = m->icoarse_max - m->icoarse_min + 1;
+  const double scale = p->boxlen / (double)nx_loc;
+  const double dxl = pow(0.5, ilevel);
+  const double dx = dxl * scale;
+  const double pi = acos(-1.0);
+  const double B0 = 1.0 / sqrt(4.0 * pi);
+  const double skip[2] = {(double)m->icoarse_min, (double)m->jcoarse_min};
+  for (int a = 0; a < m->nactive[ilevel]; a++) {
+    const int ig = m->active[ilevel][a];
+    for (int ind = 0; ind < 8; ind++) {
+      const double xcell[2] = {((double)(ind & 1) - 0.5) * dxl, ((double)((ind >> 1) & 1) - 0.5) * dxl};
+      double x[2];
+      for (int d = 0; d < 2; d++) x[d] = (m->xg[(size_t)d * (m->ngridmax + 1) + ig] + xcell[d] - skip[d]) * scale;
+      const double xl = x[0] - 0.5 * dx, xr = x[0] + 0.5 * dx, xc = x[0];
+      const double yl = x[1] - 0.5 * dx, yr = x[1] + 0.5 * dx, yc = x[1];
+      double q[NVS];
+      q[0] = 25.0 / (36.0 * pi); q[1] = -sin(2.0 * pi * yc); q[2] = +sin(2.0 * pi * xc); q[3] = 0.0; q[4] = 5.0 / (12.0 * pi);
+      double Ar, Al;
+      Ar = B0 * (cos(4.0 * pi * xl) / (4.0 * pi) + cos(2.0 * pi * yr) / (2.0 * pi));
+      Al = B0 * (cos(4.0 * pi * xl) / (4.0 * pi) + cos(2.0 * pi * yl) / (2.0 * pi));
+      q[5] = (Ar - Al) / dx;
+      Ar = B0 * (cos(4.0 * pi * xr) / (4.0 * pi) + cos(2.0 * pi * yr) / (2.0 * pi));
+      Al = B0 * (cos(4.0 * pi * xr) / (4.0 * pi) + cos(2.0 * pi * yl) / (2.0 * pi));
+      q[NV + 0] = (Ar - Al) / dx;
+      Ar = B0 * (cos(4.0 * pi * xr) / (4.0 * pi) + cos(2.0 * pi * yl) / (2.0 * pi));
+      Al = B0 * (cos(4.0 * pi * xl) / (4.0 * pi) + cos(2.0 * pi * yl) / (2.0 * pi));
+      q[6] = (Al - Ar) / dx;
+      Ar = B0 * (cos(4.0 * pi * xr) / (4.0 * pi) + cos(2.0 * pi * yr) / (2.0 * pi));
+      Al = B0 * (cos(4.0 * pi * xl) / (4.0 * pi) + cos(2.0 * pi * yr) / (2.0 * pi));
+      q[NV + 1] = (Al - Ar) / dx;
+      q[7] = 0.0; q[NV + 2] = 0.0;
+      const int ic = m->ncoarse + ind * m->ngridmax + ig;
+      double e = 0.0;
+      e = e + 0.5 * q[0] * (q[1] * q[1]);
+      e = e + 0.5 * q[0] * (q[2] * q[2]);
+      e = e + 0.5 * q[0] * (q[3] * q[3]);
+      e = e + q[4] / (p->gamma - 1.0);
+      e = e + 0.125 * SQ(q[5] + q[NV + 0]);
+      e = e + 0.125 * SQ(q[6] + q[NV + 1]);
+      e = e + 0.125 * SQ(q[7] + q[NV + 2]);
+      UO(ic, 1) = q[0];
+      UO(ic, 2) = q[0] * q[1]; UO(ic, 3) = q[0] * q[2]; UO(ic, 4) = q[0] * q[3];
+      UO(ic, 5) = e;
+      for (int n = 0; n < 3; n++) { UO(ic, 6 + n) = q[5 + n]; UO(ic, NV + 1 + n) = q[NV + n]; }
     }
   }
 }

@@ -65,6 +65,11 @@ double orc_mhdn_courant_fine(const orc_mhd_params*, const orc_mesh*, int ilevel,
 void orc_mhdn_upload_fine(const orc_mhd_params*, const orc_mesh*, int ilevel, double* uold);
 /* tests/mhd/orszag-tang/condinit.f90 on the active octs of a level */
 void orc_mhd2_condinit_orszag_tang(const orc_mhd_params*, const orc_mesh*, int ilevel, double* uold);
+/* NDIM = 3 with AMR (no golden file: held by equality with the NDIM=2 routines on z-invariant runs) */
+void orc_mhd3_interpol_cell(const orc_mesh*, int ind_cell, int ilevel, const double* uold, double* u2 /*[8][11]*/);
+void orc_mhd3_godunov_fine(const orc_mhd_params*, const orc_mesh*, int ilevel, int levelmin, int nvector, double dt, const double* uold, double* unew);
+void orc_mhd_set_courant_ndim(int mask);   /* test hook: bit mask of the directions in cmpdt, 0 = all NDIM */
+void orc_mhd3_condinit_orszag_tang(const orc_mhd_params*, const orc_mesh*, int ilevel, double* uold);
 /* hydro_flag (hydro/hydro_flag.f90, SOLVERmhd) + hydro_refine mhd/godunov_utils.f90:113; err/flo = (d, p, b2, A, B, C, u) */
 void orc_amr_mhd_hydro_flag(const orc_mhd_params*, const orc_mesh*, int ilevel, const double* uold, int* flag1,
                             const double err[7], const double flo[7]);
