@@ -1923,6 +1923,13 @@ double orc_courant_fine(const orc_params* p, const orc_mesh* m, int ilevel, doub
 }
 
 /* make_boundary_hydro hydro/hydro_boundary.f90:5-269 (reflexive and outflow) */
+/* imposed boundaries (bound_type=3): boundary_var(ibound,1:nvar), the conservative state hydro/read_hydro_params.f90:440-468
+ * builds from d_bound, u_bound, ... and the default boundana (hydro/boundana.f90) copies into every boundary cell          */
+static double g_boundary_var[ORC_MAXBOUND][16];
+void orc_set_boundary_var(int ibound, const double* var, int nvar) {
+  for (int iv = 0; iv < nvar && iv < 16; iv++) g_boundary_var[ibound][iv] = var[iv];
+}
+
 void orc_make_boundary_hydro(const orc_params* p, const orc_mesh* m, int ilevel, double* uold) {
   const int ndim = p->ndim, nvar = p->nvar, twotondim = ipow2(ndim);
   static const int ref_x[8] = {2, 1, 4, 3, 6, 5, 8, 7}, ref_y[8] = {3, 4, 1, 2, 7, 8, 5, 6}, ref_z[8] = {5, 6, 7, 8, 1, 2, 3, 4};
@@ -1962,6 +1969,8 @@ void orc_make_boundary_hydro(const orc_params* p, const orc_mesh* m, int ilevel,
           ekin = 0.0; d = FMAX(UO(ic, 1), p->smallr);
           for (int idim = 1; idim <= ndim; idim++) { double v = UO(ic, idim + 1) / d; ekin = ekin + 0.5 * d * (v * v); }
           UO(ic, ndim + 2) = UO(ic, ndim + 2) + ekin;
+        } else { /* imposed :229-252 with the default boundana */
+          for (int iv = 1; iv <= nvar; iv++) UO(ic, iv) = g_boundary_var[ib][iv - 1];
         }
       }
     }

@@ -118,6 +118,8 @@ void orc_godunov_fine(const orc_params*, const orc_mesh*, int ilevel, double dt,
 /* returns dt_all = min(dt_in, CFL dt); sums[3] += mass, etot, eint (courant_fine.f90:1) */
 double orc_courant_fine(const orc_params*, const orc_mesh*, int ilevel, double dt_in, const double* uold, double sums[3]);
 void orc_make_boundary_hydro(const orc_params*, const orc_mesh*, int ilevel, double* uold);
+/* bound_type 3 (imposed): conservative boundary_var of region ibound (0-based) */
+void orc_set_boundary_var(int ibound, const double* var, int nvar);
 void orc_upload_fine(const orc_params*, const orc_mesh*, int ilevel, double* uold);
 
 /* run nstep level steps of a uniform (levelmin=levelmax) run: amr_step order

@@ -338,3 +338,30 @@ def test_pressure_fix_restatement(orc):
         assert p_fix.min() > 0 and s_fix.min() > 0.9 * p0 and on_adiabat(s_fix) > 0.45   # fixed: adiabatic in the expanding half
     finally:
         L.orc_set_pressure_fix(None, None, 0.0)
+
+
+def test_imposed_boundary_supersonic_inflow(orc):
+    """bound_type=3 (hydro/hydro_boundary.f90:229-252, default boundana): ghost cells hold boundary_var; a supersonic uniform
+    inflow through the left face of a 1-D tube with an outflow right face keeps the uniform state exactly, and with a denser
+    inflow the mass of the domain grows by (rho u)_in * dt per step until the front arrives at the other end."""
+    import ctypes as C
+    L = orc.lib()
+    L.orc_set_boundary_var.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
+    n = 64
+    c = Case(1, 6, riemann="hllc", slope_type=1, bound=(3, 2, 0, 0, 0, 0))
+    rho, u, p = 1.0, 3.0, 1.0                                     # Mach 2.5
+    cons = np.array([rho, rho * u, p / 0.4 + 0.5 * rho * u * u])
+    L.orc_set_boundary_var(0, orc.dptr(cons), 3)
+    d = np.zeros((3, 1, 1, n))
+    d[:, 0, 0, :] = cons[:, None]
+    c.init_dense(d)
+    out, dts = c.oracle_steps(5, nthreads=1)
+    assert np.array_equal(c.dense(out), d)                         # uniform supersonic flow is a fixed point
+    cons2 = np.array([2.0, 2.0 * u, p / 0.4 + 0.5 * 2.0 * u * u])
+    L.orc_set_boundary_var(0, orc.dptr(cons2), 3)
+    c.init_dense(d)
+    out, dts = c.oracle_steps(5, nthreads=1)
+    a = c.dense(out)
+    dx = 1.0 / n
+    assert abs((a[0].sum() - d[0].sum()) * dx - (2.0 * u - rho * u) * dts.sum()) < 1e-12     # in: 2u, out: rho u (front not there yet)
+    assert a[0][0, 0, -8:].max() == rho and a[0][0, 0, 0] > 1.5
