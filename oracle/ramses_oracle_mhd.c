@@ -1031,12 +1031,12 @@ static void godfine1(const orc_mhd_params* p, const orc_mesh* m, orc_mhd_work* w
     for (int j1 = 0; j1 <= 2; j1++)
       for (int i1 = 0; i1 <= 2; i1++) {
         int igrid_nbor = m->son[nfc[i1 + 3 * j1 + 9 * k1]];
-        if (igrid_nbor <= 0) { fprintf(stderr, "oracle(mhd): missing neighbour oct (AMR prolongation not restated)\n"); abort(); }
+        if (igrid_nbor <= 0) { fprintf(stderr, "oracle(mhd): missing neighbour oct in the uniform-grid routine (refined meshes: orc_mhd3_godunov_fine)\n"); abort(); }
         for (int k2 = 0; k2 <= 1; k2++)
           for (int j2 = 0; j2 <= 1; j2++)
             for (int i2 = 0; i2 <= 1; i2++) {
               int ic = m->ncoarse + (i2 + 2 * j2 + 4 * k2) * m->ngridmax + igrid_nbor;
-              if (m->son[ic] > 0) { fprintf(stderr, "oracle(mhd): refined cell in stencil (not restated)\n"); abort(); }
+              if (m->son[ic] > 0) { fprintf(stderr, "oracle(mhd): refined cell in the stencil of the uniform-grid routine (refined meshes: orc_mhd3_godunov_fine)\n"); abort(); }
               int i3 = 1 + 2 * (i1 - 1) + i2, j3 = 1 + 2 * (j1 - 1) + j2, k3 = 1 + 2 * (k1 - 1) + k2;
               for (int iv = 1; iv <= NVS; iv++) w->uloc[X(k3)][X(j3)][X(i3)][iv - 1] = UO(ic, iv);
             }
