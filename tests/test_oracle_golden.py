@@ -84,19 +84,7 @@ def test_imhd_tube_golden_sums(imhd_run):
 # ---------------------------------------------------------------------------------------------------------------------
 # 2-D hydro: tests/hydro/implosion (NDIM=2, AMR levels 5..8, hllc, moncen, four reflexive walls whose y-regions include the
 # corner cells, nsubcycle=10*2, nexpand=4 (first level only), interpol_type=2, t=5: 1049 coarse / 8392 fine steps)
-IMPL = [dict(type="square", x_center=0.5, y_center=0.5, length_x=1.0, length_y=1.0, exp_region=10, d=1.0, p=1.0),
-        dict(type="square", x_center=0.0, y_center=0.0, length_x=1.0, length_y=1.0, exp_region=1, d=0.125, p=0.4)]
-# BOUNDARY_PARAMS of implosion.nml:17-24 after hydro/read_hydro_params.f90:316-407: (boundary_type, i-, j-, k-range)
-IMPL_BOUND = [(1, (0, 0), (1, 1), (0, 0)), (2, (2, 2), (1, 1), (0, 0)), (4, (0, 2), (2, 2), (0, 0)), (3, (0, 2), (0, 0), (0, 0))]
-
-
-@pytest.fixture(scope="module")
-def implosion_run(orc):
-    from oracle.amr import FastAmrRun
-    r = FastAmrRun(2, 5, 8, (1, 1, 1, 1, 0, 0), 1.0, nsubcycle=[2] * 10, nexpand=[4], ngridmax=100000, riemann="hllc",
-                   slope_type=2, gamma=1.4, courant_factor=0.8, err_grad_d=0.05, err_grad_u=0.05, err_grad_p=0.05,
-                   interpol_type=2, interpol_var=0, regions=IMPL, tout=[0.0, 5.0], bound_regions=IMPL_BOUND)
-    return r, r.run()
+from conftest import IMPL, IMPL_BOUND      # the run itself is the session fixture `implosion_run` (tests/conftest.py)
 
 
 def test_implosion_golden_sums(implosion_run):
@@ -152,14 +140,6 @@ def test_amr_flux_threads_do_not_change_results(orc):
 # ---------------------------------------------------------------------------------------------------------------------
 # 2-D ideal MHD: tests/mhd/orszag-tang (NDIM=2, AMR levels 5..9, hlld / hlld, moncen, periodic, nsubcycle=1*1,2, err_grad_p=0.1,
 # interpol_type=2, the patch's condinit.f90, t=0.5: 174 coarse / 1236 fine steps, 100 066 leaf cells)
-@pytest.fixture(scope="module")
-def orszag_run(orc):
-    from oracle.amr_mhd import MhdAmrRun2D
-    r = MhdAmrRun2D(5, 9, 1.0, nsubcycle=[1], riemann="hlld", riemann2d="hlld", slope_type=2, gamma=1.6666667,
-                    courant_factor=0.8, err_grad_p=0.1, interpol_type=2, tout=[0.5], nexpand=1, ngridmax=100000)
-    return r, r.run()
-
-
 def test_orszag_tang_golden_sums(orszag_run):
     """tests/mhd/orszag-tang/orszag-tang-ref.dat at the reference's tolerance (3e-13; we get <= 2e-15 on every sum): pins the
     NDIM=2 MHD paths -- trace2d, the hlld 1-D solver and the hlld 2-D (corner EMF) solver of cmp_mag_flx, the constrained-transport

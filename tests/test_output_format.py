@@ -1,0 +1,117 @@
+"""ramses_b200/output.py writes the reference's snapshot format; the files are read back with the REFERENCE's own reader and
+checked with the REFERENCE's own check_solution (tests/visu/visu_ramses.py) against the golden sums: state -> reference file
+format -> reference reader -> reference checker.  Needs the reference tree (only present in the build container): skipped on
+machines without it."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REF_VISU = "/root/reference/tests/visu"
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF_VISU, "visu_ramses.py")),
+                                reason="reference tree not available")
+
+
+def _write_from_run(r, tmp, iout, mhd=False):
+    """the oracle AMR driver's tree / state (1-based arrays with an unused element 0) -> output_NNNNN/"""
+    from ramses_b200.output import write_snapshot
+    m = r.m
+    nb = m.nboundary
+    L = r.nlevelmax
+    nvs = r.nvar
+    return write_snapshot(
+        str(tmp), iout, ndim=r.ndim, nvar=8 if mhd else r.nvar, levelmin=r.levelmin, nlevelmax=L, ngridmax=r.ngridmax,
+        ncoarse=r.ncoarse, nxyz=(m.nx, m.ny, m.nz), coarse_min=(m.icoarse_min, m.jcoarse_min, m.kcoarse_min),
+        coarse_max=(m.icoarse_max, m.jcoarse_max, m.kcoarse_max), boxlen=r.p.boxlen, gamma=(r.pm.gamma if mhd else r.p.gamma),
+        smallr=r.p.smallr, son=r.son[1:], father=r.father[1:], nbor=r.nbor[:, 1:], xg=r.xg[:, 1:],
+        active=[r.active[l] for l in range(1, L + 1)], boundary=[[r.bound[b][l] for l in range(1, L + 1)] for b in range(nb)],
+        uold=r.uold.reshape(nvs, r.ncell), t=r.t, dtold=[r.dtold[l] for l in range(1, L + 1)],
+        dtnew=[r.dtnew[l] for l in range(1, L + 1)], nstep=r.nstep, nstep_coarse=r.nstep_coarse, tout=r.tout, mhd=mhd)
+
+
+def _check_with_reference(tmp, iout, test_name, ref_json):
+    sys.path.insert(0, REF_VISU)
+    try:
+        import visu_ramses
+    finally:
+        sys.path.remove(REF_VISU)
+    ref = json.load(open(os.path.join(GOLD, ref_json)))
+    cwd = os.getcwd()
+    os.chdir(str(tmp))
+    try:
+        with open(test_name + "-ref.dat", "w") as f:
+            for k in sorted(ref):
+                f.write("%s : %.16e\n" % (k, ref[k]))
+        data = visu_ramses.load_snapshot(iout)
+        visu_ramses.check_solution(data["data"], test_name)       # what tests/*/plot-*.py end with; prints PASSED
+    finally:
+        os.chdir(cwd)
+    return data
+
+
+def test_sod_tube_snapshot_through_reference_reader(orc, tmp_path, capsys):
+    from oracle.amr import AmrRun
+    from test_oracle_golden import SOD
+    r = AmrRun(1, 3, 10, (1, 1, 0, 0, 0, 0), 1.0, nsubcycle=[1, 1, 1, 2], nexpand=1, ngridmax=2000, riemann="hllc",
+               slope_type=2, gamma=1.4, courant_factor=0.8, err_grad_d=0.05, err_grad_u=0.05, err_grad_p=0.05,
+               interpol_type=2, interpol_var=0, regions=SOD, tout=[0.245])
+    snap = r.run()
+    # the driver stops after the output step: the state at the output time is the current one
+    _write_from_run(r, tmp_path, 2)
+    data = _check_with_reference(tmp_path, 2, "sod-tube", "sod_tube_ref.json")
+    assert "PASSED" in capsys.readouterr().out              # the reference's own verdict on the reference's own golden file
+    assert data["data"]["ncells"] == 142 and abs(data["data"]["time"] - snap["t"]) < 1e-14
+    rows = snap["rows"]
+    x = np.array([q[1][0] for q in rows])
+    order_ref, order_ours = np.argsort(data["data"]["x"]), np.argsort(x)
+    assert np.array_equal(np.sort(data["data"]["x"]), np.sort(x))
+    assert np.array_equal(data["data"]["density"][order_ref], np.array([q[2] for q in rows])[order_ours])
+    assert np.array_equal(data["data"]["pressure"][order_ref], np.array([q[4] for q in rows])[order_ours])
+
+
+def test_orszag_tang_snapshot_through_reference_reader(orc, tmp_path):
+    """a short NDIM=2 MHD AMR run: the eleven output fields survive the file format bit for bit"""
+    from oracle.amr_mhd import MhdAmrRun2D
+    r = MhdAmrRun2D(4, 6, 1.0, nsubcycle=[1], riemann="hlld", riemann2d="hlld", slope_type=2, gamma=1.6666667, courant_factor=0.8,
+                    err_grad_p=0.1, interpol_type=2, tout=[0.1], nexpand=1, ngridmax=20000)
+    snap = r.run()
+    _write_from_run(r, tmp_path, 2, mhd=True)
+    sys.path.insert(0, REF_VISU)
+    try:
+        import visu_ramses
+    finally:
+        sys.path.remove(REF_VISU)
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path))
+    try:
+        data = visu_ramses.load_snapshot(2)
+    finally:
+        os.chdir(cwd)
+    ours = snap["rows"]
+    assert data["data"]["ncells"] == len(ours["level"])
+    key_ref = np.lexsort((data["data"]["y"], data["data"]["x"]))
+    key_our = np.lexsort((ours["y"], ours["x"]))
+    for k in ("level", "x", "y", "dx", "density", "velocity_x", "velocity_y", "velocity_z", "pressure", "B_x_left", "B_y_left",
+              "B_z_left", "B_x_right", "B_y_right", "B_z_right"):
+        assert np.array_equal(np.asarray(data["data"][k])[key_ref], np.asarray(ours[k])[key_our]), k
+
+
+def test_implosion_and_orszag_tang_through_reference_checker(implosion_run, orszag_run, tmp_path, capsys):
+    """the two long golden runs (session fixtures shared with test_oracle_golden.py): write the final state in the reference's
+    format and let the REFERENCE's check_solution compare with the REFERENCE's golden file -- it prints PASSED for orszag-tang
+    (all sums to 2e-15) and for implosion (within its 3e-13 tolerance)."""
+    r, _ = orszag_run
+    d1 = tmp_path / "ot"
+    d1.mkdir()
+    _write_from_run(r, d1, 2, mhd=True)
+    _check_with_reference(d1, 2, "orszag-tang", "orszag_tang_ref.json")
+    assert "PASSED" in capsys.readouterr().out
+    r, _ = implosion_run
+    d2 = tmp_path / "impl"
+    d2.mkdir()
+    _write_from_run(r, d2, 2)
+    _check_with_reference(d2, 2, "implosion", "implosion_ref.json")
+    assert "PASSED" in capsys.readouterr().out
