@@ -213,3 +213,27 @@ def write_snapshot(outdir, iout, *, ndim, nvar, levelmin, nlevelmax, ngridmax, n
                     r.darr(u[k] / dmax)
     r.close()
     return d
+
+
+def snapshot_from_commons(a, outdir, iout, t=0.0, levelmin=None, nstep=0, nstep_coarse=0):
+    """write_snapshot for the host mirror of one rank (ramses_b200.hydro.AmrCommons as filled by the tree fabricators of
+    ramses_b200.tree, i.e. carrying the integer oct positions `_pos`): what a run does after `HydroGPU.download_state()`."""
+    L = a.nlevelmax
+    xg = np.zeros((a.ndim, a.ngridmax))
+    for l in range(1, L + 1):
+        if l not in a._pos:
+            continue
+        pos, ig0 = a._pos[l], a._igrid0[l]
+        ig = np.arange(ig0, ig0 + len(pos))
+        for k in range(a.ndim):
+            xg[k, ig - 1] = (pos[:, k] + 0.5) / 2.0 ** (l - 1)
+    empty = np.zeros(0, dtype=np.int32)
+    nb = len(a.boundary_type)
+    return write_snapshot(
+        outdir, iout, ndim=a.ndim, nvar=a.nvar, levelmin=levelmin or L, nlevelmax=L, ngridmax=a.ngridmax, ncoarse=a.ncoarse,
+        nxyz=(a.nx, a.ny, a.nz), coarse_min=(a.icoarse_min, a.jcoarse_min, a.kcoarse_min),
+        coarse_max=(a.icoarse_max, a.jcoarse_max, a.kcoarse_max), boxlen=a.boxlen, gamma=a.gamma, smallr=a.smallr, son=a.son,
+        father=a.father, nbor=a.nbor, xg=xg, active=[a.active.get(l, empty) for l in range(1, L + 1)],
+        boundary=[[(a.boundary.get(l) or [empty] * nb)[b] for l in range(1, L + 1)] for b in range(nb)], uold=a.uold, t=t,
+        dtold=[a.dtnew.get(l, 0.0) for l in range(1, L + 1)], dtnew=[a.dtnew.get(l, 0.0) for l in range(1, L + 1)], nstep=nstep,
+        nstep_coarse=nstep_coarse, mhd=a.mhd)

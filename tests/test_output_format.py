@@ -115,3 +115,41 @@ def test_implosion_and_orszag_tang_through_reference_checker(implosion_run, orsz
     _write_from_run(r, d2, 2)
     _check_with_reference(d2, 2, "implosion", "implosion_ref.json")
     assert "PASSED" in capsys.readouterr().out
+
+
+def test_snapshot_from_host_mirror_nested_tree(tmp_path):
+    """the product's host mirror (AmrCommons from ramses_b200.tree.build_nested_tree, three levels) -> snapshot -> reference
+    reader: every leaf cell comes back at its position with its value."""
+    from ramses_b200.output import snapshot_from_commons
+    from ramses_b200.tree import build_nested_tree, fill_state
+    a = build_nested_tree(3, 5, half_width=2)
+    a.gamma = 1.4
+
+    def fn(x, y, z):
+        u = np.zeros((5, len(x)))
+        u[0] = 1.0 + x + 2 * y + 4 * z
+        u[1], u[2], u[3] = 0.1 * u[0], -0.2 * u[0], 0.3 * u[0]
+        u[4] = 2.5 + 0.5 * u[0] * (0.01 + 0.04 + 0.09) + x * y
+        return u
+    for l in range(1, 6):
+        fill_state(a, l, fn)
+    snapshot_from_commons(a, str(tmp_path), 1, t=0.125, levelmin=3)
+    sys.path.insert(0, REF_VISU)
+    try:
+        import visu_ramses
+    finally:
+        sys.path.remove(REF_VISU)
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path))
+    try:
+        data = visu_ramses.load_snapshot(1)["data"]
+    finally:
+        os.chdir(cwd)
+    nleaf = sum(int((a.son[a.ncoarse + ind * a.ngridmax + a.active[l].astype(np.int64) - 1] == 0).sum())
+                for l in range(1, 6) for ind in range(8))
+    assert data["ncells"] == nleaf and data["time"] == 0.125
+    x, y, z = data["x"], data["y"], data["z"]
+    assert np.array_equal(data["density"], 1.0 + x + 2 * y + 4 * z)
+    assert np.allclose(data["velocity_y"], -0.2, rtol=0, atol=1e-16)
+    assert np.allclose(data["pressure"], 0.4 * (2.5 + x * y), rtol=1e-14, atol=0)
+    assert set(np.unique(data["level"])) == {3.0, 4.0, 5.0}
