@@ -10,6 +10,7 @@ turns them into an `output_NNNNN/` directory that the reference's own tools read
     hydro_file_descriptor.txt    io/dump_utils.f90:127-139
     header_NNNNN.txt             amr/output_amr.f90:497-575  output_header (particle families, all zero)
 
+`read_snapshot` is the restart side (amr/init_amr.f90:227-520, hydro/init_hydro.f90:57-250).
 Serial runs (ncpu=1) and the Hilbert ordering header only.  tests/test_output_format.py reads the files back with the
 reference's reader and checker (tests/visu/visu_ramses.py: load_snapshot + check_solution) and so closes the loop
 state -> reference file format -> reference reader -> reference golden sums.
@@ -237,3 +238,103 @@ def snapshot_from_commons(a, outdir, iout, t=0.0, levelmin=None, nstep=0, nstep_
         boundary=[[(a.boundary.get(l) or [empty] * nb)[b] for l in range(1, L + 1)] for b in range(nb)], uold=a.uold, t=t,
         dtold=[a.dtnew.get(l, 0.0) for l in range(1, L + 1)], dtnew=[a.dtnew.get(l, 0.0) for l in range(1, L + 1)], nstep=nstep,
         nstep_coarse=nstep_coarse, mhd=a.mhd)
+
+
+class _Reader:
+    def __init__(self, path):
+        self.b = open(path, "rb").read()
+        self.o = 0
+
+    def rec(self):
+        n = struct.unpack_from("i", self.b, self.o)[0]
+        payload = self.b[self.o + 4:self.o + 4 + n]
+        assert struct.unpack_from("i", self.b, self.o + 4 + n)[0] == n, "corrupt Fortran record"
+        self.o += n + 8
+        return payload
+
+    def ints(self):
+        return np.frombuffer(self.rec(), dtype=np.int32)
+
+    def dbls(self):
+        return np.frombuffer(self.rec(), dtype=np.float64)
+
+
+def read_snapshot(outdir, iout, smallr=1e-10):
+    """The restart side (amr/init_amr.f90:227-520 for the tree, hydro/init_hydro.f90:57-250 for the state) of a serial
+    hydro snapshot: returns a dict with the header scalars, the tree arrays in the 0-based-view convention of write_snapshot, the
+    per-level igrid lists and `uold[nvar][ncell]` rebuilt from the primitive records exactly as init_hydro does
+    (momentum = v*max(rho,smallr), E = P/(gamma-1) + sum 0.5*mom^2/max(rho,smallr))."""
+    nchar = "%05d" % iout
+    d = os.path.join(outdir, "output_" + nchar)
+    r = _Reader(os.path.join(d, "amr_" + nchar + ".out00001"))
+    ncpu = int(r.ints()[0]); ndim = int(r.ints()[0]); nx, ny, nz = (int(v) for v in r.ints())
+    nlevelmax = int(r.ints()[0]); ngridmax = int(r.ints()[0]); nboundary = int(r.ints()[0]); ngrid_current = int(r.ints()[0])
+    boxlen = float(r.dbls()[0])
+    noutput, iout2, ifout = (int(v) for v in r.ints())
+    tout = r.dbls().copy(); r.dbls()
+    t = float(r.dbls()[0])
+    dtold = r.dbls().copy(); dtnew = r.dbls().copy()
+    nstep, nstep_coarse = (int(v) for v in r.ints())
+    for _ in range(4):
+        r.dbls()
+    assert ncpu == 1
+    headl = r.ints().copy(); taill = r.ints().copy(); numbl = r.ints().copy(); r.ints()
+    numbb = np.zeros((nlevelmax, max(nboundary, 1)), dtype=np.int32)
+    if nboundary > 0:
+        r.ints(); r.ints(); numbb = r.ints().reshape(nlevelmax, nboundary).copy()
+    r.ints()                                               # headf, tailf, numbf, used_mem, used_mem_tot
+    ordering = r.rec().decode().strip()
+    r.rec()                                                # bound_key
+    T, twondim = 1 << ndim, 2 * ndim
+    ncoarse = nx * ny * nz
+    ncell = ncoarse + T * ngridmax
+    son = np.zeros(ncell, dtype=np.int32); flag1 = np.zeros(ncell, dtype=np.int32); cpu_map = np.zeros(ncell, dtype=np.int32)
+    father = np.zeros(ngridmax, dtype=np.int32); nbor = np.zeros((twondim, ngridmax), dtype=np.int32)
+    xg = np.zeros((ndim, ngridmax))
+    son[:ncoarse] = r.ints(); flag1[:ncoarse] = r.ints(); cpu_map[:ncoarse] = r.ints()
+    active = [np.zeros(0, dtype=np.int32) for _ in range(nlevelmax)]
+    boundary = [[np.zeros(0, dtype=np.int32) for _ in range(nlevelmax)] for _ in range(nboundary)]
+    for l in range(nlevelmax):
+        for dom in range(1 + nboundary):
+            ncache = int(numbl[l]) if dom == 0 else int(numbb[l, dom - 1])
+            if ncache == 0:
+                continue
+            g = r.ints().copy(); r.ints(); r.ints()
+            if dom == 0:
+                active[l] = g
+            else:
+                boundary[dom - 1][l] = g
+            gi = g.astype(np.int64) - 1
+            for k in range(ndim):
+                xg[k, gi] = r.dbls()
+            father[gi] = r.ints()
+            for j in range(twondim):
+                nbor[j, gi] = r.ints()
+            for arr in (son, cpu_map, flag1):
+                for ind in range(T):
+                    arr[ncoarse + ind * ngridmax + gi] = r.ints()
+    h = _Reader(os.path.join(d, "hydro_" + nchar + ".out00001"))
+    h.ints(); nvar = int(h.ints()[0]); h.ints(); h.ints(); h.ints(); gamma = float(h.dbls()[0])
+    uold = np.zeros((nvar, ncell))
+    for l in range(nlevelmax):
+        for dom in range(1 + nboundary):
+            h.ints(); ncache = int(h.ints()[0])
+            if ncache == 0:
+                continue
+            g = (active[l] if dom == 0 else boundary[dom - 1][l]).astype(np.int64)
+            for ind in range(T):
+                c = ncoarse + ind * ngridmax + g - 1
+                uold[0, c] = h.dbls()
+                dmax = np.maximum(uold[0, c], smallr)
+                for k in range(ndim):
+                    uold[1 + k, c] = h.dbls() * dmax
+                e = h.dbls() / (gamma - 1.0)
+                for k in range(ndim):
+                    e = e + 0.5 * uold[1 + k, c] ** 2 / dmax
+                uold[ndim + 1, c] = np.where(uold[0, c] > 0.0, e, 0.0)
+                for k in range(ndim + 2, nvar):
+                    uold[k, c] = h.dbls() * dmax
+    return dict(ndim=ndim, nxyz=(nx, ny, nz), nlevelmax=nlevelmax, ngridmax=ngridmax, nboundary=nboundary, ncoarse=ncoarse,
+                ngrid_current=ngrid_current, boxlen=boxlen, t=t, dtold=dtold, dtnew=dtnew, nstep=nstep, nstep_coarse=nstep_coarse,
+                tout=tout, ordering=ordering, gamma=gamma, nvar=nvar, son=son, father=father, nbor=nbor, xg=xg, flag1=flag1,
+                cpu_map=cpu_map, active=active, boundary=boundary, uold=uold)

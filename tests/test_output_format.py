@@ -153,3 +153,46 @@ def test_snapshot_from_host_mirror_nested_tree(tmp_path):
     assert np.allclose(data["velocity_y"], -0.2, rtol=0, atol=1e-16)
     assert np.allclose(data["pressure"], 0.4 * (2.5 + x * y), rtol=1e-14, atol=0)
     assert set(np.unique(data["level"])) == {3.0, 4.0, 5.0}
+
+
+def test_snapshot_restart_round_trip(orc, tmp_path):
+    """write_snapshot -> read_snapshot (the restart side, amr/init_amr.f90 + hydro/init_hydro.f90:57-250): the tree arrays and the
+    lists come back identically, the conserved state to round-off (the file holds primitive variables, like the reference's own
+    restart), and a second write of the restored state reproduces the amr file byte for byte."""
+    from oracle.amr import AmrRun
+    from ramses_b200.output import read_snapshot, write_snapshot
+    from test_oracle_golden import SOD
+    r = AmrRun(1, 3, 8, (1, 1, 0, 0, 0, 0), 1.0, nsubcycle=[1, 1, 1, 2], nexpand=1, ngridmax=500, riemann="hllc", slope_type=2,
+               gamma=1.4, courant_factor=0.8, err_grad_d=0.05, err_grad_u=0.05, err_grad_p=0.05, interpol_type=2, interpol_var=0,
+               regions=SOD, tout=[0.1])
+    r.run()
+    d1 = tmp_path / "a"
+    d1.mkdir()
+    _write_from_run(r, d1, 3)
+    s = read_snapshot(str(d1), 3, smallr=r.p.smallr)
+    assert s["t"] == r.t and s["nstep"] == r.nstep and s["ndim"] == 1 and s["nboundary"] == 2
+    used = np.concatenate([np.asarray(r.active[l], dtype=np.int64) for l in range(1, 9)] +
+                          [np.asarray(r.bound[b][l], dtype=np.int64) for b in range(2) for l in range(1, 9)])
+    assert np.array_equal(s["son"][:r.ncoarse], r.son[1:r.ncoarse + 1])
+    for ind in range(2):
+        c = r.ncoarse + ind * r.ngridmax + used
+        assert np.array_equal(s["son"][c - 1], r.son[c])
+    assert np.array_equal(s["father"][used - 1], r.father[used]) and np.array_equal(s["nbor"][:, used - 1], r.nbor[:, used])
+    assert np.array_equal(s["xg"][:, used - 1], r.xg[:, used])
+    for l in range(1, 9):
+        assert np.array_equal(s["active"][l - 1], np.asarray(r.active[l], dtype=np.int32))
+    U = r.uold.reshape(3, r.ncell)
+    act = np.concatenate([np.asarray(r.active[l], dtype=np.int64) for l in range(1, 9)])
+    for ind in range(2):
+        c = r.ncoarse + ind * r.ngridmax + act - 1
+        assert np.array_equal(s["uold"][0, c], U[0, c])
+        assert np.allclose(s["uold"][1:, c], U[1:, c], rtol=4e-16, atol=1e-300)
+    d2 = tmp_path / "b"
+    d2.mkdir()
+    write_snapshot(str(d2), 3, ndim=1, nvar=3, levelmin=3, nlevelmax=8, ngridmax=s["ngridmax"], ncoarse=s["ncoarse"], nxyz=s["nxyz"],
+                   coarse_min=(1, 0, 0), coarse_max=(1, 0, 0), boxlen=s["boxlen"], gamma=s["gamma"], smallr=r.p.smallr, son=s["son"],
+                   father=s["father"], nbor=s["nbor"], xg=s["xg"], active=s["active"], boundary=s["boundary"], uold=s["uold"],
+                   t=s["t"], dtold=s["dtold"], dtnew=s["dtnew"], nstep=s["nstep"], nstep_coarse=s["nstep_coarse"], tout=s["tout"],
+                   flag1=s["flag1"], cpu_map=s["cpu_map"])
+    f = "output_00003/amr_00003.out00001"
+    assert open(d1 / f, "rb").read() == open(d2 / f, "rb").read()
