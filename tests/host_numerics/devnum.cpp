@@ -1,0 +1,137 @@
+// Device numerics of ramses_b200/csrc compiled for the host (RGPU_HOST_NUMERICS): C entry points used by
+// tests/test_device_numerics_host.py to compare the formulas the kernels execute with the oracle, bit for bit, on the CPU.
+// TEST HARNESS ONLY.  Built with  g++ -O2 -ffp-contract=off  (the device build uses -fmad=false for the same reason).
+#define RGPU_HOST_NUMERICS 1
+#include "mhd_device.cuh"   // pulls hydro_device.cuh and real64.cuh
+
+using namespace rgpu;
+
+static Phys make_phys(double gamma, double smallr, double smallc, double slope_theta, double courant_factor, int slope_type,
+                      int niter) {   // mirrors rgpu_init (ramses_b200/csrc/rgpu_api.cu)
+  Phys P;
+  P.gamma = gamma; P.smallr = smallr; P.smallc = smallc; P.slope_theta = slope_theta; P.courant_factor = courant_factor;
+  P.smalle = smallc * smallc / gamma / (gamma - 1.0);
+  P.smallp = smallc * smallc / gamma;
+  P.smallpp = smallr * P.smallp;
+  P.entho = 1.0 / (gamma - 1.0);
+  P.gamma6 = (gamma + 1.0) / (2.0 * gamma);
+  P.smallc2 = smallc * smallc;
+  P.inv_gamma = 1.0 / gamma;
+  P.cfl_g = 0.0001;
+  P.cfl_rg = 1.0 / P.cfl_g;
+  P.cfl_k = std::sqrt(1.0 + 2.0 * courant_factor * P.cfl_g) - 1.0;
+  P.slope_type = slope_type; P.niter_riemann = niter;
+  return P;
+}
+
+template <int NDIM>
+static void riemann_nd(int solver, const double* ql, const double* qr, double* fg, const Phys& P) {
+  switch (solver) {
+    case RIEMANN_LLF: riemann<NDIM, RIEMANN_LLF>(ql, qr, fg, P); break;
+    case RIEMANN_EXACT: riemann<NDIM, RIEMANN_EXACT>(ql, qr, fg, P); break;
+    case RIEMANN_ACOUSTIC: riemann<NDIM, RIEMANN_ACOUSTIC>(ql, qr, fg, P); break;
+    case RIEMANN_HLLC: riemann<NDIM, RIEMANN_HLLC>(ql, qr, fg, P); break;
+    default: riemann<NDIM, RIEMANN_HLL>(ql, qr, fg, P); break;
+  }
+}
+
+extern "C" {
+
+// n Riemann problems: ql, qr [n][ndim+2] in solver order (rho, u_n, P, u_t1, u_t2), fg [n][ndim+2]
+void devnum_riemann(int ndim, int solver, int n, const double* ql, const double* qr, double* fg, double gamma, double smallr,
+                    double smallc, int niter) {
+  const Phys P = make_phys(gamma, smallr, smallc, 1.5, 0.8, 1, niter);
+  const int nv = ndim + 2;
+  for (int i = 0; i < n; i++) {
+    if (ndim == 1) riemann_nd<1>(solver, ql + i * nv, qr + i * nv, fg + i * nv, P);
+    else if (ndim == 2) riemann_nd<2>(solver, ql + i * nv, qr + i * nv, fg + i * nv, P);
+    else riemann_nd<3>(solver, ql + i * nv, qr + i * nv, fg + i * nv, P);
+  }
+}
+
+// n cells: u [n][ndim+2] conservative -> q [n][ndim+3] (rho, v, P, 1/rho as the kernels keep it is NOT part of q here)
+void devnum_ctoprim(int ndim, int n, const double* u, double* q, double gamma, double smallr, double smallc) {
+  const Phys P = make_phys(gamma, smallr, smallc, 1.5, 0.8, 1, 10);
+  const int nv = ndim + 2;
+  for (int i = 0; i < n; i++) {
+    if (ndim == 1) ctoprim<1>(u + i * nv, q + i * nv, P);
+    else if (ndim == 2) ctoprim<2>(u + i * nv, q + i * nv, P);
+    else ctoprim<3>(u + i * nv, q + i * nv, P);
+  }
+}
+
+// n cells: dt = cmpdt_cell(u, dx)
+void devnum_cmpdt(int ndim, int n, const double* u, double dx, double* dt, double gamma, double smallr, double smallc, double cfl) {
+  const Phys P = make_phys(gamma, smallr, smallc, 1.5, cfl, 1, 10);
+  const int nv = ndim + 2;
+  for (int i = 0; i < n; i++) {
+    double ei;
+    if (ndim == 1) dt[i] = cmpdt_cell<1>(u + i * nv, dx, P, ei);
+    else if (ndim == 2) dt[i] = cmpdt_cell<2>(u + i * nv, dx, P, ei);
+    else dt[i] = cmpdt_cell<3>(u + i * nv, dx, P, ei);
+  }
+}
+
+// n limited slopes of (ql, qc, qr) for slope_type 1, 2, 7, 8 (the one-dimensional limiters)
+void devnum_slope(int slope_type, int n, const double* ql, const double* qc, const double* qr, double* dq, double slope_theta) {
+  const Phys P = make_phys(1.4, 1e-10, 1e-10, slope_theta, 0.8, slope_type, 10);
+  for (int i = 0; i < n; i++) dq[i] = slope_lcr<3, -1>(ql[i], qc[i], qr[i], P);
+}
+
+static MPhys make_mphys(double gamma, double smallr, double smallc) {
+  MPhys M;
+  M.gamma = gamma; M.smallr = smallr; M.smallc = smallc; M.slope_theta = 1.5; M.courant_factor = 0.8;
+  M.smallp = smallr * (smallc * smallc) / gamma;
+  M.slope_type = 1; M.slope_mag_type = 1;
+  return M;
+}
+
+// n MHD Riemann problems in solver order (rho, P, v_n, B_n, v_t1, B_t1, v_t2, B_t2): fg [n][9]
+void devnum_mhd_riemann(int solver, int n, const double* ql, const double* qr, double* fg, double gamma, double smallr, double smallc) {
+  const MPhys M = make_mphys(gamma, smallr, smallc);
+  for (int i = 0; i < n; i++) {
+    real l[8], r[8], f[9];
+    for (int k = 0; k < 8; k++) { l[k] = ql[i * 8 + k]; r[k] = qr[i * 8 + k]; }
+    switch (solver) {
+      case MHD_LLF: riemann1d<MHD_LLF>(M, l, r, f); break;
+      case MHD_ROE: riemann1d<MHD_ROE>(M, l, r, f); break;
+      case MHD_HLL: riemann1d<MHD_HLL>(M, l, r, f); break;
+      case MHD_HLLD: riemann1d<MHD_HLLD>(M, l, r, f); break;
+      case MHD_UPWIND: riemann1d<MHD_UPWIND>(M, l, r, f); break;
+      default: riemann1d<MHD_HYDRO>(M, l, r, f); break;
+    }
+    for (int k = 0; k < 9; k++) fg[i * 9 + k] = (double)f[k];
+  }
+}
+
+// n corner EMFs from the four states (qLL, qRL, qLR, qRR) [n][8] in cmp_mag_flx's solver order
+void devnum_mhd_emf(int solver2d, int n, const double* qLL, const double* qRL, const double* qLR, const double* qRR, double* emf,
+                    double gamma, double smallr, double smallc) {
+  const MPhys M = make_mphys(gamma, smallr, smallc);
+  for (int i = 0; i < n; i++) {
+    real a[8], b[8], c[8], d[8];
+    for (int k = 0; k < 8; k++) { a[k] = qLL[i * 8 + k]; b[k] = qRL[i * 8 + k]; c[k] = qLR[i * 8 + k]; d[k] = qRR[i * 8 + k]; }
+    real e;
+    switch (solver2d) {
+      case MHD2D_LLF: e = emf_edge<MHD2D_LLF>(M, a, b, c, d); break;
+      case MHD2D_ROE: e = emf_edge<MHD2D_ROE>(M, a, b, c, d); break;
+      case MHD2D_UPWIND: e = emf_edge<MHD2D_UPWIND>(M, a, b, c, d); break;
+      case MHD2D_HLL: e = emf_edge<MHD2D_HLL>(M, a, b, c, d); break;
+      case MHD2D_HLLA: e = emf_edge<MHD2D_HLLA>(M, a, b, c, d); break;
+      default: e = emf_edge<MHD2D_HLLD>(M, a, b, c, d); break;
+    }
+    emf[i] = (double)e;
+  }
+}
+
+void devnum_mhd_cmpdt(int n, const double* u, double dx, double* dt, double gamma, double smallr, double smallc, double cfl) {
+  MPhys M = make_mphys(gamma, smallr, smallc);
+  M.courant_factor = cfl;
+  for (int i = 0; i < n; i++) {
+    real uu[11];
+    for (int k = 0; k < 11; k++) uu[k] = u[i * 11 + k];
+    dt[i] = (double)mhd_cmpdt_cell(M, uu, dx);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+"""The DEVICE numerics (ramses_b200/csrc/hydro_device.cuh, real64.cuh, mhd_device.cuh -- the formulas the kernels execute)
+compiled for the host by tests/host_numerics (g++, a stub <cuda_runtime.h>, RGPU_HOST_NUMERICS turning the three reciprocal /
+sqrt / division primitives into the IEEE operations they are bit-identical to) and compared with the oracle BIT FOR BIT on the
+CPU.  This is a test harness for machines without a GPU (a slip in a device formula shows up here before any GPU time is
+spent); the parity tests proper remain the `-m gpu` tests through the C-ABI.  Nothing here is a product path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_numerics")
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ramses_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    lib = os.path.join(HERE, "libdevnum_host.so")
+    srcs = [os.path.join(HERE, "devnum.cpp")] + [os.path.join(CSRC, f) for f in ("hydro_device.cuh", "real64.cuh", "mhd_device.cuh")]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared",
+                               "-I" + os.path.join(HERE, "stub"), "-I" + CSRC, "-o", lib, os.path.join(HERE, "devnum.cpp")])
+    L = C.CDLL(lib)
+    dp = C.POINTER(C.c_double)
+    L.devnum_riemann.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int]
+    L.devnum_cmpdt.argtypes = [C.c_int, C.c_int, dp, C.c_double, dp, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.devnum_mhd_riemann.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_double]
+    L.devnum_mhd_emf.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double]
+    L.devnum_mhd_cmpdt.argtypes = [C.c_int, dp, C.c_double, dp, C.c_double, C.c_double, C.c_double, C.c_double]
+    return L
+
+
+def _hydro_states(rng, n, ndim):
+    """left/right primitive states in solver order (rho, u_n, P, u_t...): smooth pairs, strong shocks, near-vacuum, supersonic"""
+    nv = ndim + 2
+    ql, qr = np.zeros((n, nv)), np.zeros((n, nv))
+    for q in (ql, qr):
+        q[:, 0] = 10.0 ** rng.uniform(-3, 2, n)
+        q[:, 2] = 10.0 ** rng.uniform(-5, 3, n)
+        q[:, 1] = rng.standard_normal(n) * 10.0 ** rng.uniform(-2, 1.5, n)
+        for k in range(3, nv):
+            q[:, k] = rng.standard_normal(n)
+    k = n // 4
+    qr[:k] = ql[:k] * (1 + 1e-3 * rng.standard_normal((k, nv)))       # nearly equal states
+    qr[k:2 * k, 0] = ql[k:2 * k, 0]
+    ql[2 * k:2 * k + 50, 0] = 1e-12                                     # below smallr
+    ql[2 * k + 50:2 * k + 100, 2] = 1e-30                               # below the pressure floor
+    return np.ascontiguousarray(ql), np.ascontiguousarray(qr)
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+@pytest.mark.parametrize("solver", ["llf", "exact", "acoustic", "hllc", "hll"])
+def test_hydro_riemann_device_formulas_equal_oracle(orc, dev, ndim, solver):
+    """riemann_{llf,approx,acoustic,hllc,hll} of hydro_device.cuh == the oracle's restatement of hydro/godunov_utils.f90,
+    bit for bit on 20 000 random face states -- including `exact`, whose only GPU-side deviation is CUDA's pow()."""
+    n, nv = 20000, ndim + 2
+    ql, qr = _hydro_states(np.random.default_rng(ndim * 10 + len(solver)), n, ndim)
+    fg = np.zeros((n, nv))
+    sid = {"llf": 0, "exact": 1, "acoustic": 2, "hllc": 3, "hll": 4}[solver]
+    dev.devnum_riemann(ndim, sid, n, orc.dptr(ql), orc.dptr(qr), orc.dptr(fg), 1.4, 1e-10, 1e-10, 10)
+    p = orc.make_params(ndim=ndim, riemann=solver, nvector=n, niter_riemann=10)
+    L = orc.lib()
+    f = {"llf": L.orc_riemann_llf, "exact": L.orc_riemann_approx, "acoustic": L.orc_riemann_acoustic, "hllc": L.orc_riemann_hllc,
+         "hll": L.orc_riemann_hll}[solver]
+    f.argtypes = [C.POINTER(orc.Params), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
+    qlf, qrf = np.asfortranarray(ql), np.asfortranarray(qr)              # (nvector, nvar) column-major
+    fgf = np.zeros((n, nv + 1), order="F")
+    f(C.byref(p), qlf.ctypes.data_as(C.POINTER(C.c_double)), qrf.ctypes.data_as(C.POINTER(C.c_double)),
+      fgf.ctypes.data_as(C.POINTER(C.c_double)), n)
+    assert np.isfinite(fg).all()
+    assert np.array_equal(fg, fgf[:, :nv])
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_hydro_cmpdt_device_formula_equals_oracle(orc, dev, ndim):
+    n, nv = 5000, ndim + 2
+    rng = np.random.default_rng(5 + ndim)
+    u = np.zeros((n, nv))
+    u[:, 0] = 10.0 ** rng.uniform(-3, 2, n)
+    vel = rng.standard_normal((n, ndim)) * 3
+    u[:, 1:1 + ndim] = u[:, :1] * vel
+    u[:, nv - 1] = 10.0 ** rng.uniform(-4, 2, n) + 0.5 * u[:, 0] * (vel ** 2).sum(axis=1)
+    dt = np.zeros(n)
+    dx = 1.0 / 128
+    dev.devnum_cmpdt(ndim, n, orc.dptr(np.ascontiguousarray(u)), dx, orc.dptr(dt), 1.4, 1e-10, 1e-10, 0.8)
+    p = orc.make_params(ndim=ndim, nvector=1, courant_factor=0.8)
+    L = orc.lib()
+    L.orc_cmpdt.argtypes = [C.POINTER(orc.Params), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_int]
+    ref = np.zeros(n)
+    for i in range(n):
+        uu = u[i].copy()
+        d = C.c_double(0.0)
+        L.orc_cmpdt(C.byref(p), orc.dptr(uu), None, dx, C.byref(d), 1)
+        ref[i] = d.value
+    assert np.array_equal(dt, ref)
+
+
+def _mhd_states(rng, n):
+    """(rho, P, v_n, B_n, v_t1, B_t1, v_t2, B_t2) left/right with a common B_n"""
+    ql, qr = np.zeros((n, 8)), np.zeros((n, 8))
+    for q in (ql, qr):
+        q[:, 0] = 10.0 ** rng.uniform(-2, 1, n)
+        q[:, 1] = 10.0 ** rng.uniform(-3, 2, n)
+        q[:, 2], q[:, 4], q[:, 6] = (rng.standard_normal(n) * 2 for _ in range(3))
+        q[:, 5], q[:, 7] = rng.standard_normal(n), rng.standard_normal(n)
+    bn = rng.standard_normal(n)
+    bn[: n // 10] = 0.0
+    ql[:, 3], qr[:, 3] = bn, bn
+    k = n // 5
+    qr[:k] = ql[:k] * (1 + 1e-3 * rng.standard_normal((k, 8)))
+    qr[:k, 3] = ql[:k, 3]
+    return np.ascontiguousarray(ql), np.ascontiguousarray(qr)
+
+
+@pytest.mark.parametrize("solver", ["llf", "roe", "hll", "hlld", "upwind", "hydro"])
+def test_mhd_riemann_device_formulas_equal_oracle(orc, dev, solver):
+    """lax_friedrich / athena_roe (restructured on the device: left eigenvectors column by column, shared reciprocals) / hll /
+    hlld / upwind / hydro_acoustic of mhd_device.cuh == the oracle's restatement of mhd/godunov_utils.f90, bit for bit"""
+    n = 20000
+    ql, qr = _mhd_states(np.random.default_rng(40 + len(solver)), n)
+    fg = np.zeros((n, 9))
+    dev.devnum_mhd_riemann(orc.MHD_RIEMANN[solver], n, orc.dptr(ql), orc.dptr(qr), orc.dptr(fg), 5 / 3., 1e-10, 1e-10)
+    pm = orc.make_mhd_params(riemann=solver, gamma=5 / 3.)
+    L = orc.lib()
+    L.orc_mhd_riemann.argtypes = [C.POINTER(orc.MhdParams)] + [C.POINTER(C.c_double)] * 3
+    ref = np.zeros((n, 9))
+    for i in range(n):
+        L.orc_mhd_riemann(C.byref(pm), orc.dptr(ql[i]), orc.dptr(qr[i]), orc.dptr(ref[i]))
+    nused = 8 if solver != "hlld" else 8
+    good = np.isfinite(ref[:, :nused]).all(axis=1)
+    assert good.mean() > 0.99
+    assert np.array_equal(fg[good, :nused], ref[good, :nused])
+
+
+@pytest.mark.parametrize("solver2d", ["llf", "roe", "upwind", "hll", "hlla", "hlld"])
+def test_mhd_corner_emf_device_formulas_equal_oracle(orc, dev, solver2d):
+    """emf_edge<R2D> (cmp_mag_flx, mhd/umuscl.f90:1453) for the E_z call: the four corner states in the reference's dummy-argument
+    order; the oracle is called with the cell-order corner states of the same edge"""
+    n = 10000
+    rng = np.random.default_rng(77 + len(solver2d))
+    RT, RB, LT, LB = (np.zeros((n, 8)) for _ in range(4))            # (rho, u, v, w, P, A, B, C)
+    for q in (RT, RB, LT, LB):
+        q[:, 0] = 10.0 ** rng.uniform(-1, 1, n)
+        q[:, 4] = 10.0 ** rng.uniform(-2, 1, n)
+        q[:, 1:4] = rng.standard_normal((n, 3))
+        q[:, 5:8] = rng.standard_normal((n, 3))
+    # face fields are shared: A (x-face) by the left/right pair, B (y-face) by the top/bottom pair (umuscl.f90:1506-1541)
+    lp1, lp2, lor, bp1, bp2, bor = 2, 3, 4, 6, 7, 8
+    LL, RL, LR, RR = (np.zeros((n, 8)) for _ in range(4))
+    for dst, src in ((LL, RT), (RL, LT), (LR, RB), (RR, LB)):
+        dst[:, 0], dst[:, 1] = src[:, 0], src[:, 4]
+        dst[:, 2], dst[:, 3], dst[:, 4], dst[:, 7] = src[:, lp1 - 1], src[:, lp2 - 1], src[:, lor - 1], src[:, bor - 1]
+    LL[:, 5] = RL[:, 5] = 0.5 * (RT[:, bp1 - 1] + LT[:, bp1 - 1])
+    LR[:, 5] = RR[:, 5] = 0.5 * (RB[:, bp1 - 1] + LB[:, bp1 - 1])
+    LL[:, 6] = LR[:, 6] = 0.5 * (RT[:, bp2 - 1] + RB[:, bp2 - 1])
+    RL[:, 6] = RR[:, 6] = 0.5 * (LT[:, bp2 - 1] + LB[:, bp2 - 1])
+    emf = np.zeros(n)
+    dev.devnum_mhd_emf(orc.MHD_RIEMANN2D[solver2d], n, *(orc.dptr(np.ascontiguousarray(a)) for a in (LL, RL, LR, RR)), orc.dptr(emf),
+                       5 / 3., 1e-10, 1e-10)
+    pm = orc.make_mhd_params(riemann2d=solver2d, gamma=5 / 3.)
+    L = orc.lib()
+    L.orc_mhd_emf.restype = C.c_double
+    L.orc_mhd_emf.argtypes = [C.POINTER(orc.MhdParams)] + [C.POINTER(C.c_double)] * 4 + [C.c_int]
+    ref = np.array([L.orc_mhd_emf(C.byref(pm), orc.dptr(RT[i]), orc.dptr(RB[i]), orc.dptr(LT[i]), orc.dptr(LB[i]), 2) for i in range(n)])
+    good = np.isfinite(ref)
+    assert good.mean() > 0.99
+    assert np.array_equal(emf[good], ref[good])
+
+
+def test_mhd_cmpdt_device_formula_equals_oracle(orc, dev):
+    n = 5000
+    rng = np.random.default_rng(9)
+    u = np.zeros((n, 11))
+    u[:, 0] = 10.0 ** rng.uniform(-2, 1, n)
+    vel = rng.standard_normal((n, 3)) * 2
+    u[:, 1:4] = u[:, :1] * vel
+    u[:, 5:8] = rng.standard_normal((n, 3))
+    u[:, 8:11] = u[:, 5:8] + 0.1 * rng.standard_normal((n, 3))
+    bc = 0.5 * (u[:, 5:8] + u[:, 8:11])
+    u[:, 4] = 10.0 ** rng.uniform(-3, 1, n) / (5 / 3. - 1) + 0.5 * u[:, 0] * (vel ** 2).sum(axis=1) + 0.5 * (bc ** 2).sum(axis=1)
+    dt = np.zeros(n)
+    dx = 1.0 / 64
+    dev.devnum_mhd_cmpdt(n, orc.dptr(np.ascontiguousarray(u)), dx, orc.dptr(dt), 5 / 3., 1e-10, 1e-10, 0.8)
+    pm = orc.make_mhd_params(gamma=5 / 3., courant_factor=0.8)
+    L = orc.lib()
+    L.orc_mhd_cmpdt_cell.restype = C.c_double
+    L.orc_mhd_cmpdt_cell.argtypes = [C.POINTER(orc.MhdParams), C.POINTER(C.c_double), C.c_double]
+    ref = np.array([L.orc_mhd_cmpdt_cell(C.byref(pm), orc.dptr(u[i].copy()), dx) for i in range(n)])
+    assert np.array_equal(dt, ref)
