@@ -78,6 +78,56 @@ void devnum_slope(int slope_type, int n, const double* ql, const double* qc, con
   for (int i = 0; i < n; i++) dq[i] = slope_lcr<3, -1>(ql[i], qc[i], qr[i], P);
 }
 
+// unsplit (hydro/umuscl.f90:22) on ONE 6x6x6 patch assembled from the per-cell device functions in the order the sweep kernel
+// uses them: ctoprim -> slope_lcr per direction -> trace_sources -> trace_faces -> riemann per face -> flux*dt/dx.
+// uin and flux use the oracle's array layout with nvector=1: uin[ivar*216 + (i+1) + 6*((j+1) + 6*(k+1))], i,j,k = -1..4;
+// flux[(ivar + 5*idim)*27 + (i-1) + 3*((j-1) + 3*(k-1))], faces 1..3.  slope_type 3 is not covered (27-point limiter).
+void devnum_unsplit3d(int solver, int slope_type, double slope_theta, const double* uin, double dx, double dt, double* flux,
+                      double gamma, double smallr, double smallc, int niter) {
+  const Phys P = make_phys(gamma, smallr, smallc, slope_theta, 0.8, slope_type, niter);
+  static double q[6][6][6][5], rinv[6][6][6], qm[6][6][6][3][5], qp[6][6][6][3][5];
+  for (int k = 0; k < 6; k++)
+    for (int j = 0; j < 6; j++)
+      for (int i = 0; i < 6; i++) {
+        double u[5];
+        for (int v = 0; v < 5; v++) u[v] = uin[v * 216 + i + 6 * (j + 6 * k)];
+        ctoprim<3>(u, q[k][j][i], P);
+        rinv[k][j][i] = rcp_rn(q[k][j][i][0]);
+      }
+  const double dtdx = dt / dx;
+  for (int k = 1; k <= 4; k++)
+    for (int j = 1; j <= 4; j++)
+      for (int i = 1; i <= 4; i++) {
+        double dq[3][5], s0[5];
+        for (int v = 0; v < 5; v++) {
+          dq[0][v] = slope_lcr<3, -1>(q[k][j][i - 1][v], q[k][j][i][v], q[k][j][i + 1][v], P);
+          dq[1][v] = slope_lcr<3, -1>(q[k][j - 1][i][v], q[k][j][i][v], q[k][j + 1][i][v], P);
+          dq[2][v] = slope_lcr<3, -1>(q[k - 1][j][i][v], q[k][j][i][v], q[k + 1][j][i][v], P);
+        }
+        trace_sources<3>(q[k][j][i], dq, rinv[k][j][i], s0, P);
+        for (int d = 0; d < 3; d++) trace_faces<3>(q[k][j][i], dq[d], s0, dtdx, qm[k][j][i][d], qp[k][j][i][d], P);
+      }
+  static const int perm[3][5] = {{0, 1, 4, 2, 3}, {0, 2, 4, 1, 3}, {0, 3, 4, 1, 2}};   // (rho, u_n, P, u_t1, u_t2): cmpflxm :749-789
+  for (int d = 0; d < 3; d++) {
+    const int i0 = d == 0, j0 = d == 1, k0 = d == 2;
+    for (int k3 = 1; k3 <= 2 + k0; k3++)
+      for (int j3 = 1; j3 <= 2 + j0; j3++)
+        for (int i3 = 1; i3 <= 2 + i0; i3++) {
+          const double* m_ = qm[k3 + 1 - k0][j3 + 1 - j0][i3 + 1 - i0][d];   // Fortran cell (i3-1,...) -> C index +1
+          const double* p_ = qp[k3 + 1][j3 + 1][i3 + 1][d];
+          double ql[5], qr[5], fg[5];
+          for (int v = 0; v < 5; v++) { ql[v] = m_[perm[d][v]]; qr[v] = p_[perm[d][v]]; }
+          if (solver == RIEMANN_LLF) riemann<3, RIEMANN_LLF>(ql, qr, fg, P);
+          else if (solver == RIEMANN_EXACT) riemann<3, RIEMANN_EXACT>(ql, qr, fg, P);
+          else if (solver == RIEMANN_ACOUSTIC) riemann<3, RIEMANN_ACOUSTIC>(ql, qr, fg, P);
+          else if (solver == RIEMANN_HLLC) riemann<3, RIEMANN_HLLC>(ql, qr, fg, P);
+          else riemann<3, RIEMANN_HLL>(ql, qr, fg, P);
+          for (int v = 0; v < 5; v++)
+            flux[(perm[d][v] + 5 * d) * 27 + (i3 - 1) + 3 * ((j3 - 1) + 3 * (k3 - 1))] = fg[v] * dt / dx;
+        }
+  }
+}
+
 static MPhys make_mphys(double gamma, double smallr, double smallc) {
   MPhys M;
   M.gamma = gamma; M.smallr = smallr; M.smallc = smallc; M.slope_theta = 1.5; M.courant_factor = 0.8;

@@ -28,6 +28,8 @@ def dev():
     L.devnum_mhd_riemann.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_double]
     L.devnum_mhd_emf.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double]
     L.devnum_mhd_cmpdt.argtypes = [C.c_int, dp, C.c_double, dp, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.devnum_unsplit3d.argtypes = [C.c_int, C.c_int, C.c_double, dp, C.c_double, C.c_double, dp, C.c_double, C.c_double, C.c_double,
+                                   C.c_int]
     return L
 
 
@@ -188,3 +190,45 @@ def test_mhd_cmpdt_device_formula_equals_oracle(orc, dev):
     L.orc_mhd_cmpdt_cell.argtypes = [C.POINTER(orc.MhdParams), C.POINTER(C.c_double), C.c_double]
     ref = np.array([L.orc_mhd_cmpdt_cell(C.byref(pm), orc.dptr(u[i].copy()), dx) for i in range(n)])
     assert np.array_equal(dt, ref)
+
+
+@pytest.mark.parametrize("solver", ["hllc", "llf", "exact", "acoustic", "hll"])
+@pytest.mark.parametrize("slope_type", [0, 1, 2, 7, 8])
+def test_unsplit_from_device_pieces_equals_oracle_unsplit(orc, dev, solver, slope_type):
+    """ctoprim -> slope_lcr -> trace_sources -> trace_faces -> riemann -> flux*dt/dx assembled from the per-cell DEVICE functions
+    on 6^3 patches == unsplit of the oracle (hydro/umuscl.f90:22), bit for bit, for the 36 faces of every patch"""
+    L = orc.lib()
+    L.orc_work_new.restype = C.c_void_p
+    L.orc_work_new.argtypes = [C.POINTER(orc.Params)]
+    L.orc_work_free.argtypes = [C.c_void_p]
+    dp = C.POINTER(C.c_double)
+    L.orc_unsplit.argtypes = [C.POINTER(orc.Params), C.c_void_p, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+    p = orc.make_params(ndim=3, riemann=solver, slope_type=slope_type, slope_theta=1.3, nvector=1, niter_riemann=10)
+    w = L.orc_work_new(C.byref(p))
+    rng = np.random.default_rng(100 + slope_type)
+    sid = {"llf": 0, "exact": 1, "acoustic": 2, "hllc": 3, "hll": 4}[solver]
+    dx = 1.0 / 64
+    for trial in range(12):
+        rho = 1 + 0.5 * rng.random((6, 6, 6))
+        if trial % 3 == 0:
+            rho[3:] *= 8.0                                             # a jump through the patch
+        vel = (0.5 if trial % 2 else 3.0) * rng.standard_normal((3, 6, 6, 6))
+        pres = 10.0 ** rng.uniform(-2, 1, (6, 6, 6))
+        uin = np.zeros((5, 216))
+        uin[0] = rho.reshape(-1)
+        for k in range(3):
+            uin[1 + k] = (rho * vel[k]).reshape(-1)
+        uin[4] = (pres / 0.4 + 0.5 * rho * (vel ** 2).sum(axis=0)).reshape(-1)
+        uin = np.ascontiguousarray(uin)
+        dt = 0.3 * dx / 5.0
+        f_dev = np.zeros(3 * 5 * 27)
+        dev.devnum_unsplit3d(sid, slope_type, 1.3, orc.dptr(uin), dx, dt, orc.dptr(f_dev), 1.4, 1e-10, 1e-10, 10)
+        f_orc = np.zeros(3 * 5 * 27)
+        tmp = np.zeros(3 * 2 * 27)
+        L.orc_unsplit(C.byref(p), w, orc.dptr(uin), None, orc.dptr(f_orc), orc.dptr(tmp), dx, dx, dx, dt, 1)
+        fd, fo = f_dev.reshape(3, 5, 3, 3, 3), f_orc.reshape(3, 5, 3, 3, 3)      # [idim][ivar][k3][j3][i3]
+        assert np.array_equal(fd[0][:, 0:2, 0:2, 0:3], fo[0][:, 0:2, 0:2, 0:3])
+        assert np.array_equal(fd[1][:, 0:2, 0:3, 0:2], fo[1][:, 0:2, 0:3, 0:2])
+        assert np.array_equal(fd[2][:, 0:3, 0:2, 0:2], fo[2][:, 0:3, 0:2, 0:2])
+        assert np.abs(fo).max() > 1e-4
+    L.orc_work_free(w)
