@@ -710,6 +710,7 @@ __global__ void amr_fill_shell_kernel(const AmrTree t, const double* __restrict_
   for (int is = 0; is < 8; is++) u[((size_t)n * 8 + is) * nslot + s] = u2[is];
 }
 
+#ifndef RGPU_HOST_NUMERICS   // (tests/host_numerics compiles the __device__ helpers above with g++: no kernel launches there)
 template <int NDIM, int RIEMANN>
 cudaError_t launch_amr_godfine(const AmrSweepArgs& a, cudaStream_t st) {
   const int nb = (a.nact + AMR_OPB - 1) / AMR_OPB;
@@ -723,5 +724,6 @@ cudaError_t launch_amr_godfine(const AmrSweepArgs& a, cudaStream_t st) {
   } else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
+#endif
 
 }  // namespace rgpu

@@ -3,6 +3,11 @@
 // TEST HARNESS ONLY.  Built with  g++ -O2 -ffp-contract=off  (the device build uses -fmad=false for the same reason).
 #define RGPU_HOST_NUMERICS 1
 #include "mhd_device.cuh"   // pulls hydro_device.cuh and real64.cuh
+namespace rgpu {            // reductions that rgpu_api.cu defines before including amr_kernels.cuh (kernel bodies only parse here)
+inline double warp_min(double v) { return v; }
+inline double warp_sum(double v) { return v; }
+}
+#include "amr_kernels.cuh"  // the __device__ tree-walk / prolongation helpers of the AMR kernels
 
 using namespace rgpu;
 
@@ -125,6 +130,43 @@ void devnum_unsplit3d(int solver, int slope_type, double slope_theta, const doub
           for (int v = 0; v < 5; v++)
             flux[(perm[d][v] + 5 * d) * 27 + (i3 - 1) + 3 * ((j3 - 1) + 3 * (k3 - 1))] = fg[v] * dt / dx;
         }
+  }
+}
+
+// tree walks of the AMR kernels on a host copy of the tree arrays (1-based Fortran arrays handed over as 0-based views)
+void devnum_amr_get3cubefather(int ndim, int ncoarse, int ngridmax, int nx, int ny, int nz, const int* son, const int* father,
+                               const int* nbor, int n, const int* igrid, int ilevel, int* nfc /*[n][3^ndim]*/) {
+  AmrTree t;
+  t.son = son - 1; t.father = father - 1; t.nbor = nbor; t.ncoarse = ncoarse; t.ngridmax = ngridmax; t.nx = nx; t.ny = ny; t.nz = nz;
+  t.ncell = (long long)ncoarse + (long long)(1 << ndim) * ngridmax;
+  const int n3 = ndim == 1 ? 3 : (ndim == 2 ? 9 : 27);
+  for (int i = 0; i < n; i++) {
+    int ng[8];
+    if (ndim == 1) amr_get3cubefather<1>(t, igrid[i], ilevel, nfc + i * n3, ng);
+    else if (ndim == 2) amr_get3cubefather<2>(t, igrid[i], ilevel, nfc + i * n3, ng);
+    else amr_get3cubefather<3>(t, igrid[i], ilevel, nfc + i * n3, ng);
+  }
+}
+
+void devnum_amr_getnborfather(int ndim, int ncoarse, int ngridmax, int nx, int ny, int nz, const int* son, const int* father,
+                              const int* nbor, int n, const int* cells, int ilevel, int* fa /*[n][2*ndim+1]*/) {
+  AmrTree t;
+  t.son = son - 1; t.father = father - 1; t.nbor = nbor; t.ncoarse = ncoarse; t.ngridmax = ngridmax; t.nx = nx; t.ny = ny; t.nz = nz;
+  t.ncell = (long long)ncoarse + (long long)(1 << ndim) * ngridmax;
+  for (int i = 0; i < n; i++) {
+    if (ndim == 1) amr_getnborfather<1>(t, cells[i], ilevel, fa + i * 3);
+    else if (ndim == 2) amr_getnborfather<2>(t, cells[i], ilevel, fa + i * 5);
+    else amr_getnborfather<3>(t, cells[i], ilevel, fa + i * 7);
+  }
+}
+
+// interpol_hydro for one variable: a [n][2*ndim+1] -> u2 [n][2^ndim]
+void devnum_amr_interpol(int ndim, int interpol_type, int n, const double* a, double* u2) {
+  const int na = 2 * ndim + 1, T = 1 << ndim;
+  for (int i = 0; i < n; i++) {
+    if (ndim == 1) amr_interpol_var<1>(a + i * na, interpol_type, u2 + i * T);
+    else if (ndim == 2) amr_interpol_var<2>(a + i * na, interpol_type, u2 + i * T);
+    else amr_interpol_var<3>(a + i * na, interpol_type, u2 + i * T);
   }
 }
 

@@ -14,3 +14,23 @@ using std::fmax;
 using std::fmin;
 using std::pow;
 using std::sqrt;
+
+// enough of the CUDA execution model for the KERNEL bodies of amr_kernels.cuh to parse as plain functions (they are never
+// called on the host; only the __device__ helper functions next to them are)
+struct rgpu_stub_dim3 { unsigned x, y, z; };
+static rgpu_stub_dim3 threadIdx, blockIdx, blockDim, gridDim;
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __restrict__
+inline void __syncthreads() {}
+inline void __syncwarp(unsigned = 0xffffffffu) {}
+template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __shfl_down_sync(unsigned, T v, int) { return v; }
+template <class T> inline T __shfl_up_sync(unsigned, T v, int) { return v; }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+template <class T> inline T __shfl_sync(unsigned, T v, int) { return v; }
+inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+inline int __any_sync(unsigned, int p) { return p; }
+inline int __all_sync(unsigned, int p) { return p; }
+typedef int cudaError_t;
+typedef void* cudaStream_t;

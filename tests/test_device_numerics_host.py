@@ -17,7 +17,8 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 @pytest.fixture(scope="module")
 def dev():
     lib = os.path.join(HERE, "libdevnum_host.so")
-    srcs = [os.path.join(HERE, "devnum.cpp")] + [os.path.join(CSRC, f) for f in ("hydro_device.cuh", "real64.cuh", "mhd_device.cuh")]
+    srcs = [os.path.join(HERE, "devnum.cpp"), os.path.join(HERE, "stub", "cuda_runtime.h")] + \
+        [os.path.join(CSRC, f) for f in ("hydro_device.cuh", "real64.cuh", "mhd_device.cuh", "amr_kernels.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared",
                                "-I" + os.path.join(HERE, "stub"), "-I" + CSRC, "-o", lib, os.path.join(HERE, "devnum.cpp")])
@@ -30,6 +31,10 @@ def dev():
     L.devnum_mhd_cmpdt.argtypes = [C.c_int, dp, C.c_double, dp, C.c_double, C.c_double, C.c_double, C.c_double]
     L.devnum_unsplit3d.argtypes = [C.c_int, C.c_int, C.c_double, dp, C.c_double, C.c_double, dp, C.c_double, C.c_double, C.c_double,
                                    C.c_int]
+    ip = C.POINTER(C.c_int)
+    L.devnum_amr_get3cubefather.argtypes = [C.c_int] * 6 + [ip, ip, ip, C.c_int, ip, C.c_int, ip]
+    L.devnum_amr_getnborfather.argtypes = [C.c_int] * 6 + [ip, ip, ip, C.c_int, ip, C.c_int, ip]
+    L.devnum_amr_interpol.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp]
     return L
 
 
@@ -232,3 +237,83 @@ def test_unsplit_from_device_pieces_equals_oracle_unsplit(orc, dev, solver, slop
         assert np.array_equal(fd[2][:, 0:3, 0:2, 0:2], fo[2][:, 0:3, 0:2, 0:2])
         assert np.abs(fo).max() > 1e-4
     L.orc_work_free(w)
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_amr_tree_walks_of_the_kernels_equal_oracle(orc, dev, ndim):
+    """amr_get3cubefather / amr_getnborfather (the device restatement of amr/nbors_utils.f90:5-194,404-525 used by the AMR kernels)
+    against the oracle's on an adaptively refined mesh with physical boundaries: every oct and every cell of every level"""
+    from oracle.amr import FastAmrRun
+    if ndim == 1:
+        reg = [dict(type="square", x_center=0.25, length_x=0.5, d=1.0, p=1.0), dict(type="square", x_center=0.75, length_x=0.5, d=0.125, p=0.1)]
+        r = FastAmrRun(1, 3, 8, (1, 1, 0, 0, 0, 0), 1.0, nsubcycle=[1, 2], ngridmax=500, err_grad_d=0.05, err_grad_p=0.05,
+                       interpol_type=2, regions=reg, tout=[0.05])
+    elif ndim == 2:
+        from conftest import IMPL, IMPL_BOUND
+        r = FastAmrRun(2, 4, 7, (1, 1, 1, 1, 0, 0), 1.0, nsubcycle=[2] * 10, nexpand=[2], ngridmax=20000, err_grad_d=0.05,
+                       err_grad_u=0.05, err_grad_p=0.05, interpol_type=2, regions=IMPL, tout=[0.0, 0.05], bound_regions=IMPL_BOUND)
+    else:
+        reg = [dict(type="square", x_center=0.5, y_center=0.5, z_center=0.5, length_x=10, length_y=10, length_z=10, exp_region=10, d=1.0, p=1e-5),
+               dict(type="point", x_center=0.5, y_center=0.5, z_center=0.5, p=0.4)]
+        r = FastAmrRun(3, 3, 5, (0, 0, 2, 2, 1, 1), 1.0, nsubcycle=[1, 2], ngridmax=4000, riemann="hllc", slope_type=1,
+                       err_grad_p=0.1, interpol_type=1, regions=reg, tout=[1e9])
+    r.run(max_coarse=3)
+    m = r.m
+    T, n3, nn = 1 << ndim, 3 ** ndim, 2 * ndim + 1
+    son = np.ascontiguousarray(r.son[1:], dtype=np.int32)
+    father = np.ascontiguousarray(r.father[1:], dtype=np.int32)
+    nbor = np.ascontiguousarray(r.nbor[:, 1:], dtype=np.int32)
+    geo = (ndim, r.ncoarse, r.ngridmax, m.nx, m.ny, m.nz)
+    L = orc.lib()
+    L.orc_getnborfather.argtypes = [C.POINTER(orc.MeshS), C.c_int, C.c_int, C.POINTER(C.c_int)]
+    checked = 0
+    for l in range(1, r.nlevelmax + 1):
+        octs = list(r.active[l]) + [g for b in range(m.nboundary) for g in r.bound[b][l]]
+        act = np.asarray(r.active[l], dtype=np.int32)
+        if len(act):
+            got = np.zeros((len(act), n3), dtype=np.int32)
+            dev.devnum_amr_get3cubefather(*geo, orc.iptr(son), orc.iptr(father), orc.iptr(nbor), len(act), orc.iptr(act), l, orc.iptr(got))
+            ref = np.zeros((len(act), n3), dtype=np.int32)
+            buf = (C.c_int * 27)()
+            for i, g in enumerate(act):
+                L.orc_get3cubefather(r.mp, int(r.father[g]), l, buf, None)
+                ref[i] = buf[:n3]
+            assert np.array_equal(got, ref)
+            checked += len(act)
+        if l < r.nlevelmax and len(octs):
+            cells = np.array([r.ncoarse + ind * r.ngridmax + g for g in octs for ind in range(T)], dtype=np.int32)
+            got = np.zeros((len(cells), nn), dtype=np.int32)
+            dev.devnum_amr_getnborfather(*geo, orc.iptr(son), orc.iptr(father), orc.iptr(nbor), len(cells), orc.iptr(cells), l + 1, orc.iptr(got))
+            ref = np.zeros((len(cells), nn), dtype=np.int32)
+            buf = (C.c_int * 7)()
+            for i, c in enumerate(cells):
+                L.orc_getnborfather(r.mp, int(c), l + 1, buf)
+                ref[i] = buf[:nn]
+            assert np.array_equal(got, ref)
+    assert checked > 50 and len(r.active[r.levelmin + 1]) > 0
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+@pytest.mark.parametrize("itype", [0, 1, 2, 3])
+def test_amr_prolongation_of_the_kernels_equals_oracle(orc, dev, ndim, itype):
+    """amr_interpol_var (interpol_hydro on the device, one variable at a time) == orc_interpol_hydro, bit for bit"""
+    L = orc.lib()
+    L.orc_set_interpol.argtypes = [C.c_int, C.c_int]
+    L.orc_interpol_hydro.argtypes = [C.POINTER(orc.Params), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    n, na, T = 4000, 2 * ndim + 1, 1 << ndim
+    rng = np.random.default_rng(ndim * 7 + itype)
+    a = rng.standard_normal((n, na)) * 10.0 ** rng.uniform(-3, 3, (n, 1))
+    a[: n // 4] = np.abs(a[: n // 4])
+    a[n // 4: n // 2, 1:] = a[n // 4: n // 2, :1] * (1 + 1e-3 * rng.standard_normal((n // 4, na - 1)))
+    a = np.ascontiguousarray(a)
+    got = np.zeros((n, T))
+    dev.devnum_amr_interpol(ndim, itype, n, orc.dptr(a), orc.dptr(got))
+    p = orc.make_params(ndim=ndim, nvar=1)
+    ref = np.zeros((n, T))
+    try:
+        L.orc_set_interpol(itype, 0)
+        for i in range(n):
+            L.orc_interpol_hydro(C.byref(p), orc.dptr(a[i]), orc.dptr(ref[i]))
+    finally:
+        L.orc_set_interpol(1, 0)
+    assert np.array_equal(got, ref)
