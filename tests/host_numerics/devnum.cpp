@@ -9,7 +9,34 @@ inline double warp_sum(double v) { return v; }
 }
 #include "amr_kernels.cuh"  // the __device__ tree-walk / prolongation helpers of the AMR kernels
 
+#include <pthread.h>
+#include <thread>
+#include <vector>
+
 using namespace rgpu;
+
+// ---- emulated launch of a barrier-only kernel: one OS thread per CUDA thread of a block, blocks one after the other ----------
+static pthread_barrier_t g_block_barrier;
+static void block_barrier() { pthread_barrier_wait(&g_block_barrier); }
+
+template <class Kernel, class Args>
+static void emulate_launch(Kernel kernel, const Args& a, int nblocks, int nthreads) {
+  pthread_barrier_init(&g_block_barrier, nullptr, (unsigned)nthreads);
+  rgpu_stub_sync_hook = block_barrier;
+  std::vector<std::thread> team;
+  for (int t = 0; t < nthreads; t++)
+    team.emplace_back([&, t] {
+      for (int b = 0; b < nblocks; b++) {
+        threadIdx = {(unsigned)t, 0, 0}; blockIdx = {(unsigned)b, 0, 0};
+        blockDim = {(unsigned)nthreads, 1, 1}; gridDim = {(unsigned)nblocks, 1, 1};
+        kernel(a);
+        pthread_barrier_wait(&g_block_barrier);      // the next block reuses the __shared__ storage
+      }
+    });
+  for (auto& th : team) th.join();
+  rgpu_stub_sync_hook = nullptr;
+  pthread_barrier_destroy(&g_block_barrier);
+}
 
 static Phys make_phys(double gamma, double smallr, double smallc, double slope_theta, double courant_factor, int slope_type,
                       int niter) {   // mirrors rgpu_init (ramses_b200/csrc/rgpu_api.cu)
@@ -168,6 +195,35 @@ void devnum_amr_interpol(int ndim, int interpol_type, int n, const double* a, do
     else if (ndim == 2) amr_interpol_var<2>(a + i * na, interpol_type, u2 + i * T);
     else amr_interpol_var<3>(a + i * na, interpol_type, u2 + i * T);
   }
+}
+
+// amr_godfine_kernel (the oct-batch kernel of AMR mode) run by the emulated launch on host copies of the arrays: updates unew of
+// the level's own cells and writes the outer-face fluxes rflux [nact][2*ndim][2^(ndim-1)][nvar]
+void devnum_amr_godfine(int ndim, int solver, int ncoarse, int ngridmax, int nx, int ny, int nz, const int* son, const int* father,
+                        const int* nbor, const int* active, int nact, int ilevel, const double* uold, double* unew, double* rflux,
+                        double dt, double dx, int interpol_type, int slope_type, double gamma, double smallr, double smallc,
+                        int niter) {
+  AmrSweepArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.t.son = son - 1; a.t.father = father - 1; a.t.nbor = nbor; a.t.ncoarse = ncoarse; a.t.ngridmax = ngridmax;
+  a.t.nx = nx; a.t.ny = ny; a.t.nz = nz; a.t.ncell = (long long)ncoarse + (long long)(1 << ndim) * ngridmax;
+  a.active = active; a.nact = nact; a.ilevel = ilevel; a.uold = uold; a.unew = unew; a.rflux = rflux;
+  a.P = make_phys(gamma, smallr, smallc, 1.5, 0.8, slope_type, niter);
+  a.dt = dt; a.dx = dx; a.inv_dx = 1.0 / dx;
+  int ex;
+  a.dx_pow2 = (std::frexp(dx, &ex) == 0.5) ? 1 : 0;
+  a.interpol_type = interpol_type; a.difmag = 0.0; a.nps = 0; a.flux_only = 0; a.rflux_index = nullptr; a.dt_dev = nullptr;
+  const int nb = (nact + AMR_OPB - 1) / AMR_OPB, nt = AMR_TPO * AMR_OPB;
+#define RUN(ND, RS) emulate_launch(amr_godfine_kernel<ND, RS, false, 0>, a, nb, nt)
+#define RUN_ND(ND)                                                                                              \
+  do {                                                                                                          \
+    if (solver == RIEMANN_LLF) RUN(ND, RIEMANN_LLF); else if (solver == RIEMANN_EXACT) RUN(ND, RIEMANN_EXACT);   \
+    else if (solver == RIEMANN_ACOUSTIC) RUN(ND, RIEMANN_ACOUSTIC); else if (solver == RIEMANN_HLLC) RUN(ND, RIEMANN_HLLC); \
+    else RUN(ND, RIEMANN_HLL);                                                                                  \
+  } while (0)
+  if (ndim == 1) RUN_ND(1); else if (ndim == 2) RUN_ND(2); else RUN_ND(3);
+#undef RUN_ND
+#undef RUN
 }
 
 static MPhys make_mphys(double gamma, double smallr, double smallc) {

@@ -15,14 +15,16 @@ using std::fmin;
 using std::pow;
 using std::sqrt;
 
-// enough of the CUDA execution model for the KERNEL bodies of amr_kernels.cuh to parse as plain functions (they are never
-// called on the host; only the __device__ helper functions next to them are)
+// enough of the CUDA execution model for the KERNEL bodies of amr_kernels.cuh to compile as plain functions: the test driver
+// runs a block as blockDim.x OS threads that share the function-local `static` (= __shared__) storage and meet at a barrier
+// in __syncthreads() -- good for kernels that use barriers only (no warp shuffles, no cp.async)
 struct rgpu_stub_dim3 { unsigned x, y, z; };
-static rgpu_stub_dim3 threadIdx, blockIdx, blockDim, gridDim;
+static thread_local rgpu_stub_dim3 threadIdx, blockIdx, blockDim, gridDim;   // set per emulated thread by the test driver
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __restrict__
-inline void __syncthreads() {}
+inline void (*rgpu_stub_sync_hook)() = nullptr;     // block barrier of the emulated launch (tests/host_numerics/devnum.cpp)
+inline void __syncthreads() { if (rgpu_stub_sync_hook) rgpu_stub_sync_hook(); }
 inline void __syncwarp(unsigned = 0xffffffffu) {}
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int) { return v; }

@@ -20,7 +20,7 @@ def dev():
     srcs = [os.path.join(HERE, "devnum.cpp"), os.path.join(HERE, "stub", "cuda_runtime.h")] + \
         [os.path.join(CSRC, f) for f in ("hydro_device.cuh", "real64.cuh", "mhd_device.cuh", "amr_kernels.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(s) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared",
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-pthread",
                                "-I" + os.path.join(HERE, "stub"), "-I" + CSRC, "-o", lib, os.path.join(HERE, "devnum.cpp")])
     L = C.CDLL(lib)
     dp = C.POINTER(C.c_double)
@@ -35,6 +35,8 @@ def dev():
     L.devnum_amr_get3cubefather.argtypes = [C.c_int] * 6 + [ip, ip, ip, C.c_int, ip, C.c_int, ip]
     L.devnum_amr_getnborfather.argtypes = [C.c_int] * 6 + [ip, ip, ip, C.c_int, ip, C.c_int, ip]
     L.devnum_amr_interpol.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp]
+    L.devnum_amr_godfine.argtypes = [C.c_int] * 7 + [ip, ip, ip, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_int,
+                                     C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
     return L
 
 
@@ -317,3 +319,63 @@ def test_amr_prolongation_of_the_kernels_equals_oracle(orc, dev, ndim, itype):
     finally:
         L.orc_set_interpol(1, 0)
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("ndim,solver", [(1, "hllc"), (2, "hllc"), (2, "llf"), (3, "hllc"), (3, "exact")])
+def test_amr_oct_batch_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, solver):
+    """amr_godfine_kernel itself -- 64 cooperating threads per oct, the 6^ndim patch and the face states in shared memory, five
+    block barriers -- executed by the emulated launch of tests/host_numerics (one OS thread per CUDA thread, `static` for
+    __shared__, a pthread barrier for __syncthreads) on an adaptively refined mesh: the update of the level's own cells equals
+    godfine1 of the oracle (gather with prolongated ghost octs, unsplit, flux reset at refined faces, conservative update) bit
+    for bit on every level.  The kernels that use warp shuffles / cp.async (the dense sweep) are outside this harness."""
+    from oracle.amr import FastAmrRun
+    if ndim == 1:
+        reg = [dict(type="square", x_center=0.25, length_x=0.5, d=1.0, p=1.0), dict(type="square", x_center=0.75, length_x=0.5, d=0.125, p=0.1)]
+        r = FastAmrRun(1, 3, 8, (1, 1, 0, 0, 0, 0), 1.0, nsubcycle=[1, 2], ngridmax=500, riemann=solver, slope_type=2,
+                       err_grad_d=0.05, err_grad_p=0.05, interpol_type=2, regions=reg, tout=[1e9])
+        itype, st = 2, 2
+    elif ndim == 2:
+        from conftest import IMPL, IMPL_BOUND
+        r = FastAmrRun(2, 4, 6, (1, 1, 1, 1, 0, 0), 1.0, nsubcycle=[2] * 10, nexpand=[2], ngridmax=20000, riemann=solver, slope_type=2,
+                       err_grad_d=0.05, err_grad_u=0.05, err_grad_p=0.05, interpol_type=2, regions=IMPL, tout=[0.0, 1e9],
+                       bound_regions=IMPL_BOUND)
+        itype, st = 2, 2
+    else:
+        reg = [dict(type="square", x_center=0.5, y_center=0.5, z_center=0.5, length_x=10, length_y=10, length_z=10, exp_region=10, d=1.0, p=1e-5),
+               dict(type="point", x_center=0.5, y_center=0.5, z_center=0.5, p=0.4)]
+        r = FastAmrRun(3, 3, 5, (0,) * 6, 1.0, nsubcycle=[1, 2], ngridmax=4000, riemann=solver, slope_type=1, err_grad_p=0.1,
+                       interpol_type=1, regions=reg, tout=[1e9])
+        itype, st = 1, 1
+    r.run(max_coarse=3)
+    m = r.m
+    T, nvar = 1 << ndim, ndim + 2
+    son = np.ascontiguousarray(r.son[1:], dtype=np.int32)
+    father = np.ascontiguousarray(r.father[1:], dtype=np.int32)
+    nbor = np.ascontiguousarray(r.nbor[:, 1:], dtype=np.int32)
+    sid = {"llf": 0, "exact": 1, "acoustic": 2, "hllc": 3, "hll": 4}[solver]
+    L = orc.lib()
+    nlev, moved = 0, 0.0
+    for l in range(r.levelmin, r.nlevelmax + 1):
+        act = np.ascontiguousarray(r.active[l], dtype=np.int32)
+        if len(act) == 0:
+            continue
+        dt = 0.4 * r.dtnew[r.levelmin] / 2 ** (l - r.levelmin) if r.dtnew[r.levelmin] > 0 else 1e-4
+        dx = 0.5 ** l * r.p.boxlen / (m.icoarse_max - m.icoarse_min + 1)
+        # oracle: set_unew + godunov_fine of this level only
+        unew_o = np.zeros_like(r.uold)
+        L.orc_set_unew(C.byref(r.p), r.mp, l, orc.dptr(r.uold), orc.dptr(unew_o))
+        L.orc_godunov_fine(C.byref(r.p), r.mp, l, dt, orc.dptr(r.uold), orc.dptr(unew_o), 1)
+        # emulated kernel: unew = uold on the level's cells, then the kernel adds the flux differences
+        unew_k = np.zeros_like(r.uold)
+        L.orc_set_unew(C.byref(r.p), r.mp, l, orc.dptr(r.uold), orc.dptr(unew_k))
+        rflux = np.zeros(len(act) * 2 * ndim * (T // 2) * nvar)
+        dev.devnum_amr_godfine(ndim, sid, r.ncoarse, r.ngridmax, m.nx, m.ny, m.nz, orc.iptr(son), orc.iptr(father), orc.iptr(nbor),
+                               orc.iptr(act), len(act), l, orc.dptr(r.uold), orc.dptr(unew_k), orc.dptr(rflux), dt, dx, itype, st,
+                               1.4, 1e-10, 1e-10, 10)
+        Uo, Uk = unew_o.reshape(nvar, r.ncell), unew_k.reshape(nvar, r.ncell)
+        for ind in range(T):
+            c = r.ncoarse + ind * r.ngridmax + act.astype(np.int64) - 1
+            assert np.array_equal(Uk[:, c], Uo[:, c]), (l, ind)
+            moved = max(moved, float(np.abs(Uo[:, c] - r.uold.reshape(nvar, r.ncell)[:, c]).max()))
+        nlev += 1
+    assert nlev >= 3 and moved > 1e-6
