@@ -202,7 +202,7 @@ void devnum_amr_interpol(int ndim, int interpol_type, int n, const double* a, do
 void devnum_amr_godfine(int ndim, int solver, int ncoarse, int ngridmax, int nx, int ny, int nz, const int* son, const int* father,
                         const int* nbor, const int* active, int nact, int ilevel, const double* uold, double* unew, double* rflux,
                         double dt, double dx, int interpol_type, int slope_type, double gamma, double smallr, double smallc,
-                        int niter) {
+                        int niter, double difmag) {
   AmrSweepArgs a;
   std::memset(&a, 0, sizeof a);
   a.t.son = son - 1; a.t.father = father - 1; a.t.nbor = nbor; a.t.ncoarse = ncoarse; a.t.ngridmax = ngridmax;
@@ -212,9 +212,13 @@ void devnum_amr_godfine(int ndim, int solver, int ncoarse, int ngridmax, int nx,
   a.dt = dt; a.dx = dx; a.inv_dx = 1.0 / dx;
   int ex;
   a.dx_pow2 = (std::frexp(dx, &ex) == 0.5) ? 1 : 0;
-  a.interpol_type = interpol_type; a.difmag = 0.0; a.nps = 0; a.flux_only = 0; a.rflux_index = nullptr; a.dt_dev = nullptr;
+  a.interpol_type = interpol_type; a.difmag = difmag; a.nps = 0; a.flux_only = 0; a.rflux_index = nullptr; a.dt_dev = nullptr;
   const int nb = (nact + AMR_OPB - 1) / AMR_OPB, nt = AMR_TPO * AMR_OPB;
-#define RUN(ND, RS) emulate_launch(amr_godfine_kernel<ND, RS, false, 0>, a, nb, nt)
+#define RUN(ND, RS)                                                              \
+  do {                                                                          \
+    if (difmag > 0.0) emulate_launch(amr_godfine_kernel<ND, RS, true, 0>, a, nb, nt); \
+    else emulate_launch(amr_godfine_kernel<ND, RS, false, 0>, a, nb, nt);        \
+  } while (0)
 #define RUN_ND(ND)                                                                                              \
   do {                                                                                                          \
     if (solver == RIEMANN_LLF) RUN(ND, RIEMANN_LLF); else if (solver == RIEMANN_EXACT) RUN(ND, RIEMANN_EXACT);   \

@@ -36,7 +36,7 @@ def dev():
     L.devnum_amr_getnborfather.argtypes = [C.c_int] * 6 + [ip, ip, ip, C.c_int, ip, C.c_int, ip]
     L.devnum_amr_interpol.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp]
     L.devnum_amr_godfine.argtypes = [C.c_int] * 7 + [ip, ip, ip, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_int,
-                                     C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+                                     C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double]
     return L
 
 
@@ -321,8 +321,9 @@ def test_amr_prolongation_of_the_kernels_equals_oracle(orc, dev, ndim, itype):
     assert np.array_equal(got, ref)
 
 
-@pytest.mark.parametrize("ndim,solver", [(1, "hllc"), (2, "hllc"), (2, "llf"), (3, "hllc"), (3, "exact")])
-def test_amr_oct_batch_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, solver):
+@pytest.mark.parametrize("ndim,solver,difmag", [(1, "hllc", 0.0), (2, "hllc", 0.0), (2, "llf", 0.0), (3, "hllc", 0.0), (3, "exact", 0.0),
+                                                 (2, "hllc", 0.1), (3, "hllc", 0.1)])
+def test_amr_oct_batch_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, solver, difmag):
     """amr_godfine_kernel itself -- 64 cooperating threads per oct, the 6^ndim patch and the face states in shared memory, five
     block barriers -- executed by the emulated launch of tests/host_numerics (one OS thread per CUDA thread, `static` for
     __shared__, a pthread barrier for __syncthreads) on an adaptively refined mesh: the update of the level's own cells equals
@@ -347,6 +348,7 @@ def test_amr_oct_batch_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, 
                        interpol_type=1, regions=reg, tout=[1e9])
         itype, st = 1, 1
     r.run(max_coarse=3)
+    r.p.difmag = difmag                                  # artificial diffusion (cmpdivu / consup) for the comparison step only
     m = r.m
     T, nvar = 1 << ndim, ndim + 2
     son = np.ascontiguousarray(r.son[1:], dtype=np.int32)
@@ -371,7 +373,7 @@ def test_amr_oct_batch_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, 
         rflux = np.zeros(len(act) * 2 * ndim * (T // 2) * nvar)
         dev.devnum_amr_godfine(ndim, sid, r.ncoarse, r.ngridmax, m.nx, m.ny, m.nz, orc.iptr(son), orc.iptr(father), orc.iptr(nbor),
                                orc.iptr(act), len(act), l, orc.dptr(r.uold), orc.dptr(unew_k), orc.dptr(rflux), dt, dx, itype, st,
-                               1.4, 1e-10, 1e-10, 10)
+                               1.4, 1e-10, 1e-10, 10, difmag)
         Uo, Uk = unew_o.reshape(nvar, r.ncell), unew_k.reshape(nvar, r.ncell)
         for ind in range(T):
             c = r.ncoarse + ind * r.ngridmax + act.astype(np.int64) - 1
