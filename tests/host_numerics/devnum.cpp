@@ -67,6 +67,9 @@ static void riemann_nd(int solver, const double* ql, const double* qr, double* f
   }
 }
 
+// Built with -fvisibility=hidden -Wl,-Bsymbolic: the kernels compiled here have the same mangled names as the CUDA launch stubs
+// of libramses_gpu.so (loaded RTLD_GLOBAL by the ABI tests in the same process) and must never be interposed by them.
+#pragma GCC visibility push(default)
 extern "C" {
 
 // n Riemann problems: ql, qr [n][ndim+2] in solver order (rho, u_n, P, u_t1, u_t2), fg [n][ndim+2]
@@ -287,3 +290,4 @@ void devnum_mhd_cmpdt(int n, const double* u, double dx, double* dt, double gamm
 }
 
 }  // extern "C"
+#pragma GCC visibility pop

@@ -21,8 +21,9 @@ def dev():
         [os.path.join(CSRC, f) for f in ("hydro_device.cuh", "real64.cuh", "mhd_device.cuh", "amr_kernels.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-pthread",
+                               "-fvisibility=hidden", "-fvisibility-inlines-hidden", "-Wl,-Bsymbolic",
                                "-I" + os.path.join(HERE, "stub"), "-I" + CSRC, "-o", lib, os.path.join(HERE, "devnum.cpp")])
-    L = C.CDLL(lib)
+    L = C.CDLL(lib, mode=os.RTLD_LOCAL | os.RTLD_NOW)
     dp = C.POINTER(C.c_double)
     L.devnum_riemann.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int]
     L.devnum_cmpdt.argtypes = [C.c_int, C.c_int, dp, C.c_double, dp, C.c_double, C.c_double, C.c_double, C.c_double]
