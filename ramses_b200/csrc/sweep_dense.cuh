@@ -99,11 +99,16 @@ __device__ __forceinline__ void scale_fluxes(double* f, double dt, double dx, do
   }
 }
 
+#ifdef RGPU_HOST_NUMERICS   // tests/host_numerics (g++, no CUDA): a plain copy
+inline void cp_async8(double* smem_dst, const double* gsrc) { *smem_dst = *gsrc; }
+inline void cp_async_wait_all() {}
+#else
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+#endif
 
 template <int NDIM, int BX, int BY>
 struct SweepSmem {
@@ -131,7 +136,11 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
   constexpr int TWOTONDIM = 1 << NDIM;
   constexpr int PL = QY * QX;                 // one variable of one q plane
   static_assert(BX == 32, "a warp must be one x-row of the tile");
+#ifdef RGPU_HOST_NUMERICS
+  double* smem = rgpu_host_dyn_smem;           // dynamic shared memory of the emulated launch (tests/host_numerics)
+#else
   extern __shared__ double smem[];
+#endif
   double* qring = smem;                        // [NRING][NQ][QY][QX]
   double* stage = qring + S::ring;             // [NV][QY][QX] raw conserved state of the next plane
   double* exq = stage + S::stage;              // [NV][NT] qm_y
@@ -544,6 +553,7 @@ __host__ __device__ constexpr int tile_by_default(int ndim, int riemann) {
   return ndim == 1 ? 1 : ndim == 2 ? 8 : 12;   // measured best for every solver (riemann unused)
 }
 
+#ifndef RGPU_HOST_NUMERICS   // kernel launches: product build only
 template <int NDIM, int RIEMANN, int SLOPE, int BY>
 cudaError_t launch_sweep_dense_sb(const SweepArgs& a, int nblocks, cudaStream_t st) {
   constexpr int BX = 32;
@@ -588,5 +598,6 @@ cudaError_t launch_sweep_dense(const SweepArgs& a, int nblocks, cudaStream_t st,
   if (a.P.slope_type == 2) return launch_sweep_dense_s<NDIM, RIEMANN, 2>(a, nblocks, st, by);
   return launch_sweep_dense_s<NDIM, RIEMANN, -1>(a, nblocks, st, by);
 }
+#endif
 
 }  // namespace rgpu

@@ -2,12 +2,10 @@
 // tests/test_device_numerics_host.py to compare the formulas the kernels execute with the oracle, bit for bit, on the CPU.
 // TEST HARNESS ONLY.  Built with  g++ -O2 -ffp-contract=off  (the device build uses -fmad=false for the same reason).
 #define RGPU_HOST_NUMERICS 1
-#include "mhd_device.cuh"   // pulls hydro_device.cuh and real64.cuh
-namespace rgpu {            // reductions that rgpu_api.cu defines before including amr_kernels.cuh (kernel bodies only parse here)
-inline double warp_min(double v) { return v; }
-inline double warp_sum(double v) { return v; }
-}
-#include "amr_kernels.cuh"  // the __device__ tree-walk / prolongation helpers of the AMR kernels
+#define MHD_DEFINE_KERNELS 1
+static double* rgpu_host_dyn_smem = nullptr;   // dynamic shared memory of an emulated launch (sweep_dense.cuh)
+#include "mhd_dense.cuh"    // the six MHD passes; pulls sweep_dense.cuh, mhd_device.cuh, hydro_device.cuh, real64.cuh
+#include "amr_kernels.cuh"  // the AMR oct-batch kernel and its __device__ tree-walk / prolongation helpers
 
 #include <pthread.h>
 #include <thread>
@@ -36,6 +34,18 @@ static void emulate_launch(Kernel kernel, const Args& a, int nblocks, int nthrea
   for (auto& th : team) th.join();
   rgpu_stub_sync_hook = nullptr;
   pthread_barrier_destroy(&g_block_barrier);
+}
+
+// one thread after the other: good for kernels whose threads do not communicate (the per-cell MHD passes)
+template <class Kernel, class Args>
+static void emulate_serial(Kernel kernel, const Args& a, long long nblocks, int nthreads) {
+  rgpu_stub_sync_hook = nullptr;
+  for (long long b = 0; b < nblocks; b++)
+    for (int t = 0; t < nthreads; t++) {
+      threadIdx = {(unsigned)t, 0, 0}; blockIdx = {(unsigned)b, 0, 0};
+      blockDim = {(unsigned)nthreads, 1, 1}; gridDim = {(unsigned)nblocks, 1, 1};
+      kernel(a);
+    }
 }
 
 static Phys make_phys(double gamma, double smallr, double smallc, double slope_theta, double courant_factor, int slope_type,
@@ -277,6 +287,38 @@ void devnum_mhd_emf(int solver2d, int n, const double* qLL, const double* qRL, c
     }
     emf[i] = (double)e;
   }
+}
+
+// the six passes of the dense MHD sweep (mhd_dense.cuh) in the order of launch_mhd_sweep (mhd_inst_misc.cu) on a periodic cube
+// of N^3 cells: uin/uout in the device layout [11][8][nslot] (cell_offset of sweep_dense.cuh), N even
+void devnum_mhd_sweep(int N, int r1d, int r2d, int sl, const double* uin, double* uout, double dt, double dx, double gamma,
+                      double smallr, double smallc, int slope_type, int slope_mag_type) {
+  MhdArgs a;
+  std::memset(&a, 0, sizeof a);
+  DenseGeom& g = a.g;
+  g.nox = g.noy = g.noz = N / 2; g.ncx = g.ncy = g.ncz = N;
+  g.ox0 = g.oy0 = g.oz0 = 0; g.ox1 = g.oy1 = g.oz1 = N;
+  g.wrapx = g.wrapy = g.wrapz = 1;
+  g.nslot = (long long)(N / 2) * (N / 2) * (N / 2);
+  a.uin = uin; a.uout = uout;
+  a.P = make_mphys(gamma, smallr, smallc);
+  a.P.slope_type = slope_type; a.P.slope_mag_type = slope_mag_type;
+  a.dt_dev = &dt; a.dx = dx; a.nc = (long long)N * N * N;
+  std::vector<double> W((size_t)MW_NCOMP * a.nc, 0.0), part(5 * 64, 0.0);
+  a.W = W.data(); a.part = part.data();
+  const long long nb256 = (a.nc + 255) / 256, nb128 = (a.nc + 127) / 128;
+  emulate_serial(mhd_prim_kernel, a, nb256, 256);
+  emulate_serial(mhd_efield_kernel, a, nb256, 256);
+  if (sl) emulate_serial(mhd_trace_kernel<true>, a, nb256, 256); else emulate_serial(mhd_trace_kernel<false>, a, nb256, 256);
+#define FLUX(R)                                                                                   \
+  case R: if (sl) emulate_serial(mhd_flux_kernel<R, true, 2>, a, nb128, 128); else emulate_serial(mhd_flux_kernel<R, false, 2>, a, nb128, 128); break;
+  switch (r1d) { FLUX(MHD_LLF) FLUX(MHD_ROE) FLUX(MHD_HLL) FLUX(MHD_HLLD) FLUX(MHD_UPWIND) FLUX(MHD_HYDRO) }
+#undef FLUX
+#define EMF(R)                                                                                    \
+  case R: if (sl) emulate_serial(mhd_emf_kernel<R, true, 2>, a, nb128, 128); else emulate_serial(mhd_emf_kernel<R, false, 2>, a, nb128, 128); break;
+  switch (r2d) { EMF(MHD2D_LLF) EMF(MHD2D_ROE) EMF(MHD2D_UPWIND) EMF(MHD2D_HLL) EMF(MHD2D_HLLA) EMF(MHD2D_HLLD) }
+#undef EMF
+  emulate_serial(mhd_update_kernel, a, 8, 256);
 }
 
 void devnum_mhd_cmpdt(int n, const double* u, double dx, double* dt, double gamma, double smallr, double smallc, double cfl) {

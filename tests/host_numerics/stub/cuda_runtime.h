@@ -2,6 +2,7 @@
 // (hydro_device.cuh, real64.cuh, mhd_device.cuh) as ordinary C++ so that their formulas can be compared with the oracle on a
 // machine without a GPU.  Test harness only -- nothing in the product includes this file.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #define __device__
@@ -9,6 +10,8 @@
 #define __global__
 #define __forceinline__ inline
 using std::copysign;
+using std::max;
+using std::min;
 using std::fabs;
 using std::fmax;
 using std::fmin;

@@ -382,3 +382,41 @@ def test_amr_oct_batch_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, 
             moved = max(moved, float(np.abs(Uo[:, c] - r.uold.reshape(nvar, r.ncell)[:, c]).max()))
         nlev += 1
     assert nlev >= 3 and moved > 1e-6
+
+
+def _to_slots(dense, N):
+    """dense [11][z][y][x] -> device layout [11][8][nslot] (cell_offset of sweep_dense.cuh, periodic cube, no ghost shell)"""
+    h = N // 2
+    z, y, x = np.meshgrid(np.arange(N), np.arange(N), np.arange(N), indexing="ij")
+    ind = (x & 1) | ((y & 1) << 1) | ((z & 1) << 2)
+    slot = (x >> 1) + h * ((y >> 1) + h * (z >> 1))
+    u = np.zeros((11, 8, h ** 3))
+    u[:, ind.ravel(), slot.ravel()] = dense.reshape(11, -1)
+    return u, ind, slot
+
+
+@pytest.mark.parametrize("r1d,r2d,st", [("roe", "llf", 0), ("hlld", "hlld", 1), ("llf", "llf", 2), ("hll", "hll", 1), ("hlld", "roe", 2),
+                                        ("upwind", "upwind", 1), ("hydro", "hlla", 1)])
+def test_mhd_six_pass_kernels_emulated_on_the_cpu_equal_oracle(orc, dev, r1d, r2d, st):
+    """the six MHD kernels of mhd_dense.cuh (prim, efield, trace, flux, emf, update) executed thread by thread on the CPU in the
+    order of launch_mhd_sweep, on a periodic 12^3 box in the device's slot layout: the new state equals set_unew + godunov_fine
+    (fluxes, corner EMFs, constrained-transport update of both copies of every face) of the oracle, bit for bit"""
+    from helpers import MhdCase, mhd_smooth_state
+    dp = C.POINTER(C.c_double)
+    dev.devnum_mhd_sweep.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double, C.c_double, C.c_double,
+                                     C.c_double, C.c_int, C.c_int]
+    N, level = 16, 4
+    c = MhdCase(level, riemann=r1d, riemann2d=r2d, slope_type=st)
+    d0 = mhd_smooth_state(N)
+    c.init_dense(d0)
+    dt, _ = c.oracle_courant()
+    dt *= 0.7
+    ref = c.dense(c.oracle_godunov(dt, nthreads=2))
+    uin, ind, slot = _to_slots(c.dense(), N)
+    uout = np.zeros_like(uin)
+    sl = 0 if st == 0 else 1
+    dev.devnum_mhd_sweep(N, orc.MHD_RIEMANN[r1d], orc.MHD_RIEMANN2D[r2d], sl, orc.dptr(np.ascontiguousarray(uin)), orc.dptr(uout),
+                         dt, 1.0 / N, c.p.gamma, c.p.smallr, c.p.smallc, st, st)
+    got = uout[:, ind.ravel(), slot.ravel()].reshape(11, N, N, N)
+    assert np.abs(ref - c.dense()).max() > 1e-4
+    assert np.array_equal(got, ref)
