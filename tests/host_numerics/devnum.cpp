@@ -18,21 +18,30 @@ static pthread_barrier_t g_block_barrier;
 static void block_barrier() { pthread_barrier_wait(&g_block_barrier); }
 
 template <class Kernel, class Args>
-static void emulate_launch(Kernel kernel, const Args& a, int nblocks, int nthreads) {
+static void emulate_launch(Kernel kernel, const Args& a, int nblocks, int bx, int by = 1, size_t dyn_smem_doubles = 0) {
+  const int nthreads = bx * by, nwarps = (nthreads + 31) / 32;
   pthread_barrier_init(&g_block_barrier, nullptr, (unsigned)nthreads);
   rgpu_stub_sync_hook = block_barrier;
+  const bool warps = (nthreads % 32 == 0);             // warp exchange needs full warps
+  if (warps) for (int w = 0; w < nwarps; w++) pthread_barrier_init(&rgpu_stub_warp_bar[w], nullptr, 32);
+  rgpu_stub_warp_on = warps;
+  std::vector<double> dyn(dyn_smem_doubles + 1, 0.0);
+  rgpu_host_dyn_smem = dyn.data();
   std::vector<std::thread> team;
   for (int t = 0; t < nthreads; t++)
     team.emplace_back([&, t] {
       for (int b = 0; b < nblocks; b++) {
-        threadIdx = {(unsigned)t, 0, 0}; blockIdx = {(unsigned)b, 0, 0};
-        blockDim = {(unsigned)nthreads, 1, 1}; gridDim = {(unsigned)nblocks, 1, 1};
+        threadIdx = {(unsigned)(t % bx), (unsigned)(t / bx), 0}; blockIdx = {(unsigned)b, 0, 0};
+        blockDim = {(unsigned)bx, (unsigned)by, 1}; gridDim = {(unsigned)nblocks, 1, 1};
         kernel(a);
         pthread_barrier_wait(&g_block_barrier);      // the next block reuses the __shared__ storage
       }
     });
   for (auto& th : team) th.join();
   rgpu_stub_sync_hook = nullptr;
+  rgpu_stub_warp_on = false;
+  rgpu_host_dyn_smem = nullptr;
+  if (warps) for (int w = 0; w < nwarps; w++) pthread_barrier_destroy(&rgpu_stub_warp_bar[w]);
   pthread_barrier_destroy(&g_block_barrier);
 }
 
@@ -319,6 +328,44 @@ void devnum_mhd_sweep(int N, int r1d, int r2d, int sl, const double* uin, double
   switch (r2d) { EMF(MHD2D_LLF) EMF(MHD2D_ROE) EMF(MHD2D_UPWIND) EMF(MHD2D_HLL) EMF(MHD2D_HLLA) EMF(MHD2D_HLLD) }
 #undef EMF
   emulate_serial(mhd_update_kernel, a, 8, 256);
+}
+
+// the fused dense-box sweep (sweep_dense_kernel: persistent CTAs of 32 x BY threads, cp.async staging, warp shuffles in x, shared
+// memory exchange in y, plane carry in z, fused set_unew / update / set_uold / Courant scan) on a periodic box of N^ndim cells,
+// state in the device layout [nvar][2^ndim][nslot]; nblocks persistent CTAs share the work like on the GPU
+int devnum_sweep_dense(int ndim, int solver, int N, int nblocks, const double* uin, double* uout, double dt, double dx,
+                        int slope_type, double slope_theta, double gamma, double smallr, double smallc, int niter, double* part) {
+  SweepArgs a;
+  std::memset(&a, 0, sizeof a);
+  DenseGeom& g = a.g;
+  g.nox = N / 2; g.noy = ndim > 1 ? N / 2 : 1; g.noz = ndim > 2 ? N / 2 : 1;
+  g.ncx = N; g.ncy = ndim > 1 ? N : 1; g.ncz = ndim > 2 ? N : 1;
+  g.ox0 = g.oy0 = g.oz0 = 0; g.ox1 = N; g.oy1 = ndim > 1 ? N : 1; g.oz1 = ndim > 2 ? N : 1;
+  g.wrapx = 1; g.wrapy = ndim > 1; g.wrapz = ndim > 2;
+  g.nslot = (long long)g.nox * g.noy * g.noz;
+  a.uin = uin; a.uout = uout;
+  a.P = make_phys(gamma, smallr, smallc, slope_theta, 0.8, slope_type, niter);
+  a.dt_dev = nullptr; a.dt_val = dt; a.dx = dx; a.inv_dx = 1.0 / dx;
+  int ex;
+  a.dx_pow2 = (std::frexp(dx, &ex) == 0.5) ? 1 : 0;
+  const int by = tile_by_default(ndim, solver);
+  const int txo = 30, tyo = ndim > 1 ? by - 2 : 1;                          // rgpu_bind_level (rgpu_api.cu)
+  a.ntx = (g.ox1 - g.ox0 + txo - 1) / txo;
+  a.nty = ndim > 1 ? (g.oy1 - g.oy0 + tyo - 1) / tyo : 1;
+  a.nwork = (long long)a.ntx * a.nty * (ndim > 2 ? (g.oz1 - g.oz0) : 1);
+  if (nblocks > a.nwork) nblocks = (int)a.nwork;
+  a.part = part; a.refined = nullptr;
+#define SW(ND, RS, BY) emulate_launch(sweep_dense_kernel<ND, RS, -1, 32, BY, false>, a, nblocks, 32, BY, SweepSmem<ND, 32, BY>::doubles)
+#define SW_ND(ND, BY)                                                                                    \
+  do {                                                                                                   \
+    if (solver == RIEMANN_LLF) SW(ND, RIEMANN_LLF, BY); else if (solver == RIEMANN_EXACT) SW(ND, RIEMANN_EXACT, BY);   \
+    else if (solver == RIEMANN_ACOUSTIC) SW(ND, RIEMANN_ACOUSTIC, BY); else if (solver == RIEMANN_HLLC) SW(ND, RIEMANN_HLLC, BY); \
+    else SW(ND, RIEMANN_HLL, BY);                                                                        \
+  } while (0)
+  if (ndim == 1) SW_ND(1, 1); else if (ndim == 2) SW_ND(2, 8); else SW_ND(3, 12);
+#undef SW_ND
+#undef SW
+  return nblocks;   // CTAs actually used: part is [4][nblocks]
 }
 
 void devnum_mhd_cmpdt(int n, const double* u, double dx, double* dt, double gamma, double smallr, double smallc, double cfl) {

@@ -420,3 +420,60 @@ def test_mhd_six_pass_kernels_emulated_on_the_cpu_equal_oracle(orc, dev, r1d, r2
     got = uout[:, ind.ravel(), slot.ravel()].reshape(11, N, N, N)
     assert np.abs(ref - c.dense()).max() > 1e-4
     assert np.array_equal(got, ref)
+
+
+def _hydro_to_slots(dense, ndim, N):
+    """dense [nvar][z][y][x] (unused dimensions of extent 1) -> device layout [nvar][2^ndim][nslot]"""
+    nvar = ndim + 2
+    shp = [N if d < ndim else 1 for d in range(3)]            # x, y, z extents
+    z, y, x = np.meshgrid(np.arange(shp[2]), np.arange(shp[1]), np.arange(shp[0]), indexing="ij")
+    h = [max(s // 2, 1) for s in shp]
+    ind = (x & 1)
+    slot = (x >> 1)
+    if ndim > 1:
+        ind = ind | ((y & 1) << 1)
+        slot = slot + h[0] * (y >> 1)
+    if ndim > 2:
+        ind = ind | ((z & 1) << 2)
+        slot = slot + h[0] * h[1] * (z >> 1)
+    nslot = h[0] * (h[1] if ndim > 1 else 1) * (h[2] if ndim > 2 else 1)
+    u = np.zeros((nvar, 1 << ndim, nslot))
+    u[:, ind.ravel(), slot.ravel()] = dense.reshape(nvar, -1)
+    return u, ind, slot
+
+
+@pytest.mark.parametrize("ndim,solver,st,N,nblocks", [(3, "hllc", 1, 16, 3), (3, "exact", 2, 16, 2), (3, "llf", 8, 16, 5), (2, "hllc", 2, 32, 3),
+                                                      (2, "hll", 7, 32, 1), (1, "acoustic", 1, 64, 2), (3, "hllc", 3, 16, 4)])
+def test_dense_sweep_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, solver, st, N, nblocks):
+    """sweep_dense_kernel -- THE hot kernel: persistent CTAs of 32 x BY threads, cp.async staging of the next plane, the ring of
+    primitive planes in shared memory, warp shuffles for the x neighbours, shared-memory exchange for y, per-thread carry for z,
+    fused set_unew + update + set_uold + Courant scan -- executed on the CPU by the emulated launch (one OS thread per CUDA
+    thread, block barrier, per-warp shuffle exchange) for several persistent-grid sizes: the new state equals one level step of
+    the oracle bit for bit, and the fused Courant partials reproduce the next time step."""
+    dp = C.POINTER(C.c_double)
+    dev.devnum_sweep_dense.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double, C.c_int, C.c_double,
+                                       C.c_double, C.c_double, C.c_double, C.c_int, dp]
+    from helpers import Case, smooth_state
+    level = int(np.log2(N))
+    c = Case(ndim, level, riemann=solver, slope_type=st, slope_theta=1.3)
+    d0 = smooth_state(ndim, N)
+    rough = np.random.default_rng(3).standard_normal(d0[0].shape)
+    d0[0] *= 1 + 0.3 * (rough > 1.2)
+    c.init_dense(d0)
+    dt, _ = c.oracle_courant()
+    unew = c.oracle_godunov(dt, nthreads=1)
+    ref = c.dense(unew)
+    dt_next, sums = c.oracle_courant(unew)
+    uin, ind, slot = _hydro_to_slots(c.dense(), ndim, N)
+    uout = np.zeros_like(uin)
+    part = np.zeros(4 * 64)
+    sid = {"llf": 0, "exact": 1, "acoustic": 2, "hllc": 3, "hll": 4}[solver]
+    nb = dev.devnum_sweep_dense(ndim, sid, N, nblocks, orc.dptr(np.ascontiguousarray(uin)), orc.dptr(uout), dt, 1.0 / N, st, 1.3, 1.4,
+                                1e-10, 1e-10, 10, orc.dptr(part))
+    got = uout[:, ind.ravel(), slot.ravel()].reshape(ref.shape)
+    assert np.abs(ref - c.dense()).max() > 1e-4
+    assert np.array_equal(got, ref)
+    p4 = part[:4 * nb].reshape(4, nb)                      # fused courant_fine of the new state: min dt, mass, etot, eint per CTA
+    assert p4[0].min() * 1.0 == dt_next or min(p4[0].min(), c.p.boxlen / c.p.smallc) == dt_next
+    vol = (1.0 / N) ** ndim
+    assert abs(p4[1].sum() * vol - sums[0]) <= 1e-13 * abs(sums[0]) and abs(p4[2].sum() * vol - sums[1]) <= 1e-13 * abs(sums[1])
