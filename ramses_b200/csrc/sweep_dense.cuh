@@ -127,8 +127,12 @@ struct SweepSmem {
   static constexpr size_t doubles = ring + stage + exq + exf + carry;
 };
 
-template <int NDIM, int RIEMANN, int SLOPE, int BX, int BY, bool AMRV = false>
+// LATE (experimental, not dispatched by the product yet; exercised by tests/host_numerics): the x/y part of the update of plane k
+// is finished after the FIRST barrier of plane k+1 instead of after a third barrier of its own -- the y fluxes of the row above
+// are complete by then -- so the plane loop has two CTA barriers instead of three.  Same arithmetic in the same order.
+template <int NDIM, int RIEMANN, int SLOPE, int BX, int BY, bool AMRV = false, bool LATE = false>
 __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs a) {
+  static_assert(!(LATE && AMRV), "the late-update variant exists for the plain dense sweep only");
   using S = SweepSmem<NDIM, BX, BY>;
   constexpr int NV = S::NV, HY = S::HY, HZ = S::HZ, QX = S::QX, QY = S::QY, NQ = S::NQ, NT = S::NT;
   constexpr int TXO = BX - 2;                 // owned cells per tile in x
@@ -263,12 +267,27 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
     }
     const int kbeg = HZ ? z0 - 1 : 0, kend = HZ ? z1 : 0;
     int mprev = 0;                             // AMRV: refined flag of my cell in the previous plane
+    // LATE: uold + (Fx - Fx') and my own y flux of the pending plane.  3-D: both live in per-thread shared-memory slots (the
+    // partial-update slot of `carry`, and NV*NT doubles behind `carry`: the launch must add them to the dynamic shared memory);
+    // 1-D / 2-D: the single plane keeps them in registers
+    double late_p1[(LATE && !HZ) ? NV : 1], late_fy[(LATE && !HZ) ? NV : 1];
+    double* late_fys = carry + S::carry;
+    bool late_pend = false;
     for (int k = kbeg; k <= kend; k++) {
       const int c = k - kbeg;
       const int sm1 = HZ ? c % 3 : 0, sc = HZ ? (c + 1) % 3 : 0, sp1 = HZ ? (c + 2) % 3 : 0;
       if (HZ) stage_to_ring(sp1); else load_plane_direct(0, 0);
       __syncthreads();
       if (HZ && k < kend) stage_plane_async(k + 2);
+      if (LATE && HZ && late_pend) {           // y part of the update of plane k-1: every warp has written its Fy(k-1) by now
+#pragma unroll
+        for (int n = 0; n < NV; n++) {
+          double u = carry[(2 * NV + n) * NT + tid];
+          if (HY) u = u + (late_fys[n * NT + tid] - exf[n * NT + tid + BX]);
+          carry[(2 * NV + n) * NT + tid] = u;
+        }
+        late_pend = false;
+      }
 
       const int qx = tx + 1, qy = HY ? ty + 1 : 0;
       const double* qc = qring + (size_t)sc * NQ * PL + qy * QX + qx;   // + n*PL
@@ -484,7 +503,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
       double fxr[NV];
 #pragma unroll
       for (int n = 0; n < NV; n++) fxr[n] = __shfl_down_sync(0xffffffffu, fx[n], 1);
-      __syncthreads();
+      if (!LATE) __syncthreads();
 
       // ---- conservative update (godfine1, hydro/godunov_fine.f90:751-792): x, then y, then z ----
       if (own) {
@@ -501,7 +520,17 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
             for (int n = 0; n < NV; n++) carry[(NV + n) * NT + tid] = fz[n];
           }
         }
-        if (plane_flux) {
+        if (plane_flux && LATE) {
+#pragma unroll
+          for (int n = 0; n < NV; n++) {
+            double u = ucur[n];
+            u = u + (fx[n] - fxr[n]);
+            if (HZ) { carry[(2 * NV + n) * NT + tid] = u; late_fys[n * NT + tid] = fy[n]; }
+            else { late_p1[(LATE && !HZ) ? n : 0] = u; late_fy[(LATE && !HZ) ? n : 0] = fy[n]; }
+          }
+          late_pend = true;
+        }
+        if (plane_flux && !LATE) {
 #pragma unroll
           for (int n = 0; n < NV; n++) {
             double u = ucur[n];
@@ -523,6 +552,27 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
           my_etot += unew_[NDIM + 1];
           my_eint += ei;
         }
+      }
+    }
+    if (LATE && !HZ) {                         // 1-D / 2-D: the only plane is finished after one more barrier
+      __syncthreads();
+      if (own && late_pend) {
+        double unew_[NV];
+#pragma unroll
+        for (int n = 0; n < NV; n++) {
+          double u = late_p1[(LATE && !HZ) ? n : 0];
+          if (HY) u = u + (late_fy[(LATE && !HZ) ? n : 0] - exf[n * NT + tid + BX]);
+          unew_[n] = u;
+        }
+        const long long off = cell_offset<NDIM>(g, cx, cy, 0);
+#pragma unroll
+        for (int n = 0; n < NV; n++) a.uout[n * vstride + off] = unew_[n];
+        double ei;
+        const double dtc = cmpdt_cell<NDIM>(unew_, a.dx, P, ei);
+        my_dt = dtc < my_dt ? dtc : my_dt;
+        my_mass += unew_[0];
+        my_etot += unew_[NDIM + 1];
+        my_eint += ei;
       }
     }
   }

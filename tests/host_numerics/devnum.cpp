@@ -334,7 +334,8 @@ void devnum_mhd_sweep(int N, int r1d, int r2d, int sl, const double* uin, double
 // memory exchange in y, plane carry in z, fused set_unew / update / set_uold / Courant scan) on a periodic box of N^ndim cells,
 // state in the device layout [nvar][2^ndim][nslot]; nblocks persistent CTAs share the work like on the GPU
 int devnum_sweep_dense(int ndim, int solver, int N, int nblocks, const double* uin, double* uout, double dt, double dx,
-                        int slope_type, double slope_theta, double gamma, double smallr, double smallc, int niter, double* part) {
+                        int slope_type, double slope_theta, double gamma, double smallr, double smallc, int niter, double* part,
+                        int late) {
   SweepArgs a;
   std::memset(&a, 0, sizeof a);
   DenseGeom& g = a.g;
@@ -355,7 +356,11 @@ int devnum_sweep_dense(int ndim, int solver, int N, int nblocks, const double* u
   a.nwork = (long long)a.ntx * a.nty * (ndim > 2 ? (g.oz1 - g.oz0) : 1);
   if (nblocks > a.nwork) nblocks = (int)a.nwork;
   a.part = part; a.refined = nullptr;
-#define SW(ND, RS, BY) emulate_launch(sweep_dense_kernel<ND, RS, -1, 32, BY, false>, a, nblocks, 32, BY, SweepSmem<ND, 32, BY>::doubles)
+#define SW(ND, RS, BY)                                                                                                            \
+  do {                                                                                                                           \
+    if (late) emulate_launch(sweep_dense_kernel<ND, RS, -1, 32, BY, false, true>, a, nblocks, 32, BY, SweepSmem<ND, 32, BY>::doubles + (ND + 2) * 32 * BY); \
+    else emulate_launch(sweep_dense_kernel<ND, RS, -1, 32, BY, false, false>, a, nblocks, 32, BY, SweepSmem<ND, 32, BY>::doubles); \
+  } while (0)
 #define SW_ND(ND, BY)                                                                                    \
   do {                                                                                                   \
     if (solver == RIEMANN_LLF) SW(ND, RIEMANN_LLF, BY); else if (solver == RIEMANN_EXACT) SW(ND, RIEMANN_EXACT, BY);   \

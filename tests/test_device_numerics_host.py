@@ -442,17 +442,19 @@ def _hydro_to_slots(dense, ndim, N):
     return u, ind, slot
 
 
+@pytest.mark.parametrize("late", [0, 1])
 @pytest.mark.parametrize("ndim,solver,st,N,nblocks", [(3, "hllc", 1, 16, 3), (3, "exact", 2, 16, 2), (3, "llf", 8, 16, 5), (2, "hllc", 2, 32, 3),
                                                       (2, "hll", 7, 32, 1), (1, "acoustic", 1, 64, 2), (3, "hllc", 3, 16, 4)])
-def test_dense_sweep_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, solver, st, N, nblocks):
+def test_dense_sweep_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, solver, st, N, nblocks, late):
     """sweep_dense_kernel -- THE hot kernel: persistent CTAs of 32 x BY threads, cp.async staging of the next plane, the ring of
     primitive planes in shared memory, warp shuffles for the x neighbours, shared-memory exchange for y, per-thread carry for z,
     fused set_unew + update + set_uold + Courant scan -- executed on the CPU by the emulated launch (one OS thread per CUDA
     thread, block barrier, per-warp shuffle exchange) for several persistent-grid sizes: the new state equals one level step of
-    the oracle bit for bit, and the fused Courant partials reproduce the next time step."""
+    the oracle bit for bit, and the fused Courant partials reproduce the next time step.  late=1: the experimental two-barrier
+    variant of the plane loop (template parameter LATE, not dispatched by the product yet) gives the same bits."""
     dp = C.POINTER(C.c_double)
     dev.devnum_sweep_dense.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double, C.c_int, C.c_double,
-                                       C.c_double, C.c_double, C.c_double, C.c_int, dp]
+                                       C.c_double, C.c_double, C.c_double, C.c_int, dp, C.c_int]
     from helpers import Case, smooth_state
     level = int(np.log2(N))
     c = Case(ndim, level, riemann=solver, slope_type=st, slope_theta=1.3)
@@ -469,7 +471,7 @@ def test_dense_sweep_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, so
     part = np.zeros(4 * 64)
     sid = {"llf": 0, "exact": 1, "acoustic": 2, "hllc": 3, "hll": 4}[solver]
     nb = dev.devnum_sweep_dense(ndim, sid, N, nblocks, orc.dptr(np.ascontiguousarray(uin)), orc.dptr(uout), dt, 1.0 / N, st, 1.3, 1.4,
-                                1e-10, 1e-10, 10, orc.dptr(part))
+                                1e-10, 1e-10, 10, orc.dptr(part), late)
     got = uout[:, ind.ravel(), slot.ravel()].reshape(ref.shape)
     assert np.abs(ref - c.dense()).max() > 1e-4
     assert np.array_equal(got, ref)
