@@ -373,6 +373,31 @@ int devnum_sweep_dense(int ndim, int solver, int N, int nblocks, const double* u
   return nblocks;   // CTAs actually used: part is [4][nblocks]
 }
 
+// the AMR variant of the dense sweep (AMRV=true: fluxes through faces of refined cells reset to zero, the update ACCUMULATES into
+// uout which already holds unew) on a fully refined periodic level of N^3 cells; refined[8][nslot] = son(cell)>0
+void devnum_sweep_dense_amr(int solver, int N, int nblocks, const double* uin, double* uout, const unsigned char* refined, double dt,
+                            double dx, int slope_type, double gamma, double smallr, double smallc, int niter) {
+  SweepArgs a;
+  std::memset(&a, 0, sizeof a);
+  DenseGeom& g = a.g;
+  g.nox = g.noy = g.noz = N / 2; g.ncx = g.ncy = g.ncz = N;
+  g.ox0 = g.oy0 = g.oz0 = 0; g.ox1 = g.oy1 = g.oz1 = N;
+  g.wrapx = g.wrapy = g.wrapz = 1;
+  g.nslot = (long long)(N / 2) * (N / 2) * (N / 2);
+  a.uin = uin; a.uout = uout; a.refined = refined;
+  a.P = make_phys(gamma, smallr, smallc, 1.5, 0.8, slope_type, niter);
+  a.dt_dev = nullptr; a.dt_val = dt; a.dx = dx; a.inv_dx = 1.0 / dx;
+  int ex;
+  a.dx_pow2 = (std::frexp(dx, &ex) == 0.5) ? 1 : 0;
+  a.ntx = (N + 29) / 30; a.nty = (N + 9) / 10; a.nwork = (long long)a.ntx * a.nty * N;
+  if (nblocks > a.nwork) nblocks = (int)a.nwork;
+  a.part = nullptr;
+#define SWA(RS) emulate_launch(sweep_dense_kernel<3, RS, -1, 32, 12, true, false>, a, nblocks, 32, 12, SweepSmem<3, 32, 12>::doubles)
+  if (solver == RIEMANN_LLF) SWA(RIEMANN_LLF); else if (solver == RIEMANN_EXACT) SWA(RIEMANN_EXACT);
+  else if (solver == RIEMANN_ACOUSTIC) SWA(RIEMANN_ACOUSTIC); else if (solver == RIEMANN_HLLC) SWA(RIEMANN_HLLC); else SWA(RIEMANN_HLL);
+#undef SWA
+}
+
 void devnum_mhd_cmpdt(int n, const double* u, double dx, double* dt, double gamma, double smallr, double smallc, double cfl) {
   MPhys M = make_mphys(gamma, smallr, smallc);
   M.courant_factor = cfl;

@@ -479,3 +479,53 @@ def test_dense_sweep_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, so
     assert p4[0].min() * 1.0 == dt_next or min(p4[0].min(), c.p.boxlen / c.p.smallc) == dt_next
     vol = (1.0 / N) ** ndim
     assert abs(p4[1].sum() * vol - sums[0]) <= 1e-13 * abs(sums[0]) and abs(p4[2].sum() * vol - sums[1]) <= 1e-13 * abs(sums[1])
+
+
+@pytest.mark.parametrize("solver", ["hllc", "llf"])
+def test_dense_sweep_amr_variant_emulated_on_the_cpu_equals_oracle(orc, dev, solver):
+    """sweep_dense_kernel<..., AMRV=true>: the fully refined base level of an AMR run (part of its cells refined further) swept by
+    the dense kernel -- flux masks of refined cells passed by shuffle (x), shared memory (y) and the plane carry (z), update
+    accumulated into unew -- equals godfine1 of the oracle on that level, bit for bit"""
+    from oracle.amr import FastAmrRun
+    dp = C.POINTER(C.c_double)
+    dev.devnum_sweep_dense_amr.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_ubyte), C.c_double, C.c_double, C.c_int,
+                                           C.c_double, C.c_double, C.c_double, C.c_int]
+    reg = [dict(type="square", x_center=0.5, y_center=0.5, z_center=0.5, length_x=10, length_y=10, length_z=10, exp_region=10, d=1.0, p=1e-5),
+           dict(type="point", x_center=0.5, y_center=0.5, z_center=0.5, p=0.4)]
+    r = FastAmrRun(3, 4, 5, (0,) * 6, 1.0, nsubcycle=[1, 2], ngridmax=6000, riemann=solver, slope_type=1, err_grad_p=0.1,
+                   interpol_type=1, regions=reg, tout=[1e9])
+    r.run(max_coarse=3)
+    l, N = 4, 16
+    act = np.asarray(r.active[l], dtype=np.int64)
+    assert len(act) == 8 ** 3 and len(r.active[5]) > 0
+    L = orc.lib()
+    dt = 0.5 * r.dtnew[l]
+    unew_o = np.zeros_like(r.uold)
+    L.orc_set_unew(C.byref(r.p), r.mp, l, orc.dptr(r.uold), orc.dptr(unew_o))
+    # pretend the finer level has already refluxed into unew (the kernel must add to what is there)
+    U0 = unew_o.reshape(5, r.ncell)
+    rng = np.random.default_rng(2)
+    for ind in range(8):
+        c = r.ncoarse + ind * r.ngridmax + act - 1
+        U0[:, c] += 1e-3 * rng.standard_normal((5, len(act))) * (r.son[c + 1] == 0)
+    start = unew_o.copy()
+    L.orc_godunov_fine(C.byref(r.p), r.mp, l, dt, orc.dptr(r.uold), orc.dptr(unew_o), 1)
+    # device layout of the level: oct position -> slot
+    pos = np.rint(r.xg[:, act] * 2 ** (l - 1) - 0.5).astype(np.int64)                # oct centre = (p+0.5)/2^(l-1)
+    assert len(set(map(tuple, pos.T))) == len(act)
+    h = N // 2
+    slot = pos[0] + h * (pos[1] + h * pos[2])
+    Uold, Ust, Uref = r.uold.reshape(5, r.ncell), start.reshape(5, r.ncell), unew_o.reshape(5, r.ncell)
+    uin, uout, ref = np.zeros((5, 8, h ** 3)), np.zeros((5, 8, h ** 3)), np.zeros((5, 8, h ** 3))
+    refined = np.zeros((8, h ** 3), dtype=np.uint8)
+    for ind in range(8):
+        c = r.ncoarse + ind * r.ngridmax + act - 1
+        uin[:, ind, slot], uout[:, ind, slot], ref[:, ind, slot] = Uold[:, c], Ust[:, c], Uref[:, c]
+        refined[ind, slot] = r.son[c + 1] > 0
+    assert refined.sum() > 0
+    sid = {"llf": 0, "exact": 1, "acoustic": 2, "hllc": 3, "hll": 4}[solver]
+    uout = np.ascontiguousarray(uout)
+    dev.devnum_sweep_dense_amr(sid, N, 4, orc.dptr(np.ascontiguousarray(uin)), orc.dptr(uout),
+                               np.ascontiguousarray(refined).ctypes.data_as(C.POINTER(C.c_ubyte)), dt, 1.0 / N, 1, 1.4, 1e-10, 1e-10, 10)
+    assert np.abs(ref - uin).max() > 1e-5
+    assert np.array_equal(uout, ref)
