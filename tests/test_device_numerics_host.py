@@ -245,7 +245,8 @@ def test_unsplit_from_device_pieces_equals_oracle_unsplit(orc, dev, solver, slop
 @pytest.mark.parametrize("ndim", [1, 2, 3])
 def test_amr_tree_walks_of_the_kernels_equal_oracle(orc, dev, ndim):
     """amr_get3cubefather / amr_getnborfather (the device restatement of amr/nbors_utils.f90:5-194,404-525 used by the AMR kernels)
-    against the oracle's on an adaptively refined mesh with physical boundaries: every oct and every cell of every level"""
+    against the oracle's on an adaptively refined mesh (1-D / 2-D with physical boundaries incl. corner octs, 3-D periodic): every
+    oct and every cell of every level"""
     from oracle.amr import FastAmrRun
     if ndim == 1:
         reg = [dict(type="square", x_center=0.25, length_x=0.5, d=1.0, p=1.0), dict(type="square", x_center=0.75, length_x=0.5, d=0.125, p=0.1)]
@@ -258,7 +259,7 @@ def test_amr_tree_walks_of_the_kernels_equal_oracle(orc, dev, ndim):
     else:
         reg = [dict(type="square", x_center=0.5, y_center=0.5, z_center=0.5, length_x=10, length_y=10, length_z=10, exp_region=10, d=1.0, p=1e-5),
                dict(type="point", x_center=0.5, y_center=0.5, z_center=0.5, p=0.4)]
-        r = FastAmrRun(3, 3, 5, (0, 0, 2, 2, 1, 1), 1.0, nsubcycle=[1, 2], ngridmax=4000, riemann="hllc", slope_type=1,
+        r = FastAmrRun(3, 3, 5, (0,) * 6, 1.0, nsubcycle=[1, 2], ngridmax=4000, riemann="hllc", slope_type=1,
                        err_grad_p=0.1, interpol_type=1, regions=reg, tout=[1e9])
     r.run(max_coarse=3)
     m = r.m
