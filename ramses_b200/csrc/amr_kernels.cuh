@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
 #pragma unroll
         for (int n = 0; n < NV; n++) s.uc[DIF ? n : 0][DIF ? pc : 0] = u[n];
       }
-      const double r = fmax(u[0], P.smallr);
+      const double r = fmx(u[0], P.smallr);
       const double oneoverrho = rcp_rn(r);
       q[0] = r;
       double eken;
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
       eken = 0.5 * q[1] * q[1];
       if (NDIM > 1) { q[2] = u[2] * oneoverrho; eken = eken + 0.5 * q[2] * q[2]; }
       if (NDIM > 2) { q[3] = u[3] * oneoverrho; eken = eken + 0.5 * q[3] * q[3]; }
-      const double eint = fmax(u[NDIM + 1] * oneoverrho - eken - 0.0, P.smalle);
+      const double eint = fmx(u[NDIM + 1] * oneoverrho - eken - 0.0, P.smalle);
       q[NDIM + 1] = (P.gamma - 1.0) * r * eint;
       q[1] = q[1] + 0.0;
       if (NDIM > 1) q[2] = q[2] + 0.0;
@@ -551,9 +551,9 @@ __global__ void amr_scalar_floor_kernel(const double* __restrict__ uold, double*
   const size_t c = (size_t)ncoarse + (size_t)ind * ngridmax + igrid[o] - 1;
   const double dold = uold[c], dnew = unew[c];
   if (dold < smallr && dnew > dold) {
-    for (int iv = nhydro; iv < nvar; iv++) unew[(size_t)iv * ncell + c] = uold[(size_t)iv * ncell + c] * fmax(dnew, smallr) / smallr;
+    for (int iv = nhydro; iv < nvar; iv++) unew[(size_t)iv * ncell + c] = uold[(size_t)iv * ncell + c] * fmx(dnew, smallr) / smallr;
   } else if (dnew < smallr && dold > dnew) {
-    for (int iv = nhydro; iv < nvar; iv++) unew[(size_t)iv * ncell + c] = uold[(size_t)iv * ncell + c] * smallr / fmax(dold, smallr);
+    for (int iv = nhydro; iv < nvar; iv++) unew[(size_t)iv * ncell + c] = uold[(size_t)iv * ncell + c] * smallr / fmx(dold, smallr);
   }
 }
 // ghost-oct exchange buffers on the mirrored arrays: all variables and all cells of the listed octs in one message
@@ -585,7 +585,7 @@ __global__ void amr_upload_kernel(double* __restrict__ u, const int* __restrict_
   const int gs = son1[ic];
   if (gs <= 0) return;
   double getx = 0.0;
-  for (int is = 0; is < T; is++) getx = getx + fmax(u[(size_t)ncoarse + (size_t)is * ngridmax + gs - 1], smallr);
+  for (int is = 0; is < T; is++) getx = getx + fmx(u[(size_t)ncoarse + (size_t)is * ngridmax + gs - 1], smallr);
   u[ic - 1] = getx / (double)T;
   for (int iv = 1; iv < nvar; iv++) {
     getx = 0.0;

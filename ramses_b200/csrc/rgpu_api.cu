@@ -17,6 +17,7 @@
 #include <vector>
 #include "../../include/ramses_gpu.h"
 #include "sweep_dense.cuh"
+#include "sweep_dense3.cuh"
 #include "amr_kernels.cuh"
 #include "mhd_dense.cuh"
 
@@ -27,6 +28,10 @@ template <int NDIM, int RIEMANN> cudaError_t launch_sweep_dense(const SweepArgs&
 DECL(1, 0) DECL(1, 1) DECL(1, 2) DECL(1, 3) DECL(1, 4)
 DECL(2, 0) DECL(2, 1) DECL(2, 2) DECL(2, 3) DECL(2, 4)
 DECL(3, 0) DECL(3, 1) DECL(3, 2) DECL(3, 3) DECL(3, 4)
+#undef DECL
+// round-2 form of the 3-D sweep (sweep_dense3.cuh), instantiated in sweep3_inst_*.cu
+#define DECL(R) extern template cudaError_t launch_sweep3<R>(const SweepArgs&, int, cudaStream_t, int);
+DECL(0) DECL(1) DECL(2) DECL(3) DECL(4)
 #undef DECL
 template <int NDIM, int RIEMANN> cudaError_t launch_sweep_dense_amr(const SweepArgs& a, int nblocks, cudaStream_t st);
 #define DECL(R) extern template cudaError_t launch_sweep_dense_amr<3, R>(const SweepArgs&, int, cudaStream_t);
@@ -91,6 +96,7 @@ struct Level {
   std::vector<BoundRegion> regions;
   std::vector<PeerList> peers;
   int ntx = 0, nty = 0, nblocks = 0, by = 1;
+  int variant = 0;                   // 3-D hydro: sweep3_kernel variant (100*BY + 10*MINB + VEC); 0: round-1 kernel
   long long nwork = 0;
   double* d_part = nullptr;          // [5][part_cap]
   double* d_mhdw = nullptr;          // MHD work arrays [MW_NCOMP][ncell_box]
@@ -468,6 +474,15 @@ int launch_sweep(Level& L) {
   cudaError_t e;
   if (G.p.ndim == 1) e = dispatch_sweep_nd<1>(G.p.riemann, a, L.nblocks, G.stream, L.by);
   else if (G.p.ndim == 2) e = dispatch_sweep_nd<2>(G.p.riemann, a, L.nblocks, G.stream, L.by);
+  else if (L.variant) {
+    switch (G.p.riemann) {
+      case RGPU_RIEMANN_LLF: e = launch_sweep3<RIEMANN_LLF>(a, L.nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_EXACT: e = launch_sweep3<RIEMANN_EXACT>(a, L.nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_ACOUSTIC: e = launch_sweep3<RIEMANN_ACOUSTIC>(a, L.nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_HLLC: e = launch_sweep3<RIEMANN_HLLC>(a, L.nblocks, G.stream, L.variant); break;
+      default: e = launch_sweep3<RIEMANN_HLL>(a, L.nblocks, G.stream, L.variant); break;
+    }
+  }
   else e = dispatch_sweep_nd<3>(G.p.riemann, a, L.nblocks, G.stream, L.by);
   if (e != cudaSuccess) return fail(RGPU_ECUDA, "sweep launch: %s", cudaGetErrorString(e));
   if (G.timing) {
@@ -1148,6 +1163,15 @@ static int alloc_dense_store(Level& L, int ncpu, int nboundary, const int* bound
   const int bx = 32;
   int by = tile_by_default(nd, G.p.riemann);
   if (nd == 3) { const char* e = getenv("RGPU_BY3"); if (e) { const int v = atoi(e); if (v == 8 || v == 12 || v == 16) by = v; } }
+  int minb = 1;
+  L.variant = 0;
+  if (nd == 3 && !G.p.mhd && !G.amr) {   // plain dense 3-D sweep: round-2 kernel; RGPU_SWEEP=old|<variant> for tuning runs
+    L.variant = SWEEP3_DEFAULT_VARIANT;
+    const char* e = getenv("RGPU_SWEEP");
+    if (e) L.variant = (strcmp(e, "old") == 0) ? 0 : atoi(e);
+    if ((long long)G.nvs * T_() * nslot >= (1LL << 32)) L.variant = 0;   // sweep3_kernel addresses the state with 32-bit element indices
+    if (L.variant) { by = sweep3_by_of(L.variant); minb = (L.variant / 10) % 10; if (minb < 1) minb = 1; }
+  }
   L.by = by;
   const int txo = bx - 2, tyo = nd > 1 ? by - 2 : 1;
   L.ntx = (g.ox1 - g.ox0 + txo - 1) / txo;
@@ -1157,7 +1181,7 @@ static int alloc_dense_store(Level& L, int ncpu, int nboundary, const int* bound
   {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, G.device);
-    L.nblocks = (int)std::min<long long>(nsm, L.nwork);
+    L.nblocks = (int)std::min<long long>((long long)nsm * minb, L.nwork);
   }
   L.part_cap = std::max(L.nblocks, 148 * 8);
   if (G.p.mhd) {

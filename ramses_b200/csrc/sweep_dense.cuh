@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
     // ctoprim (hydro/umuscl.f90:861) of one cell into ring slot `slot`
     auto to_ring = [&](const double* u, int slot, int i) {
       double q[NV];
-      const double r = fmax(u[0], P.smallr);
+      const double r = fmx(u[0], P.smallr);
       const double oneoverrho = rcp_rn(r);
       q[0] = r;
       double eken;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
       eken = 0.5 * q[1] * q[1];
       if (NDIM > 1) { q[2] = u[2] * oneoverrho; eken = eken + 0.5 * q[2] * q[2]; }
       if (NDIM > 2) { q[3] = u[3] * oneoverrho; eken = eken + 0.5 * q[3] * q[3]; }
-      const double eint = fmax(u[NDIM + 1] * oneoverrho - eken - 0.0, P.smalle);
+      const double eint = fmx(u[NDIM + 1] * oneoverrho - eken - 0.0, P.smalle);
       q[NDIM + 1] = (P.gamma - 1.0) * r * eint;
       q[1] = q[1] + 0.0;                       // gravity predictor with gloc = 0 (:932-938): -0 -> +0
       if (NDIM > 1) q[2] = q[2] + 0.0;

@@ -6,6 +6,7 @@
 static double* rgpu_host_dyn_smem = nullptr;   // dynamic shared memory of an emulated launch (sweep_dense.cuh)
 #include "mhd_dense.cuh"    // the six MHD passes; pulls sweep_dense.cuh, mhd_device.cuh, hydro_device.cuh, real64.cuh
 #include "amr_kernels.cuh"  // the AMR oct-batch kernel and its __device__ tree-walk / prolongation helpers
+#include "sweep_dense3.cuh" // round-2 form of the 3-D dense sweep + the lane-generic solvers (hydro_vec.cuh)
 
 #include <pthread.h>
 #include <thread>
@@ -396,6 +397,72 @@ void devnum_sweep_dense_amr(int solver, int N, int nblocks, const double* uin, d
   if (solver == RIEMANN_LLF) SWA(RIEMANN_LLF); else if (solver == RIEMANN_EXACT) SWA(RIEMANN_EXACT);
   else if (solver == RIEMANN_ACOUSTIC) SWA(RIEMANN_ACOUSTIC); else if (solver == RIEMANN_HLLC) SWA(RIEMANN_HLLC); else SWA(RIEMANN_HLL);
 #undef SWA
+}
+
+
+// lane-generic solvers of hydro_vec.cuh: n 3-D Riemann problems through (a) the branch-free scalar form riemann_v<R,double>
+// and (b) the 3-lane form riemann_v<R,V3> (problems i, i+1, i+2 in lanes a, b, c; n must be a multiple of 3)
+void devnum_riemann_vec(int solver, int n, const double* ql, const double* qr, double* fg_scalar, double* fg_v3, double gamma,
+                        double smallr, double smallc, int niter) {
+  const Phys P = make_phys(gamma, smallr, smallc, 1.5, 0.8, 1, niter);
+  auto run1 = [&](const double* l, const double* r, double* f) {
+    switch (solver) {
+      case RIEMANN_LLF: riemann_v<RIEMANN_LLF, double>(l, r, f, P); break;
+      case RIEMANN_EXACT: riemann_v<RIEMANN_EXACT, double>(l, r, f, P); break;
+      case RIEMANN_ACOUSTIC: riemann_v<RIEMANN_ACOUSTIC, double>(l, r, f, P); break;
+      case RIEMANN_HLLC: riemann_v<RIEMANN_HLLC, double>(l, r, f, P); break;
+      default: riemann_v<RIEMANN_HLL, double>(l, r, f, P); break;
+    }
+  };
+  auto run3 = [&](const V3* l, const V3* r, V3* f) {
+    switch (solver) {
+      case RIEMANN_LLF: riemann_v<RIEMANN_LLF, V3>(l, r, f, P); break;
+      case RIEMANN_EXACT: riemann_v<RIEMANN_EXACT, V3>(l, r, f, P); break;
+      case RIEMANN_ACOUSTIC: riemann_v<RIEMANN_ACOUSTIC, V3>(l, r, f, P); break;
+      case RIEMANN_HLLC: riemann_v<RIEMANN_HLLC, V3>(l, r, f, P); break;
+      default: riemann_v<RIEMANN_HLL, V3>(l, r, f, P); break;
+    }
+  };
+  for (int i = 0; i < n; i++) run1(ql + i * 5, qr + i * 5, fg_scalar + i * 5);
+  for (int i = 0; i + 2 < n; i += 3) {
+    V3 l[5], r[5], f[5];
+    for (int k = 0; k < 5; k++) {
+      l[k] = {ql[i * 5 + k], ql[(i + 1) * 5 + k], ql[(i + 2) * 5 + k]};
+      r[k] = {qr[i * 5 + k], qr[(i + 1) * 5 + k], qr[(i + 2) * 5 + k]};
+    }
+    run3(l, r, f);
+    for (int k = 0; k < 5; k++) { fg_v3[i * 5 + k] = f[k].a; fg_v3[(i + 1) * 5 + k] = f[k].b; fg_v3[(i + 2) * 5 + k] = f[k].c; }
+  }
+}
+
+// sweep3_kernel (sweep_dense3.cuh) on a periodic box of N^3 cells, emulated launch; by in {8, 12, 16}, vec in {0, 1, 2}
+int devnum_sweep3(int solver, int N, int nblocks, const double* uin, double* uout, double dt, double dx, int slope_type,
+                  double slope_theta, double gamma, double smallr, double smallc, int niter, double* part, int by, int vec) {
+  SweepArgs a;
+  std::memset(&a, 0, sizeof a);
+  DenseGeom& g = a.g;
+  g.nox = g.noy = g.noz = N / 2; g.ncx = g.ncy = g.ncz = N;
+  g.ox0 = g.oy0 = g.oz0 = 0; g.ox1 = g.oy1 = g.oz1 = N;
+  g.wrapx = g.wrapy = g.wrapz = 1;
+  g.nslot = (long long)g.nox * g.noy * g.noz;
+  a.uin = uin; a.uout = uout;
+  a.P = make_phys(gamma, smallr, smallc, slope_theta, 0.8, slope_type, niter);
+  a.dt_dev = nullptr; a.dt_val = dt; a.dx = dx; a.inv_dx = 1.0 / dx;
+  int ex;
+  a.dx_pow2 = (std::frexp(dx, &ex) == 0.5) ? 1 : 0;
+  a.ntx = (N + 29) / 30; a.nty = (N + by - 3) / (by - 2);
+  a.nwork = (long long)a.ntx * a.nty * N;
+  if (nblocks > a.nwork) nblocks = (int)a.nwork;
+  a.part = part; a.refined = nullptr;
+#define S3(RS, BY, VEC) emulate_launch(sweep3_kernel<RS, -1, BY, 1, VEC>, a, nblocks, 32, BY, Sweep3Smem<BY>::doubles)
+#define S3V(RS, BY) do { if (vec == 0) S3(RS, BY, 0); else if (vec == 1) S3(RS, BY, 1); else S3(RS, BY, 2); } while (0)
+#define S3B(RS) do { if (by == 8) S3V(RS, 8); else if (by == 16) S3V(RS, 16); else S3V(RS, 12); } while (0)
+  if (solver == RIEMANN_LLF) S3B(RIEMANN_LLF); else if (solver == RIEMANN_EXACT) S3B(RIEMANN_EXACT);
+  else if (solver == RIEMANN_ACOUSTIC) S3B(RIEMANN_ACOUSTIC); else if (solver == RIEMANN_HLLC) S3B(RIEMANN_HLLC); else S3B(RIEMANN_HLL);
+#undef S3B
+#undef S3V
+#undef S3
+  return nblocks;
 }
 
 void devnum_mhd_cmpdt(int n, const double* u, double dx, double* dt, double gamma, double smallr, double smallc, double cfl) {

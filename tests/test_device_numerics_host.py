@@ -18,7 +18,8 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 def dev():
     lib = os.path.join(HERE, "libdevnum_host.so")
     srcs = [os.path.join(HERE, "devnum.cpp"), os.path.join(HERE, "stub", "cuda_runtime.h")] + \
-        [os.path.join(CSRC, f) for f in ("hydro_device.cuh", "real64.cuh", "mhd_device.cuh", "amr_kernels.cuh")]
+        [os.path.join(CSRC, f) for f in ("hydro_device.cuh", "real64.cuh", "mhd_device.cuh", "amr_kernels.cuh", "sweep_dense.cuh",
+                                        "sweep_dense3.cuh", "hydro_vec.cuh", "mhd_dense.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-pthread",
                                "-fvisibility=hidden", "-fvisibility-inlines-hidden", "-Wl,-Bsymbolic",
@@ -530,3 +531,62 @@ def test_dense_sweep_amr_variant_emulated_on_the_cpu_equals_oracle(orc, dev, sol
                                np.ascontiguousarray(refined).ctypes.data_as(C.POINTER(C.c_ubyte)), dt, 1.0 / N, 1, 1.4, 1e-10, 1e-10, 10)
     assert np.abs(ref - uin).max() > 1e-5
     assert np.array_equal(uout, ref)
+
+
+@pytest.mark.parametrize("solver", ["llf", "exact", "acoustic", "hllc", "hll"])
+def test_vec_solvers_equal_scalar(orc, dev, solver):
+    """hydro_vec.cuh: the branch-free scalar form and the 3-lane form of every solver == the branching scalar solver of
+    hydro_device.cuh (which the test above ties to the oracle), bit for bit on 30 000 random face states."""
+    dp = C.POINTER(C.c_double)
+    dev.devnum_riemann_vec.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int]
+    n = 30000
+    ql, qr = _hydro_states(np.random.default_rng(77 + len(solver)), n, 3)
+    # supersonic pairs in both directions (the SL>0 / SR<0 branches of hllc, spout<0 of the samplers)
+    ql[100:200, 1] = 50.0; qr[100:200, 1] = 50.0
+    ql[200:300, 1] = -50.0; qr[200:300, 1] = -50.0
+    sid = {"llf": 0, "exact": 1, "acoustic": 2, "hllc": 3, "hll": 4}[solver]
+    ref, f1, f3 = np.zeros((n, 5)), np.zeros((n, 5)), np.zeros((n, 5))
+    dev.devnum_riemann(3, sid, n, orc.dptr(ql), orc.dptr(qr), orc.dptr(ref), 1.4, 1e-10, 1e-10, 10)
+    dev.devnum_riemann_vec(sid, n, orc.dptr(ql), orc.dptr(qr), orc.dptr(f1), orc.dptr(f3), 1.4, 1e-10, 1e-10, 10)
+    assert np.isfinite(ref).all()
+    assert np.array_equal(f1, ref)
+    assert np.array_equal(f3, ref)
+
+
+@pytest.mark.parametrize("solver,st,N,nblocks,by,vec", [("hllc", 1, 16, 3, 12, 1), ("hllc", 2, 16, 2, 12, 0), ("hllc", 1, 16, 5, 12, 2),
+                                                        ("exact", 1, 16, 2, 12, 1), ("llf", 8, 16, 4, 8, 1), ("hll", 7, 16, 3, 16, 1),
+                                                        ("acoustic", 3, 16, 3, 12, 1), ("hllc", 1, 64, 7, 12, 1), ("exact", 2, 32, 5, 8, 1)])
+def test_sweep3_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, solver, st, N, nblocks, by, vec):
+    """sweep3_kernel (sweep_dense3.cuh, the round-2 form of the hot kernel: 3-lane branch-free face solves, two barriers per
+    plane, face states formed before the solve) executed on the CPU by the emulated launch: the new state equals one level
+    step of the oracle bit for bit and the fused Courant partials give the oracle's next time step; tile heights 8/12/16,
+    solver forms 0 (branching scalar), 1 (3-lane), 2 (branch-free scalar)."""
+    dp = C.POINTER(C.c_double)
+    dev.devnum_sweep3.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
+                                  C.c_double, C.c_double, C.c_int, dp, C.c_int, C.c_int]
+    from helpers import Case, smooth_state
+    if N & (N - 1):                       # not a power of two: the oracle mesh is a cube of 2^level; use a coarse grid instead
+        pytest.skip("oracle meshes are powers of two")
+    level = int(np.log2(N))
+    c = Case(3, level, riemann=solver, slope_type=st, slope_theta=1.3)
+    d0 = smooth_state(3, N)
+    rough = np.random.default_rng(3).standard_normal(d0[0].shape)
+    d0[0] *= 1 + 0.3 * (rough > 1.2)
+    c.init_dense(d0)
+    dt, _ = c.oracle_courant()
+    unew = c.oracle_godunov(dt, nthreads=1)
+    ref = c.dense(unew)
+    dt_next, sums = c.oracle_courant(unew)
+    uin, ind, slot = _hydro_to_slots(c.dense(), 3, N)
+    uout = np.zeros_like(uin)
+    part = np.zeros(4 * 64)
+    sid = {"llf": 0, "exact": 1, "acoustic": 2, "hllc": 3, "hll": 4}[solver]
+    nb = dev.devnum_sweep3(sid, N, nblocks, orc.dptr(np.ascontiguousarray(uin)), orc.dptr(uout), dt, 1.0 / N, st, 1.3, 1.4,
+                           1e-10, 1e-10, 10, orc.dptr(part), by, vec)
+    got = uout[:, ind.ravel(), slot.ravel()].reshape(ref.shape)
+    assert np.abs(ref - c.dense()).max() > 1e-4
+    assert np.array_equal(got, ref)
+    p4 = part[:4 * nb].reshape(4, nb)
+    assert p4[0].min() * 1.0 == dt_next or min(p4[0].min(), c.p.boxlen / c.p.smallc) == dt_next
+    vol = (1.0 / N) ** 3
+    assert abs(p4[1].sum() * vol - sums[0]) <= 1e-13 * abs(sums[0]) and abs(p4[2].sum() * vol - sums[1]) <= 1e-13 * abs(sums[1])
