@@ -383,9 +383,12 @@ cudaError_t launch_sweep3_v(const SweepArgs& a, int nblocks, cudaStream_t st) {
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    // all of the SM's unified L1/shared storage as shared memory: MINB CTAs must be resident together
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
+    // MINB > 1: all of the SM's unified L1/shared storage as shared memory so that MINB CTAs are resident together (costs L1:
+    // measured -9 % on the one-CTA variants, profiles/r2_tune_sweep.md)
+    if (MINB > 1) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return e;
+    }
     configured = true;
   }
   kern<<<nblocks, dim3(32, BY, 1), smem, st>>>(a);
@@ -394,20 +397,21 @@ cudaError_t launch_sweep3_v(const SweepArgs& a, int nblocks, cudaStream_t st) {
 // variant = 100*BY + 10*MINB + VEC.  The product default is SWEEP3_DEFAULT_VARIANT; the others exist for the tuning runs
 // recorded under profiles/ (RGPU_SWEEP=<variant> at bind time) and are compiled for slope_type 1 only.
 #ifndef SWEEP3_DEFAULT_VARIANT
-#define SWEEP3_DEFAULT_VARIANT 1211
+#define SWEEP3_DEFAULT_VARIANT 1212
 #endif
 constexpr int sweep3_by_of(int variant) { return variant / 100; }
 template <int RIEMANN, int SLOPE>
 cudaError_t launch_sweep3_s(const SweepArgs& a, int nblocks, cudaStream_t st, int variant) {
   switch (variant) {
-    case 1211: return launch_sweep3_v<RIEMANN, SLOPE, 12, 1, 1>(a, nblocks, st);
+    case 1212: return launch_sweep3_v<RIEMANN, SLOPE, 12, 1, 2>(a, nblocks, st);
 #ifdef SWEEP3_TUNING_VARIANTS
+    case 1211: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 12, 1, 1>(a, nblocks, st); break;
     case 1210: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 12, 1, 0>(a, nblocks, st); break;
-    case 1212: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 12, 1, 2>(a, nblocks, st); break;
     case 811: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 8, 1, 1>(a, nblocks, st); break;
     case 821: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 8, 2, 1>(a, nblocks, st); break;
     case 820: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 8, 2, 0>(a, nblocks, st); break;
     case 822: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 8, 2, 2>(a, nblocks, st); break;
+    case 1612: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 16, 1, 2>(a, nblocks, st); break;
     case 812: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 8, 1, 2>(a, nblocks, st); break;
     case 1611: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 16, 1, 1>(a, nblocks, st); break;
     case 1610: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 16, 1, 0>(a, nblocks, st); break;
