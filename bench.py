@@ -5,10 +5,12 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
 
 A "step" is one level step of a levelmin=levelmax run: courant_fine -> set_unew -> godunov_fine -> set_uold
-(-> ghost exchange -> boundaries), amr/amr_step.f90:326-514.  Workload at N=1: BASELINE.json configs[1],
-"sedov3d uniform 256^3 (levelmin=levelmax=8), exact Riemann" (namelist/sedov3d.nml with riemann='exact').
-With N ranks every rank owns one 256^3 coarse cell of an (nx,ny,nz) periodic coarse grid (weak scaling, 512^3 at
-N=8), ghost octs exchanged with ncclSend/ncclRecv.  Prints ONE JSON line on rank 0.
+(-> ghost exchange -> boundaries), amr/amr_step.f90:326-514.  Default workload: BASELINE.json configs[2], "sedov3d uniform
+512^3, HLLC" (namelist/sedov3d.nml with riemann='hllc'), the size north_star quotes its roofline target on; at N=1 the
+line also carries configs[1] (256^3, exact Riemann) under "secondary".  With N ranks every rank owns one 512^3 coarse cell
+of an (nx,ny,nz) periodic coarse grid holding a copy of the same blast (weak scaling; 1024^3 at N=8), ghost octs exchanged
+over NCCL.  After the timed steps the state is compared, bit for bit, with the single-GPU run ("check").
+Prints ONE JSON line on rank 0.
 """
 import os
 os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # CPU baseline: idle OpenMP threads must not spin on a shared host
@@ -31,6 +33,8 @@ WORKLOADS = {
     # name: (levelmax per rank cube, riemann, slope_type, ic)
     "sedov3d_256_exact": dict(level=8, riemann="exact", slope_type=1, ic="sedov"),
     "sedov3d_512_hllc": dict(level=9, riemann="hllc", slope_type=1, ic="sedov"),
+    "sedov3d_256_hllc": dict(level=8, riemann="hllc", slope_type=1, ic="sedov"),
+    "sedov3d_128_hllc": dict(level=7, riemann="hllc", slope_type=1, ic="sedov"),
     "smooth_256_hllc": dict(level=8, riemann="hllc", slope_type=1, ic="smooth"),
     "smooth_256_exact": dict(level=8, riemann="exact", slope_type=1, ic="smooth"),
     "smooth_256_llf": dict(level=8, riemann="llf", slope_type=1, ic="smooth"),
@@ -284,11 +288,12 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_reference_run(workload, steps, warmup, sample_level=7):
+def cpu_reference_run(workload, steps, warmup, sample_level=None, budget_s=60.0):
     """The reference algorithm on the host cores: oracle/ (C restatement of RAMSES, reference-shaped per-oct
-    6^3 patches, nvector=32 batches, OpenMP over batches).  The F90 itself cannot be built (no gfortran/MPI).
-    The thread count is calibrated (8, 16, ... up to all host threads) on a 64^3 step and the fastest is used:
-    the GPU hosts are shared, oversubscribed thread teams run slower than smaller ones."""
+    6^3 patches, nvector=32 batches, OpenMP over batches, gcc -O3 as BASELINE.md states).  The F90 itself cannot be built
+    (no gfortran/MPI).  Thread count: the host threads this process may run on, at most 64 (more does not scale on these
+    shared hosts; recorded in `cores`).  Grid: the workload's own grid when warmup+steps steps of it fit `budget_s` seconds
+    at the rate measured on a 64^3 probe, else the next smaller power of two (`sample` says which)."""
     from oracle import orc
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import SEDOV3D_REGIONS, smooth_state
@@ -309,17 +314,21 @@ def cpu_reference_run(workload, steps, warmup, sample_level=7):
             m.dense_to_level(smooth_state(3, 1 << level), u, level, 5)
         return m, u
     nmax = host_threads()
-    cands = sorted({min(nmax, c) for c in (8, 16, 32, 64, 128, nmax)})
+    nthr = min(nmax, 64)
     mc, uc = setup(6)
-    best, best_rate = cands[0], 0.0
-    for c in cands:
-        orc.run_uniform(p, mc, 6, 1, uc, nthreads=c)
-        t0 = time.perf_counter()
-        orc.run_uniform(p, mc, 6, 2, uc, nthreads=c)
-        rate = 2 * 64 ** 3 / (time.perf_counter() - t0)
-        if rate > best_rate:
-            best, best_rate = c, rate
-    nthr = best
+    orc.run_uniform(p, mc, 6, 1, uc, nthreads=nthr)
+    t0 = time.perf_counter()
+    orc.run_uniform(p, mc, 6, 3, uc, nthreads=nthr)
+    rate = 3 * 64 ** 3 / (time.perf_counter() - t0)
+    if sample_level is None:
+        sample_level = w["level"]
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 64e9
+        while sample_level > 6 and ((steps + warmup) * 8 ** sample_level / rate > budget_s or 8 ** sample_level * 40 * 4 > 0.5 * avail):
+            sample_level -= 1
     m, u = setup(sample_level)
     ncell = (1 << sample_level) ** 3
     if warmup:
@@ -329,10 +338,11 @@ def cpu_reference_run(workload, steps, warmup, sample_level=7):
     el = time.perf_counter() - t0
     n = 1 << sample_level
     return {"value": ncell * steps / el, "unit": "cell-updates/s", "cores": nthr, "kind": "port",
+            "same_grid_as_gpu_arm": sample_level == w["level"],
             "sample": f"{w['ic']} {n}^3 periodic, riemann={w['riemann']}, {steps} level steps "
                       f"(courant_fine+set_unew+godunov_fine+set_uold), C restatement of the RAMSES algorithm "
-                      f"(oracle/ramses_oracle.c, gcc -O2 -ffp-contract=off, OpenMP over nvector=32 oct batches); "
-                      f"{nthr} of {nmax} host threads (fastest of a calibration sweep)",
+                      f"(oracle/ramses_oracle.c, gcc -O3 -ffp-contract=off, OpenMP over nvector=32 oct batches); "
+                      f"{nthr} of {nmax} host threads",
             "seconds": el}, el / steps
 
 
@@ -378,53 +388,70 @@ def cpu_reference_run_mhd(workload, steps, warmup, sample_level=6):
             "seconds": el}, el / steps
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sedov3d_256_exact", choices=sorted(WORKLOADS))
-    ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--order", default="creation")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    w = WORKLOADS[args.workload]
-    steps, warmup = args.steps, max(args.warmup, 3)
+def pin_to_gpu_numa_node(gpu_index):
+    """Bind this process to the CPUs local to its GPU (NVML affinity) BEFORE the host arrays are allocated: first-touch then
+    places them on the GPU's NUMA node and the pinned H2D/D2H copies of the Level-0 call do not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (ncpu + 63) // 64)
+        cpus = {w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
-    # ------------------------------------------------------------------ reference arm (host cores, rank 0 only)
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        cb, sec_per_step = cpu_reference_run(args.workload, steps, warmup)
-        line = {"impl": "reference", "metric": "cell_updates_per_s", "value": cb["value"], "unit": "cell-updates/s",
-                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec_per_step * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload, "note": "each step is a bounded sample of the workload (cpu_baseline.sample)"},
-                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": cb["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
-        return 0
 
-    # ------------------------------------------------------------------ our arm
+def canonical_check(a, level, coarse, rank, dts):
+    """Size-independent identity of the run: SHA-1 of the dt history and of the conserved state in the two bottom and two top
+    oct planes of the rank's cube (all eight corners: where the periodic images of the blast arrive through the ghost exchange),
+    in (z, y, x, cell, variable) order -- independent of the oct numbering and of the decomposition.  Every rank holds the same
+    periodic problem (the blast is replicated in every coarse cell), so all ranks of an N-GPU run and the single-GPU run must
+    produce the SAME hash: bench.py compares with tests/golden/bench_hashes.json (written by a single-GPU run)."""
+    import hashlib
+    pos = a._pos[level]
+    ig0 = a._igrid0[level]
+    ig = a.active[level].astype(np.int64)
+    n1 = 1 << (level - 1)
+    nx, ny = coarse[0], coarse[1]
+    myc = np.array([rank % nx, (rank // nx) % ny, rank // (nx * ny)], dtype=np.int64)
+    pl = pos[ig - ig0] - myc[None, :] * n1
+    sel = (pl[:, 2] < 2) | (pl[:, 2] >= n1 - 2)
+    pl, igs = pl[sel], ig[sel]
+    order = np.lexsort((pl[:, 0], pl[:, 1], pl[:, 2]))
+    igs = igs[order]
+    T = a.twotondim
+    cells = (a.ncoarse + np.arange(T)[None, :] * a.ngridmax + igs[:, None] - 1).ravel()
+    blk = np.ascontiguousarray(a.uold[:, cells].T)
+    act = (a.ncoarse + np.arange(T)[:, None] * a.ngridmax + ig[None, :] - 1).ravel()
+    return {"state_sha1": hashlib.sha1(blk.tobytes()).hexdigest(), "dt_sha1": hashlib.sha1(np.asarray(dts).tobytes()).hexdigest(),
+            "mass_sum": float(a.uold[0, act].sum()), "etot_sum": float(a.uold[a.ndim + 1, act].sum()), "cells_hashed": int(len(cells))}
+
+
+GOLDEN_HASHES = os.path.join(ROOT, "tests", "golden", "bench_hashes.json")
+
+
+def dense_bench(args, workload, rank, world, local_rank, secondary=False):
+    """One levelmin=levelmax workload on `world` GPUs (one cube of 2^level cells per rank).  Returns the JSON line (rank 0) or None."""
     import torch
     from ramses_b200.hydro import HydroGPU
     from ramses_b200.tree import build_uniform_tree, coarse_dims_for_ranks, fill_state
+    dist = None
     if world > 1:
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if w.get("amr"):
-        return amr_bench(args, w, rank, world, local_rank)
+    w = WORKLOADS[workload]
+    steps, warmup = args.steps, max(args.warmup, 3)
     level = w["level"]
     coarse = coarse_dims_for_ranks(3, world)
     mhd = bool(w.get("mhd"))
     nvs = 11 if mhd else 5
     bpc = MHD_BYTES_PER_CELL if mhd else BYTES_PER_CELL
+    t_setup = time.perf_counter()
     if mhd:
         # single rank: the namelist's own box (x zero-gradient boundaries, boxlen=2); several ranks: the periodic
         # image of the same tube (one coarse cell per rank, no physical boundary) -- same work per cell
@@ -434,22 +461,25 @@ def main():
         a.gamma, a.courant_factor, a.slope_type, a.riemann, a.riemann2d = MHD_GAMMA, 0.8, w["slope_type"], w["riemann"], w["riemann2d"]
         fill_state(a, level, tube_mhd_ic(1.0, 1.5, 2.0) if world == 1 else tube_mhd_ic(0.0, 0.5 * coarse[0], float(coarse[0])))
     else:
-        boxlen = 0.5
+        # every rank owns one coarse cell = one copy of the namelist's box (boxlen 0.5 per coarse cell, so dx does not depend on
+        # N); the initial condition is replicated in every coarse cell: N copies of the same periodic problem (weak scaling)
+        boxlen = 0.5 * coarse[0]
         a = build_uniform_tree(3, level, coarse=coarse, myid=rank + 1, ncpu=world, order=args.order, boxlen=boxlen)
         a.gamma, a.courant_factor, a.slope_type, a.riemann = GAMMA, 0.8, w["slope_type"], w["riemann"]
-        fill_state(a, level, sedov_ic(boxlen, coarse[0], level) if w["ic"] == "sedov" else smooth_ic(coarse))
+        base = sedov_ic(0.5, 1, level) if w["ic"] == "sedov" else smooth_ic((1, 1, 1))
+        fill_state(a, level, lambda x, y, z: base(np.mod(x, 1.0), np.mod(y, 1.0), np.mod(z, 1.0)))
+    t_setup = time.perf_counter() - t_setup
     h = HydroGPU(a, device=local_rank)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8)
+        from ramses_b200 import lib as _l
         if rank == 0:
             buf = (C.c_ubyte * 128)()
-            from ramses_b200 import lib as _l
             _l.check(h.L.rgpu_comm_unique_id(buf))
             uid = torch.tensor(list(buf), dtype=torch.uint8)
         uid = uid.cuda()
         dist.broadcast(uid, 0)
         buf = (C.c_ubyte * 128)(*uid.cpu().tolist())
-        from ramses_b200 import lib as _l
         _l.check(h.L.rgpu_comm_init(world, rank, buf))
     h.bind_level(level)
     info0 = h.level_info(level)
@@ -467,7 +497,7 @@ def main():
         torch.cuda.synchronize()
 
     # warm-up
-    h.level_steps(level, warmup)
+    dts_w, _ = h.level_steps(level, warmup)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -489,6 +519,29 @@ def main():
         t_dev, wall = tt.tolist()
     value = ncell_total * steps / t_dev
 
+    # ---- correctness inside the bench: the state after warmup+steps level steps must be the single-GPU state, bit for bit
+    h.download_state(level)
+    check = None
+    if not mhd:
+        check = canonical_check(a, level, coarse, rank, np.concatenate([dts_w, dts]))
+        key = f"{workload}:{warmup + steps}"
+        gold = json.load(open(GOLDEN_HASHES)) if os.path.exists(GOLDEN_HASHES) else {}
+        g = gold.get(key)
+        check["golden_key"] = key
+        ok = None if g is None else (g["state_sha1"] == check["state_sha1"] and g["dt_sha1"] == check["dt_sha1"])
+        if world > 1:
+            mine = torch.tensor([int(check["state_sha1"][:15], 16), int(check["dt_sha1"][:15], 16), -1 if ok is None else int(ok)],
+                                dtype=torch.int64, device="cuda")
+            allh = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            allh = torch.stack(allh).cpu().numpy()
+            check["all_ranks_same_bits"] = bool((allh[:, :2] == allh[0, :2]).all())
+            ok = None if (allh[:, 2] < 0).any() else bool(allh[:, 2].all())
+        check["equals_single_gpu_golden"] = ok
+        if args.write_golden and world == 1:
+            gold[key] = {k: check[k] for k in ("state_sha1", "dt_sha1", "mass_sum", "etot_sum", "cells_hashed")}
+            json.dump(gold, open(GOLDEN_HASHES, "w"), indent=1, sort_keys=True)
+
     # kernel-only roofline: average duration of the sweep kernel, CUDA events around each launch
     h.set_timing(True)
     ks = []
@@ -503,63 +556,156 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = bpc * ncell_rank / (k_ms * 1e-3) / 1e9
-    traffic = None
-    tf = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tf):
-        traffic = json.load(open(tf)).get(args.workload)
+    prof = {}
+    pf = os.path.join(ROOT, "profiles", "kernel_counters.json")
+    if os.path.exists(pf):
+        prof = json.load(open(pf)).get(workload, {})
+    traffic = prof.get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": ("MHD sweep: 6 kernels (prim, efield, trace, flux<%s>, emf<%s>, update)" % (w["riemann"], w["riemann2d"]))
-                if mhd else "sweep_dense_kernel<3,%s>" % w["riemann"], "kernel_ms": k_ms,
-                "algorithmic_bytes_per_launch": bpc * ncell_rank, "peak_source": peak_src,
-                "note": "FP64 issue rate, not HBM, is the binding roof for this kernel (DESIGN.md)"
+                if mhd else "%s<3,%s>" % ("sweep3_kernel" if info0.sweep_variant else "sweep_dense_kernel", w["riemann"]),
+                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": bpc * ncell_rank, "peak_source": peak_src,
+                "note": "FP64 issue rate, not HBM, is the binding roof for this kernel (DESIGN.md); see roofline.fp64"
                         + ("; kernel_ms spans the six passes of the sweep, traffic is the dominant pass (flux)" if mhd else "")}
+    if prof.get("fp64_thread_instr_per_cell"):
+        # second roof: FP64-pipe instructions per cell-update from the ncu capture of this build (profiles/
+        # kernel_counters.json: DADD+DMUL+DFMA thread instructions / cells) against the measured DFMA issue peak of a B200
+        ipc = prof["fp64_thread_instr_per_cell"]
+        pk = prof.get("fp64_peak_thread_instr_per_s", 16.7e12)
+        ach = ipc * ncell_rank / (k_ms * 1e-3)
+        roofline["fp64"] = {"instr_per_cell": ipc, "achieved_instr_s": ach, "peak_instr_s": pk, "frac": ach / pk,
+                            "source": prof.get("source"), "peak_source": "profiles/microbench/fp64_latency_b200.txt (DFMA, ILP 8, 32 warps/SM)"}
 
     # end-to-end through the reference-facing call godunov_fine(ilevel) on HOST arrays (H2D + sweep + D2H per step)
-    h.download_state(level)
     a.dtnew[level] = float(dts[-1])      # a CFL-limited dt of this run
     a.unew[:, :] = a.uold                # boundary / ghost cells of the second host array hold valid states too
-    h.godunov_fine(level)           # warm
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        h.godunov_fine(level)
-        a.uold, a.unew = a.unew, a.uold
-    barrier()
-    e2e_t = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_t = tt.item()
     info = h.level_info(level)
     gspan = info.nslot        # contiguous igrid window of the level on this rank
-    e2e = {"value": ncell_total * args.e2e_steps / e2e_t, "unit": "cell-updates/s",
-           "h2d_bytes_per_step": int(nvs * 8 * gspan * 8), "d2h_bytes_per_step": int(nvs * 8 * gspan * 8),
-           "steps": args.e2e_steps, "api": "rgpu_godunov_fine(ilevel, dt, uold_host, unew_host), pinned host arrays"}
+
+    def time_e2e(nrep):
+        h.godunov_fine(level)           # warm
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            h.godunov_fine(level)
+            a.uold, a.unew = a.unew, a.uold
+        barrier()
+        el = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([el], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            el = tt.item()
+        return ncell_total * nrep / el
+    e2e_v = time_e2e(args.e2e_steps)
+    e2e = {"value": e2e_v, "unit": "cell-updates/s",
+           "h2d_bytes_per_step": int(nvs * 8 * gspan * 8), "d2h_bytes_per_step": int(nvs * 8 * ncell_rank),
+           "steps": args.e2e_steps, "api": "rgpu_godunov_fine(ilevel, dt, uold_host, unew_host), pinned host arrays",
+           "pipeline_slabs": int(info.pipeline_slabs),
+           "mode": ("three-stream z-slab pipeline (H2D | gather+sweep+scatter | D2H), oct numbering '%s'" % args.order)
+           if info.pipeline_slabs else "serial H2D -> sweep -> D2H (oct numbering '%s' scatters z-slabs over the igrid window)" % args.order}
+    if info.pipeline_slabs and not secondary:
+        h.set_pipeline(False)           # what the same call costs when the numbering does not allow the pipeline
+        e2e["serial_order_value"] = time_e2e(max(2, args.e2e_steps // 2))
+        h.set_pipeline(True)
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not secondary:
         try:
-            cpu_baseline, _ = cpu_reference_run(args.workload, 3, 1)
+            cpu_baseline, _ = cpu_reference_run(workload, 2, 1, budget_s=45.0)
             cpu_baseline.pop("seconds", None)
         except Exception as e:      # the checker is optional for the measurement
             cpu_baseline = {"error": repr(e)}
+    h.host_unregister(a.uold)
+    h.host_unregister(a.unew)
     h.finalize()
+    if rank != 0:
+        return None
+    n = 1 << level
+    line = {"metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": t_dev / steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "grid_per_gpu": f"{n}^3", "global_grid":
+                       f"{n * coarse[0]}x{n * coarse[1]}x{n * coarse[2]}", "riemann": w["riemann"], "riemann2d": w.get("riemann2d"),
+                       "slope_type": w["slope_type"], "decomposition": f"{coarse[0]}x{coarse[1]}x{coarse[2]} coarse cells, one per rank, "
+                       "initial condition replicated per coarse cell",
+                       "oct_order": args.order, "sweep_variant": int(info0.sweep_variant), "host_setup_s": round(t_setup, 1),
+                       "l2": "inputs larger than L2 (state %.2f GB per rank vs 126 MB L2), no flush" % (nvs * 8 * ncell_rank / 1e9)},
+            "wall_ms_per_step": wall / steps * 1e3, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "check": check}
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--secondary", default="sedov3d_256_exact", help="second workload reported under 'secondary' at N=1 ('' = none)")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--order", default="lattice", choices=["lattice", "creation", "random"],
+                    help="oct numbering of the fabricated tree; 'creation' = the reference's refine order (nvector = infinity)")
+    ap.add_argument("--write-golden", action="store_true", help="single-GPU run: record the state / dt hashes in tests/golden/bench_hashes.json")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    default_workload = args.workload is None
+    if default_workload:
+        # BASELINE.json configs[2]: sedov3d uniform 512^3, HLLC -- the size north_star's roofline target is quoted on.  It needs
+        # ~14 GB of host memory per rank (two state arrays + the tree); fall back to 256^3 per GPU when the box is short of it
+        args.workload = "sedov3d_512_hllc"
+        try:
+            import psutil
+            if psutil.virtual_memory().available < 20e9 * max(world, 1):
+                args.workload = "sedov3d_256_hllc"
+        except Exception:
+            pass
+    w = WORKLOADS[args.workload]
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    # ------------------------------------------------------------------ reference arm (host cores, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb, sec_per_step = cpu_reference_run(args.workload, steps, warmup, budget_s=150.0)
+        line = {"impl": "reference", "metric": "cell_updates_per_s", "value": cb["value"], "unit": "cell-updates/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec_per_step * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "note": "each step is a bounded sample of the workload (cpu_baseline.sample)"},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    ncpus_bound = pin_to_gpu_numa_node(local_rank)
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if w.get("amr"):
+        return amr_bench(args, w, rank, world, local_rank)
+    line = dense_bench(args, args.workload, rank, world, local_rank)
+    if line is not None:
+        line["config"]["host_cpus_bound"] = ncpus_bound
+    if world == 1 and default_workload and args.secondary and args.secondary != args.workload:
+        try:      # BASELINE.json configs[1] next to the headline workload (same process, N=1 only)
+            sec = dense_bench(args, args.secondary, rank, world, local_rank, secondary=True)
+            line["secondary"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "roofline", "e2e", "check", "gpu_launches")}
+            line["secondary"]["config"] = sec["config"]
+        except Exception as e:
+            line["secondary"] = {"error": repr(e)}
     if rank == 0:
-        n = 1 << level
-        line = {"metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
-                "steps": steps, "warmup": warmup, "ms_per_step": t_dev / steps * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload, "grid_per_gpu": f"{n}^3", "global_grid":
-                           f"{n * coarse[0]}x{n * coarse[1]}x{n * coarse[2]}", "riemann": w["riemann"], "riemann2d": w.get("riemann2d"),
-                           "slope_type": w["slope_type"], "decomposition": f"{coarse[0]}x{coarse[1]}x{coarse[2]} coarse cells, one per rank",
-                           "oct_order": args.order,
-                           "l2": "inputs larger than L2 (state %.2f GB per rank vs 126 MB L2), no flush" % (nvs * 8 * ncell_rank / 1e9)},
-                "wall_ms_per_step": wall / steps * 1e3, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    failed = line is not None and line.get("check") and line["check"].get("equals_single_gpu_golden") is False
+    return 1 if failed else 0
 
 
 if __name__ == "__main__":

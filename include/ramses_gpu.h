@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RGPU_ABI_VERSION 2
+#define RGPU_ABI_VERSION 3
 
 enum {
   RGPU_OK = 0,
@@ -121,6 +121,13 @@ int rgpu_plan_level(const rgpu_params* p, int myid, int ncoarse, int ngridmax, c
  * levelmin=levelmax run).  dt = dtnew(ilevel).  Includes H2D/D2H copies.       */
 int rgpu_godunov_fine(int ilevel, double dt, const double* uold, double* unew);
 
+/* The Level-0 call runs as a three-stream pipeline over z-slabs of the level (H2D of slab s+1 | gather + sweep + scatter of
+ * slab s | D2H of slab s-1; PCIe is full duplex) whenever the oct numbering of the level is spatially coherent enough that a
+ * slab is a few contiguous igrid ranges (lattice / Morton / Hilbert order).  The reference's creation order (amr/refine_utils.f90:
+ * 395-447) scatters a slab over the whole igrid window; the call then keeps the serial order.  rgpu_set_pipeline(0) forces the
+ * serial order (measurements); RGPU_E2E_SLABS=<n> at bind time sets the number of slabs (default 32, <3 disables).            */
+int rgpu_set_pipeline(int enable);
+
 /* Page-lock / unlock a host array so the copies above run at full PCIe rate.   */
 int rgpu_host_register(void* ptr, size_t bytes);
 int rgpu_host_unregister(void* ptr);
@@ -171,6 +178,8 @@ typedef struct rgpu_level_info {
   long long kernel_launches; /* kernels launched on this level since bind          */
   double last_sweep_ms;      /* CUDA-event duration of the last sweep kernel (timing on) */
   double last_steps_ms;      /* CUDA-event duration of the last rgpu_level_steps call, on the launching stream */
+  int pipeline_slabs;        /* z-slabs of the Level-0 pipeline (rgpu_godunov_fine); 0: serial H2D -> sweep -> D2H */
+  int sweep_variant;         /* 3-D hydro: kernel variant in use (0: round-1 loop, else 100*BY + 10*CTAs/SM + solver form) */
 } rgpu_level_info;
 int rgpu_get_level_info(int ilevel, rgpu_level_info* out);
 /* bitwise check of the shared-reciprocal division (hydro_device.cuh div_rn) against the IEEE `/` on npairs

@@ -97,6 +97,23 @@ struct Level {
   std::vector<PeerList> peers;
   int ntx = 0, nty = 0, nblocks = 0, by = 1;
   int variant = 0;                   // 3-D hydro: sweep3_kernel variant (100*BY + 10*MINB + VEC); 0: round-1 kernel
+  // fused forward ghost exchange: every peer's emission / reception slots in one list, one send and one receive buffer with a
+  // contiguous segment per peer ([plane][oct] inside a segment): one pack kernel, one NCCL group, one unpack kernel per exchange
+  int *d_emit_all = nullptr, *d_recv_all = nullptr;
+  long long *d_emit_off = nullptr, *d_recv_off = nullptr;   // [npeer+1] first oct of every peer's segment
+  double *d_sbuf_all = nullptr, *d_rbuf_all = nullptr;
+  std::vector<long long> emit_off, recv_off;
+  // overlap of the exchange with the interior of the next sweep (rgpu_level_steps, multi-rank): interior / frame work maps
+  bool overlap = false;
+  SweepWork wk_int{}, wk_frame{};
+  long long nwork_int = 0, nwork_frame = 0;
+  cudaEvent_t ev_x = nullptr, ev_s = nullptr;
+  // Level-0 pipeline (rgpu_godunov_fine on host arrays): z-slabs of oct planes; per slab the igrid ranges to upload (every oct
+  // of the slab) and to download (its active octs).  Empty when the oct numbering is too scattered (serial path then).
+  struct Range { int lo, n; };
+  struct Slab { int oz_a = 0, oz_b = 0; std::vector<Range> up, down; };
+  std::vector<Slab> slabs;
+  std::vector<cudaEvent_t> ev_in, ev_c;
   long long nwork = 0;
   double* d_part = nullptr;          // [5][part_cap]
   double* d_mhdw = nullptr;          // MHD work arrays [MW_NCOMP][ncell_box]
@@ -150,8 +167,13 @@ struct Context {
   int nvs = 0;                       // stored variables per cell: nvar (hydro) or nvar+3 (MHD)
   int myid = 1, ncpu = 1, device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the Level-0 pipeline (H2D / D2H run on both DMA engines)
+  cudaStream_t s_x = nullptr;                     // ghost exchange stream (overlaps the interior sweep)
+  ncclComm_t comm_x = nullptr;                    // communicator of the exchange stream (split of `comm`)
+  cudaEvent_t ev_pipe = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   bool timing = false;
+  bool pipeline = true;              // Level-0 call: slab pipeline allowed (rgpu_set_pipeline)
   int ncoarse = 0, ngridmax = 0;
   const int *son = nullptr, *father = nullptr, *nbor = nullptr;
   Level lev[MAXLEVEL + 1];
@@ -161,17 +183,18 @@ struct Context {
 
 // ----------------------------------------------------------------------------- kernels
 __global__ void gather_slots_kernel(const double* __restrict__ mirror, double* __restrict__ u, const int* __restrict__ slot_igrid,
-                                    long long nslot, int gmin, long long gspan, int nplanes) {
-  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (s >= nslot) return;
+                                    long long nslot, int gmin, long long gspan, int nplanes, long long s0 = 0, long long s1 = -1) {
+  const long long s = s0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= (s1 < 0 ? nslot : s1)) return;
   const int ig = slot_igrid[s];
   if (ig <= 0) return;
   for (int pl = 0; pl < nplanes; pl++) u[(size_t)pl * nslot + s] = mirror[(size_t)pl * gspan + (ig - gmin)];
 }
 __global__ void scatter_slots_kernel(double* __restrict__ mirror, const double* __restrict__ u, const int* __restrict__ slot_igrid,
-                                     long long nslot, int gmin, long long gspan, int nplanes, int owned_only, DenseGeom g) {
-  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (s >= nslot) return;
+                                     long long nslot, int gmin, long long gspan, int nplanes, int owned_only, DenseGeom g,
+                                     long long s0 = 0, long long s1 = -1) {
+  const long long s = s0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= (s1 < 0 ? nslot : s1)) return;
   const int ig = slot_igrid[s];
   if (ig <= 0) return;
   if (owned_only) {   // only the active octs (owned cell range) are written back
@@ -350,6 +373,33 @@ __global__ void unpack_kernel(double* __restrict__ u, const int* __restrict__ sl
   if (accumulate) u[a] = u[a] + buf[i]; else u[a] = buf[i];
 }
 
+// fused forward exchange: all peers in one launch.  off[p] = first oct of peer p's segment, buffer segment p = [plane][oct]
+__device__ __forceinline__ int seg_of(const long long* __restrict__ off, int nseg, long long o) {
+  int p = 0;
+  while (p + 1 < nseg && o >= off[p + 1]) p++;
+  return p;
+}
+__global__ void pack_all_kernel(const double* __restrict__ u, const int* __restrict__ slots, long long ntot, long long nslot, int nplanes,
+                                double* __restrict__ buf, const long long* __restrict__ off, int nseg) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= ntot * nplanes) return;
+  const long long o = i % ntot;
+  const int pl = (int)(i / ntot);
+  const int p = seg_of(off, nseg, o);
+  const long long n = off[p + 1] - off[p];
+  buf[off[p] * nplanes + (long long)pl * n + (o - off[p])] = u[(size_t)pl * nslot + slots[o]];
+}
+__global__ void unpack_all_kernel(double* __restrict__ u, const int* __restrict__ slots, long long ntot, long long nslot, int nplanes,
+                                  const double* __restrict__ buf, const long long* __restrict__ off, int nseg) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= ntot * nplanes) return;
+  const long long o = i % ntot;
+  const int pl = (int)(i / ntot);
+  const int p = seg_of(off, nseg, o);
+  const long long n = off[p + 1] - off[p];
+  u[(size_t)pl * nslot + slots[o]] = buf[off[p] * nplanes + (long long)pl * n + (o - off[p])];
+}
+
 // self test of div_rn(a, b, rcp_rn(b)) == a / b (IEEE) on pseudo-random and adversarial operand pairs
 __device__ __forceinline__ unsigned long long xs64(unsigned long long& s) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
 __global__ void selftest_div_kernel(long long n_per_thread, unsigned long long seed, unsigned long long* mismatches) {
@@ -411,6 +461,11 @@ void oct_pos(int ilevel, int igrid, int pos[3]) {
 }
 
 void free_level(Level& L) {
+  cudaFree(L.d_emit_all); cudaFree(L.d_recv_all); cudaFree(L.d_emit_off); cudaFree(L.d_recv_off); cudaFree(L.d_sbuf_all); cudaFree(L.d_rbuf_all);
+  if (L.ev_x) cudaEventDestroy(L.ev_x);
+  if (L.ev_s) cudaEventDestroy(L.ev_s);
+  for (auto e : L.ev_in) cudaEventDestroy(e);
+  for (auto e : L.ev_c) cudaEventDestroy(e);
   cudaFree(L.d_slot_igrid); cudaFree(L.d_mirror); cudaFree(L.d_u[0]); cudaFree(L.d_u[1]);
   cudaFree(L.d_part); cudaFree(L.d_dt); cudaFree(L.d_out); cudaFree(L.d_hist); cudaFree(L.d_mhdw); cudaFree(L.d_refined);
   for (auto& r : L.regions) cudaFree(r.d_slots);
@@ -439,7 +494,9 @@ cudaError_t dispatch_sweep_nd(int riemann, const SweepArgs& a, int nb, cudaStrea
   }
 }
 
-int launch_sweep(Level& L) {
+// zlo/zhi >= 0: sweep only the owned cell planes [zlo, zhi) (Level-0 pipeline; no Courant partials then)
+// part: 0 whole level, 1 interior, 2 frame (Level::wk_int / wk_frame; Courant partials of 1 and 2 share one array)
+int launch_sweep(Level& L, int zlo = -1, int zhi = -1, int part = 0) {
   if (G.p.mhd) {
     MhdArgs m{};
     m.uin = L.d_u[L.cur]; m.uout = L.d_u[1 - L.cur]; m.g = L.g; m.P = G.mphys; m.dt_dev = L.d_dt; m.dx = L.dx;
@@ -470,20 +527,34 @@ int launch_sweep(Level& L) {
   a.dx_pow2 = (std::frexp(L.dx, &ex) == 0.5) ? 1 : 0;
   a.ntx = L.ntx; a.nty = L.nty; a.nwork = L.nwork;
   a.part = L.d_part;
+  int nblocks = L.nblocks;
+  if (part) {
+    a.wk = part == 1 ? L.wk_int : L.wk_frame;
+    a.nwork = part == 1 ? L.nwork_int : L.nwork_frame;
+    nblocks = (int)std::min<long long>(L.nblocks, a.nwork);
+    a.part_stride = 2 * L.nblocks; a.part_off = part == 1 ? 0 : L.nblocks;
+  }
+  if (zlo >= 0) {
+    a.g.oz0 = std::max(L.g.oz0, zlo); a.g.oz1 = std::min(L.g.oz1, zhi);
+    if (a.g.oz1 <= a.g.oz0) return RGPU_OK;
+    a.nwork = (long long)L.ntx * L.nty * (a.g.oz1 - a.g.oz0);
+    nblocks = (int)std::min<long long>(L.nblocks, a.nwork);
+    a.part = nullptr;
+  }
   if (G.timing) cudaEventRecord(G.ev0, G.stream);
   cudaError_t e;
-  if (G.p.ndim == 1) e = dispatch_sweep_nd<1>(G.p.riemann, a, L.nblocks, G.stream, L.by);
-  else if (G.p.ndim == 2) e = dispatch_sweep_nd<2>(G.p.riemann, a, L.nblocks, G.stream, L.by);
+  if (G.p.ndim == 1) e = dispatch_sweep_nd<1>(G.p.riemann, a, nblocks, G.stream, L.by);
+  else if (G.p.ndim == 2) e = dispatch_sweep_nd<2>(G.p.riemann, a, nblocks, G.stream, L.by);
   else if (L.variant) {
     switch (G.p.riemann) {
-      case RGPU_RIEMANN_LLF: e = launch_sweep3<RIEMANN_LLF>(a, L.nblocks, G.stream, L.variant); break;
-      case RGPU_RIEMANN_EXACT: e = launch_sweep3<RIEMANN_EXACT>(a, L.nblocks, G.stream, L.variant); break;
-      case RGPU_RIEMANN_ACOUSTIC: e = launch_sweep3<RIEMANN_ACOUSTIC>(a, L.nblocks, G.stream, L.variant); break;
-      case RGPU_RIEMANN_HLLC: e = launch_sweep3<RIEMANN_HLLC>(a, L.nblocks, G.stream, L.variant); break;
-      default: e = launch_sweep3<RIEMANN_HLL>(a, L.nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_LLF: e = launch_sweep3<RIEMANN_LLF>(a, nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_EXACT: e = launch_sweep3<RIEMANN_EXACT>(a, nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_ACOUSTIC: e = launch_sweep3<RIEMANN_ACOUSTIC>(a, nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_HLLC: e = launch_sweep3<RIEMANN_HLLC>(a, nblocks, G.stream, L.variant); break;
+      default: e = launch_sweep3<RIEMANN_HLL>(a, nblocks, G.stream, L.variant); break;
     }
   }
-  else e = dispatch_sweep_nd<3>(G.p.riemann, a, L.nblocks, G.stream, L.by);
+  else e = dispatch_sweep_nd<3>(G.p.riemann, a, nblocks, G.stream, L.by);
   if (e != cudaSuccess) return fail(RGPU_ECUDA, "sweep launch: %s", cudaGetErrorString(e));
   if (G.timing) {
     cudaEventRecord(G.ev1, G.stream);
@@ -864,11 +935,12 @@ int amr_boundaries(AmrLevel& A) {
 }
 
 int exchange_ghosts(Level& L, double* u, bool reverse);
+int exchange_ghosts_fused(Level& L, double* u, cudaStream_t st, ncclComm_t comm);
 
 // set_uold only touches the active cells: the boundary / ghost shells keep their uold values until the next
 // make_boundary_hydro / make_virtual_fine.  With ping-pong buffers those values must be carried over explicitly
 // (corner boundary octs read neighbours that are refreshed later in the same pass, hydro_boundary.f90:53).
-int carry_shells(Level& L, const double* from, double* to) {
+int carry_shells(Level& L, const double* from, double* to, bool peers = true) {
   const long long np = (long long)nplanes_();
   for (auto& r : L.regions)
     if (r.n) {
@@ -876,7 +948,7 @@ int carry_shells(Level& L, const double* from, double* to) {
       CUDA_OK(cudaGetLastError());
       L.launches++;
     }
-  for (auto& P : L.peers)
+  if (peers) for (auto& P : L.peers)
     if (P.nrecv) {
       copy_octs_kernel<<<(unsigned)(((long long)P.nrecv * np + 255) / 256), 256, 0, G.stream>>>(from, to, P.d_recv, P.nrecv, L.nslot, (int)np);
       CUDA_OK(cudaGetLastError());
@@ -934,6 +1006,10 @@ int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device) {
   CUDA_OK(cudaSetDevice(device));
   G.p = *p; G.myid = myid; G.ncpu = ncpu; G.device = device;
   CUDA_OK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&G.s_in, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&G.s_out, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&G.s_x, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&G.ev_pipe, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreate(&G.ev0));
   CUDA_OK(cudaEventCreate(&G.ev1));
   CUDA_OK(cudaEventCreate(&G.ev2));
@@ -968,8 +1044,12 @@ int rgpu_finalize(void) {
   for (int l = 0; l <= MAXLEVEL; l++) if (G.alev[l].bound) free_amr_level(G.alev[l]);
   cudaFree(G.d_son); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew); cudaFree(G.d_dtn); cudaFree(G.d_dto);
   G.d_son = G.d_father = G.d_nbor = nullptr; G.d_uold = G.d_unew = nullptr; G.d_dtn = G.d_dto = nullptr; G.ncell = 0; G.amr = false;
+  if (G.comm_x) { ncclCommDestroy(G.comm_x); G.comm_x = nullptr; }
   if (G.comm) { ncclCommDestroy(G.comm); G.comm = nullptr; }
+  cudaStreamDestroy(G.s_x);
   cudaEventDestroy(G.ev0); cudaEventDestroy(G.ev1); cudaEventDestroy(G.ev2); cudaEventDestroy(G.ev3);
+  cudaEventDestroy(G.ev_pipe);
+  cudaStreamDestroy(G.s_in); cudaStreamDestroy(G.s_out);
   cudaStreamDestroy(G.stream);
   G.init = false;
   return RGPU_OK;
@@ -1113,6 +1193,55 @@ static int plan_level(Level& L, int ilevel, int ngrid_active, const int* igrid_a
   return RGPU_OK;
 }
 
+// Level-0 pipeline plan (host only): cut the box into slabs of oct planes along z; per slab the contiguous igrid ranges of
+// its octs (upload) and of its active octs (download).  The reference numbers octs in creation order (amr/refine_utils.f90:
+// 395-447: chunks of nvector father grids, cell position outermost inside a chunk), which scatters every slab over the whole
+// igrid window in runs of ~4 octs -- then the plan is dropped and rgpu_godunov_fine keeps its serial H2D -> sweep -> D2H order.
+// A spatially coherent numbering (lattice or Morton / Hilbert order) gives a handful of ranges per slab.
+static void plan_slabs(Level& L) {
+  L.slabs.clear();
+  if (G.p.ndim != 3 || G.p.mhd || G.amr) return;
+  const DenseGeom& g = L.g;
+  int nsl = 32;
+  if (const char* e = getenv("RGPU_E2E_SLABS")) nsl = atoi(e);
+  nsl = std::min(nsl, g.noz / 4);
+  if (nsl < 3) return;
+  const size_t max_ranges = 4096;
+  const long long plane = (long long)g.nox * g.noy;
+  std::vector<Level::Slab> slabs(nsl);
+  size_t total = 0;
+  std::vector<int> ig;
+  auto coalesce = [&](std::vector<int>& v, std::vector<Level::Range>& out) {
+    std::sort(v.begin(), v.end());
+    for (size_t i = 0; i < v.size();) {
+      size_t j = i + 1;
+      while (j < v.size() && v[j] == v[j - 1] + 1) j++;
+      out.push_back({v[i], (int)(j - i)});
+      i = j;
+    }
+  };
+  for (int sl = 0; sl < nsl; sl++) {
+    Level::Slab& S = slabs[sl];
+    S.oz_a = (int)((long long)g.noz * sl / nsl); S.oz_b = (int)((long long)g.noz * (sl + 1) / nsl);
+    ig.clear();
+    for (long long t = S.oz_a * plane; t < S.oz_b * plane; t++) if (L.slot_igrid[t] > 0) ig.push_back(L.slot_igrid[t]);
+    coalesce(ig, S.up);
+    ig.clear();
+    for (int oz = S.oz_a; oz < S.oz_b; oz++) {
+      if (2 * oz < g.oz0 || 2 * oz >= g.oz1) continue;
+      for (int oy = g.oy0 / 2; oy < g.oy1 / 2; oy++)
+        for (int ox = g.ox0 / 2; ox < g.ox1 / 2; ox++) {
+          const int v = L.slot_igrid[ox + (long long)g.nox * (oy + (long long)g.noy * oz)];
+          if (v > 0) ig.push_back(v);
+        }
+    }
+    coalesce(ig, S.down);
+    total += S.up.size() + S.down.size();
+    if (total > max_ranges) return;
+  }
+  L.slabs.swap(slabs);
+}
+
 // device side of a dense level store (after plan_level): slot map, state buffers, boundary / peer lists, tiling
 static int alloc_dense_store(Level& L, int ncpu, int nboundary, const int* boundary_type) {
   const int nd = G.p.ndim;
@@ -1159,6 +1288,33 @@ static int alloc_dense_store(Level& L, int ncpu, int nboundary, const int* bound
       }
     }
   }
+  if (ncpu > 1) {   // fused forward exchange lists
+    std::vector<int> eall, rall;
+    L.emit_off.assign(1, 0); L.recv_off.assign(1, 0);
+    for (int c = 0; c < ncpu; c++) {
+      if (c != G.myid - 1) {
+        eall.insert(eall.end(), L.h_eslots[c].begin(), L.h_eslots[c].end());
+        rall.insert(rall.end(), rslots[c].begin(), rslots[c].end());
+      }
+      L.emit_off.push_back((long long)eall.size()); L.recv_off.push_back((long long)rall.size());
+    }
+    if (!eall.empty()) {
+      CUDA_OK(cudaMalloc(&L.d_emit_all, sizeof(int) * eall.size()));
+      CUDA_OK(cudaMemcpy(L.d_emit_all, eall.data(), sizeof(int) * eall.size(), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMalloc(&L.d_sbuf_all, sizeof(double) * np * eall.size()));
+    }
+    if (!rall.empty()) {
+      CUDA_OK(cudaMalloc(&L.d_recv_all, sizeof(int) * rall.size()));
+      CUDA_OK(cudaMemcpy(L.d_recv_all, rall.data(), sizeof(int) * rall.size(), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMalloc(&L.d_rbuf_all, sizeof(double) * np * rall.size()));
+    }
+    CUDA_OK(cudaMalloc(&L.d_emit_off, sizeof(long long) * (ncpu + 1)));
+    CUDA_OK(cudaMalloc(&L.d_recv_off, sizeof(long long) * (ncpu + 1)));
+    CUDA_OK(cudaMemcpy(L.d_emit_off, L.emit_off.data(), sizeof(long long) * (ncpu + 1), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(L.d_recv_off, L.recv_off.data(), sizeof(long long) * (ncpu + 1), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaEventCreateWithFlags(&L.ev_x, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&L.ev_s, cudaEventDisableTiming));
+  }
   // ---- tile decomposition of the owned range ----------------------------------------------------
   const int bx = 32;
   int by = tile_by_default(nd, G.p.riemann);
@@ -1186,7 +1342,29 @@ static int alloc_dense_store(Level& L, int ncpu, int nboundary, const int* bound
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, G.device);
     L.nblocks = (int)std::min<long long>((long long)nsm * minb, L.nwork);
   }
-  L.part_cap = std::max(L.nblocks, 148 * 8);
+  L.part_cap = std::max(2 * L.nblocks, 148 * 8);
+  // ---- interior / frame split (multi-rank 3-D hydro): a tile is interior when every cell it reads (2-cell halo) is owned
+  L.overlap = false;
+  if (nd == 3 && !G.p.mhd && !G.amr && ncpu > 1) {
+    const char* e = getenv("RGPU_OVERLAP");
+    SweepWork wi{};
+    wi.mode = 1;
+    auto range = [](int n_owned, int tile, int ntile, int wrap, int& i0, int& i1) {
+      if (wrap) { i0 = 0; i1 = ntile; return; }
+      i0 = 1; i1 = n_owned >= tile + 2 + tile ? (n_owned - (tile + 2)) / tile + 1 : 0;
+      if (i1 > ntile) i1 = ntile;
+    };
+    range(g.ox1 - g.ox0, txo, L.ntx, g.wrapx, wi.ix0, wi.ix1);
+    range(g.oy1 - g.oy0, tyo, L.nty, g.wrapy, wi.iy0, wi.iy1);
+    wi.iz0 = g.wrapz ? g.oz0 : g.oz0 + 2; wi.iz1 = g.wrapz ? g.oz1 : g.oz1 - 2;
+    const long long nxi = wi.ix1 - wi.ix0, nyi = wi.iy1 - wi.iy0, nzi = wi.iz1 - wi.iz0;
+    if (!(e && atoi(e) == 0) && nxi > 0 && nyi > 0 && nzi > 4) {
+      L.wk_int = wi; L.wk_frame = wi; L.wk_frame.mode = 2;
+      L.nwork_int = nxi * nyi * nzi;
+      L.nwork_frame = ((long long)L.ntx * L.nty - nxi * nyi) * (g.oz1 - g.oz0) + nxi * nyi * ((wi.iz0 - g.oz0) + (g.oz1 - wi.iz1));
+      L.overlap = L.nwork_frame > 0;
+    }
+  }
   if (G.p.mhd) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, G.device);
@@ -1199,6 +1377,13 @@ static int alloc_dense_store(Level& L, int ncpu, int nboundary, const int* bound
   CUDA_OK(cudaMalloc(&L.d_dt, sizeof(double)));
   CUDA_OK(cudaMalloc(&L.d_out, sizeof(double) * 5));
   L.cur = 0; L.unew_valid = false;
+  plan_slabs(L);
+  for (size_t i = 0; i < L.slabs.size(); i++) {
+    cudaEvent_t e1, e2;
+    CUDA_OK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    L.ev_in.push_back(e1); L.ev_c.push_back(e2);
+  }
   return RGPU_OK;
 }
 
@@ -1363,6 +1548,73 @@ static int download_from(Level& L, double* host, const double* srcdev, bool owne
   return RGPU_OK;
 }
 
+// Level-0 call as a three-stream pipeline over z-slabs (plan_slabs): H2D of slab s+1 (stream s_in) runs while slab s is gathered
+// into lattice slots, swept and scattered back (G.stream) and slab s-1 travels back to the host (s_out) -- PCIe is full duplex, so
+// the call costs about one direction of the link instead of two plus the sweep.  The sweep of a slab needs one oct layer of its
+// two neighbours: slabs are uploaded in the order N-1, 0, 1, ..., N-2 (the periodic wrap makes slab N-1 the lower neighbour of
+// slab 0) and slab s is swept once slab s+1 has been gathered.  Same kernels, same arithmetic as the serial path; the result is
+// bit-identical (tests/test_gpu_parity.py::test_level0_pipelined_equals_serial).
+static int godunov_fine_pipelined(Level& L, const double* uold, double* unew) {
+  const int T = T_(), nsl = (int)L.slabs.size();
+  const long long gspan = (long long)L.gmax - L.gmin + 1;
+  const size_t ncell = (size_t)G.ncoarse + (size_t)T * G.ngridmax;
+  const long long plane = (long long)L.g.nox * L.g.noy;
+  const int nthr = 256;
+  double* uin = L.d_u[L.cur];
+  double* uout = L.d_u[1 - L.cur];
+  // the copy streams must not start before the work already queued on the main stream (previous call, dt upload)
+  CUDA_OK(cudaEventRecord(G.ev_pipe, G.stream));
+  CUDA_OK(cudaStreamWaitEvent(G.s_in, G.ev_pipe, 0));
+  CUDA_OK(cudaStreamWaitEvent(G.s_out, G.ev_pipe, 0));
+  auto h2d = [&](int sl) -> int {
+    for (const auto& r : L.slabs[sl].up)
+      for (int iv = 0; iv < G.nvs; iv++)
+        CUDA_OK(cudaMemcpy2DAsync(L.d_mirror + (size_t)iv * T * gspan + (r.lo - L.gmin), sizeof(double) * gspan,
+                                  uold + (size_t)iv * ncell + G.ncoarse + (r.lo - 1), sizeof(double) * G.ngridmax,
+                                  sizeof(double) * r.n, T, cudaMemcpyHostToDevice, G.s_in));
+    CUDA_OK(cudaEventRecord(L.ev_in[sl], G.s_in));
+    return RGPU_OK;
+  };
+  auto gather = [&](int sl) -> int {
+    CUDA_OK(cudaStreamWaitEvent(G.stream, L.ev_in[sl], 0));
+    const long long s0 = L.slabs[sl].oz_a * plane, s1 = L.slabs[sl].oz_b * plane;
+    gather_slots_kernel<<<(unsigned)((s1 - s0 + nthr - 1) / nthr), nthr, 0, G.stream>>>(L.d_mirror, uin, L.d_slot_igrid, L.nslot, L.gmin, gspan,
+                                                                                      (int)nplanes_(), s0, s1);
+    CUDA_OK(cudaGetLastError());
+    L.launches++;
+    return RGPU_OK;
+  };
+  auto sweep_out = [&](int sl) -> int {
+    int rc = launch_sweep(L, 2 * L.slabs[sl].oz_a, 2 * L.slabs[sl].oz_b); if (rc) return rc;
+    const long long s0 = L.slabs[sl].oz_a * plane, s1 = L.slabs[sl].oz_b * plane;
+    scatter_slots_kernel<<<(unsigned)((s1 - s0 + nthr - 1) / nthr), nthr, 0, G.stream>>>(L.d_mirror, uout, L.d_slot_igrid, L.nslot, L.gmin, gspan,
+                                                                                       (int)nplanes_(), 1, L.g, s0, s1);
+    CUDA_OK(cudaGetLastError());
+    L.launches++;
+    CUDA_OK(cudaEventRecord(L.ev_c[sl], G.stream));
+    CUDA_OK(cudaStreamWaitEvent(G.s_out, L.ev_c[sl], 0));
+    for (const auto& r : L.slabs[sl].down)
+      for (int iv = 0; iv < G.nvs; iv++)
+        CUDA_OK(cudaMemcpy2DAsync(unew + (size_t)iv * ncell + G.ncoarse + (r.lo - 1), sizeof(double) * G.ngridmax,
+                                  L.d_mirror + (size_t)iv * T * gspan + (r.lo - L.gmin), sizeof(double) * gspan,
+                                  sizeof(double) * r.n, T, cudaMemcpyDeviceToHost, G.s_out));
+    return RGPU_OK;
+  };
+  int rc;
+  rc = h2d(nsl - 1); if (rc) return rc;
+  for (int sl = 0; sl < nsl - 1; sl++) { rc = h2d(sl); if (rc) return rc; }
+  rc = gather(nsl - 1); if (rc) return rc;
+  rc = gather(0); if (rc) return rc;
+  for (int sl = 0; sl < nsl; sl++) {
+    if (sl + 1 < nsl - 1) { rc = gather(sl + 1); if (rc) return rc; }
+    rc = sweep_out(sl); if (rc) return rc;
+  }
+  L.unew_valid = true;
+  CUDA_OK(cudaStreamSynchronize(G.s_out));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  return RGPU_OK;
+}
+
 int rgpu_upload_state(int ilevel, const double* uold) {
   if (G.amr) {   // AMR mode: the whole uold array (all levels) is mirrored; ilevel is ignored
     if (!G.d_uold || !uold) return fail(RGPU_EINVAL, "AMR mode: bind the tree first / null uold");
@@ -1521,6 +1773,7 @@ int rgpu_godunov_fine(int ilevel, double dt, const double* uold, double* unew) {
   if (!uold || !unew) return fail(RGPU_EINVAL, "null state array");
   if (!(dt > 0)) return fail(RGPU_EINVAL, "dt=%g", dt);
   CUDA_OK(cudaMemcpyAsync(L->d_dt, &dt, sizeof(double), cudaMemcpyHostToDevice, G.stream));
+  if (!L->slabs.empty() && G.pipeline && !G.timing) return godunov_fine_pipelined(*L, uold, unew);
   rc = upload_into(*L, uold, L->d_u[L->cur]); if (rc) return rc;
   rc = launch_sweep(*L); if (rc) return rc;
   L->unew_valid = true;
@@ -1537,23 +1790,56 @@ int rgpu_level_steps(int ilevel, int nstep, double* dt_hist, double sums_last[3]
     L->hist_cap = nstep + 1;
   }
   const double dt_cap = G.p.boxlen / G.p.smallc;   // pm/newdt_fine.f90:47-51
+  const bool multi = G.comm && G.nranks > 1 && !L->peers.empty();
+  const bool fused = multi && L->d_emit_off != nullptr;
+  const bool ovl = fused && L->overlap && G.comm_x != nullptr && !G.timing;   // per-kernel timing runs keep one sweep launch
   CUDA_OK(cudaEventRecord(G.ev2, G.stream));
   // amr_step order.  Ghost shells of uold are current on entry (upload / previous step).
-  rc = exchange_ghosts(*L, L->d_u[L->cur], false); if (rc) return rc;
+  if (fused) rc = exchange_ghosts_fused(*L, L->d_u[L->cur], G.stream, G.comm); else rc = exchange_ghosts(*L, L->d_u[L->cur], false);
+  if (rc) return rc;
   rc = launch_boundaries(*L, L->d_u[L->cur]); if (rc) return rc;
   rc = launch_courant(*L, dt_cap, L->d_hist); if (rc) return rc;                    // courant_fine  amr_step.f90:326
+  if (ovl) {   // unused columns of the shared partial array stay neutral (min: huge, sums: 0)
+    const size_t stride = 2 * (size_t)L->nblocks;
+    CUDA_OK(cudaMemsetAsync(L->d_part, 0x7f, sizeof(double) * stride, G.stream));
+    CUDA_OK(cudaMemsetAsync(L->d_part + stride, 0, sizeof(double) * 3 * stride, G.stream));
+    CUDA_OK(cudaEventRecord(L->ev_x, G.stream));
+  }
   for (int s = 0; s < nstep; s++) {
     if (G.comm && G.nranks > 1) {
       NCCL_OK(ncclAllReduce(L->d_dt, L->d_dt, 1, ncclDouble, ncclMin, G.comm, G.stream));
       if (s < nstep) CUDA_OK(cudaMemcpyAsync(L->d_hist + s, L->d_dt, sizeof(double), cudaMemcpyDeviceToDevice, G.stream));
     }
+    if (ovl) {
+      // interior tiles read owned cells only: they run while the exchange of the previous step (stream s_x) fills the ghost
+      // shells; the frame (outer tile ring + plane caps) waits for it.  Same kernel, same arithmetic, two launches.
+      rc = launch_sweep(*L, -1, -1, 1); if (rc) return rc;
+      CUDA_OK(cudaStreamWaitEvent(G.stream, L->ev_x, 0));
+      rc = launch_sweep(*L, -1, -1, 2); if (rc) return rc;
+      rc = launch_reduce(*L, 2 * L->nblocks, dt_cap, L->d_hist + s + 1); if (rc) return rc;
+      rc = carry_shells(*L, L->d_u[L->cur], L->d_u[1 - L->cur], false); if (rc) return rc;
+      L->cur = 1 - L->cur;
+      CUDA_OK(cudaEventRecord(L->ev_s, G.stream));
+      CUDA_OK(cudaStreamWaitEvent(G.s_x, L->ev_s, 0));
+      rc = exchange_ghosts_fused(*L, L->d_u[L->cur], G.s_x, G.comm_x); if (rc) return rc;   // make_virtual_fine :505
+      {   // make_boundary_hydro :514 on the exchange stream (it reads the fresh ghost octs at box corners)
+        cudaStream_t keep = G.stream; G.stream = G.s_x;
+        rc = launch_boundaries(*L, L->d_u[L->cur]);
+        G.stream = keep;
+        if (rc) return rc;
+      }
+      CUDA_OK(cudaEventRecord(L->ev_x, G.s_x));
+      continue;
+    }
     rc = launch_sweep(*L); if (rc) return rc;                                        // set_unew + godunov_fine + set_uold  :333,:388,:423
     rc = launch_reduce(*L, L->nblocks, dt_cap, L->d_hist + s + 1); if (rc) return rc;  // courant_fine of the next step
-    rc = carry_shells(*L, L->d_u[L->cur], L->d_u[1 - L->cur]); if (rc) return rc;
+    rc = carry_shells(*L, L->d_u[L->cur], L->d_u[1 - L->cur], !fused); if (rc) return rc;
     L->cur = 1 - L->cur;
-    rc = exchange_ghosts(*L, L->d_u[L->cur], false); if (rc) return rc;             // make_virtual_fine :505
+    if (fused) rc = exchange_ghosts_fused(*L, L->d_u[L->cur], G.stream, G.comm); else rc = exchange_ghosts(*L, L->d_u[L->cur], false);   // make_virtual_fine :505
+    if (rc) return rc;
     rc = launch_boundaries(*L, L->d_u[L->cur]); if (rc) return rc;                  // make_boundary_hydro :514
   }
+  if (ovl) CUDA_OK(cudaStreamWaitEvent(G.stream, L->ev_x, 0));
   L->unew_valid = false;
   CUDA_OK(cudaEventRecord(G.ev3, G.stream));
   if (dt_hist) CUDA_OK(cudaMemcpyAsync(dt_hist, L->d_hist, sizeof(double) * nstep, cudaMemcpyDeviceToHost, G.stream));
@@ -1679,6 +1965,9 @@ int rgpu_comm_init(int nranks, int rank, const void* unique_id_128) {
   memcpy(&id, unique_id_128, 128);
   NCCL_OK(ncclCommInitRank(&G.comm, nranks, id, rank));
   G.nranks = nranks; G.rank = rank;
+  if (G.comm_x) { ncclCommDestroy(G.comm_x); G.comm_x = nullptr; }
+  // second communicator for the exchange stream: the dt all-reduce (main stream) and the ghost exchange run concurrently
+  NCCL_OK(ncclCommSplit(G.comm, 0, rank, &G.comm_x, nullptr));
   return RGPU_OK;
 }
 
@@ -1696,6 +1985,7 @@ int rgpu_get_level_info(int ilevel, rgpu_level_info* o) {
   o->own_hi[0] = L.g.ox1; o->own_hi[1] = L.g.oy1; o->own_hi[2] = L.g.oz1;
   o->wrap[0] = L.g.wrapx; o->wrap[1] = L.g.wrapy; o->wrap[2] = L.g.wrapz;
   o->nslot = L.nslot; o->kernel_launches = L.launches; o->last_sweep_ms = L.last_sweep_ms; o->last_steps_ms = L.last_steps_ms;
+  o->pipeline_slabs = (int)L.slabs.size(); o->sweep_variant = L.variant;
   return RGPU_OK;
 }
 int rgpu_selftest_div(long long npairs, unsigned long long seed, long long* mismatches) {
@@ -1715,6 +2005,7 @@ int rgpu_selftest_div(long long npairs, unsigned long long seed, long long* mism
   return RGPU_OK;
 }
 int rgpu_set_timing(int enable) { G.timing = enable != 0; return RGPU_OK; }
+int rgpu_set_pipeline(int enable) { G.pipeline = enable != 0; return RGPU_OK; }
 int rgpu_device_synchronize(void) {
   if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
   CUDA_OK(cudaStreamSynchronize(G.stream));
@@ -1728,6 +2019,33 @@ namespace {
 // one packed message per peer inside a single NCCL group (ncclSend/ncclRecv over NVLink) instead of nvar
 // MPI_ISEND/IRECV rounds.  forward: emission octs -> peer's reception octs (copy); reverse: reception octs ->
 // owner's emission octs (accumulate, in peer order like :852-863).
+// forward exchange (make_virtual_fine_dp for all variables and ALL peers): one pack kernel, one NCCL group, one unpack kernel
+int exchange_ghosts_fused(Level& L, double* u, cudaStream_t st, ncclComm_t comm) {
+  if (L.peers.empty()) return RGPU_OK;
+  if (!comm) return fail(RGPU_EINVAL, "ghost exchange needs rgpu_comm_init");
+  const long long np = (long long)nplanes_();
+  const int nseg = (int)L.peers.size();
+  const long long ne = L.emit_off.back(), nr = L.recv_off.back();
+  if (ne) {
+    pack_all_kernel<<<(unsigned)((ne * np + 255) / 256), 256, 0, st>>>(u, L.d_emit_all, ne, L.nslot, (int)np, L.d_sbuf_all, L.d_emit_off, nseg);
+    CUDA_OK(cudaGetLastError());
+    L.launches++;
+  }
+  NCCL_OK(ncclGroupStart());
+  for (int c = 0; c < nseg; c++) {
+    const long long es = L.emit_off[c + 1] - L.emit_off[c], rs = L.recv_off[c + 1] - L.recv_off[c];
+    if (es) NCCL_OK(ncclSend(L.d_sbuf_all + L.emit_off[c] * np, (size_t)(es * np), ncclDouble, c, comm, st));
+    if (rs) NCCL_OK(ncclRecv(L.d_rbuf_all + L.recv_off[c] * np, (size_t)(rs * np), ncclDouble, c, comm, st));
+  }
+  NCCL_OK(ncclGroupEnd());
+  if (nr) {
+    unpack_all_kernel<<<(unsigned)((nr * np + 255) / 256), 256, 0, st>>>(u, L.d_recv_all, nr, L.nslot, (int)np, L.d_rbuf_all, L.d_recv_off, nseg);
+    CUDA_OK(cudaGetLastError());
+    L.launches++;
+  }
+  return RGPU_OK;
+}
+
 int exchange_ghosts(Level& L, double* u, bool reverse) {
   if (L.peers.empty()) return RGPU_OK;
   if (!G.comm) return fail(RGPU_EINVAL, "ghost exchange needs rgpu_comm_init");

@@ -42,6 +42,16 @@ struct DenseGeom {
   long long nslot;            // number of oct slots (stride between (ivar,ind) planes)
 };
 
+// Which (column tile, plane) pairs a launch covers.  mode 0: every tile x every owned plane.  Multi-GPU level steps split the
+// sweep so that the ghost-oct exchange of step s overlaps the part of sweep s+1 that does not read ghost cells:
+// mode 1 = interior (tiles [ix0,ix1) x [iy0,iy1), planes [iz0,iz1): every cell they read is an owned cell), mode 2 = the frame
+// (the complement: outer tile ring over all planes + the bottom / top plane caps of the interior columns).  3-D only.
+struct SweepWork {
+  int mode;
+  int ix0, ix1, iy0, iy1;
+  int iz0, iz1;
+};
+
 struct SweepArgs {
   const double* uin;          // state at t^n   (uold)
   double* uout;               // state at t^n+1 (unew after set_uold)
@@ -53,7 +63,9 @@ struct SweepArgs {
   int dx_pow2;                // dx is a power of two: x/dx == x*inv_dx exactly
   int ntx, nty;               // column tiles of the owned range
   long long nwork;            // ntx*nty*(owned planes): plane-tiles to distribute
-  double* part;               // per-CTA partials [4][gridDim.x]: min dt, mass, etot, eint of the new state
+  double* part;               // per-CTA partials [4][part_stride]: min dt, mass, etot, eint of the new state
+  int part_stride, part_off;  // columns of `part` and the first column of this launch (0, 0: gridDim.x columns from column 0)
+  SweepWork wk;
   // AMR variant (fully refined level inside an AMR run, godfine1 hydro/godunov_fine.f90:661-666,720-747,751-792):
   const unsigned char* refined;  // [2^ndim][nslot] son(cell)>0: fluxes through faces of refined cells are reset to zero
                                  // and the update ACCUMULATES into uout (= unew, which already holds the refluxes of the
@@ -73,6 +85,56 @@ __device__ __forceinline__ long long cell_offset(const DenseGeom& g, int x, int 
   if (NDIM > 1) { ind |= (y & 1) << 1; slot += (long long)g.nox * (y >> 1); }
   if (NDIM > 2) { ind |= (z & 1) << 2; slot += (long long)g.nox * g.noy * (z >> 1); }
   return (long long)ind * g.nslot + slot;
+}
+
+// decode work item w of a launch into (tile, first plane, number of consecutive planes before `wend` or the column end)
+__device__ __forceinline__ void sweep_work_decode(const SweepArgs& a, long long w, long long wend, int& tix, int& tiy, int& z0, int& zn) {
+  const DenseGeom& g = a.g;
+  const SweepWork& k = a.wk;
+  const int nzo = g.oz1 - g.oz0;
+  if (k.mode == 0) {
+    const long long col = w / nzo;
+    const int zs = (int)(w - col * nzo);
+    zn = (int)min((long long)(nzo - zs), wend - w);
+    tix = (int)(col % a.ntx); tiy = (int)(col / a.ntx);
+    z0 = g.oz0 + zs;
+    return;
+  }
+  const int nxi = k.ix1 - k.ix0, nyi = k.iy1 - k.iy0;
+  if (k.mode == 1) {
+    const int nzi = k.iz1 - k.iz0;
+    const long long col = w / nzi;
+    const int zs = (int)(w - col * nzi);
+    zn = (int)min((long long)(nzi - zs), wend - w);
+    tix = k.ix0 + (int)(col % nxi); tiy = k.iy0 + (int)(col / nxi);
+    z0 = k.iz0 + zs;
+    return;
+  }
+  const long long ncolA = (long long)a.ntx * a.nty - (long long)nxi * nyi;
+  const long long WA = ncolA * nzo;
+  if (w < WA) {                                 // frame tiles, all planes
+    long long c = w / nzo;
+    const int zs = (int)(w - c * nzo);
+    zn = (int)min((long long)(nzo - zs), wend - w);
+    z0 = g.oz0 + zs;
+    const long long nbot = (long long)a.ntx * k.iy0, ntop = (long long)a.ntx * (a.nty - k.iy1);
+    if (c < nbot) { tiy = (int)(c / a.ntx); tix = (int)(c % a.ntx); return; }
+    c -= nbot;
+    if (c < ntop) { tiy = k.iy1 + (int)(c / a.ntx); tix = (int)(c % a.ntx); return; }
+    c -= ntop;
+    const int nside = k.ix0 + (a.ntx - k.ix1);
+    const int r = (int)(c / nside), q = (int)(c % nside);
+    tiy = k.iy0 + r;
+    tix = q < k.ix0 ? q : k.ix1 + (q - k.ix0);
+    return;
+  }
+  const long long wc = w - WA;                  // interior columns: bottom cap [oz0, iz0), then top cap [iz1, oz1)
+  const int nlo = k.iz0 - g.oz0, nhi = g.oz1 - k.iz1, ncap = nlo + nhi;
+  const long long col = wc / ncap;
+  const int r = (int)(wc - col * ncap);
+  tix = k.ix0 + (int)(col % nxi); tiy = k.iy0 + (int)(col / nxi);
+  if (r < nlo) { z0 = g.oz0 + r; zn = (int)min((long long)(nlo - r), wend - w); }
+  else { z0 = k.iz1 + (r - nlo); zn = (int)min((long long)(nhi - (r - nlo)), wend - w); }
 }
 
 __device__ __forceinline__ double warp_min(double v) {
@@ -168,14 +230,12 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
   long long w0 = a.nwork * blockIdx.x / gridDim.x;
   const long long w1 = a.nwork * (blockIdx.x + 1) / gridDim.x;
   while (w0 < w1) {
-    const long long col = w0 / nzo;
-    const int zs = (int)(w0 - col * nzo);
-    const int zn = (int)min((long long)(nzo - zs), w1 - w0);
+    int tix, tiy, z0, zn;
+    if (HZ) sweep_work_decode(a, w0, w1, tix, tiy, z0, zn);
+    else { const long long col = w0; zn = 1; z0 = 0; tix = (int)(col % a.ntx); tiy = (int)(col / a.ntx); }
     w0 += zn;
-    const int tix = (int)(col % a.ntx), tiy = (int)(col / a.ntx);
     const int x0 = g.ox0 + tix * TXO;
     const int y0 = HY ? g.oy0 + tiy * TYO : 0;
-    const int z0 = HZ ? g.oz0 + zs : 0;
     const int z1 = HZ ? z0 + zn : 1;
     const int cx = x0 - 1 + tx;
     const int cy = HY ? y0 - 1 + ty : 0;
@@ -589,9 +649,9 @@ __global__ void __launch_bounds__(BX * BY, 1) sweep_dense_kernel(const SweepArgs
     for (int i = l; i < NT / 32; i += 32) { v0 = red[0][i] < v0 ? red[0][i] : v0; v1 += red[1][i]; v2 += red[2][i]; v3 += red[3][i]; }
     v0 = warp_min(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
     if (l == 0 && a.part) {
-      const size_t nb = gridDim.x;
-      a.part[0 * nb + blockIdx.x] = v0; a.part[1 * nb + blockIdx.x] = v1;
-      a.part[2 * nb + blockIdx.x] = v2; a.part[3 * nb + blockIdx.x] = v3;
+      const size_t nb = a.part_stride ? (size_t)a.part_stride : (size_t)gridDim.x, c0 = (size_t)a.part_off + blockIdx.x;
+      a.part[0 * nb + c0] = v0; a.part[1 * nb + c0] = v1;
+      a.part[2 * nb + c0] = v2; a.part[3 * nb + c0] = v3;
     }
   }
 }

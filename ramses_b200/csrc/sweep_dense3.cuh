@@ -58,20 +58,17 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
   const double dtdx = dt / a.dx;               // trace3d: dtdx = dt/dx (hydro/umuscl.f90:516)
   // 32-bit ELEMENT indices (host side guarantees nvar*8*nslot < 2^32): one IMAD.WIDE per access instead of 64-bit adds
   const unsigned vstride = 8u * (unsigned)g.nslot;
-  const int nzo = g.oz1 - g.oz0;
 
   double my_dt = 1e300, my_mass = 0.0, my_etot = 0.0, my_eint = 0.0;
 
   long long w0 = a.nwork * blockIdx.x / gridDim.x;
   const long long w1 = a.nwork * (blockIdx.x + 1) / gridDim.x;
   while (w0 < w1) {
-    const long long col = w0 / nzo;
-    const int zs = (int)(w0 - col * nzo);
-    const int zn = (int)min((long long)(nzo - zs), w1 - w0);
+    int tix, tiy, z0, zn;
+    sweep_work_decode(a, w0, w1, tix, tiy, z0, zn);
     w0 += zn;
-    const int tix = (int)(col % a.ntx), tiy = (int)(col / a.ntx);
     const int x0 = g.ox0 + tix * TXO, y0 = g.oy0 + tiy * TYO;
-    const int z0 = g.oz0 + zs, z1 = z0 + zn;
+    const int z1 = z0 + zn;
     const int cx = x0 - 1 + tx, cy = y0 - 1 + ty;
 
     const bool col_own = (tx >= 1) && (tx <= BX - 2) && (cx < g.ox1);
@@ -367,9 +364,9 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
     for (int i = l; i < NT / 32; i += 32) { v0 = red[0][i] < v0 ? red[0][i] : v0; v1 += red[1][i]; v2 += red[2][i]; v3 += red[3][i]; }
     v0 = warp_min(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
     if (l == 0 && a.part) {
-      const size_t nb = gridDim.x;
-      a.part[0 * nb + blockIdx.x] = v0; a.part[1 * nb + blockIdx.x] = v1;
-      a.part[2 * nb + blockIdx.x] = v2; a.part[3 * nb + blockIdx.x] = v3;
+      const size_t nb = a.part_stride ? (size_t)a.part_stride : (size_t)gridDim.x, c0 = (size_t)a.part_off + blockIdx.x;
+      a.part[0 * nb + c0] = v0; a.part[1 * nb + c0] = v1;
+      a.part[2 * nb + c0] = v2; a.part[3 * nb + c0] = v3;
     }
   }
 }

@@ -245,6 +245,10 @@ class HydroGPU:
     def set_timing(self, on):
         _lib.check(self.L.rgpu_set_timing(int(on)))
 
+    def set_pipeline(self, on):
+        """Level-0 call: allow (default) / forbid the three-stream slab pipeline (rgpu_set_pipeline)."""
+        _lib.check(self.L.rgpu_set_pipeline(int(on)))
+
     def synchronize(self):
         _lib.check(self.L.rgpu_device_synchronize())
 

@@ -34,7 +34,7 @@ class Params(C.Structure):
 class LevelInfo(C.Structure):
     _fields_ = [("dense", C.c_int), ("ncell_box", C.c_int * 3), ("own_lo", C.c_int * 3), ("own_hi", C.c_int * 3),
                 ("wrap", C.c_int * 3), ("nslot", C.c_longlong), ("kernel_launches", C.c_longlong),
-                ("last_sweep_ms", C.c_double), ("last_steps_ms", C.c_double)]
+                ("last_sweep_ms", C.c_double), ("last_steps_ms", C.c_double), ("pipeline_slabs", C.c_int), ("sweep_variant", C.c_int)]
 
 
 def build(verbose=False):
@@ -105,6 +105,7 @@ def load():
     L.rgpu_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
     L.rgpu_get_level_info.argtypes = [C.c_int, C.POINTER(LevelInfo)]
     L.rgpu_set_timing.argtypes = [C.c_int]
+    L.rgpu_set_pipeline.argtypes = [C.c_int]
     L.rgpu_selftest_div.argtypes = [C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
     _lib = L
     return L

@@ -200,8 +200,11 @@ def test_fast_div_sqrt_match_ieee(gpu):
     assert bad.value == 0
 
 
-def test_multi_gpu_bit_identical_to_single_gpu(gpu):
-    """2 (or more) GPUs with NCCL ghost-oct exchange == the same global problem on one GPU, bit for bit."""
+@pytest.mark.parametrize("level", [5, 7])
+def test_multi_gpu_bit_identical_to_single_gpu(gpu, level):
+    """2 (or more) GPUs with NCCL ghost-oct exchange == the same global problem on one GPU, bit for bit.  level 5: 32^3 per
+    rank (one tile ring: the exchange is serial with the sweep); level 7: 128^3 per rank, where rgpu_level_steps splits the sweep
+    into interior and frame launches and overlaps the fused exchange of the previous step with the interior (stream s_x)."""
     import os
     import subprocess
     import sys
@@ -212,7 +215,7 @@ def test_multi_gpu_bit_identical_to_single_gpu(gpu):
     n = 2 if n < 4 else (4 if n < 8 else 8)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-           "--master-port", "29617", os.path.join(root, "tests", "mgpu_check.py"), "5", "6", "hllc"]
+           "--master-port", str(29617 + level), os.path.join(root, "tests", "mgpu_check.py"), str(level), "6", "hllc"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "state identical=True" in r.stdout
@@ -279,3 +282,49 @@ def test_full_size_256_properties(gpu):
     assert np.abs(dense[0] - dense[0].transpose(2, 1, 0)).max() <= 1e-12 * dense[0].max()
     assert np.abs(dense[1] - dense[2].transpose(0, 2, 1)).max() <= 1e-11 * np.abs(dense[1]).max()
     assert dense[0].max() > 1.05          # the blast is there
+
+
+@pytest.mark.parametrize("bound", [(0,) * 6, (1, 1, 0, 0, 2, 2)])
+@pytest.mark.parametrize("riemann", ["hllc", "llf"])
+def test_level0_pipelined_equals_serial_and_oracle(gpu, riemann, bound):
+    """rgpu_godunov_fine on host arrays with a spatially coherent (lattice) oct numbering runs as the three-stream z-slab pipeline
+    (H2D | gather + sweep + scatter | D2H): same bits as the serial order of the same call and as the oracle; periodic box and
+    a box with reflexive x walls / outflow z faces (ghost shells in the slab direction)."""
+    from ramses_b200.hydro import HydroGPU
+    c = Case(3, 6, riemann=riemann, slope_type=1, bound=bound, order=1, seed=5)
+    d0 = smooth_state(3, 64)
+    d0[0] *= 1 + 0.3 * (np.random.default_rng(11).standard_normal(d0[0].shape) > 1.0)
+    c.init_dense(d0)
+    dt, _ = c.oracle_courant()
+    ref = c.oracle_godunov(dt).reshape(c.nvar, -1)
+    a = c.amr_commons()
+    h = HydroGPU(a)
+    h.bind_level(c.level)
+    info = h.level_info(c.level)
+    assert info.dense == 1 and info.pipeline_slabs >= 3
+    a.dtnew[c.level] = dt
+    h.host_register(a.uold); h.host_register(a.unew)
+    out = {}
+    for mode in (1, 0):
+        h.set_pipeline(mode)
+        a.unew[:, :] = a.uold
+        h.godunov_fine(c.level)
+        out[mode] = a.unew.copy()
+    h.host_unregister(a.uold); h.host_unregister(a.unew)
+    h.finalize()
+    idx = c.active_cells()
+    assert np.array_equal(out[1], out[0])                       # every cell of the host array, ghosts and other levels included
+    assert np.array_equal(out[1][:, idx], ref[:, idx])
+
+
+def test_level0_creation_order_keeps_serial_path(gpu):
+    """the reference's creation order scatters a z-slab over the whole igrid window: no pipeline plan, serial order"""
+    from ramses_b200.hydro import HydroGPU
+    c = Case(3, 6, riemann="hllc", slope_type=1, order=0)
+    c.init_dense(smooth_state(3, 64))
+    a = c.amr_commons()
+    h = HydroGPU(a)
+    h.bind_level(c.level)
+    info = h.level_info(c.level)
+    h.finalize()
+    assert info.dense == 1 and info.pipeline_slabs == 0
