@@ -107,7 +107,7 @@ def cpu_reference_run_amr(workload, steps, warmup):
             u[0] = 1.0
             u[4] = (1e-5 + 0.4 * r / dxf ** 3) / (GAMMA - 1.0)
             a.uold[:, a.ncoarse + ind * a.ngridmax + ig - 1] = u
-    r = AmrRun(3, levelmin, levelmax, (0,) * 6, 1.0, nsubcycle=[1, 2, 2, 2], ngridmax=a.ngridmax, riemann=w["riemann"],
+    r = AmrRun(3, levelmin, levelmax, (0,) * 6, 1.0, nsubcycle=[2, 2, 2, 2], ngridmax=a.ngridmax, riemann=w["riemann"],
                slope_type=w["slope_type"], gamma=GAMMA, interpol_type=1, tout=[1e9])
     r.son[1:] = a.son; r.father[1:] = a.father; r.nbor[:, 1:] = a.nbor
     for l in range(1, levelmax + 1):
@@ -159,7 +159,7 @@ def amr_bench(args, w, rank, world, local_rank):
     h.upload_state(0)
     for l in range(levelmax - 1, 0, -1):
         h.upload_fine(l)
-    nsub = [1] * (levelmin + 1) + [2] * 64
+    nsub = [1] * levelmin + [2] * 64     # by level: nsubcycle(levelmin:) = 2 as in the reference's default (amr/read_params.f90)
     dtnew = {l: 0.0 for l in range(0, levelmax + 2)}
     dtold = {l: 0.0 for l in range(0, levelmax + 2)}
     ncell = {l: 8 * len(a.active[l]) for l in range(levelmin, levelmax + 1)}

@@ -155,8 +155,13 @@ int rgpu_upload_fine(int ilevel);                          /* hydro/interpol_hyd
  * dt_hist (nstep doubles, may be NULL) receives the dt of every step; sums_last[3]
  * (may be NULL) the courant_fine sums of the final state.                         */
 int rgpu_level_steps(int ilevel, int nstep, double* dt_hist, double sums_last[3]);
-/* AMR mode: ncoarse_steps calls of amr_step(levelmin, 1) (amr/amr_step.f90: recursion over the bound levels, sub-cycling
- * nsubcycle(l) = 1 or 2 indexed by level like amr_parameters.f90:nsubcycle, :326 courant, :333 set_unew, :388 godunov_fine,
+/* numbtot(1,1:nlevelmax) of amr_commons: octs per level summed over all ranks (NCCL all-reduce of the bound levels' active
+ * counts in AMR mode).  The reference gates amr_step and its recursion on this GLOBAL count (amr/amr_step.f90:33,345); a rank
+ * that owns no oct of a level must still bind the level (ngrid_active = 0) and take part in its collectives.            */
+int rgpu_level_totals(int nlevelmax, int* numbtot);
+/* AMR mode: ncoarse_steps calls of amr_step(levelmin, 1) (amr/amr_step.f90: recursion over the levels whose GLOBAL oct count is
+ * non-zero, sub-cycling nsubcycle(l) = 1 or 2; `nsubcycle` is the Fortran array nsubcycle(1:nlevelmax) of amr_parameters.f90
+ * passed as it is: nsubcycle[l-1] = nsubcycle(l), nlevelmax elements.  :326 courant, :333 set_unew, :388 godunov_fine,
  * :397/:505 ghost exchanges, :423 set_uold, :441 upload_fine, :514 boundaries, :567-577 dt synchronisation) on a frozen mesh,
  * with dtnew/dtold device resident: no host round trip inside a coarse step.  dt_hist (may be NULL) receives dtnew(levelmin)
  * of every coarse step.                                                                                              */

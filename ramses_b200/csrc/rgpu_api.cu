@@ -155,12 +155,14 @@ struct AmrLevel {
 struct Context {
   bool init = false;
   bool amr = false;
-  int* d_son = nullptr; int* d_father = nullptr; int* d_nbor = nullptr;
+  int* d_son = nullptr; int* d_son_base = nullptr; int* d_father = nullptr; int* d_nbor = nullptr;
   double* d_uold = nullptr; double* d_unew = nullptr;
   long long ncell = 0;
   int interpol_type = 1;
   AmrLevel alev[MAXLEVEL + 1];
   double* d_dtn = nullptr; double* d_dto = nullptr;   // device-resident dtnew/dtold(0:MAXLEVEL+1) of rgpu_amr_steps
+  int numbtot[MAXLEVEL + 2] = {0};                    // numbtot(1,ilevel): octs of a level over ALL ranks (amr_commons.f90)
+  int* d_numb = nullptr;
   rgpu_params p{};
   Phys phys{};
   MPhys mphys{};
@@ -1042,8 +1044,8 @@ int rgpu_finalize(void) {
   cudaStreamSynchronize(G.stream);
   for (int l = 0; l <= MAXLEVEL; l++) if (G.lev[l].bound) free_level(G.lev[l]);
   for (int l = 0; l <= MAXLEVEL; l++) if (G.alev[l].bound) free_amr_level(G.alev[l]);
-  cudaFree(G.d_son); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew); cudaFree(G.d_dtn); cudaFree(G.d_dto);
-  G.d_son = G.d_father = G.d_nbor = nullptr; G.d_uold = G.d_unew = nullptr; G.d_dtn = G.d_dto = nullptr; G.ncell = 0; G.amr = false;
+  cudaFree(G.d_son_base); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew); cudaFree(G.d_dtn); cudaFree(G.d_dto); cudaFree(G.d_numb);
+  G.d_numb = nullptr; G.d_son_base = nullptr; G.d_son = G.d_father = G.d_nbor = nullptr; G.d_uold = G.d_unew = nullptr; G.d_dtn = G.d_dto = nullptr; G.ncell = 0; G.amr = false;
   if (G.comm_x) { ncclCommDestroy(G.comm_x); G.comm_x = nullptr; }
   if (G.comm) { ncclCommDestroy(G.comm); G.comm = nullptr; }
   cudaStreamDestroy(G.s_x);
@@ -1073,9 +1075,12 @@ int rgpu_bind_tree(int ncoarse, int ngridmax, const int* son, const int* father,
   if (G.amr) {   // mirror the tree (read-only during a step; re-bind after every regrid)
     const long long ncell = (long long)ncoarse + (long long)T_() * ngridmax;
     if (ncell != G.ncell) {
-      cudaFree(G.d_son); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew);
-      G.d_son = G.d_father = G.d_nbor = nullptr; G.d_uold = G.d_unew = nullptr;
-      CUDA_OK(cudaMalloc(&G.d_son, sizeof(int) * ncell));
+      cudaFree(G.d_son_base); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew);
+      G.d_son_base = nullptr; G.d_son = G.d_father = G.d_nbor = nullptr; G.d_uold = G.d_unew = nullptr;
+      // one leading zero: son(0) = 0 is what a missing neighbour father cell (nbor == 0 at an uncovered box corner) reads
+      CUDA_OK(cudaMalloc(&G.d_son_base, sizeof(int) * (ncell + 1)));
+      CUDA_OK(cudaMemset(G.d_son_base, 0, sizeof(int)));
+      G.d_son = G.d_son_base + 1;
       CUDA_OK(cudaMalloc(&G.d_father, sizeof(int) * ngridmax));
       CUDA_OK(cudaMalloc(&G.d_nbor, sizeof(int) * (size_t)2 * G.p.ndim * ngridmax));
       CUDA_OK(cudaMalloc(&G.d_uold, sizeof(double) * G.p.nvar * ncell));
@@ -1856,9 +1861,25 @@ int rgpu_level_steps(int ilevel, int nstep, double* dt_hist, double sums_last[3]
 // level's dt/nsubcycle and the dtnew(l-1) = dtold(l) + dtnew(l) synchronisation are tiny kernels on device-resident
 // dtnew/dtold, so the ~90 launches of a coarse step queue back to back.  Same arithmetic, same order as the host-driven
 // sequence (ramses_b200.hydro.amr_step): bit-identical state and time steps.
+// numbtot(1,ilevel) over all ranks (the reference gates amr_step and its recursion on the GLOBAL oct count, amr/amr_step.f90:33,345:
+// a rank that owns no oct of a level still takes part in the level's all-reduce and ghost exchanges)
+static int refresh_numbtot() {
+  for (int l = 0; l <= MAXLEVEL + 1; l++) G.numbtot[l] = (l >= 1 && l <= MAXLEVEL && G.alev[l].bound) ? G.alev[l].nact : 0;
+  if (G.comm && G.nranks > 1) {
+    if (!G.d_numb) CUDA_OK(cudaMalloc(&G.d_numb, sizeof(int) * (MAXLEVEL + 2)));
+    CUDA_OK(cudaMemcpyAsync(G.d_numb, G.numbtot, sizeof(int) * (MAXLEVEL + 2), cudaMemcpyHostToDevice, G.stream));
+    NCCL_OK(ncclAllReduce(G.d_numb, G.d_numb, MAXLEVEL + 2, ncclInt, ncclSum, G.comm, G.stream));
+    CUDA_OK(cudaMemcpyAsync(G.numbtot, G.d_numb, sizeof(int) * (MAXLEVEL + 2), cudaMemcpyDeviceToHost, G.stream));
+    CUDA_OK(cudaStreamSynchronize(G.stream));
+  }
+  return RGPU_OK;
+}
+
+// nsub = nsubcycle(1:nlevelmax) of amr_parameters, passed as the Fortran array: nsub[l-1] = nsubcycle(l)
 static int amr_step_dev(int l, int icount, int levelmin, const int* nsub) {
   AmrLevel& A = G.alev[l];
-  if (!A.bound || A.nact == 0) return RGPU_OK;
+  if (G.numbtot[l] == 0) return RGPU_OK;                                   // amr_step.f90:33
+  if (!A.bound) return fail(RGPU_EINVAL, "level %d holds octs on other ranks: bind it on every rank (ngrid_active = 0 is fine)", l);
   const int nlev = G.p.nlevelmax;
   int rc;
   auto op = [&](int o, int lev, double nsc, double nsl, int ic) {
@@ -1876,20 +1897,20 @@ static int amr_step_dev(int l, int icount, int levelmin, const int* nsub) {
     if (G.comm && G.nranks > 1) NCCL_OK(ncclAllReduce(A.d_dt, A.d_dt, 1, ncclDouble, ncclMin, G.comm, G.stream));
     A.launches += 2;
   }
-  op(DT_AFTER_COURANT, l, l > levelmin ? (double)nsub[l - 1] : 1.0, 1.0, icount);
+  op(DT_AFTER_COURANT, l, l > levelmin ? (double)nsub[l - 2] : 1.0, 1.0, icount);
   rc = amr_copy(A, G.d_uold, G.d_unew); if (rc) return rc;           // set_unew :333
   rc = amr_zero_ghost_unew(A); if (rc) return rc;
-  if (l < nlev && G.alev[l + 1].bound && G.alev[l + 1].nact > 0) {     // :345-361
+  if (l < nlev && G.numbtot[l + 1] > 0) {                               // :345-361
     rc = amr_step_dev(l + 1, 1, levelmin, nsub); if (rc) return rc;
-    if (nsub[l] == 2) { rc = amr_step_dev(l + 1, 2, levelmin, nsub); if (rc) return rc; }
+    if (nsub[l - 1] == 2) { rc = amr_step_dev(l + 1, 2, levelmin, nsub); if (rc) return rc; }
   } else if (l < nlev) {
-    op(DT_NO_FINER, l, 1.0, (double)nsub[l], icount);
+    op(DT_NO_FINER, l, 1.0, (double)nsub[l - 1], icount);
   }
   rc = amr_godunov(A, l, 0.0, G.d_dtn + l); if (rc) return rc;         // :388
   if (G.comm && G.nranks > 1) { rc = amr_exchange(A, G.d_unew, true); if (rc) return rc; }     // :397
   {   // set_uold :423 (+ passive-scalar floor fix)
     const int nps = G.p.nvar - (G.p.ndim + 2);
-    if (nps > 0) {
+    if (nps > 0 && A.nact > 0) {
       const int n = A.nact * T_();
       amr_scalar_floor_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_unew, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(),
                                                                   G.p.ndim + 2, G.p.nvar, G.p.smallr);
@@ -1897,7 +1918,7 @@ static int amr_step_dev(int l, int icount, int levelmin, const int* nsub) {
     }
     rc = amr_copy(A, G.d_unew, G.d_uold); if (rc) return rc;
   }
-  if (l < nlev) {                                                       // upload_fine :441
+  if (l < nlev && A.nact > 0) {                                         // upload_fine :441
     const int n = A.nact * T_();
     amr_upload_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_son - 1, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar, G.p.smallr);
     CUDA_OK(cudaGetLastError());
@@ -1905,7 +1926,7 @@ static int amr_step_dev(int l, int icount, int levelmin, const int* nsub) {
   }
   if (G.comm && G.nranks > 1) { rc = amr_exchange(A, G.d_uold, false); if (rc) return rc; }    // :505
   rc = amr_boundaries(A); if (rc) return rc;                           // :514
-  if (l > levelmin) op(DT_SYNC_COARSE, l, (double)nsub[l - 1], 1.0, icount);   // :567-577
+  if (l > levelmin) op(DT_SYNC_COARSE, l, (double)nsub[l - 2], 1.0, icount);   // :567-577
   A.launches += 4;
   return RGPU_OK;
 }
@@ -1914,7 +1935,8 @@ int rgpu_amr_steps(int levelmin, const int* nsubcycle, int ncoarse_steps, double
   if (!G.init || !G.amr) return fail(RGPU_EINVAL, "rgpu_amr_steps needs AMR mode (rgpu_set_amr)");
   if (levelmin < 1 || levelmin > G.p.nlevelmax || !nsubcycle || ncoarse_steps < 1) return fail(RGPU_EINVAL, "bad argument");
   for (int l = levelmin; l <= G.p.nlevelmax; l++)
-    if (nsubcycle[l] != 1 && nsubcycle[l] != 2) return fail(RGPU_EINVAL, "nsubcycle(%d)=%d (1 or 2)", l, nsubcycle[l]);   // amr/read_params.f90:441
+    if (nsubcycle[l - 1] != 1 && nsubcycle[l - 1] != 2) return fail(RGPU_EINVAL, "nsubcycle(%d)=%d (1 or 2)", l, nsubcycle[l - 1]);   // amr/read_params.f90:441
+  { const int rc0 = refresh_numbtot(); if (rc0) return rc0; }
   if (!G.d_dtn) {
     CUDA_OK(cudaMalloc(&G.d_dtn, sizeof(double) * (MAXLEVEL + 2)));
     CUDA_OK(cudaMalloc(&G.d_dto, sizeof(double) * (MAXLEVEL + 2)));
@@ -1936,6 +1958,14 @@ int rgpu_amr_steps(int levelmin, const int* nsubcycle, int ncoarse_steps, double
   cudaFree(d_hist);
   if (dt_hist) memcpy(dt_hist, hist.data(), sizeof(double) * ncoarse_steps);
   { float ms = 0; cudaEventElapsedTime(&ms, G.ev2, G.ev3); G.alev[levelmin].last_steps_ms = ms; }
+  return RGPU_OK;
+}
+
+int rgpu_level_totals(int nlevelmax, int* numbtot) {
+  if (!G.init || !numbtot || nlevelmax < 1 || nlevelmax > MAXLEVEL) return fail(RGPU_EINVAL, "bad argument");
+  if (G.amr) { const int rc = refresh_numbtot(); if (rc) return rc; }
+  else for (int l = 1; l <= nlevelmax; l++) G.numbtot[l] = 0;
+  for (int l = 1; l <= nlevelmax; l++) numbtot[l - 1] = G.numbtot[l];
   return RGPU_OK;
 }
 

@@ -230,11 +230,22 @@ class HydroGPU:
         return dts, list(sums)
 
     def amr_steps(self, levelmin, nsubcycle, ncoarse_steps):
-        """ncoarse_steps x amr_step(levelmin, 1) with device-resident time steps (rgpu_amr_steps); returns dtnew(levelmin) per step."""
-        ns = np.ascontiguousarray(list(nsubcycle) + [2] * 64, dtype=np.int32)[: self.a.nlevelmax + 2]
+        """ncoarse_steps x amr_step(levelmin, 1) with device-resident time steps (rgpu_amr_steps); returns dtnew(levelmin) per step.
+        nsubcycle: list indexed by LEVEL (element 0 unused), like amr_step below; the C-ABI takes the Fortran array
+        nsubcycle(1:nlevelmax), i.e. the same list without its element 0."""
+        ns = np.ascontiguousarray((list(nsubcycle) + [2] * 64)[1: self.a.nlevelmax + 1], dtype=np.int32)
         dts = np.zeros(ncoarse_steps)
         _lib.check(self.L.rgpu_amr_steps(levelmin, _ip(ns), ncoarse_steps, _dp(dts)))
         return dts
+
+    def level_totals(self):
+        """numbtot(1,1:nlevelmax): octs per level over all ranks (NCCL sum in AMR mode); stored in a.numbtot (dict by level)."""
+        n = self.a.nlevelmax
+        out = (C.c_int * n)()
+        _lib.check(self.L.rgpu_level_totals(n, out))
+        self.a.numbtot = {l: int(out[l - 1]) for l in range(1, n + 1)}
+        self.a.numbtot[n + 1] = 0
+        return self.a.numbtot
 
     def host_register(self, arr):
         _lib.check(self.L.rgpu_host_register(arr.ctypes.data, arr.nbytes))
@@ -262,7 +273,11 @@ def amr_step(h, ilevel, icount, levelmin, nsubcycle, dtnew, dtold, multi_rank=Fa
     `HydroGPU` call of the same name.  dtnew/dtold: dicts indexed by level (amr_commons dtnew/dtold); nsubcycle: list
     indexed by level (amr_parameters.f90:nsubcycle, 1 or 2).  Line numbers refer to amr/amr_step.f90."""
     a = h.a
-    if len(a.active.get(ilevel, [])) == 0:                       # numbtot(1,ilevel)==0 :37
+    # numbtot(1,ilevel): the GLOBAL oct count gates the step and the recursion (:33, :345) -- a rank without octs at a level
+    # still takes part in the level's all-reduce and exchanges.  a.numbtot (HydroGPU.level_totals) when set, else local counts
+    nt = getattr(a, "numbtot", None)
+    ntot = (lambda l: nt.get(l, 0)) if nt else (lambda l: len(a.active.get(l, [])))
+    if ntot(ilevel) == 0:
         return
     dtold[ilevel] = dtnew[ilevel]
     a.dtnew[ilevel] = a.boxlen / a.smallc                        # newdt_fine :326 (pm/newdt_fine.f90:47-51)
@@ -271,7 +286,7 @@ def amr_step(h, ilevel, icount, levelmin, nsubcycle, dtnew, dtold, multi_rank=Fa
         dtnew[ilevel] = min(dtnew[ilevel - 1] / float(nsubcycle[ilevel - 1]), dtnew[ilevel])
     a.dtnew[ilevel] = dtnew[ilevel]
     h.set_unew(ilevel)                                           # :333
-    if ilevel < a.nlevelmax and len(a.active.get(ilevel + 1, [])) > 0:     # recursive call :345-361
+    if ilevel < a.nlevelmax and ntot(ilevel + 1) > 0:                      # recursive call :345-361
         for ic in ((1, 2) if nsubcycle[ilevel] == 2 else (1,)):
             amr_step(h, ilevel + 1, ic, levelmin, nsubcycle, dtnew, dtold, multi_rank)
     elif ilevel < a.nlevelmax:

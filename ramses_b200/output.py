@@ -174,7 +174,7 @@ def write_snapshot(outdir, iout, *, ndim, nvar, levelmin, nlevelmax, ngridmax, n
     names = ["density"] + ["velocity_" + "xyz"[k] for k in range(3 if mhd else ndim)]
     if mhd:
         names += ["B_%s_left" % c for c in "xyz"] + ["B_%s_right" % c for c in "xyz"]
-    names += ["pressure"] + ["scalar_%02d" % (k + 1) for k in range(nvar - (8 if mhd else ndim + 2))]
+    names += ["pressure"] + ["scalar_%02d" % k for k in range(nvar - (8 if mhd else ndim + 2))]   # hydro/output_hydro.f90: ivar-ndim-3-nener, 0-based
     with open(os.path.join(d, "hydro_file_descriptor.txt"), "w") as f:
         f.write("# version:  1\n# ivar, variable_name, variable_type\n")
         for i, nm in enumerate(names):
@@ -236,7 +236,7 @@ def snapshot_from_commons(a, outdir, iout, t=0.0, levelmin=None, nstep=0, nstep_
         coarse_max=(a.icoarse_max, a.jcoarse_max, a.kcoarse_max), boxlen=a.boxlen, gamma=a.gamma, smallr=a.smallr, son=a.son,
         father=a.father, nbor=a.nbor, xg=xg, active=[a.active.get(l, empty) for l in range(1, L + 1)],
         boundary=[[(a.boundary.get(l) or [empty] * nb)[b] for l in range(1, L + 1)] for b in range(nb)], uold=a.uold, t=t,
-        dtold=[a.dtnew.get(l, 0.0) for l in range(1, L + 1)], dtnew=[a.dtnew.get(l, 0.0) for l in range(1, L + 1)], nstep=nstep,
+        dtold=[getattr(a, "dtold", a.dtnew).get(l, 0.0) for l in range(1, L + 1)], dtnew=[a.dtnew.get(l, 0.0) for l in range(1, L + 1)], nstep=nstep,
         nstep_coarse=nstep_coarse, mhd=a.mhd)
 
 
@@ -315,6 +315,9 @@ def read_snapshot(outdir, iout, smallr=1e-10):
                     arr[ncoarse + ind * ngridmax + gi] = r.ints()
     h = _Reader(os.path.join(d, "hydro_" + nchar + ".out00001"))
     h.ints(); nvar = int(h.ints()[0]); h.ints(); h.ints(); h.ints(); gamma = float(h.dbls()[0])
+    if nvar != ndim + 2 and nvar < ndim + 2 or nvar == 11 and ndim == 3:
+        raise ValueError("read_snapshot rebuilds hydro builds only (nvar = ndim+2 [+ passive scalars]); an MHD snapshot "
+                         "(11 records per cell: 3 velocities, 6 face fields) is not supported")
     uold = np.zeros((nvar, ncell))
     for l in range(nlevelmax):
         for dom in range(1 + nboundary):

@@ -18,8 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from ramses_b200 import lib as _l                      # noqa: E402
-from ramses_b200.hydro import HydroGPU                 # noqa: E402
-from test_gpu_amr import commons_from_run              # noqa: E402
+from ramses_b200.hydro import HydroGPU, amr_step       # noqa: E402
+from test_gpu_amr import commons_from_run, BOUND_2D_WALLS_X_OUTFLOW_Y   # noqa: E402
 
 
 def build_run(ndim):
@@ -33,7 +33,8 @@ def build_run(ndim):
         regs = [dict(type="square", x_center=0.5, y_center=0.5, length_x=10, length_y=10, exp_region=10, d=1.0, p=0.1),
                 dict(type="square", x_center=0.45, y_center=0.4, length_x=0.4, length_y=0.25, exp_region=2, d=2.0, u=0.3, v=-0.2, p=1.0)]
         r = AmrRun(2, 3, 6, (1, 1, 2, 2, 0, 0), 1.0, nsubcycle=[1, 2, 2], ngridmax=40000, riemann="hllc", slope_type=2,
-                   err_grad_d=0.05, err_grad_u=0.05, err_grad_p=0.05, interpol_type=2, regions=regs, tout=[1e9])
+                   err_grad_d=0.05, err_grad_u=0.05, err_grad_p=0.05, interpol_type=2, regions=regs, tout=[1e9],
+                   bound_regions=BOUND_2D_WALLS_X_OUTFLOW_Y)      # y regions cover the corner cells (implosion.nml:17-24)
     r.flag_coarse(); r.init_refine(); r.init_refine_2()
     for i in range(r.levelmin, r.nlevelmax + 1):
         if i > r.levelmin:
@@ -44,40 +45,9 @@ def build_run(ndim):
     return r
 
 
-def amr_step(h, a, r, ntot, l, icount, dtnew, dtold, multi):
-    if ntot[l] == 0:
-        return
-    dtold[l] = dtnew[l]
-    a.dtnew[l] = a.boxlen / a.smallc
-    dtnew[l] = h.courant_fine(l)
-    if l > r.levelmin:
-        dtnew[l] = min(dtnew[l - 1] / float(r.nsubcycle[l - 1]), dtnew[l])
-    a.dtnew[l] = dtnew[l]
-    h.set_unew(l)
-    if l < r.nlevelmax and ntot[l + 1] > 0:
-        for ic in ((1, 2) if r.nsubcycle[l] == 2 else (1,)):
-            amr_step(h, a, r, ntot, l + 1, ic, dtnew, dtold, multi)
-    elif l < r.nlevelmax:
-        dtold[l + 1] = dtnew[l] / float(r.nsubcycle[l])
-        dtnew[l + 1] = dtnew[l] / float(r.nsubcycle[l])
-    a.dtnew[l] = dtnew[l]
-    h.godunov_fine_dev(l)                                       # amr_step.f90:388
-    if multi:
-        h.make_virtual_reverse(l)                               # :397
-    h.set_uold(l)                                               # :423
-    h.upload_fine(l)                                            # :441
-    if multi:
-        h.make_virtual_fine(l)                                  # :505
-    h.make_boundary_hydro(l)                                    # :514
-    if l > r.levelmin:
-        if r.nsubcycle[l - 1] == 1:
-            dtnew[l - 1] = dtnew[l]
-        if icount == 2:
-            dtnew[l - 1] = dtold[l] + dtnew[l]
-
-
 def main():
     ndim = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    empty_top = len(sys.argv) > 2 and sys.argv[2] == "empty"     # the last rank owns NO oct of the finest level
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
@@ -90,6 +60,8 @@ def main():
         ig = np.array(r.active[l], dtype=np.int64)
         frac = r.xg[0, ig] - r.m.icoarse_min
         owner[l] = np.minimum((frac * world).astype(np.int64), world - 1)
+        if empty_top and l == L:
+            owner[l] = np.minimum(owner[l], max(world - 2, 0))
 
     def make_commons(ncpu, myid):
         a = commons_from_run(r, "hllc", r.p.slope_type)
@@ -116,11 +88,25 @@ def main():
     for l in range(1, L + 1):
         if ntot[l]:
             h.bind_level(l)          # a rank without active octs at a level is bound too: it takes part in the exchanges
+    tot = h.level_totals()           # numbtot(1,:) through the library (NCCL sum of the per-rank active counts)
+    assert all(tot[l] == ntot[l] for l in range(1, L + 1)), (tot, ntot)
+    if empty_top and rank == world - 1:
+        assert len(a.active[L]) == 0
+    a._u_start = a.uold.copy()
     h.upload_state(0)
     dtnew = {l: r.dtnew[l] for l in range(0, L + 2)}
     dtold = {l: r.dtold[l] for l in range(0, L + 2)}
-    amr_step(h, a, r, ntot, r.levelmin, 1, dtnew, dtold, True)
+    amr_step(h, r.levelmin, 1, r.levelmin, r.nsubcycle, dtnew, dtold, multi_rank=True)     # the library's host mirror of amr_step
     h.download_state(0)
+    # the same coarse step through rgpu_amr_steps (time steps on the device) from the same initial state: identical bits
+    u_host_driven = a.uold.copy()
+    a.uold[:, :] = a._u_start
+    h.upload_state(0)
+    nsl = [1] + [r.nsubcycle.get(l, 2) for l in range(1, L + 2)]        # by level, element 0 unused
+    dts_dev = h.amr_steps(r.levelmin, nsl, 1)
+    h.download_state(0)
+    same_dev = bool(np.array_equal(a.uold, u_host_driven)) and dts_dev[0] == dtnew[r.levelmin]
+    a.uold[:, :] = u_host_driven
     launches = sum(h.level_info(l).kernel_launches for l in range(1, L + 1) if ntot[l])
     h.finalize()
     # owned cells of every rank -> everybody
@@ -142,7 +128,7 @@ def main():
         h1.upload_state(0)
         d1 = {l: r.dtnew[l] for l in range(0, L + 2)}
         d2 = {l: r.dtold[l] for l in range(0, L + 2)}
-        amr_step(h1, a1, r, ntot, r.levelmin, 1, d1, d2, False)
+        amr_step(h1, r.levelmin, 1, r.levelmin, r.nsubcycle, d1, d2, multi_rank=False)
         h1.download_state(0)
         h1.finalize()
         sel = mk.cpu().numpy() > 0
@@ -156,8 +142,10 @@ def main():
         print(f"mgpu_amr_check world={world} ndim={ndim} octs/level={[ntot[l] for l in range(1, L + 1)]}: cells={int(sel.sum())} "
               f"max rel diff={err:.3e} identical fraction={nid:.6f} dt identical={same_dt} each cell owned once={once} launches/rank={launches}")
         ok = err <= 1e-13 and same_dt and once
-    flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.broadcast(flag, 0)
+    flag = torch.tensor([1 if (ok and same_dev) else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"rgpu_amr_steps == host-driven amr_step on every rank: {bool(flag.item())}")
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1 else 1)
 

@@ -62,13 +62,19 @@ def gpu_amr_step(h, a, r, l, icount, dtnew, dtold):
             dtnew[l - 1] = dtold[l] + dtnew[l]
 
 
+# 2-D box with reflexive x walls and outflow y faces: BOUNDARY_PARAMS whose y regions include the corner cells, like the
+# reference's own namelists (tests/hydro/implosion/implosion.nml:17-24) -- every oct of the box then has all its neighbour
+# father cells (a region per face only would leave the diagonal father cell of a corner oct undefined: son(0))
+BOUND_2D_WALLS_X_OUTFLOW_Y = [(1, (0, 0), (1, 1), (0, 0)), (2, (2, 2), (1, 1), (0, 0)), (13, (0, 2), (0, 0), (0, 0)), (14, (0, 2), (2, 2), (0, 0))]
+
+
 def run_case(ndim, levelmin, levelmax, bound, regions, riemann, slope_type, ncoarse_dev, interpol_type, nsub, boxlen=1.0,
-             err=0.05, nexpand=1, difmag=0.0):
+             err=0.05, nexpand=1, difmag=0.0, bound_regions=None):
     from oracle.amr import AmrRun
     from ramses_b200.hydro import HydroGPU
     r = AmrRun(ndim, levelmin, levelmax, bound, boxlen, nsubcycle=nsub, nexpand=nexpand, ngridmax=20000, riemann=riemann,
                slope_type=slope_type, err_grad_d=err, err_grad_u=err, err_grad_p=err, interpol_type=interpol_type,
-               regions=regions, tout=[1e9])
+               regions=regions, tout=[1e9], bound_regions=bound_regions)
     r.p.difmag = difmag                            # hydro_parameters.f90:81 (cmpdivu + consup in unsplit)
     r.flag_coarse(); r.init_refine(); r.init_refine_2()
     for _ in range(ncoarse_dev):                   # develop the flow with the full (regridding) driver
@@ -125,7 +131,7 @@ def test_amr_1d_sod_bitwise(riemann, slope_type, interpol_type):
 def test_amr_2d_bitwise():
     regs = [dict(type="square", x_center=0.5, y_center=0.5, length_x=10, length_y=10, exp_region=10, d=1.0, p=0.1),
             dict(type="square", x_center=0.3, y_center=0.4, length_x=0.3, length_y=0.25, exp_region=2, d=2.0, u=0.3, v=-0.2, p=1.0)]
-    got, ref, dtnew, r, nlev = run_case(2, 3, 5, (1, 1, 2, 2, 0, 0), regs, "hllc", 2, 2, 2, [1, 2])
+    got, ref, dtnew, r, nlev = run_case(2, 3, 5, (1, 1, 2, 2, 0, 0), regs, "hllc", 2, 2, 2, [1, 2], bound_regions=BOUND_2D_WALLS_X_OUTFLOW_Y)
     assert dtnew[3] == r.dtnew[3]
     assert np.array_equal(got, ref), (np.abs(got - ref).max(), nlev)
 
@@ -150,7 +156,7 @@ def test_amr_difmag_bitwise(ndim):
     elif ndim == 2:
         regs = [dict(type="square", x_center=0.5, y_center=0.5, length_x=10, length_y=10, exp_region=10, d=1.0, p=0.1),
                 dict(type="square", x_center=0.3, y_center=0.4, length_x=0.3, length_y=0.25, exp_region=2, d=2.0, u=0.3, v=-0.2, p=1.0)]
-        got, ref, dtnew, r, nlev = run_case(2, 3, 5, (1, 1, 2, 2, 0, 0), regs, "hllc", 2, 2, 2, [1, 2], difmag=0.2)
+        got, ref, dtnew, r, nlev = run_case(2, 3, 5, (1, 1, 2, 2, 0, 0), regs, "hllc", 2, 2, 2, [1, 2], difmag=0.2, bound_regions=BOUND_2D_WALLS_X_OUTFLOW_Y)
     else:
         regs = [dict(type="square", x_center=0.5, y_center=0.5, z_center=0.5, length_x=10, length_y=10, length_z=10, exp_region=10, d=1.0, p=0.1),
                 dict(type="square", x_center=0.4, y_center=0.45, z_center=0.55, length_x=0.3, length_y=0.3, length_z=0.3, exp_region=2, d=1.5, p=2.0)]

@@ -221,9 +221,12 @@ def test_multi_gpu_bit_identical_to_single_gpu(gpu, level):
     assert "state identical=True" in r.stdout
 
 
-def test_multi_gpu_amr_matches_single_gpu(gpu):
+@pytest.mark.parametrize("args", [("2",), ("3",), ("3", "empty")])
+def test_multi_gpu_amr_matches_single_gpu(gpu, args):
     """AMR mode with NCCL ghost-oct exchange (forward copy + reverse reflux accumulation) on 2 GPUs == one GPU
-    (<= 1e-13: refluxes arriving from different ranks are summed in a different order)."""
+    (<= 1e-13: refluxes arriving from different ranks are summed in a different order), through the library's amr_step and
+    through rgpu_amr_steps; "empty": the last rank owns no oct of the finest level and still takes part in that level's
+    all-reduce and exchanges (numbtot gating, amr/amr_step.f90:33,345)."""
     import os
     import subprocess
     import sys
@@ -232,7 +235,7 @@ def test_multi_gpu_amr_matches_single_gpu(gpu):
         pytest.skip("needs >= 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29641", os.path.join(root, "tests", "mgpu_amr_check.py"), "2"]
+           "--master-port", str(29641 + len(args) + int(args[0])), os.path.join(root, "tests", "mgpu_amr_check.py"), *args]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
@@ -328,3 +331,30 @@ def test_level0_creation_order_keeps_serial_path(gpu):
     info = h.level_info(c.level)
     h.finalize()
     assert info.dense == 1 and info.pipeline_slabs == 0
+
+
+@pytest.mark.parametrize("riemann,level,nstep", [("hllc", 7, 8), ("llf", 7, 8), ("exact", 7, 8), ("exact", 8, 4), ("hllc", 8, 4)])
+def test_sedov3d_large_grid_vs_oracle(gpu, riemann, level, nstep):
+    """GPU vs oracle at the sizes the bench measures (VERDICT r1 weak #1b): sedov3d on 128^3 and 256^3, fused level steps.
+    hllc / llf: dt history and conserved state bit for bit (np.array_equal); exact: <= 1e-12 relative (CUDA pow vs libm pow in
+    the rarefaction branch, hydro/godunov_utils.f90:415,453), the tolerance north_star states."""
+    from ramses_b200.hydro import HydroGPU
+    c = Case(3, level, riemann=riemann, slope_type=1, boxlen=0.5)
+    c.init_regions(SEDOV3D_REGIONS)
+    ref, dts_ref = c.oracle_steps(nstep, nthreads=16)
+    a = c.amr_commons()
+    h = HydroGPU(a)
+    h.bind_level(c.level)
+    h.upload_state(c.level)
+    dts, _ = h.level_steps(c.level, nstep)
+    h.download_state(c.level)
+    h.finalize()
+    idx = c.active_cells()
+    ref = ref.reshape(c.nvar, -1)
+    assert np.abs(ref[:, idx] - c.u.reshape(c.nvar, -1)[:, idx]).max() > 0          # the blast moved
+    if riemann == "exact":
+        assert np.allclose(dts, dts_ref, rtol=1e-12, atol=0)
+        assert max_rel_err(a.uold[:, idx], ref[:, idx]) <= 1e-12
+    else:
+        assert np.array_equal(dts, dts_ref)
+        assert np.array_equal(a.uold[:, idx], ref[:, idx])
