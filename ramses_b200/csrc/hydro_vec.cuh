@@ -214,7 +214,7 @@ __device__ __forceinline__ void riemann_hllc_v(const V* ql, const V* qr, V* fg, 
   fg[1] = ro * uo * uo + Po;
   fg[2] = (eto + Po) * uo;
 #pragma unroll
-  for (int n = 3; n < 5; n++) fg[n] = vsel(c2, ro * uo * ql[n], ro * uo * qr[n]);   // :1190-1203
+  for (int n = 3; n < 5; n++) fg[n] = ro * uo * vsel(c2, ql[n], qr[n]);   // :1190-1203 (the upwind value is selected first: one product)
 }
 
 // shared tail of 'exact' and 'acoustic' (godunov_utils.f90:474-493, :634-652)

@@ -1327,10 +1327,9 @@ static int alloc_dense_store(Level& L, int ncpu, int nboundary, const int* bound
   int minb = 1;
   L.variant = 0;
   if (nd == 3 && !G.p.mhd && !G.amr) {   // plain dense 3-D sweep: round-2 kernel; RGPU_SWEEP=old|<variant> for tuning runs
-    // measured on B200 (profiles/r2_tune_sweep.md): the two-barrier loop wins by 1-2 % for the short solvers (llf, hll, hllc);
-    // the round-1 loop stays faster for the long ones (exact, acoustic: five inlined solver copies overflow the I-cache)
-    const bool short_solver = G.p.riemann == RGPU_RIEMANN_LLF || G.p.riemann == RGPU_RIEMANN_HLL || G.p.riemann == RGPU_RIEMANN_HLLC;
-    L.variant = short_solver ? SWEEP3_DEFAULT_VARIANT : 0;
+    // measured on B200 (profiles/r2_tune_sweep.md): the two-barrier loop (sweep3_kernel, three scalar branch-free solves) is
+    // 8-11 % faster than the round-1 loop for every solver
+    L.variant = SWEEP3_DEFAULT_VARIANT;
     const char* e = getenv("RGPU_SWEEP");
     if (e) L.variant = (strcmp(e, "old") == 0) ? 0 : atoi(e);
     if ((long long)G.nvs * T_() * nslot >= (1LL << 32)) L.variant = 0;   // sweep3_kernel addresses the state with 32-bit element indices

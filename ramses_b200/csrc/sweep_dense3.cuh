@@ -74,7 +74,6 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
     const bool col_own = (tx >= 1) && (tx <= BX - 2) && (cx < g.ox1);
     const bool row_own = (ty >= 1) && (ty <= BY - 2) && (cy < g.oy1);    // warp uniform (a warp is one row)
     const bool own = col_own && row_own;
-    const bool need_tr = (cx <= g.ox1) && (cy <= g.oy1);
 
     constexpr int NOWN = (PL + NT - 1) / NT;
     unsigned offxy[NOWN];
@@ -125,8 +124,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
         to_ring(u, slot, i);
       }
     };
-    auto stage_plane_async = [&](int z) {
-      const unsigned zo = zoff(z);
+    auto stage_plane_async_off = [&](unsigned zo) {
 #pragma unroll
       for (int j = 0; j < NOWN; j++) {
         const int i = tid + j * NT;
@@ -136,6 +134,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
         for (int n = 0; n < NV; n++) cp_async8(stage + n * PL + i, a.uin + ((unsigned)n * vstride + off));
       }
     };
+    auto stage_plane_async = [&](int z) { stage_plane_async_off(zoff(z)); };
     auto stage_to_ring = [&](int slot) {
       cp_async_wait_all();
       for (int i = tid; i < PL; i += NT) {
@@ -152,12 +151,15 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
     stage_plane_async(z0);
     const int kbeg = z0 - 1, kend = z1;
     bool pend = false;                         // the x part of the update of the previous plane waits for its y and z parts
+    // ring slots of planes k-1, k, k+1 rotate; the plane offsets of k-1, k, k+2 advance incrementally (no division, no
+    // modulo inside the plane loop)
+    int sm1 = 0, sc = 1, sp1 = 2;
+    int zc2 = wrap_or_clamp(kbeg + 2, g.ncz, g.wrapz);
+    unsigned zo_m1 = zoff(kbeg - 1), zo_0 = zoff(kbeg), zo_1 = zoff(kbeg + 1), zo_2 = zoff(kbeg + 2);
     for (int k = kbeg; k <= kend; k++) {
-      const int c = k - kbeg;
-      const int sm1 = c % 3, sc = (c + 1) % 3, sp1 = (c + 2) % 3;
       stage_to_ring(sp1);
       __syncthreads();                         // ring plane k+1 complete; every row has published Fy(k-1)
-      if (k < kend) stage_plane_async(k + 2);
+      if (k < kend) stage_plane_async_off(zo_2);
       if (own && pend) {                       // y part of the update of plane k-1 (godfine1 :751-792: x, then y, then z)
 #pragma unroll
         for (int n = 0; n < NV; n++) {
@@ -170,18 +172,18 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
 
       // ---- uslope + trace3d of my cell (hydro/umuscl.f90:970, :483): all six face states ----
       const int qx = tx + 1, qy = ty + 1;
-      const double* qc = qring + (size_t)sc * NQ * PL + qy * QX + qx;
+      const double* qc = qring + sc * (NQ * PL) + qy * QX + qx;
       double qmx[NV], qpx[NV], qpy[NV], qpz[NV], qmz[NV];
       {
+        // every thread traces the ring cell under it: the ring holds a valid primitive state at all 34 x (BY+2) positions
+        // (loaded with wrap / clamp), so threads beyond the owned range need no special case (their results are never used)
         double q[NV], dq[NDIM][NV], t0[NV];
-#pragma unroll
-        for (int n = 0; n < NV; n++) { q[n] = 1.0; t0[n] = 0.0; dq[0][n] = 0.0; dq[1][n] = 0.0; dq[2][n] = 0.0; }
-        if (need_tr) {
+        {
 #pragma unroll
           for (int n = 0; n < NV; n++) q[n] = qc[n * PL];
           const double rinv = qc[NV * PL];
-          const double* qb_ = qring + (size_t)sm1 * NQ * PL + qy * QX + qx;
-          const double* qf_ = qring + (size_t)sp1 * NQ * PL + qy * QX + qx;
+          const double* qb_ = qring + sm1 * (NQ * PL) + qy * QX + qx;
+          const double* qf_ = qring + sp1 * (NQ * PL) + qy * QX + qx;
           if (SLOPE < 0 && P.slope_type == 3) {
             // positivity preserving unsplit slope :1328-1391
 #pragma unroll
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
 #pragma unroll
           for (int n = 0; n < NV; n++) t0[n] = s0[n] * dtdx * 0.5;
         }
-        // face states :592-673; threads outside the traced range carry the benign state q = 1
+        // face states :592-673
 #pragma unroll
         for (int n = 0; n < NV; n++) {
           const double hx = 0.5 * dq[0][n], hy = 0.5 * dq[1][n], hz = 0.5 * dq[2][n];
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
 #pragma unroll
       for (int n = 0; n < NV; n++) ucur[n] = 0.0;
       if (own && plane_flux) {   // set_unew: unew = uold; issued early so the latency hides under the Riemann solves
-        const unsigned off = off_own + zoff(k);
+        const unsigned off = off_own + zo_0;
 #pragma unroll
         for (int n = 0; n < NV; n++) ucur[n] = __ldg(a.uin + ((unsigned)n * vstride + off));
       }
@@ -264,41 +266,44 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
       for (int n = 0; n < NV; n++) { fx[n] = 0.0; fy[n] = 0.0; fz[n] = 0.0; }
       const double* e = exq + tid - BX;        // qm_y of row ty-1 (rows ty >= 1 only)
       const double* cq = carry + tid;          // qm_z of plane k-1
-      if (row_own && k >= z0) {
-        if (plane_flux) {
-          if (VEC == 1) {
-            // cmpflxm permutations (hydro/umuscl.f90:97,120,144): lane a = x (2,3,4), b = y (3,2,4), c = z (4,2,3)
-            V3 QL[NV], QR[NV], FG[NV];
-            QL[0] = {qlx[0], e[0 * NT], cq[0 * NT]}; QR[0] = {qpx[0], qpy[0], qpz[0]};
-            QL[1] = {qlx[1], e[2 * NT], cq[3 * NT]}; QR[1] = {qpx[1], qpy[2], qpz[3]};
-            QL[2] = {qlx[4], e[4 * NT], cq[4 * NT]}; QR[2] = {qpx[4], qpy[4], qpz[4]};
-            QL[3] = {qlx[2], e[1 * NT], cq[1 * NT]}; QR[3] = {qpx[2], qpy[1], qpz[1]};
-            QL[4] = {qlx[3], e[3 * NT], cq[2 * NT]}; QR[4] = {qpx[3], qpy[3], qpz[2]};
-            riemann_v<RIEMANN, V3>(QL, QR, FG, P);
-            fx[0] = FG[0].a; fx[1] = FG[1].a; fx[4] = FG[2].a; fx[2] = FG[3].a; fx[3] = FG[4].a;
-            fy[0] = FG[0].b; fy[2] = FG[1].b; fy[4] = FG[2].b; fy[1] = FG[3].b; fy[3] = FG[4].b;
-            fz[0] = FG[0].c; fz[3] = FG[1].c; fz[4] = FG[2].c; fz[1] = FG[3].c; fz[2] = FG[4].c;
-          } else {
-            double ql[NV], qr[NV], fg[NV];
-            ql[0] = qlx[0]; ql[1] = qlx[1]; ql[2] = qlx[4]; ql[3] = qlx[2]; ql[4] = qlx[3];
-            qr[0] = qpx[0]; qr[1] = qpx[1]; qr[2] = qpx[4]; qr[3] = qpx[2]; qr[4] = qpx[3];
-            if (VEC == 0) riemann<NDIM, RIEMANN>(ql, qr, fg, P); else riemann_v<RIEMANN, double>(ql, qr, fg, P);
-            fx[0] = fg[0]; fx[1] = fg[1]; fx[4] = fg[2]; fx[2] = fg[3]; fx[3] = fg[4];
-            ql[0] = e[0 * NT]; ql[1] = e[2 * NT]; ql[2] = e[4 * NT]; ql[3] = e[1 * NT]; ql[4] = e[3 * NT];
-            qr[0] = qpy[0]; qr[1] = qpy[2]; qr[2] = qpy[4]; qr[3] = qpy[1]; qr[4] = qpy[3];
-            if (VEC == 0) riemann<NDIM, RIEMANN>(ql, qr, fg, P); else riemann_v<RIEMANN, double>(ql, qr, fg, P);
-            fy[0] = fg[0]; fy[2] = fg[1]; fy[4] = fg[2]; fy[1] = fg[3]; fy[3] = fg[4];
-            ql[0] = cq[0 * NT]; ql[1] = cq[3 * NT]; ql[2] = cq[4 * NT]; ql[3] = cq[1 * NT]; ql[4] = cq[2 * NT];
-            qr[0] = qpz[0]; qr[1] = qpz[3]; qr[2] = qpz[4]; qr[3] = qpz[1]; qr[4] = qpz[2];
-            if (VEC == 0) riemann<NDIM, RIEMANN>(ql, qr, fg, P); else riemann_v<RIEMANN, double>(ql, qr, fg, P);
-            fz[0] = fg[0]; fz[3] = fg[1]; fz[4] = fg[2]; fz[1] = fg[3]; fz[2] = fg[4];
-          }
+      // which faces this ROW solves (warp uniform: a warp is one row): -x and -z faces of the owned rows, the -y face of rows
+      // 1 .. first row above the owned ones.  One inlined solver per direction and no other copy (I-cache)
+      const bool do_x = row_own && plane_flux;
+      const bool do_y = (ty >= 1) && (cy <= g.oy1) && plane_flux;
+      const bool do_z = row_own && (k >= z0);
+      if (VEC == 1 && do_x && do_y && do_z) {
+        // cmpflxm permutations (hydro/umuscl.f90:97,120,144): lane a = x (2,3,4), b = y (3,2,4), c = z (4,2,3)
+        V3 QL[NV], QR[NV], FG[NV];
+        QL[0] = {qlx[0], e[0 * NT], cq[0 * NT]}; QR[0] = {qpx[0], qpy[0], qpz[0]};
+        QL[1] = {qlx[1], e[2 * NT], cq[3 * NT]}; QR[1] = {qpx[1], qpy[2], qpz[3]};
+        QL[2] = {qlx[4], e[4 * NT], cq[4 * NT]}; QR[2] = {qpx[4], qpy[4], qpz[4]};
+        QL[3] = {qlx[2], e[1 * NT], cq[1 * NT]}; QR[3] = {qpx[2], qpy[1], qpz[1]};
+        QL[4] = {qlx[3], e[3 * NT], cq[2 * NT]}; QR[4] = {qpx[3], qpy[3], qpz[2]};
+        riemann_v<RIEMANN, V3>(QL, QR, FG, P);
+        fx[0] = FG[0].a; fx[1] = FG[1].a; fx[4] = FG[2].a; fx[2] = FG[3].a; fx[3] = FG[4].a;
+        fy[0] = FG[0].b; fy[2] = FG[1].b; fy[4] = FG[2].b; fy[1] = FG[3].b; fy[3] = FG[4].b;
+        fz[0] = FG[0].c; fz[3] = FG[1].c; fz[4] = FG[2].c; fz[1] = FG[3].c; fz[2] = FG[4].c;
+        scale_fluxes<NV>(fx, dt, a.dx, a.inv_dx, a.dx_pow2);
+        scale_fluxes<NV>(fy, dt, a.dx, a.inv_dx, a.dx_pow2);
+        scale_fluxes<NV>(fz, dt, a.dx, a.inv_dx, a.dx_pow2);
+      } else {
+        if (do_x) {                            // cmpflxm(...,2,3,4) hydro/umuscl.f90:97
+          double ql[NV], qr[NV], fg[NV];
+          ql[0] = qlx[0]; ql[1] = qlx[1]; ql[2] = qlx[4]; ql[3] = qlx[2]; ql[4] = qlx[3];
+          qr[0] = qpx[0]; qr[1] = qpx[1]; qr[2] = qpx[4]; qr[3] = qpx[2]; qr[4] = qpx[3];
+          if (VEC == 0) riemann<NDIM, RIEMANN>(ql, qr, fg, P); else riemann_v<RIEMANN, double>(ql, qr, fg, P);
+          fx[0] = fg[0]; fx[1] = fg[1]; fx[4] = fg[2]; fx[2] = fg[3]; fx[3] = fg[4];
           scale_fluxes<NV>(fx, dt, a.dx, a.inv_dx, a.dx_pow2);
+        }
+        if (do_y) {                            // cmpflxm(...,3,2,4) :120
+          double ql[NV], qr[NV], fg[NV];
+          ql[0] = e[0 * NT]; ql[1] = e[2 * NT]; ql[2] = e[4 * NT]; ql[3] = e[1 * NT]; ql[4] = e[3 * NT];
+          qr[0] = qpy[0]; qr[1] = qpy[2]; qr[2] = qpy[4]; qr[3] = qpy[1]; qr[4] = qpy[3];
+          if (VEC == 0) riemann<NDIM, RIEMANN>(ql, qr, fg, P); else riemann_v<RIEMANN, double>(ql, qr, fg, P);
+          fy[0] = fg[0]; fy[2] = fg[1]; fy[4] = fg[2]; fy[1] = fg[3]; fy[3] = fg[4];
           scale_fluxes<NV>(fy, dt, a.dx, a.inv_dx, a.dx_pow2);
-          scale_fluxes<NV>(fz, dt, a.dx, a.inv_dx, a.dx_pow2);
-#pragma unroll
-          for (int n = 0; n < NV; n++) exf[n * NT + tid] = fy[n];
-        } else {                               // k == z1: only the z face that closes plane z1-1
+        }
+        if (do_z) {                            // cmpflxm(...,4,2,3) :144; left state carried from the previous plane
           double ql[NV], qr[NV], fg[NV];
           ql[0] = cq[0 * NT]; ql[1] = cq[3 * NT]; ql[2] = cq[4 * NT]; ql[3] = cq[1 * NT]; ql[4] = cq[2 * NT];
           qr[0] = qpz[0]; qr[1] = qpz[3]; qr[2] = qpz[4]; qr[3] = qpz[1]; qr[4] = qpz[2];
@@ -306,13 +311,8 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
           fz[0] = fg[0]; fz[3] = fg[1]; fz[4] = fg[2]; fz[1] = fg[3]; fz[2] = fg[4];
           scale_fluxes<NV>(fz, dt, a.dx, a.inv_dx, a.dx_pow2);
         }
-      } else if (ty >= 1 && cy <= g.oy1 && plane_flux) {   // first row above the owned rows: the y face that closes them
-        double ql[NV], qr[NV], fg[NV];
-        ql[0] = e[0 * NT]; ql[1] = e[2 * NT]; ql[2] = e[4 * NT]; ql[3] = e[1 * NT]; ql[4] = e[3 * NT];
-        qr[0] = qpy[0]; qr[1] = qpy[2]; qr[2] = qpy[4]; qr[3] = qpy[1]; qr[4] = qpy[3];
-        if (VEC == 0) riemann<NDIM, RIEMANN>(ql, qr, fg, P); else riemann_v<RIEMANN, double>(ql, qr, fg, P);
-        fy[0] = fg[0]; fy[2] = fg[1]; fy[4] = fg[2]; fy[1] = fg[3]; fy[3] = fg[4];
-        scale_fluxes<NV>(fy, dt, a.dx, a.inv_dx, a.dx_pow2);
+      }
+      if (do_y) {
 #pragma unroll
         for (int n = 0; n < NV; n++) exf[n * NT + tid] = fy[n];
       }
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
           double unew_[NV];
 #pragma unroll
           for (int n = 0; n < NV; n++) unew_[n] = carry[(2 * NV + n) * NT + tid] + (carry[(NV + n) * NT + tid] - fz[n]);
-          const unsigned off = off_own + zoff(k - 1);
+          const unsigned off = off_own + zo_m1;
 #pragma unroll
           for (int n = 0; n < NV; n++) a.uout[(unsigned)n * vstride + off] = unew_[n];
           double ei;
@@ -349,6 +349,10 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
         }
       }
       pend = plane_flux;
+      { const int t = sm1; sm1 = sc; sc = sp1; sp1 = t; }
+      zo_m1 = zo_0; zo_0 = zo_1; zo_1 = zo_2;
+      zc2 = g.wrapz ? (zc2 + 1 == g.ncz ? 0 : zc2 + 1) : min(zc2 + 1, g.ncz - 1);
+      zo_2 = (unsigned)((zc2 & 1) << 2) * (unsigned)g.nslot + (unsigned)(g.nox * g.noy) * (unsigned)(zc2 >> 1);
     }
   }
 
