@@ -62,7 +62,11 @@ typedef struct rgpu_params {
   int mhd;             /* 0: hydro build, 1: MHD build                          */
   int riemann2d;       /* RGPU_MHD2D_* (mhd/hydro_parameters.f90:104)           */
   int slope_mag_type;  /* mhd/hydro_parameters.f90:93; -1 = slope_type (hydro/read_hydro_params.f90:528) */
-  int pad_;
+  int fast;            /* 0 (default): STRICT arithmetic -- no FMA contraction, correctly rounded divisions: results bit-identical
+                        * to the reference's evaluation order.  1: FAST arithmetic for the 3-D hydro dense sweep (FMA
+                        * contraction, reciprocal-multiply quotients, <= 2 ulp reciprocal / sqrt): within 1e-12 relative of
+                        * the strict result on the conserved state after N steps (north_star's tolerance), ~15 % fewer FP64
+                        * instructions.  Ignored (strict) by every other path.                                              */
 } rgpu_params;
 /* `riemann` / `riemann2d` of the MHD build: iriemann, iriemann2d (hydro/read_hydro_params.f90:190-220) */
 enum { RGPU_MHD_LLF = 0, RGPU_MHD_ROE = 1, RGPU_MHD_HLL = 2, RGPU_MHD_HLLD = 3, RGPU_MHD_UPWIND = 4, RGPU_MHD_HYDRO = 5 };

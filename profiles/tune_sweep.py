@@ -47,7 +47,9 @@ def main():
         a.gamma, a.courant_factor, a.slope_type, a.riemann = 1.4, 0.8, 1, riemann
         ref_hash = None
         for v in args.variants.split(","):
-            os.environ["RGPU_SWEEP"] = v
+            fast = v.endswith("f")                 # e.g. 1212f: the FAST arithmetic build of variant 1212
+            os.environ["RGPU_SWEEP"] = v.rstrip("f")
+            a.fast = fast
             a.uold[:, :] = ics[ic]
             h = HydroGPU(a, device=0)
             try:
@@ -66,9 +68,16 @@ def main():
                 hs = hashlib.sha1(a.uold.tobytes()).hexdigest()[:12]
                 if ref_hash is None:
                     ref_hash = hs
+                    ref_state = a.uold.copy()
+                if fast:
+                    act = a.uold[:, a.ncoarse:]
+                    ref_act = ref_state[:, a.ncoarse:]
+                    extra = {"max_rel_diff_vs_first": float(max(np.abs(act[k] - ref_act[k]).max() / np.abs(ref_act[k]).max() if np.abs(ref_act[k]).max() > 0 else 0.0 for k in range(5)))}
+                else:
+                    extra = {}
                 rec = {"ic": ic, "riemann": riemann, "variant": v, "grid": n, "ms_per_step": ms, "sweep_kernel_ms": float(np.mean(ks)),
                        "cell_updates_per_s": n ** 3 / (ms * 1e-3), "state_hash": hs, "same_bits_as_first": hs == ref_hash,
-                       "dt_last": float(dts[-1])}
+                       "dt_last": float(dts[-1]), **extra}
             except Exception as e:  # a variant that cannot launch (registers / shared memory) is reported, not fatal
                 rec = {"ic": ic, "riemann": riemann, "variant": v, "error": repr(e)}
             finally:

@@ -91,9 +91,15 @@ __device__ __forceinline__ V3 vpow_where(const B3& m, const V3& ro, const V3& nu
 }
 // sqrt(fabs(gamma*pstar/rstar)) with IEEE `/` and sqrt() (godunov_utils.f90:419, :598): kept as the library operations
 // because pstar may be exactly zero, outside the fast-path range of sqrt_rn
+#ifdef RGPU_FAST
+__device__ __forceinline__ double vcstar(double gamma, double pstar, double rstar) {   // floor far below smallc^2: sqrt_rn needs x > 0
+  return sqrt_rn(fmx(fabs(gamma * pstar * rcp_rn(rstar)), 1e-300));
+}
+#else
 __device__ __forceinline__ double vcstar(double gamma, double pstar, double rstar) { return sqrt(fabs(gamma * pstar / rstar)); }
+#endif
 __device__ __forceinline__ V3 vcstar(double gamma, const V3& pstar, const V3& rstar) {
-  return {sqrt(fabs(gamma * pstar.a / rstar.a)), sqrt(fabs(gamma * pstar.b / rstar.b)), sqrt(fabs(gamma * pstar.c / rstar.c))};
+  return {vcstar(gamma, pstar.a, rstar.a), vcstar(gamma, pstar.b, rstar.b), vcstar(gamma, pstar.c, rstar.c)};
 }
 
 template <class V> struct MaskOf { using type = bool; };

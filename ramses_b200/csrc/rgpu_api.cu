@@ -34,6 +34,16 @@ DECL(3, 0) DECL(3, 1) DECL(3, 2) DECL(3, 3) DECL(3, 4)
 DECL(0) DECL(1) DECL(2) DECL(3) DECL(4)
 #undef DECL
 template <int NDIM, int RIEMANN> cudaError_t launch_sweep_dense_amr(const SweepArgs& a, int nblocks, cudaStream_t st);
+}  // namespace rgpu
+// FAST arithmetic mode: the same kernels built with FMA contraction under namespace rgpu_fast (sweep3_fast_inst_*.cu)
+extern "C" {
+cudaError_t rgpu_fast_launch_sweep3_llf(const void*, int, cudaStream_t, int);
+cudaError_t rgpu_fast_launch_sweep3_exact(const void*, int, cudaStream_t, int);
+cudaError_t rgpu_fast_launch_sweep3_acoustic(const void*, int, cudaStream_t, int);
+cudaError_t rgpu_fast_launch_sweep3_hllc(const void*, int, cudaStream_t, int);
+cudaError_t rgpu_fast_launch_sweep3_hll(const void*, int, cudaStream_t, int);
+}
+namespace rgpu {
 #define DECL(R) extern template cudaError_t launch_sweep_dense_amr<3, R>(const SweepArgs&, int, cudaStream_t);
 DECL(0) DECL(1) DECL(2) DECL(3) DECL(4)
 #undef DECL
@@ -547,6 +557,15 @@ int launch_sweep(Level& L, int zlo = -1, int zhi = -1, int part = 0) {
   cudaError_t e;
   if (G.p.ndim == 1) e = dispatch_sweep_nd<1>(G.p.riemann, a, nblocks, G.stream, L.by);
   else if (G.p.ndim == 2) e = dispatch_sweep_nd<2>(G.p.riemann, a, nblocks, G.stream, L.by);
+  else if (L.variant && G.p.fast) {
+    switch (G.p.riemann) {
+      case RGPU_RIEMANN_LLF: e = rgpu_fast_launch_sweep3_llf(&a, nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_EXACT: e = rgpu_fast_launch_sweep3_exact(&a, nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_ACOUSTIC: e = rgpu_fast_launch_sweep3_acoustic(&a, nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_HLLC: e = rgpu_fast_launch_sweep3_hllc(&a, nblocks, G.stream, L.variant); break;
+      default: e = rgpu_fast_launch_sweep3_hll(&a, nblocks, G.stream, L.variant); break;
+    }
+  }
   else if (L.variant) {
     switch (G.p.riemann) {
       case RGPU_RIEMANN_LLF: e = launch_sweep3<RIEMANN_LLF>(a, nblocks, G.stream, L.variant); break;

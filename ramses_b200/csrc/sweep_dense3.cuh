@@ -222,8 +222,14 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
           }
           double s0[NV];
           trace_sources<NDIM>(q, dq, rinv, s0, P);
+#ifdef RGPU_FAST
+          const double hdtdx = dtdx * 0.5;
+#pragma unroll
+          for (int n = 0; n < NV; n++) t0[n] = s0[n] * hdtdx;
+#else
 #pragma unroll
           for (int n = 0; n < NV; n++) t0[n] = s0[n] * dtdx * 0.5;
+#endif
         }
         // face states :592-673
 #pragma unroll

@@ -96,6 +96,7 @@ def make_params(amr):
             raise ValueError("unknown Riemann solver")      # hydro/umuscl.f90:801-803
         p.riemann = _lib.RIEMANN[amr.riemann]
     p.pressure_fix = int(bool(amr.pressure_fix))
+    p.fast = int(bool(getattr(amr, "fast", False)))        # rgpu_params.fast: FAST arithmetic of the 3-D dense sweep
     p.gamma, p.smallr, p.smallc = amr.gamma, amr.smallr, amr.smallc
     p.slope_theta, p.difmag, p.courant_factor, p.boxlen = amr.slope_theta, amr.difmag, amr.courant_factor, amr.boxlen
     p.nx, p.ny, p.nz = amr.nx, amr.ny, amr.nz

@@ -28,7 +28,7 @@ class Params(C.Structure):
                 ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
                 ("icoarse_min", C.c_int), ("icoarse_max", C.c_int), ("jcoarse_min", C.c_int), ("jcoarse_max", C.c_int),
                 ("kcoarse_min", C.c_int), ("kcoarse_max", C.c_int), ("nlevelmax", C.c_int),
-                ("mhd", C.c_int), ("riemann2d", C.c_int), ("slope_mag_type", C.c_int), ("pad_", C.c_int)]
+                ("mhd", C.c_int), ("riemann2d", C.c_int), ("slope_mag_type", C.c_int), ("fast", C.c_int)]
 
 
 class LevelInfo(C.Structure):

@@ -358,3 +358,37 @@ def test_sedov3d_large_grid_vs_oracle(gpu, riemann, level, nstep):
     else:
         assert np.array_equal(dts, dts_ref)
         assert np.array_equal(a.uold[:, idx], ref[:, idx])
+
+
+@pytest.mark.parametrize("riemann", ["hllc", "exact", "llf", "hll", "acoustic"])
+@pytest.mark.parametrize("ic", ["sedov", "smooth"])
+def test_fast_mode_within_tolerance(gpu, riemann, ic):
+    """rgpu_params.fast = 1 (FMA contraction, reciprocal-multiply quotients, <= 2 ulp reciprocal / sqrt in the 3-D dense sweep):
+    after 12 fused level steps the conserved state and the dt history stay within north_star's tolerance (1e-12 relative) of the
+    STRICT path and of the oracle; the strict path itself remains bit-identical to the oracle (other tests)."""
+    from ramses_b200.hydro import HydroGPU
+    c = Case(3, 6, riemann=riemann, slope_type=1, boxlen=0.5)
+    if ic == "sedov":
+        c.init_regions(SEDOV3D_REGIONS)
+    else:
+        c.init_dense(smooth_state(3, 64))
+    ref, dts_ref = c.oracle_steps(12, nthreads=8)
+    ref = ref.reshape(c.nvar, -1)
+    out = {}
+    for fast in (False, True):
+        a = c.amr_commons()
+        a.fast = fast
+        h = HydroGPU(a)
+        h.bind_level(c.level)
+        h.upload_state(c.level)
+        dts, _ = h.level_steps(c.level, 12)
+        h.download_state(c.level)
+        h.finalize()
+        out[fast] = (a.uold.copy(), dts)
+    idx = c.active_cells()
+    us, uf = out[False][0][:, idx], out[True][0][:, idx]
+    assert not np.array_equal(us, uf)                      # the fast build really is a different arithmetic
+    assert max_rel_err(uf, us) <= 1e-12
+    assert max_rel_err(uf, ref[:, idx]) <= 1e-12
+    assert np.allclose(out[True][1], out[False][1], rtol=1e-12, atol=0)
+    assert np.allclose(out[True][1], dts_ref, rtol=1e-12, atol=0)
