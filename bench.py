@@ -407,7 +407,7 @@ def pin_to_gpu_numa_node(gpu_index):
     return None
 
 
-def canonical_check(a, level, coarse, rank, dts):
+def canonical_check(a, level, coarse, rank, dts, keep_block=False):
     """Size-independent identity of the run: SHA-1 of the dt history and of the conserved state in the two bottom and two top
     oct planes of the rank's cube (all eight corners: where the periodic images of the blast arrive through the ghost exchange),
     in (z, y, x, cell, variable) order -- independent of the oct numbering and of the decomposition.  Every rank holds the same
@@ -429,8 +429,11 @@ def canonical_check(a, level, coarse, rank, dts):
     cells = (a.ncoarse + np.arange(T)[None, :] * a.ngridmax + igs[:, None] - 1).ravel()
     blk = np.ascontiguousarray(a.uold[:, cells].T)
     act = (a.ncoarse + np.arange(T)[:, None] * a.ngridmax + ig[None, :] - 1).ravel()
-    return {"state_sha1": hashlib.sha1(blk.tobytes()).hexdigest(), "dt_sha1": hashlib.sha1(np.asarray(dts).tobytes()).hexdigest(),
-            "mass_sum": float(a.uold[0, act].sum()), "etot_sum": float(a.uold[a.ndim + 1, act].sum()), "cells_hashed": int(len(cells))}
+    out = {"state_sha1": hashlib.sha1(blk.tobytes()).hexdigest(), "dt_sha1": hashlib.sha1(np.asarray(dts).tobytes()).hexdigest(),
+           "mass_sum": float(a.uold[0, act].sum()), "etot_sum": float(a.uold[a.ndim + 1, act].sum()), "cells_hashed": int(len(cells))}
+    if keep_block:
+        out["_block"] = blk
+    return out
 
 
 GOLDEN_HASHES = os.path.join(ROOT, "tests", "golden", "bench_hashes.json")
@@ -523,7 +526,8 @@ def dense_bench(args, workload, rank, world, local_rank, secondary=False):
     h.download_state(level)
     check = None
     if not mhd:
-        check = canonical_check(a, level, coarse, rank, np.concatenate([dts_w, dts]))
+        check = canonical_check(a, level, coarse, rank, np.concatenate([dts_w, dts]), keep_block=True)
+        strict_block = check.pop("_block")
         key = f"{workload}:{warmup + steps}"
         gold = json.load(open(GOLDEN_HASHES)) if os.path.exists(GOLDEN_HASHES) else {}
         g = gold.get(key)
@@ -618,6 +622,48 @@ def dense_bench(args, workload, rank, world, local_rank, secondary=False):
     h.host_unregister(a.uold)
     h.host_unregister(a.unew)
     h.finalize()
+    # ---- FAST arithmetic mode (rgpu_params.fast = 1) on the same workload: reported next to the strict headline, never as it
+    fast = None
+    if not mhd and not args.no_fast:
+        a.uold[:, :] = 0.0
+        base = sedov_ic(0.5, 1, level) if w["ic"] == "sedov" else smooth_ic((1, 1, 1))
+        fill_state(a, level, lambda x, y, z: base(np.mod(x, 1.0), np.mod(y, 1.0), np.mod(z, 1.0)))
+        a.fast = True
+        hf = HydroGPU(a, device=local_rank)
+        if world > 1:
+            from ramses_b200 import lib as _l
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                buf = (C.c_ubyte * 128)()
+                _l.check(hf.L.rgpu_comm_unique_id(buf))
+                uid = torch.tensor(list(buf), dtype=torch.uint8)
+            uid = uid.cuda()
+            dist.broadcast(uid, 0)
+            buf = (C.c_ubyte * 128)(*uid.cpu().tolist())
+            _l.check(hf.L.rgpu_comm_init(world, rank, buf))
+        hf.bind_level(level)
+        hf.upload_state(level)
+        fw, _ = hf.level_steps(level, warmup)
+        hf.synchronize()
+        if world > 1:
+            dist.barrier()
+        fd, _ = hf.level_steps(level, steps)
+        f_ms = hf.level_info(level).last_steps_ms
+        if world > 1:
+            tt = torch.tensor([f_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            f_ms = tt.item()
+        hf.download_state(level)
+        hf.finalize()
+        a.fast = False
+        fb = canonical_check(a, level, coarse, rank, np.concatenate([fw, fd]), keep_block=True)["_block"]
+        scale = np.abs(strict_block).max(axis=0, keepdims=True)
+        scale[scale == 0] = 1.0
+        rel = float((np.abs(fb - strict_block) / scale).max())
+        fast = {"value": ncell_total * steps / (f_ms * 1e-3), "unit": "cell-updates/s", "ms_per_step": f_ms / steps,
+                "max_rel_diff_vs_strict": rel, "tolerance": 1e-12, "within_tolerance": rel <= 1e-12,
+                "what": "rgpu_params.fast = 1: FMA contraction, reciprocal-multiply quotients, <= 2 ulp reciprocal / sqrt in the 3-D dense "
+                        "sweep; difference on the hashed planes of the conserved state after warmup+steps level steps, per variable maximum"}
     if rank != 0:
         return None
     n = 1 << level
@@ -631,7 +677,7 @@ def dense_bench(args, workload, rank, world, local_rank, secondary=False):
                        "oct_order": args.order, "sweep_variant": int(info0.sweep_variant), "host_setup_s": round(t_setup, 1),
                        "l2": "inputs larger than L2 (state %.2f GB per rank vs 126 MB L2), no flush" % (nvs * 8 * ncell_rank / 1e9)},
             "wall_ms_per_step": wall / steps * 1e3, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "check": check}
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "check": check, "fast": fast}
     return line
 
 
@@ -645,6 +691,7 @@ def main():
     ap.add_argument("--secondary", default="sedov3d_256_exact", help="second workload reported under 'secondary' at N=1 ('' = none)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fast", action="store_true", help="skip the FAST-arithmetic re-run of the workload")
     ap.add_argument("--order", default="lattice", choices=["lattice", "creation", "random"],
                     help="oct numbering of the fabricated tree; 'creation' = the reference's refine order (nvector = infinity)")
     ap.add_argument("--write-golden", action="store_true", help="single-GPU run: record the state / dt hashes in tests/golden/bench_hashes.json")
@@ -696,7 +743,7 @@ def main():
     if world == 1 and default_workload and args.secondary and args.secondary != args.workload:
         try:      # BASELINE.json configs[1] next to the headline workload (same process, N=1 only)
             sec = dense_bench(args, args.secondary, rank, world, local_rank, secondary=True)
-            line["secondary"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "roofline", "e2e", "check", "gpu_launches")}
+            line["secondary"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "roofline", "e2e", "check", "gpu_launches", "fast")}
             line["secondary"]["config"] = sec["config"]
         except Exception as e:
             line["secondary"] = {"error": repr(e)}

@@ -14,6 +14,7 @@ from ramses_b200.tree import build_uniform_tree, fill_state
 a = build_uniform_tree(3, level, coarse=(1, 1, 1), myid=1, ncpu=1, order="creation", boxlen=0.5)
 fill_state(a, level, bench.sedov_ic(0.5, 1, level) if ic == "sedov" else bench.smooth_ic((1, 1, 1)))
 a.gamma, a.courant_factor, a.slope_type, a.riemann = 1.4, 0.8, 1, riemann
+a.fast = os.environ.get("RGPU_FAST_MODE", "0") == "1"
 h = HydroGPU(a, device=0)
 h.bind_level(level)
 h.upload_state(level)
