@@ -689,6 +689,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--secondary", default="sedov3d_256_exact", help="second workload reported under 'secondary' at N=1 ('' = none)")
+    ap.add_argument("--config5", default="tube_mhd_256_roe", help="MHD workload (BASELINE.json configs[4]) reported under 'config5' at N=1 ('' = none)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast", action="store_true", help="skip the FAST-arithmetic re-run of the workload")
@@ -747,6 +748,13 @@ def main():
             line["secondary"]["config"] = sec["config"]
         except Exception as e:
             line["secondary"] = {"error": repr(e)}
+    if world == 1 and default_workload and args.config5:
+        try:      # BASELINE.json configs[4]: tube_mhd 256^3, 8-wave MHD path (roe / llf), same process
+            sec = dense_bench(args, args.config5, rank, world, local_rank, secondary=True)
+            line["config5"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "roofline", "e2e", "gpu_launches")}
+            line["config5"]["config"] = sec["config"]
+        except Exception as e:
+            line["config5"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -90,7 +90,10 @@ int rgpu_bind_tree(int ncoarse, int ngridmax, const int* son, const int* father,
 /* AMR mode (levelmin < nlevelmax): call once after rgpu_init and before rgpu_bind_tree.  The device then mirrors
  * son/father/nbor and the whole uold/unew arrays; every level is processed as a list of octs by the oct-batch kernel
  * (godfine1 with interpol_hydro ghost prolongation, flux masking and coarse refluxing, hydro/godunov_fine.f90:486-911).
- * interpol_type / interpol_var: &REFINE_PARAMS (hydro/hydro_parameters.f90:88-89); interpol_var must be 0.
+ * interpol_type / interpol_var: &REFINE_PARAMS (hydro/hydro_parameters.f90:88-89): interpol_var 0 (conservative variables),
+ * 1 (internal energy instead of total energy), 2 (velocities + internal energy, total momentum of the oct restored,
+ * hydro/interpol_hydro.f90:318-345,393-440; upload_fine then averages the internal energy :204-261); interpol_type 0 (straight
+ * injection), 1 (minmod), 2 (MonCen), 3 (central), 4 (central for the velocities, MonCen for the rest; needs interpol_var = 2).
  * In this mode rgpu_upload_state / rgpu_download_state move the WHOLE arrays (ilevel ignored).                       */
 int rgpu_set_amr(int on, int interpol_type, int interpol_var);
 

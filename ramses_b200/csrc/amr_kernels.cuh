@@ -112,6 +112,58 @@ __device__ void amr_interpol_var(const double* a, int interpol_type, double* u2)
   }
 }
 
+// interpol_hydro (hydro/interpol_hydro.f90:268-444) for ONE father cell and ALL variables: u1[(2*ndim+1)][nvar] (cell, then its
+// 2*ndim neighbours) -> u2[2^ndim][nvar].  interpol_var 0: conservative variables (rho, rho u, E); 1: (rho, rho u, rho eps)
+// :318-345; 2: (rho, u, rho eps) with the momentum correction :393-415.  interpol_type 0..3 as amr_interpol_var; 4 = type 3 for
+// the velocities and type 2 for everything else (:357-366; only meaningful with interpol_var = 2).  NVX = nvar (compile time).
+template <int NDIM, int NVX>
+__device__ void amr_interpol_hydro(double (*u1)[NVX], int interpol_type, int interpol_var, double smallr, double (*u2)[NVX]) {
+  constexpr int T = 1 << NDIM, TW = 2 * NDIM;
+  const double oneover_twotondim = 1.0 / (double)T;
+  if (interpol_var == 1 || interpol_var == 2) {
+    for (int j = 0; j <= TW; j++) {
+      double ekin = 0.0;
+#pragma unroll
+      for (int d = 1; d <= NDIM; d++) ekin = ekin + 0.5 * (u1[j][d] * u1[j][d]) / fmx(u1[j][0], smallr);
+      u1[j][NDIM + 1] = u1[j][NDIM + 1] - ekin - 0.0;
+      if (interpol_var == 2) {
+#pragma unroll
+        for (int d = 1; d <= NDIM; d++) u1[j][d] = u1[j][d] / fmx(u1[j][0], smallr);
+      }
+    }
+  }
+#pragma unroll 1
+  for (int iv = 0; iv < NVX; iv++) {
+    double a[7], v2[T];
+    for (int j = 0; j <= TW; j++) a[j] = u1[j][iv];
+    int tt = interpol_type;
+    if (interpol_type == 4) tt = (iv >= 1 && iv <= NDIM) ? 3 : 2;
+    amr_interpol_var<NDIM>(a, tt, v2);
+#pragma unroll
+    for (int is = 0; is < T; is++) u2[is][iv] = v2[is];
+  }
+  if (interpol_var == 1 || interpol_var == 2) {
+    if (interpol_var == 2) {
+      for (int is = 0; is < T; is++)
+#pragma unroll
+        for (int d = 1; d <= NDIM; d++) u2[is][d] = u2[is][d] * u2[is][0];
+#pragma unroll
+      for (int d = 1; d <= NDIM; d++) {
+        double mom = 0.0;
+        for (int is = 0; is < T; is++) mom = mom + u2[is][d] * oneover_twotondim;
+        mom = mom - u1[0][d] * u1[0][0];
+        for (int is = 0; is < T; is++) u2[is][d] = u2[is][d] - mom;
+      }
+    }
+    for (int is = 0; is < T; is++) {
+      double ekin = 0.0;
+#pragma unroll
+      for (int d = 1; d <= NDIM; d++) ekin = ekin + 0.5 * (u2[is][d] * u2[is][d]) / fmx(u2[is][0], smallr);
+      u2[is][NDIM + 1] = u2[is][NDIM + 1] + ekin + 0.0;
+    }
+  }
+}
+
 // get3cubefather (amr/nbors_utils.f90:5-194, get3cubepos :199): the 3^ndim father cells around the father cell of an oct
 template <int NDIM>
 __device__ __forceinline__ void amr_get3cubefather(const AmrTree& t, int igrid, int ilevel, int* nfc /*[3^ndim]*/, int* ng /*[8]*/) {
@@ -171,7 +223,7 @@ struct AmrSweepArgs {
   double* rflux;          // [nact][2*ndim sides][2^(ndim-1) faces][nvar]: scaled, masked fluxes through the oct's outer faces
   Phys P;
   double dt, dx, inv_dx;
-  int dx_pow2, interpol_type;
+  int dx_pow2, interpol_type, interpol_var;
   double difmag;          // hydro_parameters.f90:81
   int nps;                // passive scalars: nvar - (ndim+2)
   // patch mode: the level's own cells are updated by the dense kernel; this launch only evaluates the scaled, masked fluxes
@@ -241,7 +293,28 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
       for (int n = 0; n < NV; n++) s.q[n][pc] = UO(ic, n);
       s.ok[pc] = t.son[ic] > 0;
     }
-    // missing neighbour octs: interpol_hydro from the coarser level, one thread per (father, variable)
+    // missing neighbour octs: interpol_hydro from the coarser level.  interpol_var 1, 2 and interpol_type 4 couple the
+    // variables (internal energy / velocities): one thread per father cell interpolates the whole state
+    if (a.interpol_var != 0 || a.interpol_type == 4) {
+      for (int jf = tl; jf < N3; jf += AMR_TPO) {
+        if (s.gnb[jf] > 0) continue;
+        int fa[7];
+        amr_getnborfather<NDIM>(t, s.nfc[jf], a.ilevel, fa);
+        double u1[7][NV], u2[T][NV];
+        for (int j = 0; j <= TW; j++)
+#pragma unroll
+          for (int n = 0; n < NV; n++) u1[j][n] = UO(fa[j], n);
+        amr_interpol_hydro<NDIM, NV>(u1, a.interpol_type, a.interpol_var, P.smallr, u2);
+        const int i1 = jf % 3, j1 = (jf / 3) % 3, k1 = jf / 9;
+        for (int is = 0; is < T; is++) {
+          const int i3 = 1 + 2 * (i1 - 1) + (is & 1), j3 = HY ? 1 + 2 * (j1 - 1) + ((is >> 1) & 1) : 1, k3 = HZ ? 1 + 2 * (k1 - 1) + ((is >> 2) & 1) : 1;
+          const int pc = (i3 + 1) + 6 * ((HY ? j3 + 1 : 0) + PJ * (HZ ? k3 + 1 : 0));
+#pragma unroll
+          for (int n = 0; n < NV; n++) s.q[n][pc] = u2[is][n];
+          s.ok[pc] = 0;
+        }
+      }
+    } else
     for (int e = tl; e < N3 * NV; e += AMR_TPO) {
       const int jf = e / NV, n = e % NV;
       if (s.gnb[jf] > 0) continue;
@@ -577,7 +650,7 @@ __global__ void amr_unpack_kernel(double* __restrict__ u, const int* __restrict_
 }
 // upload_fine (hydro/interpol_hydro.f90:5, upl :73): split cells <- mean of their sons
 __global__ void amr_upload_kernel(double* __restrict__ u, const int* __restrict__ son1, const int* __restrict__ igrid, int n, int ncoarse,
-                                  int ngridmax, long long ncell, int T, int nvar, double smallr) {
+                                  int ngridmax, long long ncell, int T, int nvar, double smallr, int interpol_var = 0, int ndim = 3) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * T) return;
   const int o = i % n, ind = i / n;
@@ -591,6 +664,18 @@ __global__ void amr_upload_kernel(double* __restrict__ u, const int* __restrict_
     getx = 0.0;
     for (int is = 0; is < T; is++) getx = getx + u[(size_t)iv * ncell + ncoarse + (size_t)is * ngridmax + gs - 1];
     u[(size_t)iv * ncell + ic - 1] = getx / (double)T;
+  }
+  if (interpol_var == 1 || interpol_var == 2) {   // average the internal energy instead of the total energy :204-261
+    getx = 0.0;
+    for (int is = 0; is < T; is++) {
+      const size_t cs = (size_t)ncoarse + (size_t)is * ngridmax + gs - 1;
+      double ekin = 0.0;
+      for (int d = 1; d <= ndim; d++) ekin = ekin + 0.5 * (u[(size_t)d * ncell + cs] * u[(size_t)d * ncell + cs]) / fmx(u[cs], smallr);
+      getx = getx + u[(size_t)(ndim + 1) * ncell + cs] - ekin - 0.0;
+    }
+    double ekin = 0.0;
+    for (int d = 1; d <= ndim; d++) ekin = ekin + 0.5 * (u[(size_t)d * ncell + ic - 1] * u[(size_t)d * ncell + ic - 1]) / fmx(u[ic - 1], smallr);
+    u[(size_t)(ndim + 1) * ncell + ic - 1] = getx / (double)T + ekin + 0.0;
   }
 }
 // make_boundary_hydro (hydro/hydro_boundary.f90:5) on the mirrored arrays
@@ -708,6 +793,26 @@ __global__ void amr_fill_shell_kernel(const AmrTree t, const double* __restrict_
   amr_interpol_var<3>(av, interpol_type, u2);
 #pragma unroll
   for (int is = 0; is < 8; is++) u[((size_t)n * 8 + is) * nslot + s] = u2[is];
+}
+
+// the same for interpol_var 1, 2 / interpol_type 4 (coupled variables): one thread per shell slot, nvar = 5
+__global__ void amr_fill_shell_coupled_kernel(const AmrTree t, const double* __restrict__ uold, double* __restrict__ u,
+                                              const int* __restrict__ shell_father, long long nslot, int ilevel, int interpol_type,
+                                              int interpol_var, double smallr) {
+  const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= nslot) return;
+  const int fc = shell_father[s];
+  if (fc <= 0) return;
+  int fa[7];
+  amr_getnborfather<3>(t, fc, ilevel, fa);
+  double u1[7][5], u2[8][5];
+  for (int j = 0; j < 7; j++)
+#pragma unroll
+    for (int n = 0; n < 5; n++) u1[j][n] = uold[(size_t)n * t.ncell + fa[j] - 1];
+  amr_interpol_hydro<3, 5>(u1, interpol_type, interpol_var, smallr, u2);
+  for (int is = 0; is < 8; is++)
+#pragma unroll
+    for (int n = 0; n < 5; n++) u[((size_t)n * 8 + is) * nslot + s] = u2[is][n];
 }
 
 #ifndef RGPU_HOST_NUMERICS   // (tests/host_numerics compiles the __device__ helpers above with g++: no kernel launches there)

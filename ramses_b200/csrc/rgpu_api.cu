@@ -120,7 +120,7 @@ struct Level {
   cudaEvent_t ev_x = nullptr, ev_s = nullptr;
   // Level-0 pipeline (rgpu_godunov_fine on host arrays): z-slabs of oct planes; per slab the igrid ranges to upload (every oct
   // of the slab) and to download (its active octs).  Empty when the oct numbering is too scattered (serial path then).
-  struct Range { int lo, n; };
+  struct Range { int lo, n, stride, count; };   // `count` runs of n consecutive igrids, `stride` igrids apart (count 1: one run)
   struct Slab { int oz_a = 0, oz_b = 0; std::vector<Range> up, down; };
   std::vector<Slab> slabs;
   std::vector<cudaEvent_t> ev_in, ev_c;
@@ -168,7 +168,7 @@ struct Context {
   int* d_son = nullptr; int* d_son_base = nullptr; int* d_father = nullptr; int* d_nbor = nullptr;
   double* d_uold = nullptr; double* d_unew = nullptr;
   long long ncell = 0;
-  int interpol_type = 1;
+  int interpol_type = 1, interpol_var = 0;
   AmrLevel alev[MAXLEVEL + 1];
   double* d_dtn = nullptr; double* d_dto = nullptr;   // device-resident dtnew/dtold(0:MAXLEVEL+1) of rgpu_amr_steps
   int numbtot[MAXLEVEL + 2] = {0};                    // numbtot(1,ilevel): octs of a level over ALL ranks (amr_commons.f90)
@@ -798,6 +798,10 @@ int amr_godunov_dense(AmrLevel& A, int ilevel, double dt, const double* dt_dev) 
   CUDA_OK(cudaGetLastError());
   if (A.patch) {   // ghost shell: prolongation from level l-1 (what godfine1 does for every missing neighbour oct, :583-593)
     const long long n = L.nslot * G.p.nvar;
+    if (G.interpol_var != 0 || G.interpol_type == 4)
+      amr_fill_shell_coupled_kernel<<<(unsigned)((L.nslot + nthr - 1) / nthr), nthr, 0, G.stream>>>(amr_tree(), G.d_uold, L.d_u[0], A.d_shell_father, L.nslot,
+                                                                                              ilevel, G.interpol_type, G.interpol_var, G.p.smallr);
+    else
     amr_fill_shell_kernel<<<(unsigned)((n + nthr - 1) / nthr), nthr, 0, G.stream>>>(amr_tree(), G.d_uold, L.d_u[0], A.d_shell_father, L.nslot, ilevel,
                                                                                 G.p.nvar, G.interpol_type);
     CUDA_OK(cudaGetLastError());
@@ -826,7 +830,7 @@ int amr_godunov_dense(AmrLevel& A, int ilevel, double dt, const double* dt_dev) 
     s.active = A.d_surf_igrid; s.nact = A.nsurf; s.ilevel = ilevel;
     s.uold = G.d_uold; s.unew = G.d_unew; s.rflux = A.d_rflux;
     s.P = G.phys; s.dt = dt; s.dt_dev = dt_dev; s.dx = A.dx; s.inv_dx = 1.0 / A.dx; s.dx_pow2 = a.dx_pow2;
-    s.interpol_type = G.interpol_type; s.difmag = 0.0; s.nps = 0;
+    s.interpol_type = G.interpol_type; s.interpol_var = G.interpol_var; s.difmag = 0.0; s.nps = 0;
     s.flux_only = 1; s.rflux_index = A.d_surf_io;
     e = dispatch_amr_nd<3>(G.p.riemann, s, G.stream);
     if (e != cudaSuccess) return fail(RGPU_ECUDA, "patch surface flux launch: %s", cudaGetErrorString(e));
@@ -856,7 +860,7 @@ int amr_godunov(AmrLevel& A, int ilevel, double dt, const double* dt_dev = nullp
   a.P = G.phys; a.dt = dt; a.dx = A.dx; a.inv_dx = 1.0 / A.dx;
   int ex;
   a.dx_pow2 = (std::frexp(A.dx, &ex) == 0.5) ? 1 : 0;
-  a.interpol_type = G.interpol_type;
+  a.interpol_type = G.interpol_type; a.interpol_var = G.interpol_var;
   a.difmag = G.p.difmag;
   a.nps = G.p.nvar - (G.p.ndim + 2);
   cudaError_t e;
@@ -1079,10 +1083,12 @@ int rgpu_finalize(void) {
 int rgpu_set_amr(int on, int interpol_type, int interpol_var) {
   if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
   if (on && G.p.mhd) return fail(RGPU_EUNSUPPORTED, "MHD build: AMR mode (divergence-free prolongation, EMF refluxing) not supported; levelmin=levelmax only");
-  if (on && interpol_var != 0) return fail(RGPU_EUNSUPPORTED, "interpol_var=%d not supported (0 only)", interpol_var);
-  if (on && (interpol_type < 0 || interpol_type > 3)) return fail(RGPU_EUNSUPPORTED, "interpol_type=%d not supported", interpol_type);
+  if (on && (interpol_var < 0 || interpol_var > 2)) return fail(RGPU_EINVAL, "interpol_var=%d (0, 1 or 2: hydro/interpol_hydro.f90:318-345)", interpol_var);
+  if (on && (interpol_type < 0 || interpol_type > 4)) return fail(RGPU_EINVAL, "interpol_type=%d (0..4)", interpol_type);
+  if (on && interpol_type == 4 && interpol_var != 2)
+    return fail(RGPU_EINVAL, "interpol_type=4 (central slopes for the velocities) is designed for interpol_var=2 (hydro/interpol_hydro.f90:357-366)");
   G.amr = on != 0;
-  G.interpol_type = interpol_type;
+  G.interpol_type = interpol_type; G.interpol_var = interpol_var;
   return RGPU_OK;
 }
 
@@ -1230,18 +1236,33 @@ static void plan_slabs(Level& L) {
   if (const char* e = getenv("RGPU_E2E_SLABS")) nsl = atoi(e);
   nsl = std::min(nsl, g.noz / 4);
   if (nsl < 3) return;
-  const size_t max_ranges = 4096;
+  const size_t max_copies = 24576;   // cudaMemcpy2DAsync calls per direction and call (a few microseconds of host time each)
   const long long plane = (long long)g.nox * g.noy;
   std::vector<Level::Slab> slabs(nsl);
   size_t total = 0;
   std::vector<int> ig;
+  // sorted igrids -> runs of consecutive igrids -> blocks of equally long, equally spaced runs (one pitched copy per block and
+  // (variable, cell position): the owned octs of an oct plane of a rank's box are such a block in a lattice numbering)
+  size_t ncopies = 0;
   auto coalesce = [&](std::vector<int>& v, std::vector<Level::Range>& out) {
     std::sort(v.begin(), v.end());
+    std::vector<Level::Range> runs;
     for (size_t i = 0; i < v.size();) {
       size_t j = i + 1;
       while (j < v.size() && v[j] == v[j - 1] + 1) j++;
-      out.push_back({v[i], (int)(j - i)});
+      runs.push_back({v[i], (int)(j - i), 0, 1});
       i = j;
+    }
+    for (size_t i = 0; i < runs.size();) {
+      size_t j = i + 1;
+      int stride = 0;
+      if (j < runs.size() && runs[j].n == runs[i].n) {
+        stride = runs[j].lo - runs[i].lo;
+        while (j < runs.size() && runs[j].n == runs[i].n && runs[j].lo - runs[j - 1].lo == stride) j++;
+      }
+      const int cnt = (int)(j - i);
+      if (cnt >= 3) { out.push_back({runs[i].lo, runs[i].n, stride, cnt}); ncopies += (size_t)G.nvs * T_(); i = j; }
+      else { out.push_back(runs[i]); ncopies += (size_t)G.nvs; i++; }
     }
   };
   for (int sl = 0; sl < nsl; sl++) {
@@ -1260,8 +1281,8 @@ static void plan_slabs(Level& L) {
         }
     }
     coalesce(ig, S.down);
-    total += S.up.size() + S.down.size();
-    if (total > max_ranges) return;
+    total = ncopies;
+    if (total > 2 * max_copies) return;
   }
   L.slabs.swap(slabs);
 }
@@ -1352,7 +1373,7 @@ static int alloc_dense_store(Level& L, int ncpu, int nboundary, const int* bound
     const char* e = getenv("RGPU_SWEEP");
     if (e) L.variant = (strcmp(e, "old") == 0) ? 0 : atoi(e);
     if ((long long)G.nvs * T_() * nslot >= (1LL << 32)) L.variant = 0;   // sweep3_kernel addresses the state with 32-bit element indices
-    if (L.variant) { by = sweep3_by_of(L.variant); minb = (L.variant / 10) % 10; if (minb < 1) minb = 1; }
+    if (L.variant) { by = sweep3_by_of(L.variant); minb = (L.variant / 10) % 10; if (minb < 1 || minb == 9) minb = 1; }
   }
   L.by = by;
   const int txo = bx - 2, tyo = nd > 1 ? by - 2 : 1;
@@ -1495,6 +1516,7 @@ int rgpu_plan_level(const rgpu_params* p, int myid, int ncoarse, int ngridmax, c
   if (!p || !father || !info) return fail(RGPU_EINVAL, "null argument");
   if (G.init) return fail(RGPU_EINVAL, "rgpu_plan_level is a dry-run entry point: call it before rgpu_init or after rgpu_finalize");
   G.p = *p; G.myid = myid; G.ncoarse = ncoarse; G.ngridmax = ngridmax; G.father = father;
+  G.nvs = p->mhd ? p->nvar + 3 : p->nvar;
   Level L;
   const int rc = plan_level(L, ilevel, ngrid_active, igrid_active, ncpu, ngrid_recv, igrid_recv, ngrid_emit, igrid_emit, nboundary,
                             boundary_type, ngrid_bound, igrid_bound);
@@ -1508,6 +1530,8 @@ int rgpu_plan_level(const rgpu_params* p, int myid, int ncoarse, int ngridmax, c
     info->own_hi[0] = L.g.ox1; info->own_hi[1] = L.g.oy1; info->own_hi[2] = L.g.oz1;
     info->wrap[0] = L.g.wrapx; info->wrap[1] = L.g.wrapy; info->wrap[2] = L.g.wrapz;
     info->nslot = L.nslot;
+    plan_slabs(L);                       // Level-0 pipeline plan (host only): 0 slabs = serial order
+    info->pipeline_slabs = (int)L.slabs.size();
     if (slot_igrid_out) {
       if (slot_cap < L.nslot) return fail(RGPU_EINVAL, "slot_igrid_out too small (%lld < %lld)", slot_cap, L.nslot);
       memcpy(slot_igrid_out, L.slot_igrid.data(), sizeof(int) * L.nslot);
@@ -1591,10 +1615,18 @@ static int godunov_fine_pipelined(Level& L, const double* uold, double* unew) {
   CUDA_OK(cudaStreamWaitEvent(G.s_out, G.ev_pipe, 0));
   auto h2d = [&](int sl) -> int {
     for (const auto& r : L.slabs[sl].up)
-      for (int iv = 0; iv < G.nvs; iv++)
-        CUDA_OK(cudaMemcpy2DAsync(L.d_mirror + (size_t)iv * T * gspan + (r.lo - L.gmin), sizeof(double) * gspan,
-                                  uold + (size_t)iv * ncell + G.ncoarse + (r.lo - 1), sizeof(double) * G.ngridmax,
-                                  sizeof(double) * r.n, T, cudaMemcpyHostToDevice, G.s_in));
+      for (int iv = 0; iv < G.nvs; iv++) {
+        if (r.count == 1) {   // one run: the 2^ndim cell positions are the rows of one pitched copy
+          CUDA_OK(cudaMemcpy2DAsync(L.d_mirror + (size_t)iv * T * gspan + (r.lo - L.gmin), sizeof(double) * gspan,
+                                    uold + (size_t)iv * ncell + G.ncoarse + (r.lo - 1), sizeof(double) * G.ngridmax,
+                                    sizeof(double) * r.n, T, cudaMemcpyHostToDevice, G.s_in));
+        } else {              // a block of equally spaced runs: the runs are the rows, one copy per cell position
+          for (int ind = 0; ind < T; ind++)
+            CUDA_OK(cudaMemcpy2DAsync(L.d_mirror + ((size_t)iv * T + ind) * gspan + (r.lo - L.gmin), sizeof(double) * r.stride,
+                                      uold + (size_t)iv * ncell + G.ncoarse + (size_t)ind * G.ngridmax + (r.lo - 1), sizeof(double) * r.stride,
+                                      sizeof(double) * r.n, r.count, cudaMemcpyHostToDevice, G.s_in));
+        }
+      }
     CUDA_OK(cudaEventRecord(L.ev_in[sl], G.s_in));
     return RGPU_OK;
   };
@@ -1617,10 +1649,18 @@ static int godunov_fine_pipelined(Level& L, const double* uold, double* unew) {
     CUDA_OK(cudaEventRecord(L.ev_c[sl], G.stream));
     CUDA_OK(cudaStreamWaitEvent(G.s_out, L.ev_c[sl], 0));
     for (const auto& r : L.slabs[sl].down)
-      for (int iv = 0; iv < G.nvs; iv++)
-        CUDA_OK(cudaMemcpy2DAsync(unew + (size_t)iv * ncell + G.ncoarse + (r.lo - 1), sizeof(double) * G.ngridmax,
-                                  L.d_mirror + (size_t)iv * T * gspan + (r.lo - L.gmin), sizeof(double) * gspan,
-                                  sizeof(double) * r.n, T, cudaMemcpyDeviceToHost, G.s_out));
+      for (int iv = 0; iv < G.nvs; iv++) {
+        if (r.count == 1) {
+          CUDA_OK(cudaMemcpy2DAsync(unew + (size_t)iv * ncell + G.ncoarse + (r.lo - 1), sizeof(double) * G.ngridmax,
+                                    L.d_mirror + (size_t)iv * T * gspan + (r.lo - L.gmin), sizeof(double) * gspan,
+                                    sizeof(double) * r.n, T, cudaMemcpyDeviceToHost, G.s_out));
+        } else {
+          for (int ind = 0; ind < T; ind++)
+            CUDA_OK(cudaMemcpy2DAsync(unew + (size_t)iv * ncell + G.ncoarse + (size_t)ind * G.ngridmax + (r.lo - 1), sizeof(double) * r.stride,
+                                      L.d_mirror + ((size_t)iv * T + ind) * gspan + (r.lo - L.gmin), sizeof(double) * r.stride,
+                                      sizeof(double) * r.n, r.count, cudaMemcpyDeviceToHost, G.s_out));
+        }
+      }
     return RGPU_OK;
   };
   int rc;
@@ -1938,7 +1978,7 @@ static int amr_step_dev(int l, int icount, int levelmin, const int* nsub) {
   }
   if (l < nlev && A.nact > 0) {                                         // upload_fine :441
     const int n = A.nact * T_();
-    amr_upload_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_son - 1, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar, G.p.smallr);
+    amr_upload_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_son - 1, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar, G.p.smallr, G.interpol_var, G.p.ndim);
     CUDA_OK(cudaGetLastError());
     A.launches++;
   }
@@ -1992,7 +2032,8 @@ int rgpu_upload_fine(int ilevel) {
   AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
   if (A->nact == 0 || ilevel >= G.p.nlevelmax) return RGPU_OK;
   const int n = A->nact * T_();
-  amr_upload_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_son - 1, A->d_active, A->nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar, G.p.smallr);
+  amr_upload_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_son - 1, A->d_active, A->nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar, G.p.smallr,
+                                                         G.interpol_var, G.p.ndim);
   CUDA_OK(cudaGetLastError());
   A->launches++;
   return RGPU_OK;

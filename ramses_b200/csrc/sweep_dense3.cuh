@@ -33,7 +33,9 @@ struct Sweep3Smem {
 
 // VEC: 0 = three scalar solves with the branching solvers of hydro_device.cuh (round-1 arithmetic path, new loop);
 //      1 = one 3-lane solve (hydro_vec.cuh); 2 = three scalar solves with the branch-free forms of hydro_vec.cuh.
-template <int RIEMANN, int SLOPE, int BY, int MINB, int VEC>
+// CONVW: the two halo-row warps (ty = 0 and ty = BY-1, idle while the owned rows solve their faces) stage plane k+3 and convert
+//        plane k+2 to primitive variables during the solve phase of plane k; the other warps never touch the staging buffer.
+template <int RIEMANN, int SLOPE, int BY, int MINB, int VEC, bool CONVW = false>
 __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a) {
   using S = Sweep3Smem<BY>;
   constexpr int NDIM = 3, BX = 32, NV = S::NV, QX = S::QX, NQ = S::NQ, NT = S::NT, PL = S::PL;
@@ -145,21 +147,61 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
       }
     };
 
+    // converter threads (CONVW): 64 threads (rows 0 and BY-1) own the cells i = ctid + 64 j of the staged plane
+    constexpr int NCONV = (PL + 63) / 64;
+    const bool conv_thread = CONVW && (ty == 0 || ty == BY - 1);
+    const int ctid = tx + (ty == 0 ? 0 : 32);
+    unsigned coff[CONVW ? NCONV : 1];
+    if (conv_thread) {
+#pragma unroll
+      for (int j = 0; j < (CONVW ? NCONV : 1); j++) {
+        const int i = min(ctid + j * 64, PL - 1);
+        const int xc = wrap_or_clamp(x0 - 2 + i % QX, g.ncx, g.wrapx);
+        const int yc = wrap_or_clamp(y0 - 2 + i / QX, g.ncy, g.wrapy);
+        coff[j] = (unsigned)cell_offset<NDIM>(g, xc, yc, 0);
+      }
+    }
+    auto conv_stage = [&](unsigned zo) {       // cp.async of the converter's cells of one plane
+#pragma unroll
+      for (int j = 0; j < (CONVW ? NCONV : 1); j++) {
+        const int i = ctid + j * 64;
+        if (i >= PL) break;
+        const unsigned off = coff[j] + zo;
+#pragma unroll
+        for (int n = 0; n < NV; n++) cp_async8(stage + n * PL + i, a.uin + ((unsigned)n * vstride + off));
+      }
+    };
+    auto conv_to_ring = [&](int slot) {
+      cp_async_wait_all();
+#pragma unroll 1
+      for (int i = ctid; i < PL; i += 64) {
+        double u[NV];
+#pragma unroll
+        for (int n = 0; n < NV; n++) u[n] = stage[n * PL + i];
+        to_ring(u, slot, i);
+      }
+    };
+
     __syncthreads();                           // previous segment done with shared memory
     load_plane_direct(z0 - 2, 0);
     load_plane_direct(z0 - 1, 1);
-    stage_plane_async(z0);
+    if (CONVW) {
+      load_plane_direct(z0, 2);
+      if (conv_thread) conv_stage(zoff(z0 + 1));
+    } else {
+      stage_plane_async(z0);
+    }
     const int kbeg = z0 - 1, kend = z1;
     bool pend = false;                         // the x part of the update of the previous plane waits for its y and z parts
     // ring slots of planes k-1, k, k+1 rotate; the plane offsets of k-1, k, k+2 advance incrementally (no division, no
     // modulo inside the plane loop)
     int sm1 = 0, sc = 1, sp1 = 2;
-    int zc2 = wrap_or_clamp(kbeg + 2, g.ncz, g.wrapz);
-    unsigned zo_m1 = zoff(kbeg - 1), zo_0 = zoff(kbeg), zo_1 = zoff(kbeg + 1), zo_2 = zoff(kbeg + 2);
+    int zc3 = wrap_or_clamp(kbeg + 3, g.ncz, g.wrapz);
+    unsigned zo_m1 = zoff(kbeg - 1), zo_0 = zoff(kbeg), zo_1 = zoff(kbeg + 1), zo_2 = zoff(kbeg + 2), zo_3 = zoff(kbeg + 3);
     for (int k = kbeg; k <= kend; k++) {
-      stage_to_ring(sp1);
+      if (!CONVW) stage_to_ring(sp1);
       __syncthreads();                         // ring plane k+1 complete; every row has published Fy(k-1)
-      if (k < kend) stage_plane_async_off(zo_2);
+      if (!CONVW && k < kend) stage_plane_async_off(zo_2);
       if (own && pend) {                       // y part of the update of plane k-1 (godfine1 :751-792: x, then y, then z)
 #pragma unroll
         for (int n = 0; n < NV; n++) {
@@ -267,6 +309,10 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
       }
       __syncthreads();                         // qm_y of every row is visible
 
+      if (CONVW && conv_thread) {              // the solve phase of the owned rows: convert plane k+2, stage plane k+3
+        if (k + 2 <= kend + 1) conv_to_ring(sm1);          // slot of plane k-1: nobody reads it after the barrier above
+        if (k + 3 <= kend + 1) conv_stage(zo_3);
+      }
       double fx[NV], fy[NV], fz[NV];
 #pragma unroll
       for (int n = 0; n < NV; n++) { fx[n] = 0.0; fy[n] = 0.0; fz[n] = 0.0; }
@@ -356,9 +402,9 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
       }
       pend = plane_flux;
       { const int t = sm1; sm1 = sc; sc = sp1; sp1 = t; }
-      zo_m1 = zo_0; zo_0 = zo_1; zo_1 = zo_2;
-      zc2 = g.wrapz ? (zc2 + 1 == g.ncz ? 0 : zc2 + 1) : min(zc2 + 1, g.ncz - 1);
-      zo_2 = (unsigned)((zc2 & 1) << 2) * (unsigned)g.nslot + (unsigned)(g.nox * g.noy) * (unsigned)(zc2 >> 1);
+      zo_m1 = zo_0; zo_0 = zo_1; zo_1 = zo_2; zo_2 = zo_3;
+      zc3 = g.wrapz ? (zc3 + 1 == g.ncz ? 0 : zc3 + 1) : min(zc3 + 1, g.ncz - 1);
+      zo_3 = (unsigned)((zc3 & 1) << 2) * (unsigned)g.nslot + (unsigned)(g.nox * g.noy) * (unsigned)(zc3 >> 1);
     }
   }
 
@@ -382,10 +428,10 @@ __global__ void __launch_bounds__(32 * BY, MINB) sweep3_kernel(const SweepArgs a
 }
 
 #ifndef RGPU_HOST_NUMERICS
-template <int RIEMANN, int SLOPE, int BY, int MINB, int VEC>
+template <int RIEMANN, int SLOPE, int BY, int MINB, int VEC, bool CONVW = false>
 cudaError_t launch_sweep3_v(const SweepArgs& a, int nblocks, cudaStream_t st) {
   constexpr size_t smem = sizeof(double) * Sweep3Smem<BY>::doubles;
-  auto kern = sweep3_kernel<RIEMANN, SLOPE, BY, MINB, VEC>;
+  auto kern = sweep3_kernel<RIEMANN, SLOPE, BY, MINB, VEC, CONVW>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -413,6 +459,11 @@ cudaError_t launch_sweep3_s(const SweepArgs& a, int nblocks, cudaStream_t st, in
     case 1212: return launch_sweep3_v<RIEMANN, SLOPE, 12, 1, 2>(a, nblocks, st);
 #ifdef SWEEP3_TUNING_VARIANTS
     case 1211: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 12, 1, 1>(a, nblocks, st); break;
+    case 1292: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 12, 1, 2, true>(a, nblocks, st); break;   // 9: converter warps
+    case 1412: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 14, 1, 2>(a, nblocks, st); break;
+    case 1492: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 14, 1, 2, true>(a, nblocks, st); break;
+    case 1692: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 16, 1, 2, true>(a, nblocks, st); break;
+    case 1291: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 12, 1, 1, true>(a, nblocks, st); break;
     case 1210: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 12, 1, 0>(a, nblocks, st); break;
     case 811: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 8, 1, 1>(a, nblocks, st); break;
     case 821: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 8, 2, 1>(a, nblocks, st); break;

@@ -89,6 +89,17 @@ static void riemann_nd(int solver, const double* ql, const double* qr, double* f
 
 // Built with -fvisibility=hidden -Wl,-Bsymbolic: the kernels compiled here have the same mangled names as the CUDA launch stubs
 // of libramses_gpu.so (loaded RTLD_GLOBAL by the ABI tests in the same process) and must never be interposed by them.
+// interpol_hydro for the whole state (interpol_var 0/1/2, interpol_type 0..4): u1 [n][2*ndim+1][ndim+2] -> u2 [n][2^ndim][ndim+2]
+template <int ND>
+static void interpol_full_nd(int itype, int ivar, int n, const double* u1, double* u2, double smallr) {
+  constexpr int NVX = ND + 2, T = 1 << ND, NA = 2 * ND + 1;
+  for (int i = 0; i < n; i++) {
+    double a[7][NVX], b[T][NVX];
+    for (int j = 0; j < NA; j++) for (int v = 0; v < NVX; v++) a[j][v] = u1[(i * NA + j) * NVX + v];
+    amr_interpol_hydro<ND, NVX>(a, itype, ivar, smallr, b);
+    for (int t = 0; t < T; t++) for (int v = 0; v < NVX; v++) u2[(i * T + t) * NVX + v] = b[t][v];
+  }
+}
 #pragma GCC visibility push(default)
 extern "C" {
 
@@ -218,6 +229,12 @@ void devnum_amr_interpol(int ndim, int interpol_type, int n, const double* a, do
     else if (ndim == 2) amr_interpol_var<2>(a + i * na, interpol_type, u2 + i * T);
     else amr_interpol_var<3>(a + i * na, interpol_type, u2 + i * T);
   }
+}
+
+void devnum_amr_interpol_full(int ndim, int interpol_type, int interpol_var, int n, const double* u1, double* u2, double smallr) {
+  if (ndim == 1) interpol_full_nd<1>(interpol_type, interpol_var, n, u1, u2, smallr);
+  else if (ndim == 2) interpol_full_nd<2>(interpol_type, interpol_var, n, u1, u2, smallr);
+  else interpol_full_nd<3>(interpol_type, interpol_var, n, u1, u2, smallr);
 }
 
 // amr_godfine_kernel (the oct-batch kernel of AMR mode) run by the emulated launch on host copies of the arrays: updates unew of
@@ -455,7 +472,8 @@ int devnum_sweep3(int solver, int N, int nblocks, const double* uin, double* uou
   if (nblocks > a.nwork) nblocks = (int)a.nwork;
   a.part = part; a.refined = nullptr;
 #define S3(RS, BY, VEC) emulate_launch(sweep3_kernel<RS, -1, BY, 1, VEC>, a, nblocks, 32, BY, Sweep3Smem<BY>::doubles)
-#define S3V(RS, BY) do { if (vec == 0) S3(RS, BY, 0); else if (vec == 1) S3(RS, BY, 1); else S3(RS, BY, 2); } while (0)
+#define S3C(RS, BY) emulate_launch(sweep3_kernel<RS, -1, BY, 1, 2, true>, a, nblocks, 32, BY, Sweep3Smem<BY>::doubles)
+#define S3V(RS, BY) do { if (vec == 0) S3(RS, BY, 0); else if (vec == 1) S3(RS, BY, 1); else if (vec == 12) S3C(RS, BY); else S3(RS, BY, 2); } while (0)
 #define S3B(RS) do { if (by == 8) S3V(RS, 8); else if (by == 16) S3V(RS, 16); else S3V(RS, 12); } while (0)
   if (solver == RIEMANN_LLF) S3B(RIEMANN_LLF); else if (solver == RIEMANN_EXACT) S3B(RIEMANN_EXACT);
   else if (solver == RIEMANN_ACOUSTIC) S3B(RIEMANN_ACOUSTIC); else if (solver == RIEMANN_HLLC) S3B(RIEMANN_HLLC); else S3B(RIEMANN_HLL);

@@ -217,3 +217,17 @@ def test_bench_reference_arm_contract():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert j["gpu_launches"] == 0
+
+
+@pytest.mark.parametrize("order,ncpu,expect", [("lattice", 1, True), ("lattice", 8, True), ("creation", 1, False), ("random", 8, False)])
+def test_level0_pipeline_plan_host_only(order, ncpu, expect):
+    """plan of the Level-0 slab pipeline (host only, rgpu_plan_level): a spatially coherent oct numbering gives a plan -- also for
+    a rank of a 2x2x2 decomposition, whose owned octs inside a slab are equally spaced runs (pitched copies) --, the reference's
+    creation order and a random numbering scatter every slab over the igrid window (no plan: serial order)."""
+    from ramses_b200.hydro import plan_level
+    from ramses_b200.tree import build_uniform_tree, coarse_dims_for_ranks
+    coarse = coarse_dims_for_ranks(3, ncpu)
+    a = build_uniform_tree(3, 6, coarse=coarse, myid=1, ncpu=ncpu, order=order, boxlen=1.0)
+    info, slots = plan_level(a, 6)
+    assert info.dense == 1
+    assert (info.pipeline_slabs >= 3) == expect, info.pipeline_slabs

@@ -324,6 +324,42 @@ def test_amr_prolongation_of_the_kernels_equals_oracle(orc, dev, ndim, itype):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+@pytest.mark.parametrize("itype,ivar", [(1, 1), (2, 1), (3, 1), (0, 2), (1, 2), (2, 2), (3, 2), (4, 2), (2, 0)])
+def test_amr_coupled_prolongation_equals_oracle(orc, dev, ndim, itype, ivar):
+    """amr_interpol_hydro (the whole state: interpol_var 1 = internal energy, 2 = velocities + internal energy with the momentum
+    correction, interpol_type 4 = central slopes for the velocities; hydro/interpol_hydro.f90:318-440) == orc_interpol_hydro"""
+    L = orc.lib()
+    dp = C.POINTER(C.c_double)
+    L.orc_set_interpol.argtypes = [C.c_int, C.c_int]
+    L.orc_interpol_hydro.argtypes = [C.POINTER(orc.Params), dp, dp]
+    dev.devnum_amr_interpol_full.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_double]
+    n, na, T, nv = 3000, 2 * ndim + 1, 1 << ndim, ndim + 2
+    rng = np.random.default_rng(100 * ndim + 10 * itype + ivar)
+    u1 = np.zeros((n, na, nv))
+    rho = 10.0 ** rng.uniform(-2, 2, (n, 1)) * (1 + 0.3 * rng.standard_normal((n, na)))
+    rho = np.abs(rho) + 1e-3
+    rho[:50, 2] = 1e-13                                    # below smallr: the floor of the velocity / kinetic-energy divisions
+    v = rng.standard_normal((n, na, ndim)) * 10.0 ** rng.uniform(-2, 1, (n, 1, 1))
+    eint = 10.0 ** rng.uniform(-3, 2, (n, na))
+    u1[:, :, 0] = rho
+    u1[:, :, 1:1 + ndim] = rho[:, :, None] * v
+    u1[:, :, ndim + 1] = eint + 0.5 * rho * (v ** 2).sum(axis=2)
+    u1 = np.ascontiguousarray(u1)
+    got = np.zeros((n, T, nv))
+    dev.devnum_amr_interpol_full(ndim, itype, ivar, n, orc.dptr(u1), orc.dptr(got), 1e-10)
+    p = orc.make_params(ndim=ndim)
+    ref = np.zeros((n, T, nv))
+    try:
+        L.orc_set_interpol(itype, ivar)
+        for i in range(n):
+            L.orc_interpol_hydro(C.byref(p), orc.dptr(u1[i]), orc.dptr(ref[i]))
+    finally:
+        L.orc_set_interpol(1, 0)
+    assert np.isfinite(got).all()
+    assert np.array_equal(got, ref)
+
+
 @pytest.mark.parametrize("ndim,solver,difmag", [(1, "hllc", 0.0), (2, "hllc", 0.0), (2, "llf", 0.0), (3, "hllc", 0.0), (3, "exact", 0.0),
                                                  (2, "hllc", 0.1), (3, "hllc", 0.1)])
 def test_amr_oct_batch_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, solver, difmag):
@@ -555,7 +591,8 @@ def test_vec_solvers_equal_scalar(orc, dev, solver):
 
 @pytest.mark.parametrize("solver,st,N,nblocks,by,vec", [("hllc", 1, 16, 3, 12, 1), ("hllc", 2, 16, 2, 12, 0), ("hllc", 1, 16, 5, 12, 2),
                                                         ("exact", 1, 16, 2, 12, 1), ("llf", 8, 16, 4, 8, 1), ("hll", 7, 16, 3, 16, 1),
-                                                        ("acoustic", 3, 16, 3, 12, 1), ("hllc", 1, 64, 7, 12, 1), ("exact", 2, 32, 5, 8, 1)])
+                                                        ("acoustic", 3, 16, 3, 12, 1), ("hllc", 1, 64, 7, 12, 1), ("exact", 2, 32, 5, 8, 1),
+                                                        ("hllc", 1, 16, 3, 12, 12), ("hllc", 2, 64, 5, 12, 12), ("exact", 1, 32, 4, 16, 12)])
 def test_sweep3_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, solver, st, N, nblocks, by, vec):
     """sweep3_kernel (sweep_dense3.cuh, the round-2 form of the hot kernel: 3-lane branch-free face solves, two barriers per
     plane, face states formed before the solve) executed on the CPU by the emulated launch: the new state equals one level

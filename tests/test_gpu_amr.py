@@ -69,12 +69,12 @@ BOUND_2D_WALLS_X_OUTFLOW_Y = [(1, (0, 0), (1, 1), (0, 0)), (2, (2, 2), (1, 1), (
 
 
 def run_case(ndim, levelmin, levelmax, bound, regions, riemann, slope_type, ncoarse_dev, interpol_type, nsub, boxlen=1.0,
-             err=0.05, nexpand=1, difmag=0.0, bound_regions=None):
+             err=0.05, nexpand=1, difmag=0.0, bound_regions=None, interpol_var=0):
     from oracle.amr import AmrRun
     from ramses_b200.hydro import HydroGPU
     r = AmrRun(ndim, levelmin, levelmax, bound, boxlen, nsubcycle=nsub, nexpand=nexpand, ngridmax=20000, riemann=riemann,
                slope_type=slope_type, err_grad_d=err, err_grad_u=err, err_grad_p=err, interpol_type=interpol_type,
-               regions=regions, tout=[1e9], bound_regions=bound_regions)
+               interpol_var=interpol_var, regions=regions, tout=[1e9], bound_regions=bound_regions)
     r.p.difmag = difmag                            # hydro_parameters.f90:81 (cmpdivu + consup in unsplit)
     r.flag_coarse(); r.init_refine(); r.init_refine_2()
     for _ in range(ncoarse_dev):                   # develop the flow with the full (regridding) driver
@@ -98,7 +98,7 @@ def run_case(ndim, levelmin, levelmax, bound, regions, riemann, slope_type, ncoa
     nlev = [len(r.active[l]) for l in range(1, levelmax + 1)]
     assert sum(1 for n in nlev[levelmin:] if n > 0) >= 1, nlev      # a genuinely refined mesh
     a = commons_from_run(r, riemann, slope_type)
-    h = HydroGPU(a, amr_mode=True, interpol_type=interpol_type)
+    h = HydroGPU(a, amr_mode=True, interpol_type=interpol_type, interpol_var=interpol_var)
     for l in range(1, levelmax + 1):
         if len(a.active[l]):
             h.bind_level(l)
@@ -146,6 +146,25 @@ def test_amr_3d_sedov_like(riemann):
         assert (np.abs(got - ref) / scale).max() <= 1e-12
     else:
         assert np.array_equal(got, ref), (np.abs(got - ref).max(), nlev)
+
+
+@pytest.mark.parametrize("ndim,itype,ivar", [(3, 2, 1), (3, 4, 2), (3, 1, 2), (2, 2, 2), (2, 4, 2), (1, 2, 1)])
+def test_amr_interpol_var_bitwise(ndim, itype, ivar):
+    """interpol_var 1, 2 and interpol_type 4 (hydro/interpol_hydro.f90:318-440) on adaptively refined meshes: the oct-batch
+    kernel's ghost prolongation and upload_fine's internal-energy averaging equal the oracle bit for bit."""
+    if ndim == 1:
+        got, ref, dtnew, r, nlev = run_case(1, 3, 8, (1, 1, 0, 0, 0, 0), SOD, "hllc", 2, 6, itype, [1, 1, 1, 2], interpol_var=ivar)
+    elif ndim == 2:
+        regs = [dict(type="square", x_center=0.5, y_center=0.5, length_x=10, length_y=10, exp_region=10, d=1.0, p=0.1),
+                dict(type="square", x_center=0.3, y_center=0.4, length_x=0.3, length_y=0.25, exp_region=2, d=2.0, u=0.3, v=-0.2, p=1.0)]
+        got, ref, dtnew, r, nlev = run_case(2, 3, 5, (1, 1, 2, 2, 0, 0), regs, "hllc", 2, 2, itype, [1, 2], interpol_var=ivar,
+                                            bound_regions=BOUND_2D_WALLS_X_OUTFLOW_Y)
+    else:
+        regs = [dict(type="square", x_center=0.5, y_center=0.5, z_center=0.5, length_x=10, length_y=10, length_z=10, exp_region=10, d=1.0, p=0.1),
+                dict(type="square", x_center=0.4, y_center=0.45, z_center=0.55, length_x=0.3, length_y=0.3, length_z=0.3, exp_region=2, d=1.5, u=0.2, p=2.0)]
+        got, ref, dtnew, r, nlev = run_case(3, 3, 4, (0,) * 6, regs, "hllc", 1, 1, itype, [2, 2], interpol_var=ivar)
+    assert dtnew[3] == r.dtnew[3]
+    assert np.array_equal(got, ref), (np.abs(got - ref).max(), nlev)
 
 
 @pytest.mark.parametrize("ndim", [1, 2, 3])
@@ -218,9 +237,9 @@ def _nested_case(levelmin, levelmax, half_width, riemann="hllc", slope_type=1):
     return a
 
 
-def _run_nested_gpu(a, levelmin, levelmax, ncoarse_steps=1):
+def _run_nested_gpu(a, levelmin, levelmax, ncoarse_steps=1, interpol_type=1, interpol_var=0):
     from ramses_b200.hydro import HydroGPU, amr_step
-    h = HydroGPU(a, amr_mode=True, interpol_type=1)
+    h = HydroGPU(a, amr_mode=True, interpol_type=interpol_type, interpol_var=interpol_var)
     for l in range(1, levelmax + 1):
         h.bind_level(l)
     h.upload_state(0)
@@ -240,20 +259,23 @@ def _run_nested_gpu(a, levelmin, levelmax, ncoarse_steps=1):
     return u0, dtnew, nsub, launches
 
 
-def test_nested_tree_gpu_matches_oracle_bitwise():
-    """Product-side tree fabricator (ramses_b200.tree.build_nested_tree: 3 refined levels, 2:1 nesting) driven by the host
+@pytest.mark.parametrize("itype,ivar", [(1, 0), (2, 1), (4, 2), (1, 2)])
+def test_nested_tree_gpu_matches_oracle_bitwise(itype, ivar):
+    """(interpol_type, interpol_var) incl. the coupled prolongations (internal energy / velocities, type 4) in the oct-batch
+    kernel, the patch-mode shell fill and upload_fine.
+    Product-side tree fabricator (ramses_b200.tree.build_nested_tree: 3 refined levels, 2:1 nesting) driven by the host
     mirror of amr_step (ramses_b200.hydro.amr_step, sub-cycling 1,2,2) == the oracle's amr_step on the same arrays."""
     from oracle.amr import AmrRun
     levelmin, levelmax, hw = 4, 6, 3
     a = _nested_case(levelmin, levelmax, hw)
     r = AmrRun(3, levelmin, levelmax, (0,) * 6, 1.0, nsubcycle=[1, 2, 2], ngridmax=a.ngridmax, riemann="hllc", slope_type=1,
-               interpol_type=1, tout=[1e9])
+               interpol_type=itype, interpol_var=ivar, tout=[1e9])
     assert r.ncell == a.ncell
     r.son[1:] = a.son; r.father[1:] = a.father; r.nbor[:, 1:] = a.nbor
     for l in range(1, levelmax + 1):
         r.active[l] = [int(g) for g in a.active[l]]
     r.push_all()
-    u0, dtnew, nsub, launches = _run_nested_gpu(a, levelmin, levelmax)
+    u0, dtnew, nsub, launches = _run_nested_gpu(a, levelmin, levelmax, interpol_type=itype, interpol_var=ivar)
     r.uold[:] = u0.ravel()
     r.static = True
     r.amr_step(levelmin, 1)
