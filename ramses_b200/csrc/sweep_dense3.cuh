@@ -447,19 +447,19 @@ cudaError_t launch_sweep3_v(const SweepArgs& a, int nblocks, cudaStream_t st) {
   kern<<<nblocks, dim3(32, BY, 1), smem, st>>>(a);
   return cudaGetLastError();
 }
-// variant = 100*BY + 10*MINB + VEC.  The product default is SWEEP3_DEFAULT_VARIANT; the others exist for the tuning runs
+// variant = 100*BY + 10*MINB + VEC (MINB digit 9: one CTA per SM with converter warps).  The product default is SWEEP3_DEFAULT_VARIANT; the others exist for the tuning runs
 // recorded under profiles/ (RGPU_SWEEP=<variant> at bind time) and are compiled for slope_type 1 only.
 #ifndef SWEEP3_DEFAULT_VARIANT
-#define SWEEP3_DEFAULT_VARIANT 1212
+#define SWEEP3_DEFAULT_VARIANT 1292
 #endif
 constexpr int sweep3_by_of(int variant) { return variant / 100; }
 template <int RIEMANN, int SLOPE>
 cudaError_t launch_sweep3_s(const SweepArgs& a, int nblocks, cudaStream_t st, int variant) {
   switch (variant) {
-    case 1212: return launch_sweep3_v<RIEMANN, SLOPE, 12, 1, 2>(a, nblocks, st);
+    case 1292: return launch_sweep3_v<RIEMANN, SLOPE, 12, 1, 2, true>(a, nblocks, st);   // 9 = converter warps, one CTA per SM
 #ifdef SWEEP3_TUNING_VARIANTS
+    case 1212: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 12, 1, 2>(a, nblocks, st); break;
     case 1211: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 12, 1, 1>(a, nblocks, st); break;
-    case 1292: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 12, 1, 2, true>(a, nblocks, st); break;   // 9: converter warps
     case 1412: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 14, 1, 2>(a, nblocks, st); break;
     case 1492: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 14, 1, 2, true>(a, nblocks, st); break;
     case 1692: if (SLOPE == 1) return launch_sweep3_v<RIEMANN, SLOPE == 1 ? 1 : SLOPE, 16, 1, 2, true>(a, nblocks, st); break;
