@@ -115,6 +115,7 @@ struct Level {
   std::vector<long long> emit_off, recv_off;
   // overlap of the exchange with the interior of the next sweep (rgpu_level_steps, multi-rank): interior / frame work maps
   bool overlap = false;
+  int reserve_sms = 0;
   SweepWork wk_int{}, wk_frame{};
   long long nwork_int = 0, nwork_frame = 0;
   cudaEvent_t ev_x = nullptr, ev_s = nullptr;
@@ -544,6 +545,9 @@ int launch_sweep(Level& L, int zlo = -1, int zhi = -1, int part = 0) {
     a.wk = part == 1 ? L.wk_int : L.wk_frame;
     a.nwork = part == 1 ? L.nwork_int : L.nwork_frame;
     nblocks = (int)std::min<long long>(L.nblocks, a.nwork);
+    // the interior launch leaves a few SMs to the pack / NCCL / unpack kernels of the exchange stream: a persistent CTA per SM
+    // holds the whole register file, nothing else could become resident before the interior ends (RGPU_OVERLAP_RESERVE)
+    if (part == 1 && nblocks > 4 * L.reserve_sms) nblocks -= L.reserve_sms;
     a.part_stride = 2 * L.nblocks; a.part_off = part == 1 ? 0 : L.nblocks;
   }
   if (zlo >= 0) {
@@ -1391,6 +1395,7 @@ static int alloc_dense_store(Level& L, int ncpu, int nboundary, const int* bound
   L.overlap = false;
   if (nd == 3 && !G.p.mhd && !G.amr && ncpu > 1) {
     const char* e = getenv("RGPU_OVERLAP");
+    if (const char* r = getenv("RGPU_OVERLAP_RESERVE")) L.reserve_sms = std::max(0, atoi(r));
     SweepWork wi{};
     wi.mode = 1;
     auto range = [](int n_owned, int tile, int ntile, int wrap, int& i0, int& i1) {
@@ -1402,7 +1407,12 @@ static int alloc_dense_store(Level& L, int ncpu, int nboundary, const int* bound
     range(g.oy1 - g.oy0, tyo, L.nty, g.wrapy, wi.iy0, wi.iy1);
     wi.iz0 = g.wrapz ? g.oz0 : g.oz0 + 2; wi.iz1 = g.wrapz ? g.oz1 : g.oz1 - 2;
     const long long nxi = wi.ix1 - wi.ix0, nyi = wi.iy1 - wi.iy0, nzi = wi.iz1 - wi.iz0;
-    if (!(e && atoi(e) == 0) && nxi > 0 && nyi > 0 && nzi > 4) {
+    // measured on 2 B200 (profiles/r2_mgpu_overlap_probe.txt): the split pays 4 % at 256^3 per rank; at 512^3 the exchange is
+    // 2 % of the step and a NCCL kernel that becomes resident on one rank before the persistent interior CTAs (and then spins
+    // for its peer) costs more than the overlap gains -- default: overlap only below 100 M owned cells (RGPU_OVERLAP=1 forces it)
+    const long long nown = (long long)(g.ox1 - g.ox0) * (g.oy1 - g.oy0) * (g.oz1 - g.oz0);
+    const bool want = e ? atoi(e) != 0 : nown <= 100000000LL;
+    if (want && nxi > 0 && nyi > 0 && nzi > 4) {
       L.wk_int = wi; L.wk_frame = wi; L.wk_frame.mode = 2;
       L.nwork_int = nxi * nyi * nzi;
       L.nwork_frame = ((long long)L.ntx * L.nty - nxi * nyi) * (g.oz1 - g.oz0) + nxi * nyi * ((wi.iz0 - g.oz0) + (g.oz1 - wi.iz1));
