@@ -155,6 +155,13 @@ int rgpu_make_virtual_fine(int ilevel);                    /* amr/virtual_bounda
 int rgpu_make_virtual_reverse(int ilevel);                 /* amr/virtual_boundaries.f90:693   */
 int rgpu_upload_fine(int ilevel);                          /* hydro/interpol_hydro.f90:5 (restriction of split cells) */
 
+/* hydro_flag (hydro/hydro_flag.f90:1, hydro_refine hydro/godunov_utils.f90:125-263) on the device-resident state (AMR mode):
+ * flag1(cell) = 1 for every active cell of the level whose relative gradient of density / velocity / pressure towards a
+ * neighbour (a missing neighbour cell is replaced by its father cell) exceeds err_grad = (err_grad_d, err_grad_u, err_grad_p)
+ * (-1 disables a test), floor = (floor_d, floor_u, floor_p).  flag1 is the host array flag1(1:ncell) of amr_commons: only the
+ * 4-byte flags of the level travel, the state stays on the device for the flag_fine pass.                                  */
+int rgpu_hydro_flag(int ilevel, const double err_grad[3], const double floor[3], int* flag1);
+
 /* ---- fused fast path --------------------------------------------------------------
  * nstep level steps of a levelmin=levelmax run in amr_step order
  * (amr/amr_step.f90:326 courant, :333 set_unew, :388 godunov_fine, :423 set_uold,

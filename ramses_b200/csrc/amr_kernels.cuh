@@ -678,6 +678,84 @@ __global__ void amr_upload_kernel(double* __restrict__ u, const int* __restrict_
     u[(size_t)(ndim + 1) * ncell + ic - 1] = getx / (double)T + ekin + 0.0;
   }
 }
+// hydro_refine (hydro/godunov_utils.f90:125-263) for one (left, centre, right) triple of conservative states: relative
+// gradients of density, pressure and Mach-scaled velocity against err_grad_d / _u / _p (a negative threshold disables a test)
+template <int NDIM>
+__device__ bool amr_hydro_refine(const double* ug_, const double* um_, const double* ud_, double gamma, double smallr,
+                                 double err_d, double err_u, double err_p, double floor_d, double floor_u, double floor_p) {
+  constexpr int IP = NDIM + 1;
+  double u[3][NDIM + 2];
+  const double* src[3] = {ug_, um_, ud_};
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+#pragma unroll
+    for (int v = 0; v < NDIM + 2; v++) u[s][v] = src[s][v];
+    u[s][0] = u[s][0] > smallr ? u[s][0] : smallr;
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) u[s][d + 1] = u[s][d + 1] / u[s][0];
+    double ek = 0.0;
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) ek = ek + 0.5 * u[s][0] * (u[s][d + 1] * u[s][d + 1]);
+    u[s][IP] = (gamma - 1.0) * (u[s][IP] - ek);
+  }
+  const double *g = u[0], *c = u[1], *d_ = u[2];
+  bool ok = false;
+  if (err_d >= 0.0) {
+    const double a = fabs((d_[0] - c[0]) / (d_[0] + c[0] + floor_d)), b = fabs((c[0] - g[0]) / (c[0] + g[0] + floor_d));
+    const double e = 2.0 * (a > b ? a : b);
+    ok = ok || e > err_d;
+  }
+  if (err_p >= 0.0) {
+    const double a = fabs((d_[IP] - c[IP]) / (d_[IP] + c[IP] + floor_p)), b = fabs((c[IP] - g[IP]) / (c[IP] + g[IP] + floor_p));
+    const double e = 2.0 * (a > b ? a : b);
+    ok = ok || e > err_p;
+  }
+  if (err_u >= 0.0) {
+    const double f2 = floor_u * floor_u;
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) {
+      const double vg = g[k + 1], vm = c[k + 1], vd = d_[k + 1];
+      const double tg = gamma * g[IP] / g[0], tm = gamma * c[IP] / c[0], td = gamma * d_[IP] / d_[0];
+      const double cg = sqrt(tg > f2 ? tg : f2), cm = sqrt(tm > f2 ? tm : f2), cd = sqrt(td > f2 ? td : f2);
+      const double a = fabs((vd - vm) / (cd + cm + fabs(vd) + fabs(vm) + floor_u));
+      const double b = fabs((vm - vg) / (cm + cg + fabs(vm) + fabs(vg) + floor_u));
+      const double e = 2.0 * (a > b ? a : b);
+      ok = ok || e > err_u;
+    }
+  }
+  return ok;
+}
+// hydro_flag (hydro/hydro_flag.f90:1-200) on the device: one thread per active cell; a missing neighbour cell is replaced by its
+// father cell (:113-119 -- exactly what amr_getnborfather returns one level down).  out[i*T + ind] = 1 where the cell must be
+// flagged (the host ORs it into flag1: the state never leaves the device for a flag_fine pass).
+template <int NDIM>
+__global__ void amr_hydro_flag_kernel(const AmrTree t, const double* __restrict__ uold, const int* __restrict__ igrid, int n, int ilevel,
+                                      double gamma, double smallr, double err_d, double err_u, double err_p, double floor_d,
+                                      double floor_u, double floor_p, int* __restrict__ out) {
+  constexpr int T = 1 << NDIM, NV = NDIM + 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * T) return;
+  const int o = i / T, ind = i % T;
+  const int c = amr_cell(t, ind, igrid[o]);
+  int fa[7];
+  amr_getnborfather<NDIM>(t, c, ilevel + 1, fa);
+  bool ok = false;
+  double um[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) um[v] = uold[(size_t)v * t.ncell + c - 1];
+#pragma unroll
+  for (int d = 0; d < NDIM; d++) {
+    double ug[NV], ud[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      ug[v] = uold[(size_t)v * t.ncell + fa[2 * d + 1] - 1];
+      ud[v] = uold[(size_t)v * t.ncell + fa[2 * d + 2] - 1];
+    }
+    ok = ok || amr_hydro_refine<NDIM>(ug, um, ud, gamma, smallr, err_d, err_u, err_p, floor_d, floor_u, floor_p);
+  }
+  out[i] = ok ? 1 : 0;
+}
+
 // make_boundary_hydro (hydro/hydro_boundary.f90:5) on the mirrored arrays
 struct AmrBoundArgs {
   int n; const int* igrid; int inbor; int ind_ref[8]; double gs[3]; int kind; int ndim, nvar; double smallr;

@@ -2037,6 +2037,35 @@ int rgpu_level_totals(int nlevelmax, int* numbtot) {
   return RGPU_OK;
 }
 
+int rgpu_hydro_flag(int ilevel, const double err_grad[3], const double floor[3], int* flag1) {
+  if (!G.init || !G.amr) return fail(RGPU_EINVAL, "rgpu_hydro_flag needs AMR mode (rgpu_set_amr)");
+  AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
+  if (!err_grad || !floor || !flag1) return fail(RGPU_EINVAL, "null argument");
+  if (G.p.nvar != G.p.ndim + 2) return fail(RGPU_EUNSUPPORTED, "hydro_flag: nvar = ndim+2 only");
+  if (ilevel >= G.p.nlevelmax || A->nact == 0) return RGPU_OK;                                   // hydro_flag.f90:31-32
+  if (err_grad[0] == -1.0 && err_grad[1] == -1.0 && err_grad[2] == -1.0) return RGPU_OK;          // :56-66
+  const int T = T_(), n = A->nact * T;
+  int* d_out = nullptr;
+  CUDA_OK(cudaMalloc(&d_out, sizeof(int) * n));
+  const int nb = (n + 127) / 128;
+#define HF(ND) amr_hydro_flag_kernel<ND><<<nb, 128, 0, G.stream>>>(amr_tree(), G.d_uold, A->d_active, A->nact, ilevel, G.p.gamma, G.p.smallr, \
+                 err_grad[0], err_grad[1], err_grad[2], floor[0], floor[1], floor[2], d_out)
+  if (G.p.ndim == 1) HF(1); else if (G.p.ndim == 2) HF(2); else HF(3);
+#undef HF
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { cudaFree(d_out); return fail(RGPU_ECUDA, "hydro_flag launch: %s", cudaGetErrorString(e)); }
+  A->launches++;
+  std::vector<int> out(n), act(A->nact);
+  CUDA_OK(cudaMemcpyAsync(out.data(), d_out, sizeof(int) * n, cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaMemcpyAsync(act.data(), A->d_active, sizeof(int) * A->nact, cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  cudaFree(d_out);
+  for (int o = 0; o < A->nact; o++)
+    for (int ind = 0; ind < T; ind++)
+      if (out[(size_t)o * T + ind]) flag1[(size_t)G.ncoarse + (size_t)ind * G.ngridmax + act[o] - 1] = 1;   // flag1(ind_cell) = 1 :193
+  return RGPU_OK;
+}
+
 int rgpu_upload_fine(int ilevel) {
   if (!G.amr) return RGPU_OK;   // a dense (levelmin=levelmax) level has no split cells: upload_fine is a no-op
   AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;

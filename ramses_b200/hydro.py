@@ -239,6 +239,14 @@ class HydroGPU:
         _lib.check(self.L.rgpu_amr_steps(levelmin, _ip(ns), ncoarse_steps, _dp(dts)))
         return dts
 
+    def hydro_flag(self, ilevel, flag1, err_grad, floor=(1e-10, 1e-10, 1e-10)):
+        """hydro_flag(ilevel) (hydro/hydro_flag.f90): ORs the gradient criteria into the host array flag1(1:ncell) (int32);
+        err_grad = (err_grad_d, err_grad_u, err_grad_p), floor = (floor_d, floor_u, floor_p) of &REFINE_PARAMS."""
+        assert flag1.dtype == np.int32 and flag1.flags["C_CONTIGUOUS"]
+        e = (C.c_double * 3)(*err_grad)
+        f = (C.c_double * 3)(*floor)
+        _lib.check(self.L.rgpu_hydro_flag(ilevel, e, f, _ip(flag1)))
+
     def level_totals(self):
         """numbtot(1,1:nlevelmax): octs per level over all ranks (NCCL sum in AMR mode); stored in a.numbtot (dict by level)."""
         n = self.a.nlevelmax

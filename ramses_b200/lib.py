@@ -107,6 +107,7 @@ def load():
     L.rgpu_set_timing.argtypes = [C.c_int]
     L.rgpu_set_pipeline.argtypes = [C.c_int]
     L.rgpu_level_totals.argtypes = [C.c_int, ip]
+    L.rgpu_hydro_flag.argtypes = [C.c_int, dp, dp, ip]
     L.rgpu_selftest_div.argtypes = [C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
     _lib = L
     return L

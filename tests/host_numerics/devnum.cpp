@@ -221,6 +221,24 @@ void devnum_amr_getnborfather(int ndim, int ncoarse, int ngridmax, int nx, int n
   }
 }
 
+// amr_hydro_flag_kernel (hydro_flag + hydro_refine on the device) over the active octs of one level, thread by thread
+void devnum_amr_hydro_flag(int ndim, int ncoarse, int ngridmax, int nx, int ny, int nz, const int* son, const int* father,
+                           const int* nbor, const int* active, int nact, int ilevel, const double* uold, double gamma,
+                           double smallr, const double* err, const double* flo, int* out /*[nact][2^ndim]*/) {
+  AmrTree t;
+  t.son = son - 1; t.father = father - 1; t.nbor = nbor; t.ncoarse = ncoarse; t.ngridmax = ngridmax; t.nx = nx; t.ny = ny; t.nz = nz;
+  t.ncell = (long long)ncoarse + (long long)(1 << ndim) * ngridmax;
+  const int n = nact * (1 << ndim), nb = (n + 127) / 128;
+  rgpu_stub_sync_hook = nullptr;
+  for (int b = 0; b < nb; b++)
+    for (int th = 0; th < 128; th++) {
+      threadIdx = {(unsigned)th, 0, 0}; blockIdx = {(unsigned)b, 0, 0}; blockDim = {128, 1, 1}; gridDim = {(unsigned)nb, 1, 1};
+      if (ndim == 1) amr_hydro_flag_kernel<1>(t, uold, active, nact, ilevel, gamma, smallr, err[0], err[1], err[2], flo[0], flo[1], flo[2], out);
+      else if (ndim == 2) amr_hydro_flag_kernel<2>(t, uold, active, nact, ilevel, gamma, smallr, err[0], err[1], err[2], flo[0], flo[1], flo[2], out);
+      else amr_hydro_flag_kernel<3>(t, uold, active, nact, ilevel, gamma, smallr, err[0], err[1], err[2], flo[0], flo[1], flo[2], out);
+    }
+}
+
 // interpol_hydro for one variable: a [n][2*ndim+1] -> u2 [n][2^ndim]
 void devnum_amr_interpol(int ndim, int interpol_type, int n, const double* a, double* u2) {
   const int na = 2 * ndim + 1, T = 1 << ndim;

@@ -299,6 +299,52 @@ def test_amr_tree_walks_of_the_kernels_equal_oracle(orc, dev, ndim):
 
 
 @pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_amr_hydro_flag_kernel_equals_oracle(orc, dev, ndim):
+    """amr_hydro_flag_kernel (hydro_flag + hydro_refine, hydro/hydro_flag.f90, godunov_utils.f90:125-263) executed thread by thread
+    on the CPU == the oracle's hydro_flag on an adaptively refined mesh with a developed flow: every active cell of every level,
+    all three criteria (density, velocity, pressure)."""
+    from oracle.amr import FastAmrRun
+    if ndim == 1:
+        reg = [dict(type="square", x_center=0.25, length_x=0.5, d=1.0, p=1.0), dict(type="square", x_center=0.75, length_x=0.5, d=0.125, p=0.1)]
+        r = FastAmrRun(1, 3, 8, (1, 1, 0, 0, 0, 0), 1.0, nsubcycle=[1, 2], ngridmax=500, err_grad_d=0.05, err_grad_u=0.1, err_grad_p=0.05,
+                       interpol_type=2, regions=reg, tout=[0.05])
+    elif ndim == 2:
+        from conftest import IMPL, IMPL_BOUND
+        r = FastAmrRun(2, 4, 7, (1, 1, 1, 1, 0, 0), 1.0, nsubcycle=[2] * 10, nexpand=[2], ngridmax=20000, err_grad_d=0.05,
+                       err_grad_u=0.05, err_grad_p=0.05, interpol_type=2, regions=IMPL, tout=[0.0, 0.05], bound_regions=IMPL_BOUND)
+    else:
+        reg = [dict(type="square", x_center=0.5, y_center=0.5, z_center=0.5, length_x=10, length_y=10, length_z=10, exp_region=10, d=1.0, p=1e-5),
+               dict(type="point", x_center=0.5, y_center=0.5, z_center=0.5, p=0.4)]
+        r = FastAmrRun(3, 3, 5, (0,) * 6, 1.0, nsubcycle=[1, 2], ngridmax=4000, riemann="hllc", slope_type=1,
+                       err_grad_d=0.2, err_grad_u=0.3, err_grad_p=0.1, interpol_type=1, regions=reg, tout=[1e9])
+    r.run(max_coarse=3)
+    m = r.m
+    T = 1 << ndim
+    son = np.ascontiguousarray(r.son[1:], dtype=np.int32)
+    father = np.ascontiguousarray(r.father[1:], dtype=np.int32)
+    nbor = np.ascontiguousarray(r.nbor[:, 1:], dtype=np.int32)
+    geo = (ndim, r.ncoarse, r.ngridmax, m.nx, m.ny, m.nz)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    dev.devnum_amr_hydro_flag.argtypes = [C.c_int] * 6 + [ip, ip, ip, ip, C.c_int, C.c_int, dp, C.c_double, C.c_double, dp, dp, ip]
+    err = np.array([r.err_grad_d, r.err_grad_u, r.err_grad_p])
+    flo = np.array([r.floor_d, r.floor_u, r.floor_p])
+    nflag = 0
+    for l in range(r.levelmin, r.nlevelmax):
+        act = np.asarray(r.active[l], dtype=np.int32)
+        if not len(act):
+            continue
+        got = np.zeros((len(act), T), dtype=np.int32)
+        dev.devnum_amr_hydro_flag(*geo, orc.iptr(son), orc.iptr(father), orc.iptr(nbor), orc.iptr(act), len(act), l, orc.dptr(r.uold),
+                                  r.p.gamma, r.p.smallr, orc.dptr(err), orc.dptr(flo), orc.iptr(got))
+        r.flag1[:] = 0
+        r.hydro_flag(l)
+        ref = np.array([[r.flag1[r.cell(ind, int(g))] for ind in range(T)] for g in act], dtype=np.int32)
+        assert np.array_equal(got, ref), l
+        nflag += int(ref.sum())
+    assert nflag > 10
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
 @pytest.mark.parametrize("itype", [0, 1, 2, 3])
 def test_amr_prolongation_of_the_kernels_equals_oracle(orc, dev, ndim, itype):
     """amr_interpol_var (interpol_hydro on the device, one variable at a time) == orc_interpol_hydro, bit for bit"""

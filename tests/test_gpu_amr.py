@@ -441,3 +441,46 @@ def test_amr_steps_device_resident_dt_equals_host_driven():
     assert np.array_equal(res[0][0], res[1][0]), (res[0][0], res[1][0])
     assert np.array_equal(res[0][1], res[1][1])
     assert (res[0][0] > 0).all()
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_hydro_flag_on_device_equals_oracle(ndim):
+    """rgpu_hydro_flag (hydro/hydro_flag.f90 + hydro_refine on the device-resident state; only the 4-byte flags of the level travel)
+    == the oracle's hydro_flag on an adaptively refined mesh: flag1 of every active cell of every level below levelmax."""
+    from oracle.amr import AmrRun
+    from ramses_b200.hydro import HydroGPU
+    if ndim == 2:
+        regs = [dict(type="square", x_center=0.5, y_center=0.5, length_x=10, length_y=10, exp_region=10, d=1.0, p=0.1),
+                dict(type="square", x_center=0.3, y_center=0.4, length_x=0.3, length_y=0.25, exp_region=2, d=2.0, u=0.3, v=-0.2, p=1.0)]
+        r = AmrRun(2, 3, 5, (1, 1, 2, 2, 0, 0), 1.0, nsubcycle=[1, 2], ngridmax=20000, riemann="hllc", slope_type=2, err_grad_d=0.05,
+                   err_grad_u=0.05, err_grad_p=0.05, interpol_type=2, regions=regs, tout=[1e9], bound_regions=BOUND_2D_WALLS_X_OUTFLOW_Y)
+    else:
+        regs = [dict(type="square", x_center=0.5, y_center=0.5, z_center=0.5, length_x=10, length_y=10, length_z=10, exp_region=10, d=1.0, p=0.1),
+                dict(type="square", x_center=0.4, y_center=0.45, z_center=0.55, length_x=0.3, length_y=0.3, length_z=0.3, exp_region=2, d=1.5, u=0.2, p=2.0)]
+        r = AmrRun(3, 3, 4, (0,) * 6, 1.0, nsubcycle=[2, 2], ngridmax=20000, riemann="hllc", slope_type=1, err_grad_d=0.05,
+                   err_grad_u=0.05, err_grad_p=0.05, interpol_type=1, regions=regs, tout=[1e9])
+    r.flag_coarse(); r.init_refine(); r.init_refine_2()
+    for i in range(r.levelmin, r.nlevelmax + 1):
+        if i > r.levelmin:
+            r.make_boundary_hydro(i)
+        r.refine_fine(i)
+    for l in range(1, r.nlevelmax + 1):
+        r.make_boundary_hydro(l)
+    a = commons_from_run(r, "hllc", r.p.slope_type)
+    h = HydroGPU(a, amr_mode=True, interpol_type=1)
+    for l in range(1, r.nlevelmax + 1):
+        if len(a.active[l]):
+            h.bind_level(l)
+    h.upload_state(0)
+    nflag = 0
+    for l in range(r.levelmin, r.nlevelmax):
+        if not len(a.active[l]):
+            continue
+        flag1 = np.zeros(a.ncell, dtype=np.int32)
+        h.hydro_flag(l, flag1, (r.err_grad_d, r.err_grad_u, r.err_grad_p), (r.floor_d, r.floor_u, r.floor_p))
+        r.flag1[:] = 0
+        r.hydro_flag(l)
+        assert np.array_equal(flag1, np.asarray(r.flag1[1:], dtype=np.int32)), l
+        nflag += int(flag1.sum())
+    h.finalize()
+    assert nflag > 10
