@@ -373,69 +373,57 @@ __device__ __forceinline__ void athena_roe(const MPhys& M, real* ql, real* qr, r
          alf, lem61, lem71)
 #undef WAVE
   }
-  /* ---- right eigenvectors :1332-1388 ---- */
-  real rem[7][7];
-  rem[0][0] = alpha_f;
-  rem[0][1] = alpha_f * (vx - cfast);
-  rem[0][2] = alpha_f * vy + Qslow * beta_ystar;
-  rem[0][3] = alpha_f * vz + Qslow * beta_zstar;
-  rem[0][4] = alpha_f * (hp - vx * cfast) + Qslow * vbeta + Aspbb;
-  rem[0][5] = as_prime * beta_ystar;
-  rem[0][6] = as_prime * beta_zstar;
-  rem[1][0] = 0.; rem[1][1] = 0.;
-  rem[1][2] = -beta_z;
-  rem[1][3] = beta_y;
-  rem[1][4] = -(vy * beta_z - vz * beta_y);
-  rem[1][5] = -s * beta_z / rdroot;
-  rem[1][6] = s * beta_y / rdroot;
-  rem[2][0] = alpha_s;
-  rem[2][1] = alpha_s * (vx - cslow);
-  rem[2][2] = alpha_s * vy - Qfast * beta_ystar;
-  rem[2][3] = alpha_s * vz - Qfast * beta_zstar;
-  rem[2][4] = alpha_s * (hp - vx * cslow) - Qfast * vbeta - Afpbb;
-  rem[2][5] = -af_prime * beta_ystar;
-  rem[2][6] = -af_prime * beta_zstar;
-  rem[3][0] = 1.0; rem[3][1] = vx; rem[3][2] = vy; rem[3][3] = vz;
-  rem[3][4] = 0.5 * vsq + (gamma - 2.) * Xfac / (gamma - 1.);
-  rem[3][5] = 0.; rem[3][6] = 0.;
-  rem[4][0] = alpha_s;
-  rem[4][1] = alpha_s * (vx + cslow);
-  rem[4][2] = alpha_s * vy + Qfast * beta_ystar;
-  rem[4][3] = alpha_s * vz + Qfast * beta_zstar;
-  rem[4][4] = alpha_s * (hp + vx * cslow) + Qfast * vbeta - Afpbb;
-  rem[4][5] = rem[2][5];
-  rem[4][6] = rem[2][6];
-  rem[5][0] = 0.; rem[5][1] = 0.;
-  rem[5][2] = beta_z;
-  rem[5][3] = -beta_y;
-  rem[5][4] = -rem[1][4];
-  rem[5][5] = rem[1][5];
-  rem[5][6] = rem[1][6];
-  rem[6][0] = alpha_f;
-  rem[6][1] = alpha_f * (vx + cfast);
-  rem[6][2] = alpha_f * vy - Qslow * beta_ystar;
-  rem[6][3] = alpha_f * vz - Qslow * beta_zstar;
-  rem[6][4] = alpha_f * (hp + vx * cfast) - Qslow * vbeta + Aspbb;
-  rem[6][5] = rem[0][5];
-  rem[6][6] = rem[0][6];
+  /* ---- right eigenvectors :1332-1388, ROW BY ROW: row n is formed, used by the intermediate-state check (:996-1033) and by the
+   * flux assembly (:1046-1066), and dropped -- the 7x7 matrix never exists in registers.  The two accumulations keep the
+   * reference's order (n = 1..7 inside each sum); the flux is assembled speculatively and replaced by the LLF flux when one of
+   * the intermediate states is unphysical, exactly like the early return of the reference.  The physical fluxes fl, fr and the
+   * conservative states are recomputed here (find_mhd_flux is deterministic: same bits) instead of being held since the top. */
   eigenvalues(M, dl, vxl, pl, bx, byl, bzl, lambdal);
   eigenvalues(M, dr, vxr, pr, bx, byr, bzr, lambdar);
-  /* ---- intermediate states: fall back to LLF when one of them is unphysical :996-1033 ---- */
+#pragma unroll
+  for (int n = 0; n < 7; n += 2) {
+    real l1 = fmn(lambdal[n], lambda[n]);
+    real l2 = fmx(lambdar[n], lambda[n]);
+    if (l1 < zero && l2 > zero) lambda[n] = (lambda[n] * (l2 + l1) - two * l2 * l1) / (l2 - l1);
+  }
+  find_mhd_flux(M, ql, ul_, fl);
+  find_mhd_flux(M, qr, ur_, fr);
   bool llf = false;
   real dim = dl, mxm = mxl, mym = myl, mzm = mzl, eim = el, bym = byl, bzm = bzl;
-#pragma unroll
-  for (int n = 0; n < 7; n++) {
-    dim = dim + a[n] * rem[n][0];
-    mxm = mxm + a[n] * rem[n][1];
-    mym = mym + a[n] * rem[n][2];
-    mzm = mzm + a[n] * rem[n][3];
-    eim = eim + a[n] * rem[n][4];
-    bym = bym + a[n] * rem[n][5];
-    bzm = bzm + a[n] * rem[n][6];
-    real etm = eim - 0.5 * (mxm * mxm + mym * mym + mzm * mzm) / dim - 0.5 * (bx * bx + bym * bym + bzm * bzm);
-    if (dim <= zero || etm <= zero) llf = true;
+  real fluxd = fl[0] * zero_flux + fr[0] * zero_flux, fluxe = fl[1] * zero_flux + fr[1] * zero_flux;
+  real fluxmx = fl[2] * zero_flux + fr[2] * zero_flux, fluxmy = fl[4] * zero_flux + fr[4] * zero_flux;
+  real fluxby = fl[5] * zero_flux + fr[5] * zero_flux, fluxmz = fl[6] * zero_flux + fr[6] * zero_flux;
+  real fluxbz = fl[7] * zero_flux + fr[7] * zero_flux;
+  const real r15 = -s * beta_z / rdroot, r16 = s * beta_y / rdroot;          /* rem(2,6), rem(2,7) = rem(6,6), rem(6,7) */
+  const real r14 = -(vy * beta_z - vz * beta_y);                             /* rem(2,5) */
+  const real r05 = as_prime * beta_ystar, r06 = as_prime * beta_zstar;      /* rem(1,6:7) = rem(7,6:7) */
+  const real r25 = -af_prime * beta_ystar, r26 = -af_prime * beta_zstar;    /* rem(3,6:7) = rem(5,6:7) */
+#define ROW(n, R0, R1, R2, R3, R4, R5, R6)                                                                         \
+  {                                                                                                                \
+    const real c0 = (R0), c1 = (R1), c2 = (R2), c3 = (R3), c4 = (R4), c5 = (R5), c6 = (R6);                        \
+    dim = dim + a[n] * c0; mxm = mxm + a[n] * c1; mym = mym + a[n] * c2; mzm = mzm + a[n] * c3;                    \
+    eim = eim + a[n] * c4; bym = bym + a[n] * c5; bzm = bzm + a[n] * c6;                                           \
+    real etm = eim - 0.5 * (mxm * mxm + mym * mym + mzm * mzm) / dim - 0.5 * (bx * bx + bym * bym + bzm * bzm);    \
+    if (dim <= zero || etm <= zero) llf = true;                                                                    \
+    real coef = rabs(lambda[n]) * a[n];                                                                            \
+    fluxd = fluxd - coef * c0; fluxe = fluxe - coef * c4; fluxmx = fluxmx - coef * c1; fluxmy = fluxmy - coef * c2; \
+    fluxby = fluxby - coef * c5; fluxmz = fluxmz - coef * c3; fluxbz = fluxbz - coef * c6;                         \
   }
-  if (llf) {
+  ROW(0, alpha_f, alpha_f * (vx - cfast), alpha_f * vy + Qslow * beta_ystar, alpha_f * vz + Qslow * beta_zstar,
+      alpha_f * (hp - vx * cfast) + Qslow * vbeta + Aspbb, r05, r06)
+  ROW(1, real(0.), real(0.), -beta_z, beta_y, r14, r15, r16)
+  ROW(2, alpha_s, alpha_s * (vx - cslow), alpha_s * vy - Qfast * beta_ystar, alpha_s * vz - Qfast * beta_zstar,
+      alpha_s * (hp - vx * cslow) - Qfast * vbeta - Afpbb, r25, r26)
+  ROW(3, real(1.0), vx, vy, vz, 0.5 * vsq + (gamma - 2.) * Xfac / (gamma - 1.), real(0.), real(0.))
+  ROW(4, alpha_s, alpha_s * (vx + cslow), alpha_s * vy + Qfast * beta_ystar, alpha_s * vz + Qfast * beta_zstar,
+      alpha_s * (hp + vx * cslow) + Qfast * vbeta - Afpbb, r25, r26)
+  ROW(5, real(0.), real(0.), beta_z, -beta_y, -r14, r15, r16)
+  ROW(6, alpha_f, alpha_f * (vx + cfast), alpha_f * vy - Qslow * beta_ystar, alpha_f * vz - Qslow * beta_zstar,
+      alpha_f * (hp + vx * cfast) - Qslow * vbeta + Aspbb, r05, r06)
+#undef ROW
+  if (llf) {   /* intermediate state unphysical: LLF flux :1018-1031 (rare: states and fluxes are formed again, same bits) */
+    find_mhd_flux(M, ql, ul_, fl);
+    find_mhd_flux(M, qr, ur_, fr);
     real vl = find_speed_info(M, ql), vr = find_speed_info(M, qr);
     real vm = fmx(vl, vr);
 #pragma unroll
@@ -445,27 +433,6 @@ __device__ __forceinline__ void athena_roe(const MPhys& M, real* ql, real* qr, r
       fm[n] = fmean - vm * udiff;
     }
     return;
-  }
-#pragma unroll
-  for (int n = 0; n < 7; n += 2) {
-    real l1 = fmn(lambdal[n], lambda[n]);
-    real l2 = fmx(lambdar[n], lambda[n]);
-    if (l1 < zero && l2 > zero) lambda[n] = (lambda[n] * (l2 + l1) - two * l2 * l1) / (l2 - l1);
-  }
-#pragma unroll
-  for (int n = 0; n < 9; n++) { fl[n] = fl[n] * zero_flux; fr[n] = fr[n] * zero_flux; }
-  real fluxd = fl[0] + fr[0], fluxe = fl[1] + fr[1], fluxmx = fl[2] + fr[2], fluxmy = fl[4] + fr[4];
-  real fluxby = fl[5] + fr[5], fluxmz = fl[6] + fr[6], fluxbz = fl[7] + fr[7];
-#pragma unroll
-  for (int n = 0; n < 7; n++) {
-    real coef = rabs(lambda[n]) * a[n];
-    fluxd = fluxd - coef * rem[n][0];
-    fluxe = fluxe - coef * rem[n][4];
-    fluxmx = fluxmx - coef * rem[n][1];
-    fluxmy = fluxmy - coef * rem[n][2];
-    fluxby = fluxby - coef * rem[n][5];
-    fluxmz = fluxmz - coef * rem[n][3];
-    fluxbz = fluxbz - coef * rem[n][6];
   }
   fm[0] = half * fluxd; fm[1] = half * fluxe; fm[2] = half * fluxmx; fm[3] = zero; fm[4] = half * fluxmy;
   fm[5] = half * fluxby; fm[6] = half * fluxmz; fm[7] = half * fluxbz; fm[8] = zero;
