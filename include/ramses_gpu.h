@@ -132,7 +132,7 @@ int rgpu_godunov_fine(int ilevel, double dt, const double* uold, double* unew);
  * slab s | D2H of slab s-1; PCIe is full duplex) whenever the oct numbering of the level is spatially coherent enough that a
  * slab is a few contiguous igrid ranges (lattice / Morton / Hilbert order).  The reference's creation order (amr/refine_utils.f90:
  * 395-447) scatters a slab over the whole igrid window; the call then keeps the serial order.  rgpu_set_pipeline(0) forces the
- * serial order (measurements); RGPU_E2E_SLABS=<n> at bind time sets the number of slabs (default 32, <3 disables).            */
+ * serial order (measurements); RGPU_E2E_SLABS=<n> at bind time sets the number of slabs (default 64, <3 disables).            */
 int rgpu_set_pipeline(int enable);
 
 /* Page-lock / unlock a host array so the copies above run at full PCIe rate.   */

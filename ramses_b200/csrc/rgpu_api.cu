@@ -18,6 +18,7 @@
 #include "../../include/ramses_gpu.h"
 #include "sweep_dense.cuh"
 #include "sweep_dense3.cuh"
+#include "sweep_dense4.cuh"
 #include "amr_kernels.cuh"
 #include "mhd_dense.cuh"
 
@@ -30,7 +31,8 @@ DECL(2, 0) DECL(2, 1) DECL(2, 2) DECL(2, 3) DECL(2, 4)
 DECL(3, 0) DECL(3, 1) DECL(3, 2) DECL(3, 3) DECL(3, 4)
 #undef DECL
 // round-2 form of the 3-D sweep (sweep_dense3.cuh), instantiated in sweep3_inst_*.cu
-#define DECL(R) extern template cudaError_t launch_sweep3<R>(const SweepArgs&, int, cudaStream_t, int);
+#define DECL(R) extern template cudaError_t launch_sweep3<R>(const SweepArgs&, int, cudaStream_t, int); \
+                extern template cudaError_t launch_sweep4<R>(const SweepArgs&, int, cudaStream_t, int);
 DECL(0) DECL(1) DECL(2) DECL(3) DECL(4)
 #undef DECL
 template <int NDIM, int RIEMANN> cudaError_t launch_sweep_dense_amr(const SweepArgs& a, int nblocks, cudaStream_t st);
@@ -568,6 +570,15 @@ int launch_sweep(Level& L, int zlo = -1, int zhi = -1, int part = 0) {
       case RGPU_RIEMANN_ACOUSTIC: e = rgpu_fast_launch_sweep3_acoustic(&a, nblocks, G.stream, L.variant); break;
       case RGPU_RIEMANN_HLLC: e = rgpu_fast_launch_sweep3_hllc(&a, nblocks, G.stream, L.variant); break;
       default: e = rgpu_fast_launch_sweep3_hll(&a, nblocks, G.stream, L.variant); break;
+    }
+  }
+  else if (L.variant >= 40000) {   // one-barrier loop (sweep_dense4.cuh): tuning builds
+    switch (G.p.riemann) {
+      case RGPU_RIEMANN_LLF: e = launch_sweep4<RIEMANN_LLF>(a, nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_EXACT: e = launch_sweep4<RIEMANN_EXACT>(a, nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_ACOUSTIC: e = launch_sweep4<RIEMANN_ACOUSTIC>(a, nblocks, G.stream, L.variant); break;
+      case RGPU_RIEMANN_HLLC: e = launch_sweep4<RIEMANN_HLLC>(a, nblocks, G.stream, L.variant); break;
+      default: e = launch_sweep4<RIEMANN_HLL>(a, nblocks, G.stream, L.variant); break;
     }
   }
   else if (L.variant) {
@@ -1236,7 +1247,7 @@ static void plan_slabs(Level& L) {
   L.slabs.clear();
   if (G.p.ndim != 3 || G.p.mhd || G.amr) return;
   const DenseGeom& g = L.g;
-  int nsl = 32;
+  int nsl = 64;   // fill (3 slabs up before the first sweep) + drain (2 slabs down after the last) cost 5/nsl of one direction
   if (const char* e = getenv("RGPU_E2E_SLABS")) nsl = atoi(e);
   nsl = std::min(nsl, g.noz / 4);
   if (nsl < 3) return;
@@ -1377,7 +1388,7 @@ static int alloc_dense_store(Level& L, int ncpu, int nboundary, const int* bound
     const char* e = getenv("RGPU_SWEEP");
     if (e) L.variant = (strcmp(e, "old") == 0) ? 0 : atoi(e);
     if ((long long)G.nvs * T_() * nslot >= (1LL << 32)) L.variant = 0;   // sweep3_kernel addresses the state with 32-bit element indices
-    if (L.variant) { by = sweep3_by_of(L.variant); minb = (L.variant / 10) % 10; if (minb < 1 || minb == 9) minb = 1; }
+    if (L.variant) { by = sweep3_by_of(L.variant); minb = (L.variant / 10) % 10; if (minb < 1 || minb == 9 || L.variant >= 40000) minb = 1; }
   }
   L.by = by;
   const int txo = bx - 2, tyo = nd > 1 ? by - 2 : 1;

@@ -1,5 +1,6 @@
-// explicit instantiation of the round-2 3-D dense sweep (sweep_dense3.cuh), riemann = acoustic
-#include "sweep_dense3.cuh"
+// explicit instantiation of the round-2 3-D dense sweeps (sweep_dense3.cuh; sweep_dense4.cuh: tuning builds), riemann = acoustic
+#include "sweep_dense4.cuh"
 namespace rgpu {
 template cudaError_t launch_sweep3<RIEMANN_ACOUSTIC>(const SweepArgs&, int, cudaStream_t, int);
+template cudaError_t launch_sweep4<RIEMANN_ACOUSTIC>(const SweepArgs&, int, cudaStream_t, int);
 }

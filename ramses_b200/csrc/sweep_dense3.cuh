@@ -452,7 +452,7 @@ cudaError_t launch_sweep3_v(const SweepArgs& a, int nblocks, cudaStream_t st) {
 #ifndef SWEEP3_DEFAULT_VARIANT
 #define SWEEP3_DEFAULT_VARIANT 1292
 #endif
-constexpr int sweep3_by_of(int variant) { return variant / 100; }
+constexpr int sweep3_by_of(int variant) { return (variant % 10000) / 100; }   // 4BBOV: sweep4_kernel (sweep_dense4.cuh), O = order, V = solver form
 template <int RIEMANN, int SLOPE>
 cudaError_t launch_sweep3_s(const SweepArgs& a, int nblocks, cudaStream_t st, int variant) {
   switch (variant) {

@@ -6,6 +6,7 @@
 static double* rgpu_host_dyn_smem = nullptr;   // dynamic shared memory of an emulated launch (sweep_dense.cuh)
 #include "mhd_dense.cuh"    // the six MHD passes; pulls sweep_dense.cuh, mhd_device.cuh, hydro_device.cuh, real64.cuh
 #include "amr_kernels.cuh"  // the AMR oct-batch kernel and its __device__ tree-walk / prolongation helpers
+#include "sweep_dense4.cuh" // one-barrier form (includes sweep_dense3.cuh)
 #include "sweep_dense3.cuh" // round-2 form of the 3-D dense sweep + the lane-generic solvers (hydro_vec.cuh)
 
 #include <pthread.h>
@@ -491,7 +492,9 @@ int devnum_sweep3(int solver, int N, int nblocks, const double* uin, double* uou
   a.part = part; a.refined = nullptr;
 #define S3(RS, BY, VEC) emulate_launch(sweep3_kernel<RS, -1, BY, 1, VEC>, a, nblocks, 32, BY, Sweep3Smem<BY>::doubles)
 #define S3C(RS, BY) emulate_launch(sweep3_kernel<RS, -1, BY, 1, 2, true>, a, nblocks, 32, BY, Sweep3Smem<BY>::doubles)
-#define S3V(RS, BY) do { if (vec == 0) S3(RS, BY, 0); else if (vec == 1) S3(RS, BY, 1); else if (vec == 12) S3C(RS, BY); else S3(RS, BY, 2); } while (0)
+#define S4(RS, BY, ORD) emulate_launch(sweep4_kernel<RS, -1, BY, 2, ORD>, a, nblocks, 32, BY, Sweep4Smem<BY>::doubles)
+#define S3V(RS, BY) do { if (vec == 0) S3(RS, BY, 0); else if (vec == 1) S3(RS, BY, 1); else if (vec == 12) S3C(RS, BY); else if (vec == 40) S4(RS, BY, 0); \
+                         else if (vec == 41) S4(RS, BY, 1); else if (vec == 42) S4(RS, BY, 2); else S3(RS, BY, 2); } while (0)
 #define S3B(RS) do { if (by == 8) S3V(RS, 8); else if (by == 16) S3V(RS, 16); else S3V(RS, 12); } while (0)
   if (solver == RIEMANN_LLF) S3B(RIEMANN_LLF); else if (solver == RIEMANN_EXACT) S3B(RIEMANN_EXACT);
   else if (solver == RIEMANN_ACOUSTIC) S3B(RIEMANN_ACOUSTIC); else if (solver == RIEMANN_HLLC) S3B(RIEMANN_HLLC); else S3B(RIEMANN_HLL);
