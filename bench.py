@@ -131,7 +131,7 @@ def cpu_reference_run_amr(workload, steps, warmup):
             "seconds": el}, el / steps
 
 
-def amr_bench(args, w, rank, world, local_rank):
+def amr_bench(args, w, rank, world, local_rank, workload=None, embedded=False):
     """configs[3]: one GPU, AMR mode.  A `step` is one coarse step of amr_step (levelmin .. levelmax with sub-cycling 2 per
     level: 1+2+4+8 level steps), every per-level routine through the C-ABI in the reference's order (hydro.amr_step)."""
     import torch
@@ -195,7 +195,7 @@ def amr_bench(args, w, rank, world, local_rank):
     line = {"metric": "cell_updates_per_s", "value": updates * steps / wall, "unit": "cell-updates/s", "n_gpus": 1, "steps": steps,
             "warmup": warmup, "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "levelmin": levelmin, "levelmax": levelmax, "cells_per_level": ncell,
+            "config": {"workload": workload or args.workload, "levelmin": levelmin, "levelmax": levelmax, "cells_per_level": ncell,
                        "level_steps_per_coarse_step": {l: 2 ** (l - levelmin) for l in ncell}, "riemann": w["riemann"],
                        "mesh": "static nested refinement (ramses_b200.tree.build_nested_tree), periodic box",
                        "timing": "CUDA events on the launching stream around K coarse steps of rgpu_amr_steps (device-resident time steps)",
@@ -209,13 +209,15 @@ def amr_bench(args, w, rank, world, local_rank):
                          "kernel": "whole coarse step (amr_godfine_kernel + reflux + list passes)", "kernel_ms": wall / steps * 1e3,
                          "algorithmic_bytes_per_launch": BYTES_PER_CELL * updates},
             "cpu_baseline": None}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not embedded:
         try:
-            cb, _ = cpu_reference_run_amr(args.workload, 2, 1)
+            cb, _ = cpu_reference_run_amr(workload or args.workload, 2, 1)
             cb.pop("seconds", None)
             line["cpu_baseline"] = cb
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
+    if embedded:
+        return line
     print(json.dumps(line))
     return 0
 
@@ -690,6 +692,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--secondary", default="sedov3d_256_exact", help="second workload reported under 'secondary' at N=1 ('' = none)")
     ap.add_argument("--config5", default="tube_mhd_256_roe", help="MHD workload (BASELINE.json configs[4]) reported under 'config5' at N=1 ('' = none)")
+    ap.add_argument("--config4", default="sedov3d_amr_7_10_hllc", help="AMR workload (BASELINE.json configs[3]) reported under 'config4' at N=1 ('' = none)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast", action="store_true", help="skip the FAST-arithmetic re-run of the workload")
@@ -755,6 +758,12 @@ def main():
             line["config5"]["config"] = sec["config"]
         except Exception as e:
             line["config5"] = {"error": repr(e)}
+    if world == 1 and default_workload and args.config4:
+        try:      # BASELINE.json configs[3]: sedov3d AMR levelmin=7 levelmax=10 (one GPU), same process
+            sec = amr_bench(args, WORKLOADS[args.config4], rank, world, local_rank, workload=args.config4, embedded=True)
+            line["config4"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "roofline", "e2e", "gpu_launches", "config")}
+        except Exception as e:
+            line["config4"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

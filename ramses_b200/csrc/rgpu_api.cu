@@ -137,6 +137,7 @@ struct Level {
   double* d_out = nullptr;           // [5] dt, mass, etot, eint (, emag) of the last scan
   double* d_hist = nullptr; int hist_cap = 0;
   long long launches = 0;
+  double dt_by_value = 0.0, dt_stage = 0.0;   // rgpu_godunov_fine_dev: time step of the pending launch (hydro: passed by value)
   double last_sweep_ms = 0;
   double last_steps_ms = 0;
   double dx = 0;
@@ -536,6 +537,7 @@ int launch_sweep(Level& L, int zlo = -1, int zhi = -1, int part = 0) {
   a.g = L.g;
   a.P = G.phys;
   a.dt_dev = L.d_dt;
+  if (L.dt_by_value > 0.0) { a.dt_dev = nullptr; a.dt_val = L.dt_by_value; }
   a.dx = L.dx;
   a.inv_dx = 1.0 / L.dx;   // correctly rounded reciprocal (IEEE division on the host)
   int ex;
@@ -1749,10 +1751,19 @@ int rgpu_godunov_fine_dev(int ilevel, double dt) {
   }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (!(dt > 0)) return fail(RGPU_EINVAL, "dt=%g", dt);
-  CUDA_OK(cudaMemcpyAsync(L->d_dt, &dt, sizeof(double), cudaMemcpyHostToDevice, G.stream));
-  CUDA_OK(cudaStreamSynchronize(G.stream));
+  // dt travels by value in the launch arguments (hydro kernels): no copy, no host synchronisation per call.  The MHD passes
+  // read it from device memory: asynchronous copy from a buffer that outlives the call
+  if (G.p.mhd) {
+    L->dt_stage = dt;
+    CUDA_OK(cudaMemcpyAsync(L->d_dt, &L->dt_stage, sizeof(double), cudaMemcpyHostToDevice, G.stream));
+    CUDA_OK(cudaStreamSynchronize(G.stream));
+  } else {
+    L->dt_by_value = dt;
+  }
   // the fused kernel evaluates unew = uold + dF for the owned cells (== set_unew followed by the flux update)
-  rc = launch_sweep(*L); if (rc) return rc;
+  rc = launch_sweep(*L);
+  L->dt_by_value = 0.0;
+  if (rc) return rc;
   L->unew_valid = true;
   return RGPU_OK;
 }
