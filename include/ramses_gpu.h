@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RGPU_ABI_VERSION 3
+#define RGPU_ABI_VERSION 4
 
 enum {
   RGPU_OK = 0,
@@ -50,7 +50,9 @@ typedef struct rgpu_params {
   int niter_riemann;   /* Newton iterations of riemann='exact'                */
   int scheme;          /* RGPU_SCHEME_MUSCL only                              */
   int riemann;         /* RGPU_RIEMANN_*                                       */
-  int pressure_fix;    /* must be 0 (tmp/divu/enew path not built)            */
+  int pressure_fix;    /* amr_parameters.f90:197.  1: divu / enew ride along the sweep (godfine1 :737-903), add_pdv_source_terms and
+                        * the energy switch of set_uold (:203-227, with beta_fix below).  Oct-batch kernel only (rgpu_set_amr),
+                        * nvar = ndim+2, difmag = 0; divu and enew live on the device (rgpu_download_pressure_fix)            */
   double gamma, smallr, smallc, slope_theta, difmag, courant_factor;
                        /* difmag>0 (cmpdivu/consup, hydro/uplmde.f90:702,769): oct-batch kernel only, i.e. after rgpu_set_amr(1,..) */
   double boxlen;
@@ -67,6 +69,11 @@ typedef struct rgpu_params {
                         * contraction, reciprocal-multiply quotients, <= 2 ulp reciprocal / sqrt): within 1e-12 relative of
                         * the strict result on the conserved state after N steps (north_star's tolerance), ~15 % fewer FP64
                         * instructions.  Ignored (strict) by every other path.                                              */
+  int poisson;         /* amr_parameters.f90 `poisson`.  1: the acceleration f(1:ncell,1:ndim) of poisson_commons is an INPUT
+                        * (rgpu_upload_force; the Poisson solver is out of scope): gravity predictor of ctoprim (umuscl.f90:932-938),
+                        * gloc gather of godfine1 (:637-647), add_gravity_source_terms in set_uold (:237-289), gravity term of cmpdt
+                        * (godunov_utils.f90:99-111).  Oct-batch kernel only (rgpu_set_amr), nvar = ndim+2, difmag = 0              */
+  double beta_fix;     /* amr_parameters.f90:167 (pressure_fix truncation-error factor)                                          */
 } rgpu_params;
 /* `riemann` / `riemann2d` of the MHD build: iriemann, iriemann2d (hydro/read_hydro_params.f90:190-220) */
 enum { RGPU_MHD_LLF = 0, RGPU_MHD_ROE = 1, RGPU_MHD_HLL = 2, RGPU_MHD_HLLD = 3, RGPU_MHD_UPWIND = 4, RGPU_MHD_HYDRO = 5 };
@@ -151,6 +158,11 @@ int rgpu_set_uold(int ilevel);                             /* hydro/godunov_fine
  * MHD build (mhd/courant_fine.f90:1): sums must hold 4 values, sums[3] += magnetic E */
 int rgpu_courant_fine(int ilevel, double* dt_io, double sums[3]);
 int rgpu_make_boundary_hydro(int ilevel);                  /* hydro/hydro_boundary.f90:5       */
+/* imposed boundaries (bound_type = 3, boundary_type = 20+direction): var = boundary_var(ibound, 1:nvar), the conservative state
+ * hydro/read_hydro_params.f90:440-468 builds from d_bound, u_bound, ...; what the default boundana (hydro/boundana.f90) copies
+ * into every cell of the region (hydro_boundary.f90:229-252).  ibound is 1-based like the Fortran index; call once after
+ * rgpu_init for every imposed region.  A patched boundana (position-dependent inflow) is not supported.                      */
+int rgpu_set_boundary_var(int ibound, const double* var);
 int rgpu_make_virtual_fine(int ilevel);                    /* amr/virtual_boundaries.f90:373, all nvar at once */
 int rgpu_make_virtual_reverse(int ilevel);                 /* amr/virtual_boundaries.f90:693   */
 int rgpu_upload_fine(int ilevel);                          /* hydro/interpol_hydro.f90:5 (restriction of split cells) */
@@ -161,6 +173,13 @@ int rgpu_upload_fine(int ilevel);                          /* hydro/interpol_hyd
  * (-1 disables a test), floor = (floor_d, floor_u, floor_p).  flag1 is the host array flag1(1:ncell) of amr_commons: only the
  * 4-byte flags of the level travel, the state stays on the device for the flag_fine pass.                                  */
 int rgpu_hydro_flag(int ilevel, const double err_grad[3], const double floor[3], int* flag1);
+
+/* Source terms (AMR mode).  rgpu_upload_force: the host array f(1:ncell,1:ndim) of poisson_commons (amr/init_poisson.f90) after
+ * force_fine / gravana -- call it whenever the host recomputed the acceleration (rgpu_params.poisson = 1).
+ * rgpu_download_pressure_fix: the device-resident divu(1:ncell) / enew(1:ncell) of hydro_commons (hydro/init_hydro.f90:40-42)
+ * for diagnostics or a host-side pass that needs them (either pointer may be NULL).                                          */
+int rgpu_upload_force(const double* f);
+int rgpu_download_pressure_fix(double* divu, double* enew);
 
 /* ---- fused fast path --------------------------------------------------------------
  * nstep level steps of a levelmin=levelmax run in amr_step order

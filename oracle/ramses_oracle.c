@@ -1387,6 +1387,11 @@ void orc_condinit_regions(const orc_params* p, const orc_mesh* m, int ilevel, do
  * the caller; NULL switches the option off.  hexp = 0 (no cosmology).                                                       */
 static double *g_divu = NULL, *g_enew = NULL;
 static double g_beta_fix = 0.0, g_dt_level[64];
+/* poisson=.true.: the acceleration f(1:ncell,1:ndim) of poisson_commons (amr/init_poisson.f90), owned by the caller; NULL = off.
+ * The Poisson solver itself is out of scope: f is an input (an analytic field, gravity_type>0, or whatever the host computed). */
+static const double* g_force = NULL;
+void orc_set_gravity(const double* f) { g_force = f; }
+#define FO(ic, idim) g_force[(size_t)((idim)-1) * m->ncell + (ic)-1]
 void orc_set_pressure_fix(double* divu, double* enew, double beta_fix) { g_divu = divu; g_enew = enew; g_beta_fix = beta_fix; }
 
 void orc_set_unew(const orc_params* p, const orc_mesh* m, int ilevel, const double* uold, double* unew) {
@@ -1470,10 +1475,37 @@ static void add_pdv_source_terms(const orc_params* p, const orc_mesh* m, int ile
   }
 }
 
-/* set_uold hydro/godunov_fine.f90:135-232 (no gravity, no pressure_fix) */
+/* add_gravity_source_terms hydro/godunov_fine.f90:237-289: momentum and total energy of unew get the half-step kick
+ * f*dt/2 weighted by the OLD density (strict_equilibrium = 0)                                                          */
+static void add_gravity_source_terms(const orc_params* p, const orc_mesh* m, int ilevel, const double* uold, double* unew) {
+  const int ndim = p->ndim, twotondim = ipow2(ndim);
+  const double req = 0.0;
+  for (int ind = 0; ind < twotondim; ind++) {
+    const int iskip = m->ncoarse + ind * m->ngridmax;
+    for (int a = 0; a < m->nactive[ilevel]; a++) {
+      const int ic = m->active[ilevel][a] + iskip;
+      double d = FMAX(UN(ic, 1), p->smallr), u = 0, v = 0, w = 0;
+      if (ndim > 0) u = UN(ic, 2) / d;
+      if (ndim > 1) v = UN(ic, 3) / d;
+      if (ndim > 2) w = UN(ic, 4) / d;
+      double e_kin = 0.5 * d * (u * u + v * v + w * w);
+      const double e_prim = UN(ic, ndim + 2) - e_kin;
+      const double d_old = FMAX(UO(ic, 1), p->smallr);
+      const double fact = (d_old - req) / d * 0.5 * g_dt_level[ilevel];
+      if (ndim > 0) { u = u + FO(ic, 1) * fact; UN(ic, 2) = d * u; }
+      if (ndim > 1) { v = v + FO(ic, 2) * fact; UN(ic, 3) = d * v; }
+      if (ndim > 2) { w = w + FO(ic, 3) * fact; UN(ic, 4) = d * w; }
+      e_kin = 0.5 * d * (u * u + v * v + w * w);
+      UN(ic, ndim + 2) = e_prim + e_kin;
+    }
+  }
+}
+
+/* set_uold hydro/godunov_fine.f90:135-232 */
 void orc_set_uold(const orc_params* p, const orc_mesh* m, int ilevel, double* uold, const double* unew) {
   const int twotondim = ipow2(p->ndim), ndim = p->ndim, nvar = p->nvar;
   const double smallr = p->smallr;
+  if (g_force) add_gravity_source_terms(p, m, ilevel, uold, (double*)unew);   /* :159-161 */
   if (g_divu) add_pdv_source_terms(p, m, ilevel, uold);             /* :164-168 */
   for (int ind = 0; ind < twotondim; ind++) {
     int iskip = m->ncoarse + ind * m->ngridmax;
@@ -1704,11 +1736,14 @@ static void godfine1(const orc_params* p, const orc_mesh* m, orc_work* w, const 
                   for (int iv = 1; iv <= nvar; iv++) w->uloc[(iv - 1) * np + x] = u2[ind_son * nvar + iv - 1];
                   w->ok[x] = 0;               /* :664-666 */
                 }
+                if (g_force)                  /* :637-647: straight injection of the father's f for buffer cells */
+                  for (int idim = 1; idim <= ndim; idim++)
+                    w->gloc[(idim - 1) * np + x] = igrid_nbor > 0 ? FO(ic, idim) : FO(nfc[ind_father], idim);
               }
         }
   }
   /* fluxes :681 */
-  orc_unsplit(p, w, w->uloc, NULL, w->flux, w->tmp, dx, dx, dx, dt, ncache);
+  orc_unsplit(p, w, w->uloc, g_force ? w->gloc : NULL, w->flux, w->tmp, dx, dx, dx, dt, ncache);
   /* reset flux along direction at refined interface :720-747 */
   for (int idim = 0; idim < ndim; idim++) {
     int i0 = idim == 0, j0 = idim == 1, k0 = idim == 2;
@@ -1885,6 +1920,7 @@ double orc_courant_fine(const orc_params* p, const orc_mesh* m, int ilevel, doub
 #endif
   {
     double* uu = (double*)calloc((size_t)nv * nvar, 8);
+    double* gg = (double*)calloc((size_t)nv * 3, 8);
     int* ind_leaf = (int*)calloc(nv, sizeof(int));
 #ifdef _OPENMP
 #pragma omp for schedule(static)
@@ -1911,12 +1947,15 @@ double orc_courant_fine(const orc_params* p, const orc_mesh* m, int ilevel, doub
           }
         if (nleaf > 0) {
           double dt_lev;
-          orc_cmpdt(p, uu, NULL, dx, &dt_lev, nleaf);
+          if (g_force)                         /* courant_fine.f90:75-83 */
+            for (int idim = 1; idim <= ndim; idim++)
+              for (int i = 0; i < nleaf; i++) gg[i + (size_t)nv * (idim - 1)] = FO(ind_leaf[i], idim);
+          orc_cmpdt(p, uu, g_force ? gg : NULL, dx, &dt_lev, nleaf);
           dt_loc = FMIN(dt_loc, dt_lev);
         }
       }
     }
-    free(uu); free(ind_leaf);
+    free(uu); free(gg); free(ind_leaf);
   }
   if (sums) { sums[0] += mass_loc; sums[1] += ekin_loc; sums[2] += eint_loc; }
   return FMIN(dt_in, dt_loc);

@@ -137,6 +137,9 @@ void orc_mesh_set_list(orc_mesh*, int kind, int b, int ilevel, int n, const int*
 
 /* pressure_fix: caller-owned divu / enew cell arrays [ncell] (NULL = off) and beta_fix (amr_parameters.f90:167)      */
 void orc_set_pressure_fix(double* divu, double* enew, double beta_fix);
+/* poisson: caller-owned acceleration f[ndim][ncell] (NULL = off): gravity predictor in ctoprim (umuscl.f90:932-938), gloc gather
+ * in godfine1 (godunov_fine.f90:637-647), add_gravity_source_terms in set_uold (:237-289), gravity term of cmpdt            */
+void orc_set_gravity(const double* f);
 void orc_set_threads(int n);
 void orc_set_amr_threads(int n);   /* flux phase of orc_godunov_fine(nthreads=1); results do not depend on it */
 int orc_abi_version(void);

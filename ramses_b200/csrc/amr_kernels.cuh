@@ -231,6 +231,13 @@ struct AmrSweepArgs {
   int flux_only;
   const int* rflux_index; // list position -> oct index of rflux (NULL: identity)
   const double* dt_dev;   // device-resident dtnew(ilevel) (rgpu_amr_steps); NULL: use dt
+  // source terms (SRC instantiation): poisson -- f[ndim][ncell], the acceleration of poisson_commons (NULL: none);
+  // pressure_fix -- divu and enew are columns nvar and nvar+1 of unew (rgpu_api.cu), their face "fluxes" tmp(:,1:2) ride
+  // behind the nvar conservative fluxes in rflux, so the update, the coarse reflux and the reverse exchange treat them like
+  // two more variables (hydro/godunov_fine.f90:737-745,:773-786,:830-851,:882-903)
+  const double* force;
+  int pfix;
+  int nvr;                // entries per face in rflux: nvar (+2 with pressure_fix)
 };
 
 constexpr int AMR_TPO = 64;   // threads per oct
@@ -239,7 +246,9 @@ constexpr int AMR_OPB = 1;    // octs per block (26 KB of static shared memory p
 // DIF: artificial diffusion difmag>0 (cmpdivu hydro/uplmde.f90:702 + consup :769, called from unsplit hydro/umuscl.f90:160-168)
 // NPS: passive scalars (NVAR = NDIM+2+NPS): q = u/rho in ctoprim (umuscl.f90:948-961), advected in trace (:680-704), carried
 // through cmpflxm like the transverse velocities (:781-789,:835-842), every solver upwinds them with the mass flux
-template <int NDIM, int RIEMANN, bool DIF, int NPS = 0>
+// SRC: gravity predictor (gloc gather :637-647, ctoprim umuscl.f90:932-938) and/or pressure_fix (tmp1 = face velocity,
+// tmp2 = internal-energy flux, cmpflxm umuscl.f90:844-850) -- selected at run time by a.force / a.pfix
+template <int NDIM, int RIEMANN, bool DIF, int NPS = 0, bool SRC = false>
 __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const AmrSweepArgs a) {
   constexpr int NV = NDIM + 2 + NPS, NH = NDIM + 2, T = 1 << NDIM, TW = 2 * NDIM;
   constexpr int N3 = (NDIM == 1) ? 3 : (NDIM == 2 ? 9 : 27);
@@ -259,6 +268,8 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
     int nfc[27], gnb[27], ng[8];
     double uc[DIF ? NV : 1][DIF ? NP : 1];   // conservative patch (consup needs uin next to the primitives)
     double div[DIF ? 27 : 1];                // velocity divergence on the 3^ndim vertex lattice if1:if2 x jf1:jf2 x kf1:kf2
+    double g[SRC ? NDIM : 1][SRC ? NP : 1];  // gloc
+    double tmp[SRC ? NDIM : 1][2][SRC ? NF : 1];
   };
   __shared__ Sm sm_[AMR_OPB];
   const int grp = threadIdx.x / AMR_TPO, tl = threadIdx.x % AMR_TPO;
@@ -292,7 +303,21 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
 #pragma unroll
       for (int n = 0; n < NV; n++) s.q[n][pc] = UO(ic, n);
       s.ok[pc] = t.son[ic] > 0;
+      if (SRC) {
+#pragma unroll
+        for (int d = 0; d < NDIM; d++) s.g[SRC ? d : 0][SRC ? pc : 0] = a.force ? a.force[(size_t)d * NC + ic - 1] : 0.0;
+      }
     }
+    if (SRC)   // buffer cells: straight injection of the father cell's acceleration (:642-646)
+      for (int e = tl; e < N3 * T; e += AMR_TPO) {
+        const int jf = e / T, is = e % T;
+        if (s.gnb[jf] > 0) continue;
+        const int i1 = jf % 3, j1 = (jf / 3) % 3, k1 = jf / 9;
+        const int i3 = 1 + 2 * (i1 - 1) + (is & 1), j3 = HY ? 1 + 2 * (j1 - 1) + ((is >> 1) & 1) : 1, k3 = HZ ? 1 + 2 * (k1 - 1) + ((is >> 2) & 1) : 1;
+        const int pc = (i3 + 1) + 6 * ((HY ? j3 + 1 : 0) + PJ * (HZ ? k3 + 1 : 0));
+#pragma unroll
+        for (int d = 0; d < NDIM; d++) s.g[SRC ? d : 0][SRC ? pc : 0] = (a.force && s.nfc[jf] > 0) ? a.force[(size_t)d * NC + s.nfc[jf] - 1] : 0.0;
+      }
     // missing neighbour octs: interpol_hydro from the coarser level.  interpol_var 1, 2 and interpol_type 4 couple the
     // variables (internal energy / velocities): one thread per father cell interpolates the whole state
     if (a.interpol_var != 0 || a.interpol_type == 4) {
@@ -335,6 +360,7 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
     }
   }
   __syncthreads();
+  const double dt_ = a.dt_dev ? *a.dt_dev : a.dt;
   // ---- ctoprim on the whole patch (hydro/umuscl.f90:861) ----
   if (live)
     for (int pc = tl; pc < NP; pc += AMR_TPO) {
@@ -355,9 +381,16 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
       if (NDIM > 2) { q[3] = u[3] * oneoverrho; eken = eken + 0.5 * q[3] * q[3]; }
       const double eint = fmx(u[NDIM + 1] * oneoverrho - eken - 0.0, P.smalle);
       q[NDIM + 1] = (P.gamma - 1.0) * r * eint;
-      q[1] = q[1] + 0.0;
-      if (NDIM > 1) q[2] = q[2] + 0.0;
-      if (NDIM > 2) q[3] = q[3] + 0.0;
+      if (SRC) {   // gravity predictor :932-938
+        const double dtxhalf = dt_ * 0.5;
+        q[1] = q[1] + s.g[0][SRC ? pc : 0] * dtxhalf;
+        if (NDIM > 1) q[2] = q[2] + s.g[SRC ? 1 % NDIM : 0][SRC ? pc : 0] * dtxhalf;
+        if (NDIM > 2) q[3] = q[3] + s.g[SRC ? 2 % NDIM : 0][SRC ? pc : 0] * dtxhalf;
+      } else {
+        q[1] = q[1] + 0.0;
+        if (NDIM > 1) q[2] = q[2] + 0.0;
+        if (NDIM > 2) q[3] = q[3] + 0.0;
+      }
 #pragma unroll
       for (int n = NH; n < NV; n++) q[n] = u[n] * oneoverrho;
 #pragma unroll
@@ -388,7 +421,6 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
     }
   }
   // ---- uslope + trace on cells 0..3 (hydro/umuscl.f90:970, :176/:305/:483) ----
-  const double dt_ = a.dt_dev ? *a.dt_dev : a.dt;
   const double dtdx = dt_ / a.dx;
   if (live)
     for (int tc = tl; tc < NTR; tc += AMR_TPO) {
@@ -498,7 +530,8 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
       if (NDIM > 2) { ql[4 % NV] = s.qm[d][lt2 % NV][tL]; qr[4 % NV] = s.qp[d][lt2 % NV][tR]; }
 #pragma unroll
       for (int n = NH; n < NV; n++) { ql[n] = s.qm[d][n][tL]; qr[n] = s.qp[d][n][tR]; }
-      riemann<NDIM, RIEMANN, NPS>(ql, qr, fg, P);
+      double fe = 0.0;
+      riemann<NDIM, RIEMANN, NPS>(ql, qr, fg, P, (SRC && a.pfix) ? &fe : nullptr);
       fl[0] = fg[0]; fl[ln] = fg[1]; fl[NDIM + 1] = fg[2];
       if (NDIM > 1) fl[lt1 % NV] = fg[3];
       if (NDIM > 2) fl[lt2 % NV] = fg[4 % NV];
@@ -535,11 +568,20 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
         if (masked) v = 0.0;
         s.flux[d][n][f] = v;
       }
+      if (SRC && a.pfix) {   // tmp1 = half*(qleft(ln)+qright(ln)), tmp2 = fgdnv(nvar+1) (umuscl.f90:844-850), scaled :111-112
+        const double t1 = 0.5 * (ql[1] + qr[1]);
+        double v1 = a.dx_pow2 ? (t1 * dt_) * a.inv_dx : div_rn(t1 * dt_, a.dx, a.inv_dx);
+        double v2 = a.dx_pow2 ? (fe * dt_) * a.inv_dx : div_rn(fe * dt_, a.dx, a.inv_dx);
+        if (masked) { v1 = 0.0; v2 = 0.0; }
+        s.tmp[SRC ? d : 0][0][SRC ? f : 0] = v1;
+        s.tmp[SRC ? d : 0][1][SRC ? f : 0] = v2;
+      }
     }
   __syncthreads();
   // ---- conservative update of the oct's own cells (:751-792), x then y then z ----
   if (live) {
-    for (int e = tl; e < (a.flux_only ? 0 : T * NV); e += AMR_TPO) {
+    const int nvu = NV + ((SRC && a.pfix) ? 2 : 0);     // + divu, enew
+    for (int e = tl; e < (a.flux_only ? 0 : T * nvu); e += AMR_TPO) {
       const int is = e % T, n = e / T;
       const int c3[3] = {1 + (is & 1), 1 + ((is >> 1) & 1), 1 + ((is >> 2) & 1)};
       const int ic = amr_cell(t, is, igrid);
@@ -553,13 +595,15 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
           fr_ += (c3[dd] - 1 + (dd == d ? 1 : 0)) * mul;
           mul *= ext;
         }
-        u = u + (s.flux[d][n][fl_] - s.flux[d][n][fr_]);
+        if (SRC && n >= NV) u = u + (s.tmp[SRC ? d : 0][SRC ? n - NV : 0][SRC ? fl_ : 0] - s.tmp[SRC ? d : 0][SRC ? n - NV : 0][SRC ? fr_ : 0]);
+        else u = u + (s.flux[d][n < NV ? n : 0][fl_] - s.flux[d][n < NV ? n : 0][fr_]);
       }
       a.unew[(size_t)n * NC + ic - 1] = u;
     }
     // fluxes through the outer faces, for the coarse reflux pass: side = 2*d + (0 left | 1 right)
-    for (int e = tl; e < TW * NSF * NV; e += AMR_TPO) {
-      const int n = e % NV, fs = (e / NV) % NSF, side = e / (NV * NSF);
+    const int nvr = (SRC && a.pfix) ? NV + 2 : NV;
+    for (int e = tl; e < TW * NSF * nvr; e += AMR_TPO) {
+      const int n = e % nvr, fs = (e / nvr) % NSF, side = e / (nvr * NSF);
       const int d = side / 2, right = side % 2;
       int f = 0, mul = 1, rem = fs;
       for (int dd = 0; dd < NDIM; dd++) {
@@ -571,7 +615,8 @@ __global__ void __launch_bounds__(AMR_TPO* AMR_OPB) amr_godfine_kernel(const Amr
         mul *= ext;
       }
       const int ro = a.rflux_index ? a.rflux_index[io] : io;
-      a.rflux[(((size_t)ro * TW + side) * NSF + fs) * NV + n] = s.flux[d][n][f];
+      a.rflux[(((size_t)ro * TW + side) * NSF + fs) * nvr + n] =
+          (SRC && n >= NV) ? s.tmp[SRC ? d : 0][SRC ? n - NV : 0][SRC ? f : 0] : s.flux[d][n < NV ? n : 0][f];
     }
   }
 }
@@ -628,6 +673,110 @@ __global__ void amr_scalar_floor_kernel(const double* __restrict__ uold, double*
   } else if (dnew < smallr && dold > dnew) {
     for (int iv = nhydro; iv < nvar; iv++) unew[(size_t)iv * ncell + c] = uold[(size_t)iv * ncell + c] * smallr / fmx(dold, smallr);
   }
+}
+// ---- source terms of set_unew / set_uold (poisson, pressure_fix) on the mirrored arrays ---------------------------------------
+// set_unew, pressure_fix part (hydro/godunov_fine.f90:71-90): divu = 0, enew = internal energy of uold on the active cells
+__global__ void amr_pfix_init_kernel(const double* __restrict__ uold, double* __restrict__ divu, double* __restrict__ enew,
+                                     const int* __restrict__ igrid, int n, int ncoarse, int ngridmax, long long ncell, int T, int ndim,
+                                     double smallr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * T) return;
+  const int o = i % n, ind = i / n;
+  const size_t c = (size_t)ncoarse + (size_t)ind * ngridmax + igrid[o] - 1;
+  const double d = fmx(uold[c], smallr);
+  double u = 0, v = 0, w = 0;
+  if (ndim > 0) u = uold[(size_t)1 * ncell + c] / d;
+  if (ndim > 1) v = uold[(size_t)2 * ncell + c] / d;
+  if (ndim > 2) w = uold[(size_t)3 * ncell + c] / d;
+  const double e_kin = 0.5 * d * (u * u + v * v + w * w);
+  divu[c] = 0.0;
+  enew[c] = uold[(size_t)(ndim + 1) * ncell + c] - e_kin;
+}
+// add_gravity_source_terms (hydro/godunov_fine.f90:237-289)
+__global__ void amr_gravity_src_kernel(const double* __restrict__ uold, double* __restrict__ unew, const double* __restrict__ force,
+                                       const int* __restrict__ igrid, int n, int ncoarse, int ngridmax, long long ncell, int T, int ndim,
+                                       double smallr, double dt, const double* __restrict__ dt_dev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * T) return;
+  const int o = i % n, ind = i / n;
+  const size_t c = (size_t)ncoarse + (size_t)ind * ngridmax + igrid[o] - 1;
+  const double dtl = dt_dev ? *dt_dev : dt;
+  const double d = fmx(unew[c], smallr);
+  double u = 0, v = 0, w = 0;
+  if (ndim > 0) u = unew[(size_t)1 * ncell + c] / d;
+  if (ndim > 1) v = unew[(size_t)2 * ncell + c] / d;
+  if (ndim > 2) w = unew[(size_t)3 * ncell + c] / d;
+  double e_kin = 0.5 * d * (u * u + v * v + w * w);
+  const double e_prim = unew[(size_t)(ndim + 1) * ncell + c] - e_kin;
+  const double d_old = fmx(uold[c], smallr);
+  const double req = 0.0;                               // strict_equilibrium = 0
+  const double fact = (d_old - req) / d * 0.5 * dtl;
+  if (ndim > 0) { u = u + force[c] * fact; unew[(size_t)1 * ncell + c] = d * u; }
+  if (ndim > 1) { v = v + force[(size_t)1 * ncell + c] * fact; unew[(size_t)2 * ncell + c] = d * v; }
+  if (ndim > 2) { w = w + force[(size_t)2 * ncell + c] * fact; unew[(size_t)3 * ncell + c] = d * w; }
+  e_kin = 0.5 * d * (u * u + v * v + w * w);
+  unew[(size_t)(ndim + 1) * ncell + c] = e_prim + e_kin;
+}
+// add_pdv_source_terms, pressure_fix part (hydro/godunov_fine.f90:294-437): enew -= (gamma-1) e_old div(u) dt, the velocity
+// divergence from the face neighbours in uold (the coarser father cell, 1.5 dx away, where no neighbour oct exists)
+__global__ void amr_pdv_kernel(const AmrTree t, const double* __restrict__ uold, double* __restrict__ enew, const int* __restrict__ igrid,
+                               int n, int ndim, double gamma, double smallr, double dx_loc, double dt, const double* __restrict__ dt_dev) {
+  const int T = 1 << ndim;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * T) return;
+  const int o = i % n, ind = i / n;
+  const int ig = igrid[o];
+  const size_t NC = (size_t)t.ncell;
+  const double dtl = dt_dev ? *dt_dev : dt;
+  auto UO = [&](int icell, int iv) -> double { return uold[(size_t)iv * NC + icell - 1]; };
+  double divu_loc = 0.0;
+  for (int d = 0; d < ndim; d++) {
+    const int b = (ind >> d) & 1;                       // position of the cell inside its oct along d
+    const int other = ind ^ (1 << d);                   // jjj: the cell across the oct's mid-plane / in the neighbour oct
+    const int cl_nb = amr_nbor(t, ig, 2 * d + 1), cr_nb = amr_nbor(t, ig, 2 * d + 2);
+    // left neighbour: inside the oct for b = 1 (iii = 0), the left neighbour oct for b = 0
+    int c1, c2;
+    double dx_g, dx_d;
+    if (b == 1) { c1 = amr_cell(t, other, ig); dx_g = dx_loc; }
+    else { const int g1 = t.son[cl_nb]; c1 = g1 > 0 ? amr_cell(t, other, g1) : cl_nb; dx_g = g1 > 0 ? dx_loc : dx_loc * 1.5; }
+    if (b == 0) { c2 = amr_cell(t, other, ig); dx_d = dx_loc; }
+    else { const int g2 = t.son[cr_nb]; c2 = g2 > 0 ? amr_cell(t, other, g2) : cr_nb; dx_d = g2 > 0 ? dx_loc : dx_loc * 1.5; }
+    const double velg = UO(c1, d + 1) / fmx(UO(c1, 0), smallr);
+    const double veld = UO(c2, d + 1) / fmx(UO(c2, 0), smallr);
+    divu_loc = divu_loc + (veld - velg) / (dx_g + dx_d);
+  }
+  const int ic = amr_cell(t, ind, ig);
+  const double dd = fmx(UO(ic, 0), smallr);
+  double u = 0, v = 0, w = 0;
+  if (ndim > 0) u = UO(ic, 1) / dd;
+  if (ndim > 1) v = UO(ic, 2) / dd;
+  if (ndim > 2) w = UO(ic, 3) / dd;
+  const double eold = UO(ic, ndim + 1) - 0.5 * dd * (u * u + v * v + w * w);
+  enew[ic - 1] = enew[ic - 1] - (gamma - 1.0) * eold * divu_loc * dtl;
+}
+// set_uold, pressure_fix part (hydro/godunov_fine.f90:203-227), after uold <- unew: total energy = kinetic + enew where the
+// conservative internal energy is below the truncation error beta_fix*d*(|div u| dx)^2  (hexp = 0: no cosmology)
+__global__ void amr_pfix_switch_kernel(double* __restrict__ uold, const double* __restrict__ divu, const double* __restrict__ enew,
+                                       const int* __restrict__ igrid, int n, int ncoarse, int ngridmax, long long ncell, int T, int ndim,
+                                       double smallr, double beta_fix, double dx, double dt, const double* __restrict__ dt_dev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * T) return;
+  const int o = i % n, ind = i / n;
+  const size_t c = (size_t)ncoarse + (size_t)ind * ngridmax + igrid[o] - 1;
+  const double dtl = dt_dev ? *dt_dev : dt;
+  const double d = fmx(uold[c], smallr);
+  double u = 0, v = 0, w = 0;
+  if (ndim > 0) u = uold[(size_t)1 * ncell + c] / d;
+  if (ndim > 1) v = uold[(size_t)2 * ncell + c] / d;
+  if (ndim > 2) w = uold[(size_t)3 * ncell + c] / d;
+  const double e_kin = 0.5 * d * (u * u + v * v + w * w);
+  const double e_cons = uold[(size_t)(ndim + 1) * ncell + c] - e_kin;
+  const double e_prim = enew[c];
+  const double div = fabs(divu[c]) * dx / dtl;          // divu = -div.u*dt
+  const double hexp = 0.0;
+  const double mx = fmx(div, 3.0 * hexp * dx);
+  const double e_trunc = beta_fix * d * (mx * mx);
+  if (e_cons < e_trunc) uold[(size_t)(ndim + 1) * ncell + c] = e_prim + e_kin;
 }
 // ghost-oct exchange buffers on the mirrored arrays: all variables and all cells of the listed octs in one message
 // (make_virtual_fine_dp / make_virtual_reverse_dp, amr/virtual_boundaries.f90:373,693)
@@ -759,6 +908,7 @@ __global__ void amr_hydro_flag_kernel(const AmrTree t, const double* __restrict_
 // make_boundary_hydro (hydro/hydro_boundary.f90:5) on the mirrored arrays
 struct AmrBoundArgs {
   int n; const int* igrid; int inbor; int ind_ref[8]; double gs[3]; int kind; int ndim, nvar; double smallr;
+  double bvar[8];   // kind 2: boundary_var(ibound, :) (imposed boundary, default boundana)
 };
 __global__ void amr_boundary_kernel(double* __restrict__ u, const AmrTree t, const AmrBoundArgs b) {
   const int T = 1 << b.ndim;
@@ -766,9 +916,14 @@ __global__ void amr_boundary_kernel(double* __restrict__ u, const AmrTree t, con
   if (i >= b.n * T) return;
   const int o = i / T, ind = i % T;
   const int ig = b.igrid[o];
+  const size_t NC = (size_t)t.ncell;
+  if (b.kind == 2) {   // hydro_boundary.f90:229-252
+    const int ic2 = amr_cell(t, ind, ig);
+    for (int iv = 0; iv < b.nvar; iv++) u[(size_t)iv * NC + ic2 - 1] = b.bvar[iv];
+    return;
+  }
   const int gref = t.son[amr_nbor(t, ig, b.inbor)];
   const int ic = amr_cell(t, ind, ig), icr = amr_cell(t, b.ind_ref[ind] - 1, gref);
-  const size_t NC = (size_t)t.ncell;
   double uu[8];
   for (int iv = 0; iv < b.nvar; iv++) uu[iv] = u[(size_t)iv * NC + icr - 1];
   if (b.kind == 0) {
@@ -790,7 +945,7 @@ __global__ void amr_boundary_kernel(double* __restrict__ u, const AmrTree t, con
 // courant_fine over the LEAF cells of the listed octs (hydro/courant_fine.f90:61)
 template <int NDIM>
 __global__ void amr_courant_kernel(const double* __restrict__ u, const AmrTree t, const int* __restrict__ igrid, int n, Phys P, double dx,
-                                   double* __restrict__ part) {
+                                   double* __restrict__ part, const double* __restrict__ force = nullptr) {
   constexpr int NV = NDIM + 2, T = 1 << NDIM;
   __shared__ double red[4][32];
   double my_dt = 1e300, m0 = 0, m1 = 0, m2 = 0;
@@ -803,7 +958,13 @@ __global__ void amr_courant_kernel(const double* __restrict__ u, const AmrTree t
 #pragma unroll
     for (int k = 0; k < NV; k++) uu[k] = u[(size_t)k * NC + ic - 1];
     double ei;
-    const double dtc = cmpdt_cell<NDIM>(uu, dx, P, ei);
+    double dtc;
+    if (force) {   // gg = f (courant_fine.f90:75-83)
+      double gs = 0.0;
+#pragma unroll
+      for (int d = 0; d < NDIM; d++) gs = gs + fabs(force[(size_t)d * NC + ic - 1]);
+      dtc = cmpdt_cell<NDIM>(uu, dx, P, ei, gs);
+    } else dtc = cmpdt_cell<NDIM>(uu, dx, P, ei);
     my_dt = dtc < my_dt ? dtc : my_dt;
     m0 += uu[0]; m1 += uu[NDIM + 1]; m2 += ei;
   }
@@ -897,6 +1058,11 @@ __global__ void amr_fill_shell_coupled_kernel(const AmrTree t, const double* __r
 template <int NDIM, int RIEMANN>
 cudaError_t launch_amr_godfine(const AmrSweepArgs& a, cudaStream_t st) {
   const int nb = (a.nact + AMR_OPB - 1) / AMR_OPB;
+  if (a.force || a.pfix) {   // source terms: hydro variables only, no difmag (checked by rgpu_init)
+    if (a.nps != 0 || a.difmag > 0.0) return cudaErrorInvalidValue;
+    amr_godfine_kernel<NDIM, RIEMANN, false, 0, true><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);
+    return cudaGetLastError();
+  }
   if (a.nps == 0) {
     if (a.difmag > 0.0) amr_godfine_kernel<NDIM, RIEMANN, true><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);
     else amr_godfine_kernel<NDIM, RIEMANN, false><<<nb, AMR_TPO * AMR_OPB, 0, st>>>(a);

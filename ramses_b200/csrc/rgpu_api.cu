@@ -158,6 +158,7 @@ struct AmrLevel {
   double* d_part = nullptr; double* d_out = nullptr; double* d_dt = nullptr;
   long long launches = 0;
   double dx = 0;
+  double dt_last = 0;                 // dtnew(ilevel) of the last godunov_fine (set_uold's source terms need it)
   double last_steps_ms = 0;           // CUDA-event duration of the last rgpu_amr_steps call (recorded on the levelmin entry)
   bool dense_sweep = false;           // the level is a Cartesian box: godunov_fine runs the dense kernel (AMR variant)
   bool patch = false;                 // ... with a prolongated ghost shell and coarse refluxes (refined patch)
@@ -171,6 +172,10 @@ struct Context {
   bool amr = false;
   int* d_son = nullptr; int* d_son_base = nullptr; int* d_father = nullptr; int* d_nbor = nullptr;
   double* d_uold = nullptr; double* d_unew = nullptr;
+  double bvar[64][8] = {{0}};        // boundary_var(ibound, 1:nvar) of the imposed boundaries (rgpu_set_boundary_var)
+  bool bvar_set[64] = {false};
+  double* d_force = nullptr;         // poisson: f[ndim][ncell] (rgpu_upload_force)
+  int nvn = 0;                       // columns of d_unew: nvar, + divu and enew with pressure_fix
   long long ncell = 0;
   int interpol_type = 1, interpol_var = 0;
   AmrLevel alev[MAXLEVEL + 1];
@@ -279,8 +284,9 @@ __global__ void amr_refined_mask_kernel(const int* __restrict__ son0 /*son(1:nce
 // make_boundary_hydro (hydro/hydro_boundary.f90:5-269) for one boundary region.
 struct BoundArgs {
   int n; const int* slots; long long nslot; long long nbr_off; // slot offset of the reference oct (towards the domain)
-  int ind_ref[8]; double gs[3]; int kind;  // 0 wall (reflexive), 1 free (outflow)
+  int ind_ref[8]; double gs[3]; int kind;  // 0 wall (reflexive), 1 free (outflow), 2 imposed (boundary_var, default boundana)
   int ndim, nvar; double smallr;
+  double bvar[8];
 };
 __global__ void boundary_kernel(double* __restrict__ u, const BoundArgs b) {
   const int T = 1 << b.ndim;
@@ -289,6 +295,10 @@ __global__ void boundary_kernel(double* __restrict__ u, const BoundArgs b) {
   const int o = i / T, ind = i % T;
   const long long s = b.slots[o], sr = s + b.nbr_off;
   const int indr = b.ind_ref[ind] - 1;
+  if (b.kind == 2) {   // :229-252 with the default boundana (hydro/boundana.f90): u = boundary_var(ibound, :)
+    for (int iv = 0; iv < b.nvar; iv++) u[((size_t)iv * T + ind) * b.nslot + s] = b.bvar[iv];
+    return;
+  }
   double uu[8];
   for (int iv = 0; iv < b.nvar; iv++) uu[iv] = u[((size_t)iv * T + indr) * b.nslot + sr];
   if (b.kind == 0) {   // :141-157
@@ -637,10 +647,13 @@ int launch_boundaries(Level& L, double* u) {
   static const int ref_x[8] = {2, 1, 4, 3, 6, 5, 8, 7}, ref_y[8] = {3, 4, 1, 2, 7, 8, 5, 6}, ref_z[8] = {5, 6, 7, 8, 1, 2, 3, 4};
   static const int fre[6][8] = {{1, 1, 3, 3, 5, 5, 7, 7}, {2, 2, 4, 4, 6, 6, 8, 8}, {1, 2, 1, 2, 5, 6, 5, 6},
                                 {3, 4, 3, 4, 7, 8, 7, 8}, {1, 2, 3, 4, 1, 2, 3, 4}, {5, 6, 7, 8, 5, 6, 7, 8}};
+  int ibr = -1;
   for (auto& r : L.regions) {
+    ibr++;
     if (r.n == 0) continue;
     const int bt = r.type, dir = bt - 10 * (bt / 10);
-    if (bt / 10 > 1) return fail(RGPU_EUNSUPPORTED, "imposed boundary (boundana) type %d not supported", bt);
+    if (bt / 10 > 2 || (bt / 10 == 2 && G.p.mhd)) return fail(RGPU_EUNSUPPORTED, "boundary type %d not supported", bt);
+    if (bt / 10 == 2 && !G.bvar_set[ibr]) return fail(RGPU_EINVAL, "imposed boundary %d: call rgpu_set_boundary_var first", ibr + 1);
     const long long str[3] = {1, L.g.nox, (long long)L.g.nox * L.g.noy};
     const int d = (dir - 1) / 2;
     if (G.p.mhd) {   // mhd/hydro_boundary.f90:53-139
@@ -670,6 +683,7 @@ int launch_boundaries(Level& L, double* u) {
     if (bt >= 1 && bt <= 6) b.gs[d] = -1.0;
     b.kind = bt / 10;
     b.ndim = G.p.ndim; b.nvar = G.p.nvar; b.smallr = G.p.smallr;
+    for (int iv = 0; iv < 8; iv++) b.bvar[iv] = G.bvar[ibr][iv];
     const int nthr = r.n * T_();
     boundary_kernel<<<(nthr + 127) / 128, 128, 0, G.stream>>>(u, b);
     CUDA_OK(cudaGetLastError());
@@ -689,6 +703,9 @@ AmrTree amr_tree() {
   t.ncell = G.ncell;
   return t;
 }
+inline bool src_terms() { return G.p.poisson || G.p.pressure_fix; }
+inline double* d_divu() { return G.d_unew + (size_t)G.p.nvar * G.ncell; }
+inline double* d_enew() { return G.d_unew + (size_t)(G.p.nvar + 1) * G.ncell; }
 void free_amr_level(AmrLevel& A) {
   cudaFree(A.d_active); cudaFree(A.d_rflux); cudaFree(A.d_rcell); cudaFree(A.d_rstart); cudaFree(A.d_rsrc);
   cudaFree(A.d_part); cudaFree(A.d_out); cudaFree(A.d_dt);
@@ -712,7 +729,7 @@ int amr_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int nc
   AmrLevel& A = G.alev[ilevel];
   if (A.bound) free_amr_level(A);
   if (ncpu > 1 && ngrid_recv && igrid_recv && ngrid_emit && igrid_emit) {
-    const size_t per = (size_t)G.p.nvar * T_();
+    const size_t per = (size_t)G.nvn * T_();     // the reverse exchange of unew carries divu and enew too
     A.peers.resize(ncpu);
     for (int cpu = 0; cpu < ncpu; cpu++) {
       if (cpu == G.myid - 1) continue;
@@ -735,7 +752,8 @@ int amr_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int nc
   A.nact = ngrid_active;
   CUDA_OK(cudaMalloc(&A.d_active, sizeof(int) * std::max(1, ngrid_active)));
   if (ngrid_active > 0) CUDA_OK(cudaMemcpy(A.d_active, igrid_active, sizeof(int) * ngrid_active, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMalloc(&A.d_rflux, sizeof(double) * (size_t)std::max(1, ngrid_active) * TW * NSF * nvar));
+  CUDA_OK(cudaMalloc(&A.d_rflux, sizeof(double) * (size_t)std::max(1, ngrid_active) * TW * NSF * G.nvn));
+  (void)nvar;
   A.regions.resize(nboundary);
   for (int b = 0; b < nboundary; b++) {
     A.regions[b].type = boundary_type[b];
@@ -867,6 +885,7 @@ int amr_godunov_dense(AmrLevel& A, int ilevel, double dt, const double* dt_dev) 
 }
 
 int amr_godunov(AmrLevel& A, int ilevel, double dt, const double* dt_dev = nullptr) {
+  A.dt_last = dt;
   if (A.nact == 0) return RGPU_OK;
   if (A.dense_sweep) return amr_godunov_dense(A, ilevel, dt, dt_dev);
   AmrSweepArgs a{};
@@ -880,6 +899,7 @@ int amr_godunov(AmrLevel& A, int ilevel, double dt, const double* dt_dev = nullp
   a.interpol_type = G.interpol_type; a.interpol_var = G.interpol_var;
   a.difmag = G.p.difmag;
   a.nps = G.p.nvar - (G.p.ndim + 2);
+  a.force = G.p.poisson ? G.d_force : nullptr; a.pfix = G.p.pressure_fix ? 1 : 0; a.nvr = G.nvn;
   cudaError_t e;
   if (G.p.ndim == 1) e = dispatch_amr_nd<1>(G.p.riemann, a, G.stream);
   else if (G.p.ndim == 2) e = dispatch_amr_nd<2>(G.p.riemann, a, G.stream);
@@ -889,9 +909,9 @@ int amr_godunov(AmrLevel& A, int ilevel, double dt, const double* dt_dev = nullp
   if (A.nent > 0) {
     RefluxArgs r{};
     r.nent = A.nent; r.cell = A.d_rcell; r.start = A.d_rstart; r.src = A.d_rsrc; r.rflux = A.d_rflux; r.unew = G.d_unew;
-    r.ncell = G.ncell; r.nvar = G.p.nvar; r.nsides = 2 * G.p.ndim; r.nsf = 1 << (G.p.ndim - 1);
+    r.ncell = G.ncell; r.nvar = G.nvn; r.nsides = 2 * G.p.ndim; r.nsf = 1 << (G.p.ndim - 1);   // nvn: divu / enew reflux like variables
     r.oneontwotondim = 1.0 / (double)(1 << G.p.ndim);
-    const int n = A.nent * G.p.nvar;
+    const int n = A.nent * G.nvn;
     amr_reflux_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(r);
     CUDA_OK(cudaGetLastError());
     A.launches++;
@@ -911,7 +931,8 @@ int amr_copy(AmrLevel& A, const double* src, double* dst) {
 int amr_exchange(AmrLevel& A, double* u, bool reverse) {
   if (A.peers.empty()) return RGPU_OK;
   if (!G.comm) return fail(RGPU_EINVAL, "ghost exchange needs rgpu_comm_init");
-  const int T = T_(), nvar = G.p.nvar;
+  // reverse runs on unew: with pressure_fix its columns nvar, nvar+1 are divu and enew (amr_step.f90:397-404)
+  const int T = T_(), nvar = (reverse && u == G.d_unew) ? G.nvn : G.p.nvar;
   const long long per = (long long)T * nvar;
   for (auto& P : A.peers) {
     const int n = reverse ? P.nrecv : P.nemit;
@@ -939,15 +960,70 @@ int amr_exchange(AmrLevel& A, double* u, bool reverse) {
   }
   return RGPU_OK;
 }
-int amr_zero_ghost_unew(AmrLevel& A) {   // set_unew: unew = 0 in the reception octs (godunov_fine.f90:93-100)
-  const long long per = (long long)T_() * G.p.nvar;
+int amr_zero_ghost_unew(AmrLevel& A) {   // set_unew: unew (and divu, enew) = 0 in the reception octs (godunov_fine.f90:93-126)
+  const long long per = (long long)T_() * G.nvn;
   for (auto& P : A.peers)
     if (P.nrecv) {
-      amr_unpack_kernel<<<(unsigned)((P.nrecv * per + 255) / 256), 256, 0, G.stream>>>(G.d_unew, P.d_recv, P.nrecv, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar,
+      amr_unpack_kernel<<<(unsigned)((P.nrecv * per + 255) / 256), 256, 0, G.stream>>>(G.d_unew, P.d_recv, P.nrecv, G.ncoarse, G.ngridmax, G.ncell, T_(), G.nvn,
                                                                                    nullptr, 2);
       CUDA_OK(cudaGetLastError());
       A.launches++;
     }
+  return RGPU_OK;
+}
+
+// set_unew (hydro/godunov_fine.f90:40-130): unew = uold on the active octs (+ divu = 0, enew = e_int), 0 on the reception octs
+int amr_set_unew(AmrLevel& A) {
+  int rc = amr_copy(A, G.d_uold, G.d_unew); if (rc) return rc;
+  if (G.p.pressure_fix && A.nact > 0) {
+    const int n = A.nact * T_();
+    amr_pfix_init_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, d_divu(), d_enew(), A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(),
+                                                             G.p.ndim, G.p.smallr);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  return amr_zero_ghost_unew(A);
+}
+// set_uold (hydro/godunov_fine.f90:135-232): gravity and pdV sources on unew / enew, scalar floor fix, uold = unew, energy switch
+int amr_set_uold(AmrLevel& A, int ilevel, const double* dt_dev) {
+  (void)ilevel;
+  if (A.nact == 0) return RGPU_OK;
+  const int n = A.nact * T_(), nb = (n + 127) / 128;
+  if (src_terms() && !dt_dev && !(A.dt_last > 0)) return fail(RGPU_EINVAL, "set_uold with source terms before godunov_fine (dtnew(ilevel) unknown)");
+  if (G.p.poisson) {
+    amr_gravity_src_kernel<<<nb, 128, 0, G.stream>>>(G.d_uold, G.d_unew, G.d_force, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.ndim,
+                                                  G.p.smallr, A.dt_last, dt_dev);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  if (G.p.pressure_fix) {
+    amr_pdv_kernel<<<nb, 128, 0, G.stream>>>(amr_tree(), G.d_uold, d_enew(), A.d_active, A.nact, G.p.ndim, G.p.gamma, G.p.smallr, A.dx, A.dt_last, dt_dev);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  const int nps = G.p.nvar - (G.p.ndim + 2);
+  if (nps > 0) {   // passive-scalar fix for floored densities, before the copy (godunov_fine.f90:176-190)
+    amr_scalar_floor_kernel<<<nb, 128, 0, G.stream>>>(G.d_uold, G.d_unew, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(),
+                                                   G.p.ndim + 2, G.p.nvar, G.p.smallr);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  int rc = amr_copy(A, G.d_unew, G.d_uold); if (rc) return rc;
+  if (G.p.pressure_fix) {
+    amr_pfix_switch_kernel<<<nb, 128, 0, G.stream>>>(G.d_uold, d_divu(), d_enew(), A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.ndim,
+                                                  G.p.smallr, G.p.beta_fix, A.dx, A.dt_last, dt_dev);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  return RGPU_OK;
+}
+int amr_courant_launch(AmrLevel& A) {
+  const int nb = 148 * 8;
+  const double* f = G.p.poisson ? G.d_force : nullptr;
+  if (G.p.ndim == 1) amr_courant_kernel<1><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.phys, A.dx, A.d_part, f);
+  else if (G.p.ndim == 2) amr_courant_kernel<2><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.phys, A.dx, A.d_part, f);
+  else amr_courant_kernel<3><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.phys, A.dx, A.d_part, f);
+  CUDA_OK(cudaGetLastError());
   return RGPU_OK;
 }
 
@@ -956,10 +1032,13 @@ int amr_boundaries(AmrLevel& A) {
   static const int fre[6][8] = {{1, 1, 3, 3, 5, 5, 7, 7}, {2, 2, 4, 4, 6, 6, 8, 8}, {1, 2, 1, 2, 5, 6, 5, 6},
                                 {3, 4, 3, 4, 7, 8, 7, 8}, {1, 2, 3, 4, 1, 2, 3, 4}, {5, 6, 7, 8, 5, 6, 7, 8}};
   static const int inb[7] = {0, 2, 1, 4, 3, 6, 5};
+  int ibr = -1;
   for (auto& r : A.regions) {
+    ibr++;
     if (r.n == 0) continue;
     const int bt = r.type, dir = bt - 10 * (bt / 10);
-    if (bt / 10 > 1) return fail(RGPU_EUNSUPPORTED, "imposed boundary (boundana) type %d not supported", bt);
+    if (bt / 10 > 2) return fail(RGPU_EUNSUPPORTED, "boundary type %d not supported", bt);
+    if (bt / 10 == 2 && !G.bvar_set[ibr]) return fail(RGPU_EINVAL, "imposed boundary %d: call rgpu_set_boundary_var first", ibr + 1);
     AmrBoundArgs b{};
     b.n = r.n; b.igrid = r.d_igrid; b.inbor = inb[dir];
     const int d = (dir - 1) / 2;
@@ -968,6 +1047,7 @@ int amr_boundaries(AmrLevel& A) {
     b.gs[0] = b.gs[1] = b.gs[2] = 1.0;
     if (bt >= 1 && bt <= 6) b.gs[d] = -1.0;
     b.kind = bt / 10; b.ndim = G.p.ndim; b.nvar = G.p.nvar; b.smallr = G.p.smallr;
+    for (int iv = 0; iv < 8; iv++) b.bvar[iv] = G.bvar[ibr][iv];
     const int nthr = r.n * T_();
     amr_boundary_kernel<<<(nthr + 127) / 128, 128, 0, G.stream>>>(G.d_uold, amr_tree(), b);
     CUDA_OK(cudaGetLastError());
@@ -1029,7 +1109,12 @@ int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device) {
   if (p->riemann < 0 || p->riemann > 4) return fail(RGPU_EINVAL, "unknown Riemann solver %d", p->riemann);
   }
   if (p->scheme != RGPU_SCHEME_MUSCL) return fail(RGPU_EUNSUPPORTED, "scheme='plmde' not supported");
-  if (p->pressure_fix) return fail(RGPU_EUNSUPPORTED, "pressure_fix not supported");
+  if (p->pressure_fix || p->poisson) {   // built in the oct-batch kernel (rgpu_set_amr), hydro variables only
+    if (p->mhd) return fail(RGPU_EUNSUPPORTED, "MHD build: poisson / pressure_fix not supported");
+    if (p->nvar != p->ndim + 2 || p->difmag > 0.0)
+      return fail(RGPU_EUNSUPPORTED, "poisson / pressure_fix: built for nvar=ndim+2 and difmag=0 (no passive scalars, NENER)");
+    if (p->pressure_fix && !(p->beta_fix >= 0.0)) return fail(RGPU_EINVAL, "beta_fix=%g", p->beta_fix);
+  }
   if (p->difmag > 0.0 && p->mhd) return fail(RGPU_EUNSUPPORTED, "MHD build: difmag>0 not supported");
   if (p->difmag < 0.0) return fail(RGPU_EINVAL, "difmag=%g", p->difmag);
   {
@@ -1071,6 +1156,8 @@ int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device) {
   P.cfl_k = std::sqrt(1.0 + 2.0 * p->courant_factor * P.cfl_g) - 1.0;
   P.slope_type = p->slope_type; P.niter_riemann = p->niter_riemann;
   G.nvs = p->mhd ? p->nvar + 3 : p->nvar;
+  G.nvn = p->nvar + (p->pressure_fix ? 2 : 0);
+  for (int b = 0; b < 64; b++) G.bvar_set[b] = false;
   MPhys& M = G.mphys;
   M.gamma = p->gamma; M.smallr = p->smallr; M.smallc = p->smallc; M.slope_theta = p->slope_theta; M.courant_factor = p->courant_factor;
   M.smallp = p->smallr * (p->smallc * p->smallc) / p->gamma;
@@ -1084,7 +1171,7 @@ int rgpu_finalize(void) {
   cudaStreamSynchronize(G.stream);
   for (int l = 0; l <= MAXLEVEL; l++) if (G.lev[l].bound) free_level(G.lev[l]);
   for (int l = 0; l <= MAXLEVEL; l++) if (G.alev[l].bound) free_amr_level(G.alev[l]);
-  cudaFree(G.d_son_base); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew); cudaFree(G.d_dtn); cudaFree(G.d_dto); cudaFree(G.d_numb);
+  cudaFree(G.d_son_base); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew); cudaFree(G.d_force); G.d_force = nullptr; cudaFree(G.d_dtn); cudaFree(G.d_dto); cudaFree(G.d_numb);
   G.d_numb = nullptr; G.d_son_base = nullptr; G.d_son = G.d_father = G.d_nbor = nullptr; G.d_uold = G.d_unew = nullptr; G.d_dtn = G.d_dto = nullptr; G.ncell = 0; G.amr = false;
   if (G.comm_x) { ncclCommDestroy(G.comm_x); G.comm_x = nullptr; }
   if (G.comm) { ncclCommDestroy(G.comm); G.comm = nullptr; }
@@ -1117,8 +1204,8 @@ int rgpu_bind_tree(int ncoarse, int ngridmax, const int* son, const int* father,
   if (G.amr) {   // mirror the tree (read-only during a step; re-bind after every regrid)
     const long long ncell = (long long)ncoarse + (long long)T_() * ngridmax;
     if (ncell != G.ncell) {
-      cudaFree(G.d_son_base); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew);
-      G.d_son_base = nullptr; G.d_son = G.d_father = G.d_nbor = nullptr; G.d_uold = G.d_unew = nullptr;
+      cudaFree(G.d_son_base); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew); cudaFree(G.d_force);
+      G.d_son_base = nullptr; G.d_son = G.d_father = G.d_nbor = nullptr; G.d_uold = G.d_unew = nullptr; G.d_force = nullptr;
       // one leading zero: son(0) = 0 is what a missing neighbour father cell (nbor == 0 at an uncovered box corner) reads
       CUDA_OK(cudaMalloc(&G.d_son_base, sizeof(int) * (ncell + 1)));
       CUDA_OK(cudaMemset(G.d_son_base, 0, sizeof(int)));
@@ -1126,9 +1213,13 @@ int rgpu_bind_tree(int ncoarse, int ngridmax, const int* son, const int* father,
       CUDA_OK(cudaMalloc(&G.d_father, sizeof(int) * ngridmax));
       CUDA_OK(cudaMalloc(&G.d_nbor, sizeof(int) * (size_t)2 * G.p.ndim * ngridmax));
       CUDA_OK(cudaMalloc(&G.d_uold, sizeof(double) * G.p.nvar * ncell));
-      CUDA_OK(cudaMalloc(&G.d_unew, sizeof(double) * G.p.nvar * ncell));
+      CUDA_OK(cudaMalloc(&G.d_unew, sizeof(double) * G.nvn * ncell));
       CUDA_OK(cudaMemset(G.d_uold, 0, sizeof(double) * G.p.nvar * ncell));
-      CUDA_OK(cudaMemset(G.d_unew, 0, sizeof(double) * G.p.nvar * ncell));
+      CUDA_OK(cudaMemset(G.d_unew, 0, sizeof(double) * G.nvn * ncell));
+      if (G.p.poisson) {
+        CUDA_OK(cudaMalloc(&G.d_force, sizeof(double) * G.p.ndim * ncell));
+        CUDA_OK(cudaMemset(G.d_force, 0, sizeof(double) * G.p.ndim * ncell));
+      }
       G.ncell = ncell;
     }
     CUDA_OK(cudaMemcpy(G.d_son, son, sizeof(int) * ncell, cudaMemcpyHostToDevice));
@@ -1472,7 +1563,7 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
     const char* env = getenv("RGPU_AMR_DENSE");
     const char* envp = getenv("RGPU_AMR_PATCH");
     const bool eligible = !(env && atoi(env) == 0) && G.p.ndim == 3 && !G.p.mhd && !(G.p.difmag > 0.0) && G.p.nvar == G.p.ndim + 2 &&
-                          ngrid_active > 0;
+                          ngrid_active > 0 && !src_terms();   // gravity / pressure_fix: oct-batch kernel only
     const bool base = eligible && A.nent == 0 && ncpu == 1;   // multi-rank AMR keeps the oct-batch kernel (tested path)
     // a refined level whose octs form a Cartesian box (nested / zoom refinement): dense kernel on the box + a prolongated
     // ghost shell; the octs at its surface go through the oct-batch kernel once more for the refluxed faces only
@@ -1516,9 +1607,9 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
     }
     return RGPU_OK;
   }
-  if (G.p.difmag > 0.0 || (!G.p.mhd && G.p.nvar != G.p.ndim + 2))
-    return fail(RGPU_EUNSUPPORTED, "difmag>0 (cmpdivu/consup) and passive scalars (nvar>ndim+2) are built in the oct-batch kernel only: call "
-                                   "rgpu_set_amr(1, interpol_type, 0) after rgpu_init (works for levelmin=levelmax runs too)");
+  if (G.p.difmag > 0.0 || (!G.p.mhd && G.p.nvar != G.p.ndim + 2) || src_terms())
+    return fail(RGPU_EUNSUPPORTED, "difmag>0 (cmpdivu/consup), passive scalars (nvar>ndim+2), poisson and pressure_fix are built in the oct-batch "
+                                   "kernel only: call rgpu_set_amr(1, interpol_type, 0) after rgpu_init (works for levelmin=levelmax runs too)");
   Level& L = G.lev[ilevel];
   if (L.bound) free_level(L);
   {
@@ -1727,7 +1818,7 @@ int rgpu_download_state(int ilevel, double* uold) {
 }
 
 int rgpu_set_unew(int ilevel) {
-  if (G.amr) { AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc; rc = amr_copy(*A, G.d_uold, G.d_unew); if (rc) return rc; return amr_zero_ghost_unew(*A); }
+  if (G.amr) { AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc; return amr_set_unew(*A); }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   const size_t n = nplanes_() * (size_t)L->nslot;
   copy_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, G.stream>>>(L->d_u[L->cur], L->d_u[1 - L->cur], n);
@@ -1771,15 +1862,7 @@ int rgpu_godunov_fine_dev(int ilevel, double dt) {
 int rgpu_set_uold(int ilevel) {
   if (G.amr) {
     AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
-    const int nps = G.p.nvar - (G.p.ndim + 2);
-    if (nps > 0 && A->nact > 0) {   // passive-scalar fix for floored densities, before the copy (godunov_fine.f90:176-190)
-      const int n = A->nact * T_();
-      amr_scalar_floor_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_unew, A->d_active, A->nact, G.ncoarse, G.ngridmax, G.ncell, T_(),
-                                                                  G.p.ndim + 2, G.p.nvar, G.p.smallr);
-      CUDA_OK(cudaGetLastError());
-      A->launches++;
-    }
-    return amr_copy(*A, G.d_unew, G.d_uold);
+    return amr_set_uold(*A, ilevel, nullptr);
   }
   Level* L; int rc = check_level(ilevel, &L); if (rc) return rc;
   if (!L->unew_valid) return fail(RGPU_EINVAL, "set_uold before set_unew/godunov_fine");
@@ -1795,10 +1878,7 @@ int rgpu_courant_fine(int ilevel, double* dt_io, double sums[3]) {
     AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
     if (!dt_io) return fail(RGPU_EINVAL, "null dt");
     const int nb = 148 * 8;
-    if (G.p.ndim == 1) amr_courant_kernel<1><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A->d_active, A->nact, G.phys, A->dx, A->d_part);
-    else if (G.p.ndim == 2) amr_courant_kernel<2><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A->d_active, A->nact, G.phys, A->dx, A->d_part);
-    else amr_courant_kernel<3><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A->d_active, A->nact, G.phys, A->dx, A->d_part);
-    CUDA_OK(cudaGetLastError());
+    rc = amr_courant_launch(*A); if (rc) return rc;
     const double vol = std::pow(A->dx, G.p.ndim), dt0 = G.p.courant_factor * A->dx / G.p.smallc;
     courant_reduce_kernel<<<1, 1024, 0, G.stream>>>(A->d_part, nb, *dt_io, dt0, vol, A->d_out, A->d_dt, nullptr);
     CUDA_OK(cudaGetLastError());
@@ -1856,6 +1936,7 @@ int rgpu_godunov_fine(int ilevel, double dt, const double* uold, double* unew) {
     AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
     if (!uold || !unew) return fail(RGPU_EINVAL, "null state array");
     if (!(dt > 0)) return fail(RGPU_EINVAL, "dt=%g", dt);
+    if (G.p.pressure_fix) return fail(RGPU_EUNSUPPORTED, "pressure_fix: divu / enew live on the device; use the device-resident calls (rgpu_set_unew ... rgpu_set_uold)");
     const size_t bytes = sizeof(double) * G.p.nvar * G.ncell;
     CUDA_OK(cudaMemcpyAsync(G.d_uold, uold, bytes, cudaMemcpyHostToDevice, G.stream));
     CUDA_OK(cudaMemcpyAsync(G.d_unew, unew, bytes, cudaMemcpyHostToDevice, G.stream));
@@ -1978,9 +2059,7 @@ static int amr_step_dev(int l, int icount, int levelmin, const int* nsub) {
   op(DT_SAVE_OLD, l, 1.0, 1.0, icount);
   {   // courant_fine :326 (newdt_fine: dtnew = boxlen/smallc, then the CFL scan)
     const int nb = 148 * 8;
-    if (G.p.ndim == 1) amr_courant_kernel<1><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.phys, A.dx, A.d_part);
-    else if (G.p.ndim == 2) amr_courant_kernel<2><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.phys, A.dx, A.d_part);
-    else amr_courant_kernel<3><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.phys, A.dx, A.d_part);
+    rc = amr_courant_launch(A); if (rc) return rc;
     const double vol = std::pow(A.dx, G.p.ndim), dt0 = G.p.courant_factor * A.dx / G.p.smallc;
     courant_reduce_kernel<<<1, 1024, 0, G.stream>>>(A.d_part, nb, G.p.boxlen / G.p.smallc, dt0, vol, A.d_out, A.d_dt, nullptr);
     CUDA_OK(cudaGetLastError());
@@ -1988,8 +2067,7 @@ static int amr_step_dev(int l, int icount, int levelmin, const int* nsub) {
     A.launches += 2;
   }
   op(DT_AFTER_COURANT, l, l > levelmin ? (double)nsub[l - 2] : 1.0, 1.0, icount);
-  rc = amr_copy(A, G.d_uold, G.d_unew); if (rc) return rc;           // set_unew :333
-  rc = amr_zero_ghost_unew(A); if (rc) return rc;
+  rc = amr_set_unew(A); if (rc) return rc;                            // set_unew :333
   if (l < nlev && G.numbtot[l + 1] > 0) {                               // :345-361
     rc = amr_step_dev(l + 1, 1, levelmin, nsub); if (rc) return rc;
     if (nsub[l - 1] == 2) { rc = amr_step_dev(l + 1, 2, levelmin, nsub); if (rc) return rc; }
@@ -1998,16 +2076,7 @@ static int amr_step_dev(int l, int icount, int levelmin, const int* nsub) {
   }
   rc = amr_godunov(A, l, 0.0, G.d_dtn + l); if (rc) return rc;         // :388
   if (G.comm && G.nranks > 1) { rc = amr_exchange(A, G.d_unew, true); if (rc) return rc; }     // :397
-  {   // set_uold :423 (+ passive-scalar floor fix)
-    const int nps = G.p.nvar - (G.p.ndim + 2);
-    if (nps > 0 && A.nact > 0) {
-      const int n = A.nact * T_();
-      amr_scalar_floor_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_unew, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(),
-                                                                  G.p.ndim + 2, G.p.nvar, G.p.smallr);
-      A.launches++;
-    }
-    rc = amr_copy(A, G.d_unew, G.d_uold); if (rc) return rc;
-  }
+  rc = amr_set_uold(A, l, G.d_dtn + l); if (rc) return rc;            // set_uold :423 (source terms, scalar floor fix, energy switch)
   if (l < nlev && A.nact > 0) {                                         // upload_fine :441
     const int n = A.nact * T_();
     amr_upload_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_son - 1, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar, G.p.smallr, G.interpol_var, G.p.ndim);
@@ -2085,6 +2154,31 @@ int rgpu_hydro_flag(int ilevel, const double err_grad[3], const double floor[3],
   for (int o = 0; o < A->nact; o++)
     for (int ind = 0; ind < T; ind++)
       if (out[(size_t)o * T + ind]) flag1[(size_t)G.ncoarse + (size_t)ind * G.ngridmax + act[o] - 1] = 1;   // flag1(ind_cell) = 1 :193
+  return RGPU_OK;
+}
+
+int rgpu_set_boundary_var(int ibound, const double* var) {
+  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  if (ibound < 1 || ibound > 64 || !var) return fail(RGPU_EINVAL, "ibound=%d (1..64) / null var", ibound);
+  if (G.p.mhd) return fail(RGPU_EUNSUPPORTED, "MHD build: imposed boundaries not supported");
+  for (int iv = 0; iv < G.p.nvar && iv < 8; iv++) G.bvar[ibound - 1][iv] = var[iv];
+  G.bvar_set[ibound - 1] = true;
+  return RGPU_OK;
+}
+int rgpu_upload_force(const double* f) {
+  if (!G.init || !G.amr) return fail(RGPU_EINVAL, "rgpu_upload_force needs AMR mode (rgpu_set_amr)");
+  if (!G.p.poisson) return fail(RGPU_EINVAL, "rgpu_upload_force: rgpu_params.poisson is 0");
+  if (!G.d_force || !f) return fail(RGPU_EINVAL, "bind the tree first / null f");
+  CUDA_OK(cudaMemcpyAsync(G.d_force, f, sizeof(double) * G.p.ndim * G.ncell, cudaMemcpyHostToDevice, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  return RGPU_OK;
+}
+int rgpu_download_pressure_fix(double* divu, double* enew) {
+  if (!G.init || !G.amr || !G.p.pressure_fix) return fail(RGPU_EINVAL, "rgpu_download_pressure_fix needs AMR mode and rgpu_params.pressure_fix");
+  if (!G.d_unew) return fail(RGPU_EINVAL, "bind the tree first");
+  if (divu) CUDA_OK(cudaMemcpyAsync(divu, d_divu(), sizeof(double) * G.ncell, cudaMemcpyDeviceToHost, G.stream));
+  if (enew) CUDA_OK(cudaMemcpyAsync(enew, d_enew(), sizeof(double) * G.ncell, cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
   return RGPU_OK;
 }
 

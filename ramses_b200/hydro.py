@@ -96,6 +96,8 @@ def make_params(amr):
             raise ValueError("unknown Riemann solver")      # hydro/umuscl.f90:801-803
         p.riemann = _lib.RIEMANN[amr.riemann]
     p.pressure_fix = int(bool(amr.pressure_fix))
+    p.poisson = int(bool(getattr(amr, "poisson", False)))   # f(1:ncell,1:ndim) is an input: HydroGPU.upload_force
+    p.beta_fix = float(getattr(amr, "beta_fix", 0.0))
     p.fast = int(bool(getattr(amr, "fast", False)))        # rgpu_params.fast: FAST arithmetic of the 3-D dense sweep
     p.gamma, p.smallr, p.smallc = amr.gamma, amr.smallr, amr.smallc
     p.slope_theta, p.difmag, p.courant_factor, p.boxlen = amr.slope_theta, amr.difmag, amr.courant_factor, amr.boxlen
@@ -246,6 +248,23 @@ class HydroGPU:
         e = (C.c_double * 3)(*err_grad)
         f = (C.c_double * 3)(*floor)
         _lib.check(self.L.rgpu_hydro_flag(ilevel, e, f, _ip(flag1)))
+
+    def set_boundary_var(self, ibound, var):
+        """boundary_var(ibound, 1:nvar) of an imposed boundary region (bound_type=3); ibound is 1-based."""
+        v = np.ascontiguousarray(var, dtype=np.float64)
+        assert v.size >= self.a.nvar
+        _lib.check(self.L.rgpu_set_boundary_var(int(ibound), _dp(v)))
+
+    def upload_force(self, f):
+        """poisson_commons' f(1:ncell,1:ndim) (numpy [ndim][ncell], C order = the Fortran column-major array) -> device."""
+        assert f.dtype == np.float64 and f.flags["C_CONTIGUOUS"] and f.shape == (self.a.ndim, self.a.ncell)
+        _lib.check(self.L.rgpu_upload_force(_dp(f)))
+
+    def download_pressure_fix(self):
+        """divu(1:ncell), enew(1:ncell) of hydro_commons from the device (pressure_fix)."""
+        divu, enew = np.zeros(self.a.ncell), np.zeros(self.a.ncell)
+        _lib.check(self.L.rgpu_download_pressure_fix(_dp(divu), _dp(enew)))
+        return divu, enew
 
     def level_totals(self):
         """numbtot(1,1:nlevelmax): octs per level over all ranks (NCCL sum in AMR mode); stored in a.numbtot (dict by level)."""

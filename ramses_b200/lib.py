@@ -28,7 +28,8 @@ class Params(C.Structure):
                 ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
                 ("icoarse_min", C.c_int), ("icoarse_max", C.c_int), ("jcoarse_min", C.c_int), ("jcoarse_max", C.c_int),
                 ("kcoarse_min", C.c_int), ("kcoarse_max", C.c_int), ("nlevelmax", C.c_int),
-                ("mhd", C.c_int), ("riemann2d", C.c_int), ("slope_mag_type", C.c_int), ("fast", C.c_int)]
+                ("mhd", C.c_int), ("riemann2d", C.c_int), ("slope_mag_type", C.c_int), ("fast", C.c_int),
+                ("poisson", C.c_int), ("beta_fix", C.c_double)]
 
 
 class LevelInfo(C.Structure):
@@ -108,6 +109,9 @@ def load():
     L.rgpu_set_pipeline.argtypes = [C.c_int]
     L.rgpu_level_totals.argtypes = [C.c_int, ip]
     L.rgpu_hydro_flag.argtypes = [C.c_int, dp, dp, ip]
+    L.rgpu_upload_force.argtypes = [dp]
+    L.rgpu_set_boundary_var.argtypes = [C.c_int, dp]
+    L.rgpu_download_pressure_fix.argtypes = [dp, dp]
     L.rgpu_selftest_div.argtypes = [C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]
     _lib = L
     return L

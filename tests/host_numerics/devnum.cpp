@@ -289,6 +289,87 @@ void devnum_amr_godfine(int ndim, int solver, int ncoarse, int ngridmax, int nx,
 #undef RUN
 }
 
+// ---- poisson / pressure_fix (the SRC instantiation of the oct-batch kernel and the list passes of set_unew / set_uold) ------------
+// unew holds nvar+2 columns when pfix (divu, enew behind the state); rflux [nact][2*ndim][2^(ndim-1)][nvar(+2)]
+void devnum_amr_godfine_src(int ndim, int solver, int ncoarse, int ngridmax, int nx, int ny, int nz, const int* son, const int* father,
+                            const int* nbor, const int* active, int nact, int ilevel, const double* uold, double* unew, double* rflux,
+                            double dt, double dx, int interpol_type, int slope_type, double gamma, double smallr, double smallc,
+                            int niter, const double* force, int pfix) {
+  AmrSweepArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.t.son = son - 1; a.t.father = father - 1; a.t.nbor = nbor; a.t.ncoarse = ncoarse; a.t.ngridmax = ngridmax;
+  a.t.nx = nx; a.t.ny = ny; a.t.nz = nz; a.t.ncell = (long long)ncoarse + (long long)(1 << ndim) * ngridmax;
+  a.active = active; a.nact = nact; a.ilevel = ilevel; a.uold = uold; a.unew = unew; a.rflux = rflux;
+  a.P = make_phys(gamma, smallr, smallc, 1.5, 0.8, slope_type, niter);
+  a.dt = dt; a.dx = dx; a.inv_dx = 1.0 / dx;
+  int ex;
+  a.dx_pow2 = (std::frexp(dx, &ex) == 0.5) ? 1 : 0;
+  a.interpol_type = interpol_type; a.force = force; a.pfix = pfix; a.nvr = ndim + 2 + (pfix ? 2 : 0);
+  const int nb = (nact + AMR_OPB - 1) / AMR_OPB, nt = AMR_TPO * AMR_OPB;
+#define RUN(ND, RS) emulate_launch(amr_godfine_kernel<ND, RS, false, 0, true>, a, nb, nt)
+#define RUN_ND(ND)                                                                                              \
+  do {                                                                                                          \
+    if (solver == RIEMANN_LLF) RUN(ND, RIEMANN_LLF); else if (solver == RIEMANN_EXACT) RUN(ND, RIEMANN_EXACT);   \
+    else if (solver == RIEMANN_ACOUSTIC) RUN(ND, RIEMANN_ACOUSTIC); else if (solver == RIEMANN_HLLC) RUN(ND, RIEMANN_HLLC); \
+    else RUN(ND, RIEMANN_HLL);                                                                                  \
+  } while (0)
+  if (ndim == 1) RUN_ND(1); else if (ndim == 2) RUN_ND(2); else RUN_ND(3);
+#undef RUN_ND
+#undef RUN
+}
+
+// kind 0: amr_pfix_init_kernel, 1: amr_gravity_src_kernel, 2: amr_pdv_kernel, 3: amr_pfix_switch_kernel -- run thread after thread
+void devnum_amr_src_pass(int kind, int ndim, int ncoarse, int ngridmax, int nx, int ny, int nz, const int* son, const int* father,
+                         const int* nbor, const int* active, int nact, double* uold, double* unew, double* divu, double* enew,
+                         const double* force, double gamma, double smallr, double beta_fix, double dx, double dt) {
+  AmrTree t;
+  std::memset(&t, 0, sizeof t);
+  t.son = son - 1; t.father = father - 1; t.nbor = nbor; t.ncoarse = ncoarse; t.ngridmax = ngridmax; t.nx = nx; t.ny = ny; t.nz = nz;
+  t.ncell = (long long)ncoarse + (long long)(1 << ndim) * ngridmax;
+  const int T = 1 << ndim, n = nact * T, nb = (n + 127) / 128;
+  for (int b = 0; b < nb; b++)
+    for (int th = 0; th < 128; th++) {
+      threadIdx = {(unsigned)th, 0, 0}; blockIdx = {(unsigned)b, 0, 0}; blockDim = {128, 1, 1}; gridDim = {(unsigned)nb, 1, 1};
+      if (kind == 0) amr_pfix_init_kernel(uold, divu, enew, active, nact, ncoarse, ngridmax, t.ncell, T, ndim, smallr);
+      else if (kind == 1) amr_gravity_src_kernel(uold, unew, force, active, nact, ncoarse, ngridmax, t.ncell, T, ndim, smallr, dt, nullptr);
+      else if (kind == 2) amr_pdv_kernel(t, uold, enew, active, nact, ndim, gamma, smallr, dx, dt, nullptr);
+      else amr_pfix_switch_kernel(uold, divu, enew, active, nact, ncoarse, ngridmax, t.ncell, T, ndim, smallr, beta_fix, dx, dt, nullptr);
+    }
+}
+
+// n cells: dt = cmpdt_cell(u, dx, sum|g|)
+void devnum_cmpdt_grav(int ndim, int n, const double* u, const double* gsum, double dx, double* dt, double gamma, double smallr,
+                       double smallc, double cfl) {
+  const Phys P = make_phys(gamma, smallr, smallc, 1.5, cfl, 1, 10);
+  const int nv = ndim + 2;
+  for (int i = 0; i < n; i++) {
+    double ei;
+    if (ndim == 1) dt[i] = cmpdt_cell<1>(u + i * nv, dx, P, ei, gsum[i]);
+    else if (ndim == 2) dt[i] = cmpdt_cell<2>(u + i * nv, dx, P, ei, gsum[i]);
+    else dt[i] = cmpdt_cell<3>(u + i * nv, dx, P, ei, gsum[i]);
+  }
+}
+
+// n Riemann problems, internal-energy flux fgdnv(nvar+1) only (pressure_fix)
+void devnum_riemann_eflux(int ndim, int solver, int n, const double* ql, const double* qr, double* fe, double gamma, double smallr,
+                          double smallc, int niter) {
+  const Phys P = make_phys(gamma, smallr, smallc, 1.5, 0.8, 1, niter);
+  const int nv = ndim + 2;
+  for (int i = 0; i < n; i++) {
+    double fg[5];
+#define RE(ND)                                                                                                      \
+    switch (solver) {                                                                                               \
+      case RIEMANN_LLF: riemann<ND, RIEMANN_LLF>(ql + i * nv, qr + i * nv, fg, P, fe + i); break;                    \
+      case RIEMANN_EXACT: riemann<ND, RIEMANN_EXACT>(ql + i * nv, qr + i * nv, fg, P, fe + i); break;                \
+      case RIEMANN_ACOUSTIC: riemann<ND, RIEMANN_ACOUSTIC>(ql + i * nv, qr + i * nv, fg, P, fe + i); break;          \
+      case RIEMANN_HLLC: riemann<ND, RIEMANN_HLLC>(ql + i * nv, qr + i * nv, fg, P, fe + i); break;                  \
+      default: riemann<ND, RIEMANN_HLL>(ql + i * nv, qr + i * nv, fg, P, fe + i); break;                             \
+    }
+    if (ndim == 1) { RE(1) } else if (ndim == 2) { RE(2) } else { RE(3) }
+#undef RE
+  }
+}
+
 static MPhys make_mphys(double gamma, double smallr, double smallc) {
   MPhys M;
   M.gamma = gamma; M.smallr = smallr; M.smallc = smallc; M.slope_theta = 1.5; M.courant_factor = 0.8;

@@ -25,7 +25,7 @@ def test_library_exports_every_header_symbol():
     assert len(syms) >= 25
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/ramses_gpu.h but not exported"
-    assert L.rgpu_abi_version() == 3
+    assert L.rgpu_abi_version() == 4
     # every entry point documents the reference interface it replaces
     txt = open(lib.HEADER).read()
     assert len(re.findall(r"\.f90:\d+", txt)) >= 15

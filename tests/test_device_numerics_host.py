@@ -39,6 +39,11 @@ def dev():
     L.devnum_amr_interpol.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp]
     L.devnum_amr_godfine.argtypes = [C.c_int] * 7 + [ip, ip, ip, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_int,
                                      C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double]
+    L.devnum_amr_godfine_src.argtypes = [C.c_int] * 7 + [ip, ip, ip, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_int,
+                                         C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, dp, C.c_int]
+    L.devnum_amr_src_pass.argtypes = [C.c_int] * 7 + [ip, ip, ip, ip, C.c_int, dp, dp, dp, dp, dp] + [C.c_double] * 5
+    L.devnum_cmpdt_grav.argtypes = [C.c_int, C.c_int, dp, dp, C.c_double, dp, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.devnum_riemann_eflux.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int]
     return L
 
 
@@ -81,6 +86,44 @@ def test_hydro_riemann_device_formulas_equal_oracle(orc, dev, ndim, solver):
       fgf.ctypes.data_as(C.POINTER(C.c_double)), n)
     assert np.isfinite(fg).all()
     assert np.array_equal(fg, fgf[:, :nv])
+    # the internal-energy flux fgdnv(nvar+1) that only pressure_fix consumes (tmp2 of cmpflxm, umuscl.f90:848)
+    fe = np.zeros(n)
+    dev.devnum_riemann_eflux(ndim, sid, n, orc.dptr(ql), orc.dptr(qr), orc.dptr(fe), 1.4, 1e-10, 1e-10, 10)
+    assert np.isfinite(fe).all() and np.abs(fe).max() > 0
+    assert np.array_equal(fe, fgf[:, nv])
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_hydro_cmpdt_with_gravity_device_formula_equals_oracle(orc, dev, ndim):
+    """cmpdt with the gravity strength ratio (hydro/godunov_utils.f90:99-111): weak, comparable and dominant accelerations."""
+    n, nv = 5000, ndim + 2
+    rng = np.random.default_rng(55 + ndim)
+    u = np.zeros((n, nv))
+    u[:, 0] = 10.0 ** rng.uniform(-3, 2, n)
+    vel = rng.standard_normal((n, ndim)) * 3
+    u[:, 1:1 + ndim] = u[:, :1] * vel
+    u[:, nv - 1] = 10.0 ** rng.uniform(-4, 2, n) + 0.5 * u[:, 0] * (vel ** 2).sum(axis=1)
+    g = rng.standard_normal((n, ndim)) * 10.0 ** rng.uniform(-3, 5, (n, 1))
+    g[:50] = 0.0
+    dx = 1.0 / 128
+    gsum = np.zeros(n)
+    for d in range(ndim):                      # uu(k,1) = uu(k,1) + abs(gg(k,idim)) in this order
+        gsum = gsum + np.abs(g[:, d])
+    dt = np.zeros(n)
+    dev.devnum_cmpdt_grav(ndim, n, orc.dptr(np.ascontiguousarray(u)), orc.dptr(gsum), dx, orc.dptr(dt), 1.4, 1e-10, 1e-10, 0.8)
+    p = orc.make_params(ndim=ndim, nvector=1, courant_factor=0.8)
+    L = orc.lib()
+    L.orc_cmpdt.argtypes = [C.POINTER(orc.Params), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_int]
+    ref = np.zeros(n)
+    for i in range(n):
+        uu = u[i].copy()
+        gg = np.zeros(3)
+        gg[:ndim] = g[i]
+        o = C.c_double(0)
+        L.orc_cmpdt(C.byref(p), orc.dptr(uu), orc.dptr(gg), dx, C.byref(o), 1)
+        ref[i] = o.value
+    assert np.array_equal(dt, ref)
+    assert (dt[50:] < 0.999 * dt[:50].max()).any()
 
 
 @pytest.mark.parametrize("ndim", [1, 2, 3])
@@ -466,6 +509,111 @@ def test_amr_oct_batch_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, ndim, 
             moved = max(moved, float(np.abs(Uo[:, c] - r.uold.reshape(nvar, r.ncell)[:, c]).max()))
         nlev += 1
     assert nlev >= 3 and moved > 1e-6
+
+
+@pytest.mark.parametrize("ndim,solver,grav,pfix", [(1, "hllc", True, True), (2, "hllc", True, True), (2, "exact", False, True),
+                                                    (3, "hllc", True, True), (3, "llf", True, False), (3, "acoustic", False, True),
+                                                    (3, "hll", True, True)])
+def test_amr_source_terms_emulated_on_the_cpu_equal_oracle(orc, dev, ndim, solver, grav, pfix):
+    """poisson and pressure_fix on an adaptively refined mesh, one level step per level: the SRC instantiation of the oct-batch
+    kernel (gloc gather incl. the father's f in buffer cells, gravity predictor in ctoprim, tmp1/tmp2 -> divu/enew) run by the
+    emulated launch, and the list passes of set_unew / set_uold (divu/enew reset, add_gravity_source_terms,
+    add_pdv_source_terms, the energy switch) equal the oracle's set_unew -> godunov_fine -> set_uold bit for bit on the level's
+    own cells (state, divu and enew)."""
+    from oracle.amr import FastAmrRun
+    if ndim == 1:
+        reg = [dict(type="square", x_center=0.25, length_x=0.5, d=1.0, p=1.0), dict(type="square", x_center=0.75, length_x=0.5, d=0.125, p=0.1)]
+        r = FastAmrRun(1, 3, 8, (1, 1, 0, 0, 0, 0), 1.0, nsubcycle=[1, 2], ngridmax=500, riemann=solver, slope_type=2,
+                       err_grad_d=0.05, err_grad_p=0.05, interpol_type=2, regions=reg, tout=[1e9])
+        itype, st = 2, 2
+    elif ndim == 2:
+        from conftest import IMPL, IMPL_BOUND
+        r = FastAmrRun(2, 4, 6, (1, 1, 1, 1, 0, 0), 1.0, nsubcycle=[2] * 10, nexpand=[2], ngridmax=20000, riemann=solver, slope_type=2,
+                       err_grad_d=0.05, err_grad_u=0.05, err_grad_p=0.05, interpol_type=2, regions=IMPL, tout=[0.0, 1e9],
+                       bound_regions=IMPL_BOUND)
+        itype, st = 2, 2
+    else:
+        reg = [dict(type="square", x_center=0.5, y_center=0.5, z_center=0.5, length_x=10, length_y=10, length_z=10, exp_region=10, d=1.0, p=1e-5),
+               dict(type="point", x_center=0.5, y_center=0.5, z_center=0.5, p=0.4)]
+        r = FastAmrRun(3, 3, 5, (0,) * 6, 1.0, nsubcycle=[1, 2], ngridmax=4000, riemann=solver, slope_type=1, err_grad_p=0.1,
+                       interpol_type=1, regions=reg, tout=[1e9])
+        itype, st = 1, 1
+    r.run(max_coarse=3)
+    m = r.m
+    T, nvar, nc = 1 << ndim, ndim + 2, r.ncell
+    son = np.ascontiguousarray(r.son[1:], dtype=np.int32)
+    father = np.ascontiguousarray(r.father[1:], dtype=np.int32)
+    nbor = np.ascontiguousarray(r.nbor[:, 1:], dtype=np.int32)
+    sid = {"llf": 0, "exact": 1, "acoustic": 2, "hllc": 3, "hll": 4}[solver]
+    L = orc.lib()
+    L.orc_set_pressure_fix.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double]
+    L.orc_set_gravity.argtypes = [C.POINTER(C.c_double)]
+    rng = np.random.default_rng(7 * ndim + sid)
+    # an arbitrary acceleration field (f is an input of the path): a uniform pull plus cell-to-cell structure, strong enough to matter
+    force = np.ascontiguousarray((np.array([0.7, -0.4, 0.3])[:ndim, None] + 0.3 * rng.standard_normal((ndim, nc))) * 5.0)
+    beta_fix = 0.5
+    nlev, switched, gmoved, dmax = 0, 0, 0.0, 0.0
+    try:
+        for l in range(r.levelmin, r.nlevelmax + 1):
+            act = np.ascontiguousarray(r.active[l], dtype=np.int32)
+            if len(act) == 0:
+                continue
+            dt = 0.4 * r.dtnew[r.levelmin] / 2 ** (l - r.levelmin) if r.dtnew[r.levelmin] > 0 else 1e-4
+            dx = 0.5 ** l * r.p.boxlen / (m.icoarse_max - m.icoarse_min + 1)
+            cells = np.concatenate([r.ncoarse + ind * r.ngridmax + act.astype(np.int64) - 1 for ind in range(T)])
+            # ---- oracle: set_unew -> godunov_fine -> set_uold of this level with the options on
+            uold_o, unew_o = r.uold.copy(), np.zeros_like(r.uold)
+            divu_o, enew_o = np.full(nc, 7.0), np.full(nc, -3.0)          # garbage that set_unew must overwrite on the level
+            L.orc_set_pressure_fix(orc.dptr(divu_o) if pfix else None, orc.dptr(enew_o) if pfix else None, beta_fix)
+            L.orc_set_gravity(orc.dptr(force) if grav else None)
+            L.orc_set_unew(C.byref(r.p), r.mp, l, orc.dptr(uold_o), orc.dptr(unew_o))
+            L.orc_godunov_fine(C.byref(r.p), r.mp, l, dt, orc.dptr(uold_o), orc.dptr(unew_o), 1)
+            divu_mid, enew_mid = divu_o.copy(), enew_o.copy()
+            L.orc_set_uold(C.byref(r.p), r.mp, l, orc.dptr(uold_o), orc.dptr(unew_o))
+            L.orc_set_pressure_fix(None, None, 0.0)
+            L.orc_set_gravity(None)
+            # ---- device code on the host: unew holds nvar (+2) columns
+            ncol = nvar + (2 if pfix else 0)
+            uold_k = r.uold.copy()
+            unew_k = np.zeros(ncol * nc)
+            unew_k[: nvar * nc].reshape(nvar, nc)[:, cells] = r.uold.reshape(nvar, nc)[:, cells]                 # set_unew copy
+            divu_k = unew_k[nvar * nc: (nvar + 1) * nc] if pfix else np.zeros(nc)
+            enew_k = unew_k[(nvar + 1) * nc:] if pfix else np.zeros(nc)
+            if pfix:
+                divu_k[:] = 7.0; enew_k[:] = -3.0
+            args = (ndim, r.ncoarse, r.ngridmax, m.nx, m.ny, m.nz, orc.iptr(son), orc.iptr(father), orc.iptr(nbor), orc.iptr(act), len(act))
+            tail = (orc.dptr(force), 1.4, 1e-10, beta_fix, dx, dt)
+            if pfix:
+                dev.devnum_amr_src_pass(0, *args, orc.dptr(uold_k), orc.dptr(unew_k), orc.dptr(divu_k), orc.dptr(enew_k), *tail)
+            rflux = np.zeros(len(act) * 2 * ndim * (T // 2) * ncol)
+            dev.devnum_amr_godfine_src(ndim, sid, r.ncoarse, r.ngridmax, m.nx, m.ny, m.nz, orc.iptr(son), orc.iptr(father), orc.iptr(nbor),
+                                       orc.iptr(act), len(act), l, orc.dptr(uold_k), orc.dptr(unew_k), orc.dptr(rflux), dt, dx, itype, st,
+                                       1.4, 1e-10, 1e-10, 10, orc.dptr(force) if grav else None, 1 if pfix else 0)
+            if pfix:   # after the sweep, before the sources: divu / enew of the level's cells
+                assert np.array_equal(divu_k[cells], divu_mid[cells]), l
+                assert np.array_equal(enew_k[cells], enew_mid[cells]), l
+                dmax = max(dmax, float(np.abs(divu_mid[cells]).max()))
+            if grav:
+                dev.devnum_amr_src_pass(1, *args, orc.dptr(uold_k), orc.dptr(unew_k), orc.dptr(divu_k), orc.dptr(enew_k), *tail)
+            if pfix:
+                dev.devnum_amr_src_pass(2, *args, orc.dptr(uold_k), orc.dptr(unew_k), orc.dptr(divu_k), orc.dptr(enew_k), *tail)
+            before = uold_k.reshape(nvar, nc)[:, cells].copy()
+            uold_k.reshape(nvar, nc)[:, cells] = unew_k[: nvar * nc].reshape(nvar, nc)[:, cells]                 # uold <- unew
+            if pfix:
+                pre = uold_k.reshape(nvar, nc)[nvar - 1, cells].copy()
+                dev.devnum_amr_src_pass(3, *args, orc.dptr(uold_k), orc.dptr(unew_k), orc.dptr(divu_k), orc.dptr(enew_k), *tail)
+                switched += int((uold_k.reshape(nvar, nc)[nvar - 1, cells] != pre).sum())
+                assert np.array_equal(enew_k[cells], enew_o[cells]), l
+            got, ref = uold_k.reshape(nvar, nc)[:, cells], uold_o.reshape(nvar, nc)[:, cells]
+            assert np.array_equal(got, ref), (l, np.abs(got - ref).max())
+            gmoved = max(gmoved, float(np.abs(ref - before).max()))
+            nlev += 1
+    finally:
+        L.orc_set_pressure_fix(None, None, 0.0)
+        L.orc_set_gravity(None)
+    assert nlev >= 3 and gmoved > 1e-6 and (dmax > 0 or not pfix)
+    if pfix and ndim == 3:
+        assert switched > 0          # the cold Sedov background (p = 1e-5) does trip the energy switch
 
 
 def _to_slots(dense, N):

@@ -69,7 +69,8 @@ BOUND_2D_WALLS_X_OUTFLOW_Y = [(1, (0, 0), (1, 1), (0, 0)), (2, (2, 2), (1, 1), (
 
 
 def run_case(ndim, levelmin, levelmax, bound, regions, riemann, slope_type, ncoarse_dev, interpol_type, nsub, boxlen=1.0,
-             err=0.05, nexpand=1, difmag=0.0, bound_regions=None, interpol_var=0):
+             err=0.05, nexpand=1, difmag=0.0, bound_regions=None, interpol_var=0, gravity=False, pressure_fix=False, beta_fix=0.5,
+             device_resident=False):
     from oracle.amr import AmrRun
     from ramses_b200.hydro import HydroGPU
     r = AmrRun(ndim, levelmin, levelmax, bound, boxlen, nsubcycle=nsub, nexpand=nexpand, ngridmax=20000, riemann=riemann,
@@ -98,27 +99,88 @@ def run_case(ndim, levelmin, levelmax, bound, regions, riemann, slope_type, ncoa
     nlev = [len(r.active[l]) for l in range(1, levelmax + 1)]
     assert sum(1 for n in nlev[levelmin:] if n > 0) >= 1, nlev      # a genuinely refined mesh
     a = commons_from_run(r, riemann, slope_type)
+    # source terms are switched on for the compared coarse step only (the mesh was developed without them): poisson with an
+    # arbitrary acceleration field f (an INPUT of the path) and pressure_fix (divu / enew, reset by set_unew of every level)
+    a.poisson, a.pressure_fix, a.beta_fix = bool(gravity), bool(pressure_fix), beta_fix
+    force = None
+    if gravity:
+        rng = np.random.default_rng(17 + ndim)
+        force = np.ascontiguousarray((np.array([0.7, -0.4, 0.3])[:ndim, None] + 0.3 * rng.standard_normal((ndim, m_ncell(r)))) * 5.0)
     h = HydroGPU(a, amr_mode=True, interpol_type=interpol_type, interpol_var=interpol_var)
     for l in range(1, levelmax + 1):
         if len(a.active[l]):
             h.bind_level(l)
     h.upload_state(0)
+    if gravity:
+        h.upload_force(force)
     for l in range(1, levelmax + 1):
         if len(a.active[l]):
             h.make_boundary_hydro(l)
     dtnew = {l: r.dtnew[l] for l in range(0, levelmax + 2)}
     dtold = {l: r.dtold[l] for l in range(0, levelmax + 2)}
-    gpu_amr_step(h, a, r, levelmin, 1, dtnew, dtold)
+    if device_resident:      # rgpu_amr_steps: dtnew / dtold stay on the device, the source passes read dt from there
+        a.numbtot = {l: len(a.active[l]) for l in range(1, levelmax + 1)}
+        dts = h.amr_steps(levelmin, [0] + [r.nsubcycle[l] for l in range(1, levelmax + 1)], 1)
+        dtnew[levelmin] = dts[0]
+    else:
+        gpu_amr_step(h, a, r, levelmin, 1, dtnew, dtold)
     h.download_state(0)
+    extra = h.download_pressure_fix() if pressure_fix else None
     h.finalize()
     # oracle: the same coarse step on the frozen mesh
     r.static = True
     for l in range(1, levelmax + 1):
         r.make_boundary_hydro(l)
-    r.amr_step(levelmin, 1)
+    import ctypes as C
+    from oracle import orc
+    L = orc.lib()
+    L.orc_set_pressure_fix.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double]
+    L.orc_set_gravity.argtypes = [C.POINTER(C.c_double)]
+    divu_o, enew_o = np.zeros(m_ncell(r)), np.zeros(m_ncell(r))
+    try:
+        if pressure_fix:
+            L.orc_set_pressure_fix(orc.dptr(divu_o), orc.dptr(enew_o), beta_fix)
+        if gravity:
+            L.orc_set_gravity(orc.dptr(force))
+        r.amr_step(levelmin, 1)
+    finally:
+        L.orc_set_pressure_fix(None, None, 0.0)
+        L.orc_set_gravity(None)
     ref = r.uold.reshape(r.nvar, -1)
     cells = np.concatenate([[r.cell(ind, ig) - 1 for ig in r.active[l] for ind in range(r.T)] for l in range(1, levelmax + 1) if r.active[l]]).astype(np.int64)
+    if pressure_fix:
+        r.pfix_cmp = (extra[0][cells], divu_o[cells], extra[1][cells], enew_o[cells])
     return a.uold[:, cells], ref[:, cells], dtnew, r, nlev
+
+
+def m_ncell(r):
+    return r.m.ncell
+
+
+@pytest.mark.parametrize("ndim,gravity,pfix,resident", [(1, True, True, False), (2, True, True, False), (3, True, True, False),
+                                                        (3, True, False, True), (3, False, True, True), (2, True, True, True)])
+def test_amr_gravity_and_pressure_fix_bitwise(ndim, gravity, pfix, resident):
+    """poisson (gloc gather, gravity predictor, add_gravity_source_terms, gravity-limited Courant step) and pressure_fix (divu /
+    enew through the sweep, the coarse refluxes and set_uold's pdV source and energy switch) over one sub-cycled coarse step of
+    a refined mesh: state, divu, enew and dtnew equal the oracle's, host-driven and with the device-resident stepper."""
+    kw = dict(gravity=gravity, pressure_fix=pfix, device_resident=resident)
+    if ndim == 1:
+        got, ref, dtnew, r, nlev = run_case(1, 3, 8, (1, 1, 0, 0, 0, 0), SOD, "hllc", 2, 6, 2, [1, 1, 1, 2], **kw)
+    elif ndim == 2:
+        regs = [dict(type="square", x_center=0.5, y_center=0.5, length_x=10, length_y=10, exp_region=10, d=1.0, p=0.1),
+                dict(type="square", x_center=0.3, y_center=0.4, length_x=0.3, length_y=0.25, exp_region=2, d=2.0, u=0.3, v=-0.2, p=1.0)]
+        got, ref, dtnew, r, nlev = run_case(2, 3, 5, (1, 1, 2, 2, 0, 0), regs, "hllc", 2, 2, 2, [1, 2], bound_regions=BOUND_2D_WALLS_X_OUTFLOW_Y, **kw)
+    else:
+        regs = [dict(type="square", x_center=0.5, y_center=0.5, z_center=0.5, length_x=10, length_y=10, length_z=10, exp_region=10, d=1.0, p=1e-5),
+                dict(type="square", x_center=0.4, y_center=0.45, z_center=0.55, length_x=0.3, length_y=0.3, length_z=0.3, exp_region=2, d=1.5, p=2.0)]
+        got, ref, dtnew, r, nlev = run_case(3, 3, 4, (0,) * 6, regs, "hllc", 1, 1, 1, [2, 2], **kw)
+    lm = r.levelmin
+    assert dtnew[lm] == r.dtnew[lm]
+    assert np.array_equal(got, ref), (np.abs(got - ref).max(), nlev)
+    if pfix:
+        dk, do, ek, eo = r.pfix_cmp
+        assert np.array_equal(dk, do) and np.array_equal(ek, eo)
+        assert np.abs(do).max() > 0
 
 
 @pytest.mark.parametrize("riemann,slope_type,interpol_type", [("hllc", 2, 2), ("llf", 1, 1), ("hll", 7, 3), ("acoustic", 8, 0)])

@@ -145,6 +145,49 @@ def test_3d_reflexive_and_outflow(gpu):
     assert np.array_equal(a.uold[:, idx], ref.reshape(c.nvar, -1)[:, idx])
 
 
+@pytest.mark.parametrize("amr_mode", [False, True])
+def test_imposed_boundary_inflow(gpu, orc, amr_mode):
+    """bound_type=3 (imposed, hydro/hydro_boundary.f90:229-252 with the default boundana): a denser supersonic inflow through the
+    left face of a 1-D tube (outflow right face), dense kernel and oct-batch kernel: bit-identical to the oracle; the mass of the
+    domain grows by the inflow."""
+    import ctypes as C
+    from ramses_b200.hydro import HydroGPU
+    L = orc.lib()
+    L.orc_set_boundary_var.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int]
+    n = 64
+    c = Case(1, 6, riemann="hllc", slope_type=1, bound=(3, 2, 0, 0, 0, 0))
+    rho, u, p = 1.0, 3.0, 1.0
+    cons = np.array([rho, rho * u, p / 0.4 + 0.5 * rho * u * u])
+    cons2 = np.array([2.0, 2.0 * u, p / 0.4 + 0.5 * 2.0 * u * u])
+    L.orc_set_boundary_var(0, orc.dptr(cons2), 3)
+    d = np.zeros((3, 1, 1, n))
+    d[:, 0, 0, :] = cons[:, None]
+    c.init_dense(d)
+    ref, dts_ref = c.oracle_steps(12, nthreads=1)
+    a = c.amr_commons()
+    h = HydroGPU(a, amr_mode=amr_mode)
+    h.set_boundary_var(1, cons2)
+    h.bind_level(c.level)
+    h.upload_state(c.level)
+    if amr_mode:
+        from ramses_b200.hydro import amr_step
+        dtnew = {l: 0.0 for l in range(0, c.level + 2)}
+        dtold = dict(dtnew)
+        dts = []
+        for _ in range(12):
+            amr_step(h, c.level, 1, c.level, [1] * 64, dtnew, dtold)
+            dts.append(dtnew[c.level])
+        dts = np.array(dts)
+    else:
+        dts, _ = h.level_steps(c.level, 12)
+    h.download_state(c.level)
+    h.finalize()
+    idx = c.active_cells()
+    assert np.array_equal(dts, dts_ref)
+    assert np.array_equal(a.uold[:, idx], ref.reshape(c.nvar, -1)[:, idx])
+    assert a.uold[0, idx].sum() > 1.05 * n
+
+
 def test_courant_fine_parity(gpu):
     from ramses_b200.hydro import HydroGPU
     c = Case(3, 5, riemann="hllc", slope_type=1)
