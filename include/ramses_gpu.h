@@ -178,6 +178,9 @@ int rgpu_hydro_flag(int ilevel, const double err_grad[3], const double floor[3],
  * force_fine / gravana -- call it whenever the host recomputed the acceleration (rgpu_params.poisson = 1).
  * rgpu_download_pressure_fix: the device-resident divu(1:ncell) / enew(1:ncell) of hydro_commons (hydro/init_hydro.f90:40-42)
  * for diagnostics or a host-side pass that needs them (either pointer may be NULL).                                          */
+/* MHD build in AMR mode: interpol_mag_type of &HYDRO_PARAMS (limiter of the face-field prolongation, interpol_mag
+ * mhd/interpol_hydro.f90:990); -1 (default) = interpol_type (hydro/read_hydro_params.f90:531).                               */
+int rgpu_set_interpol_mag(int interpol_mag_type);
 int rgpu_upload_force(const double* f);
 int rgpu_download_pressure_fix(double* divu, double* enew);
 

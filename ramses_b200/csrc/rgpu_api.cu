@@ -20,6 +20,8 @@
 #include "sweep_dense3.cuh"
 #include "sweep_dense4.cuh"
 #include "amr_kernels.cuh"
+#include "mhd_amr.cuh"
+#include "amr_schedules.h"
 #include "mhd_dense.cuh"
 
 namespace rgpu {
@@ -159,6 +161,10 @@ struct AmrLevel {
   long long launches = 0;
   double dx = 0;
   double dt_last = 0;                 // dtnew(ilevel) of the last godunov_fine (set_uold's source terms need it)
+  // MHD, NDIM = 2: corner EMFs of every oct and their coarse-reflux schedule (mhd/godunov_fine.f90:1176-1270)
+  double* d_remf = nullptr;
+  int nemf = 0;
+  int *d_ecell = nullptr, *d_evar = nullptr, *d_estart = nullptr, *d_ecode = nullptr;
   double last_steps_ms = 0;           // CUDA-event duration of the last rgpu_amr_steps call (recorded on the levelmin entry)
   bool dense_sweep = false;           // the level is a Cartesian box: godunov_fine runs the dense kernel (AMR variant)
   bool patch = false;                 // ... with a prolongated ghost shell and coarse refluxes (refined patch)
@@ -178,6 +184,7 @@ struct Context {
   int nvn = 0;                       // columns of d_unew: nvar, + divu and enew with pressure_fix
   long long ncell = 0;
   int interpol_type = 1, interpol_var = 0;
+  int interpol_mag_type = -1;        // -1: interpol_type (hydro/read_hydro_params.f90:531)
   AmrLevel alev[MAXLEVEL + 1];
   double* d_dtn = nullptr; double* d_dto = nullptr;   // device-resident dtnew/dtold(0:MAXLEVEL+1) of rgpu_amr_steps
   int numbtot[MAXLEVEL + 2] = {0};                    // numbtot(1,ilevel): octs of a level over ALL ranks (amr_commons.f90)
@@ -710,6 +717,7 @@ void free_amr_level(AmrLevel& A) {
   cudaFree(A.d_active); cudaFree(A.d_rflux); cudaFree(A.d_rcell); cudaFree(A.d_rstart); cudaFree(A.d_rsrc);
   cudaFree(A.d_part); cudaFree(A.d_out); cudaFree(A.d_dt);
   cudaFree(A.d_surf_igrid); cudaFree(A.d_surf_io); cudaFree(A.d_act_slot); cudaFree(A.d_shell_father);
+  cudaFree(A.d_remf); cudaFree(A.d_ecell); cudaFree(A.d_evar); cudaFree(A.d_estart); cudaFree(A.d_ecode);
   for (auto& r : A.regions) cudaFree(r.d_igrid);
   for (auto& p : A.peers) { cudaFree(p.d_recv); cudaFree(p.d_emit); cudaFree(p.d_sbuf); cudaFree(p.d_rbuf); }
   A = AmrLevel();
@@ -763,32 +771,10 @@ int amr_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int nc
       CUDA_OK(cudaMemcpy(A.regions[b].d_igrid, igrid_bound[b], sizeof(int) * ngrid_bound[b], cudaMemcpyHostToDevice));
     }
   }
-  // reflux schedule (hydro/godunov_fine.f90:798-908): contributions in the order the reference visits them --
-  // batch of nvector octs, direction, left then right, face, oct of the batch with son(nbor)==0
+  // reflux schedule (hydro/godunov_fine.f90:798-908): contributions in the order the reference visits them (amr_schedules.h)
   {
-    const int nv = std::max(1, G.p.nvector);
-    std::vector<int> tgt, src;
-    for (int i0 = 0; i0 < ngrid_active; i0 += nv) {
-      const int ng = std::min(nv, ngrid_active - i0);
-      for (int d = 0; d < nd; d++)
-        for (int s = 0; s < 2; s++)
-          for (int f = 0; f < NSF; f++)
-            for (int i = 0; i < ng; i++) {
-              const int ig = igrid_active[i0 + i];
-              const int nb = G.nbor[(size_t)(2 * d + s) * G.ngridmax + ig - 1];
-              if (nb > 0 && G.son[nb - 1] == 0) { tgt.push_back(nb); src.push_back(((i0 + i) << 6) | ((2 * d + s) << 3) | f); }
-            }
-    }
-    // group by target cell, keeping the visiting order inside each group (stable)
-    std::vector<int> order(tgt.size());
-    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tgt[x] < tgt[y]; });
-    std::vector<int> cells, start, srcs;
-    for (size_t k = 0; k < order.size(); k++) {
-      if (k == 0 || tgt[order[k]] != tgt[order[k - 1]]) { cells.push_back(tgt[order[k]]); start.push_back((int)k); }
-      srcs.push_back(src[order[k]]);
-    }
-    start.push_back((int)order.size());
+    std::vector<int> cells, start, srcs, src;
+    build_reflux_schedule(nd, G.p.nvector, ngrid_active, igrid_active, G.nbor, G.son, G.ngridmax, cells, start, srcs, src);
     A.nent = (int)cells.size();
     {   // octs that own at least one refluxed face, in active-list order
       std::vector<char> mark((size_t)std::max(1, ngrid_active), 0);
@@ -884,9 +870,11 @@ int amr_godunov_dense(AmrLevel& A, int ilevel, double dt, const double* dt_dev) 
   return RGPU_OK;
 }
 
+int mhd_amr_godunov(AmrLevel& A, int ilevel, double dt, const double* dt_dev);
 int amr_godunov(AmrLevel& A, int ilevel, double dt, const double* dt_dev = nullptr) {
   A.dt_last = dt;
   if (A.nact == 0) return RGPU_OK;
+  if (G.p.mhd) return mhd_amr_godunov(A, ilevel, dt, dt_dev);
   if (A.dense_sweep) return amr_godunov_dense(A, ilevel, dt, dt_dev);
   AmrSweepArgs a{};
   a.dt_dev = dt_dev;
@@ -920,8 +908,8 @@ int amr_godunov(AmrLevel& A, int ilevel, double dt, const double* dt_dev = nullp
 }
 int amr_copy(AmrLevel& A, const double* src, double* dst) {
   if (A.nact == 0) return RGPU_OK;
-  const long long n = (long long)A.nact * T_() * G.p.nvar;
-  amr_copy_octs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, G.stream>>>(src, dst, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar);
+  const long long n = (long long)A.nact * T_() * G.nvs;
+  amr_copy_octs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, G.stream>>>(src, dst, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.nvs);
   CUDA_OK(cudaGetLastError());
   A.launches++;
   return RGPU_OK;
@@ -932,7 +920,7 @@ int amr_exchange(AmrLevel& A, double* u, bool reverse) {
   if (A.peers.empty()) return RGPU_OK;
   if (!G.comm) return fail(RGPU_EINVAL, "ghost exchange needs rgpu_comm_init");
   // reverse runs on unew: with pressure_fix its columns nvar, nvar+1 are divu and enew (amr_step.f90:397-404)
-  const int T = T_(), nvar = (reverse && u == G.d_unew) ? G.nvn : G.p.nvar;
+  const int T = T_(), nvar = (reverse && u == G.d_unew) ? G.nvn : G.nvs;
   const long long per = (long long)T * nvar;
   for (auto& P : A.peers) {
     const int n = reverse ? P.nrecv : P.nemit;
@@ -972,6 +960,91 @@ int amr_zero_ghost_unew(AmrLevel& A) {   // set_unew: unew (and divu, enew) = 0 
   return RGPU_OK;
 }
 
+// ---- ideal MHD in AMR mode, NDIM = 1, 2 (mhd_amr.cuh) -----------------------------------------------------------------------
+int mhd_amr_bind_extra(AmrLevel& A, int ilevel, int ngrid_active, const int* igrid_active) {
+  if (G.p.ndim != 2 || ngrid_active == 0) return RGPU_OK;
+  CUDA_OK(cudaMalloc(&A.d_remf, sizeof(double) * 4 * (size_t)ngrid_active));
+  // the 3x3 father cells of every oct (device tree walk), then the schedule on the host in the reference's visiting order:
+  // batch of nvector octs -> edge X0Y0, X0Y1, X1Y1, X1Y0 -> oct of the batch -> the statements of :1196-1268
+  std::vector<int> nfc((size_t)ngrid_active * 9);
+  int* d_nfc = nullptr;
+  CUDA_OK(cudaMalloc(&d_nfc, sizeof(int) * nfc.size()));
+  amr_nfc_kernel<2><<<(ngrid_active + 127) / 128, 128, 0, G.stream>>>(amr_tree(), A.d_active, ngrid_active, ilevel, d_nfc);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(nfc.data(), d_nfc, sizeof(int) * nfc.size(), cudaMemcpyDeviceToHost, G.stream));
+  CUDA_OK(cudaStreamSynchronize(G.stream));
+  cudaFree(d_nfc);
+  if (ngrid_active >= (1 << 26)) return fail(RGPU_EUNSUPPORTED, "too many octs for the packed EMF reflux schedule");
+  std::vector<int> cells, vars, start, codes;
+  build_emf_schedule_2d(G.p.nvector, ngrid_active, nfc.data(), G.son, cells, vars, start, codes);
+  A.nemf = (int)cells.size();
+  if (A.nemf > 0) {
+    CUDA_OK(cudaMalloc(&A.d_ecell, sizeof(int) * cells.size()));
+    CUDA_OK(cudaMalloc(&A.d_evar, sizeof(int) * vars.size()));
+    CUDA_OK(cudaMalloc(&A.d_estart, sizeof(int) * start.size()));
+    CUDA_OK(cudaMalloc(&A.d_ecode, sizeof(int) * codes.size()));
+    CUDA_OK(cudaMemcpy(A.d_ecell, cells.data(), sizeof(int) * cells.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(A.d_evar, vars.data(), sizeof(int) * vars.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(A.d_estart, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(A.d_ecode, codes.data(), sizeof(int) * codes.size(), cudaMemcpyHostToDevice));
+  }
+  return RGPU_OK;
+}
+int mhd_amr_godunov(AmrLevel& A, int ilevel, double dt, const double* dt_dev) {
+  MhdAmrArgs a{};
+  a.t = amr_tree(); a.active = A.d_active; a.nact = A.nact; a.ilevel = ilevel;
+  a.uold = G.d_uold; a.unew = G.d_unew; a.rflux = A.d_rflux; a.remf = A.d_remf;
+  a.P = G.mphys; a.dt = dt; a.dx = A.dx; a.dt_dev = dt_dev;
+  a.interpol_type = G.interpol_type; a.interpol_mag_type = G.interpol_mag_type < 0 ? G.interpol_type : G.interpol_mag_type;
+  a.riemann = G.p.riemann; a.riemann2d = G.p.riemann2d;
+  if (G.p.ndim == 1) mhd_amr1_godfine_kernel<<<(A.nact + 63) / 64, 64, 0, G.stream>>>(a);
+  else mhd_amr2_godfine_kernel<<<A.nact, MHD2_TPO, 0, G.stream>>>(a);
+  CUDA_OK(cudaGetLastError());
+  A.launches++;
+  if (A.nent > 0) {   // Euler fluxes into the coarser level (:1030-1168)
+    RefluxArgs r{};
+    r.nent = A.nent; r.cell = A.d_rcell; r.start = A.d_rstart; r.src = A.d_rsrc; r.rflux = A.d_rflux; r.unew = G.d_unew;
+    r.ncell = G.ncell; r.nvar = MNVS; r.nsides = 2 * G.p.ndim; r.nsf = 1 << (G.p.ndim - 1);
+    r.oneontwotondim = 1.0 / (double)(1 << G.p.ndim);
+    const int n = A.nent * MNVS;
+    mhd_amr_reflux_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(r);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  if (A.nemf > 0) {   // corner EMFs into the coarser level (:1176-1270)
+    EmfRefluxArgs r{};
+    r.nent = A.nemf; r.cell = A.d_ecell; r.var = A.d_evar; r.start = A.d_estart; r.code = A.d_ecode; r.remf = A.d_remf; r.unew = G.d_unew;
+    r.ncell = G.ncell;
+    mhd_amr_emf_reflux_kernel<<<(A.nemf + 127) / 128, 128, 0, G.stream>>>(r);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  return RGPU_OK;
+}
+int mhd_amr_upload(AmrLevel& A) {
+  if (A.nact == 0) return RGPU_OK;
+  const int n = A.nact * T_();
+  for (int pass = 0; pass < 2; pass++) {
+    mhd_amr_upload_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.p.ndim, G.p.smallr, pass);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  return RGPU_OK;
+}
+int mhd_amr_boundaries(AmrLevel& A) {
+  for (auto& r : A.regions) {
+    if (r.n == 0) continue;
+    const int bt = r.type, dir = bt - 10 * (bt / 10);
+    if (G.p.ndim != 1 || bt / 10 > 1) return fail(RGPU_EUNSUPPORTED, "MHD AMR mode: boundary type %d with NDIM=%d not supported (NDIM=1 reflexive / outflow; periodic otherwise)", bt, G.p.ndim);
+    MhdAmrBoundArgs b{};
+    b.n = r.n; b.igrid = r.d_igrid; b.dir = dir; b.kind = bt / 10; b.smallr = G.p.smallr;
+    mhd_amr1_boundary_kernel<<<(r.n * 2 + 127) / 128, 128, 0, G.stream>>>(G.d_uold, amr_tree(), b);
+    CUDA_OK(cudaGetLastError());
+    A.launches++;
+  }
+  return RGPU_OK;
+}
+
 // set_unew (hydro/godunov_fine.f90:40-130): unew = uold on the active octs (+ divu = 0, enew = e_int), 0 on the reception octs
 int amr_set_unew(AmrLevel& A) {
   int rc = amr_copy(A, G.d_uold, G.d_unew); if (rc) return rc;
@@ -1001,7 +1074,7 @@ int amr_set_uold(AmrLevel& A, int ilevel, const double* dt_dev) {
     CUDA_OK(cudaGetLastError());
     A.launches++;
   }
-  const int nps = G.p.nvar - (G.p.ndim + 2);
+  const int nps = G.p.mhd ? 0 : G.p.nvar - (G.p.ndim + 2);
   if (nps > 0) {   // passive-scalar fix for floored densities, before the copy (godunov_fine.f90:176-190)
     amr_scalar_floor_kernel<<<nb, 128, 0, G.stream>>>(G.d_uold, G.d_unew, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(),
                                                    G.p.ndim + 2, G.p.nvar, G.p.smallr);
@@ -1019,6 +1092,11 @@ int amr_set_uold(AmrLevel& A, int ilevel, const double* dt_dev) {
 }
 int amr_courant_launch(AmrLevel& A) {
   const int nb = 148 * 8;
+  if (G.p.mhd) {
+    mhd_amr_courant_kernel<<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.mphys, A.dx, G.p.ndim, A.d_part);
+    CUDA_OK(cudaGetLastError());
+    return RGPU_OK;
+  }
   const double* f = G.p.poisson ? G.d_force : nullptr;
   if (G.p.ndim == 1) amr_courant_kernel<1><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.phys, A.dx, A.d_part, f);
   else if (G.p.ndim == 2) amr_courant_kernel<2><<<nb, 256, 0, G.stream>>>(G.d_uold, amr_tree(), A.d_active, A.nact, G.phys, A.dx, A.d_part, f);
@@ -1028,6 +1106,7 @@ int amr_courant_launch(AmrLevel& A) {
 }
 
 int amr_boundaries(AmrLevel& A) {
+  if (G.p.mhd) return mhd_amr_boundaries(A);
   static const int ref_x[8] = {2, 1, 4, 3, 6, 5, 8, 7}, ref_y[8] = {3, 4, 1, 2, 7, 8, 5, 6}, ref_z[8] = {5, 6, 7, 8, 1, 2, 3, 4};
   static const int fre[6][8] = {{1, 1, 3, 3, 5, 5, 7, 7}, {2, 2, 4, 4, 6, 6, 8, 8}, {1, 2, 1, 2, 5, 6, 5, 6},
                                 {3, 4, 3, 4, 7, 8, 7, 8}, {1, 2, 3, 4, 1, 2, 3, 4}, {5, 6, 7, 8, 5, 6, 7, 8}};
@@ -1091,7 +1170,7 @@ int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device) {
   if (!p) return fail(RGPU_EINVAL, "null params");
   if (p->ndim < 1 || p->ndim > 3) return fail(RGPU_EINVAL, "ndim=%d", p->ndim);
   if (p->mhd) {
-    if (p->ndim != 3) return fail(RGPU_EUNSUPPORTED, "MHD build: NDIM=%d not supported (3 only)", p->ndim);
+    // NDIM = 3: dense levelmin=levelmax path (mhd_dense.cuh); NDIM = 1, 2: AMR mode (rgpu_set_amr; mhd_amr.cuh)
     if (p->nvar != 8) return fail(RGPU_EUNSUPPORTED, "MHD build: nvar=%d: passive scalars / NENER not supported (need nvar=8)", p->nvar);
     if (p->riemann < 0 || p->riemann > 5) return fail(RGPU_EINVAL, "unknown riemann solver");     // mhd/umuscl.f90:1435
     if (p->riemann2d < 0 || p->riemann2d > 5) return fail(RGPU_EINVAL, "unknown 2D riemann solver"); // mhd/umuscl.f90:1886
@@ -1156,8 +1235,9 @@ int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device) {
   P.cfl_k = std::sqrt(1.0 + 2.0 * p->courant_factor * P.cfl_g) - 1.0;
   P.slope_type = p->slope_type; P.niter_riemann = p->niter_riemann;
   G.nvs = p->mhd ? p->nvar + 3 : p->nvar;
-  G.nvn = p->nvar + (p->pressure_fix ? 2 : 0);
+  G.nvn = G.nvs + (p->pressure_fix ? 2 : 0);
   for (int b = 0; b < 64; b++) G.bvar_set[b] = false;
+  G.interpol_mag_type = -1;
   MPhys& M = G.mphys;
   M.gamma = p->gamma; M.smallr = p->smallr; M.smallc = p->smallc; M.slope_theta = p->slope_theta; M.courant_factor = p->courant_factor;
   M.smallp = p->smallr * (p->smallc * p->smallc) / p->gamma;
@@ -1186,7 +1266,11 @@ int rgpu_finalize(void) {
 
 int rgpu_set_amr(int on, int interpol_type, int interpol_var) {
   if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
-  if (on && G.p.mhd) return fail(RGPU_EUNSUPPORTED, "MHD build: AMR mode (divergence-free prolongation, EMF refluxing) not supported; levelmin=levelmax only");
+  if (on && G.p.mhd && G.p.ndim == 3)
+    return fail(RGPU_EUNSUPPORTED, "MHD build, NDIM=3: AMR mode (divergence-free prolongation, EMF refluxing on 12 edges) not supported; levelmin=levelmax only");
+  if (on && G.p.mhd && interpol_var != 0) return fail(RGPU_EUNSUPPORTED, "MHD build: interpol_var=%d not supported (0 only)", interpol_var);
+  if (on && G.p.mhd && !(G.p.slope_type >= 0 && G.p.slope_type <= 2))
+    return fail(RGPU_EUNSUPPORTED, "MHD AMR mode (NDIM=1,2): slope_type=%d not supported (0, 1, 2)", G.p.slope_type);
   if (on && (interpol_var < 0 || interpol_var > 2)) return fail(RGPU_EINVAL, "interpol_var=%d (0, 1 or 2: hydro/interpol_hydro.f90:318-345)", interpol_var);
   if (on && (interpol_type < 0 || interpol_type > 4)) return fail(RGPU_EINVAL, "interpol_type=%d (0..4)", interpol_type);
   if (on && interpol_type == 4 && interpol_var != 2)
@@ -1212,9 +1296,9 @@ int rgpu_bind_tree(int ncoarse, int ngridmax, const int* son, const int* father,
       G.d_son = G.d_son_base + 1;
       CUDA_OK(cudaMalloc(&G.d_father, sizeof(int) * ngridmax));
       CUDA_OK(cudaMalloc(&G.d_nbor, sizeof(int) * (size_t)2 * G.p.ndim * ngridmax));
-      CUDA_OK(cudaMalloc(&G.d_uold, sizeof(double) * G.p.nvar * ncell));
+      CUDA_OK(cudaMalloc(&G.d_uold, sizeof(double) * G.nvs * ncell));
       CUDA_OK(cudaMalloc(&G.d_unew, sizeof(double) * G.nvn * ncell));
-      CUDA_OK(cudaMemset(G.d_uold, 0, sizeof(double) * G.p.nvar * ncell));
+      CUDA_OK(cudaMemset(G.d_uold, 0, sizeof(double) * G.nvs * ncell));
       CUDA_OK(cudaMemset(G.d_unew, 0, sizeof(double) * G.nvn * ncell));
       if (G.p.poisson) {
         CUDA_OK(cudaMalloc(&G.d_force, sizeof(double) * G.p.ndim * ncell));
@@ -1555,6 +1639,7 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
   if (G.amr) {
     int rc = amr_bind_level(ilevel, ngrid_active, igrid_active, ncpu, ngrid_recv, igrid_recv, ngrid_emit, igrid_emit, nboundary, boundary_type, ngrid_bound, igrid_bound);
     if (rc) return rc;
+    if (G.p.mhd) return mhd_amr_bind_extra(G.alev[ilevel], ilevel, ngrid_active, igrid_active);
     // A level that is a complete Cartesian box and sends no refluxes to a coarser level (the fully refined base of the
     // run) is swept by the dense kernel: ~10x the throughput of the oct-batch kernel.  RGPU_AMR_DENSE=0 disables.
     AmrLevel& A = G.alev[ilevel];
@@ -1607,6 +1692,8 @@ int rgpu_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int n
     }
     return RGPU_OK;
   }
+  if (G.p.mhd && G.p.ndim != 3)
+    return fail(RGPU_EUNSUPPORTED, "MHD build, NDIM=%d: built in AMR mode only -- call rgpu_set_amr(1, interpol_type, 0) after rgpu_init", G.p.ndim);
   if (G.p.difmag > 0.0 || (!G.p.mhd && G.p.nvar != G.p.ndim + 2) || src_terms())
     return fail(RGPU_EUNSUPPORTED, "difmag>0 (cmpdivu/consup), passive scalars (nvar>ndim+2), poisson and pressure_fix are built in the oct-batch "
                                    "kernel only: call rgpu_set_amr(1, interpol_type, 0) after rgpu_init (works for levelmin=levelmax runs too)");
@@ -1795,7 +1882,7 @@ static int godunov_fine_pipelined(Level& L, const double* uold, double* unew) {
 int rgpu_upload_state(int ilevel, const double* uold) {
   if (G.amr) {   // AMR mode: the whole uold array (all levels) is mirrored; ilevel is ignored
     if (!G.d_uold || !uold) return fail(RGPU_EINVAL, "AMR mode: bind the tree first / null uold");
-    CUDA_OK(cudaMemcpyAsync(G.d_uold, uold, sizeof(double) * G.p.nvar * G.ncell, cudaMemcpyHostToDevice, G.stream));
+    CUDA_OK(cudaMemcpyAsync(G.d_uold, uold, sizeof(double) * G.nvs * G.ncell, cudaMemcpyHostToDevice, G.stream));
     CUDA_OK(cudaStreamSynchronize(G.stream));
     return RGPU_OK;
   }
@@ -1808,7 +1895,7 @@ int rgpu_upload_state(int ilevel, const double* uold) {
 int rgpu_download_state(int ilevel, double* uold) {
   if (G.amr) {
     if (!G.d_uold || !uold) return fail(RGPU_EINVAL, "AMR mode: bind the tree first / null uold");
-    CUDA_OK(cudaMemcpyAsync(uold, G.d_uold, sizeof(double) * G.p.nvar * G.ncell, cudaMemcpyDeviceToHost, G.stream));
+    CUDA_OK(cudaMemcpyAsync(uold, G.d_uold, sizeof(double) * G.nvs * G.ncell, cudaMemcpyDeviceToHost, G.stream));
     CUDA_OK(cudaStreamSynchronize(G.stream));
     return RGPU_OK;
   }
@@ -1937,7 +2024,7 @@ int rgpu_godunov_fine(int ilevel, double dt, const double* uold, double* unew) {
     if (!uold || !unew) return fail(RGPU_EINVAL, "null state array");
     if (!(dt > 0)) return fail(RGPU_EINVAL, "dt=%g", dt);
     if (G.p.pressure_fix) return fail(RGPU_EUNSUPPORTED, "pressure_fix: divu / enew live on the device; use the device-resident calls (rgpu_set_unew ... rgpu_set_uold)");
-    const size_t bytes = sizeof(double) * G.p.nvar * G.ncell;
+    const size_t bytes = sizeof(double) * G.nvs * G.ncell;
     CUDA_OK(cudaMemcpyAsync(G.d_uold, uold, bytes, cudaMemcpyHostToDevice, G.stream));
     CUDA_OK(cudaMemcpyAsync(G.d_unew, unew, bytes, cudaMemcpyHostToDevice, G.stream));
     rc = amr_godunov(*A, ilevel, dt); if (rc) return rc;
@@ -2077,7 +2164,8 @@ static int amr_step_dev(int l, int icount, int levelmin, const int* nsub) {
   rc = amr_godunov(A, l, 0.0, G.d_dtn + l); if (rc) return rc;         // :388
   if (G.comm && G.nranks > 1) { rc = amr_exchange(A, G.d_unew, true); if (rc) return rc; }     // :397
   rc = amr_set_uold(A, l, G.d_dtn + l); if (rc) return rc;            // set_uold :423 (source terms, scalar floor fix, energy switch)
-  if (l < nlev && A.nact > 0) {                                         // upload_fine :441
+  if (l < nlev && A.nact > 0 && G.p.mhd) { rc = mhd_amr_upload(A); if (rc) return rc; }
+  else if (l < nlev && A.nact > 0) {                                    // upload_fine :441
     const int n = A.nact * T_();
     amr_upload_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_son - 1, A.d_active, A.nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar, G.p.smallr, G.interpol_var, G.p.ndim);
     CUDA_OK(cudaGetLastError());
@@ -2157,6 +2245,12 @@ int rgpu_hydro_flag(int ilevel, const double err_grad[3], const double floor[3],
   return RGPU_OK;
 }
 
+int rgpu_set_interpol_mag(int interpol_mag_type) {
+  if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
+  if (interpol_mag_type < -1 || interpol_mag_type > 3) return fail(RGPU_EINVAL, "interpol_mag_type=%d (-1 = interpol_type, 0..3)", interpol_mag_type);
+  G.interpol_mag_type = interpol_mag_type;
+  return RGPU_OK;
+}
 int rgpu_set_boundary_var(int ibound, const double* var) {
   if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
   if (ibound < 1 || ibound > 64 || !var) return fail(RGPU_EINVAL, "ibound=%d (1..64) / null var", ibound);
@@ -2186,6 +2280,7 @@ int rgpu_upload_fine(int ilevel) {
   if (!G.amr) return RGPU_OK;   // a dense (levelmin=levelmax) level has no split cells: upload_fine is a no-op
   AmrLevel* A; int rc = check_amr_level(ilevel, &A); if (rc) return rc;
   if (A->nact == 0 || ilevel >= G.p.nlevelmax) return RGPU_OK;
+  if (G.p.mhd) return mhd_amr_upload(*A);
   const int n = A->nact * T_();
   amr_upload_kernel<<<(n + 127) / 128, 128, 0, G.stream>>>(G.d_uold, G.d_son - 1, A->d_active, A->nact, G.ncoarse, G.ngridmax, G.ncell, T_(), G.p.nvar, G.p.smallr,
                                                          G.interpol_var, G.p.ndim);

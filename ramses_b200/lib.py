@@ -110,6 +110,7 @@ def load():
     L.rgpu_level_totals.argtypes = [C.c_int, ip]
     L.rgpu_hydro_flag.argtypes = [C.c_int, dp, dp, ip]
     L.rgpu_upload_force.argtypes = [dp]
+    L.rgpu_set_interpol_mag.argtypes = [C.c_int]
     L.rgpu_set_boundary_var.argtypes = [C.c_int, dp]
     L.rgpu_download_pressure_fix.argtypes = [dp, dp]
     L.rgpu_selftest_div.argtypes = [C.c_longlong, C.c_ulonglong, C.POINTER(C.c_longlong)]

@@ -6,6 +6,8 @@
 static double* rgpu_host_dyn_smem = nullptr;   // dynamic shared memory of an emulated launch (sweep_dense.cuh)
 #include "mhd_dense.cuh"    // the six MHD passes; pulls sweep_dense.cuh, mhd_device.cuh, hydro_device.cuh, real64.cuh
 #include "amr_kernels.cuh"  // the AMR oct-batch kernel and its __device__ tree-walk / prolongation helpers
+#include "mhd_amr.cuh"      // ideal MHD in AMR mode, NDIM = 1, 2
+#include "amr_schedules.h"  // host-side reflux schedules (shared with rgpu_api.cu)
 #include "sweep_dense4.cuh" // one-barrier form (includes sweep_dense3.cuh)
 #include "sweep_dense3.cuh" // round-2 form of the 3-D dense sweep + the lane-generic solvers (hydro_vec.cuh)
 
@@ -376,6 +378,91 @@ static MPhys make_mphys(double gamma, double smallr, double smallc) {
   M.smallp = smallr * (smallc * smallc) / gamma;
   M.slope_type = 1; M.slope_mag_type = 1;
   return M;
+}
+
+// ---- ideal MHD in AMR mode (mhd_amr.cuh): godunov_fine of one level = godfine kernel + Euler reflux + (2-D) EMF reflux, with the
+// schedules of amr_schedules.h exactly as rgpu_api.cu builds them at bind time.  uold/unew [11][ncell].
+void devnum_mhd_amr_godunov(int ndim, int ncoarse, int ngridmax, int nx, int ny, int nz, const int* son, const int* father, const int* nbor,
+                            const int* active, int nact, int ilevel, const double* uold, double* unew, double dt, double dx,
+                            int interpol_type, int interpol_mag_type, int riemann, int riemann2d, int slope_type, int slope_mag_type,
+                            double gamma, double smallr, double smallc, int nvector) {
+  MhdAmrArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.t.son = son - 1; a.t.father = father - 1; a.t.nbor = nbor; a.t.ncoarse = ncoarse; a.t.ngridmax = ngridmax;
+  a.t.nx = nx; a.t.ny = ny; a.t.nz = nz; a.t.ncell = (long long)ncoarse + (long long)(1 << ndim) * ngridmax;
+  const int TW = 2 * ndim, NSF = 1 << (ndim - 1);
+  std::vector<double> rflux((size_t)std::max(1, nact) * TW * NSF * MNV, 0.0), remf((size_t)std::max(1, nact) * 4, 0.0);
+  a.active = active; a.nact = nact; a.ilevel = ilevel; a.uold = uold; a.unew = unew; a.rflux = rflux.data(); a.remf = remf.data();
+  a.P = make_mphys(gamma, smallr, smallc);
+  a.P.slope_type = slope_type; a.P.slope_mag_type = slope_mag_type;
+  a.dt = dt; a.dx = dx; a.dt_dev = nullptr;
+  a.interpol_type = interpol_type; a.interpol_mag_type = interpol_mag_type < 0 ? interpol_type : interpol_mag_type;
+  a.riemann = riemann; a.riemann2d = riemann2d;
+  if (ndim == 1) emulate_serial(mhd_amr1_godfine_kernel, a, (nact + 63) / 64, 64);
+  else emulate_launch(mhd_amr2_godfine_kernel, a, nact, MHD2_TPO);
+  std::vector<int> cells, start, srcs, src;
+  build_reflux_schedule(ndim, nvector, nact, active, nbor, son, ngridmax, cells, start, srcs, src);
+  if (!cells.empty()) {
+    RefluxArgs r;
+    std::memset(&r, 0, sizeof r);
+    r.nent = (int)cells.size(); r.cell = cells.data(); r.start = start.data(); r.src = srcs.data(); r.rflux = rflux.data(); r.unew = unew;
+    r.ncell = a.t.ncell; r.nvar = MNVS; r.nsides = TW; r.nsf = NSF; r.oneontwotondim = 1.0 / (double)(1 << ndim);
+    emulate_serial(mhd_amr_reflux_kernel, r, (r.nent * MNVS + 127) / 128, 128);
+  }
+  if (ndim == 2 && nact > 0) {
+    std::vector<int> nfc((size_t)nact * 9);
+    for (int i = 0; i < nact; i++) {
+      int f[27], ng[8];
+      amr_get3cubefather<2>(a.t, active[i], ilevel, f, ng);
+      for (int j = 0; j < 9; j++) nfc[(size_t)i * 9 + j] = f[j];
+    }
+    std::vector<int> ec, ev, es, ecode;
+    build_emf_schedule_2d(nvector, nact, nfc.data(), son, ec, ev, es, ecode);
+    if (!ec.empty()) {
+      EmfRefluxArgs r;
+      std::memset(&r, 0, sizeof r);
+      r.nent = (int)ec.size(); r.cell = ec.data(); r.var = ev.data(); r.start = es.data(); r.code = ecode.data(); r.remf = remf.data();
+      r.unew = unew; r.ncell = a.t.ncell;
+      emulate_serial(mhd_amr_emf_reflux_kernel, r, (r.nent + 127) / 128, 128);
+    }
+  }
+}
+
+// kind 0: upload_fine (both passes), 1: make_boundary_hydro (NDIM = 1; dir, bkind), 2: per-cell Courant steps of the leaf cells -> dtc[nact*T]
+void devnum_mhd_amr_pass(int kind, int ndim, int ncoarse, int ngridmax, int nx, int ny, int nz, const int* son, const int* father,
+                         const int* nbor, const int* list, int n, double* u, double gamma, double smallr, double smallc, double cfl,
+                         double dx, int dir, int bkind, double* dtc) {
+  AmrTree t;
+  std::memset(&t, 0, sizeof t);
+  t.son = son - 1; t.father = father - 1; t.nbor = nbor; t.ncoarse = ncoarse; t.ngridmax = ngridmax; t.nx = nx; t.ny = ny; t.nz = nz;
+  t.ncell = (long long)ncoarse + (long long)(1 << ndim) * ngridmax;
+  const int T = 1 << ndim;
+  MPhys P = make_mphys(gamma, smallr, smallc);
+  P.courant_factor = cfl;
+  if (kind == 0) {
+    for (int pass = 0; pass < 2; pass++)
+      for (int b = 0; b < (n * T + 127) / 128; b++)
+        for (int th = 0; th < 128; th++) {
+          threadIdx = {(unsigned)th, 0, 0}; blockIdx = {(unsigned)b, 0, 0}; blockDim = {128, 1, 1}; gridDim = {1, 1, 1};
+          mhd_amr_upload_kernel(u, t, list, n, ndim, smallr, pass);
+        }
+  } else if (kind == 1) {
+    MhdAmrBoundArgs bb;
+    bb.n = n; bb.igrid = list; bb.dir = dir; bb.kind = bkind; bb.smallr = smallr;
+    for (int b = 0; b < (n * 2 + 127) / 128; b++)
+      for (int th = 0; th < 128; th++) {
+        threadIdx = {(unsigned)th, 0, 0}; blockIdx = {(unsigned)b, 0, 0}; blockDim = {128, 1, 1}; gridDim = {1, 1, 1};
+        mhd_amr1_boundary_kernel(u, t, bb);
+      }
+  } else {
+    for (int o = 0; o < n; o++)
+      for (int ind = 0; ind < T; ind++) {
+        const int ic = amr_cell(t, ind, list[o]);
+        double uu[MNVS];
+        for (int k = 0; k < MNVS; k++) uu[k] = u[(size_t)k * t.ncell + ic - 1];
+        dtc[o * T + ind] = (t.son[ic] != 0) ? 1e300 : mhd_cmpdt_cell_nd(P, uu, dx, ndim);
+      }
+  }
 }
 
 // n MHD Riemann problems in solver order (rho, P, v_n, B_n, v_t1, B_t1, v_t2, B_t2): fg [n][9]

@@ -9,6 +9,7 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__ inline
 using std::copysign;
 using std::max;
 using std::min;

@@ -19,7 +19,7 @@ def dev():
     lib = os.path.join(HERE, "libdevnum_host.so")
     srcs = [os.path.join(HERE, "devnum.cpp"), os.path.join(HERE, "stub", "cuda_runtime.h")] + \
         [os.path.join(CSRC, f) for f in ("hydro_device.cuh", "real64.cuh", "mhd_device.cuh", "amr_kernels.cuh", "sweep_dense.cuh",
-                                        "sweep_dense3.cuh", "sweep_dense4.cuh", "hydro_vec.cuh", "mhd_dense.cuh")]
+                                        "sweep_dense3.cuh", "sweep_dense4.cuh", "hydro_vec.cuh", "mhd_dense.cuh", "mhd_amr.cuh", "amr_schedules.h")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-pthread",
                                "-fvisibility=hidden", "-fvisibility-inlines-hidden", "-Wl,-Bsymbolic",
@@ -44,6 +44,9 @@ def dev():
     L.devnum_amr_src_pass.argtypes = [C.c_int] * 7 + [ip, ip, ip, ip, C.c_int, dp, dp, dp, dp, dp] + [C.c_double] * 5
     L.devnum_cmpdt_grav.argtypes = [C.c_int, C.c_int, dp, dp, C.c_double, dp, C.c_double, C.c_double, C.c_double, C.c_double]
     L.devnum_riemann_eflux.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int]
+    L.devnum_mhd_amr_godunov.argtypes = [C.c_int] * 6 + [ip, ip, ip, ip, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double] + [C.c_int] * 6 + \
+        [C.c_double] * 3 + [C.c_int]
+    L.devnum_mhd_amr_pass.argtypes = [C.c_int] * 7 + [ip, ip, ip, ip, C.c_int, dp] + [C.c_double] * 5 + [C.c_int, C.c_int, dp]
     return L
 
 
@@ -614,6 +617,118 @@ def test_amr_source_terms_emulated_on_the_cpu_equal_oracle(orc, dev, ndim, solve
     assert nlev >= 3 and gmoved > 1e-6 and (dmax > 0 or not pfix)
     if pfix and ndim == 3:
         assert switched > 0          # the cold Sedov background (p = 1e-5) does trip the energy switch
+
+
+MHD_R1D = {"llf": 0, "roe": 1, "hll": 2, "hlld": 3, "upwind": 4, "hydro": 5}
+MHD_R2D = {"llf": 0, "roe": 1, "upwind": 2, "hll": 3, "hlla": 4, "hlld": 5}
+
+
+def _mhd_amr_compare_levels(orc, dev, r, ndim, riemann, riemann2d, slope_type, interpol_type, godunov, upload, courant, boundary=None):
+    """every populated level of the run `r`: godunov_fine (own cells AND the refluxed coarse cells: the whole unew array),
+    upload_fine, the leaf-cell Courant step and (1-D) make_boundary_hydro of the device code == the oracle's, bit for bit"""
+    m = r.m
+    T, nc = 1 << ndim, r.ncell
+    son = np.ascontiguousarray(r.son[1:], dtype=np.int32)
+    father = np.ascontiguousarray(r.father[1:], dtype=np.int32)
+    nbor = np.ascontiguousarray(r.nbor[:, 1:], dtype=np.int32)
+    L = orc.lib()
+    tree = (ndim, r.ncoarse, r.ngridmax, m.nx, m.ny, m.nz, orc.iptr(son), orc.iptr(father), orc.iptr(nbor))
+    nlev, nrefl, moved = 0, 0, 0.0
+    for l in range(r.levelmin, r.nlevelmax + 1):
+        act = np.ascontiguousarray(r.active[l], dtype=np.int32)
+        if len(act) == 0:
+            continue
+        dt = 0.5 * r.dtnew[r.levelmin] / 2 ** (l - r.levelmin) if r.dtnew[r.levelmin] > 0 else 1e-4
+        dx = 0.5 ** l * r.p.boxlen / (m.icoarse_max - m.icoarse_min + 1)
+        # ---- godunov_fine
+        unew_o, unew_k = np.zeros_like(r.uold), np.zeros_like(r.uold)
+        if l > r.levelmin:          # the coarser level has been through set_unew: its cells carry the state, refluxes add to it
+            L.orc_mhdn_set_unew(r.mp, l - 1, orc.dptr(r.uold), orc.dptr(unew_o))
+            L.orc_mhdn_set_unew(r.mp, l - 1, orc.dptr(r.uold), orc.dptr(unew_k))
+        L.orc_mhdn_set_unew(r.mp, l, orc.dptr(r.uold), orc.dptr(unew_o))
+        L.orc_mhdn_set_unew(r.mp, l, orc.dptr(r.uold), orc.dptr(unew_k))
+        before = unew_o.copy()
+        godunov(C.byref(r.pm), r.mp, l, r.levelmin, r.nvector, dt, orc.dptr(r.uold), orc.dptr(unew_o))
+        dev.devnum_mhd_amr_godunov(*tree[:9], orc.iptr(act), len(act), l, orc.dptr(r.uold), orc.dptr(unew_k), dt, dx, interpol_type, -1,
+                                   MHD_R1D[riemann], MHD_R2D[riemann2d], slope_type, slope_type, r.pm.gamma, r.pm.smallr, r.pm.smallc, r.nvector)
+        assert np.isfinite(unew_k).all()
+        assert np.array_equal(unew_k, unew_o), (l, np.abs(unew_k - unew_o).max())
+        moved = max(moved, float(np.abs(unew_o - before).max()))
+        if l > r.levelmin:
+            own = np.zeros(nc, dtype=bool)
+            for ind in range(T):
+                own[r.ncoarse + ind * r.ngridmax + act.astype(np.int64) - 1] = True
+            d = (unew_o != before).reshape(11, nc)
+            nrefl += int(d[:, ~own].any(axis=0).sum())
+        # ---- upload_fine
+        if l < r.nlevelmax:
+            u_o, u_k = r.uold.copy(), r.uold.copy()
+            upload(C.byref(r.pm), r.mp, l, orc.dptr(u_o))
+            dev.devnum_mhd_amr_pass(0, *tree, orc.iptr(act), len(act), orc.dptr(u_k), r.pm.gamma, r.pm.smallr, r.pm.smallc, r.pm.courant_factor, dx, 0, 0, None)
+            assert np.array_equal(u_k, u_o), l
+        # ---- courant_fine
+        dt_o = courant(C.byref(r.pm), r.mp, l, r.p.boxlen / r.p.smallc, orc.dptr(r.uold))
+        dtc = np.zeros(len(act) * T)
+        u_k = r.uold.copy()
+        dev.devnum_mhd_amr_pass(2, *tree, orc.iptr(act), len(act), orc.dptr(u_k), r.pm.gamma, r.pm.smallr, r.pm.smallc, r.pm.courant_factor, dx, 0, 0, orc.dptr(dtc))
+        if (dtc < 1e299).any():
+            assert min(dtc.min(), r.pm.courant_factor * dx / r.pm.smallc, r.p.boxlen / r.p.smallc) == dt_o, l
+        else:                       # a fully refined level has no leaf cell: courant_fine leaves dtnew alone
+            assert dt_o == r.p.boxlen / r.p.smallc
+        # ---- make_boundary_hydro (1-D)
+        if boundary is not None:
+            u_o, u_k = r.uold.copy(), r.uold.copy()
+            # scramble the boundary octs first so that the pass has something to do
+            for b in range(m.nboundary):
+                for ig in r.bound[b][l]:
+                    for ind in range(T):
+                        u_o.reshape(11, nc)[:, r.cell(ind, ig) - 1] = 9.0
+                        u_k.reshape(11, nc)[:, r.cell(ind, ig) - 1] = 9.0
+            boundary(C.byref(r.pm), r.mp, l, orc.dptr(u_o))
+            for b in range(m.nboundary):
+                lst = np.ascontiguousarray(r.bound[b][l], dtype=np.int32)
+                if len(lst) == 0:
+                    continue
+                bt = m.boundary_type[b]
+                dev.devnum_mhd_amr_pass(1, *tree, orc.iptr(lst), len(lst), orc.dptr(u_k), r.pm.gamma, r.pm.smallr, r.pm.smallc, r.pm.courant_factor, dx,
+                                        bt % 10, bt // 10, None)
+            assert np.array_equal(u_k, u_o), l
+        nlev += 1
+    return nlev, nrefl, moved
+
+
+@pytest.mark.parametrize("riemann,slope_type", [("hlld", 1), ("roe", 2), ("llf", 0), ("hll", 1)])
+def test_mhd_amr_1d_kernels_emulated_on_the_cpu_equal_oracle(orc, dev, riemann, slope_type):
+    """NDIM=1 ideal MHD on the refined mesh of the imhd-tube problem (tests/mhd/imhd-tube): mhd_amr1_godfine_kernel + the coarse
+    reflux pass, upload_fine, cmpdt and the outflow boundaries (mhd_amr.cuh) against mhd1_godfine1 & co. of the oracle, which
+    reproduces imhd-tube-ref.dat."""
+    from oracle.amr_mhd import MhdAmrRun
+    from test_oracle_golden import IMHD
+    r = MhdAmrRun(5, 10, (2, 2, 0, 0, 0, 0), 3.5, nsubcycle=[1, 1, 1, 1], riemann=riemann, slope_type=slope_type, gamma=1.6666667,
+                  courant_factor=0.8, err_grad_d=0.01, err_grad_u=0.05, err_grad_p=0.05, interpol_type=2, regions=IMHD,
+                  tout=[1e9], ngridmax=10000)
+    r.run(max_coarse=12)
+    L = orc.lib()
+    nlev, nrefl, moved = _mhd_amr_compare_levels(orc, dev, r, 1, riemann, "llf", slope_type, 2, L.orc_mhd1_godunov_fine, L.orc_mhd1_upload_fine,
+                                                 L.orc_mhd1_courant_fine, boundary=L.orc_mhd1_make_boundary_hydro)
+    assert nlev >= 4 and nrefl > 0 and moved > 1e-6
+
+
+@pytest.mark.parametrize("r1,r2,slope_type", [("hlld", "hlld", 2), ("roe", "llf", 1), ("llf", "roe", 2), ("hll", "hll", 0), ("hydro", "hlla", 1),
+                                               ("upwind", "upwind", 2)])
+def test_mhd_amr_2d_kernels_emulated_on_the_cpu_equal_oracle(orc, dev, r1, r2, slope_type):
+    """NDIM=2 ideal MHD on the adaptively refined Orszag-Tang vortex (tests/mhd/orszag-tang): mhd_amr2_godfine_kernel (64
+    cooperating threads per oct: divergence-free prolongation of the ghost octs, trace2d, 12 face and 9 corner Riemann problems,
+    constrained transport) + the Euler and corner-EMF coarse refluxes in the reference's accumulation order, upload_fine with
+    face-centred restriction and cmpdt, against mhd2_godfine1 & co. of the oracle, which reproduces orszag-tang-ref.dat."""
+    from oracle.amr_mhd import MhdAmrRun2D
+    r = MhdAmrRun2D(4, 6, 1.0, nsubcycle=[1], riemann=r1, riemann2d=r2, slope_type=slope_type, gamma=1.6666667, courant_factor=0.8,
+                    err_grad_p=0.1, interpol_type=2, tout=[1e9], nexpand=1, ngridmax=20000)
+    r.run(max_coarse=16)
+    L = orc.lib()
+    nlev, nrefl, moved = _mhd_amr_compare_levels(orc, dev, r, 2, r1, r2, slope_type, 2, L.orc_mhd2_godunov_fine, L.orc_mhdn_upload_fine,
+                                                 L.orc_mhdn_courant_fine)
+    assert nlev >= 3 and nrefl > 0 and moved > 1e-6
 
 
 def _to_slots(dense, N):

@@ -217,3 +217,115 @@ def test_mhd_full_size_256_properties():
     assert abs(U[0, 0, 0, n // 2] - 0.2) > 1e-3 and U[0, 0, 0, 0] == 1.0 and U[0, 0, 0, -1] == 0.2
     # sums of courant_fine: mass = integral of rho over the box (zero-gradient ends: inflow/outflow is still zero there)
     assert abs(sums[0] - U[0].sum() * (2.0 / n) ** 3) < 1e-12 * sums[0]
+
+
+# ---- ideal MHD in AMR mode, NDIM = 1, 2: the reference's own MHD test problems (tests/mhd/imhd-tube, tests/mhd/orszag-tang) -----
+def _mhd_commons_from_run(r, ndim, riemann, riemann2d, slope_type):
+    from ramses_b200.hydro import AmrCommons
+    m = r.m
+    a = AmrCommons(ndim, 8, m.ncoarse, m.ngridmax, m.nx, m.ny, m.nz, (m.icoarse_min, m.icoarse_max), (m.jcoarse_min, m.jcoarse_max),
+                   (m.kcoarse_min, m.kcoarse_max), nlevelmax=r.nlevelmax, boxlen=r.p.boxlen, mhd=True)
+    a.son[:] = r.son[1:]
+    a.father[:] = r.father[1:]
+    a.nbor[:, :] = r.nbor[:, 1:]
+    a.uold[:, :] = r.uold.reshape(11, m.ncell)
+    for l in range(1, r.nlevelmax + 1):
+        a.active[l] = np.array(r.active[l], dtype=np.int32)
+        a.boundary[l] = [np.array(r.bound[b][l], dtype=np.int32) for b in range(m.nboundary)]
+    a.boundary_type = [m.boundary_type[b] for b in range(m.nboundary)]
+    a.gamma, a.courant_factor = r.pm.gamma, r.pm.courant_factor
+    a.slope_type, a.slope_mag_type, a.riemann, a.riemann2d, a.nvector = slope_type, -1, riemann, riemann2d, r.nvector
+    return a
+
+
+def _mhd_amr_gpu_vs_oracle(r, ndim, riemann, riemann2d, slope_type, ncoarse, resident):
+    """ncoarse coarse steps (with sub-cycling) of the frozen mesh of run `r` on the device -- host-driven amr_step order or the
+    device-resident stepper -- against the oracle's amr_step: every active cell of every level, and dtnew(levelmin)"""
+    from ramses_b200.hydro import amr_step
+    levelmin, levelmax = r.levelmin, r.nlevelmax
+    # regrid once more like the head of amr_step, then freeze the mesh (tests/test_gpu_amr.py::run_case)
+    for i in range(levelmin, levelmax + 1):
+        if i > levelmin:
+            r.make_boundary_hydro(i)
+        r.refine_fine(i)
+    nlev = [len(r.active[l]) for l in range(1, levelmax + 1)]
+    assert sum(1 for n in nlev[levelmin:] if n > 0) >= 1, nlev
+    a = _mhd_commons_from_run(r, ndim, riemann, riemann2d, slope_type)
+    h = HydroGPU(a, amr_mode=True, interpol_type=2)
+    for l in range(1, levelmax + 1):
+        if len(a.active[l]):
+            h.bind_level(l)
+    h.upload_state(0)
+    for l in range(1, levelmax + 1):
+        if len(a.active[l]):
+            h.make_boundary_hydro(l)
+    nsub = [0] + [r.nsubcycle[l] for l in range(1, levelmax + 1)] + [2] * 8
+    if resident:
+        a.numbtot = {l: len(a.active[l]) for l in range(1, levelmax + 1)}
+        dts = list(h.amr_steps(levelmin, nsub, ncoarse))
+    else:
+        dtnew = {l: r.dtnew[l] for l in range(0, levelmax + 2)}
+        dtold = {l: r.dtold[l] for l in range(0, levelmax + 2)}
+        dts = []
+        for _ in range(ncoarse):
+            amr_step(h, levelmin, 1, levelmin, nsub, dtnew, dtold)
+            dts.append(dtnew[levelmin])
+    h.download_state(0)
+    h.finalize()
+    r.static = True
+    for l in range(1, levelmax + 1):
+        r.make_boundary_hydro(l)
+    dts_ref = []
+    for _ in range(ncoarse):
+        r.amr_step(levelmin, 1)
+        dts_ref.append(r.dtnew[levelmin])
+    ref = r.uold.reshape(11, -1)
+    cells = np.concatenate([[r.cell(ind, ig) - 1 for ig in r.active[l] for ind in range(r.T)] for l in range(1, levelmax + 1) if r.active[l]]).astype(np.int64)
+    assert np.array_equal(np.array(dts), np.array(dts_ref)), (dts, dts_ref)
+    got = a.uold[:, cells]
+    assert np.isfinite(got).all()
+    assert np.array_equal(got, ref[:, cells]), (np.abs(got - ref[:, cells]).max(), nlev)
+    return nlev
+
+
+@pytest.mark.parametrize("riemann,slope_type,resident", [("hlld", 0, False), ("hlld", 1, True), ("roe", 2, False), ("llf", 1, True)])
+def test_mhd_amr_1d_imhd_tube_bitwise(orc, riemann, slope_type, resident):
+    """tests/mhd/imhd-tube (NDIM=1, levelmin=5, AMR, outflow boundaries; slope_type=0 hlld is the reference's namelist): 3 coarse
+    steps of the refined tube on the device == the oracle that reproduces imhd-tube-ref.dat, bit for bit."""
+    from oracle.amr_mhd import MhdAmrRun
+    from test_oracle_golden import IMHD            # the regions of tests/mhd/imhd-tube/imhd-tube.nml
+    r = MhdAmrRun(5, 10, (2, 2, 0, 0, 0, 0), 3.5, nsubcycle=[1, 1, 2, 2], riemann=riemann, slope_type=slope_type, gamma=1.6666667,
+                  courant_factor=0.8, err_grad_d=0.01, err_grad_u=0.05, err_grad_p=0.05, interpol_type=2, regions=IMHD,
+                  tout=[1e9], ngridmax=10000)
+    r.run(max_coarse=12)
+    nlev = _mhd_amr_gpu_vs_oracle(r, 1, riemann, "llf", slope_type, 3, resident)
+    assert sum(1 for n in nlev if n > 0) >= 6
+
+
+@pytest.mark.parametrize("r1,r2,slope_type,resident", [("hlld", "hlld", 2, False), ("hlld", "hlld", 2, True), ("roe", "llf", 1, False),
+                                                       ("llf", "roe", 2, True), ("hll", "hlla", 1, False)])
+def test_mhd_amr_2d_orszag_tang_bitwise(orc, r1, r2, slope_type, resident):
+    """tests/mhd/orszag-tang (NDIM=2, AMR, periodic; hlld/hlld with slope_type=2 is the reference's namelist): 2 coarse steps of the
+    adaptively refined vortex on the device -- divergence-free prolongation, constrained transport, Euler and corner-EMF
+    refluxing, face-centred restriction -- == the oracle that reproduces orszag-tang-ref.dat, bit for bit; div B stays at
+    round-off on the device-computed state."""
+    from oracle.amr_mhd import MhdAmrRun2D
+    r = MhdAmrRun2D(4, 6, 1.0, nsubcycle=[1, 2], riemann=r1, riemann2d=r2, slope_type=slope_type, gamma=1.6666667, courant_factor=0.8,
+                    err_grad_p=0.1, interpol_type=2, tout=[1e9], nexpand=1, ngridmax=20000)
+    r.run(max_coarse=16)
+    nlev = _mhd_amr_gpu_vs_oracle(r, 2, r1, r2, slope_type, 2, resident)
+    assert sum(1 for n in nlev if n > 0) >= 5
+    assert r.divb_max() < 5e-14
+
+
+def test_mhd_low_dimensional_builds_need_amr_mode(orc):
+    """NDIM=1,2 MHD is built in AMR mode only: the dense path refuses; NDIM=3 AMR mode refuses."""
+    from ramses_b200 import lib as _l
+    from oracle.amr_mhd import MhdAmrRun2D
+    r = MhdAmrRun2D(3, 3, 1.0, nsubcycle=[1], riemann="llf", riemann2d="llf", slope_type=1, tout=[1e9], ngridmax=2000)
+    r.flag_coarse(); r.init_refine(); r.init_refine_2()
+    a = _mhd_commons_from_run(r, 2, "llf", "llf", 1)
+    h = HydroGPU(a)
+    with pytest.raises(_l.RgpuError):
+        h.bind_level(3)
+    h.finalize()
