@@ -7,7 +7,7 @@
  * structure courant_fine -> set_unew -> godunov_fine -> set_uold.  Every
  * floating-point expression keeps the Fortran evaluation order (left to
  * right, `**2` = x*x, `**3` = x*x*x, sign(one,x) = copysign, MAX/MIN keep the
- * first argument on ties); build with  -O2 -ffp-contract=off  (no FMA, no
+ * first argument on ties); build with  -O3 -ffp-contract=off  (no FMA, no
  * fast-math) to mirror `gfortran -O3` on baseline x86-64 (bin/Makefile:99-106).
  *
  * PARITY PINNING STATUS ("how do we know this restatement is right?"):
@@ -41,6 +41,12 @@
  *       NDIM=3 branches are tied to the golden-pinned NDIM=2 branches.
  *   NOT covered by a golden file (none exists in the reference): the bodies of
  *   riemann='exact'/'acoustic'/'hll'/'llf' and slope types other than 2 -- held by 2-5.
+ *   PARITY UNPINNED for two options: poisson (gravity predictor, gloc gather, add_gravity_source_terms,
+ *   gravity term of cmpdt; orc_set_gravity) and pressure_fix (divu / enew, add_pdv_source_terms, the
+ *   energy switch; orc_set_pressure_fix).  Every reference test that enables them also needs cooling,
+ *   sinks, RT or a patched condinit, which are outside this path, so no golden vector exists for them;
+ *   they are restated from the reference text and held by the properties of
+ *   tests/test_oracle.py::test_gravity_restatement / test_pressure_fix_restatement only.
  *
  * Citations are reference file:line.
  */
