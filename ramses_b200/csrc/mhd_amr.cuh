@@ -461,6 +461,422 @@ __global__ void __launch_bounds__(MHD2_TPO) mhd_amr2_godfine_kernel(const MhdAmr
 #undef C49
 }
 
+// ====================================================================================================== NDIM = 3
+// compute_2d_tvd, one direction (mhd/interpol_hydro.f90:1478)
+__device__ __forceinline__ double mhd_tvd2(int mt, double b0, double bl, double br) {
+  if (mt == 3) { const double dlft = 0.5 * (b0 - bl), drgt = 0.5 * (br - b0); return dlft + drgt; }
+  return mslope((double)mt, bl, b0, br);
+}
+// interpol_hydro + interpol_mag for one father cell, NDIM = 3: u2[8][11]
+__device__ void mhd3_interpol_cell(const AmrTree& t, const double* __restrict__ uold, int ind_cell, int ilevel, int interpol_type,
+                                   int mt, double smallr, double (*u2)[MNVS]) {
+  const size_t NC = (size_t)t.ncell;
+  auto UO = [&](int ic, int iv) -> double { return uold[(size_t)iv * NC + ic - 1]; };
+  int fa[7], ind1[7];
+  amr_getnborfather<3>(t, ind_cell, ilevel, fa);
+  double u1[7][MNVS];
+  for (int j = 0; j < 7; j++) {
+    for (int iv = 0; iv < MNVS; iv++) u1[j][iv] = UO(fa[j], iv);
+    ind1[j] = t.son[fa[j]];
+  }
+  amr_interpol_hydro<3, MNVS>(u1, interpol_type, 0, smallr, u2);   // variables 1..5 (cell centred); the face fields are overwritten
+  double u[3][2][2], v[2][3][2], w[2][2][3];                       // u[i+1][j][k], v[i][j+1][k], w[i][j][k+1]
+#define B1(j_, c_) u1[(j_)][((c_) <= 3 ? 4 + (c_) : MNV + (c_)-4)]
+  for (int side = 0; side < 2; side++) {   // interpol_faces :1052
+    const int cx = side == 0 ? 1 : 4, cy = side == 0 ? 2 : 5, cz = side == 0 ? 3 : 6, f = side == 0 ? 0 : 2;
+    double s1 = 0.0, s2 = 0.0;
+    if (mt > 0) { s1 = mhd_tvd2(mt, B1(0, cx), B1(3, cx), B1(4, cx)); s2 = mhd_tvd2(mt, B1(0, cx), B1(5, cx), B1(6, cx)); }
+    for (int j = 0; j <= 1; j++)
+      for (int k = 0; k <= 1; k++) u[f][j][k] = B1(0, cx) + 0.5 * s1 * ((double)j - 0.5) + 0.5 * s2 * ((double)k - 0.5);
+    s1 = s2 = 0.0;
+    if (mt > 0) { s1 = mhd_tvd2(mt, B1(0, cy), B1(1, cy), B1(2, cy)); s2 = mhd_tvd2(mt, B1(0, cy), B1(5, cy), B1(6, cy)); }
+    for (int i = 0; i <= 1; i++)
+      for (int k = 0; k <= 1; k++) v[i][f][k] = B1(0, cy) + 0.5 * s1 * ((double)i - 0.5) + 0.5 * s2 * ((double)k - 0.5);
+    s1 = s2 = 0.0;
+    if (mt > 0) { s1 = mhd_tvd2(mt, B1(0, cz), B1(1, cz), B1(2, cz)); s2 = mhd_tvd2(mt, B1(0, cz), B1(3, cz), B1(4, cz)); }
+    for (int i = 0; i <= 1; i++)
+      for (int j = 0; j <= 1; j++) w[i][j][f] = B1(0, cz) + 0.5 * s1 * ((double)i - 0.5) + 0.5 * s2 * ((double)j - 0.5);
+  }
+#undef B1
+  for (int a = 0; a <= 1; a++)             // copy_from_refined_faces :1246
+    for (int b = 0; b <= 1; b++) {
+      if (ind1[1] > 0) u[0][a][b] = UO(amr_cell(t, 1 + a * 2 + b * 4, ind1[1]), MNV + 0);
+      if (ind1[2] > 0) u[2][a][b] = UO(amr_cell(t, 0 + a * 2 + b * 4, ind1[2]), 5);
+      if (ind1[3] > 0) v[a][0][b] = UO(amr_cell(t, a + 1 * 2 + b * 4, ind1[3]), MNV + 1);
+      if (ind1[4] > 0) v[a][2][b] = UO(amr_cell(t, a + 0 * 2 + b * 4, ind1[4]), 6);
+      if (ind1[5] > 0) w[a][b][0] = UO(amr_cell(t, a + b * 2 + 1 * 4, ind1[5]), MNV + 2);
+      if (ind1[6] > 0) w[a][b][2] = UO(amr_cell(t, a + b * 2 + 0 * 4, ind1[6]), 7);
+    }
+  double UXX = 0, VYY = 0, WZZ = 0, UXYZ = 0, VXYZ = 0, WXYZ = 0;   // cmp_central_faces :1354, NDIM == 3
+  for (int i = 0; i <= 1; i++)
+    for (int j = 0; j <= 1; j++)
+      for (int k = 0; k <= 1; k++) {
+        const int ii = 2 * i - 1, jj = 2 * j - 1, kk = 2 * k - 1;
+        UXX = UXX + ((double)(ii * jj) * v[i][jj + 1][k] + (double)(ii * kk) * w[i][j][kk + 1]) * 0.125;
+        VYY = VYY + ((double)(jj * kk) * w[i][j][kk + 1] + (double)(ii * jj) * u[ii + 1][j][k]) * 0.125;
+        WZZ = WZZ + ((double)(ii * kk) * u[ii + 1][j][k] + (double)(jj * kk) * v[i][jj + 1][k]) * 0.125;
+        UXYZ = UXYZ + ((double)(ii * jj * kk) * u[ii + 1][j][k]) * 0.125;
+        VXYZ = VXYZ + ((double)(ii * jj * kk) * v[i][jj + 1][k]) * 0.125;
+        WXYZ = WXYZ + ((double)(ii * jj * kk) * w[i][j][kk + 1]) * 0.125;
+      }
+  for (int j = 0; j <= 1; j++)
+    for (int k = 0; k <= 1; k++)
+      u[1][j][k] = 0.5 * (u[0][j][k] + u[2][j][k]) + UXX + ((double)k - 0.5) * VXYZ + ((double)j - 0.5) * WXYZ;
+  for (int i = 0; i <= 1; i++)
+    for (int k = 0; k <= 1; k++)
+      v[i][1][k] = 0.5 * (v[i][0][k] + v[i][2][k]) + VYY + ((double)i - 0.5) * WXYZ + ((double)k - 0.5) * UXYZ;
+  for (int i = 0; i <= 1; i++)
+    for (int j = 0; j <= 1; j++)
+      w[i][j][1] = 0.5 * (w[i][j][0] + w[i][j][2]) + WZZ + ((double)j - 0.5) * UXYZ + ((double)i - 0.5) * VXYZ;
+  for (int i = 0; i <= 1; i++)
+    for (int j = 0; j <= 1; j++)
+      for (int k = 0; k <= 1; k++) {
+        const int ind = i + 2 * j + 4 * k;
+        u2[ind][5] = u[i][j][k]; u2[ind][MNV + 0] = u[i + 1][j][k];
+        u2[ind][6] = v[i][j][k]; u2[ind][MNV + 1] = v[i][j + 1][k];
+        u2[ind][7] = w[i][j][k]; u2[ind][MNV + 2] = w[i][j][k + 1];
+      }
+}
+
+__device__ __noinline__ double mhd_emf_rt(int r2d, const MPhys& M, const double* RT, const double* RB, const double* LT, const double* LB, int dir) {
+  switch (r2d) {
+    case MHD2D_LLF: return emf_corners<MHD2D_LLF>(M, RT, RB, LT, LB, dir);
+    case MHD2D_ROE: return emf_corners<MHD2D_ROE>(M, RT, RB, LT, LB, dir);
+    case MHD2D_UPWIND: return emf_corners<MHD2D_UPWIND>(M, RT, RB, LT, LB, dir);
+    case MHD2D_HLL: return emf_corners<MHD2D_HLL>(M, RT, RB, LT, LB, dir);
+    case MHD2D_HLLA: return emf_corners<MHD2D_HLLA>(M, RT, RB, LT, LB, dir);
+    default: return emf_corners<MHD2D_HLLD>(M, RT, RB, LT, LB, dir);
+  }
+}
+
+constexpr int MHD3_TPO = 128;   // threads per oct
+// shared-memory image of mag_unsplit on one 6^3 patch (mhd/umuscl.f90:31): ~160 KB, one oct per SM at a time (dynamic shared memory)
+struct Mhd3Sm {
+  double uloc[216][MNVS];
+  double q[216][MNV];
+  double bf[343][3];            // [k+1][j+1][i+1], Fortran -1..5
+  double dq[64][MNV][3];        // cells 0..3
+  double dbf[343][3][2];
+  double Ex[216], Ey[216], Ez[216];
+  double qm[64][MNV][3], qp[64][MNV][3];
+  double qRT[64][MNV][3], qRB[64][MNV][3], qLT[64][MNV][3], qLB[64][MNV][3];
+  double flux[3][27][MNV];      // [idim][(k3-1)*9 + (j3-1)*3 + (i3-1)]
+  double emf[3][27];            // [dir: x, y, z][(k3-1)*9 + (j3-1)*3 + (i3-1)]
+  int nfc[27], gnb[27], ng[8];
+  unsigned char ok[216];
+};
+// one block of 128 threads per oct
+__global__ void __launch_bounds__(MHD3_TPO) mhd_amr3_godfine_kernel(const MhdAmrArgs a) {
+#ifdef RGPU_HOST_NUMERICS
+  double* smem = rgpu_host_dyn_smem;
+#else
+  extern __shared__ double smem[];
+#endif
+  Mhd3Sm& s = *reinterpret_cast<Mhd3Sm*>(smem);
+  const int tl = threadIdx.x, io = blockIdx.x;
+  if (io >= a.nact) return;
+  const AmrTree& t = a.t;
+  const MPhys& P = a.P;
+  const size_t NC = (size_t)t.ncell;
+  const int igrid = a.active[io];
+  const double dt = a.dt_dev ? *a.dt_dev : a.dt, dx = a.dx;
+  const double smallr = P.smallr, smallp = P.smallp, gamma = P.gamma;
+#define X_(i) ((i) + 1)
+#define C6(k, j, i) ((X_(k) * 6 + X_(j)) * 6 + X_(i))
+#define C7(k, j, i) ((X_(k) * 7 + X_(j)) * 7 + X_(i))
+#define C4(k, j, i) (((k) * 4 + (j)) * 4 + (i))            /* trace region 0..3 */
+#define F3(k3, j3, i3) ((((k3)-1) * 3 + ((j3)-1)) * 3 + ((i3)-1))
+  if (tl == 0) {
+    amr_get3cubefather<3>(t, igrid, a.ilevel, s.nfc, s.ng);
+    for (int j = 0; j < 27; j++) s.gnb[j] = s.nfc[j] > 0 ? t.son[s.nfc[j]] : 0;
+  }
+  __syncthreads();
+  // ---- gather ----
+  for (int e = tl; e < 27 * 8; e += MHD3_TPO) {
+    const int jf = e / 8, is = e % 8;
+    const int g = s.gnb[jf];
+    if (g <= 0) continue;
+    const int i1 = jf % 3, j1 = (jf / 3) % 3, k1 = jf / 9;
+    const int i3 = 1 + 2 * (i1 - 1) + (is & 1), j3 = 1 + 2 * (j1 - 1) + ((is >> 1) & 1), k3 = 1 + 2 * (k1 - 1) + (is >> 2);
+    const int ic = amr_cell(t, is, g);
+    for (int iv = 0; iv < MNVS; iv++) s.uloc[C6(k3, j3, i3)][iv] = a.uold[(size_t)iv * NC + ic - 1];
+    s.ok[C6(k3, j3, i3)] = t.son[ic] > 0;
+  }
+  for (int jf = tl; jf < 27; jf += MHD3_TPO) {
+    if (s.gnb[jf] > 0) continue;
+    double u2[8][MNVS];
+    mhd3_interpol_cell(t, a.uold, s.nfc[jf], a.ilevel, a.interpol_type, a.interpol_mag_type, smallr, u2);
+    const int i1 = jf % 3, j1 = (jf / 3) % 3, k1 = jf / 9;
+    for (int is = 0; is < 8; is++) {
+      const int i3 = 1 + 2 * (i1 - 1) + (is & 1), j3 = 1 + 2 * (j1 - 1) + ((is >> 1) & 1), k3 = 1 + 2 * (k1 - 1) + (is >> 2);
+      for (int iv = 0; iv < MNVS; iv++) s.uloc[C6(k3, j3, i3)][iv] = u2[is][iv];
+      s.ok[C6(k3, j3, i3)] = 0;
+    }
+  }
+  __syncthreads();
+  // ---- ctoprim :2029 ----
+  for (int e = tl; e < 216; e += MHD3_TPO) mhd_ctoprim_cell(P, s.uloc[e], s.q[e]);
+  for (int e = tl; e < 343; e += MHD3_TPO) {
+    const int i = e % 7 - 1, j = (e / 7) % 7 - 1, k = e / 49 - 1;
+    if (j <= 4 && k <= 4) s.bf[e][0] = (i <= 4) ? s.uloc[C6(k, j, i)][5] : s.uloc[C6(k, j, i - 1)][MNV + 0];
+    if (i <= 4 && k <= 4) s.bf[e][1] = (j <= 4) ? s.uloc[C6(k, j, i)][6] : s.uloc[C6(k, j - 1, i)][MNV + 1];
+    if (i <= 4 && j <= 4) s.bf[e][2] = (k <= 4) ? s.uloc[C6(k, j, i)][7] : s.uloc[C6(k - 1, j, i)][MNV + 2];
+  }
+  for (int e = tl; e < 343 * 6; e += MHD3_TPO) (&s.dbf[0][0][0])[e] = 0.0;
+  __syncthreads();
+  // ---- uslope :2187 (slope types 0, 1, 2) ----
+  for (int e = tl; e < 64 * MNV; e += MHD3_TPO) {
+    const int n = e % MNV, c = e / MNV, i = c % 4, j = (c / 4) % 4, k = c / 16;
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+    if (P.slope_type == 1 || P.slope_type == 2) {
+      const double st = (double)P.slope_type;
+      d0 = mslope(st, s.q[C6(k, j, i - 1)][n], s.q[C6(k, j, i)][n], s.q[C6(k, j, i + 1)][n]);
+      d1 = mslope(st, s.q[C6(k, j - 1, i)][n], s.q[C6(k, j, i)][n], s.q[C6(k, j + 1, i)][n]);
+      d2 = mslope(st, s.q[C6(k - 1, j, i)][n], s.q[C6(k, j, i)][n], s.q[C6(k + 1, j, i)][n]);
+    }
+    s.dq[C4(k, j, i)][n][0] = d0; s.dq[C4(k, j, i)][n][1] = d1; s.dq[C4(k, j, i)][n][2] = d2;
+  }
+  if (P.slope_mag_type == 1 || P.slope_mag_type == 2) {
+    const double st = (double)P.slope_mag_type;
+    for (int e = tl; e < 4 * 4 * 5; e += MHD3_TPO) {
+      {   // bf x: k 0..3, j 0..3, i 0..4
+        const int i = e % 5, j = (e / 5) % 4, k = e / 20;
+        s.dbf[C7(k, j, i)][0][0] = mslope(st, s.bf[C7(k, j - 1, i)][0], s.bf[C7(k, j, i)][0], s.bf[C7(k, j + 1, i)][0]);
+        s.dbf[C7(k, j, i)][0][1] = mslope(st, s.bf[C7(k - 1, j, i)][0], s.bf[C7(k, j, i)][0], s.bf[C7(k + 1, j, i)][0]);
+      }
+      {   // bf y: k 0..3, j 0..4, i 0..3
+        const int i = e % 4, j = (e / 4) % 5, k = e / 20;
+        s.dbf[C7(k, j, i)][1][0] = mslope(st, s.bf[C7(k, j, i - 1)][1], s.bf[C7(k, j, i)][1], s.bf[C7(k, j, i + 1)][1]);
+        s.dbf[C7(k, j, i)][1][1] = mslope(st, s.bf[C7(k - 1, j, i)][1], s.bf[C7(k, j, i)][1], s.bf[C7(k + 1, j, i)][1]);
+      }
+      {   // bf z: k 0..4, j 0..3, i 0..3
+        const int i = e % 4, j = (e / 4) % 4, k = e / 16;
+        s.dbf[C7(k, j, i)][2][0] = mslope(st, s.bf[C7(k, j, i - 1)][2], s.bf[C7(k, j, i)][2], s.bf[C7(k, j, i + 1)][2]);
+        s.dbf[C7(k, j, i)][2][1] = mslope(st, s.bf[C7(k, j - 1, i)][2], s.bf[C7(k, j, i)][2], s.bf[C7(k, j + 1, i)][2]);
+      }
+    }
+  }
+  // ---- trace3d :750: edge-centred electric fields :812-836 on i,j,k = 0..4 ----
+  for (int e = tl; e < 125; e += MHD3_TPO) {
+    const int i = e % 5, j = (e / 5) % 5, k = e / 25;
+#define Q(di, dj, dk, n) s.q[C6(k + (dk), j + (dj), i + (di))][n]
+#define BF(di, dj, dk, n) s.bf[C7(k + (dk), j + (dj), i + (di))][n]
+    double v = 0.25 * (Q(0, -1, -1, 2) + Q(0, -1, 0, 2) + Q(0, 0, -1, 2) + Q(0, 0, 0, 2));
+    double ww = 0.25 * (Q(0, -1, -1, 3) + Q(0, -1, 0, 3) + Q(0, 0, -1, 3) + Q(0, 0, 0, 3));
+    double B = 0.5 * (BF(0, 0, -1, 1) + BF(0, 0, 0, 1));
+    double C = 0.5 * (BF(0, -1, 0, 2) + BF(0, 0, 0, 2));
+    s.Ex[C6(k, j, i)] = v * C - ww * B;
+    double u = 0.25 * (Q(-1, 0, -1, 1) + Q(-1, 0, 0, 1) + Q(0, 0, -1, 1) + Q(0, 0, 0, 1));
+    ww = 0.25 * (Q(-1, 0, -1, 3) + Q(-1, 0, 0, 3) + Q(0, 0, -1, 3) + Q(0, 0, 0, 3));
+    double A = 0.5 * (BF(0, 0, -1, 0) + BF(0, 0, 0, 0));
+    C = 0.5 * (BF(-1, 0, 0, 2) + BF(0, 0, 0, 2));
+    s.Ey[C6(k, j, i)] = ww * A - u * C;
+    u = 0.25 * (Q(-1, -1, 0, 1) + Q(-1, 0, 0, 1) + Q(0, -1, 0, 1) + Q(0, 0, 0, 1));
+    v = 0.25 * (Q(-1, -1, 0, 2) + Q(-1, 0, 0, 2) + Q(0, -1, 0, 2) + Q(0, 0, 0, 2));
+    A = 0.5 * (BF(0, -1, 0, 0) + BF(0, 0, 0, 0));
+    B = 0.5 * (BF(-1, 0, 0, 1) + BF(0, 0, 0, 1));
+    s.Ez[C6(k, j, i)] = u * B - v * A;
+  }
+  __syncthreads();
+  const double dtdx = dt / dx, dtdy = dt / dx, dtdz = dt / dx;
+  for (int e = tl; e < 64; e += MHD3_TPO) {
+    const int i = e % 4, j = (e / 4) % 4, k = e / 16;
+    const double* q = s.q[C6(k, j, i)];
+    double(*dq)[3] = s.dq[C4(k, j, i)];
+    double r = q[0], u = q[1], v = q[2], ww = q[3], pp = q[4], A = q[5], B = q[6], C = q[7];
+    double AL = BF(0, 0, 0, 0), AR = BF(1, 0, 0, 0), BL = BF(0, 0, 0, 1), BR = BF(0, 1, 0, 1), CL = BF(0, 0, 0, 2), CR = BF(0, 0, 1, 2);
+    const double drx = 0.5 * dq[0][0], dux = 0.5 * dq[1][0], dvx = 0.5 * dq[2][0], dwx = 0.5 * dq[3][0], dpx = 0.5 * dq[4][0];
+    const double dBx = 0.5 * dq[6][0], dCx = 0.5 * dq[7][0];
+    const double dry = 0.5 * dq[0][1], duy = 0.5 * dq[1][1], dvy = 0.5 * dq[2][1], dwy = 0.5 * dq[3][1], dpy = 0.5 * dq[4][1];
+    const double dAy = 0.5 * dq[5][1], dCy = 0.5 * dq[7][1];
+    const double drz = 0.5 * dq[0][2], duz = 0.5 * dq[1][2], dvz = 0.5 * dq[2][2], dwz = 0.5 * dq[3][2], dpz = 0.5 * dq[4][2];
+    const double dAz = 0.5 * dq[5][2], dBz = 0.5 * dq[6][2];
+#define DBF(di, dj, dk, c, tt) s.dbf[C7(k + (dk), j + (dj), i + (di))][c][tt]
+    const double dALy = 0.5 * DBF(0, 0, 0, 0, 0), dARy = 0.5 * DBF(1, 0, 0, 0, 0), dALz = 0.5 * DBF(0, 0, 0, 0, 1), dARz = 0.5 * DBF(1, 0, 0, 0, 1);
+    const double dBLx = 0.5 * DBF(0, 0, 0, 1, 0), dBRx = 0.5 * DBF(0, 1, 0, 1, 0), dBLz = 0.5 * DBF(0, 0, 0, 1, 1), dBRz = 0.5 * DBF(0, 1, 0, 1, 1);
+    const double dCLx = 0.5 * DBF(0, 0, 0, 2, 0), dCRx = 0.5 * DBF(0, 0, 1, 2, 0), dCLy = 0.5 * DBF(0, 0, 0, 2, 1), dCRy = 0.5 * DBF(0, 0, 1, 2, 1);
+#define EX(dj, dk) s.Ex[C6(k + (dk), j + (dj), i)]
+#define EY(di, dk) s.Ey[C6(k + (dk), j, i + (di))]
+#define EZ(di, dj) s.Ez[C6(k, j + (dj), i + (di))]
+    const double ELL = EX(0, 0), ELR = EX(0, 1), ERL = EX(1, 0), ERR = EX(1, 1);
+    const double FLL = EY(0, 0), FLR = EY(0, 1), FRL = EY(1, 0), FRR = EY(1, 1);
+    const double GLL = EZ(0, 0), GLR = EZ(0, 1), GRL = EZ(1, 0), GRR = EZ(1, 1);
+    const double sAL0 = +(GLR - GLL) * dtdy * 0.5 - (FLR - FLL) * dtdz * 0.5;
+    const double sAR0 = +(GRR - GRL) * dtdy * 0.5 - (FRR - FRL) * dtdz * 0.5;
+    const double sBL0 = -(GRL - GLL) * dtdx * 0.5 + (ELR - ELL) * dtdz * 0.5;
+    const double sBR0 = -(GRR - GLR) * dtdx * 0.5 + (ERR - ERL) * dtdz * 0.5;
+    const double sCL0 = +(FRL - FLL) * dtdx * 0.5 - (ERL - ELL) * dtdy * 0.5;
+    const double sCR0 = +(FRR - FLR) * dtdx * 0.5 - (ERR - ELR) * dtdy * 0.5;
+    AL = AL + sAL0; AR = AR + sAR0; BL = BL + sBL0; BR = BR + sBR0; CL = CL + sCL0; CR = CR + sCR0;
+    const double sr0 = (-u * drx - dux * r) * dtdx + (-v * dry - dvy * r) * dtdy + (-ww * drz - dwz * r) * dtdz;
+    const double su0 = (-u * dux - (dpx + B * dBx + C * dCx) / r) * dtdx + (-v * duy + B * dAy / r) * dtdy + (-ww * duz + C * dAz / r) * dtdz;
+    const double sv0 = (-u * dvx + A * dBx / r) * dtdx + (-v * dvy - (dpy + A * dAy + C * dCy) / r) * dtdy + (-ww * dvz + C * dBz / r) * dtdz;
+    const double sw0 = (-u * dwx + A * dCx / r) * dtdx + (-v * dwy + B * dCy / r) * dtdy + (-ww * dwz - (dpz + A * dAz + B * dBz) / r) * dtdz;
+    const double sp0 = (-u * dpx - dux * gamma * pp) * dtdx + (-v * dpy - dvy * gamma * pp) * dtdy + (-ww * dpz - dwz * gamma * pp) * dtdz;
+    r = r + sr0; u = u + su0; v = v + sv0; ww = ww + sw0; pp = pp + sp0;
+    A = 0.5 * (AL + AR); B = 0.5 * (BL + BR); C = 0.5 * (CL + CR);
+    const int c4 = C4(k, j, i);
+    auto SET = [&](double (*arr)[MNV][3], int d, double R, double U, double V, double W, double P_, double A_, double B_, double C_) {
+      double(*s_)[3] = arr[c4];
+      s_[0][d] = R; s_[1][d] = U; s_[2][d] = V; s_[3][d] = W; s_[4][d] = P_; s_[5][d] = A_; s_[6][d] = B_; s_[7][d] = C_;
+      if (s_[0][d] < smallr) s_[0][d] = r;
+      s_[4][d] = fmx(smallp, s_[4][d]);
+    };
+    SET(s.qp, 0, r - drx, u - dux, v - dvx, ww - dwx, pp - dpx, AL, B - dBx, C - dCx);
+    SET(s.qm, 0, r + drx, u + dux, v + dvx, ww + dwx, pp + dpx, AR, B + dBx, C + dCx);
+    SET(s.qp, 1, r - dry, u - duy, v - dvy, ww - dwy, pp - dpy, A - dAy, BL, C - dCy);
+    SET(s.qm, 1, r + dry, u + duy, v + dvy, ww + dwy, pp + dpy, A + dAy, BR, C + dCy);
+    SET(s.qp, 2, r - drz, u - duz, v - dvz, ww - dwz, pp - dpz, A - dAz, B - dBz, CL);
+    SET(s.qm, 2, r + drz, u + duz, v + dvz, ww + dwz, pp + dpz, A + dAz, B + dBz, CR);
+    SET(s.qRT, 0, r + (+dry + drz), u + (+duy + duz), v + (+dvy + dvz), ww + (+dwy + dwz), pp + (+dpy + dpz), A + (+dAy + dAz), BR + (+dBRz), CR + (+dCRy));
+    SET(s.qRB, 0, r + (+dry - drz), u + (+duy - duz), v + (+dvy - dvz), ww + (+dwy - dwz), pp + (+dpy - dpz), A + (+dAy - dAz), BR + (-dBRz), CL + (+dCLy));
+    SET(s.qLT, 0, r + (-dry + drz), u + (-duy + duz), v + (-dvy + dvz), ww + (-dwy + dwz), pp + (-dpy + dpz), A + (-dAy + dAz), BL + (+dBLz), CR + (-dCRy));
+    SET(s.qLB, 0, r + (-dry - drz), u + (-duy - duz), v + (-dvy - dvz), ww + (-dwy - dwz), pp + (-dpy - dpz), A + (-dAy - dAz), BL + (-dBLz), CL + (-dCLy));
+    SET(s.qRT, 1, r + (+drx + drz), u + (+dux + duz), v + (+dvx + dvz), ww + (+dwx + dwz), pp + (+dpx + dpz), AR + (+dARz), B + (+dBx + dBz), CR + (+dCRx));
+    SET(s.qRB, 1, r + (+drx - drz), u + (+dux - duz), v + (+dvx - dvz), ww + (+dwx - dwz), pp + (+dpx - dpz), AR + (-dARz), B + (+dBx - dBz), CL + (+dCLx));
+    SET(s.qLT, 1, r + (-drx + drz), u + (-dux + duz), v + (-dvx + dvz), ww + (-dwx + dwz), pp + (-dpx + dpz), AL + (+dALz), B + (-dBx + dBz), CR + (-dCRx));
+    SET(s.qLB, 1, r + (-drx - drz), u + (-dux - duz), v + (-dvx - dvz), ww + (-dwx - dwz), pp + (-dpx - dpz), AL + (-dALz), B + (-dBx - dBz), CL + (-dCLx));
+    SET(s.qRT, 2, r + (+drx + dry), u + (+dux + duy), v + (+dvx + dvy), ww + (+dwx + dwy), pp + (+dpx + dpy), AR + (+dARy), BR + (+dBRx), C + (+dCx + dCy));
+    SET(s.qRB, 2, r + (+drx - dry), u + (+dux - duy), v + (+dvx - dvy), ww + (+dwx - dwy), pp + (+dpx - dpy), AR + (-dARy), BL + (+dBLx), C + (+dCx - dCy));
+    SET(s.qLT, 2, r + (-drx + dry), u + (-dux + duy), v + (-dvx + dvy), ww + (-dwx + dwy), pp + (-dpx + dpy), AL + (+dALy), BR + (-dBRx), C + (-dCx + dCy));
+    SET(s.qLB, 2, r + (-drx - dry), u + (-dux - duy), v + (-dvx - dvy), ww + (-dwx - dwy), pp + (-dpx - dpy), AL + (-dALy), BL + (-dBLx), C + (-dCx - dCy));
+  }
+#undef Q
+#undef BF
+#undef DBF
+#undef EX
+#undef EY
+#undef EZ
+  __syncthreads();
+  // ---- cmpflxm :1308: 3 x 12 faces; cmp_mag_flx :1453: 3 x 18 edges; resets at refined faces / edges :760-879 ----
+  for (int e = tl; e < 36 + 54; e += MHD3_TPO) {
+    if (e < 36) {
+      const int idim = e / 12, f = e % 12;
+      const int i0 = idim == 0, j0 = idim == 1, k0 = idim == 2;
+      const int ni = 2 + i0, nj = 2 + j0;
+      const int i = 1 + f % ni, j = 1 + (f / ni) % nj, k = 1 + f / (ni * nj);
+      const int perm[3][6] = {{2, 3, 4, 6, 7, 8}, {3, 2, 4, 7, 6, 8}, {4, 2, 3, 8, 6, 7}};
+      const int ln = perm[idim][0] - 1, lt1 = perm[idim][1] - 1, lt2 = perm[idim][2] - 1;
+      const int bn = perm[idim][3] - 1, bt1 = perm[idim][4] - 1, bt2 = perm[idim][5] - 1;
+      double(*qm)[3] = s.qm[C4(k - k0, j - j0, i - i0)];
+      double(*qp)[3] = s.qp[C4(k, j, i)];
+      real ql[8], qr[8], fg[9];
+      const double bn_mean = 0.5 * (qm[bn][idim] + qp[bn][idim]);
+      ql[0] = qm[0][idim]; ql[1] = qm[4][idim]; ql[2] = qm[ln][idim]; ql[3] = bn_mean;
+      ql[4] = qm[lt1][idim]; ql[5] = qm[bt1][idim]; ql[6] = qm[lt2][idim]; ql[7] = qm[bt2][idim];
+      qr[0] = qp[0][idim]; qr[1] = qp[4][idim]; qr[2] = qp[ln][idim]; qr[3] = bn_mean;
+      qr[4] = qp[lt1][idim]; qr[5] = qp[bt1][idim]; qr[6] = qp[lt2][idim]; qr[7] = qp[bt2][idim];
+      mhd_riemann1d_rt(a.riemann, P, ql, qr, fg);
+      double* fl = s.flux[idim][F3(k, j, i)];
+      fl[0] = fg[0].v; fl[4] = fg[1].v; fl[ln] = fg[2].v; fl[bn] = fg[3].v; fl[lt1] = fg[4].v; fl[bt1] = fg[5].v; fl[lt2] = fg[6].v; fl[bt2] = fg[7].v;
+      for (int n = 0; n < MNV; n++) fl[n] = fl[n] * dt / dx;
+      if (s.ok[C6(k - k0, j - j0, i - i0)] || s.ok[C6(k, j, i)])
+        for (int n = 0; n < MNV; n++) fl[n] = 0.0;
+      fl[5] = 0.0; fl[6] = 0.0; fl[7] = 0.0;
+    } else {
+      const int g = e - 36, dir = 2 - g / 18, h = g % 18;   // emfz first like the reference (:147-240); the order is immaterial
+      double RT[8], RB[8], LT[8], LB[8];
+      int i, j, k;
+      bool masked;
+      if (dir == 2) {        // k 1..2, j 1..3, i 1..3
+        i = 1 + h % 3; j = 1 + (h / 3) % 3; k = 1 + h / 9;
+        for (int n = 0; n < 8; n++) {
+          RT[n] = s.qRT[C4(k, j - 1, i - 1)][n][2]; RB[n] = s.qRB[C4(k, j, i - 1)][n][2];
+          LT[n] = s.qLT[C4(k, j - 1, i)][n][2];     LB[n] = s.qLB[C4(k, j, i)][n][2];
+        }
+        masked = s.ok[C6(k, j, i)] || s.ok[C6(k, j - 1, i)] || s.ok[C6(k, j, i - 1)] || s.ok[C6(k, j - 1, i - 1)];
+      } else if (dir == 1) { // k 1..3, j 1..2, i 1..3; second and third arguments swapped (:213-218)
+        i = 1 + h % 3; j = 1 + (h / 3) % 2; k = 1 + h / 6;
+        for (int n = 0; n < 8; n++) {
+          RT[n] = s.qRT[C4(k - 1, j, i - 1)][n][1]; RB[n] = s.qLT[C4(k - 1, j, i)][n][1];
+          LT[n] = s.qRB[C4(k, j, i - 1)][n][1];     LB[n] = s.qLB[C4(k, j, i)][n][1];
+        }
+        masked = s.ok[C6(k, j, i)] || s.ok[C6(k - 1, j, i)] || s.ok[C6(k, j, i - 1)] || s.ok[C6(k - 1, j, i - 1)];
+      } else {               // k 1..3, j 1..3, i 1..2
+        i = 1 + h % 2; j = 1 + (h / 2) % 3; k = 1 + h / 6;
+        for (int n = 0; n < 8; n++) {
+          RT[n] = s.qRT[C4(k - 1, j - 1, i)][n][0]; RB[n] = s.qRB[C4(k, j - 1, i)][n][0];
+          LT[n] = s.qLT[C4(k - 1, j, i)][n][0];     LB[n] = s.qLB[C4(k, j, i)][n][0];
+        }
+        masked = s.ok[C6(k, j, i)] || s.ok[C6(k - 1, j, i)] || s.ok[C6(k, j - 1, i)] || s.ok[C6(k - 1, j - 1, i)];
+      }
+      double ez = mhd_emf_rt(a.riemann2d, P, RT, RB, LT, LB, dir) * dt / dx;
+      if (masked) ez = 0.0;
+      s.emf[dir][F3(k, j, i)] = ez;
+    }
+  }
+  __syncthreads();
+  // ---- update of the oct's own cells: Euler system x, y, z (:886-934), then constrained transport (:939-995) ----
+#define RX(i3, j3, k3) s.emf[0][F3(k3, j3, i3)]
+#define RY(i3, j3, k3) s.emf[1][F3(k3, j3, i3)]
+#define RZ(i3, j3, k3) s.emf[2][F3(k3, j3, i3)]
+  for (int e = tl; e < 8 * MNVS; e += MHD3_TPO) {
+    const int is = e % 8, iv = e / 8;
+    const int i3 = 1 + (is & 1), j3 = 1 + ((is >> 1) & 1), k3 = 1 + (is >> 2);
+    const int ic = amr_cell(t, is, igrid);
+    const int src = iv < MNV ? iv : 5 + (iv - MNV);
+    double u = a.unew[(size_t)iv * NC + ic - 1];
+    u = u + (s.flux[0][F3(k3, j3, i3)][src] - s.flux[0][F3(k3, j3, i3 + 1)][src]);
+    u = u + (s.flux[1][F3(k3, j3, i3)][src] - s.flux[1][F3(k3, j3 + 1, i3)][src]);
+    u = u + (s.flux[2][F3(k3, j3, i3)][src] - s.flux[2][F3(k3 + 1, j3, i3)][src]);
+    if (iv == 5) u = u + ((RY(i3, j3, k3) - RY(i3, j3, k3 + 1)) - (RZ(i3, j3, k3) - RZ(i3, j3 + 1, k3)));
+    if (iv == MNV + 0) u = u + ((RY(i3 + 1, j3, k3) - RY(i3 + 1, j3, k3 + 1)) - (RZ(i3 + 1, j3, k3) - RZ(i3 + 1, j3 + 1, k3)));
+    if (iv == 6) u = u + ((RZ(i3, j3, k3) - RZ(i3 + 1, j3, k3)) - (RX(i3, j3, k3) - RX(i3, j3, k3 + 1)));
+    if (iv == MNV + 1) u = u + ((RZ(i3, j3 + 1, k3) - RZ(i3 + 1, j3 + 1, k3)) - (RX(i3, j3 + 1, k3) - RX(i3, j3 + 1, k3 + 1)));
+    if (iv == 7) u = u + ((RX(i3, j3, k3) - RX(i3, j3 + 1, k3)) - (RY(i3, j3, k3) - RY(i3 + 1, j3, k3)));
+    if (iv == MNV + 2) u = u + ((RX(i3, j3, k3 + 1) - RX(i3, j3 + 1, k3 + 1)) - (RY(i3, j3, k3 + 1) - RY(i3 + 1, j3, k3 + 1)));
+    a.unew[(size_t)iv * NC + ic - 1] = u;
+  }
+#undef RX
+#undef RY
+#undef RZ
+  // ---- outer-face fluxes [side][face = j/k fastest-first transverse index][8] and all 54 edge EMFs for the coarse refluxing ----
+  for (int e = tl; e < 6 * 4 * MNV; e += MHD3_TPO) {
+    const int n = e % MNV, fs = (e / MNV) % 4, side = e / (4 * MNV);
+    const int idim = side / 2, right = side % 2;
+    const int a0 = fs & 1, a1 = fs >> 1;   // transverse face coordinates, lower dimension first (the loop order k3, j3, i3 of :1030-1168)
+    int i3, j3, k3;
+    if (idim == 0) { i3 = right ? 3 : 1; j3 = 1 + a0; k3 = 1 + a1; }
+    else if (idim == 1) { j3 = right ? 3 : 1; i3 = 1 + a0; k3 = 1 + a1; }
+    else { k3 = right ? 3 : 1; i3 = 1 + a0; j3 = 1 + a1; }
+    a.rflux[(((size_t)io * 6 + side) * 4 + fs) * MNV + n] = s.flux[idim][F3(k3, j3, i3)][n];
+  }
+  for (int e = tl; e < 81; e += MHD3_TPO) a.remf[(size_t)io * 81 + e] = s.emf[e / 27][e % 27];
+#undef X_
+#undef C6
+#undef C7
+#undef C4
+#undef F3
+}
+
+// coarse refluxing of the edge EMFs, NDIM = 3 (:1176-1455): per target (cell, variable) the contributions
+// (emf(c0) + emf(c1)) * 0.25 * weight [* 0.5], code = oct << 7 | edge (0..11) << 3 | (weight 0.5 ? 4 : 0) | (half ? 2 : 0) | (minus ? 1 : 0)
+struct MhdEdge3 { signed char dir, c0, c1; };   // c = (k3-1)*9 + (j3-1)*3 + (i3-1) of the two emf entries of the edge
+struct Emf3RefluxArgs {
+  int nent;
+  const int* cell; const int* var; const int* start; const int* code;
+  const double* remf;  // [nact][3][27]
+  double* unew;
+  long long ncell;
+  signed char edir[12], ec0[12], ec1[12];
+};
+__global__ void mhd_amr_emf3_reflux_kernel(const Emf3RefluxArgs a) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.nent) return;
+  const size_t idx = (size_t)a.var[e] * a.ncell + a.cell[e] - 1;
+  double u = a.unew[idx];
+  for (int k = a.start[e]; k < a.start[e + 1]; k++) {
+    const int c = a.code[k];
+    const int oct = c >> 7, edge = (c >> 3) & 15;
+    const double weight = (c & 4) ? 0.5 : 1.0;
+    const double* em = a.remf + (size_t)oct * 81 + (size_t)a.edir[edge] * 27;
+    const double dflux = (em[a.ec0[edge]] + em[a.ec1[edge]]) * 0.25 * weight;
+    const double v = (c & 2) ? dflux * 0.5 : dflux;
+    if (c & 1) u = u - v; else u = u + v;
+  }
+  a.unew[idx] = u;
+}
+
 // coarse refluxing of the Euler fluxes (mhd/godunov_fine.f90:1030-1168): same schedule as the hydro pass (RefluxArgs: target
 // cells with their contributions (oct, side, face) in the reference's visiting order); variables 1..nvar take the fluxes
 // 1..nvar, nvar+1..nvar+3 the fluxes 6..8

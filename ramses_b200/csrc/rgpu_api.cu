@@ -962,21 +962,25 @@ int amr_zero_ghost_unew(AmrLevel& A) {   // set_unew: unew (and divu, enew) = 0 
 
 // ---- ideal MHD in AMR mode, NDIM = 1, 2 (mhd_amr.cuh) -----------------------------------------------------------------------
 int mhd_amr_bind_extra(AmrLevel& A, int ilevel, int ngrid_active, const int* igrid_active) {
-  if (G.p.ndim != 2 || ngrid_active == 0) return RGPU_OK;
-  CUDA_OK(cudaMalloc(&A.d_remf, sizeof(double) * 4 * (size_t)ngrid_active));
-  // the 3x3 father cells of every oct (device tree walk), then the schedule on the host in the reference's visiting order:
-  // batch of nvector octs -> edge X0Y0, X0Y1, X1Y1, X1Y0 -> oct of the batch -> the statements of :1196-1268
-  std::vector<int> nfc((size_t)ngrid_active * 9);
+  (void)igrid_active;
+  if (G.p.ndim == 1 || ngrid_active == 0) return RGPU_OK;
+  const int nd = G.p.ndim, N3 = nd == 2 ? 9 : 27, nemf = nd == 2 ? 4 : 81;
+  CUDA_OK(cudaMalloc(&A.d_remf, sizeof(double) * nemf * (size_t)ngrid_active));
+  // the 3^ndim father cells of every oct (device tree walk), then the schedule on the host in the reference's visiting order:
+  // batch of nvector octs -> edge -> oct of the batch -> the statements of the edge (amr_schedules.h)
+  std::vector<int> nfc((size_t)ngrid_active * N3);
   int* d_nfc = nullptr;
   CUDA_OK(cudaMalloc(&d_nfc, sizeof(int) * nfc.size()));
-  amr_nfc_kernel<2><<<(ngrid_active + 127) / 128, 128, 0, G.stream>>>(amr_tree(), A.d_active, ngrid_active, ilevel, d_nfc);
+  if (nd == 2) amr_nfc_kernel<2><<<(ngrid_active + 127) / 128, 128, 0, G.stream>>>(amr_tree(), A.d_active, ngrid_active, ilevel, d_nfc);
+  else amr_nfc_kernel<3><<<(ngrid_active + 127) / 128, 128, 0, G.stream>>>(amr_tree(), A.d_active, ngrid_active, ilevel, d_nfc);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(nfc.data(), d_nfc, sizeof(int) * nfc.size(), cudaMemcpyDeviceToHost, G.stream));
   CUDA_OK(cudaStreamSynchronize(G.stream));
   cudaFree(d_nfc);
-  if (ngrid_active >= (1 << 26)) return fail(RGPU_EUNSUPPORTED, "too many octs for the packed EMF reflux schedule");
+  if (ngrid_active >= (1 << 24)) return fail(RGPU_EUNSUPPORTED, "too many octs for the packed EMF reflux schedule");
   std::vector<int> cells, vars, start, codes;
-  build_emf_schedule_2d(G.p.nvector, ngrid_active, nfc.data(), G.son, cells, vars, start, codes);
+  if (nd == 2) build_emf_schedule_2d(G.p.nvector, ngrid_active, nfc.data(), G.son, cells, vars, start, codes);
+  else build_emf_schedule_3d(G.p.nvector, ngrid_active, nfc.data(), G.son, cells, vars, start, codes);
   A.nemf = (int)cells.size();
   if (A.nemf > 0) {
     CUDA_OK(cudaMalloc(&A.d_ecell, sizeof(int) * cells.size()));
@@ -998,7 +1002,12 @@ int mhd_amr_godunov(AmrLevel& A, int ilevel, double dt, const double* dt_dev) {
   a.interpol_type = G.interpol_type; a.interpol_mag_type = G.interpol_mag_type < 0 ? G.interpol_type : G.interpol_mag_type;
   a.riemann = G.p.riemann; a.riemann2d = G.p.riemann2d;
   if (G.p.ndim == 1) mhd_amr1_godfine_kernel<<<(A.nact + 63) / 64, 64, 0, G.stream>>>(a);
-  else mhd_amr2_godfine_kernel<<<A.nact, MHD2_TPO, 0, G.stream>>>(a);
+  else if (G.p.ndim == 2) mhd_amr2_godfine_kernel<<<A.nact, MHD2_TPO, 0, G.stream>>>(a);
+  else {
+    static bool attr = false;
+    if (!attr) { CUDA_OK(cudaFuncSetAttribute(mhd_amr3_godfine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Mhd3Sm))); attr = true; }
+    mhd_amr3_godfine_kernel<<<A.nact, MHD3_TPO, sizeof(Mhd3Sm), G.stream>>>(a);
+  }
   CUDA_OK(cudaGetLastError());
   A.launches++;
   if (A.nent > 0) {   // Euler fluxes into the coarser level (:1030-1168)
@@ -1012,10 +1021,23 @@ int mhd_amr_godunov(AmrLevel& A, int ilevel, double dt, const double* dt_dev) {
     A.launches++;
   }
   if (A.nemf > 0) {   // corner EMFs into the coarser level (:1176-1270)
+    if (G.p.ndim == 3) {
+      Emf3RefluxArgs r{};
+      r.nent = A.nemf; r.cell = A.d_ecell; r.var = A.d_evar; r.start = A.d_estart; r.code = A.d_ecode; r.remf = A.d_remf; r.unew = G.d_unew;
+      r.ncell = G.ncell;
+      const MhdEdge3Host* E = mhd_edges3();
+      for (int e = 0; e < 12; e++) {
+        r.edir[e] = (signed char)E[e].dir;
+        r.ec0[e] = (signed char)(((E[e].c[0][2] - 1) * 3 + (E[e].c[0][1] - 1)) * 3 + (E[e].c[0][0] - 1));
+        r.ec1[e] = (signed char)(((E[e].c[1][2] - 1) * 3 + (E[e].c[1][1] - 1)) * 3 + (E[e].c[1][0] - 1));
+      }
+      mhd_amr_emf3_reflux_kernel<<<(A.nemf + 127) / 128, 128, 0, G.stream>>>(r);
+    } else {
     EmfRefluxArgs r{};
     r.nent = A.nemf; r.cell = A.d_ecell; r.var = A.d_evar; r.start = A.d_estart; r.code = A.d_ecode; r.remf = A.d_remf; r.unew = G.d_unew;
     r.ncell = G.ncell;
     mhd_amr_emf_reflux_kernel<<<(A.nemf + 127) / 128, 128, 0, G.stream>>>(r);
+    }
     CUDA_OK(cudaGetLastError());
     A.launches++;
   }
@@ -1266,11 +1288,9 @@ int rgpu_finalize(void) {
 
 int rgpu_set_amr(int on, int interpol_type, int interpol_var) {
   if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
-  if (on && G.p.mhd && G.p.ndim == 3)
-    return fail(RGPU_EUNSUPPORTED, "MHD build, NDIM=3: AMR mode (divergence-free prolongation, EMF refluxing on 12 edges) not supported; levelmin=levelmax only");
   if (on && G.p.mhd && interpol_var != 0) return fail(RGPU_EUNSUPPORTED, "MHD build: interpol_var=%d not supported (0 only)", interpol_var);
   if (on && G.p.mhd && !(G.p.slope_type >= 0 && G.p.slope_type <= 2))
-    return fail(RGPU_EUNSUPPORTED, "MHD AMR mode (NDIM=1,2): slope_type=%d not supported (0, 1, 2)", G.p.slope_type);
+    return fail(RGPU_EUNSUPPORTED, "MHD AMR mode: slope_type=%d not supported (0, 1, 2)", G.p.slope_type);
   if (on && (interpol_var < 0 || interpol_var > 2)) return fail(RGPU_EINVAL, "interpol_var=%d (0, 1 or 2: hydro/interpol_hydro.f90:318-345)", interpol_var);
   if (on && (interpol_type < 0 || interpol_type > 4)) return fail(RGPU_EINVAL, "interpol_type=%d (0..4)", interpol_type);
   if (on && interpol_type == 4 && interpol_var != 2)

@@ -391,7 +391,7 @@ void devnum_mhd_amr_godunov(int ndim, int ncoarse, int ngridmax, int nx, int ny,
   a.t.son = son - 1; a.t.father = father - 1; a.t.nbor = nbor; a.t.ncoarse = ncoarse; a.t.ngridmax = ngridmax;
   a.t.nx = nx; a.t.ny = ny; a.t.nz = nz; a.t.ncell = (long long)ncoarse + (long long)(1 << ndim) * ngridmax;
   const int TW = 2 * ndim, NSF = 1 << (ndim - 1);
-  std::vector<double> rflux((size_t)std::max(1, nact) * TW * NSF * MNV, 0.0), remf((size_t)std::max(1, nact) * 4, 0.0);
+  std::vector<double> rflux((size_t)std::max(1, nact) * TW * NSF * MNV, 0.0), remf((size_t)std::max(1, nact) * (ndim == 3 ? 81 : 4), 0.0);
   a.active = active; a.nact = nact; a.ilevel = ilevel; a.uold = uold; a.unew = unew; a.rflux = rflux.data(); a.remf = remf.data();
   a.P = make_mphys(gamma, smallr, smallc);
   a.P.slope_type = slope_type; a.P.slope_mag_type = slope_mag_type;
@@ -399,7 +399,8 @@ void devnum_mhd_amr_godunov(int ndim, int ncoarse, int ngridmax, int nx, int ny,
   a.interpol_type = interpol_type; a.interpol_mag_type = interpol_mag_type < 0 ? interpol_type : interpol_mag_type;
   a.riemann = riemann; a.riemann2d = riemann2d;
   if (ndim == 1) emulate_serial(mhd_amr1_godfine_kernel, a, (nact + 63) / 64, 64);
-  else emulate_launch(mhd_amr2_godfine_kernel, a, nact, MHD2_TPO);
+  else if (ndim == 2) emulate_launch(mhd_amr2_godfine_kernel, a, nact, MHD2_TPO);
+  else emulate_launch(mhd_amr3_godfine_kernel, a, nact, MHD3_TPO, 1, sizeof(Mhd3Sm) / sizeof(double) + 1);
   std::vector<int> cells, start, srcs, src;
   build_reflux_schedule(ndim, nvector, nact, active, nbor, son, ngridmax, cells, start, srcs, src);
   if (!cells.empty()) {
@@ -424,6 +425,29 @@ void devnum_mhd_amr_godunov(int ndim, int ncoarse, int ngridmax, int nx, int ny,
       r.nent = (int)ec.size(); r.cell = ec.data(); r.var = ev.data(); r.start = es.data(); r.code = ecode.data(); r.remf = remf.data();
       r.unew = unew; r.ncell = a.t.ncell;
       emulate_serial(mhd_amr_emf_reflux_kernel, r, (r.nent + 127) / 128, 128);
+    }
+  }
+  if (ndim == 3 && nact > 0) {
+    std::vector<int> nfc((size_t)nact * 27);
+    for (int i = 0; i < nact; i++) {
+      int f[27], ng[8];
+      amr_get3cubefather<3>(a.t, active[i], ilevel, f, ng);
+      for (int j = 0; j < 27; j++) nfc[(size_t)i * 27 + j] = f[j];
+    }
+    std::vector<int> ec, ev, es, ecode;
+    build_emf_schedule_3d(nvector, nact, nfc.data(), son, ec, ev, es, ecode);
+    if (!ec.empty()) {
+      Emf3RefluxArgs r;
+      std::memset(&r, 0, sizeof r);
+      r.nent = (int)ec.size(); r.cell = ec.data(); r.var = ev.data(); r.start = es.data(); r.code = ecode.data(); r.remf = remf.data();
+      r.unew = unew; r.ncell = a.t.ncell;
+      const MhdEdge3Host* E = mhd_edges3();
+      for (int e = 0; e < 12; e++) {
+        r.edir[e] = (signed char)E[e].dir;
+        r.ec0[e] = (signed char)(((E[e].c[0][2] - 1) * 3 + (E[e].c[0][1] - 1)) * 3 + (E[e].c[0][0] - 1));
+        r.ec1[e] = (signed char)(((E[e].c[1][2] - 1) * 3 + (E[e].c[1][1] - 1)) * 3 + (E[e].c[1][0] - 1));
+      }
+      emulate_serial(mhd_amr_emf3_reflux_kernel, r, (r.nent + 127) / 128, 128);
     }
   }
 }

@@ -731,6 +731,80 @@ def test_mhd_amr_2d_kernels_emulated_on_the_cpu_equal_oracle(orc, dev, r1, r2, s
     assert nlev >= 3 and nrefl > 0 and moved > 1e-6
 
 
+def _mhd3_static_run(riemann, riemann2d, slope_type, lmin=3, lmax=5):
+    """MhdAmrRun3D on a statically nested cube (levels lmin..lmax) with a genuinely three-dimensional, divergence-free state:
+    the z-invariant Orszag-Tang fields + a B_z(x,y) component + z-dependent density and velocities, advanced by two sub-cycled
+    coarse steps of the oracle so that every component of every face field and EMF is at work"""
+    from oracle.amr_mhd import MhdAmrRun3D
+
+    class Run(MhdAmrRun3D):
+        def smooth_fine(self, l):
+            pass
+
+        def hydro_flag(self, l):
+            if l == self.nlevelmax or self.numbtot(l) == 0:
+                return
+            hw = {lmin: 0.25, lmin + 1: 0.125}.get(l, 0.0)
+            igs = np.asarray(self.active[l])
+            dx = 0.5 ** l
+            for ind in range(8):
+                x = [self.xg[k, igs] + (((ind >> k) & 1) - 0.5) * dx for k in range(3)]
+                inside = (np.abs(x[0] - 0.5) < hw) & (np.abs(x[1] - 0.4) < hw) & (np.abs(x[2] - 0.6) < hw)
+                self.flag1[self.ncoarse + ind * self.ngridmax + igs[inside]] = 1
+
+        def init_flow_fine(self, l):
+            super().init_flow_fine(l)
+            if self.numbtot(l) == 0:
+                return
+            U = self.uold.reshape(11, self.ncell)
+            igs = np.asarray(self.active[l])
+            dx = 0.5 ** l
+            tp = 2 * np.pi
+            for ind in range(8):
+                x, y, z = [self.xg[k, igs] + (((ind >> k) & 1) - 0.5) * dx for k in range(3)]
+                c = self.ncoarse + ind * self.ngridmax + igs - 1
+                # B_z(x,y) as the exact average over the cell's (x,y) footprint: both z faces equal (d/dz = 0) and a coarse face
+                # equals the mean of the four fine faces it covers, on every level: div B = 0 to round-off
+                sx = (np.cos(tp * (x - 0.5 * dx)) - np.cos(tp * (x + 0.5 * dx))) / (tp * dx)
+                cy = (np.sin(tp * (y + 0.5 * dx)) - np.sin(tp * (y - 0.5 * dx))) / (tp * dx)
+                bz = 0.2 + 0.3 * sx * cy
+                d0 = U[0, c].copy()
+                vel = [U[1 + k, c] / d0 for k in range(3)]
+                eint = U[4, c] - 0.5 * d0 * sum(v * v for v in vel) - 0.125 * sum((U[5 + k, c] + U[8 + k, c]) ** 2 for k in range(3))
+                d = d0 * (1 + 0.3 * np.sin(tp * z) * np.cos(tp * x))
+                vel[0] = vel[0] + 0.2 * np.sin(tp * z)
+                vel[1] = vel[1] - 0.15 * np.cos(tp * z + 1.0)
+                vel[2] = 0.3 * np.sin(tp * (x + y)) * np.cos(tp * z)
+                U[7, c] = bz; U[10, c] = bz
+                U[0, c] = d
+                for k in range(3):
+                    U[1 + k, c] = d * vel[k]
+                U[4, c] = eint + 0.5 * d * sum(v * v for v in vel) + 0.125 * sum((U[5 + k, c] + U[8 + k, c]) ** 2 for k in range(3))
+    r = Run(lmin, lmax, 1.0, nsubcycle=[1, 2], riemann=riemann, riemann2d=riemann2d, slope_type=slope_type, gamma=1.6666667, courant_factor=0.8,
+            err_grad_p=0.1, interpol_type=2, tout=[1e9], nexpand=1, ngridmax=4000)
+    r.flag_coarse(); r.init_refine(); r.init_refine_2()
+    r.static = True
+    for _ in range(2):
+        r.amr_step(lmin, 1)
+        r.nstep_coarse += 1
+    return r
+
+
+@pytest.mark.parametrize("r1,r2,slope_type", [("hlld", "hlld", 2), ("roe", "llf", 1), ("llf", "roe", 0), ("hll", "hlla", 2)])
+def test_mhd_amr_3d_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, r1, r2, slope_type):
+    """NDIM=3 ideal MHD with AMR: mhd_amr3_godfine_kernel (128 cooperating threads per oct, the 6^3 patch and every intermediate of
+    mag_unsplit in 155 KB of shared memory: 36 face and 54 edge Riemann problems, 3-D divergence-free prolongation of the ghost
+    octs, constrained transport) + the Euler and twelve-edge EMF coarse refluxes, upload_fine and cmpdt, executed by the emulated
+    launch on a nested three-level mesh with a fully three-dimensional field, against mhd3_godfine1 & co. of the oracle."""
+    r = _mhd3_static_run(r1, r2, slope_type)
+    assert [len(r.active[l]) for l in (3, 4, 5)] == [64, 64, 64]
+    assert r.divb_max() < 1e-13
+    L = orc.lib()
+    nlev, nrefl, moved = _mhd_amr_compare_levels(orc, dev, r, 3, r1, r2, slope_type, 2, L.orc_mhd3_godunov_fine, L.orc_mhdn_upload_fine,
+                                                 L.orc_mhdn_courant_fine)
+    assert nlev == 3 and nrefl > 0 and moved > 1e-6
+
+
 def _to_slots(dense, N):
     """dense [11][z][y][x] -> device layout [11][8][nslot] (cell_offset of sweep_dense.cuh, periodic cube, no ghost shell)"""
     h = N // 2

@@ -238,13 +238,13 @@ def _mhd_commons_from_run(r, ndim, riemann, riemann2d, slope_type):
     return a
 
 
-def _mhd_amr_gpu_vs_oracle(r, ndim, riemann, riemann2d, slope_type, ncoarse, resident):
+def _mhd_amr_gpu_vs_oracle(r, ndim, riemann, riemann2d, slope_type, ncoarse, resident, regrid=True):
     """ncoarse coarse steps (with sub-cycling) of the frozen mesh of run `r` on the device -- host-driven amr_step order or the
     device-resident stepper -- against the oracle's amr_step: every active cell of every level, and dtnew(levelmin)"""
     from ramses_b200.hydro import amr_step
     levelmin, levelmax = r.levelmin, r.nlevelmax
     # regrid once more like the head of amr_step, then freeze the mesh (tests/test_gpu_amr.py::run_case)
-    for i in range(levelmin, levelmax + 1):
+    for i in range(levelmin, levelmax + 1 if regrid else levelmin):
         if i > levelmin:
             r.make_boundary_hydro(i)
         r.refine_fine(i)
@@ -318,8 +318,21 @@ def test_mhd_amr_2d_orszag_tang_bitwise(orc, r1, r2, slope_type, resident):
     assert r.divb_max() < 5e-14
 
 
+@pytest.mark.parametrize("r1,r2,slope_type,resident", [("hlld", "hlld", 2, False), ("roe", "llf", 1, True), ("llf", "roe", 0, False)])
+def test_mhd_amr_3d_nested_mesh_bitwise(orc, r1, r2, slope_type, resident):
+    """NDIM=3 ideal MHD with AMR on the device: two sub-cycled coarse steps (1+2+4 level steps) of a three-level nested mesh with a
+    fully three-dimensional divergence-free field -- 3-D divergence-free prolongation, 36 face / 54 edge Riemann problems per oct,
+    constrained transport, Euler and twelve-edge EMF refluxing, face-centred restriction -- == the oracle (whose NDIM=3 AMR routines
+    are tied to the golden-pinned NDIM=2 code by test_3d_amr_mhd_equals_golden_pinned_2d_on_embedded_problem), bit for bit."""
+    from test_device_numerics_host import _mhd3_static_run
+    r = _mhd3_static_run(r1, r2, slope_type)
+    nlev = _mhd_amr_gpu_vs_oracle(r, 3, r1, r2, slope_type, 2, resident, regrid=False)
+    assert nlev[2:] == [64, 64, 64]
+    assert r.divb_max() < 1e-13
+
+
 def test_mhd_low_dimensional_builds_need_amr_mode(orc):
-    """NDIM=1,2 MHD is built in AMR mode only: the dense path refuses; NDIM=3 AMR mode refuses."""
+    """NDIM=1,2 MHD is built in AMR mode only: the dense path refuses."""
     from ramses_b200 import lib as _l
     from oracle.amr_mhd import MhdAmrRun2D
     r = MhdAmrRun2D(3, 3, 1.0, nsubcycle=[1], riemann="llf", riemann2d="llf", slope_type=1, tout=[1e9], ngridmax=2000)
