@@ -185,6 +185,11 @@ struct Context {
   long long ncell = 0;
   int interpol_type = 1, interpol_var = 0;
   int interpol_mag_type = -1;        // -1: interpol_type (hydro/read_hydro_params.f90:531)
+  // one coarse step of rgpu_amr_steps as a CUDA graph (single rank, mesh unchanged since the capture): ~200 short launches per
+  // coarse step of a 4-level run replay without per-launch CPU work or inter-kernel launch gaps
+  cudaGraphExec_t amr_graph = nullptr;
+  int amr_graph_levelmin = 0; int amr_graph_nsub[MAXLEVEL + 2] = {0};
+  long long amr_graph_launches[MAXLEVEL + 1] = {0};   // kernel launches per level inside one captured coarse step
   AmrLevel alev[MAXLEVEL + 1];
   double* d_dtn = nullptr; double* d_dto = nullptr;   // device-resident dtnew/dtold(0:MAXLEVEL+1) of rgpu_amr_steps
   int numbtot[MAXLEVEL + 2] = {0};                    // numbtot(1,ilevel): octs of a level over ALL ranks (amr_commons.f90)
@@ -711,6 +716,7 @@ AmrTree amr_tree() {
   return t;
 }
 inline bool src_terms() { return G.p.poisson || G.p.pressure_fix; }
+inline void drop_amr_graph() { if (G.amr_graph) { cudaGraphExecDestroy(G.amr_graph); G.amr_graph = nullptr; } }
 inline double* d_divu() { return G.d_unew + (size_t)G.p.nvar * G.ncell; }
 inline double* d_enew() { return G.d_unew + (size_t)(G.p.nvar + 1) * G.ncell; }
 void free_amr_level(AmrLevel& A) {
@@ -735,6 +741,7 @@ int amr_bind_level(int ilevel, int ngrid_active, const int* igrid_active, int nc
                    const int* ngrid_emit, const int* const* igrid_emit, int nboundary, const int* boundary_type,
                    const int* ngrid_bound, const int* const* igrid_bound) {
   AmrLevel& A = G.alev[ilevel];
+  drop_amr_graph();
   if (A.bound) free_amr_level(A);
   if (ncpu > 1 && ngrid_recv && igrid_recv && ngrid_emit && igrid_emit) {
     const size_t per = (size_t)G.nvn * T_();     // the reverse exchange of unew carries divu and enew too
@@ -1271,6 +1278,7 @@ int rgpu_init(const rgpu_params* p, int myid, int ncpu, int device) {
 int rgpu_finalize(void) {
   if (!G.init) return RGPU_OK;
   cudaStreamSynchronize(G.stream);
+  drop_amr_graph();
   for (int l = 0; l <= MAXLEVEL; l++) if (G.lev[l].bound) free_level(G.lev[l]);
   for (int l = 0; l <= MAXLEVEL; l++) if (G.alev[l].bound) free_amr_level(G.alev[l]);
   cudaFree(G.d_son_base); cudaFree(G.d_father); cudaFree(G.d_nbor); cudaFree(G.d_uold); cudaFree(G.d_unew); cudaFree(G.d_force); G.d_force = nullptr; cudaFree(G.d_dtn); cudaFree(G.d_dto); cudaFree(G.d_numb);
@@ -1295,6 +1303,7 @@ int rgpu_set_amr(int on, int interpol_type, int interpol_var) {
   if (on && (interpol_type < 0 || interpol_type > 4)) return fail(RGPU_EINVAL, "interpol_type=%d (0..4)", interpol_type);
   if (on && interpol_type == 4 && interpol_var != 2)
     return fail(RGPU_EINVAL, "interpol_type=4 (central slopes for the velocities) is designed for interpol_var=2 (hydro/interpol_hydro.f90:357-366)");
+  drop_amr_graph();
   G.amr = on != 0;
   G.interpol_type = interpol_type; G.interpol_var = interpol_var;
   return RGPU_OK;
@@ -1304,6 +1313,7 @@ int rgpu_bind_tree(int ncoarse, int ngridmax, const int* son, const int* father,
   if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
   if (!son || !father || !nbor) return fail(RGPU_EINVAL, "null tree array");
   if (ncoarse != G.p.nx * G.p.ny * G.p.nz) return fail(RGPU_EINVAL, "ncoarse=%d != nx*ny*nz", ncoarse);
+  drop_amr_graph();
   G.ncoarse = ncoarse; G.ngridmax = ngridmax; G.son = son; G.father = father; G.nbor = nbor;
   if (G.amr) {   // mirror the tree (read-only during a step; re-bind after every regrid)
     const long long ncell = (long long)ncoarse + (long long)T_() * ngridmax;
@@ -2214,9 +2224,39 @@ int rgpu_amr_steps(int levelmin, const int* nsubcycle, int ncoarse_steps, double
   double* d_hist = nullptr;
   CUDA_OK(cudaMalloc(&d_hist, sizeof(double) * ncoarse_steps));
   CUDA_OK(cudaEventRecord(G.ev2, G.stream));
+  // Graph replay: single rank, no timing instrumentation; the first step of a call always runs eagerly (it also performs the
+  // one-time cudaFuncSetAttribute calls), the second is captured, the rest replay.  RGPU_AMR_GRAPH=0 disables.
+  static int graph_env = -1;
+  if (graph_env < 0) { const char* e = getenv("RGPU_AMR_GRAPH"); graph_env = e ? atoi(e) : 1; }
+  const bool graph_ok = graph_env != 0 && !(G.comm && G.nranks > 1) && !G.timing;
+  if (G.amr_graph) {   // captured for another levelmin / nsubcycle?
+    bool same = G.amr_graph_levelmin == levelmin;
+    for (int l = levelmin; l <= G.p.nlevelmax && same; l++) same = G.amr_graph_nsub[l] == nsubcycle[l - 1];
+    if (!same) drop_amr_graph();
+  }
   for (int s = 0; s < ncoarse_steps; s++) {
-    const int rc = amr_step_dev(levelmin, 1, levelmin, nsubcycle);
-    if (rc) { cudaFree(d_hist); return rc; }
+    if (graph_ok && s > 0 && !G.amr_graph) {
+      long long before[MAXLEVEL + 1];
+      for (int l = 0; l <= MAXLEVEL; l++) before[l] = G.alev[l].launches;
+      cudaGraph_t g = nullptr;
+      CUDA_OK(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = amr_step_dev(levelmin, 1, levelmin, nsubcycle);
+      const cudaError_t ce = cudaStreamEndCapture(G.stream, &g);
+      if (rc || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); cudaFree(d_hist); return rc ? rc : fail(RGPU_ECUDA, "graph capture of the coarse step: %s", cudaGetErrorString(ce)); }
+      const cudaError_t ie = cudaGraphInstantiate(&G.amr_graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ie != cudaSuccess) { G.amr_graph = nullptr; cudaFree(d_hist); return fail(RGPU_ECUDA, "graph instantiation: %s", cudaGetErrorString(ie)); }
+      for (int l = 0; l <= MAXLEVEL; l++) { G.amr_graph_launches[l] = G.alev[l].launches - before[l]; G.alev[l].launches = before[l]; }
+      G.amr_graph_levelmin = levelmin;
+      for (int l = levelmin; l <= G.p.nlevelmax; l++) G.amr_graph_nsub[l] = nsubcycle[l - 1];
+    }
+    if (graph_ok && s > 0 && G.amr_graph) {
+      CUDA_OK(cudaGraphLaunch(G.amr_graph, G.stream));
+      for (int l = 0; l <= MAXLEVEL; l++) G.alev[l].launches += G.amr_graph_launches[l];
+    } else {
+      const int rc = amr_step_dev(levelmin, 1, levelmin, nsubcycle);
+      if (rc) { cudaFree(d_hist); return rc; }
+    }
     CUDA_OK(cudaMemcpyAsync(d_hist + s, G.d_dtn + levelmin, sizeof(double), cudaMemcpyDeviceToDevice, G.stream));
   }
   CUDA_OK(cudaEventRecord(G.ev3, G.stream));
@@ -2268,6 +2308,7 @@ int rgpu_hydro_flag(int ilevel, const double err_grad[3], const double floor[3],
 int rgpu_set_interpol_mag(int interpol_mag_type) {
   if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
   if (interpol_mag_type < -1 || interpol_mag_type > 3) return fail(RGPU_EINVAL, "interpol_mag_type=%d (-1 = interpol_type, 0..3)", interpol_mag_type);
+  drop_amr_graph();
   G.interpol_mag_type = interpol_mag_type;
   return RGPU_OK;
 }
@@ -2275,6 +2316,7 @@ int rgpu_set_boundary_var(int ibound, const double* var) {
   if (!G.init) return fail(RGPU_EINVAL, "rgpu_init has not been called");
   if (ibound < 1 || ibound > 64 || !var) return fail(RGPU_EINVAL, "ibound=%d (1..64) / null var", ibound);
   if (G.p.mhd) return fail(RGPU_EUNSUPPORTED, "MHD build: imposed boundaries not supported");
+  drop_amr_graph();
   for (int iv = 0; iv < G.p.nvar && iv < 8; iv++) G.bvar[ibound - 1][iv] = var[iv];
   G.bvar_set[ibound - 1] = true;
   return RGPU_OK;

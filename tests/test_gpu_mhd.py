@@ -150,8 +150,12 @@ def test_mhd_rejects_unsupported():
     with pytest.raises(ValueError):
         HydroGPU(a)
     a = c.amr_commons()
+    a.slope_type = 7                               # the AMR-mode MHD kernels cover slope types 0, 1, 2
     with pytest.raises(_l.RgpuError):
         HydroGPU(a, amr_mode=True)
+    a = c.amr_commons()
+    with pytest.raises(_l.RgpuError):
+        HydroGPU(a, amr_mode=True, interpol_var=1)  # interpol_var = 0 only in the MHD build
 
 
 def test_mhd_multi_gpu_bit_identical_to_single_gpu():
