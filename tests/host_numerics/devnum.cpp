@@ -296,7 +296,7 @@ void devnum_amr_godfine(int ndim, int solver, int ncoarse, int ngridmax, int nx,
 void devnum_amr_godfine_src(int ndim, int solver, int ncoarse, int ngridmax, int nx, int ny, int nz, const int* son, const int* father,
                             const int* nbor, const int* active, int nact, int ilevel, const double* uold, double* unew, double* rflux,
                             double dt, double dx, int interpol_type, int slope_type, double gamma, double smallr, double smallc,
-                            int niter, const double* force, int pfix) {
+                            int niter, const double* force, int pfix, int nvector_reflux) {
   AmrSweepArgs a;
   std::memset(&a, 0, sizeof a);
   a.t.son = son - 1; a.t.father = father - 1; a.t.nbor = nbor; a.t.ncoarse = ncoarse; a.t.ngridmax = ngridmax;
@@ -318,6 +318,16 @@ void devnum_amr_godfine_src(int ndim, int solver, int ncoarse, int ngridmax, int
   if (ndim == 1) RUN_ND(1); else if (ndim == 2) RUN_ND(2); else RUN_ND(3);
 #undef RUN_ND
 #undef RUN
+  // coarse reflux of the state AND of divu / enew (hydro/godunov_fine.f90:798-908) with the schedule rgpu_api.cu builds at bind time
+  std::vector<int> cells, start, srcs, src;
+  build_reflux_schedule(ndim, nvector_reflux, nact, active, nbor, son, ngridmax, cells, start, srcs, src);
+  if (!cells.empty()) {
+    RefluxArgs r;
+    std::memset(&r, 0, sizeof r);
+    r.nent = (int)cells.size(); r.cell = cells.data(); r.start = start.data(); r.src = srcs.data(); r.rflux = rflux; r.unew = unew;
+    r.ncell = a.t.ncell; r.nvar = a.nvr; r.nsides = 2 * ndim; r.nsf = 1 << (ndim - 1); r.oneontwotondim = 1.0 / (double)(1 << ndim);
+    emulate_serial(amr_reflux_kernel, r, (r.nent * r.nvar + 127) / 128, 128);
+  }
 }
 
 // kind 0: amr_pfix_init_kernel, 1: amr_gravity_src_kernel, 2: amr_pdv_kernel, 3: amr_pfix_switch_kernel -- run thread after thread

@@ -40,7 +40,7 @@ def dev():
     L.devnum_amr_godfine.argtypes = [C.c_int] * 7 + [ip, ip, ip, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_int,
                                      C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double]
     L.devnum_amr_godfine_src.argtypes = [C.c_int] * 7 + [ip, ip, ip, ip, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_int,
-                                         C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, dp, C.c_int]
+                                         C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, dp, C.c_int, C.c_int]
     L.devnum_amr_src_pass.argtypes = [C.c_int] * 7 + [ip, ip, ip, ip, C.c_int, dp, dp, dp, dp, dp] + [C.c_double] * 5
     L.devnum_cmpdt_grav.argtypes = [C.c_int, C.c_int, dp, dp, C.c_double, dp, C.c_double, C.c_double, C.c_double, C.c_double]
     L.devnum_riemann_eflux.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int]
@@ -555,7 +555,7 @@ def test_amr_source_terms_emulated_on_the_cpu_equal_oracle(orc, dev, ndim, solve
     # an arbitrary acceleration field (f is an input of the path): a uniform pull plus cell-to-cell structure, strong enough to matter
     force = np.ascontiguousarray((np.array([0.7, -0.4, 0.3])[:ndim, None] + 0.3 * rng.standard_normal((ndim, nc))) * 5.0)
     beta_fix = 0.5
-    nlev, switched, gmoved, dmax = 0, 0, 0.0, 0.0
+    nlev, switched, gmoved, dmax, nrefl = 0, 0, 0.0, 0.0, 0
     try:
         for l in range(r.levelmin, r.nlevelmax + 1):
             act = np.ascontiguousarray(r.active[l], dtype=np.int32)
@@ -571,7 +571,7 @@ def test_amr_source_terms_emulated_on_the_cpu_equal_oracle(orc, dev, ndim, solve
             L.orc_set_gravity(orc.dptr(force) if grav else None)
             L.orc_set_unew(C.byref(r.p), r.mp, l, orc.dptr(uold_o), orc.dptr(unew_o))
             L.orc_godunov_fine(C.byref(r.p), r.mp, l, dt, orc.dptr(uold_o), orc.dptr(unew_o), 1)
-            divu_mid, enew_mid = divu_o.copy(), enew_o.copy()
+            divu_mid, enew_mid, unew_mid = divu_o.copy(), enew_o.copy(), unew_o.copy()
             L.orc_set_uold(C.byref(r.p), r.mp, l, orc.dptr(uold_o), orc.dptr(unew_o))
             L.orc_set_pressure_fix(None, None, 0.0)
             L.orc_set_gravity(None)
@@ -591,10 +591,14 @@ def test_amr_source_terms_emulated_on_the_cpu_equal_oracle(orc, dev, ndim, solve
             rflux = np.zeros(len(act) * 2 * ndim * (T // 2) * ncol)
             dev.devnum_amr_godfine_src(ndim, sid, r.ncoarse, r.ngridmax, m.nx, m.ny, m.nz, orc.iptr(son), orc.iptr(father), orc.iptr(nbor),
                                        orc.iptr(act), len(act), l, orc.dptr(uold_k), orc.dptr(unew_k), orc.dptr(rflux), dt, dx, itype, st,
-                                       1.4, 1e-10, 1e-10, 10, orc.dptr(force) if grav else None, 1 if pfix else 0)
-            if pfix:   # after the sweep, before the sources: divu / enew of the level's cells
-                assert np.array_equal(divu_k[cells], divu_mid[cells]), l
-                assert np.array_equal(enew_k[cells], enew_mid[cells]), l
+                                       1.4, 1e-10, 1e-10, 10, orc.dptr(force) if grav else None, 1 if pfix else 0, r.nvector)
+            # after the sweep and the coarse reflux pass, before the sources: the WHOLE arrays -- the level's own cells and the coarser
+            # cells that received refluxes (state, and with pressure_fix divu / enew, which reflux like two more variables)
+            assert np.array_equal(unew_k[: nvar * nc], unew_mid), l
+            nrefl += int((unew_mid.reshape(nvar, nc)[:, np.setdiff1d(np.arange(nc), cells)] != 0).any(axis=0).sum())
+            if pfix:
+                assert np.array_equal(divu_k, divu_mid), l
+                assert np.array_equal(enew_k, enew_mid), l
                 dmax = max(dmax, float(np.abs(divu_mid[cells]).max()))
             if grav:
                 dev.devnum_amr_src_pass(1, *args, orc.dptr(uold_k), orc.dptr(unew_k), orc.dptr(divu_k), orc.dptr(enew_k), *tail)
@@ -614,7 +618,7 @@ def test_amr_source_terms_emulated_on_the_cpu_equal_oracle(orc, dev, ndim, solve
     finally:
         L.orc_set_pressure_fix(None, None, 0.0)
         L.orc_set_gravity(None)
-    assert nlev >= 3 and gmoved > 1e-6 and (dmax > 0 or not pfix)
+    assert nlev >= 3 and gmoved > 1e-6 and (dmax > 0 or not pfix) and nrefl > 0
     if pfix and ndim == 3:
         assert switched > 0          # the cold Sedov background (p = 1e-5) does trip the energy switch
 
