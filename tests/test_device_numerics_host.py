@@ -627,7 +627,8 @@ MHD_R1D = {"llf": 0, "roe": 1, "hll": 2, "hlld": 3, "upwind": 4, "hydro": 5}
 MHD_R2D = {"llf": 0, "roe": 1, "upwind": 2, "hll": 3, "hlla": 4, "hlld": 5}
 
 
-def _mhd_amr_compare_levels(orc, dev, r, ndim, riemann, riemann2d, slope_type, interpol_type, godunov, upload, courant, boundary=None):
+def _mhd_amr_compare_levels(orc, dev, r, ndim, riemann, riemann2d, slope_type, interpol_type, godunov, upload, courant, boundary=None,
+                            interpol_mag_type=-1):
     """every populated level of the run `r`: godunov_fine (own cells AND the refluxed coarse cells: the whole unew array),
     upload_fine, the leaf-cell Courant step and (1-D) make_boundary_hydro of the device code == the oracle's, bit for bit"""
     m = r.m
@@ -653,7 +654,7 @@ def _mhd_amr_compare_levels(orc, dev, r, ndim, riemann, riemann2d, slope_type, i
         L.orc_mhdn_set_unew(r.mp, l, orc.dptr(r.uold), orc.dptr(unew_k))
         before = unew_o.copy()
         godunov(C.byref(r.pm), r.mp, l, r.levelmin, r.nvector, dt, orc.dptr(r.uold), orc.dptr(unew_o))
-        dev.devnum_mhd_amr_godunov(*tree[:9], orc.iptr(act), len(act), l, orc.dptr(r.uold), orc.dptr(unew_k), dt, dx, interpol_type, -1,
+        dev.devnum_mhd_amr_godunov(*tree[:9], orc.iptr(act), len(act), l, orc.dptr(r.uold), orc.dptr(unew_k), dt, dx, interpol_type, interpol_mag_type,
                                    MHD_R1D[riemann], MHD_R2D[riemann2d], slope_type, slope_type, r.pm.gamma, r.pm.smallr, r.pm.smallc, r.nvector)
         assert np.isfinite(unew_k).all()
         assert np.array_equal(unew_k, unew_o), (l, np.abs(unew_k - unew_o).max())
@@ -807,6 +808,40 @@ def test_mhd_amr_3d_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, r1, r2, s
     nlev, nrefl, moved = _mhd_amr_compare_levels(orc, dev, r, 3, r1, r2, slope_type, 2, L.orc_mhd3_godunov_fine, L.orc_mhdn_upload_fine,
                                                  L.orc_mhdn_courant_fine)
     assert nlev == 3 and nrefl > 0 and moved > 1e-6
+
+
+@pytest.mark.parametrize("ndim,itype,mtype", [(2, 1, -1), (2, 3, -1), (2, 0, 0), (2, 2, 3), (2, 1, 2), (3, 1, -1), (3, 3, -1), (3, 0, 0), (3, 2, 1),
+                                              (1, 1, -1), (1, 3, -1), (1, 0, -1)])
+def test_mhd_amr_prolongation_variants_emulated_on_the_cpu_equal_oracle(orc, dev, ndim, itype, mtype):
+    """interpol_type 0..3 (cell-centred variables) and interpol_mag_type 0..3 (face fields; -1 = interpol_type) of the ghost-oct
+    prolongation inside the MHD AMR kernels (mhd/interpol_hydro.f90:612-1400): the level update of refined meshes in 1-D / 2-D / 3-D
+    stays bit-identical to the oracle for every limiter choice (the golden runs and the GPU tests use type 2)."""
+    L = orc.lib()
+    L.orc_mhd_set_interpol.argtypes = [C.c_int, C.c_int]
+    if ndim == 1:
+        from oracle.amr_mhd import MhdAmrRun
+        from test_oracle_golden import IMHD
+        r = MhdAmrRun(5, 9, (2, 2, 0, 0, 0, 0), 3.5, nsubcycle=[1, 1, 1, 1], riemann="hlld", slope_type=1, gamma=1.6666667,
+                      courant_factor=0.8, err_grad_d=0.01, err_grad_u=0.05, err_grad_p=0.05, interpol_type=2, regions=IMHD,
+                      tout=[1e9], ngridmax=10000)
+        r.run(max_coarse=10)
+        fns = (L.orc_mhd1_godunov_fine, L.orc_mhd1_upload_fine, L.orc_mhd1_courant_fine)
+    elif ndim == 2:
+        from oracle.amr_mhd import MhdAmrRun2D
+        r = MhdAmrRun2D(4, 6, 1.0, nsubcycle=[1], riemann="hlld", riemann2d="hlld", slope_type=2, gamma=1.6666667, courant_factor=0.8,
+                        err_grad_p=0.1, interpol_type=2, tout=[1e9], nexpand=1, ngridmax=20000)
+        r.run(max_coarse=6)
+        fns = (L.orc_mhd2_godunov_fine, L.orc_mhdn_upload_fine, L.orc_mhdn_courant_fine)
+    else:
+        r = _mhd3_static_run("hlld", "hlld", 2)
+        fns = (L.orc_mhd3_godunov_fine, L.orc_mhdn_upload_fine, L.orc_mhdn_courant_fine)
+    try:
+        L.orc_mhd_set_interpol(itype, mtype)          # the oracle's godfine1 reads these globals (the 1-D path: interpol_type only)
+        nlev, nrefl, moved = _mhd_amr_compare_levels(orc, dev, r, ndim, "hlld", "hlld" if ndim > 1 else "llf", 1 if ndim == 1 else 2, itype, *fns,
+                                                     interpol_mag_type=mtype)
+    finally:
+        L.orc_mhd_set_interpol(2, -1)
+    assert nlev >= 2 and moved > 1e-6
 
 
 def _to_slots(dense, N):
