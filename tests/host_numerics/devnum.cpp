@@ -291,6 +291,27 @@ void devnum_amr_godfine(int ndim, int solver, int ncoarse, int ngridmax, int nx,
 #undef RUN
 }
 
+// godunov_fine of one level with the plain oct-batch kernel: kernel + coarse reflux pass with the bind-time schedule (what
+// rgpu_godunov_fine does in AMR mode).  uold/unew [nvar][ncell], nvar = ndim+2.
+void devnum_amr_godunov(int ndim, int solver, int ncoarse, int ngridmax, int nx, int ny, int nz, const int* son, const int* father,
+                        const int* nbor, const int* active, int nact, int ilevel, const double* uold, double* unew, double dt, double dx,
+                        int interpol_type, int slope_type, double gamma, double smallr, double smallc, int niter, int nvector) {
+  const int nvar = ndim + 2, TW = 2 * ndim, NSF = 1 << (ndim - 1);
+  std::vector<double> rflux((size_t)std::max(1, nact) * TW * NSF * nvar, 0.0);
+  devnum_amr_godfine(ndim, solver, ncoarse, ngridmax, nx, ny, nz, son, father, nbor, active, nact, ilevel, uold, unew, rflux.data(), dt, dx,
+                     interpol_type, slope_type, gamma, smallr, smallc, niter, 0.0);
+  std::vector<int> cells, start, srcs, src;
+  build_reflux_schedule(ndim, nvector, nact, active, nbor, son, ngridmax, cells, start, srcs, src);
+  if (!cells.empty()) {
+    RefluxArgs r;
+    std::memset(&r, 0, sizeof r);
+    r.nent = (int)cells.size(); r.cell = cells.data(); r.start = start.data(); r.src = srcs.data(); r.rflux = rflux.data(); r.unew = unew;
+    r.ncell = (long long)ncoarse + (long long)(1 << ndim) * ngridmax; r.nvar = nvar; r.nsides = TW; r.nsf = NSF;
+    r.oneontwotondim = 1.0 / (double)(1 << ndim);
+    emulate_serial(amr_reflux_kernel, r, (r.nent * nvar + 127) / 128, 128);
+  }
+}
+
 // ---- poisson / pressure_fix (the SRC instantiation of the oct-batch kernel and the list passes of set_unew / set_uold) ------------
 // unew holds nvar+2 columns when pfix (divu, enew behind the state); rflux [nact][2*ndim][2^(ndim-1)][nvar(+2)]
 void devnum_amr_godfine_src(int ndim, int solver, int ncoarse, int ngridmax, int nx, int ny, int nz, const int* son, const int* father,

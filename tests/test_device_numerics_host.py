@@ -1014,7 +1014,7 @@ def test_vec_solvers_equal_scalar(orc, dev, solver):
 @pytest.mark.parametrize("solver,st,N,nblocks,by,vec", [("hllc", 1, 16, 3, 12, 1), ("hllc", 2, 16, 2, 12, 0), ("hllc", 1, 16, 5, 12, 2),
                                                         ("exact", 1, 16, 2, 12, 1), ("llf", 8, 16, 4, 8, 1), ("hll", 7, 16, 3, 16, 1),
                                                         ("acoustic", 3, 16, 3, 12, 1), ("hllc", 1, 32, 7, 12, 1), ("exact", 2, 32, 5, 8, 1),
-                                                        ("hllc", 1, 16, 3, 12, 12), ("hllc", 2, 64, 5, 12, 12), ("exact", 1, 32, 4, 16, 12),
+                                                        ("hllc", 1, 16, 3, 12, 12), ("hllc", 2, 32, 5, 12, 12), ("exact", 1, 32, 4, 16, 12),
                                                         ("hllc", 1, 16, 3, 12, 41), ("hllc", 2, 32, 5, 12, 41), ("exact", 1, 32, 4, 12, 40),
                                                         ("llf", 8, 32, 3, 12, 42), ("hllc", 3, 16, 2, 8, 41)])
 def test_sweep3_kernel_emulated_on_the_cpu_equals_oracle(orc, dev, solver, st, N, nblocks, by, vec):
