@@ -231,3 +231,33 @@ def test_level0_pipeline_plan_host_only(order, ncpu, expect):
     info, slots = plan_level(a, 6)
     assert info.dense == 1
     assert (info.pipeline_slabs >= 3) == expect, info.pipeline_slabs
+
+
+def test_params_struct_mirrors_agree():
+    import os
+    """struct rgpu_params: the C header, the ctypes mirror (ramses_b200/lib.py) and the ISO_C_BINDING type shown to the Fortran
+    maintainer (INTEGRATION.md) list the same fields, in the same order, with the same types."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = open(os.path.join(root, "include", "ramses_gpu.h")).read()
+    body = h[h.index("typedef struct rgpu_params {") + len("typedef struct rgpu_params {"):h.index("} rgpu_params;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = []
+    for stmt in body.split(";"):
+        m = re.match(r"\s*(int|double)\s+(.*)", stmt.strip().replace("\n", " "))
+        if m:
+            c_fields += [(m.group(1), n.strip()) for n in m.group(2).split(",")]
+    from ramses_b200 import lib as _l
+    import ctypes as C
+    py_fields = [("int" if t is C.c_int else "double", n) for n, t in _l.Params._fields_]
+    assert c_fields == py_fields
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    blk = doc[doc.index("type, bind(C) :: rgpu_params"):doc.index("end type")]
+    f_fields = []
+    for line in blk.splitlines()[1:]:
+        line = line.split("!")[0]
+        m = re.match(r"\s*(integer\(c_int\)|real\(c_double\))\s*::\s*(.*)", line)
+        if m:
+            f_fields += [("int" if "integer" in m.group(1) else "double", n.strip()) for n in m.group(2).split(",") if n.strip()]
+    assert f_fields == c_fields
+    assert f"RGPU_ABI_VERSION ({_l.load().rgpu_abi_version()})" in doc
