@@ -261,3 +261,11 @@ def test_params_struct_mirrors_agree():
             f_fields += [("int" if "integer" in m.group(1) else "double", n.strip()) for n in m.group(2).split(",") if n.strip()]
     assert f_fields == c_fields
     assert f"RGPU_ABI_VERSION ({_l.load().rgpu_abi_version()})" in doc
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md (the binding a maintainer adds) mentions every entry point of include/ramses_gpu.h."""
+    import os
+    from ramses_b200 import lib as _l
+    doc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    assert [s for s in _l.exported_symbols() if s not in doc] == []
