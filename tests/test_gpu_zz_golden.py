@@ -121,7 +121,8 @@ def test_implosion_golden_with_gpu_godunov_fine(orc):
     """tests/hydro/implosion: 1049 coarse / 8392 fine steps, levels 5..8, four reflexive walls"""
     from conftest import IMPL, IMPL_BOUND
     from oracle.amr import FastAmrRun, check_sums
-    r = FastAmrRun(2, 5, 8, (1, 1, 1, 1, 0, 0), 1.0, nsubcycle=[2] * 10, nexpand=[4], ngridmax=100000, riemann="hllc",
+    # ngridmax: the run peaks at 6 739 octs (incl. boundary octs); a small array keeps the per-call host<->device traffic small
+    r = FastAmrRun(2, 5, 8, (1, 1, 1, 1, 0, 0), 1.0, nsubcycle=[2] * 10, nexpand=[4], ngridmax=12000, riemann="hllc",
                    slope_type=2, gamma=1.4, courant_factor=0.8, err_grad_d=0.05, err_grad_u=0.05, err_grad_p=0.05,
                    interpol_type=2, interpol_var=0, regions=IMPL, tout=[0.0, 5.0], bound_regions=IMPL_BOUND)
     h, st = attach_gpu_godunov(r, riemann="hllc", slope_type=2)
@@ -139,7 +140,7 @@ def test_orszag_tang_golden_with_gpu_godunov_fine(orc):
     """tests/mhd/orszag-tang: levels 5..9, hlld / hlld, moncen, periodic"""
     from oracle.amr_mhd import MhdAmrRun2D, check_sums_cols
     r = MhdAmrRun2D(5, 9, 1.0, nsubcycle=[1], riemann="hlld", riemann2d="hlld", slope_type=2, gamma=1.6666667,
-                    courant_factor=0.8, err_grad_p=0.1, interpol_type=2, tout=[0.5], nexpand=1, ngridmax=100000)
+                    courant_factor=0.8, err_grad_p=0.1, interpol_type=2, tout=[0.5], nexpand=1, ngridmax=40000)   # peaks at 33 585 octs
     h, st = attach_gpu_godunov(r, mhd=True, riemann="hlld", riemann2d="hlld", slope_type=2)
     snap = r.run()
     h.finalize()
